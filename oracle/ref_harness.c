@@ -1,0 +1,314 @@
+/*
+ * ref_harness.c -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+ *
+ * A thin driver, written for this repository, that is compiled TOGETHER WITH the unmodified
+ * reference sources (see oracle/Makefile.ref) into oracle/_ref/libludwig_ref.so.  It builds
+ * the reference's own objects (pe/cs/physics/lb/hydro/map/field/field_grad/fe_symm/pth/phi_ch)
+ * exactly as the reference driver does for `free_energy none` and `free_energy symmetric`
+ * (/root/reference/src/ludwig.c:1147-1260, 202-429), calls the reference's own hot-path entry
+ * points in the reference's own order (/root/reference/src/ludwig.c:528-860), and copies raw
+ * arrays in/out in a layout-neutral "canonical" form so that tests can compare
+ * (a) our C restatement in oracle/lb_oracle.c and (b) the CUDA product against the reference
+ * itself on identical inputs.
+ *
+ * Canonical array layout used at this interface (and by oracle/ and the product's C-ABI):
+ *   site index  = reference cs_index(): ((ic+nhalo-1)*nall[Y] + (jc+nhalo-1))*nall[Z] + (kc+nhalo-1)
+ *   scalar a    : a[index]
+ *   rank-1 (nf) : a[n*nsites + index]            (structure of arrays on the allocated lattice)
+ *   f           : f[(n*nvel + p)*nsites + index]
+ */
+
+#include <assert.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#include "pe.h"
+#include "coords.h"
+#include "physics.h"
+#include "leesedwards.h"
+#include "lb_data.h"
+#include "collision.h"
+#include "propagation.h"
+#include "hydro.h"
+#include "map.h"
+#include "field.h"
+#include "field_grad.h"
+#include "field_phi_init.h"
+#include "gradient_3d_27pt_fluid.h"
+#include "symmetric.h"
+#include "phi_force.h"
+#include "phi_force_stress.h"
+#include "phi_force_colloid.h"
+#include "phi_cahn_hilliard.h"
+#include "advection.h"
+#include "advection_s.h"
+#include "wall.h"
+#include "fe_force_method.h"
+#include "noise.h"
+
+typedef struct ref_cfg_s {
+  int ntotal[3];
+  int nhalo;
+  int periodic[3];
+  int ndist;
+  int nrelax;          /* 0 m10, 1 bgk, 2 trt */
+  int ghost_off;       /* 1 = "ghost_modes off" */
+  int halo_reduced;    /* 1 = lb_halo_reduced */
+  int have_phi;        /* 1 = free_energy symmetric (FD route) */
+  int adv_order;       /* 1,2,3 */
+  int conserve;        /* cahn_hilliard_options_conserve */
+  double rho0;
+  double eta_shear;
+  double eta_bulk;
+  double fbody[3];
+  double a, b, kappa;
+  double mobility;
+  double gradmu[3];
+} ref_cfg_t;
+
+typedef struct ref_sim_s {
+  ref_cfg_t cfg;
+  pe_t * pe;
+  cs_t * cs;
+  physics_t * phys;
+  lees_edw_t * le;
+  lb_t * lb;
+  hydro_t * hydro;
+  map_t * map;
+  wall_t * wall;
+  field_t * phi;
+  field_grad_t * phi_grad;
+  fe_symm_t * fe;
+  pth_t * pth;
+  phi_ch_t * pch;
+  int nsites;
+} ref_sim_t;
+
+enum {REF_F = 0, REF_PHI = 1, REF_U = 2, REF_RHO = 3, REF_FORCE = 4,
+      REF_GRAD = 5, REF_DELSQ = 6, REF_STR = 7, REF_FLUX = 8, REF_MAP = 9};
+
+static int mpi_up = 0;
+
+ref_sim_t * ref_create(const ref_cfg_t * cfg) {
+
+  ref_sim_t * s = (ref_sim_t *) calloc(1, sizeof(ref_sim_t));
+  s->cfg = *cfg;
+
+  if (!mpi_up) {
+    static char arg0[] = "ref_harness";
+    static char * argv_[] = {arg0, NULL};
+    int argc = 1;
+    char ** argv = argv_;
+    MPI_Init(&argc, &argv);
+    mpi_up = 1;
+  }
+
+  pe_create(MPI_COMM_WORLD, PE_QUIET, &s->pe);
+  cs_create(s->pe, &s->cs);
+  cs_nhalo_set(s->cs, cfg->nhalo);
+  cs_ntotal_set(s->cs, cfg->ntotal);
+  cs_periodicity_set(s->cs, cfg->periodic);
+  cs_init(s->cs);
+  cs_nsites(s->cs, &s->nsites);
+
+  physics_create(s->pe, &s->phys);
+  physics_rho0_set(s->phys, cfg->rho0);
+  physics_eta_shear_set(s->phys, cfg->eta_shear);
+  physics_eta_bulk_set(s->phys, cfg->eta_bulk);
+  { double fb[3] = {cfg->fbody[0], cfg->fbody[1], cfg->fbody[2]};
+    physics_fbody_set(s->phys, fb); }
+  physics_mobility_set(s->phys, cfg->mobility);
+  { double gm[3] = {cfg->gradmu[0], cfg->gradmu[1], cfg->gradmu[2]};
+    physics_grad_mu_set(s->phys, gm); }
+
+  { lees_edw_options_t opts = {0};
+    lees_edw_create(s->pe, s->cs, &opts, &s->le); }
+
+  { lb_data_options_t opts = lb_data_options_ndim_nvel_ndist(NDIM, NVEL, cfg->ndist);
+    opts.nrelax = (lb_relaxation_enum_t) cfg->nrelax;
+    opts.halo = cfg->halo_reduced ? LB_HALO_REDUCED : LB_HALO_FULL;
+    lb_data_create(s->pe, s->cs, &opts, &s->lb); }
+  if (cfg->ghost_off) lb_collision_ghost_modes_off(s->lb);
+
+  { hydro_options_t opts = hydro_options_default();
+    hydro_create(s->pe, s->cs, s->le, &opts, &s->hydro); }
+
+  { map_options_t opts = map_options_default();
+    map_create(s->pe, s->cs, &opts, &s->map); }
+
+  wall_create(s->pe, s->cs, s->map, s->lb, &s->wall);
+
+  if (cfg->have_phi) {
+    field_options_t opts = field_options_ndata_nhalo(1, cfg->nhalo);
+    phi_ch_info_t ch = {0};
+    fe_symm_param_t p = {0};
+    field_create(s->pe, s->cs, s->le, "phi", &opts, &s->phi);
+    field_grad_create(s->pe, s->phi, 2, &s->phi_grad);
+    field_grad_set(s->phi_grad, grad_3d_27pt_fluid_d2, grad_3d_27pt_fluid_d4);
+    fe_symm_create(s->pe, s->cs, s->phi, s->phi_grad, &s->fe);
+    p.a = cfg->a; p.b = cfg->b; p.kappa = cfg->kappa;
+    fe_symm_param_set(s->fe, p);
+    ch.conserve = cfg->conserve;
+    phi_ch_create(s->pe, s->cs, s->le, &ch, &s->pch);
+    pth_create(s->pe, s->cs, FE_FORCE_METHOD_STRESS_DIVERGENCE, &s->pth);
+    advection_order_set(cfg->adv_order);
+  }
+  else {
+    pth_create(s->pe, s->cs, FE_FORCE_METHOD_NO_FORCE, &s->pth);
+  }
+
+  return s;
+}
+
+void ref_free(ref_sim_t * s) {
+  if (s == NULL) return;
+  if (s->pch) phi_ch_free(s->pch);
+  if (s->pth) pth_free(s->pth);
+  if (s->fe) fe_symm_free(s->fe);
+  if (s->phi_grad) field_grad_free(s->phi_grad);
+  if (s->phi) field_free(s->phi);
+  wall_free(s->wall);
+  map_free(&s->map);
+  hydro_free(s->hydro);
+  lb_free(s->lb);
+  lees_edw_free(s->le);
+  physics_free(s->phys);
+  cs_free(s->cs);
+  pe_free(s->pe);
+  free(s);
+}
+
+int ref_nsites(ref_sim_t * s) { return s->nsites; }
+int ref_nvel(void) { return NVEL; }
+
+/* --- initial conditions through the reference's own routines --------------------------- */
+
+int ref_init_rest(ref_sim_t * s, double rho0) { return lb_init_rest_f(s->lb, rho0); }
+
+int ref_init_uniform_u(ref_sim_t * s, double rho, const double u[3]) {
+  int nlocal[3];
+  double uu[3] = {u[0], u[1], u[2]};
+  cs_nlocal(s->cs, nlocal);
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++)
+	lb_1st_moment_equilib_set(s->lb, cs_index(s->cs, ic, jc, kc), rho, uu);
+  return 0;
+}
+
+int ref_init_spinodal(ref_sim_t * s, int seed, double phi0, double amp) {
+  assert(s->phi);
+  return field_phi_init_spinodal(s->phi, seed, phi0, amp);
+}
+
+/* --- array access ------------------------------------------------------------------------ */
+
+static int ref_copy(ref_sim_t * s, int what, double * buf, int put) {
+
+  const int ns = s->nsites;
+
+#define XFER(hostexpr, k) do { if (put) (hostexpr) = buf[(k)]; else buf[(k)] = (hostexpr); } while (0)
+
+  switch (what) {
+  case REF_F:
+    for (int n = 0; n < s->lb->ndist; n++)
+      for (int p = 0; p < NVEL; p++)
+	for (int i = 0; i < ns; i++)
+	  XFER(s->lb->f[LB_ADDR(ns, s->lb->ndist, NVEL, i, n, p)], (size_t) (n*NVEL + p)*ns + i);
+    break;
+  case REF_PHI:
+    for (int i = 0; i < ns; i++) XFER(s->phi->data[addr_rank1(ns, 1, i, 0)], i);
+    break;
+  case REF_U:
+    for (int a = 0; a < 3; a++)
+      for (int i = 0; i < ns; i++) XFER(s->hydro->u->data[addr_rank1(ns, 3, i, a)], (size_t) a*ns + i);
+    break;
+  case REF_RHO:
+    for (int i = 0; i < ns; i++) XFER(s->hydro->rho->data[addr_rank0(ns, i)], i);
+    break;
+  case REF_FORCE:
+    for (int a = 0; a < 3; a++)
+      for (int i = 0; i < ns; i++) XFER(s->hydro->force->data[addr_rank1(ns, 3, i, a)], (size_t) a*ns + i);
+    break;
+  case REF_GRAD:
+    for (int a = 0; a < 3; a++)
+      for (int i = 0; i < ns; i++) XFER(s->phi_grad->grad[addr_rank2(ns, 1, 3, i, 0, a)], (size_t) a*ns + i);
+    break;
+  case REF_DELSQ:
+    for (int i = 0; i < ns; i++) XFER(s->phi_grad->delsq[addr_rank1(ns, 1, i, 0)], i);
+    break;
+  case REF_STR:
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++)
+	for (int i = 0; i < ns; i++) XFER(s->pth->str[addr_rank2(ns, 3, 3, i, a, b)], (size_t) (a*3 + b)*ns + i);
+    break;
+  case REF_FLUX:
+    for (int i = 0; i < ns; i++) {
+      XFER(s->pch->flux->fw[addr_rank0(ns, i)], (size_t) 0*ns + i);
+      XFER(s->pch->flux->fe[addr_rank0(ns, i)], (size_t) 1*ns + i);
+      XFER(s->pch->flux->fy[addr_rank0(ns, i)], (size_t) 2*ns + i);
+      XFER(s->pch->flux->fz[addr_rank0(ns, i)], (size_t) 3*ns + i);
+    }
+    break;
+  case REF_MAP:
+    for (int i = 0; i < ns; i++) {
+      if (put) s->map->status[i] = (char) buf[i]; else buf[i] = (double) s->map->status[i];
+    }
+    break;
+  default:
+    return -1;
+  }
+#undef XFER
+  return 0;
+}
+
+int ref_get(ref_sim_t * s, int what, double * out) { return ref_copy(s, what, out, 0); }
+int ref_set(ref_sim_t * s, int what, const double * in) { return ref_copy(s, what, (double *) in, 1); }
+
+/* --- individual hot-path operators, reference entry points unchanged ---------------------- */
+
+int ref_hydro_f_zero(ref_sim_t * s) { double z[3] = {0.0, 0.0, 0.0}; return hydro_f_zero(s->hydro, z); }
+int ref_hydro_u_zero(ref_sim_t * s) { double z[3] = {0.0, 0.0, 0.0}; return hydro_u_zero(s->hydro, z); }
+int ref_hydro_u_halo(ref_sim_t * s) { return hydro_u_halo(s->hydro); }
+int ref_phi_halo(ref_sim_t * s) { return field_halo(s->phi); }
+int ref_grad_compute(ref_sim_t * s) { return field_grad_compute(s->phi_grad); }
+int ref_phi_force(ref_sim_t * s) {
+  return phi_force_calculation(s->pe, s->cs, s->le, s->wall, s->pth, (fe_t *) s->fe, s->map,
+			       s->phi, s->hydro);
+}
+int ref_cahn_hilliard(ref_sim_t * s) {
+  return phi_cahn_hilliard(s->pch, (fe_t *) s->fe, s->phi, s->hydro, s->map, NULL);
+}
+int ref_collide(ref_sim_t * s) {
+  return lb_collide(s->lb, s->hydro, s->map, NULL, (fe_t *) s->fe, NULL);
+}
+int ref_lb_halo(ref_sim_t * s) { return lb_halo(s->lb); }
+int ref_propagation(ref_sim_t * s) { return lb_propagation(s->lb); }
+
+/* One full time step in the reference driver's order (/root/reference/src/ludwig.c:528-860) */
+
+int ref_step(ref_sim_t * s, int nsteps) {
+  for (int n = 0; n < nsteps; n++) {
+    ref_hydro_f_zero(s);
+    if (s->phi) {
+      ref_phi_halo(s);
+      ref_grad_compute(s);
+      ref_phi_force(s);
+      ref_cahn_hilliard(s);
+    }
+    ref_hydro_u_zero(s);
+    ref_collide(s);
+    ref_lb_halo(s);
+    ref_propagation(s);
+  }
+  return 0;
+}
+
+/* Wall-clock of nsteps full steps, for the CPU baseline (bench.py --impl reference) */
+
+double ref_time_steps(ref_sim_t * s, int nsteps) {
+  double t0 = MPI_Wtime();
+  ref_step(s, nsteps);
+  return MPI_Wtime() - t0;
+}

@@ -1,0 +1,118 @@
+"""ctypes binding of oracle/_ref/libludwig_ref.so (the UNMODIFIED reference built by
+oracle/Makefile.ref plus our harness oracle/ref_harness.c).  Test infrastructure only."""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "..", "oracle", "_ref", "libludwig_ref.so")
+REF_FAST_SO = os.path.join(HERE, "..", "oracle", "_ref", "libludwig_ref_fast.so")
+
+REF_F, REF_PHI, REF_U, REF_RHO, REF_FORCE, REF_GRAD, REF_DELSQ, REF_STR, REF_FLUX, REF_MAP = range(10)
+NCOMP = {REF_PHI: 1, REF_U: 3, REF_RHO: 1, REF_FORCE: 3, REF_GRAD: 3, REF_DELSQ: 1,
+         REF_STR: 9, REF_FLUX: 4, REF_MAP: 1}
+
+
+class RefCfg(C.Structure):
+    _fields_ = [("ntotal", C.c_int * 3), ("nhalo", C.c_int), ("periodic", C.c_int * 3),
+                ("ndist", C.c_int), ("nrelax", C.c_int), ("ghost_off", C.c_int),
+                ("halo_reduced", C.c_int), ("have_phi", C.c_int), ("adv_order", C.c_int),
+                ("conserve", C.c_int),
+                ("rho0", C.c_double), ("eta_shear", C.c_double), ("eta_bulk", C.c_double),
+                ("fbody", C.c_double * 3), ("a", C.c_double), ("b", C.c_double),
+                ("kappa", C.c_double), ("mobility", C.c_double), ("gradmu", C.c_double * 3)]
+
+
+def available(fast=False):
+    return os.path.exists(REF_FAST_SO if fast else REF_SO)
+
+
+_libs = {}
+
+
+def _lib(fast=False):
+    if fast not in _libs:
+        lib = C.CDLL(REF_FAST_SO if fast else REF_SO)
+        lib.ref_create.restype = C.c_void_p
+        lib.ref_create.argtypes = [C.POINTER(RefCfg)]
+        lib.ref_time_steps.restype = C.c_double
+        lib.ref_time_steps.argtypes = [C.c_void_p, C.c_int]
+        for name in ("ref_free", "ref_nsites", "ref_hydro_f_zero", "ref_hydro_u_zero", "ref_hydro_u_halo",
+                     "ref_phi_halo", "ref_grad_compute", "ref_phi_force", "ref_cahn_hilliard",
+                     "ref_collide", "ref_lb_halo", "ref_propagation"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.ref_step.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.ref_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.ref_init_rest.argtypes = [C.c_void_p, C.c_double]
+        lib.ref_init_uniform_u.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double * 3)]
+        lib.ref_init_spinodal.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        _libs[fast] = lib
+    return _libs[fast]
+
+
+class RefSim:
+    """One reference simulation (the reference keeps a `physics` singleton: one at a time)."""
+
+    def __init__(self, ntotal, nhalo=1, periodic=(1, 1, 1), ndist=1, nrelax=0, ghost_off=0,
+                 halo_reduced=0, have_phi=0, adv_order=1, conserve=0, rho0=1.0, eta_shear=1.0 / 6.0,
+                 eta_bulk=None, fbody=(0, 0, 0), a=0.0, b=0.0, kappa=0.0, mobility=0.0,
+                 gradmu=(0, 0, 0), fast=False):
+        self.lib = _lib(fast)
+        cfg = RefCfg()
+        cfg.ntotal[:] = ntotal
+        cfg.nhalo = nhalo
+        cfg.periodic[:] = periodic
+        cfg.ndist, cfg.nrelax, cfg.ghost_off, cfg.halo_reduced = ndist, nrelax, ghost_off, halo_reduced
+        cfg.have_phi, cfg.adv_order, cfg.conserve = have_phi, adv_order, conserve
+        cfg.rho0, cfg.eta_shear = rho0, eta_shear
+        cfg.eta_bulk = eta_shear if eta_bulk is None else eta_bulk
+        cfg.fbody[:] = fbody
+        cfg.a, cfg.b, cfg.kappa, cfg.mobility = a, b, kappa, mobility
+        cfg.gradmu[:] = gradmu
+        self.cfg = cfg
+        self.h = self.lib.ref_create(C.byref(cfg))
+        self.nsites = self.lib.ref_nsites(self.h)
+        self.ndist = ndist
+        self.nvel = 19
+
+    def close(self):
+        if self.h:
+            self.lib.ref_free(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def get(self, what):
+        n = self.ndist * self.nvel if what == REF_F else NCOMP[what]
+        out = np.empty((n, self.nsites), dtype=np.float64)
+        rc = self.lib.ref_get(self.h, what, out.ctypes.data)
+        assert rc == 0
+        return out
+
+    def set(self, what, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        rc = self.lib.ref_set(self.h, what, arr.ctypes.data)
+        assert rc == 0
+
+    def init_rest(self, rho0=1.0):
+        self.lib.ref_init_rest(self.h, rho0)
+
+    def init_uniform_u(self, rho, u):
+        self.lib.ref_init_uniform_u(self.h, rho, C.byref((C.c_double * 3)(*u)))
+
+    def init_spinodal(self, seed, phi0, amp):
+        self.lib.ref_init_spinodal(self.h, seed, phi0, amp)
+
+    def op(self, name):
+        return getattr(self.lib, "ref_" + name)(self.h)
+
+    def step(self, n=1):
+        self.lib.ref_step(self.h, n)
+
+    def time_steps(self, n):
+        return self.lib.ref_time_steps(self.h, n)
