@@ -1,0 +1,106 @@
+/*
+ * lb_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C, single-threaded-semantics (OpenMP over independent sites only) CPU restatement of
+ * the reference's (ludwig-cf/ludwig v0.23.0) per-timestep lattice-Boltzmann hot path.
+ * It is the checker the CUDA product is compared with; the product never calls it
+ * (only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it).
+ *
+ * Parity status: PINNED.  Every function below is compared bit-for-bit with the unmodified
+ * reference compiled from /root/reference (oracle/_ref/libludwig_ref.so, oracle/Makefile.ref)
+ * in tests/test_oracle_vs_reference.py, with golden vectors produced by that reference in
+ * tests/golden/ (script tests/golden/make_golden.py), and with the printed statistics of the
+ * reference's own regression logs (tests/regression/d3q19-short/serial-spin-fd1.log,
+ * serial-dist-3du.log).
+ *
+ * Array layout ("canonical", also used by the product's C-ABI for host arrays):
+ *   nall[a] = nlocal[a] + 2*nhalo,  nsites = nall[X]*nall[Y]*nall[Z]
+ *   index(ic,jc,kc) = ((ic+nhalo-1)*nall[Y] + (jc+nhalo-1))*nall[Z] + (kc+nhalo-1)   (z fastest;
+ *                      reference src/coords.c:617-631), ic in [1-nhalo, nlocal+nhalo]
+ *   scalar: a[index]; nf-vector: a[n*nsites + index]; distributions: f[(n*nvel + p)*nsites + index]
+ */
+#ifndef LB_ORACLE_H
+#define LB_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_geom_s {
+  int nlocal[3];
+  int nhalo;
+  int periodic[3];
+} orc_geom_t;
+
+typedef struct orc_model_s {
+  int nvel;
+  int ndim;
+  signed char cv[27][3];
+  double wv[27];
+  double na[27];
+  double ma[27][27];     /* ma[m][p] */
+  double mi[27][27];     /* mi[p][m] = wv[p]*na[m]*ma[m][p] */
+} orc_model_t;
+
+enum {ORC_RELAX_M10 = 0, ORC_RELAX_BGK = 1, ORC_RELAX_TRT = 2};
+enum {ORC_MAP_FLUID = 0};
+
+typedef struct orc_collide_param_s {
+  int nrelax;            /* ORC_RELAX_* */
+  double rho0;
+  double eta_shear;
+  double eta_bulk;
+  double force_global[3];
+} orc_collide_param_t;
+
+typedef struct orc_symm_param_s {
+  double a, b, kappa;
+  double mobility;
+  double gradmu[3];
+  int adv_order;         /* 1, 2, 3 */
+} orc_symm_param_t;
+
+int orc_nsites(const orc_geom_t * g);
+int orc_index(const orc_geom_t * g, int ic, int jc, int kc);
+
+int orc_model_create(int nvel, orc_model_t * model);
+
+/* lb_propagation: fprime <- pull(f) on the interior, self copy on y/z halo of x in [1,N] */
+void orc_propagation(const orc_geom_t * g, const orc_model_t * m, int ndist,
+		     const double * f, double * fprime);
+/* lb_halo, full or reduced */
+void orc_lb_halo(const orc_geom_t * g, const orc_model_t * m, int ndist, int reduced, double * f);
+/* field_halo: nhalo deep, nf components */
+void orc_field_halo(const orc_geom_t * g, int nf, double * data);
+
+/* lb_collide (ndist = 1): all sites x in [1,N], all y,z incl. halo when include_halo != 0
+ * (as the reference), interior only otherwise. status may be NULL (all fluid). */
+void orc_collide(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+		 const char * status, int include_halo,
+		 double * f, const double * force, double * rho, double * u);
+
+void orc_grad_27pt(const orc_geom_t * g, const double * phi, double * grad, double * delsq);
+void orc_stress_symm(const orc_geom_t * g, const orc_symm_param_t * sp, const double * phi,
+		     const double * grad, const double * delsq, double * str);
+void orc_force_divergence(const orc_geom_t * g, const double * str, double * force);
+void orc_advection(const orc_geom_t * g, int order, const double * u, const double * phi,
+		   double * flux);
+void orc_flux_mu(const orc_geom_t * g, const orc_symm_param_t * sp, const double * phi,
+		 const double * delsq, double * flux);
+void orc_flux_mu_ext(const orc_geom_t * g, const orc_symm_param_t * sp, double * flux);
+void orc_no_flux(const orc_geom_t * g, const char * status, double * flux);
+void orc_phi_update(const orc_geom_t * g, const double * flux, double * phi);
+
+void orc_field_set(const orc_geom_t * g, int nf, double * data, const double * values);
+
+/* Whole step(s), reference order (reference src/ludwig.c:528-860). binary != 0: symmetric FD route.
+ * Work arrays are allocated inside.  f has ndist = 1. */
+void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+	      const orc_symm_param_t * sp, int binary, int halo_reduced, int nsteps,
+	      double * f, double * phi, double * u, double * rho, double * force,
+	      double * grad, double * delsq);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,187 @@
+"""ctypes binding of oracle/liboracle.so (the plain-C CPU restatement, oracle/lb_oracle.c).
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(HERE, "..", "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(ORACLE_DIR, "lb_oracle.c")
+    deps = [src, os.path.join(ORACLE_DIR, "lb_oracle.h"), os.path.join(ORACLE_DIR, "d3q19_tables.h")]
+    if (not force and os.path.exists(ORACLE_SO)
+            and all(os.path.getmtime(ORACLE_SO) >= os.path.getmtime(d) for d in deps)):
+        return ORACLE_SO
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-Wall",
+                           "-o", ORACLE_SO, src, "-lm"])
+    return ORACLE_SO
+
+
+class Geom(C.Structure):
+    _fields_ = [("nlocal", C.c_int * 3), ("nhalo", C.c_int), ("periodic", C.c_int * 3)]
+
+
+class Model(C.Structure):
+    _fields_ = [("nvel", C.c_int), ("ndim", C.c_int), ("cv", (C.c_byte * 3) * 27),
+                ("wv", C.c_double * 27), ("na", C.c_double * 27),
+                ("ma", (C.c_double * 27) * 27), ("mi", (C.c_double * 27) * 27)]
+
+
+class CollideParam(C.Structure):
+    _fields_ = [("nrelax", C.c_int), ("rho0", C.c_double), ("eta_shear", C.c_double),
+                ("eta_bulk", C.c_double), ("force_global", C.c_double * 3)]
+
+
+class SymmParam(C.Structure):
+    _fields_ = [("a", C.c_double), ("b", C.c_double), ("kappa", C.c_double),
+                ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(ORACLE_SO)
+    return _lib
+
+
+def _p(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Stateless operator set bound to one geometry + model."""
+
+    def __init__(self, nlocal, nhalo=1, periodic=(1, 1, 1), nvel=19):
+        self.lib = lib()
+        self.g = Geom()
+        self.g.nlocal[:] = nlocal
+        self.g.nhalo = nhalo
+        self.g.periodic[:] = periodic
+        self.nlocal = tuple(nlocal)
+        self.nhalo = nhalo
+        self.nall = tuple(n + 2 * nhalo for n in nlocal)
+        self.nsites = int(np.prod(self.nall))
+        self.m = Model()
+        rc = self.lib.orc_model_create(nvel, C.byref(self.m))
+        assert rc == 0
+        self.nvel = nvel
+        self.cv = np.array([[self.m.cv[p][a] for a in range(3)] for p in range(nvel)], dtype=np.int64)
+        self.wv = np.array(self.m.wv[:nvel])
+
+    # ---- helpers -------------------------------------------------------------------------
+    def interior(self, a):
+        """View of the interior of a (ncomp, nsites) canonical array as (ncomp, Nx, Ny, Nz)."""
+        h = self.nhalo
+        v = a.reshape((-1,) + self.nall)
+        return v[:, h:h + self.nlocal[0], h:h + self.nlocal[1], h:h + self.nlocal[2]]
+
+    def region(self, a, extra):
+        """View of [1-extra, N+extra]^3."""
+        h = self.nhalo - extra
+        v = a.reshape((-1,) + self.nall)
+        return v[:, h:self.nall[0] - h, h:self.nall[1] - h, h:self.nall[2] - h]
+
+    def collide_param(self, nrelax=0, rho0=1.0, eta_shear=1.0 / 6.0, eta_bulk=None, force=(0, 0, 0)):
+        cp = CollideParam()
+        cp.nrelax, cp.rho0, cp.eta_shear = nrelax, rho0, eta_shear
+        cp.eta_bulk = eta_shear if eta_bulk is None else eta_bulk
+        cp.force_global[:] = force
+        return cp
+
+    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1):
+        sp = SymmParam()
+        sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order = a, b, kappa, mobility, adv_order
+        sp.gradmu[:] = gradmu
+        return sp
+
+    def equilibrium(self, rho, u):
+        """f_p = rho w_p (1 + 3 u.c + 4.5 (cc - 1/3 I):uu), reference src/lb_data.c:809-834 (same op order)."""
+        f = np.zeros((self.nvel, self.nsites))
+        cs2 = 1.0 / 3.0
+        rcs2 = 1.0 / cs2
+        for p in range(self.nvel):
+            udotc = 0.0
+            sdotq = 0.0
+            for ia in range(3):
+                udotc = udotc + u[ia] * float(self.cv[p, ia])
+                for ib in range(3):
+                    dab = 1.0 if ia == ib else 0.0
+                    sdotq = sdotq + (float(self.cv[p, ia] * self.cv[p, ib]) - cs2 * dab) * u[ia] * u[ib]
+            f[p] = rho * self.wv[p] * (1.0 + rcs2 * udotc + 0.5 * rcs2 * rcs2 * sdotq)
+        return f
+
+    # ---- operators (in place on canonical arrays) -------------------------------------------
+    def propagation(self, f, fprime, ndist=1):
+        self.lib.orc_propagation(C.byref(self.g), C.byref(self.m), ndist, _p(f), _p(fprime))
+
+    def lb_halo(self, f, ndist=1, reduced=0):
+        self.lib.orc_lb_halo(C.byref(self.g), C.byref(self.m), ndist, reduced, _p(f))
+
+    def field_halo(self, a):
+        self.lib.orc_field_halo(C.byref(self.g), a.shape[0], _p(a))
+
+    def collide(self, cp, f, force, rho, u, status=None, include_halo=0):
+        st = status.ctypes.data_as(C.c_void_p) if status is not None else None
+        self.lib.orc_collide(C.byref(self.g), C.byref(self.m), C.byref(cp), st, include_halo,
+                             _p(f), _p(force), _p(rho), _p(u))
+
+    def grad_27pt(self, phi, grad, delsq):
+        self.lib.orc_grad_27pt(C.byref(self.g), _p(phi), _p(grad), _p(delsq))
+
+    def stress_symm(self, sp, phi, grad, delsq, str_):
+        self.lib.orc_stress_symm(C.byref(self.g), C.byref(sp), _p(phi), _p(grad), _p(delsq), _p(str_))
+
+    def force_divergence(self, str_, force):
+        self.lib.orc_force_divergence(C.byref(self.g), _p(str_), _p(force))
+
+    def advection(self, order, u, phi, flux):
+        self.lib.orc_advection(C.byref(self.g), order, _p(u), _p(phi), _p(flux))
+
+    def flux_mu(self, sp, phi, delsq, flux):
+        self.lib.orc_flux_mu(C.byref(self.g), C.byref(sp), _p(phi), _p(delsq), _p(flux))
+
+    def flux_mu_ext(self, sp, flux):
+        self.lib.orc_flux_mu_ext(C.byref(self.g), C.byref(sp), _p(flux))
+
+    def no_flux(self, status, flux):
+        st = status.ctypes.data_as(C.c_void_p) if status is not None else None
+        self.lib.orc_no_flux(C.byref(self.g), st, _p(flux))
+
+    def phi_update(self, flux, phi):
+        self.lib.orc_phi_update(C.byref(self.g), _p(flux), _p(phi))
+
+    def step(self, cp, sp, binary, nsteps, f, phi, u, rho, force, grad, delsq, halo_reduced=0):
+        spp = C.byref(sp) if sp is not None else None
+        args = [(_p(x) if x is not None else None) for x in (f, phi, u, rho, force, grad, delsq)]
+        self.lib.orc_step(C.byref(self.g), C.byref(self.m), C.byref(cp), spp, int(binary),
+                          halo_reduced, nsteps, *args)
+
+
+# ---- observables the reference prints (numpy restatement) -----------------------------------
+
+def stats_scalar(orc, a):
+    """sum, mean, variance, min, max over the interior (reference src/phi_stats.c:91-145)."""
+    v = orc.interior(a)[0].ravel()
+    n = v.size
+    s = float(np.sum(v, dtype=np.longdouble))
+    mean = s / n
+    var = float(np.sum(v.astype(np.longdouble) ** 2)) / n - mean * mean
+    return s, mean, var, float(v.min()), float(v.max())
+
+
+def fed_density(orc, sp, phi, grad):
+    """(1/V) sum_interior [(a/2 + b/4 phi^2) phi^2 + kappa/2 |grad phi|^2]
+    (reference src/symmetric.c:284-299, src/stats_free_energy.c:76-134)."""
+    ph = orc.interior(phi)[0].astype(np.longdouble)
+    g = orc.interior(grad).astype(np.longdouble)
+    fed = (0.5 * sp.a + 0.25 * sp.b * ph * ph) * ph * ph + 0.5 * sp.kappa * (g * g).sum(axis=0)
+    return float(fed.sum() / ph.size)
