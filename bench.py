@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""bench.py -- MLUPS of the D3Q19 symmetric binary-fluid time step (BASELINE.json metric).
+
+One "step" = one full Ludwig time step of the hot path (reference src/ludwig.c:528-860: phi halo,
+27-pt gradient, stress-divergence force, Cahn-Hilliard update with 3rd-order advection, u halo,
+pull-stream + MRT collision, distribution halo) on a 256^3 lattice PER GPU (x-slab decomposition,
+weak scaling), FP64, synthetic spinodal initial state.
+
+  python bench.py --gpus N --steps K --warmup W              our arm (CUDA, libludwig_b200.so)
+  python bench.py --impl reference --gpus N --steps K ...    the reference's own CPU code on the
+                                                             host cores (oracle/_ref, else the C port)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = {"step_binary": 496.0, "collide": 360.0, "force_ch": 96.0, "grad": 40.0}
+BINARY = dict(a=-0.00625, b=0.00625, kappa=0.004, mobility=1.25)
+ETA = 0.00625
+ADV_ORDER = 3
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            if "hbm_gbs" in d:
+                return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                t = [x.strip() for x in line.split(",")]
+                if len(t) < 9:
+                    continue
+                try:
+                    sm.append(float(t[1])); mx.append(float(t[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def initial_state(nlocal, nhalo, rank):
+    """Synthetic spinodal start: rho = 1, u = 0 (f = w_p), phi = 0.05 (r - 1/2), r uniform (seeded)."""
+    import numpy as np
+    nall = tuple(n + 2 * nhalo for n in nlocal)
+    ns = nall[0] * nall[1] * nall[2]
+    wv = np.array([12.0] + [2.0 if sum(abs(c) for c in cv) == 1 else 1.0 for cv in CV19[1:]]) / 36.0
+    return ns, nall, wv
+
+
+CV19 = [(0, 0, 0), (1, 1, 0), (1, 0, 1), (1, 0, 0), (1, 0, -1), (1, -1, 0), (0, 1, 1), (0, 1, 0), (0, 1, -1),
+        (0, 0, 1), (0, 0, -1), (0, -1, 1), (0, -1, 0), (0, -1, -1), (-1, 1, 0), (-1, 0, 1), (-1, 0, 0),
+        (-1, 0, -1), (-1, -1, 0)]
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref) or the C port (oracle/), host cores
+# ------------------------------------------------------------------------------------------------------
+
+def cpu_steps_per_second(n, nsteps, warm=1):
+    """(seconds per step, kind, threads) for an n^3 binary-fluid lattice on the host CPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    import refharness
+    if refharness.available(fast=True):
+        sim = refharness.RefSim((n, n, n), nhalo=2, have_phi=1, adv_order=ADV_ORDER, eta_shear=ETA,
+                                ghost_off=1, fast=True, **BINARY)
+        sim.init_rest(1.0)
+        sim.init_spinodal(8361235, 0.0, 0.05)
+        sim.step(warm)
+        t = sim.time_steps(nsteps)
+        sim.close()
+        return t / nsteps, "reference", threads
+    import numpy as np
+    from oracle import Oracle
+    orc = Oracle((n, n, n), nhalo=2)
+    rng = np.random.default_rng(8361235)
+    f = orc.equilibrium(1.0, (0.0, 0.0, 0.0))
+    phi = np.zeros((1, orc.nsites))
+    orc.interior(phi)[0] = 0.05 * (rng.random((n, n, n)) - 0.5)
+    z3 = lambda: np.zeros((3, orc.nsites))
+    z1 = lambda: np.zeros((1, orc.nsites))
+    u, rho, force, grad, delsq = z3(), z1(), z3(), z3(), z1()
+    cp = orc.collide_param(0, 1.0, ETA)
+    sp = orc.symm_param(adv_order=ADV_ORDER, **BINARY)
+    orc.step(cp, sp, 1, warm, f, phi, u, rho, force, grad, delsq)
+    t0 = time.perf_counter()
+    orc.step(cp, sp, 1, nsteps, f, phi, u, rho, force, grad, delsq)
+    return (time.perf_counter() - t0) / nsteps, "port", threads
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    # bounded sample: the largest n^3 (<= 256) for which steps + warmup finish in ~150 s
+    t64, kind, threads = cpu_steps_per_second(64, 2, warm=1)
+    per_site = t64 / 64 ** 3
+    total = args.steps + args.warmup
+    n = 64
+    for cand in (96, 128, 192, 256):
+        if per_site * cand ** 3 * total <= 150.0:
+            n = cand
+    t0 = time.perf_counter()
+    tstep, kind, threads = cpu_steps_per_second(n, args.steps, warm=max(args.warmup, 1))
+    mlups = n ** 3 / tstep / 1e6
+    line = {
+        "impl": "reference", "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tstep * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "D3Q19 symmetric binary fluid (spinodal), 27pt gradient, stress-divergence force, "
+                               "Cahn-Hilliard advection order 3, MRT(M10) collision + propagation + halos; "
+                               f"CPU sample lattice {n}^3 (target workload 256^3 per GPU)"},
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} full time steps of a {n}^3 lattice after {max(args.warmup, 1)} warm-up "
+                                   f"steps, OpenMP threads = {threads}"},
+        "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import ludwig_b200 as lb
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    n = args.size
+    nlocal = (n, n, n)
+    nhalo = 2
+    sim = lb.Lb200(nlocal, nhalo=nhalo, have_phi=True, math=lb.MATH_STRICT if args.strict else lb.MATH_FAST,
+                   device=local_rank, cart_size=world, cart_rank=rank)
+    if world > 1:
+        ids = [sim.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sim.nccl_init(ids[0], world, rank)
+
+    ns = sim.nsites
+    nall = sim.nall
+    # pinned host state (the reference's host arrays: lb->f, phi->data, hydro->u, hydro->rho)
+    h_f = torch.empty((19, ns), dtype=torch.float64, pin_memory=True)
+    h_phi = torch.empty((1, ns), dtype=torch.float64, pin_memory=True)
+    h_u = torch.empty((3, ns), dtype=torch.float64, pin_memory=True)
+    h_rho = torch.empty((1, ns), dtype=torch.float64, pin_memory=True)
+    wv = np.array([12.0] + [2.0 if sum(abs(c) for c in cv) == 1 else 1.0 for cv in CV19[1:]]) / 36.0
+    fv = h_f.numpy()
+    for p in range(19):
+        fv[p, :] = wv[p]                         # rho = 1, u = 0 equilibrium
+    rng = np.random.default_rng(8361235 + rank)
+    pv = h_phi.numpy().reshape(nall)
+    pv[...] = 0.0
+    pv[nhalo:-nhalo, nhalo:-nhalo, nhalo:-nhalo] = 0.05 * (rng.random(nlocal) - 0.5)
+
+    cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA)
+    sp = lb.SymmParam.make(adv_order=ADV_ORDER, **BINARY)
+    stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sim.sync()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    H2D, D2H = 1, 2
+
+    def upload():
+        sim.memcpy_async(lb.F, h_f.data_ptr(), H2D)
+        sim.memcpy_async(lb.PHI, h_phi.data_ptr(), H2D)
+
+    def download():
+        sim.memcpy_async(lb.PHI, h_phi.data_ptr(), D2H)
+        sim.memcpy_async(lb.U, h_u.data_ptr(), D2H)
+        sim.memcpy_async(lb.RHO, h_rho.data_ptr(), D2H)
+
+    # ---- device-resident timing: inputs in HBM before the timed region -------------------------------
+    upload()
+    sim.sync()
+    sim.step(cp, sp, args.warmup)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.step(cp, sp, args.steps)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = sim.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+
+    phi_sum = float(np.nansum(sim.interior(sim.get(lb.PHI))))      # sanity: finite, conserved
+    sites_total = float(n) ** 3 * world
+    mlups = sites_total * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel device time (CUDA events on the launching stream), short separate pass -----------
+    sim.profile(True)
+    sim.step(cp, sp, min(args.steps, 20))
+    sim.sync()
+    prof = sim.profile_get()
+    sim.profile(False)
+    kernels = {k: {"ms_per_launch": (t / c if c else None), "launches": c} for k, (t, c) in prof.items()}
+    peak, peak_src = measured_peaks()
+    col_ms = kernels["collide"]["ms_per_launch"]
+    ach = B_ALG["collide"] * float(n) ** 3 / (col_ms * 1e-3) / 1e9 if col_ms else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("collide_bytes_per_launch_256")
+            if n != 256:
+                traffic = None
+        except Exception:
+            traffic = None
+
+    # ---- end to end through the C-ABI with HOST buffers: H2D state, K steps, D2H observables ----------
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    t0.record(stream)
+    upload()
+    sim.step(cp, sp, args.steps)
+    download()
+    t1.record(stream)
+    sim.sync()
+    wall = time.perf_counter() - w0
+    barrier()
+    e2e_ms = max_over_ranks(max(t0.elapsed_time(t1), wall * 1e3))
+    e2e = sites_total * args.steps / (e2e_ms * 1e-3) / 1e6
+    h2d = (19 + 1) * ns * 8 / args.steps
+    d2h = (1 + 3 + 1) * ns * 8 / args.steps
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            nsamp = args.cpu_size
+            tstep, kind, threads = cpu_steps_per_second(nsamp, 3, warm=1)
+            cpu = {"value": nsamp ** 3 / tstep / 1e6, "unit": "MLUPS", "cores": threads, "kind": kind,
+                   "sample": f"3 full time steps of a {nsamp}^3 lattice (same physics, same parameters) after 1 warm-up step"}
+        except Exception as exc:          # the baseline is reported, never allowed to sink the bench
+            cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"D3Q19 symmetric binary fluid (spinodal decomposition), {n}^3 per GPU, "
+                                   "27pt phi gradient + stress-divergence force + Cahn-Hilliard (advection order 3) "
+                                   "+ MRT(M10) pull-stream-collide + phi/u/f halos",
+                       "lattice_per_gpu": [n, n, n], "decomposition": f"{world}_1_1 x-slabs",
+                       "math": "strict" if args.strict else "fast(fma)",
+                       "l2": "inputs (2.8 GB of lattice state per sweep) exceed the 126 MB L2; no flush needed",
+                       "e2e_protocol": "pinned-host f+phi -> device, K steps, phi+u+rho -> pinned host "
+                                       "(the reference's own lb_memcpy/field_memcpy usage, src/ludwig.c:501-506, 985)"},
+            "roofline": {"bound": "hbm", "kernel": "collide_d3q19 (pull-stream + MRT collision)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak if ach else None),
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_site": B_ALG["collide"],
+                         "whole_step": {"algorithmic_bytes_per_site": B_ALG["step_binary"],
+                                        "achieved": mlups / world * 1e6 * B_ALG["step_binary"] / 1e9,
+                                        "frac": mlups / world * 1e6 * B_ALG["step_binary"] / 1e9 / peak}},
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+            "clocks": clk,
+            "e2e": {"value": e2e, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "check": {"phi_sum": phi_sum},
+        }
+        print(json.dumps(line), flush=True)
+
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=256, help="lattice edge per GPU")
+    ap.add_argument("--cpu-size", type=int, default=128, help="edge of the CPU-baseline sample lattice")
+    ap.add_argument("--strict", action="store_true", help="bit-exact arithmetic mode (no FMA contraction)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # not under torchrun: launch ourselves one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

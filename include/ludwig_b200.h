@@ -1,0 +1,179 @@
+/*
+ * ludwig_b200.h -- C-ABI of libludwig_b200.so: a Blackwell (sm_100a) implementation of the
+ * per-timestep lattice-Boltzmann hot path of Ludwig (ludwig-cf/ludwig v0.23.0).
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes.  Each entry point replaces the
+ * device side of one reference host function (cited as reference file:line, paths relative to
+ * the reference root).  The reference-side binding (what a Ludwig maintainer adds to collision.c,
+ * propagation.c, ... to route the hot path through this library) is shown in INTEGRATION.md, and
+ * ludwig_b200/host/ holds a C host layer with the reference's own function names on top of this ABI.
+ *
+ * Host arrays crossing this boundary use the "canonical" structure-of-arrays layout on the
+ * reference's allocated lattice (identical to the reference's -DADDR_SOA host layout,
+ * src/memory.h:182-195):
+ *     nall[a] = nlocal[a] + 2*nhalo;  nsites = nall[X]*nall[Y]*nall[Z]
+ *     index(ic,jc,kc) = ((ic+nhalo-1)*nall[Y] + (jc+nhalo-1))*nall[Z] + (kc+nhalo-1)   src/coords.c:617-631
+ *     scalar a[index];  vector a[ia*nsites + index];  f[(n*nvel + p)*nsites + index]
+ *
+ * All functions return 0 on success and a negative LB200_E* code on failure (and record a message
+ * retrievable with lb200_last_error()); like the reference they are synchronous unless stated.
+ * There is NO CPU fallback: without a CUDA device lb200_create() fails with LB200_ENODEVICE.
+ */
+#ifndef LUDWIG_B200_H
+#define LUDWIG_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lb200_s lb200_t;          /* opaque: geometry + every device-resident lattice array */
+
+enum lb200_error {
+  LB200_OK = 0,
+  LB200_EINVAL = -1,        /* bad argument / unsupported option */
+  LB200_ENODEVICE = -2,     /* no CUDA device (there is no CPU fallback) */
+  LB200_ECUDA = -3,         /* CUDA runtime error (message in lb200_last_error) */
+  LB200_ENOMEM = -4,
+  LB200_ESTATE = -5,        /* operation needs an array this context does not hold (e.g. no phi) */
+  LB200_ECOMM = -6          /* NCCL / peer communication error */
+};
+
+/* lb_relaxation_enum_t: src/lb_data_options.h:21-24 */
+enum lb200_relaxation {LB200_RELAXATION_M10 = 0, LB200_RELAXATION_BGK = 1, LB200_RELAXATION_TRT = 2};
+/* lb_halo_enum_t: src/lb_data_options.h:26-29 */
+enum lb200_halo_scheme {LB200_HALO_FULL = 1, LB200_HALO_REDUCED = 2};
+/* tdpMemcpyKind: target/target.h */
+enum lb200_memcpy_kind {LB200_HOST_TO_DEVICE = 1, LB200_DEVICE_TO_HOST = 2};
+/* arithmetic mode of the kernels */
+enum lb200_math {
+  LB200_MATH_FAST = 0,      /* FMA contraction allowed (default): within 1e-12 relative of the reference */
+  LB200_MATH_STRICT = 1     /* no contraction, reference operation order: bit-identical to the reference
+                               built -ffp-contract=off */
+};
+
+/* lattice arrays held by a context */
+enum lb200_array {
+  LB200_F = 0,              /* lb->f              ndist*nvel x nsites   src/lb_data.h:123 */
+  LB200_PHI = 1,            /* field "phi"        1 x nsites            src/field.h:68-85 */
+  LB200_U = 2,              /* hydro->u           3 x nsites            src/hydro.h:32-47 */
+  LB200_RHO = 3,            /* hydro->rho         1 x nsites */
+  LB200_FORCE = 4,          /* hydro->force       3 x nsites */
+  LB200_GRAD = 5,           /* field_grad->grad   3 x nsites            src/field_grad.h:24-42 */
+  LB200_DELSQ = 6,          /* field_grad->delsq  1 x nsites */
+  LB200_MAP = 7             /* map->status        1 x nsites, passed as double, 0 = MAP_FLUID  src/map.h:26-48 */
+};
+
+typedef struct lb200_options_s {
+  int nlocal[3];            /* local lattice extent (cs_nlocal), src/coords.c:211-215 */
+  int nhalo;                /* cs_nhalo: 1 (single fluid) or 2 (binary fluid FD route, src/ludwig.c:1198) */
+  int periodic[3];          /* cs periodicity of the GLOBAL system */
+  int nvel;                 /* 15, 19 or 27 (-D_D3Q15_/-D_D3Q19_/-D_D3Q27_, src/lb_data.h:30-42) */
+  int ndist;                /* 1 (2 = symmetric_lb: not yet supported -> LB200_EINVAL) */
+  int have_phi;             /* allocate phi, grad, delsq (free_energy symmetric) */
+  int halo_scheme;          /* enum lb200_halo_scheme */
+  int math;                 /* enum lb200_math */
+  int device;               /* CUDA device ordinal, -1 = current */
+  /* x-slab domain decomposition across the GPUs of one box (cs "grid Px_1_1", src/coords.c:151-201) */
+  int cart_size;            /* number of slabs (1 = single GPU) */
+  int cart_rank;            /* this slab */
+} lb200_options_t;
+
+/* lb_collide_param_t / collide_param_t as seen by the collision: src/lb_data.h:59-76,
+ * src/collision.c:60-75, 1906-1958 (re-read from `physics` on every lb_collide call) */
+typedef struct lb200_collide_param_s {
+  int nrelax;               /* enum lb200_relaxation */
+  double rho0;              /* physics rho0 */
+  double eta_shear;         /* physics eta_shear */
+  double eta_bulk;          /* physics eta_bulk */
+  double force_global[3];   /* constant + pulsatile body force, src/collision.c:1942-1945 */
+} lb200_collide_param_t;
+
+/* fe_symm_param_t + Cahn-Hilliard controls: src/symmetric.h:41-47, src/phi_cahn_hilliard.c:298-404,
+ * 1329-1397, src/advection.c:74 */
+typedef struct lb200_symm_param_s {
+  double a, b, kappa;       /* symmetric free energy A, B, kappa */
+  double mobility;          /* physics mobility */
+  double gradmu[3];         /* physics grad_mu (external chemical potential gradient) */
+  int adv_order;            /* fd_advection_scheme_order 1, 2 or 3 */
+} lb200_symm_param_t;
+
+const char * lb200_last_error(void);
+int lb200_version(void);
+
+/* lb_data_create + hydro_create + field_create + field_grad_create + map_create device sides:
+ * src/lb_data.c:67-241, src/hydro.c:52-121, src/field.c:59-136, src/field_grad.c:35-164 */
+int lb200_create(const lb200_options_t * options, lb200_t ** ctx);
+/* lb_free / hydro_free / field_free: src/lb_data.c:251-296 */
+int lb200_free(lb200_t * ctx);
+
+int lb200_nsites(const lb200_t * ctx);
+/* device pointer of an array in its current (device) layout; for zero-copy interop */
+int lb200_device_ptr(lb200_t * ctx, int array, void ** ptr);
+
+/* lb_memcpy / field_memcpy / hydro_memcpy / map_memcpy: src/lb_data.c:529-583, src/field.c:224-288.
+ * `host` is a canonical array (see top); synchronous. */
+int lb200_memcpy(lb200_t * ctx, int array, double * host, int kind);
+/* same, but asynchronous on the context's stream; `host` should be pinned */
+int lb200_memcpy_async(lb200_t * ctx, int array, double * host, int kind);
+int lb200_sync(lb200_t * ctx);
+
+/* hydro_f_zero / hydro_u_zero: src/hydro.c:217-263 (the value is 0 in every caller) */
+int lb200_hydro_f_zero(lb200_t * ctx);
+int lb200_hydro_u_zero(lb200_t * ctx);
+/* hydro_u_halo: src/hydro.c:185-191; field_halo(phi): src/field.c:371-404 */
+int lb200_hydro_u_halo(lb200_t * ctx);
+int lb200_phi_halo(lb200_t * ctx);
+/* field_grad_compute with d2 = grad_3d_27pt_fluid_d2: src/field_grad.c:319-340,
+ * src/gradient_3d_27pt_fluid.c:76-99, 219-363 */
+int lb200_phi_grad_compute(lb200_t * ctx);
+/* phi_force_calculation, stress-divergence method, fluid only: src/phi_force.c:74-137,
+ * src/phi_force_stress.c:171-284, src/phi_force_colloid.c:274-465 */
+int lb200_phi_force_calculation(lb200_t * ctx, const lb200_symm_param_t * sp);
+/* phi_cahn_hilliard (no noise; conserve = 0): src/phi_cahn_hilliard.c:213-288 */
+int lb200_phi_cahn_hilliard(lb200_t * ctx, const lb200_symm_param_t * sp);
+/* lb_collide (ndist = 1): src/collision.c:143-232, 253-593 */
+int lb200_lb_collide(lb200_t * ctx, const lb200_collide_param_t * cp);
+/* lb_halo: src/lb_data.c:754-762, 1124-1477 */
+int lb200_lb_halo(lb200_t * ctx);
+/* lb_propagation: src/propagation.c:43-95, 153-240 */
+int lb200_lb_propagation(lb200_t * ctx);
+
+/* nsteps whole time steps in the reference driver's order (src/ludwig.c:528-860), fused:
+ * pull-stream + collide in one sweep, stress + force + Cahn-Hilliard in one sweep, zeroing folded
+ * into the producers.  sp == NULL (or no phi) = single fluid.  Asynchronous on the context stream;
+ * call lb200_sync() (or any lb200_memcpy) to wait. */
+int lb200_step(lb200_t * ctx, const lb200_collide_param_t * cp, const lb200_symm_param_t * sp,
+	       int nsteps);
+
+/* number of kernels this library has launched on this context since creation */
+long long lb200_launch_count(const lb200_t * ctx);
+/* the context's CUDA stream (cudaStream_t) for event timing by the caller */
+void * lb200_stream(lb200_t * ctx);
+
+/* per-kernel-class device timing (CUDA events on the context stream) for the roofline report */
+enum lb200_kernel_class {
+  LB200_K_COLLIDE = 0,      /* (pull-stream +) collision sweep */
+  LB200_K_PROPAGATE = 1,    /* stand-alone propagation sweep */
+  LB200_K_HALO = 2,         /* halo shells incl. x-plane exchange */
+  LB200_K_GRAD = 3,         /* 27-point gradient */
+  LB200_K_FORCE_CH = 4,     /* stress-divergence force and/or Cahn-Hilliard update */
+  LB200_KCLASS_MAX = 5
+};
+int lb200_profile(lb200_t * ctx, int on);      /* clears accumulated timings */
+int lb200_profile_get(lb200_t * ctx, int kernel_class, double * total_ms, int * count);
+
+/* multi-GPU: attach an NCCL communicator (ncclComm_t, one rank per slab, rank == cart_rank) used
+ * for the x-direction halo planes; replaces MPI_Isend/Irecv of lb_halo_post/field_halo_post
+ * (src/lb_data.c:1317-1420, src/field.c:1412-1531). */
+int lb200_attach_nccl(lb200_t * ctx, void * nccl_comm);
+/* helpers so that a host without nccl.h can create the communicator: unique id is 128 bytes */
+int lb200_nccl_unique_id(void * id128);
+int lb200_nccl_comm_create(const void * id128, int nranks, int rank, void ** nccl_comm);
+int lb200_nccl_comm_destroy(void * nccl_comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,253 @@
+"""ctypes binding of libludwig_b200.so (include/ludwig_b200.h)."""
+import ctypes as C
+import os
+import numpy as np
+
+F, PHI, U, RHO, FORCE, GRAD, DELSQ, MAP = range(8)
+RELAX_M10, RELAX_BGK, RELAX_TRT = 0, 1, 2
+HALO_FULL, HALO_REDUCED = 1, 2
+MATH_FAST, MATH_STRICT = 0, 1
+H2D, D2H = 1, 2
+
+_NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1}
+
+
+class Lb200Error(RuntimeError):
+    pass
+
+
+class Options(C.Structure):
+    _fields_ = [("nlocal", C.c_int * 3), ("nhalo", C.c_int), ("periodic", C.c_int * 3),
+                ("nvel", C.c_int), ("ndist", C.c_int), ("have_phi", C.c_int),
+                ("halo_scheme", C.c_int), ("math", C.c_int), ("device", C.c_int),
+                ("cart_size", C.c_int), ("cart_rank", C.c_int)]
+
+
+class CollideParam(C.Structure):
+    _fields_ = [("nrelax", C.c_int), ("rho0", C.c_double), ("eta_shear", C.c_double),
+                ("eta_bulk", C.c_double), ("force_global", C.c_double * 3)]
+
+    @classmethod
+    def make(cls, nrelax=RELAX_M10, rho0=1.0, eta_shear=1.0 / 6.0, eta_bulk=None, force=(0.0, 0.0, 0.0)):
+        cp = cls()
+        cp.nrelax, cp.rho0, cp.eta_shear = nrelax, rho0, eta_shear
+        cp.eta_bulk = eta_shear if eta_bulk is None else eta_bulk
+        cp.force_global[:] = force
+        return cp
+
+
+class SymmParam(C.Structure):
+    _fields_ = [("a", C.c_double), ("b", C.c_double), ("kappa", C.c_double),
+                ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int)]
+
+    @classmethod
+    def make(cls, a, b, kappa, mobility, gradmu=(0.0, 0.0, 0.0), adv_order=1):
+        sp = cls()
+        sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order = a, b, kappa, mobility, adv_order
+        sp.gradmu[:] = gradmu
+        return sp
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libludwig_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libludwig_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise Lb200Error(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                         " (make -C ludwig_b200/csrc)")
+    lib = C.CDLL(path)
+    lib.lb200_last_error.restype = C.c_char_p
+    lib.lb200_create.argtypes = [C.POINTER(Options), C.POINTER(C.c_void_p)]
+    lib.lb200_free.argtypes = [C.c_void_p]
+    lib.lb200_nsites.argtypes = [C.c_void_p]
+    lib.lb200_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.lb200_memcpy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.lb200_memcpy_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    for name in ("lb200_sync", "lb200_hydro_f_zero", "lb200_hydro_u_zero", "lb200_hydro_u_halo",
+                 "lb200_phi_halo", "lb200_phi_grad_compute", "lb200_lb_halo", "lb200_lb_propagation"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.lb200_phi_force_calculation.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
+    lib.lb200_phi_cahn_hilliard.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
+    lib.lb200_lb_collide.argtypes = [C.c_void_p, C.POINTER(CollideParam)]
+    lib.lb200_step.argtypes = [C.c_void_p, C.POINTER(CollideParam), C.POINTER(SymmParam), C.c_int]
+    lib.lb200_launch_count.argtypes = [C.c_void_p]
+    lib.lb200_launch_count.restype = C.c_longlong
+    lib.lb200_stream.argtypes = [C.c_void_p]
+    lib.lb200_stream.restype = C.c_void_p
+    lib.lb200_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.lb200_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    lib.lb200_attach_nccl.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lb200_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.lb200_nccl_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.lb200_nccl_comm_destroy.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+class Lb200:
+    """One device-resident lattice (the lb_t / hydro_t / field_t / field_grad_t / map_t device sides)."""
+
+    def __init__(self, nlocal, nhalo=1, periodic=(1, 1, 1), nvel=19, ndist=1, have_phi=False,
+                 halo_scheme=HALO_FULL, math=MATH_FAST, device=-1, cart_size=1, cart_rank=0):
+        self.lib = load_library()
+        o = Options()
+        o.nlocal[:] = nlocal
+        o.nhalo = nhalo
+        o.periodic[:] = periodic
+        o.nvel, o.ndist, o.have_phi = nvel, ndist, int(bool(have_phi))
+        o.halo_scheme, o.math, o.device = halo_scheme, math, device
+        o.cart_size, o.cart_rank = cart_size, cart_rank
+        self.options = o
+        self.h = C.c_void_p()
+        self._check(self.lib.lb200_create(C.byref(o), C.byref(self.h)))
+        self.nlocal = tuple(nlocal)
+        self.nhalo = nhalo
+        self.nall = tuple(n + 2 * nhalo for n in nlocal)
+        self.nsites = self.lib.lb200_nsites(self.h)
+        self.nvel, self.ndist = nvel, ndist
+        self._nccl = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Lb200Error(f"lb200 error {rc}: {self.lib.lb200_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lb200_free(self.h)
+            self.h = None
+        if getattr(self, "_nccl", None):
+            self.lib.lb200_nccl_comm_destroy(self._nccl)
+            self._nccl = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data movement -------------------------------------------------------------------
+    def ncomp(self, array):
+        return self.nvel * self.ndist if array == F else _NCOMP[array]
+
+    def put(self, array, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        assert host.size == self.ncomp(array) * self.nsites, (host.shape, self.ncomp(array), self.nsites)
+        self._check(self.lib.lb200_memcpy(self.h, array, host.ctypes.data, H2D))
+
+    def get(self, array):
+        out = np.empty((self.ncomp(array), self.nsites), dtype=np.float64)
+        self._check(self.lib.lb200_memcpy(self.h, array, out.ctypes.data, D2H))
+        return out
+
+    def memcpy_async(self, array, host_ptr, kind):
+        self._check(self.lib.lb200_memcpy_async(self.h, array, host_ptr, kind))
+
+    def device_ptr(self, array):
+        p = C.c_void_p()
+        self._check(self.lib.lb200_device_ptr(self.h, array, C.byref(p)))
+        return p.value
+
+    def interior(self, a):
+        h = self.nhalo
+        v = a.reshape((-1,) + self.nall)
+        return v[:, h:h + self.nlocal[0], h:h + self.nlocal[1], h:h + self.nlocal[2]]
+
+    # ---- operators (names follow the reference entry points) ------------------------------------
+    def sync(self):
+        self._check(self.lib.lb200_sync(self.h))
+
+    def hydro_f_zero(self):
+        self._check(self.lib.lb200_hydro_f_zero(self.h))
+
+    def hydro_u_zero(self):
+        self._check(self.lib.lb200_hydro_u_zero(self.h))
+
+    def hydro_u_halo(self):
+        self._check(self.lib.lb200_hydro_u_halo(self.h))
+
+    def phi_halo(self):
+        self._check(self.lib.lb200_phi_halo(self.h))
+
+    def phi_grad_compute(self):
+        self._check(self.lib.lb200_phi_grad_compute(self.h))
+
+    def phi_force_calculation(self, sp):
+        self._check(self.lib.lb200_phi_force_calculation(self.h, C.byref(sp)))
+
+    def phi_cahn_hilliard(self, sp):
+        self._check(self.lib.lb200_phi_cahn_hilliard(self.h, C.byref(sp)))
+
+    def lb_collide(self, cp):
+        self._check(self.lib.lb200_lb_collide(self.h, C.byref(cp)))
+
+    def lb_halo(self):
+        self._check(self.lib.lb200_lb_halo(self.h))
+
+    def lb_propagation(self):
+        self._check(self.lib.lb200_lb_propagation(self.h))
+
+    def step(self, cp, sp=None, nsteps=1):
+        self._check(self.lib.lb200_step(self.h, C.byref(cp), C.byref(sp) if sp is not None else None, nsteps))
+
+    def step_api(self, cp, sp=None, nsteps=1):
+        """The same time step through the individual reference-named entry points, in the
+        reference driver's order (src/ludwig.c:528-860)."""
+        for _ in range(nsteps):
+            self.hydro_f_zero()
+            if sp is not None:
+                self.phi_halo()
+                self.phi_grad_compute()
+                self.phi_force_calculation(sp)
+                self.phi_cahn_hilliard(sp)
+            self.hydro_u_zero()
+            self.lb_collide(cp)
+            self.lb_halo()
+            self.lb_propagation()
+
+    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch")
+
+    def profile(self, on=True):
+        self._check(self.lib.lb200_profile(self.h, int(on)))
+
+    def profile_get(self):
+        """{class: (total_ms, launches)} accumulated since profile(True)."""
+        out = {}
+        for i, name in enumerate(self.KCLASSES):
+            t, n = C.c_double(), C.c_int()
+            self._check(self.lib.lb200_profile_get(self.h, i, C.byref(t), C.byref(n)))
+            out[name] = (t.value, n.value)
+        return out
+
+    def launch_count(self):
+        return int(self.lib.lb200_launch_count(self.h))
+
+    def stream(self):
+        return self.lib.lb200_stream(self.h)
+
+    # ---- multi-GPU ------------------------------------------------------------------------------
+    def nccl_unique_id(self):
+        buf = (C.c_char * 128)()
+        self._check(self.lib.lb200_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def nccl_init(self, unique_id, nranks, rank):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        comm = C.c_void_p()
+        self._check(self.lib.lb200_nccl_comm_create(buf, nranks, rank, C.byref(comm)))
+        self._nccl = comm
+        self._check(self.lib.lb200_attach_nccl(self.h, comm))

@@ -1,0 +1,778 @@
+// lb200_api.cu -- context object and C-ABI of libludwig_b200.so (see include/ludwig_b200.h).
+//
+// Host-side logic only: owns the device arrays, tracks lazily-applied operations (pending
+// propagation, logically-zero force / velocity), derives the per-call collision constants the way
+// the reference's host code does, and launches the kernels in lb200_kernels.cu.
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+#ifndef LB200_NO_NCCL
+#include <nccl.h>
+#endif
+
+#include "ludwig_b200.h"
+#include "lb200_kernels.h"
+
+// ------------------------------------------------------------------------------------------------
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char * fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+  return fail(LB200_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); } while (0)
+
+enum ZeroState {ARRAY_CLEAN = 0, ZERO_PENDING = 1, INTERIOR_ONLY = 2};
+
+struct lb200_s {
+  lb200_options_t opt;
+  Lb200Geom g;
+  int device;
+  cudaStream_t stream;
+  const Lb200Kernels * k;
+
+  int nvel, ndist;
+  Lb200ModelDev model_h;
+  Lb200ModelDev * model_d;
+  int unrolled19;            // use the unrolled D3Q19 projections (reference -D_D3Q19_ build)
+
+  double * f;                // current distributions
+  double * fprime;           // propagation target
+  double * phi;
+  double * phinew;
+  double * u;
+  double * rho;
+  double * force;
+  double * grad;
+  double * delsq;
+  char * status;             // device copy of map->status, nullptr if all fluid
+  int map_all_fluid;
+
+  // x-plane staging for slab decomposition
+  double * xlo;
+  double * xhi;
+  size_t stage_doubles;
+
+  int prop_pending;          // lb_propagation requested, not yet applied (fused into next collide)
+  int force_state;           // ZeroState
+  int u_state;
+
+  long long launches;
+  void * nccl;               // ncclComm_t
+
+  // optional per-kernel-class timing with CUDA events on the launching stream
+  int profile;
+  std::vector<cudaEvent_t> * ev[LB200_KCLASS_MAX];   // pairs (start, stop)
+};
+
+// bracket one launch (or a short sequence) with events when profiling is on
+struct ProfScope {
+  lb200_t * c; int cls; cudaEvent_t stop;
+  ProfScope(lb200_t * c_, int cls_) : c(c_), cls(cls_), stop(nullptr) {
+    if (!c->profile) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+    c->ev[cls]->push_back(a); c->ev[cls]->push_back(b);
+    stop = b;
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, c->stream); }
+};
+
+const char * lb200_last_error(void) { return g_err; }
+int lb200_version(void) { return 100; }
+
+// ---- model tables: same double-precision expressions as the reference host code --------------
+// (src/lb_d3q19.c:108-150, src/lb_d3q15.c:150-178, src/lb_d3q27.c:155-195, normalisers
+//  src/lb_d3q19.c:72-78, inverse src/lb_data.c:640-646)
+
+static const signed char cv19[19][3] = {
+  { 0,  0,  0},
+  { 1,  1,  0}, { 1,  0,  1}, { 1,  0,  0}, { 1,  0, -1}, { 1, -1,  0}, { 0,  1,  1},
+  { 0,  1,  0}, { 0,  1, -1}, { 0,  0,  1}, { 0,  0, -1}, { 0, -1,  1}, { 0, -1,  0},
+  { 0, -1, -1}, {-1,  1,  0}, {-1,  0,  1}, {-1,  0,  0}, {-1,  0, -1}, {-1, -1,  0}};
+
+static const signed char cv15[15][3] = {
+  { 0,  0,  0},
+  { 1,  1,  1}, { 1,  1, -1}, { 1,  0,  0}, { 1, -1,  1}, { 1, -1, -1}, { 0,  1,  0},
+  { 0,  0,  1}, { 0,  0, -1}, { 0, -1,  0}, {-1,  1,  1}, {-1,  1, -1}, {-1,  0,  0},
+  {-1, -1,  1}, {-1, -1, -1}};
+
+static int model_init(int nvel, Lb200ModelDev * md) {
+  const double cs2 = (1.0/3.0);
+  double wv[27], na[27];
+  memset(md, 0, sizeof(*md));
+  md->nvel = nvel;
+
+  if (nvel == 19) {
+    for (int p = 0; p < 19; p++) {
+      int c1 = 0;
+      for (int a = 0; a < 3; a++) { md->cv[p][a] = cv19[p][a]; c1 += abs(cv19[p][a]); }
+      wv[p] = (c1 == 0) ? 12.0/36.0 : (c1 == 1) ? 2.0/36.0 : 1.0/36.0;
+    }
+  }
+  else if (nvel == 15) {
+    for (int p = 0; p < 15; p++) {
+      int c1 = 0;
+      for (int a = 0; a < 3; a++) { md->cv[p][a] = cv15[p][a]; c1 += abs(cv15[p][a]); }
+      wv[p] = (c1 == 0) ? 16.0/72.0 : (c1 == 1) ? 8.0/72.0 : 1.0/72.0;
+    }
+  }
+  else if (nvel == 27) {
+    int p = 1;
+    wv[0] = 64.0/216.0;
+    for (int i = -1; i <= 1; i++)
+      for (int j = -1; j <= 1; j++)
+	for (int k = -1; k <= 1; k++) {
+	  int c1 = abs(i) + abs(j) + abs(k);
+	  if (c1 == 0) continue;
+	  md->cv[p][0] = i; md->cv[p][1] = j; md->cv[p][2] = k;
+	  wv[p] = (c1 == 1) ? 16.0/216.0 : (c1 == 2) ? 4.0/216.0 : 1.0/216.0;
+	  p++;
+	}
+  }
+  else {
+    return -1;
+  }
+
+  for (int p = 0; p < nvel; p++) {
+    double rho = 1.0;
+    double cx = rho*md->cv[p][0];
+    double cy = rho*md->cv[p][1];
+    double cz = rho*md->cv[p][2];
+    double (*ma)[27] = md->ma;
+    ma[0][p] = rho;  ma[1][p] = cx;  ma[2][p] = cy;  ma[3][p] = cz;
+    ma[4][p] = cx*cx - cs2;  ma[5][p] = cx*cy;  ma[6][p] = cx*cz;
+    ma[7][p] = cy*cy - cs2;  ma[8][p] = cy*cz;  ma[9][p] = cz*cz - cs2;
+    if (nvel == 19) {
+      double c2   = cx*cx + cy*cy + cz*cz;
+      double chi1 = (2.0*c2 - 3.0)*(3.0*cz*cz - c2);
+      double chi2 = (2.0*c2 - 3.0)*(cy*cy - cx*cx);
+      double chi3 = 3.0*c2*c2 - 6.0*c2 + 1;
+      ma[10][p] = chi1; ma[11][p] = chi1*cx; ma[12][p] = chi1*cy; ma[13][p] = chi1*cz;
+      ma[14][p] = chi2; ma[15][p] = chi2*cx; ma[16][p] = chi2*cy; ma[17][p] = chi2*cz;
+      ma[18][p] = chi3;
+    }
+    if (nvel == 15) {
+      ma[10][p] = cx*cy*cz;
+      ma[11][p] = 3.0*(cz*cz - cs2)*cx;
+      ma[12][p] = 3.0*(cx*cx - cs2)*cy;
+      ma[13][p] = 3.0*(cy*cy - cs2)*cz;
+      ma[14][p] = 9.0*(cx*cx - cs2)*(cy*cy - cs2) - 3.0*(cz*cz - cs2);
+    }
+    if (nvel == 27) {
+      ma[10][p] = 3.0*(cx*cx - cs2)*cy;  ma[11][p] = 3.0*(cx*cx - cs2)*cz;
+      ma[12][p] = 3.0*(cy*cy - cs2)*cz;  ma[13][p] = 3.0*(cy*cy - cs2)*cx;
+      ma[14][p] = 3.0*(cz*cz - cs2)*cx;  ma[15][p] = 3.0*(cz*cz - cs2)*cy;
+      ma[16][p] = cx*cy*cz;
+      ma[17][p] = 9.0*(cx*cx - cs2)*(cy*cy - cs2);
+      ma[18][p] = 9.0*(cy*cy - cs2)*(cz*cz - cs2);
+      ma[19][p] = 9.0*(cz*cz - cs2)*(cx*cx - cs2);
+      ma[20][p] = 9.0*(cx*cx - cs2)*cy*cz;
+      ma[21][p] = 9.0*(cy*cy - cs2)*cz*cx;
+      ma[22][p] = 9.0*(cz*cz - cs2)*cx*cy;
+      ma[23][p] = 9.0*(cx*cx - cs2)*(cy*cy - cs2)*cz;
+      ma[24][p] = 9.0*(cy*cy - cs2)*(cz*cz - cs2)*cx;
+      ma[25][p] = 9.0*(cz*cz - cs2)*(cx*cx - cs2)*cy;
+      ma[26][p] = 27.0*(cx*cx - cs2)*(cy*cy - cs2)*(cz*cz - cs2);
+    }
+  }
+  for (int m = 0; m < nvel; m++) {
+    double wip = 0.0;
+    for (int p = 0; p < nvel; p++) wip += wv[p]*md->ma[m][p]*md->ma[m][p];
+    na[m] = 1.0/wip;
+  }
+  for (int p = 0; p < nvel; p++)
+    for (int m = 0; m < nvel; m++) {
+      double maba = md->ma[m][p];
+      md->mi[p][m] = wv[p]*na[m]*maba;
+    }
+  return 0;
+}
+
+// ---- collision constants per call: src/collision.c:1269-1520 (rates), 1906-1958 ---------------
+
+static int collide_dev(const lb200_t * c, const lb200_collide_param_t * cp, Lb200CollideDev * d) {
+  const double cs2 = (1.0/3.0);
+  memset(d, 0, sizeof(*d));
+  for (int a = 0; a < 3; a++) d->fg[a] = cp->force_global[a];
+  d->rtau = 1.0/(0.5 + cp->eta_shear/(cp->rho0*cs2));
+  if (cp->nrelax == LB200_RELAXATION_BGK) d->rtau_bulk = 1.0/(0.5 + cp->eta_shear/(cp->rho0*cs2));
+  else d->rtau_bulk = 1.0/(0.5 + cp->eta_bulk/(cp->rho0*cs2));
+  d->tmr = 2.0 - d->rtau;
+  for (int m = 0; m < 27; m++) d->rtau_ghost[m] = 1.0;
+  d->ghost = 0;
+  if (cp->nrelax == LB200_RELAXATION_BGK) {
+    for (int m = 10; m < c->nvel; m++) d->rtau_ghost[m] = d->rtau;
+    d->ghost = 1;
+  }
+  else if (cp->nrelax == LB200_RELAXATION_TRT) {
+    double tau = cp->eta_shear/(cp->rho0*cs2);
+    double rg = 0.5 + 2.0*tau/(tau + 3.0/8.0);
+    if (rg > 2.0) rg = 2.0;
+    if (c->nvel == 15) {
+      d->rtau_ghost[10] = d->rtau; d->rtau_ghost[14] = d->rtau;
+      d->rtau_ghost[11] = rg; d->rtau_ghost[12] = rg; d->rtau_ghost[13] = rg;
+    }
+    else if (c->nvel == 19) {
+      d->rtau_ghost[10] = d->rtau; d->rtau_ghost[14] = d->rtau; d->rtau_ghost[18] = d->rtau;
+      d->rtau_ghost[11] = rg; d->rtau_ghost[12] = rg; d->rtau_ghost[13] = rg;
+      d->rtau_ghost[15] = rg; d->rtau_ghost[16] = rg; d->rtau_ghost[17] = rg;
+    }
+    else {
+      return fail(LB200_EINVAL, "TRT is defined for D3Q15 and D3Q19 only (reference src/collision.c:1219-1242)");
+    }
+    d->ghost = 1;
+  }
+  else if (cp->nrelax != LB200_RELAXATION_M10) {
+    return fail(LB200_EINVAL, "unknown relaxation scheme %d", cp->nrelax);
+  }
+  return 0;
+}
+
+static void symm_dev(const lb200_t * c, const lb200_symm_param_t * sp, Lb200SymmDev * d) {
+  d->a = sp->a; d->b = sp->b; d->kappa = sp->kappa; d->mobility = sp->mobility;
+  for (int a = 0; a < 3; a++) d->gm[a] = sp->gradmu[a];
+  d->order = sp->adv_order;
+  d->wz = (c->g.nl[2] == 1) ? 0.0 : 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+
+static int alloc_d(double ** p, size_t n) {
+  CUDA_TRY(cudaMalloc((void **) p, n*sizeof(double)));
+  CUDA_TRY(cudaMemset(*p, 0, n*sizeof(double)));
+  return 0;
+}
+
+int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
+  if (o == nullptr || pctx == nullptr) return fail(LB200_EINVAL, "null argument");
+  *pctx = nullptr;
+  for (int a = 0; a < 3; a++) if (o->nlocal[a] < 1) return fail(LB200_EINVAL, "nlocal[%d] = %d", a, o->nlocal[a]);
+  if (o->nhalo < 1 || o->nhalo > 3) return fail(LB200_EINVAL, "nhalo = %d", o->nhalo);
+  if (o->have_phi && o->nhalo < 2) return fail(LB200_EINVAL, "the symmetric FD route needs nhalo >= 2 (reference src/ludwig.c:1198)");
+  if (o->nvel != 15 && o->nvel != 19 && o->nvel != 27) return fail(LB200_EINVAL, "nvel = %d", o->nvel);
+  if (o->ndist != 1) return fail(LB200_EINVAL, "ndist = %d: only the single-distribution path is built (symmetric_lb is a 'next' row)", o->ndist);
+  if (o->cart_size < 1 || o->cart_rank < 0 || o->cart_rank >= o->cart_size) return fail(LB200_EINVAL, "bad cart_size/cart_rank");
+  if (o->halo_scheme != LB200_HALO_FULL && o->halo_scheme != LB200_HALO_REDUCED) return fail(LB200_EINVAL, "halo_scheme = %d", o->halo_scheme);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(LB200_ENODEVICE, "no CUDA device: libludwig_b200 has no CPU fallback");
+  }
+
+  lb200_t * c = new (std::nothrow) lb200_t();
+  if (c == nullptr) return fail(LB200_ENOMEM, "host allocation failed");
+  memset(c, 0, sizeof(*c));
+  c->opt = *o;
+  if (o->device >= 0) { CUDA_TRY(cudaSetDevice(o->device)); }
+  CUDA_TRY(cudaGetDevice(&c->device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->k = (o->math == LB200_MATH_STRICT) ? &lb200_kernels_strict : &lb200_kernels_fast;
+  c->nvel = o->nvel;
+  c->ndist = o->ndist;
+
+  Lb200Geom & g = c->g;
+  for (int a = 0; a < 3; a++) { g.nl[a] = o->nlocal[a]; g.nall[a] = o->nlocal[a] + 2*o->nhalo; g.per[a] = o->periodic[a] != 0; }
+  g.nh = o->nhalo;
+  g.ys = g.nall[2];
+  g.xs = g.nall[1]*g.nall[2];
+  const long long ns = (long long) g.nall[0]*g.nall[1]*g.nall[2];
+  if (ns*c->nvel*c->ndist > 2147483647LL) {
+    delete c;
+    return fail(LB200_EINVAL, "nsites*nvel exceeds INT_MAX (reference guard src/lb_data.c:116-120)");
+  }
+  g.nsites = (int) ns;
+  g.remote_x = (o->cart_size > 1);
+  g.has_lo = g.per[0] || o->cart_rank > 0;
+  g.has_hi = g.per[0] || o->cart_rank < o->cart_size - 1;
+
+  if (model_init(c->nvel, &c->model_h) != 0) { delete c; return fail(LB200_EINVAL, "model"); }
+  CUDA_TRY(cudaMalloc((void **) &c->model_d, sizeof(Lb200ModelDev)));
+  CUDA_TRY(cudaMemcpy(c->model_d, &c->model_h, sizeof(Lb200ModelDev), cudaMemcpyHostToDevice));
+  c->unrolled19 = (c->nvel == 19);
+  {
+    const char * e = getenv("LB200_GENERIC_D3Q19");     // model matrices instead of coded constants
+    if (e && atoi(e) != 0) c->unrolled19 = 0;
+  }
+
+  const size_t nsz = (size_t) g.nsites;
+  int rc = 0;
+  rc |= alloc_d(&c->f, nsz*c->nvel*c->ndist);
+  rc |= alloc_d(&c->fprime, nsz*c->nvel*c->ndist);
+  rc |= alloc_d(&c->u, nsz*3);
+  rc |= alloc_d(&c->rho, nsz);
+  rc |= alloc_d(&c->force, nsz*3);
+  if (o->have_phi) {
+    rc |= alloc_d(&c->phi, nsz);
+    rc |= alloc_d(&c->phinew, nsz);
+    rc |= alloc_d(&c->grad, nsz*3);
+    rc |= alloc_d(&c->delsq, nsz);
+  }
+  if (g.remote_x) {
+    // staging for the widest exchange: max(nvel planes of depth 1, 3 components of depth nhalo)
+    size_t a = (size_t) c->nvel*c->ndist*g.xs;
+    size_t b = (size_t) 3*g.nh*g.xs;
+    c->stage_doubles = a > b ? a : b;
+    rc |= alloc_d(&c->xlo, c->stage_doubles);
+    rc |= alloc_d(&c->xhi, c->stage_doubles);
+  }
+  if (rc != 0) { lb200_free(c); return LB200_ECUDA; }
+  CUDA_TRY(cudaMalloc((void **) &c->status, nsz));
+  CUDA_TRY(cudaMemset(c->status, 0, nsz));
+  c->map_all_fluid = 1;
+
+  c->force_state = ARRAY_CLEAN;
+  c->u_state = ARRAY_CLEAN;
+  for (int i = 0; i < LB200_KCLASS_MAX; i++) c->ev[i] = new std::vector<cudaEvent_t>();
+  *pctx = c;
+  return 0;
+}
+
+int lb200_profile(lb200_t * c, int on) {
+  if (c == nullptr) return fail(LB200_EINVAL, "null context");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < LB200_KCLASS_MAX; i++) {
+    for (cudaEvent_t e : *c->ev[i]) cudaEventDestroy(e);
+    c->ev[i]->clear();
+  }
+  c->profile = on;
+  return 0;
+}
+
+int lb200_profile_get(lb200_t * c, int kclass, double * total_ms, int * count) {
+  if (c == nullptr || kclass < 0 || kclass >= LB200_KCLASS_MAX) return fail(LB200_EINVAL, "bad argument");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  double t = 0.0;
+  const std::vector<cudaEvent_t> & v = *c->ev[kclass];
+  for (size_t i = 0; i + 1 < v.size(); i += 2) {
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+    t += ms;
+  }
+  if (total_ms) *total_ms = t;
+  if (count) *count = (int) (v.size()/2);
+  return 0;
+}
+
+int lb200_free(lb200_t * c) {
+  if (c == nullptr) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->f); cudaFree(c->fprime); cudaFree(c->u); cudaFree(c->rho); cudaFree(c->force);
+  cudaFree(c->phi); cudaFree(c->phinew); cudaFree(c->grad); cudaFree(c->delsq);
+  cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->model_d);
+  for (int i = 0; i < LB200_KCLASS_MAX; i++) {
+    if (c->ev[i]) { for (cudaEvent_t e : *c->ev[i]) cudaEventDestroy(e); delete c->ev[i]; }
+  }
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int lb200_nsites(const lb200_t * c) { return c ? c->g.nsites : LB200_EINVAL; }
+long long lb200_launch_count(const lb200_t * c) { return c ? c->launches : 0; }
+void * lb200_stream(lb200_t * c) { return c ? (void *) c->stream : nullptr; }
+
+int lb200_sync(lb200_t * c) {
+  if (c == nullptr) return fail(LB200_EINVAL, "null context");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static const char * status_ptr(const lb200_t * c) { return c->map_all_fluid ? nullptr : c->status; }
+static const Lb200ModelDev * model_ptr(const lb200_t * c) { return c->unrolled19 ? nullptr : c->model_d; }
+
+// ---- lazily applied operations --------------------------------------------------------------------
+
+// apply a pending lb_propagation as a stand-alone sweep (reference semantics, src/propagation.c)
+static int materialise_propagation(lb200_t * c) {
+  if (!c->prop_pending) return 0;
+  {
+    ProfScope ps(c, LB200_K_PROPAGATE);
+    c->launches += c->k->propagate(c->stream, c->g, c->model_d, c->nvel, c->ndist, c->f, c->fprime);
+  }
+  double * t = c->f; c->f = c->fprime; c->fprime = t;       // lb_model_swapf, src/propagation.c:211-240
+  c->prop_pending = 0;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int materialise_zero(lb200_t * c, double * a, int * state) {
+  if (*state == ZERO_PENDING) {
+    CUDA_TRY(cudaMemsetAsync(a, 0, (size_t) 3*c->g.nsites*sizeof(double), c->stream));
+  }
+  else if (*state == INTERIOR_ONLY) {
+    c->launches += c->k->zero_outside(c->stream, c->g, 3, a);
+  }
+  *state = ARRAY_CLEAN;
+  return 0;
+}
+
+// ---- memcpy --------------------------------------------------------------------------------------
+
+static int array_info(lb200_t * c, int array, double ** dev, size_t * ncomp) {
+  switch (array) {
+  case LB200_F:     *dev = c->f;     *ncomp = (size_t) c->nvel*c->ndist; break;
+  case LB200_PHI:   *dev = c->phi;   *ncomp = 1; break;
+  case LB200_U:     *dev = c->u;     *ncomp = 3; break;
+  case LB200_RHO:   *dev = c->rho;   *ncomp = 1; break;
+  case LB200_FORCE: *dev = c->force; *ncomp = 3; break;
+  case LB200_GRAD:  *dev = c->grad;  *ncomp = 3; break;
+  case LB200_DELSQ: *dev = c->delsq; *ncomp = 1; break;
+  default: return fail(LB200_EINVAL, "unknown array id %d", array);
+  }
+  if (*dev == nullptr) return fail(LB200_ESTATE, "array %d is not allocated in this context (have_phi = 0?)", array);
+  return 0;
+}
+
+static int do_memcpy(lb200_t * c, int array, double * host, int kind, int async) {
+  if (c == nullptr || host == nullptr) return fail(LB200_EINVAL, "null argument");
+  if (kind != LB200_HOST_TO_DEVICE && kind != LB200_DEVICE_TO_HOST) return fail(LB200_EINVAL, "memcpy kind %d", kind);
+  CUDA_TRY(cudaSetDevice(c->device));
+
+  if (array == LB200_MAP) {
+    // status is exchanged as doubles at this interface and held as bytes on the device
+    const size_t ns = (size_t) c->g.nsites;
+    std::vector<char> tmp(ns);
+    if (kind == LB200_HOST_TO_DEVICE) {
+      int all_fluid = 1;
+      for (size_t i = 0; i < ns; i++) { tmp[i] = (char) host[i]; if (tmp[i] != 0) all_fluid = 0; }
+      CUDA_TRY(cudaMemcpyAsync(c->status, tmp.data(), ns, cudaMemcpyHostToDevice, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      c->map_all_fluid = all_fluid;
+    }
+    else {
+      CUDA_TRY(cudaMemcpyAsync(tmp.data(), c->status, ns, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      for (size_t i = 0; i < ns; i++) host[i] = (double) tmp[i];
+    }
+    return 0;
+  }
+
+  double * dev = nullptr;
+  size_t ncomp = 0;
+  int rc = array_info(c, array, &dev, &ncomp);
+  if (rc != 0) return rc;
+
+  if (array == LB200_F) {
+    rc = materialise_propagation(c);
+    if (rc != 0) return rc;
+    dev = c->f;
+  }
+  if (kind == LB200_DEVICE_TO_HOST) {
+    if (array == LB200_FORCE) materialise_zero(c, c->force, &c->force_state);
+    if (array == LB200_U) materialise_zero(c, c->u, &c->u_state);
+  }
+  else {
+    if (array == LB200_FORCE) c->force_state = ARRAY_CLEAN;
+    if (array == LB200_U) c->u_state = ARRAY_CLEAN;
+  }
+
+  const size_t bytes = ncomp*(size_t) c->g.nsites*sizeof(double);
+  if (kind == LB200_HOST_TO_DEVICE) {
+    CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  else {
+    CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (!async) CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int lb200_memcpy(lb200_t * c, int array, double * host, int kind) { return do_memcpy(c, array, host, kind, 0); }
+int lb200_memcpy_async(lb200_t * c, int array, double * host, int kind) { return do_memcpy(c, array, host, kind, 1); }
+
+int lb200_device_ptr(lb200_t * c, int array, void ** ptr) {
+  if (c == nullptr || ptr == nullptr) return fail(LB200_EINVAL, "null argument");
+  if (array == LB200_MAP) { *ptr = c->status; return 0; }
+  double * dev = nullptr;
+  size_t ncomp = 0;
+  int rc = array_info(c, array, &dev, &ncomp);
+  if (rc != 0) return rc;
+  if (array == LB200_F) { rc = materialise_propagation(c); dev = c->f; }
+  *ptr = dev;
+  return rc;
+}
+
+// ---- x-plane exchange between slabs (NCCL send/recv over NVLink) --------------------------------
+// Replaces MPI_Isend/Irecv/Waitall of lb_halo_post / field_halo_post.  For each component the
+// `depth` boundary planes at either end of the slab are contiguous in the SOA layout, so no pack
+// kernel is needed on the send side.
+
+static int exchange_x(lb200_t * c, const double * data, int ncomp, int depth) {
+  if (!c->g.remote_x) return 0;
+#ifdef LB200_NO_NCCL
+  return fail(LB200_ECOMM, "library built without NCCL");
+#else
+  if (c->nccl == nullptr) return fail(LB200_ECOMM, "cart_size > 1 but no NCCL communicator attached (lb200_attach_nccl)");
+  ncclComm_t comm = (ncclComm_t) c->nccl;
+  const Lb200Geom & g = c->g;
+  const int size = c->opt.cart_size, rank = c->opt.cart_rank;
+  const int left = (rank - 1 + size) % size;
+  const int right = (rank + 1) % size;
+  const size_t chunk = (size_t) depth*g.xs;
+  const size_t ns = (size_t) g.nsites;
+  // my top planes i in [N-d+1, N] go right (-> neighbour's xlo); my bottom planes i in [1, d] go left
+  const size_t off_hi = (size_t) (g.nl[0] - depth + 1 + g.nh - 1)*g.xs;
+  const size_t off_lo = (size_t) (1 + g.nh - 1)*g.xs;
+
+  ncclResult_t r = ncclGroupStart();
+  for (int n = 0; n < ncomp && r == ncclSuccess; n++) {
+    if (g.has_hi) r = ncclSend(data + n*ns + off_hi, chunk, ncclDouble, right, comm, c->stream);
+    if (g.has_lo && r == ncclSuccess) r = ncclSend(data + n*ns + off_lo, chunk, ncclDouble, left, comm, c->stream);
+    if (g.has_lo && r == ncclSuccess) r = ncclRecv(c->xlo + n*chunk, chunk, ncclDouble, left, comm, c->stream);
+    if (g.has_hi && r == ncclSuccess) r = ncclRecv(c->xhi + n*chunk, chunk, ncclDouble, right, comm, c->stream);
+  }
+  ncclResult_t r2 = ncclGroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess) {
+    return fail(LB200_ECOMM, "NCCL halo exchange: %s", ncclGetErrorString(r != ncclSuccess ? r : r2));
+  }
+  return 0;
+#endif
+}
+
+int lb200_attach_nccl(lb200_t * c, void * comm) {
+  if (c == nullptr) return fail(LB200_EINVAL, "null context");
+  c->nccl = comm;
+  return 0;
+}
+
+int lb200_nccl_unique_id(void * id128) {
+#ifdef LB200_NO_NCCL
+  return fail(LB200_ECOMM, "library built without NCCL");
+#else
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclResult_t r = ncclGetUniqueId((ncclUniqueId *) id128);
+  if (r != ncclSuccess) return fail(LB200_ECOMM, "ncclGetUniqueId: %s", ncclGetErrorString(r));
+  return 0;
+#endif
+}
+
+int lb200_nccl_comm_create(const void * id128, int nranks, int rank, void ** comm) {
+#ifdef LB200_NO_NCCL
+  return fail(LB200_ECOMM, "library built without NCCL");
+#else
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t cm;
+  ncclResult_t r = ncclCommInitRank(&cm, nranks, id, rank);
+  if (r != ncclSuccess) return fail(LB200_ECOMM, "ncclCommInitRank: %s", ncclGetErrorString(r));
+  *comm = (void *) cm;
+  return 0;
+#endif
+}
+
+int lb200_nccl_comm_destroy(void * comm) {
+#ifndef LB200_NO_NCCL
+  if (comm) ncclCommDestroy((ncclComm_t) comm);
+#endif
+  return 0;
+}
+
+// ---- operators ------------------------------------------------------------------------------------
+
+#define CTX_ENTER(c) do { if ((c) == nullptr) return fail(LB200_EINVAL, "null context"); \
+  CUDA_TRY(cudaSetDevice((c)->device)); } while (0)
+#define CTX_LEAVE_SYNC(c) do { CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaStreamSynchronize((c)->stream)); return 0; } while (0)
+
+int lb200_hydro_f_zero(lb200_t * c) {
+  CTX_ENTER(c);
+  c->force_state = ZERO_PENDING;         // folded into the next producer / consumer of the force
+  return 0;
+}
+
+int lb200_hydro_u_zero(lb200_t * c) {
+  CTX_ENTER(c);
+  c->u_state = ZERO_PENDING;
+  return 0;
+}
+
+static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int reduced) {
+  ProfScope ps(c, LB200_K_HALO);
+  int rc = exchange_x(c, data, ncomp, depth);
+  if (rc != 0) return rc;
+  c->launches += c->k->halo(c->stream, c->g, c->model_d, ncomp, depth, reduced, data, c->xlo, c->xhi);
+  return 0;
+}
+
+static int u_halo_async(lb200_t * c) {
+  if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+  int rc = halo_field(c, c->u, 3, c->g.nh, 0);
+  c->u_state = ARRAY_CLEAN;              // every halo site within nhalo has just been written
+  return rc;
+}
+
+int lb200_hydro_u_halo(lb200_t * c) {
+  CTX_ENTER(c);
+  int rc = u_halo_async(c);
+  if (rc != 0) return rc;
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_phi_halo(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  int rc = halo_field(c, c->phi, 1, c->g.nh, 0);
+  if (rc != 0) return rc;
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_phi_grad_compute(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  {
+    ProfScope ps(c, LB200_K_GRAD);
+    c->launches += c->k->grad27(c->stream, c->g, c->phi, c->grad, c->delsq);
+  }
+  CTX_LEAVE_SYNC(c);
+}
+
+static int phi_force_async(lb200_t * c, const Lb200SymmDev & sd) {
+  const int accumulate = (c->force_state != ZERO_PENDING);
+  ProfScope ps(c, LB200_K_FORCE_CH);
+  c->launches += c->k->phi_force(c->stream, c->g, sd, accumulate, c->phi, c->grad, c->delsq, c->force);
+  if (c->force_state == ZERO_PENDING) c->force_state = INTERIOR_ONLY;
+  return 0;
+}
+
+int lb200_phi_force_calculation(lb200_t * c, const lb200_symm_param_t * sp) {
+  CTX_ENTER(c);
+  if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  if (sp == nullptr) return fail(LB200_EINVAL, "null parameters");
+  Lb200SymmDev sd;
+  symm_dev(c, sp, &sd);
+  phi_force_async(c, sd);
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_phi_cahn_hilliard(lb200_t * c, const lb200_symm_param_t * sp) {
+  CTX_ENTER(c);
+  if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  if (sp == nullptr) return fail(LB200_EINVAL, "null parameters");
+  if (sp->adv_order < 1 || sp->adv_order > 3) return fail(LB200_EINVAL, "advection order %d: device kernels exist for 1-3 (reference src/advection.c:456-480)", sp->adv_order);
+  Lb200SymmDev sd;
+  symm_dev(c, sp, &sd);
+  int rc = u_halo_async(c);               // hydro_u_halo inside phi_cahn_hilliard, src/phi_cahn_hilliard.c:229
+  if (rc != 0) return rc;
+  // phinew holds phi everywhere (halo included) so that the swap keeps the reference's view
+  CUDA_TRY(cudaMemcpyAsync(c->phinew, c->phi, (size_t) c->g.nsites*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  {
+    ProfScope ps(c, LB200_K_FORCE_CH);
+    c->launches += c->k->cahn_hilliard(c->stream, c->g, sd, c->phi, c->delsq, c->u, status_ptr(c), c->phinew);
+  }
+  double * t = c->phi; c->phi = c->phinew; c->phinew = t;
+  CTX_LEAVE_SYNC(c);
+}
+
+static int collide_async(lb200_t * c, const Lb200CollideDev & cd) {
+  ProfScope ps(c, LB200_K_COLLIDE);
+  const double * force = (c->force_state == ZERO_PENDING) ? nullptr : c->force;
+  if (c->prop_pending) {
+    // lb_propagation(t) fused with lb_collide(t+1): one read and one write of every population
+    c->launches += c->k->collide(c->stream, c->g, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime,
+				 force, status_ptr(c), c->rho, c->u);
+    double * t = c->f; c->f = c->fprime; c->fprime = t;
+    c->prop_pending = 0;
+  }
+  else {
+    c->launches += c->k->collide(c->stream, c->g, cd, model_ptr(c), c->nvel, 0, c->f, c->f,
+				 force, status_ptr(c), c->rho, c->u);
+  }
+  if (c->u_state == ZERO_PENDING) c->u_state = INTERIOR_ONLY;
+  return 0;
+}
+
+int lb200_lb_collide(lb200_t * c, const lb200_collide_param_t * cp) {
+  CTX_ENTER(c);
+  if (cp == nullptr) return fail(LB200_EINVAL, "null parameters");
+  Lb200CollideDev cd;
+  int rc = collide_dev(c, cp, &cd);
+  if (rc != 0) return rc;
+  collide_async(c, cd);
+  CTX_LEAVE_SYNC(c);
+}
+
+static int lb_halo_async(lb200_t * c) {
+  int rc = materialise_propagation(c);
+  if (rc != 0) return rc;
+  return halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED);
+}
+
+int lb200_lb_halo(lb200_t * c) {
+  CTX_ENTER(c);
+  int rc = lb_halo_async(c);
+  if (rc != 0) return rc;
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_lb_propagation(lb200_t * c) {
+  CTX_ENTER(c);
+  int rc = materialise_propagation(c);   // two propagations in a row: apply the first
+  if (rc != 0) return rc;
+  c->prop_pending = 1;
+  return 0;
+}
+
+// ---- whole time steps ---------------------------------------------------------------------------------
+// Order of operations of the reference driver (src/ludwig.c:528-860):
+//   hydro_f_zero; field_halo(phi); field_grad_compute; phi_force_calculation; phi_cahn_hilliard
+//   (hydro_u_halo inside); hydro_u_zero; lb_collide; lb_halo; lb_propagation.
+// Fusions (results unchanged): propagation(t) + collide(t+1) in one pull kernel; stress + force
+// divergence + Cahn-Hilliard fluxes + update in one kernel; the two zeroing sweeps folded away.
+
+int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_param_t * sp, int nsteps) {
+  CTX_ENTER(c);
+  if (cp == nullptr) return fail(LB200_EINVAL, "null collision parameters");
+  const int binary = (sp != nullptr && c->phi != nullptr);
+  if (binary && (sp->adv_order < 1 || sp->adv_order > 3)) return fail(LB200_EINVAL, "advection order %d", sp->adv_order);
+  Lb200CollideDev cd;
+  Lb200SymmDev sd;
+  int rc = collide_dev(c, cp, &cd);
+  if (rc != 0) return rc;
+  if (binary) symm_dev(c, sp, &sd);
+
+  for (int n = 0; n < nsteps; n++) {
+    c->force_state = ZERO_PENDING;                                       // hydro_f_zero
+    if (binary) {
+      rc = halo_field(c, c->phi, 1, c->g.nh, 0);                         // field_halo(phi)
+      if (rc != 0) return rc;
+      {
+	ProfScope ps(c, LB200_K_GRAD);
+	c->launches += c->k->grad27(c->stream, c->g, c->phi, c->grad, c->delsq);   // field_grad_compute
+      }
+      rc = u_halo_async(c);                                              // hydro_u_halo
+      if (rc != 0) return rc;
+      {
+	// phi_force_calculation + phi_cahn_hilliard
+	ProfScope ps(c, LB200_K_FORCE_CH);
+	c->launches += c->k->force_ch(c->stream, c->g, sd, 0, c->phi, c->grad, c->delsq, c->u,
+				      status_ptr(c), c->force, c->phinew);
+      }
+      c->force_state = INTERIOR_ONLY;
+      double * t = c->phi; c->phi = c->phinew; c->phinew = t;
+    }
+    c->u_state = ZERO_PENDING;                                           // hydro_u_zero
+    collide_async(c, cd);                                                // (lb_propagation +) lb_collide
+    rc = lb_halo_async(c);                                               // lb_halo
+    if (rc != 0) return rc;
+    c->prop_pending = 1;                                                 // lb_propagation (lazy)
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,70 @@
+// lb200_kernels.h -- launcher table shared by the two builds of lb200_kernels.cu
+// (fast: FMA contraction on; strict: -fmad=false, bit-identical to the reference CPU build).
+#pragma once
+
+#include <cuda_runtime.h>
+
+struct Lb200Geom {
+  int nl[3];        // local extent
+  int nh;           // halo width of the allocation
+  int nall[3];      // nl + 2 nh
+  int xs, ys;       // strides (zs = 1)
+  int nsites;
+  int per[3];       // periodic (global)
+  int has_lo;       // an x-neighbour exists on the low / high side (periodic or interior slab)
+  int has_hi;
+  int remote_x;     // 1: x-neighbours are other GPUs, their planes arrive in staging buffers
+};
+
+struct Lb200CollideDev {
+  double fg[3];         // force_global
+  double rtau;          // 1/tau_shear
+  double rtau_bulk;
+  double tmr;           // 2.0 - rtau
+  double rtau_ghost[27];
+  int ghost;            // 0: every ghost mode relaxes at rate 1 (M10): ghosts are not projected
+};
+
+struct Lb200SymmDev {
+  double a, b, kappa, mobility;
+  double gm[3];
+  int order;
+  double wz;            // 0 if nlocal[Z] == 1
+};
+
+struct Lb200ModelDev {       // generic (non-unrolled) model tables
+  int nvel;
+  signed char cv[27][3];
+  double ma[27][27];
+  double mi[27][27];
+};
+
+struct Lb200Kernels {
+  // fused pull-stream + collide (pull = 1: fdst <- collide(pull(fsrc)));  pull = 0: in place on fsrc
+  // force == nullptr: force field is identically zero.  status == nullptr: all fluid.
+  int (*collide)(cudaStream_t, const Lb200Geom &, const Lb200CollideDev &, const Lb200ModelDev *,
+		 int nvel, int pull, const double * fsrc, double * fdst, const double * force,
+		 const char * status, double * rho, double * u);
+  // reference propagation: fprime <- pull(f), x in [1,N], y/z halo self copy
+  int (*propagate)(cudaStream_t, const Lb200Geom &, const Lb200ModelDev *, int nvel, int ndist,
+		   const double * f, double * fprime);
+  // halo shell of depth d for ncomp components; reduced != 0 only for distributions (needs cv)
+  int (*halo)(cudaStream_t, const Lb200Geom &, const Lb200ModelDev *, int ncomp, int depth,
+	      int reduced, double * data, const double * xlo, const double * xhi);
+  int (*grad27)(cudaStream_t, const Lb200Geom &, const double * phi, double * grad, double * delsq);
+  // force = [force +] -div P(phi, grad, delsq)   (accumulate = 0: plain store)
+  int (*phi_force)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, int accumulate,
+		   const double * phi, const double * grad, const double * delsq, double * force);
+  // phinew(interior) = phi - div(flux(phi, delsq, u)); status may be nullptr
+  int (*cahn_hilliard)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, const double * phi,
+		       const double * delsq, const double * u, const char * status, double * phinew);
+  // both of the above in one sweep
+  int (*force_ch)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, int accumulate,
+		  const double * phi, const double * grad, const double * delsq, const double * u,
+		  const char * status, double * force, double * phinew);
+  // zero everything outside the interior (ncomp components)
+  int (*zero_outside)(cudaStream_t, const Lb200Geom &, int ncomp, double * data);
+};
+
+extern const Lb200Kernels lb200_kernels_fast;
+extern const Lb200Kernels lb200_kernels_strict;
