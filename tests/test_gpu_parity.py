@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import ludwig_b200 as lb
-from common import BINARY, ETA, rel_err, seeded_state
+from common import BINARY, ETA, close_fast, rel_err, seeded_state
 from oracle import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -107,7 +107,7 @@ def test_collide(nvel, nrelax, math):
         if math == lb.MATH_STRICT:
             assert np.array_equal(a, b)
         else:
-            assert rel_err(a, b) <= TOL_FAST
+            assert close_fast(a, b)
 
 
 @pytest.mark.parametrize("nlocal", [(8, 8, 8), (5, 6, 37)])
@@ -148,7 +148,7 @@ def test_phi_force(math):
     if math == lb.MATH_STRICT:
         assert np.array_equal(got, force) and np.array_equal(got2, force2)
     else:
-        assert rel_err(got, force) <= TOL_FAST and rel_err(got2, force2) <= TOL_FAST
+        assert close_fast(got, force) and close_fast(got2, force2)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
@@ -183,7 +183,7 @@ def test_cahn_hilliard(order, math, solid):
     if math == lb.MATH_STRICT:
         assert np.array_equal(got, rphi)
     else:
-        assert rel_err(got, rphi) <= TOL_FAST
+        assert close_fast(got, rphi)
 
 
 @pytest.mark.parametrize("nlocal", [(16, 16, 16), (8, 12, 36)])
@@ -221,7 +221,7 @@ def test_binary_steps_fast_tolerance(nrelax):
         got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO))}
     orc.step(cpo, spo, 1, nsteps, st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
     for k in got:
-        assert rel_err(orc.interior(got[k]), orc.interior(st[k])) <= TOL_FAST, k
+        assert close_fast(orc.interior(got[k]), orc.interior(st[k])), k
 
 
 @pytest.mark.parametrize("nvel", [19, 15, 27])
