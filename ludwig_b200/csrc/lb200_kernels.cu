@@ -274,8 +274,8 @@ int launch_propagate(cudaStream_t st, const Lb200Geom & g, const Lb200ModelDev *
 // Halo shell.  Replaces the 26 pack kernels + MPI messages + 26 unpack kernels of
 // lb_halo (src/lb_data.c:924-1114, 1183-1210, 1317-1477) and field_halo (src/field.c:1093-1251,
 // 1329-1355, 1412-1531): every halo site within `depth` of the interior copies from the interior
-// site it is the periodic image of.  Across a non-periodic boundary nothing arrives (the
-// reference has no neighbour there: src/lb_data.c:1160-1172).  With x-slab decomposition the
+// site it is the periodic image of.  Across a non-periodic boundary there is no neighbour
+// (src/lb_data.c:1160-1172) and the reference unpacks zeros.  With x-slab decomposition the
 // x-images live on the neighbouring GPUs; their boundary planes are staged in xlo / xhi
 // (depth planes each, full y-z extent) before this kernel runs.
 // Reduced distribution halo: only populations with c_p . m = |m|^2 travel in direction m
@@ -327,10 +327,10 @@ halo_shell_kernel(const Lb200Geom g, const Lb200ModelDev * __restrict__ md, int 
   const int my = (jc < 1) ? 1 : (jc > g.nl[1] ? -1 : 0);
   const int mz = (kc < 1) ? 1 : (kc > g.nl[2] ? -1 : 0);
 
-  if (my != 0 && !g.per[1]) return;
-  if (mz != 0 && !g.per[2]) return;
-  if (mx > 0 && !g.has_lo) return;
-  if (mx < 0 && !g.has_hi) return;
+  // No neighbour in direction -m (non-periodic boundary): the reference unpacks its never-written,
+  // calloc'ed receive buffer there, i.e. zeros arrive (src/lb_data.c:1010-1011, src/field.c:1178-1187).
+  const bool absent = (my != 0 && !g.per[1]) || (mz != 0 && !g.per[2]) || (mx > 0 && !g.has_lo)
+    || (mx < 0 && !g.has_hi);
 
   const int sj = jc + my*g.nl[1];
   const int sk = kc + mz*g.nl[2];
@@ -341,7 +341,12 @@ halo_shell_kernel(const Lb200Geom g, const Lb200ModelDev * __restrict__ md, int 
   size_t sstride;
   size_t sidx;
 
-  if (mx != 0 && g.remote_x) {
+  if (absent) {
+    src = data;
+    sstride = 0;
+    sidx = 0;
+  }
+  else if (mx != 0 && g.remote_x) {
     // staging: [comp][d planes][nall_y][nall_z]; plane q of xlo = neighbour's i = N-d+1+q
     const int q = (mx > 0) ? (ic + d - 1) : (ic - g.nl[0] - 1);
     src = (mx > 0) ? xlo : xhi;
@@ -360,11 +365,11 @@ halo_shell_kernel(const Lb200Geom g, const Lb200ModelDev * __restrict__ md, int 
     for (int c = 0; c < ncomp; c++) {
       const int p = c % md->nvel;
       const int dot = mx*md->cv[p][0] + my*md->cv[p][1] + mz*md->cv[p][2];
-      if (dot == mm) data[c*ns + dst] = src[c*sstride + sidx];
+      if (dot == mm) data[c*ns + dst] = absent ? 0.0 : src[c*sstride + sidx];
     }
   }
   else {
-    for (int c = 0; c < ncomp; c++) data[c*ns + dst] = src[c*sstride + sidx];
+    for (int c = 0; c < ncomp; c++) data[c*ns + dst] = absent ? 0.0 : src[c*sstride + sidx];
   }
 }
 

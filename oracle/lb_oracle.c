@@ -201,7 +201,7 @@ void orc_propagation(const orc_geom_t * g, const orc_model_t * m, int ndist,
 /* ---- halo exchange on one periodic rank --------------------------------------------------
  * lb_halo regions: src/lb_data.c:1183-1210; reduced set: src/lb_data.c:1224-1239;
  * self-message short circuit: src/lb_data.c:1009-1011; no neighbour across a non-periodic
- * boundary: src/lb_data.c:1160-1172.
+ * boundary (src/lb_data.c:1160-1172): zeros are unpacked there.
  * field_halo regions: src/field.c:1329-1355.                                                */
 
 typedef struct { int imin, imax, jmin, jmax, kmin, kmax; } lim_t;
@@ -238,8 +238,12 @@ void orc_lb_halo(const orc_geom_t * g, const orc_model_t * m, int ndist, int red
 	int c[3] = {cx, cy, cz};
 	int mm = cx*cx + cy*cy + cz*cz;
 	lim_t s, r;
+	int absent;
 	if (mm == 0) continue;
-	if ((cx && !g->periodic[X]) || (cy && !g->periodic[Y]) || (cz && !g->periodic[Z])) continue;
+	/* No neighbour across a non-periodic boundary: nothing is received, but the reference still
+	 * unpacks its (calloc'ed, never written) receive buffer, i.e. zeros arrive
+	 * (src/lb_data.c:1010-1011 vs 1262-1266). */
+	absent = ((cx && !g->periodic[X]) || (cy && !g->periodic[Y]) || (cz && !g->periodic[Z]));
 	halo_limits(g, 1, c, &s, &r);
 
 	for (int q = 0; q < m->nvel; q++) {
@@ -251,7 +255,7 @@ void orc_lb_halo(const orc_geom_t * g, const orc_model_t * m, int ndist, int red
 	      for (int j = 0; j <= s.jmax - s.jmin; j++)
 		for (int k = 0; k <= s.kmax - s.kmin; k++) {
 		  fq[orc_index(g, r.imin + i, r.jmin + j, r.kmin + k)]
-		    = fq[orc_index(g, s.imin + i, s.jmin + j, s.kmin + k)];
+		    = absent ? 0.0 : fq[orc_index(g, s.imin + i, s.jmin + j, s.kmin + k)];
 		}
 	  }
 	}
@@ -269,8 +273,10 @@ void orc_field_halo(const orc_geom_t * g, int nf, double * data) {
       for (int cz = -1; cz <= 1; cz++) {
 	int c[3] = {cx, cy, cz};
 	lim_t s, r;
+	int absent;
 	if (cx == 0 && cy == 0 && cz == 0) continue;
-	if ((cx && !g->periodic[X]) || (cy && !g->periodic[Y]) || (cz && !g->periodic[Z])) continue;
+	/* as for lb_halo: zeros arrive from an absent neighbour (src/field.c:1178-1187, 1364) */
+	absent = ((cx && !g->periodic[X]) || (cy && !g->periodic[Y]) || (cz && !g->periodic[Z]));
 	halo_limits(g, g->nhalo, c, &s, &r);
 	for (int n = 0; n < nf; n++) {
 	  double * d = data + (size_t) n*ns;
@@ -278,7 +284,7 @@ void orc_field_halo(const orc_geom_t * g, int nf, double * data) {
 	    for (int j = 0; j <= s.jmax - s.jmin; j++)
 	      for (int k = 0; k <= s.kmax - s.kmin; k++) {
 		d[orc_index(g, r.imin + i, r.jmin + j, r.kmin + k)]
-		  = d[orc_index(g, s.imin + i, s.jmin + j, s.kmin + k)];
+		  = absent ? 0.0 : d[orc_index(g, s.imin + i, s.jmin + j, s.kmin + k)];
 	      }
 	}
       }

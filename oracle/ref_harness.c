@@ -118,7 +118,7 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
   physics_eta_bulk_set(s->phys, cfg->eta_bulk);
   { double fb[3] = {cfg->fbody[0], cfg->fbody[1], cfg->fbody[2]};
     physics_fbody_set(s->phys, fb); }
-  physics_mobility_set(s->phys, cfg->mobility);
+  if (cfg->mobility != 0.0) physics_mobility_set(s->phys, cfg->mobility);
   { double gm[3] = {cfg->gradmu[0], cfg->gradmu[1], cfg->gradmu[2]};
     physics_grad_mu_set(s->phys, gm); }
 

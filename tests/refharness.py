@@ -23,16 +23,23 @@ class RefCfg(C.Structure):
                 ("kappa", C.c_double), ("mobility", C.c_double), ("gradmu", C.c_double * 3)]
 
 
-def available(fast=False):
-    return os.path.exists(REF_FAST_SO if fast else REF_SO)
+def _so(fast=False, nvel=19):
+    if nvel != 19:
+        return os.path.join(HERE, "..", "oracle", "_ref", f"libludwig_ref_d3q{nvel}.so")
+    return REF_FAST_SO if fast else REF_SO
+
+
+def available(fast=False, nvel=19):
+    return os.path.exists(_so(fast, nvel))
 
 
 _libs = {}
 
 
-def _lib(fast=False):
-    if fast not in _libs:
-        lib = C.CDLL(REF_FAST_SO if fast else REF_SO)
+def _lib(fast=False, nvel=19):
+    key = (fast, nvel)
+    if key not in _libs:
+        lib = C.CDLL(_so(fast, nvel))
         lib.ref_create.restype = C.c_void_p
         lib.ref_create.argtypes = [C.POINTER(RefCfg)]
         lib.ref_time_steps.restype = C.c_double
@@ -47,8 +54,10 @@ def _lib(fast=False):
         lib.ref_init_rest.argtypes = [C.c_void_p, C.c_double]
         lib.ref_init_uniform_u.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double * 3)]
         lib.ref_init_spinodal.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
-        _libs[fast] = lib
-    return _libs[fast]
+        lib.ref_nvel.restype = C.c_int
+        assert lib.ref_nvel() == nvel
+        _libs[key] = lib
+    return _libs[key]
 
 
 class RefSim:
@@ -57,8 +66,8 @@ class RefSim:
     def __init__(self, ntotal, nhalo=1, periodic=(1, 1, 1), ndist=1, nrelax=0, ghost_off=0,
                  halo_reduced=0, have_phi=0, adv_order=1, conserve=0, rho0=1.0, eta_shear=1.0 / 6.0,
                  eta_bulk=None, fbody=(0, 0, 0), a=0.0, b=0.0, kappa=0.0, mobility=0.0,
-                 gradmu=(0, 0, 0), fast=False):
-        self.lib = _lib(fast)
+                 gradmu=(0, 0, 0), fast=False, nvel=19):
+        self.lib = _lib(fast, nvel)
         cfg = RefCfg()
         cfg.ntotal[:] = ntotal
         cfg.nhalo = nhalo
@@ -74,7 +83,7 @@ class RefSim:
         self.h = self.lib.ref_create(C.byref(cfg))
         self.nsites = self.lib.ref_nsites(self.h)
         self.ndist = ndist
-        self.nvel = 19
+        self.nvel = nvel
 
     def close(self):
         if self.h:

@@ -1,0 +1,213 @@
+"""Pins the oracle: oracle/lb_oracle.c (the CPU restatement the GPU tests check against) must agree
+BIT FOR BIT with the UNMODIFIED reference (ludwig-cf/ludwig v0.23.0) compiled from /root/reference by
+oracle/Makefile.ref into oracle/_ref/ (strict build: -O2 -ffp-contract=off, asserts on), driven through
+the reference's own entry points by oracle/ref_harness.c.
+
+Skipped when oracle/_ref has not been built (it needs /root/reference, i.e. this container); the
+committed golden vectors in tests/golden/ (test_golden.py) carry the same pin everywhere else."""
+import numpy as np
+import pytest
+
+import refharness as rh
+from common import BINARY, ETA
+from ludwig_b200.initial import equilibrium_f, spinodal_phi
+from oracle import Oracle
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def fill_random(sim, orc, what, rng, scale=1.0, shift=0.0):
+    a = scale * (rng.random((sim.get(what).shape[0], orc.nsites)) + shift)
+    sim.set(what, a)
+    return a
+
+
+@pytest.mark.parametrize("nvel", [19, 15, 27])
+@pytest.mark.parametrize("nlocal,nhalo", [((6, 5, 7), 1), ((4, 6, 5), 2)])
+def test_propagation(nvel, nlocal, nhalo):
+    if not rh.available(nvel=nvel):
+        pytest.skip("reference build for this velocity set missing")
+    orc = Oracle(nlocal, nhalo=nhalo, nvel=nvel)
+    rng = np.random.default_rng(1)
+    with rh.RefSim(nlocal, nhalo=nhalo, nvel=nvel) as s:
+        f = fill_random(s, orc, rh.REF_F, rng)
+        s.op("propagation")
+        ref = s.get(rh.REF_F)
+    fp = np.zeros_like(f)                 # reference fprime starts calloc'ed
+    orc.propagation(f, fp)
+    assert np.array_equal(fp, ref)
+
+
+@pytest.mark.parametrize("reduced", [0, 1])
+@pytest.mark.parametrize("periodic", [(1, 1, 1), (1, 0, 1), (0, 0, 0)])
+@pytest.mark.parametrize("nvel,nlocal,nhalo", [(19, (6, 5, 7), 1), (19, (4, 6, 5), 2), (15, (4, 4, 4), 1), (27, (3, 4, 5), 1)])
+def test_lb_halo(nvel, nlocal, nhalo, periodic, reduced):
+    if not rh.available(nvel=nvel):
+        pytest.skip("reference build for this velocity set missing")
+    orc = Oracle(nlocal, nhalo=nhalo, periodic=periodic, nvel=nvel)
+    rng = np.random.default_rng(2)
+    with rh.RefSim(nlocal, nhalo=nhalo, periodic=periodic, halo_reduced=reduced, nvel=nvel) as s:
+        f = fill_random(s, orc, rh.REF_F, rng)
+        s.op("lb_halo")
+        ref = s.get(rh.REF_F)
+    orc.lb_halo(f, reduced=reduced)
+    assert np.array_equal(f, ref)
+
+
+@pytest.mark.parametrize("periodic", [(1, 1, 1), (0, 1, 1)])
+@pytest.mark.parametrize("nlocal,nhalo", [((6, 5, 7), 2), ((4, 4, 4), 1), ((5, 3, 8), 3)])
+def test_field_halo(nlocal, nhalo, periodic):
+    orc = Oracle(nlocal, nhalo=nhalo, periodic=periodic)
+    rng = np.random.default_rng(3)
+    with rh.RefSim(nlocal, nhalo=nhalo, periodic=periodic, have_phi=int(nhalo >= 2), **(BINARY if nhalo >= 2 else {})) as s:
+        u = fill_random(s, orc, rh.REF_U, rng)
+        s.op("hydro_u_halo")
+        ref_u = s.get(rh.REF_U)
+        if nhalo >= 2:
+            phi = fill_random(s, orc, rh.REF_PHI, rng)
+            s.op("phi_halo")
+            ref_phi = s.get(rh.REF_PHI)
+    orc.field_halo(u)
+    assert np.array_equal(u, ref_u)
+    if nhalo >= 2:
+        orc.field_halo(phi)
+        assert np.array_equal(phi, ref_phi)
+
+
+@pytest.mark.parametrize("nrelax", [0, 1, 2])
+@pytest.mark.parametrize("nvel", [19, 15, 27])
+def test_collide(nvel, nrelax):
+    if not rh.available(nvel=nvel):
+        pytest.skip("reference build for this velocity set missing")
+    if nvel == 27 and nrelax == 2:
+        pytest.skip("TRT undefined for D3Q27 in the reference")
+    nlocal = (5, 4, 6)
+    orc = Oracle(nlocal, nhalo=1, nvel=nvel)
+    rng = np.random.default_rng(4)
+    fg = (1e-6, -2e-6, 3e-6)
+    with rh.RefSim(nlocal, nhalo=1, nrelax=nrelax, eta_shear=0.02, eta_bulk=0.05, fbody=fg, nvel=nvel) as s:
+        f = fill_random(s, orc, rh.REF_F, rng, scale=0.1, shift=0.5)
+        force = fill_random(s, orc, rh.REF_FORCE, rng, scale=1e-4, shift=-0.5)
+        s.op("collide")
+        ref_f, ref_u, ref_rho = s.get(rh.REF_F), s.get(rh.REF_U), s.get(rh.REF_RHO)
+    u = np.zeros((3, orc.nsites)); rho = np.zeros((1, orc.nsites))
+    cp = orc.collide_param(nrelax, 1.0, 0.02, eta_bulk=0.05, force=fg)
+    # the reference collides every y,z of the allocation for x in [1,N] (src/kernel_3d_v.c:50-71)
+    orc.collide(cp, f, force, rho, u, include_halo=1)
+    assert np.array_equal(f, ref_f)
+    assert np.array_equal(u, ref_u)
+    assert np.array_equal(rho, ref_rho)
+
+
+def test_gradient_stress_force_fluxes():
+    """Every stage of the phi sector on its own, including the stored stress and the four flux arrays."""
+    nlocal = (6, 5, 7)
+    orc = Oracle(nlocal, nhalo=2)
+    rng = np.random.default_rng(5)
+    gm = (1e-4, -2e-4, 3e-4)
+    for order in (1, 2, 3):
+        with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=order, eta_shear=ETA, gradmu=gm, **BINARY) as s:
+            phi = fill_random(s, orc, rh.REF_PHI, rng, scale=0.1, shift=-0.5)
+            u = fill_random(s, orc, rh.REF_U, rng, scale=0.05, shift=-0.5)
+            s.op("hydro_f_zero")
+            s.op("phi_halo"); s.op("grad_compute")
+            ref_phi_h, ref_grad, ref_delsq = s.get(rh.REF_PHI), s.get(rh.REF_GRAD), s.get(rh.REF_DELSQ)
+            s.op("phi_force")
+            ref_str, ref_force = s.get(rh.REF_STR), s.get(rh.REF_FORCE)
+            s.op("cahn_hilliard")
+            ref_flux, ref_phi = s.get(rh.REF_FLUX), s.get(rh.REF_PHI)
+        sp = orc.symm_param(gradmu=gm, adv_order=order, **BINARY)
+        grad = np.zeros((3, orc.nsites)); delsq = np.zeros((1, orc.nsites))
+        strs = np.zeros((9, orc.nsites)); force = np.zeros((3, orc.nsites)); flux = np.zeros((4, orc.nsites))
+        orc.field_halo(phi)
+        assert np.array_equal(phi, ref_phi_h)
+        orc.grad_27pt(phi, grad, delsq)
+        assert np.array_equal(grad, ref_grad) and np.array_equal(delsq, ref_delsq)
+        orc.stress_symm(sp, phi, grad, delsq, strs)
+        # the reference's stress array is malloc'ed; it is defined for x in [0,N+1], all y,z
+        xs_ = slice(orc.nhalo - 1, orc.nhalo + nlocal[0] + 1)
+        assert np.array_equal(strs.reshape((9,) + orc.nall)[:, xs_], ref_str.reshape((9,) + orc.nall)[:, xs_])
+        orc.force_divergence(strs, force)
+        assert np.array_equal(force, ref_force)
+        orc.field_halo(u)
+        orc.advection(order, u, phi, flux)
+        orc.flux_mu(sp, phi, delsq, flux)
+        orc.flux_mu_ext(sp, flux)
+        # flux arrays: compare where the reference defines them (x in [1,N], y,z in [0,N])
+        h = orc.nhalo
+        sl = (slice(None), slice(h, h + nlocal[0]), slice(h - 1, h + nlocal[1]), slice(h - 1, h + nlocal[2]))
+        assert np.array_equal(flux.reshape((4,) + orc.nall)[sl], ref_flux.reshape((4,) + orc.nall)[sl])
+        orc.phi_update(flux, phi)
+        assert np.array_equal(orc.interior(phi), orc.interior(ref_phi))
+
+
+def test_no_flux_mask_with_solid_sites():
+    nlocal = (6, 5, 7)
+    orc = Oracle(nlocal, nhalo=2)
+    rng = np.random.default_rng(6)
+    status = (rng.random(orc.nsites) < 0.15).astype(np.int8)
+    with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=3, eta_shear=ETA, **BINARY) as s:
+        s.set(rh.REF_MAP, status.astype(np.float64))
+        phi = fill_random(s, orc, rh.REF_PHI, rng, scale=0.1, shift=-0.5)
+        u = fill_random(s, orc, rh.REF_U, rng, scale=0.05, shift=-0.5)
+        delsq = fill_random(s, orc, rh.REF_DELSQ, rng, scale=0.1, shift=-0.5)
+        s.op("cahn_hilliard")
+        ref_phi = s.get(rh.REF_PHI)
+    sp = orc.symm_param(adv_order=3, **BINARY)
+    flux = np.zeros((4, orc.nsites))
+    orc.field_halo(u)
+    orc.advection(3, u, phi, flux)
+    orc.flux_mu(sp, phi, delsq, flux)
+    orc.flux_mu_ext(sp, flux)
+    orc.no_flux(status, flux)
+    orc.phi_update(flux, phi)
+    assert np.array_equal(orc.interior(phi), orc.interior(ref_phi))
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("nlocal", [(12, 10, 8), (16, 16, 16)])
+def test_binary_time_steps(order, nlocal):
+    nsteps = 8
+    orc = Oracle(nlocal, nhalo=2)
+    fg = (1e-6, 2e-6, 3e-6)
+    with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=order, ghost_off=1, eta_shear=ETA, fbody=fg, **BINARY) as s:
+        s.init_rest(1.0)
+        s.init_spinodal(8361235, 0.0, 0.05)
+        f, phi = s.get(rh.REF_F), s.get(rh.REF_PHI)
+        assert np.array_equal(f, equilibrium_f(nlocal, 2))
+        assert np.array_equal(phi, spinodal_phi(nlocal, 2, 8361235))
+        s.step(nsteps)
+        ref = {k: s.get(w) for k, w in (("f", rh.REF_F), ("phi", rh.REF_PHI), ("u", rh.REF_U), ("rho", rh.REF_RHO),
+                                         ("force", rh.REF_FORCE), ("grad", rh.REF_GRAD), ("delsq", rh.REF_DELSQ))}
+    st = dict(f=f, phi=phi, u=np.zeros((3, orc.nsites)), rho=np.zeros((1, orc.nsites)),
+              force=np.zeros((3, orc.nsites)), grad=np.zeros((3, orc.nsites)), delsq=np.zeros((1, orc.nsites)))
+    orc.step(orc.collide_param(0, 1.0, ETA, force=fg), orc.symm_param(adv_order=order, **BINARY), 1, nsteps,
+             st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    for k in ref:
+        assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k
+
+
+@pytest.mark.parametrize("nrelax,reduced", [(0, 0), (1, 1), (2, 0)])
+@pytest.mark.parametrize("nvel", [19, 15, 27])
+def test_single_fluid_time_steps(nvel, nrelax, reduced):
+    if not rh.available(nvel=nvel):
+        pytest.skip("reference build for this velocity set missing")
+    if nvel == 27 and nrelax == 2:
+        pytest.skip("TRT undefined for D3Q27 in the reference")
+    nlocal, nsteps = (8, 6, 10), 6
+    orc = Oracle(nlocal, nhalo=1, nvel=nvel)
+    fg = (1e-6, 2e-6, 3e-6)
+    rng = np.random.default_rng(7)
+    with rh.RefSim(nlocal, nhalo=1, nrelax=nrelax, halo_reduced=reduced, eta_shear=0.1, fbody=fg, nvel=nvel) as s:
+        s.init_uniform_u(1.0, (0.002, 0.003, 0.004))
+        f = s.get(rh.REF_F)
+        orc.interior(f)[...] *= 1.0 + 1e-3 * (rng.random((nvel,) + nlocal) - 0.5)
+        s.set(rh.REF_F, f)
+        s.step(nsteps)
+        ref_f, ref_u, ref_rho = s.get(rh.REF_F), s.get(rh.REF_U), s.get(rh.REF_RHO)
+    u = np.zeros((3, orc.nsites)); rho = np.zeros((1, orc.nsites)); force = np.zeros((3, orc.nsites))
+    orc.step(orc.collide_param(nrelax, 1.0, 0.1, force=fg), None, 0, nsteps, f, None, u, rho, force, None, None,
+             halo_reduced=reduced)
+    assert np.array_equal(orc.interior(f), orc.interior(ref_f))
+    assert np.array_equal(orc.interior(u), orc.interior(ref_u))
+    assert np.array_equal(orc.interior(rho), orc.interior(ref_rho))

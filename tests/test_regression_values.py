@@ -1,0 +1,81 @@
+"""Known answers printed by the reference's own regression logs (8-11 significant digits), reproduced by the
+oracle from the reference's own initial conditions (restated in ludwig_b200/initial.py):
+
+* tests/regression/d3q19-short/serial-spin-fd1.{inp,log}: 64^3 spinodal binary fluid, A = -B = -0.00625,
+  K = 0.004, M = 1.25, eta = 0.00625, ghost modes off, 27pt gradient, advection order 1, seed 8361235.
+  Log lines 82-84 (t = 0) and 95-107 (t = 10).
+* tests/regression/d3q19-short/serial-dist-3du.log: uniform u = (0.002, 0.003, 0.004) on 32^3... momentum
+  6.5536e+01 9.8304e+01 1.31072e+02 preserved exactly (lines 66, 75)."""
+import numpy as np
+import pytest
+
+from common import BINARY, ETA
+from ludwig_b200.initial import equilibrium_f, spinodal_phi
+from oracle import Oracle, fed_density, stats_scalar
+
+
+def approx(v, digits):
+    return pytest.approx(v, rel=0.5 * 10.0 ** (1 - digits), abs=1e-30)
+
+
+def test_serial_spin_fd1_log():
+    n = (64, 64, 64)
+    orc = Oracle(n, nhalo=2)
+    f = equilibrium_f(n, 2)
+    phi = spinodal_phi(n, 2, 8361235, 0.0, 0.1)       # default "noise" amplitude 0.1 (src/field_phi_init_rt.c:27)
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+    sp = orc.symm_param(adv_order=1, **BINARY)
+    cp = orc.collide_param(0, 1.0, ETA)
+
+    # t = 0 (log lines 82-86): statistics after the initial phi halo + gradient
+    s = stats_scalar(orc, phi)
+    assert s[0] == approx(3.1484764e+00, 8) and s[1] == approx(1.2010484e-05, 8)
+    assert s[2] == approx(8.3289934e-04, 8)
+    assert s[3] == approx(-4.9999916e-02, 8) and s[4] == approx(4.9999705e-02, 8)
+    ph = phi.copy()
+    orc.field_halo(ph)
+    orc.grad_27pt(ph, grad, delsq)
+    assert fed_density(orc, sp, ph, grad) == approx(-2.3227909424e-06, 11)
+
+    orc.step(cp, sp, 1, 10, f, phi, u, rho, force, grad, delsq)
+
+    # t = 10 (log lines 95-107)
+    s = stats_scalar(orc, phi)
+    assert s[0] == approx(3.1484764e+00, 8) and s[1] == approx(1.2010484e-05, 8)
+    assert s[2] == approx(3.7820523e-04, 8)
+    assert s[3] == approx(-4.7270149e-02, 8) and s[4] == approx(4.6821679e-02, 8)
+    assert fed_density(orc, sp, phi, grad) == approx(-9.7510518349e-07, 11)
+    # [rho] is printed from the distributions after propagation (src/stats_distribution.c:125-200)
+    rho_f = f.sum(axis=0, keepdims=True)
+    r = stats_scalar(orc, rho_f)
+    assert r[0] == approx(262144.00, 8)
+    # variance of rho ~ 1 is <q^2> - <q>^2 in double in the reference: only ~2 digits survive the cancellation
+    assert r[2] == pytest.approx(1.5449642e-11, rel=5e-2)
+    assert r[3] == approx(0.99998006808, 11) and r[4] == approx(1.00001625877, 11)
+    ui = orc.interior(u)
+    for a, (lo, hi) in enumerate(((-1.3145696e-05, 1.2773457e-05), (-1.3301763e-05, 1.3768024e-05),
+                                  (-1.2618505e-05, 1.2966490e-05))):
+        assert ui[a].min() == approx(lo, 8) and ui[a].max() == approx(hi, 8)
+    # total momentum is a cancellation-dominated sum: the reference's tolerance is absolute 1e-12
+    fi = orc.interior(f)
+    mom = [(fi * orc.cv[:, a, None, None, None]).sum() for a in range(3)]
+    assert np.allclose(mom, 0.0, atol=1e-10)
+
+
+def test_serial_dist_3du_log():
+    n = (64, 64, 64)                       # size 64_64_64 in serial-dist-3du.inp -> 262144 sites
+    orc = Oracle(n, nhalo=1)
+    f = equilibrium_f(n, 1, 1.0, (0.002, 0.003, 0.004))
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force = z(3), z(1), z(3)
+
+    def momentum():
+        fi = orc.interior(f).astype(np.longdouble)
+        return [float((fi * orc.cv[:, a, None, None, None]).sum()) for a in range(3)]
+
+    expect = [262144 * 0.002, 262144 * 0.003, 262144 * 0.004]     # 5.24288e+02 ... scaled from the log's 32^3
+    assert momentum() == pytest.approx(expect, rel=1e-12)
+    orc.step(orc.collide_param(0, 1.0, 0.1), None, 0, 10, f, None, u, rho, force, None, None)
+    assert momentum() == pytest.approx(expect, rel=1e-12)
+    assert np.allclose(orc.interior(u)[0], 0.002, rtol=1e-13) and np.allclose(orc.interior(u)[2], 0.004, rtol=1e-13)
