@@ -62,9 +62,18 @@ struct lb200_s {
   int map_all_fluid;
 
   // x-plane staging for slab decomposition
-  double * xlo;
+  double * xlo;              // receive staging (planes of the low / high neighbour)
   double * xhi;
+  double * slo;              // send staging (my low / high boundary planes, all components contiguous)
+  double * shi;
   size_t stage_doubles;
+
+  // second stream: halo exchanges of lb200_step run here, overlapped with the compute kernels
+  cudaStream_t comm;
+  cudaEvent_t ev_main;       // last producer on the main stream
+  cudaEvent_t ev_phi, ev_u, ev_f;   // halo of phi / u / f complete (comm stream)
+  int phi_halo_valid;        // lb200_step already exchanged the halo of the current phi / u
+  int u_halo_valid;
 
   int prop_pending;          // lb_propagation requested, not yet applied (fused into next collide)
   int force_state;           // ZeroState
@@ -80,16 +89,16 @@ struct lb200_s {
 
 // bracket one launch (or a short sequence) with events when profiling is on
 struct ProfScope {
-  lb200_t * c; int cls; cudaEvent_t stop;
-  ProfScope(lb200_t * c_, int cls_) : c(c_), cls(cls_), stop(nullptr) {
+  lb200_t * c; int cls; cudaEvent_t stop; cudaStream_t st;
+  ProfScope(lb200_t * c_, int cls_, cudaStream_t st_ = nullptr) : c(c_), cls(cls_), stop(nullptr), st(st_ ? st_ : c_->stream) {
     if (!c->profile) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, c->stream);
+    cudaEventRecord(a, st);
     c->ev[cls]->push_back(a); c->ev[cls]->push_back(b);
     stop = b;
   }
-  ~ProfScope() { if (stop) cudaEventRecord(stop, c->stream); }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
 };
 
 const char * lb200_last_error(void) { return g_err; }
@@ -282,6 +291,11 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   if (o->device >= 0) { CUDA_TRY(cudaSetDevice(o->device)); }
   CUDA_TRY(cudaGetDevice(&c->device));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_phi, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_u, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_f, cudaEventDisableTiming));
   c->k = (o->math == LB200_MATH_STRICT) ? &lb200_kernels_strict : &lb200_kernels_fast;
   c->nvel = o->nvel;
   c->ndist = o->ndist;
@@ -324,12 +338,12 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
     rc |= alloc_d(&c->delsq, nsz);
   }
   if (g.remote_x) {
-    // staging for the widest exchange: max(nvel planes of depth 1, 3 components of depth nhalo)
-    size_t a = (size_t) c->nvel*c->ndist*g.xs;
-    size_t b = (size_t) 3*g.nh*g.xs;
-    c->stage_doubles = a > b ? a : b;
+    // staging: nvel planes of depth 1 (f) | 3 components of depth nhalo (u) | nhalo planes (phi)
+    c->stage_doubles = (size_t) c->nvel*c->ndist*g.xs + (size_t) 3*g.nh*g.xs + (size_t) g.nh*g.xs;
     rc |= alloc_d(&c->xlo, c->stage_doubles);
     rc |= alloc_d(&c->xhi, c->stage_doubles);
+    rc |= alloc_d(&c->slo, c->stage_doubles);
+    rc |= alloc_d(&c->shi, c->stage_doubles);
   }
   if (rc != 0) { lb200_free(c); return LB200_ECUDA; }
   CUDA_TRY(cudaMalloc((void **) &c->status, nsz));
@@ -375,10 +389,13 @@ int lb200_free(lb200_t * c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->f); cudaFree(c->fprime); cudaFree(c->u); cudaFree(c->rho); cudaFree(c->force);
   cudaFree(c->phi); cudaFree(c->phinew); cudaFree(c->grad); cudaFree(c->delsq);
-  cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->model_d);
+  cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->slo); cudaFree(c->shi); cudaFree(c->model_d);
   for (int i = 0; i < LB200_KCLASS_MAX; i++) {
     if (c->ev[i]) { for (cudaEvent_t e : *c->ev[i]) cudaEventDestroy(e); delete c->ev[i]; }
   }
+  cudaStreamSynchronize(c->comm);
+  cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_phi); cudaEventDestroy(c->ev_u); cudaEventDestroy(c->ev_f);
+  cudaStreamDestroy(c->comm);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -481,7 +498,8 @@ static int do_memcpy(lb200_t * c, int array, double * host, int kind, int async)
   }
   else {
     if (array == LB200_FORCE) c->force_state = ARRAY_CLEAN;
-    if (array == LB200_U) c->u_state = ARRAY_CLEAN;
+    if (array == LB200_U) { c->u_state = ARRAY_CLEAN; c->u_halo_valid = 0; }
+    if (array == LB200_PHI) c->phi_halo_valid = 0;
   }
 
   const size_t bytes = ncomp*(size_t) c->g.nsites*sizeof(double);
@@ -510,12 +528,23 @@ int lb200_device_ptr(lb200_t * c, int array, void ** ptr) {
   return rc;
 }
 
+// staging areas: f | u | phi are disjoint so that exchanges in flight at the same time never alias
+static double * stage_ptr(lb200_t * c, double * base, const double * data) {
+  if (base == nullptr) return nullptr;
+  const size_t xs = (size_t) c->g.xs;
+  if (data == c->u) return base + (size_t) c->nvel*c->ndist*xs;
+  if (data == c->phi || data == c->phinew) return base + (size_t) c->nvel*c->ndist*xs + (size_t) 3*c->g.nh*xs;
+  return base;
+}
+static double * stage_lo(lb200_t * c, const double * data) { return stage_ptr(c, c->xlo, data); }
+static double * stage_hi(lb200_t * c, const double * data) { return stage_ptr(c, c->xhi, data); }
+
 // ---- x-plane exchange between slabs (NCCL send/recv over NVLink) --------------------------------
 // Replaces MPI_Isend/Irecv/Waitall of lb_halo_post / field_halo_post.  For each component the
 // `depth` boundary planes at either end of the slab are contiguous in the SOA layout, so no pack
 // kernel is needed on the send side.
 
-static int exchange_x(lb200_t * c, const double * data, int ncomp, int depth) {
+static int exchange_x(lb200_t * c, cudaStream_t st, const double * data, int ncomp, int depth) {
   if (!c->g.remote_x) return 0;
 #ifdef LB200_NO_NCCL
   return fail(LB200_ECOMM, "library built without NCCL");
@@ -531,14 +560,32 @@ static int exchange_x(lb200_t * c, const double * data, int ncomp, int depth) {
   // my top planes i in [N-d+1, N] go right (-> neighbour's xlo); my bottom planes i in [1, d] go left
   const size_t off_hi = (size_t) (g.nl[0] - depth + 1 + g.nh - 1)*g.xs;
   const size_t off_lo = (size_t) (1 + g.nh - 1)*g.xs;
+  double * xlo = stage_lo(c, data);
+  double * xhi = stage_hi(c, data);
+
+  // One message per direction: the boundary planes of all components are first gathered into a
+  // contiguous send buffer with one strided device copy (each component's planes are already
+  // contiguous), laid out exactly as the receiver's staging area.  (One ncclSend per component cost
+  // 0.70 ms for the 19 populations at 256^2 planes; see profiles/r01_halo_exchange.md.)
+  const double * send_hi = data + off_hi;
+  const double * send_lo = data + off_lo;
+  if (ncomp > 1) {
+    double * shi = stage_ptr(c, c->shi, data);
+    double * slo = stage_ptr(c, c->slo, data);
+    if (g.has_hi) CUDA_TRY(cudaMemcpy2DAsync(shi, chunk*sizeof(double), data + off_hi, ns*sizeof(double),
+					     chunk*sizeof(double), ncomp, cudaMemcpyDeviceToDevice, st));
+    if (g.has_lo) CUDA_TRY(cudaMemcpy2DAsync(slo, chunk*sizeof(double), data + off_lo, ns*sizeof(double),
+					     chunk*sizeof(double), ncomp, cudaMemcpyDeviceToDevice, st));
+    send_hi = shi;
+    send_lo = slo;
+  }
+  const size_t count = (size_t) ncomp*chunk;
 
   ncclResult_t r = ncclGroupStart();
-  for (int n = 0; n < ncomp && r == ncclSuccess; n++) {
-    if (g.has_hi) r = ncclSend(data + n*ns + off_hi, chunk, ncclDouble, right, comm, c->stream);
-    if (g.has_lo && r == ncclSuccess) r = ncclSend(data + n*ns + off_lo, chunk, ncclDouble, left, comm, c->stream);
-    if (g.has_lo && r == ncclSuccess) r = ncclRecv(c->xlo + n*chunk, chunk, ncclDouble, left, comm, c->stream);
-    if (g.has_hi && r == ncclSuccess) r = ncclRecv(c->xhi + n*chunk, chunk, ncclDouble, right, comm, c->stream);
-  }
+  if (g.has_hi && r == ncclSuccess) r = ncclSend(send_hi, count, ncclDouble, right, comm, st);
+  if (g.has_lo && r == ncclSuccess) r = ncclSend(send_lo, count, ncclDouble, left, comm, st);
+  if (g.has_lo && r == ncclSuccess) r = ncclRecv(xlo, count, ncclDouble, left, comm, st);
+  if (g.has_hi && r == ncclSuccess) r = ncclRecv(xhi, count, ncclDouble, right, comm, st);
   ncclResult_t r2 = ncclGroupEnd();
   if (r != ncclSuccess || r2 != ncclSuccess) {
     return fail(LB200_ECOMM, "NCCL halo exchange: %s", ncclGetErrorString(r != ncclSuccess ? r : r2));
@@ -588,7 +635,7 @@ int lb200_nccl_comm_destroy(void * comm) {
 // ---- operators ------------------------------------------------------------------------------------
 
 #define CTX_ENTER(c) do { if ((c) == nullptr) return fail(LB200_EINVAL, "null context"); \
-  CUDA_TRY(cudaSetDevice((c)->device)); } while (0)
+  CUDA_TRY(cudaSetDevice((c)->device)); (c)->phi_halo_valid = 0; (c)->u_halo_valid = 0; } while (0)
 #define CTX_LEAVE_SYNC(c) do { CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaStreamSynchronize((c)->stream)); return 0; } while (0)
 
 int lb200_hydro_f_zero(lb200_t * c) {
@@ -603,11 +650,12 @@ int lb200_hydro_u_zero(lb200_t * c) {
   return 0;
 }
 
-static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int reduced) {
-  ProfScope ps(c, LB200_K_HALO);
-  int rc = exchange_x(c, data, ncomp, depth);
+static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int reduced, cudaStream_t st = nullptr) {
+  if (st == nullptr) st = c->stream;
+  ProfScope ps(c, LB200_K_HALO, st);
+  int rc = exchange_x(c, st, data, ncomp, depth);
   if (rc != 0) return rc;
-  c->launches += c->k->halo(c->stream, c->g, c->model_d, ncomp, depth, reduced, data, c->xlo, c->xhi);
+  c->launches += c->k->halo(st, c->g, c->model_d, ncomp, depth, reduced, data, stage_lo(c, data), stage_hi(c, data));
   return 0;
 }
 
@@ -737,7 +785,8 @@ int lb200_lb_propagation(lb200_t * c) {
 // divergence + Cahn-Hilliard fluxes + update in one kernel; the two zeroing sweeps folded away.
 
 int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_param_t * sp, int nsteps) {
-  CTX_ENTER(c);
+  if (c == nullptr) return fail(LB200_EINVAL, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
   if (cp == nullptr) return fail(LB200_EINVAL, "null collision parameters");
   const int binary = (sp != nullptr && c->phi != nullptr);
   if (binary && (sp->adv_order < 1 || sp->adv_order > 3)) return fail(LB200_EINVAL, "advection order %d", sp->adv_order);
@@ -746,32 +795,81 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   int rc = collide_dev(c, cp, &cd);
   if (rc != 0) return rc;
   if (binary) symm_dev(c, sp, &sd);
+  if (nsteps <= 0) return 0;
+
+  // The three halo exchanges run on the comm stream, each overlapped with a compute kernel that does
+  // not touch the array in flight:   phi(t+1) halo || collide(t);   f(t) and u(t) halos || grad(t+1),
+  // force+CH(t+1).  Same operations on the same data as the serial order, so results are unchanged.
+  cudaStream_t S = c->stream, C = c->comm;
+
+  // anything still pending on the main stream must be visible to the comm stream
+  CUDA_TRY(cudaEventRecord(c->ev_main, S));
+  CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
 
   for (int n = 0; n < nsteps; n++) {
     c->force_state = ZERO_PENDING;                                       // hydro_f_zero
     if (binary) {
-      rc = halo_field(c, c->phi, 1, c->g.nh, 0);                         // field_halo(phi)
-      if (rc != 0) return rc;
+      if (!c->phi_halo_valid) {                                          // field_halo(phi)
+	rc = halo_field(c, c->phi, 1, c->g.nh, 0, C);
+	if (rc != 0) return rc;
+	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+      }
+      CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
       {
 	ProfScope ps(c, LB200_K_GRAD);
-	c->launches += c->k->grad27(c->stream, c->g, c->phi, c->grad, c->delsq);   // field_grad_compute
+	c->launches += c->k->grad27(S, c->g, c->phi, c->grad, c->delsq);       // field_grad_compute
       }
-      rc = u_halo_async(c);                                              // hydro_u_halo
-      if (rc != 0) return rc;
+      if (!c->u_halo_valid) {                                            // hydro_u_halo
+	if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+	CUDA_TRY(cudaEventRecord(c->ev_main, S));
+	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+	rc = halo_field(c, c->u, 3, c->g.nh, 0, C);
+	if (rc != 0) return rc;
+	CUDA_TRY(cudaEventRecord(c->ev_u, C));
+	c->u_state = ARRAY_CLEAN;
+      }
+      CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
       {
 	// phi_force_calculation + phi_cahn_hilliard
 	ProfScope ps(c, LB200_K_FORCE_CH);
-	c->launches += c->k->force_ch(c->stream, c->g, sd, 0, c->phi, c->grad, c->delsq, c->u,
+	c->launches += c->k->force_ch(S, c->g, sd, 0, c->phi, c->grad, c->delsq, c->u,
 				      status_ptr(c), c->force, c->phinew);
       }
       c->force_state = INTERIOR_ONLY;
       double * t = c->phi; c->phi = c->phinew; c->phinew = t;
+      // halo of the NEW phi (needed by the next step's gradient) while the collision runs
+      CUDA_TRY(cudaEventRecord(c->ev_main, S));
+      CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+      rc = halo_field(c, c->phi, 1, c->g.nh, 0, C);
+      if (rc != 0) return rc;
+      CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+      c->phi_halo_valid = 1;
     }
     c->u_state = ZERO_PENDING;                                           // hydro_u_zero
+    if (c->prop_pending) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));   // halo of f from the previous step
     collide_async(c, cd);                                                // (lb_propagation +) lb_collide
-    rc = lb_halo_async(c);                                               // lb_halo
+    // lb_halo and the next step's hydro_u_halo while the next gradient / force kernels run
+    rc = materialise_propagation(c);
     if (rc != 0) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_main, S));
+    CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+    rc = halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED, C);   // lb_halo
+    if (rc != 0) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_f, C));
+    if (binary) {
+      rc = halo_field(c, c->u, 3, c->g.nh, 0, C);
+      if (rc != 0) return rc;
+      CUDA_TRY(cudaEventRecord(c->ev_u, C));
+      c->u_state = ARRAY_CLEAN;
+      c->u_halo_valid = 1;
+    }
     c->prop_pending = 1;                                                 // lb_propagation (lazy)
+  }
+  // rejoin: everything issued on the comm stream is ordered before whatever follows on the main stream
+  CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
+  if (binary) {
+    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
+    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
   }
   CUDA_TRY(cudaGetLastError());
   return 0;

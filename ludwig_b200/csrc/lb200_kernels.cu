@@ -14,6 +14,7 @@
 // reference root).
 
 #include <cstdint>
+#include <cstdlib>
 #include "lb200_kernels.h"
 #include "d3q19_proj.cuh"
 
@@ -28,11 +29,37 @@ namespace lb200_fast {
 namespace {
 
 constexpr int TPB = 128;
+constexpr int TPB_MAX = 256;
 
-__host__ inline void block_shape(int nz, dim3 & blk) {
+// threads per block of the site-per-thread kernels; LB200_TPB (64/128/256) overrides for tuning runs
+__host__ inline int tuned_tpb() {
+  static int tpb = 0;
+  if (tpb == 0) {
+    const char * e = getenv("LB200_TPB");
+    tpb = e ? atoi(e) : TPB;
+    if (tpb != 64 && tpb != 128 && tpb != 256) tpb = TPB;
+  }
+  return tpb;
+}
+
+__host__ inline int tuned_flag(const char * name, int dflt) {
+  const char * e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+__host__ inline void block_shape_n(int nz, int tpb, dim3 & blk) {
   int bx = ((nz + 31)/32)*32;
-  if (bx > TPB) bx = TPB;
-  blk = dim3(bx, TPB/bx, 1);
+  if (bx > tpb) bx = tpb;
+  blk = dim3(bx, tpb/bx, 1);
+}
+
+__host__ inline void block_shape(int nz, dim3 & blk) { block_shape_n(nz, tuned_tpb(), blk); }
+
+// streaming (evict-first) store: every population is written once per step and not re-read before
+// 2.8 GB of other traffic has passed through the 126 MB L2
+template <bool STREAM>
+__device__ __forceinline__ void store_f(double * p, double v) {
+  if (STREAM) __stcs(p, v); else *p = v;
 }
 
 // D3Q19 velocity set, reference src/lb_d3q19.h:26-39
@@ -85,8 +112,8 @@ __device__ __forceinline__ void relax_hydro(double * __restrict__ mode, const do
 // One thread per interior site.  PULL: read the 19 populations from the upwind neighbours of
 // fsrc (lb_propagation, src/propagation.c:153-200) and write the post-collision state to fdst,
 // so each population is read once and written once per time step.  !PULL: in-place collision.
-template <bool PULL, bool GHOST, bool HAS_FORCE, bool HAS_MAP>
-__global__ void __launch_bounds__(TPB)
+template <bool PULL, bool GHOST, bool HAS_FORCE, bool HAS_MAP, bool STREAM>
+__global__ void __launch_bounds__(TPB_MAX)
 collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 		     const double * __restrict__ fsrc, double * __restrict__ fdst,
 		     const double * __restrict__ hforce, const char * __restrict__ status,
@@ -139,7 +166,7 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
   d3q19_mode2f<GHOST>(mode, f);
 
 #pragma unroll
-  for (int p = 0; p < 19; p++) fdst[p*ns + index] = f[p];
+  for (int p = 0; p < 19; p++) store_f<STREAM>(fdst + p*ns + index, f[p]);
 
   rho_out[index] = rho;
 #pragma unroll
@@ -149,7 +176,7 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 // Generic velocity set (D3Q15, D3Q27; also D3Q19 with the model matrices instead of the coded
 // constants): reference src/collision.c:335-342, 541-551.
 template <bool PULL>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB_MAX)
 collide_generic_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 		       const Lb200ModelDev * __restrict__ md,
 		       const double * __restrict__ fsrc, double * __restrict__ fdst,
@@ -212,11 +239,14 @@ int launch_collide(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev &
 		   double * fdst, const double * force, const char * status,
 		   double * rho, double * u) {
   dim3 blk;
-  block_shape(g.nl[2], blk);
+  static const int ctpb = tuned_flag("LB200_COLLIDE_TPB", 256);
+  block_shape_n(g.nl[2], (ctpb == 64 || ctpb == 128 || ctpb == 256) ? ctpb : 256, blk);
   dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
 
   if (nvel == 19 && md == nullptr) {
-#define LB200_GO(P, G, F, M) collide_d3q19_kernel<P, G, F, M><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u)
+    static const int stream_stores = tuned_flag("LB200_STCS", 1);
+#define LB200_GO(P, G, F, M) do { if (stream_stores && P) collide_d3q19_kernel<P, G, F, M, true><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u); \
+    else collide_d3q19_kernel<P, G, F, M, false><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u); } while (0)
 #define LB200_SEL_M(P, G, F) do { if (status) LB200_GO(P, G, F, true); else LB200_GO(P, G, F, false); } while (0)
 #define LB200_SEL_F(P, G) do { if (force) LB200_SEL_M(P, G, true); else LB200_SEL_M(P, G, false); } while (0)
 #define LB200_SEL_G(P) do { if (cp.ghost) LB200_SEL_F(P, true); else LB200_SEL_F(P, false); } while (0)
@@ -238,7 +268,7 @@ int launch_collide(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev &
 // x in [1,N], every y,z of the allocation; y/z halo sites copy themselves.
 // ---------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB_MAX)
 propagate_kernel(const Lb200Geom g, const Lb200ModelDev * __restrict__ md, int nvel, int ndist,
 		 const double * __restrict__ f, double * __restrict__ fprime) {
 
@@ -392,60 +422,76 @@ int launch_halo(cudaStream_t st, const Lb200Geom & g, const Lb200ModelDev * md, 
 // ne = nhalo - 1 (:91-95).  Summation order as written there.
 // ---------------------------------------------------------------------------------------------
 
+// One thread per (j,k) column of the extended region, marching GRAD_XC planes along x with the three
+// 3x3 planes of the stencil held in registers: 9 new loads per site instead of 27 (the first version
+// of this kernel was L1-bound at 72 % l1tex throughput, profiles/r01_ncu_full_step_256_baseline.md).
+// The (j,k) plane is flattened so that no block is left with a sliver of the 258-wide rows.
+constexpr int GRAD_XC = 16;
+
 __global__ void __launch_bounds__(TPB)
 grad27_kernel(const Lb200Geom g, const double * __restrict__ field, double * __restrict__ grad,
 	      double * __restrict__ delsq) {
   const int ne = g.nh - 1;
-  const int kc = 1 - ne + blockIdx.x*blockDim.x + threadIdx.x;
-  const int jc = 1 - ne + blockIdx.y*blockDim.y + threadIdx.y;
-  const int ic = 1 - ne + blockIdx.z;
-  if (kc > g.nl[2] + ne || jc > g.nl[1] + ne) return;
+  const int ey = g.nl[1] + 2*ne, ez = g.nl[2] + 2*ne;
+  const int q = blockIdx.x*blockDim.x + threadIdx.x;
+  if (q >= ey*ez) return;
+  const int jc = 1 - ne + q/ez;
+  const int kc = 1 - ne + q%ez;
+  const int ic0 = 1 - ne + blockIdx.y*GRAD_XC;
+  int ic1 = ic0 + GRAD_XC - 1;
+  if (ic1 > g.nl[0] + ne) ic1 = g.nl[0] + ne;
 
   const int ys = g.ys;
-  const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
-  const int indexm1 = index - g.xs;
-  const int indexp1 = index + g.xs;
   const size_t ns = (size_t) g.nsites;
   const double r9 = (1.0/9.0);
+  int index = ((ic0 + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
 
-  // the 27 values, named [x][y][z] with 0 = -1, 1 = 0, 2 = +1
-  const double m_mm = field[indexm1-ys-1], m_m0 = field[indexm1-ys], m_mp = field[indexm1-ys+1];
-  const double m_0m = field[indexm1   -1], m_00 = field[indexm1   ], m_0p = field[indexm1   +1];
-  const double m_pm = field[indexm1+ys-1], m_p0 = field[indexm1+ys], m_pp = field[indexm1+ys+1];
-  const double c_mm = field[index  -ys-1], c_m0 = field[index  -ys], c_mp = field[index  -ys+1];
-  const double c_0m = field[index     -1], c_00 = field[index     ], c_0p = field[index     +1];
-  const double c_pm = field[index  +ys-1], c_p0 = field[index  +ys], c_pp = field[index  +ys+1];
-  const double p_mm = field[indexp1-ys-1], p_m0 = field[indexp1-ys], p_mp = field[indexp1-ys+1];
-  const double p_0m = field[indexp1   -1], p_00 = field[indexp1   ], p_0p = field[indexp1   +1];
-  const double p_pm = field[indexp1+ys-1], p_p0 = field[indexp1+ys], p_pp = field[indexp1+ys+1];
+  // planes x-1 (m_), x (c_), x+1 (p_); second letter y offset, third z offset (m = -1, 0, p = +1)
+  double m_mm, m_m0, m_mp, m_0m, m_00, m_0p, m_pm, m_p0, m_pp;
+  double c_mm, c_m0, c_mp, c_0m, c_00, c_0p, c_pm, c_p0, c_pp;
+  double p_mm, p_m0, p_mp, p_0m, p_00, p_0p, p_pm, p_p0, p_pp;
 
-  grad[0*ns + index] = 0.5*r9*
-    (+ p_mm - m_mm + p_m0 - m_m0 + p_mp - m_mp
-     + p_0m - m_0m + p_00 - m_00 + p_0p - m_0p
-     + p_pm - m_pm + p_p0 - m_p0 + p_pp - m_pp);
-  grad[1*ns + index] = 0.5*r9*
-    (+ m_pm - m_mm + m_p0 - m_m0 + m_pp - m_mp
-     + c_pm - c_mm + c_p0 - c_m0 + c_pp - c_mp
-     + p_pm - p_mm + p_p0 - p_m0 + p_pp - p_mp);
-  grad[2*ns + index] = 0.5*r9*
-    (+ m_mp - m_mm + m_0p - m_0m + m_pp - m_pm
-     + c_mp - c_mm + c_0p - c_0m + c_pp - c_pm
-     + p_mp - p_mm + p_0p - p_0m + p_pp - p_pm);
-  delsq[index] = r9*
-    (+ m_mm + m_m0 + m_mp + m_0m + m_00 + m_0p + m_pm + m_p0 + m_pp
-     + c_mm + c_m0 + c_mp + c_0m        + c_0p + c_pm + c_p0 + c_pp
-     + p_mm + p_m0 + p_mp + p_0m + p_00 + p_0p + p_pm + p_p0 + p_pp
-     - 26.0*c_00);
+#define LB200_LOAD_PLANE(P, base) \
+  P##_mm = field[(base)-ys-1]; P##_m0 = field[(base)-ys]; P##_mp = field[(base)-ys+1]; \
+  P##_0m = field[(base)   -1]; P##_00 = field[(base)   ]; P##_0p = field[(base)   +1]; \
+  P##_pm = field[(base)+ys-1]; P##_p0 = field[(base)+ys]; P##_pp = field[(base)+ys+1]
+
+  LB200_LOAD_PLANE(c, index - g.xs);
+  LB200_LOAD_PLANE(p, index);
+
+  for (int ic = ic0; ic <= ic1; ic++) {
+    m_mm = c_mm; m_m0 = c_m0; m_mp = c_mp; m_0m = c_0m; m_00 = c_00; m_0p = c_0p; m_pm = c_pm; m_p0 = c_p0; m_pp = c_pp;
+    c_mm = p_mm; c_m0 = p_m0; c_mp = p_mp; c_0m = p_0m; c_00 = p_00; c_0p = p_0p; c_pm = p_pm; c_p0 = p_p0; c_pp = p_pp;
+    LB200_LOAD_PLANE(p, index + g.xs);
+
+    grad[0*ns + index] = 0.5*r9*
+      (+ p_mm - m_mm + p_m0 - m_m0 + p_mp - m_mp
+       + p_0m - m_0m + p_00 - m_00 + p_0p - m_0p
+       + p_pm - m_pm + p_p0 - m_p0 + p_pp - m_pp);
+    grad[1*ns + index] = 0.5*r9*
+      (+ m_pm - m_mm + m_p0 - m_m0 + m_pp - m_mp
+       + c_pm - c_mm + c_p0 - c_m0 + c_pp - c_mp
+       + p_pm - p_mm + p_p0 - p_m0 + p_pp - p_mp);
+    grad[2*ns + index] = 0.5*r9*
+      (+ m_mp - m_mm + m_0p - m_0m + m_pp - m_pm
+       + c_mp - c_mm + c_0p - c_0m + c_pp - c_pm
+       + p_mp - p_mm + p_0p - p_0m + p_pp - p_pm);
+    delsq[index] = r9*
+      (+ m_mm + m_m0 + m_mp + m_0m + m_00 + m_0p + m_pm + m_p0 + m_pp
+       + c_mm + c_m0 + c_mp + c_0m        + c_0p + c_pm + c_p0 + c_pp
+       + p_mm + p_m0 + p_mp + p_0m + p_00 + p_0p + p_pm + p_p0 + p_pp
+       - 26.0*c_00);
+    index += g.xs;
+  }
+#undef LB200_LOAD_PLANE
 }
 
 int launch_grad27(cudaStream_t st, const Lb200Geom & g, const double * phi, double * grad,
 		  double * delsq) {
   const int ne = g.nh - 1;
   const int ex = g.nl[0] + 2*ne, ey = g.nl[1] + 2*ne, ez = g.nl[2] + 2*ne;
-  dim3 blk;
-  block_shape(ez, blk);
-  dim3 grd((ez + blk.x - 1)/blk.x, (ey + blk.y - 1)/blk.y, ex);
-  grad27_kernel<<<grd, blk, 0, st>>>(g, phi, grad, delsq);
+  dim3 grd((ey*ez + TPB - 1)/TPB, (ex + GRAD_XC - 1)/GRAD_XC, 1);
+  grad27_kernel<<<grd, TPB, 0, st>>>(g, phi, grad, delsq);
   return 1;
 }
 
@@ -524,113 +570,41 @@ __device__ __forceinline__ void site_force(const Lb200SymmDev & sp, const SiteFE
 // five kernels; here the six face fluxes of a site are formed in registers.
 // ---------------------------------------------------------------------------------------------
 
-// flux through the face between site s and s + str ("east"-like face of s), component velocity
-// u0 = u_a(s), u1 = u_a(s + str)
-template <int ORDER>
-__device__ __forceinline__ double adv_hi(const double * __restrict__ phi, int s, int str,
-					 double u0, double u1) {
+// Advective flux through the face between a "lo" site and the "hi" site one step up an axis, with the
+// four phi values along that axis already in registers: pm1 = phi(lo-1), plo, phi_, pp1 = phi(hi+1).
+// WEST = false: the face is owned by its lo site (fe, fy, fz: upwind test "u < 0");
+// WEST = true : the x face owned by its hi site (fw: upwind test "u > 0").  The two only differ in
+// which side a velocity of exactly zero picks (the flux is zero either way).
+template <int ORDER, bool WEST>
+__device__ __forceinline__ double adv_face(double u_lo, double u_hi, double pm1, double plo,
+					   double phi_, double pp1) {
   if (ORDER == 1) {
-    const double uf = 0.5*(u0 + u1);
-    const int idx = (uf < 0.0) ? s + str : s;
-    return uf*phi[idx];
+    const double uf = 0.5*(u_lo + u_hi);
+    const double up = WEST ? ((uf > 0.0) ? plo : phi_) : ((uf < 0.0) ? phi_ : plo);
+    return uf*up;
   }
   else if (ORDER == 2) {
-    return 0.5*(u0 + u1)*1.0*0.5*(phi[s] + phi[s + str]);
+    return 0.5*(u_lo + u_hi)*1.0*0.5*(plo + phi_);
   }
   else {
     const double a1 = -0.213933;
     const double a2 =  0.927865;
     const double a3 =  0.286067;
-    const double uf = 0.5*(u0 + u1);
-    double fd1, fd2, fd3;
-    if (uf < 0.0) { fd1 = phi[s + 2*str]; fd2 = phi[s + str]; fd3 = phi[s]; }
-    else          { fd1 = phi[s - str];   fd2 = phi[s];       fd3 = phi[s + str]; }
+    const double uf = 0.5*(u_lo + u_hi);
+    const bool from_lo = WEST ? (uf > 0.0) : !(uf < 0.0);       // flow from lo to hi
+    const double fd1 = from_lo ? pm1 : pp1;
+    const double fd2 = from_lo ? plo : phi_;
+    const double fd3 = from_lo ? phi_ : plo;
     return uf*(a1*fd1 + a2*fd2 + a3*fd3);
   }
 }
 
-// flux through the face between s - str and s as computed AT s ("west" face, x only)
-template <int ORDER>
-__device__ __forceinline__ double adv_west(const double * __restrict__ phi, int s, int str,
-					   double u0, double u1) {
-  if (ORDER == 1) {
-    const double uf = 0.5*(u0 + u1);
-    const int idx = (uf > 0.0) ? s - str : s;
-    return uf*phi[idx];
-  }
-  else if (ORDER == 2) {
-    return 0.5*(u0 + u1)*1.0*0.5*(phi[s - str] + phi[s]);
-  }
-  else {
-    const double a1 = -0.213933;
-    const double a2 =  0.927865;
-    const double a3 =  0.286067;
-    const double uf = 0.5*(u0 + u1);
-    double fd1, fd2, fd3;
-    if (uf > 0.0) { fd1 = phi[s - 2*str]; fd2 = phi[s - str]; fd3 = phi[s]; }
-    else          { fd1 = phi[s + str];   fd2 = phi[s];       fd3 = phi[s - str]; }
-    return uf*(a1*fd1 + a2*fd2 + a3*fd3);
-  }
-}
-
-template <int ORDER, bool HAS_MAP>
-__device__ __forceinline__ double site_phi_update(const Lb200Geom & g, const Lb200SymmDev & sp,
-						  const double * __restrict__ phi,
-						  const double * __restrict__ delsq,
-						  const double * __restrict__ u,
-						  const char * __restrict__ status, int s) {
-  const size_t ns = (size_t) g.nsites;
-  const int xs = g.xs, ys = g.ys;
-  const double M = sp.mobility;
-
-  const double mu0 = symm_mu(sp, phi[s], delsq[s]);
-  const double ux0 = u[0*ns + s], uy0 = u[1*ns + s], uz0 = u[2*ns + s];
-
-  double mk = 1.0, mkxm = 1.0, mkxp = 1.0, mkyp = 1.0, mkym = 1.0, mkzp = 1.0, mkzm = 1.0;
-  if (HAS_MAP) {
-    mk   = (status[s] == 0);
-    mkxm = (status[s - xs] == 0); mkxp = (status[s + xs] == 0);
-    mkym = (status[s - ys] == 0); mkyp = (status[s + ys] == 0);
-    mkzm = (status[s - 1] == 0);  mkzp = (status[s + 1] == 0);
-  }
-
-  // west (computed at s): u1 = u_x(s - x)
-  double fw = adv_west<ORDER>(phi, s, xs, ux0, u[0*ns + s - xs]);
-  fw -= M*(mu0 - symm_mu(sp, phi[s - xs], delsq[s - xs]));
-  fw -= M*sp.gm[0];
-  if (HAS_MAP) fw *= mk*mkxm;
-  // east
-  double fe = adv_hi<ORDER>(phi, s, xs, ux0, u[0*ns + s + xs]);
-  fe -= M*(symm_mu(sp, phi[s + xs], delsq[s + xs]) - mu0);
-  fe -= M*sp.gm[0];
-  if (HAS_MAP) fe *= mk*mkxp;
-  // y: face (s, s+y) computed at s
-  double fy = adv_hi<ORDER>(phi, s, ys, uy0, u[1*ns + s + ys]);
-  fy -= M*(symm_mu(sp, phi[s + ys], delsq[s + ys]) - mu0);
-  fy -= M*sp.gm[1];
-  if (HAS_MAP) fy *= mk*mkyp;
-  // y: face (s-y, s) computed at s - y
-  double fym = adv_hi<ORDER>(phi, s - ys, ys, u[1*ns + s - ys], uy0);
-  fym -= M*(mu0 - symm_mu(sp, phi[s - ys], delsq[s - ys]));
-  fym -= M*sp.gm[1];
-  if (HAS_MAP) fym *= mkym*mk;
-  // z
-  double fz = adv_hi<ORDER>(phi, s, 1, uz0, u[2*ns + s + 1]);
-  fz -= M*(symm_mu(sp, phi[s + 1], delsq[s + 1]) - mu0);
-  fz -= M*sp.gm[2];
-  if (HAS_MAP) fz *= mk*mkzp;
-  double fzm = adv_hi<ORDER>(phi, s - 1, 1, u[2*ns + s - 1], uz0);
-  fzm -= M*(mu0 - symm_mu(sp, phi[s - 1], delsq[s - 1]));
-  fzm -= M*sp.gm[2];
-  if (HAS_MAP) fzm *= mkzm*mk;
-
-  double ph = phi[s];
-  ph -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
-  return ph;
-}
-
-template <bool DO_FORCE, bool DO_CH, bool ACCUM, int ORDER, bool HAS_MAP>
-__global__ void __launch_bounds__(TPB)
+// One thread per interior site.  Every operand of the site (13-point phi star, 7-point delsq / grad
+// stars, 9 face velocities) is loaded up front into registers -- about 50 independent loads in flight
+// per thread -- and everything after that is arithmetic: the first version of this kernel chased the
+// upwind site with a dependent load and sat at 32 % DRAM throughput (profiles/r01_*baseline.md).
+template <bool DO_FORCE, bool DO_CH, bool ACCUM, int ORDER, bool HAS_MAP, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
 force_ch_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __restrict__ phi,
 		const double * __restrict__ grad, const double * __restrict__ delsq,
 		const double * __restrict__ u, const char * __restrict__ status,
@@ -643,17 +617,47 @@ force_ch_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __restr
 
   const int s = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
   const size_t ns = (size_t) g.nsites;
+  const int xs = g.xs, ys = g.ys;
+
+  // ---- loads ----
+  const double ph_c = phi[s];
+  const double ph_xm = phi[s - xs], ph_xp = phi[s + xs];
+  const double ph_ym = phi[s - ys], ph_yp = phi[s + ys];
+  const double ph_zm = phi[s - 1],  ph_zp = phi[s + 1];
+  const double d_c = delsq[s];
+  const double d_xm = delsq[s - xs], d_xp = delsq[s + xs];
+  const double d_ym = delsq[s - ys], d_yp = delsq[s + ys];
+  const double d_zm = delsq[s - 1],  d_zp = delsq[s + 1];
+
+  double ph_xm2 = 0.0, ph_xp2 = 0.0, ph_ym2 = 0.0, ph_yp2 = 0.0, ph_zm2 = 0.0, ph_zp2 = 0.0;
+  double ux_c = 0.0, ux_xm = 0.0, ux_xp = 0.0, uy_c = 0.0, uy_ym = 0.0, uy_yp = 0.0;
+  double uz_c = 0.0, uz_zm = 0.0, uz_zp = 0.0;
+  if (DO_CH) {
+    if (ORDER == 3) {
+      ph_xm2 = phi[s - 2*xs]; ph_xp2 = phi[s + 2*xs];
+      ph_ym2 = phi[s - 2*ys]; ph_yp2 = phi[s + 2*ys];
+      ph_zm2 = phi[s - 2];    ph_zp2 = phi[s + 2];
+    }
+    ux_c = u[0*ns + s]; ux_xm = u[0*ns + s - xs]; ux_xp = u[0*ns + s + xs];
+    uy_c = u[1*ns + s]; uy_ym = u[1*ns + s - ys]; uy_yp = u[1*ns + s + ys];
+    uz_c = u[2*ns + s]; uz_zm = u[2*ns + s - 1];  uz_zp = u[2*ns + s + 1];
+  }
 
   if (DO_FORCE) {
+    SiteFE s0, xp, xm, yp, ym, zp, zm;
+#define LB200_FE(S, PH, D, IDX) \
+    S.phi = PH; S.delsq = D; S.gx = grad[0*ns + (IDX)]; S.gy = grad[1*ns + (IDX)]; S.gz = grad[2*ns + (IDX)]
+    LB200_FE(s0, ph_c, d_c, s);
+    LB200_FE(xp, ph_xp, d_xp, s + xs);
+    LB200_FE(xm, ph_xm, d_xm, s - xs);
+    LB200_FE(yp, ph_yp, d_yp, s + ys);
+    LB200_FE(ym, ph_ym, d_ym, s - ys);
+    LB200_FE(zp, ph_zp, d_zp, s + 1);
+    LB200_FE(zm, ph_zm, d_zm, s - 1);
+#undef LB200_FE
     double fo[3];
-    const SiteFE s0 = load_fe(phi, grad, delsq, ns, s);
-    const SiteFE xp = load_fe(phi, grad, delsq, ns, s + g.xs);
-    const SiteFE xm = load_fe(phi, grad, delsq, ns, s - g.xs);
-    const SiteFE yp = load_fe(phi, grad, delsq, ns, s + g.ys);
-    const SiteFE ym = load_fe(phi, grad, delsq, ns, s - g.ys);
-    const SiteFE zp = load_fe(phi, grad, delsq, ns, s + 1);
-    const SiteFE zm = load_fe(phi, grad, delsq, ns, s - 1);
     site_force(sp, s0, xp, xm, yp, ym, zp, zm, fo);
+#pragma unroll
     for (int a = 0; a < 3; a++) {
       if (ACCUM) force[a*ns + s] += fo[a];
       else       force[a*ns + s] = fo[a];
@@ -661,7 +665,50 @@ force_ch_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __restr
   }
 
   if (DO_CH) {
-    phinew[s] = site_phi_update<ORDER, HAS_MAP>(g, sp, phi, delsq, u, status, s);
+    const double M = sp.mobility;
+    const double mu0 = symm_mu(sp, ph_c, d_c);
+
+    double mk = 1.0, mkxm = 1.0, mkxp = 1.0, mkyp = 1.0, mkym = 1.0, mkzp = 1.0, mkzm = 1.0;
+    if (HAS_MAP) {
+      mk   = (status[s] == 0);
+      mkxm = (status[s - xs] == 0); mkxp = (status[s + xs] == 0);
+      mkym = (status[s - ys] == 0); mkyp = (status[s + ys] == 0);
+      mkzm = (status[s - 1] == 0);  mkzp = (status[s + 1] == 0);
+    }
+
+    // west face (s-x, s), owned by s
+    double fw = adv_face<ORDER, true>(ux_xm, ux_c, ph_xm2, ph_xm, ph_c, ph_xp);
+    fw -= M*(mu0 - symm_mu(sp, ph_xm, d_xm));
+    fw -= M*sp.gm[0];
+    if (HAS_MAP) fw *= mk*mkxm;
+    // east face (s, s+x)
+    double fe = adv_face<ORDER, false>(ux_c, ux_xp, ph_xm, ph_c, ph_xp, ph_xp2);
+    fe -= M*(symm_mu(sp, ph_xp, d_xp) - mu0);
+    fe -= M*sp.gm[0];
+    if (HAS_MAP) fe *= mk*mkxp;
+    // y face (s, s+y), owned by s
+    double fy = adv_face<ORDER, false>(uy_c, uy_yp, ph_ym, ph_c, ph_yp, ph_yp2);
+    fy -= M*(symm_mu(sp, ph_yp, d_yp) - mu0);
+    fy -= M*sp.gm[1];
+    if (HAS_MAP) fy *= mk*mkyp;
+    // y face (s-y, s), owned by s-y
+    double fym = adv_face<ORDER, false>(uy_ym, uy_c, ph_ym2, ph_ym, ph_c, ph_yp);
+    fym -= M*(mu0 - symm_mu(sp, ph_ym, d_ym));
+    fym -= M*sp.gm[1];
+    if (HAS_MAP) fym *= mkym*mk;
+    // z faces
+    double fz = adv_face<ORDER, false>(uz_c, uz_zp, ph_zm, ph_c, ph_zp, ph_zp2);
+    fz -= M*(symm_mu(sp, ph_zp, d_zp) - mu0);
+    fz -= M*sp.gm[2];
+    if (HAS_MAP) fz *= mk*mkzp;
+    double fzm = adv_face<ORDER, false>(uz_zm, uz_c, ph_zm2, ph_zm, ph_c, ph_zp);
+    fzm -= M*(mu0 - symm_mu(sp, ph_zm, d_zm));
+    fzm -= M*sp.gm[2];
+    if (HAS_MAP) fzm *= mkzm*mk;
+
+    double ph = ph_c;
+    ph -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
+    phinew[s] = ph;
   }
 }
 
@@ -670,9 +717,14 @@ int launch_force_ch_t(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
 		      const double * phi, const double * grad, const double * delsq,
 		      const double * u, const char * status, double * force, double * phinew) {
   dim3 blk;
-  block_shape(g.nl[2], blk);
+  block_shape_n(g.nl[2], TPB, blk);
   dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
-#define LB200_GO(A, O, M) force_ch_kernel<DO_FORCE, DO_CH, A, O, M><<<grd, blk, 0, st>>>(g, sp, phi, grad, delsq, u, status, force, phinew)
+  static const int minb = tuned_flag("LB200_FCH_MINB", 4);
+#define LB200_GO(A, O, M) do { \
+    if (minb == 6)      force_ch_kernel<DO_FORCE, DO_CH, A, O, M, 6><<<grd, blk, 0, st>>>(g, sp, phi, grad, delsq, u, status, force, phinew); \
+    else if (minb == 5) force_ch_kernel<DO_FORCE, DO_CH, A, O, M, 5><<<grd, blk, 0, st>>>(g, sp, phi, grad, delsq, u, status, force, phinew); \
+    else if (minb == 3) force_ch_kernel<DO_FORCE, DO_CH, A, O, M, 3><<<grd, blk, 0, st>>>(g, sp, phi, grad, delsq, u, status, force, phinew); \
+    else                force_ch_kernel<DO_FORCE, DO_CH, A, O, M, 4><<<grd, blk, 0, st>>>(g, sp, phi, grad, delsq, u, status, force, phinew); } while (0)
 #define LB200_SEL_M(A, O) do { if (status) LB200_GO(A, O, true); else LB200_GO(A, O, false); } while (0)
 #define LB200_SEL_O(A) do { if (sp.order == 1) LB200_SEL_M(A, 1); else if (sp.order == 2) LB200_SEL_M(A, 2); else LB200_SEL_M(A, 3); } while (0)
   if (accumulate) LB200_SEL_O(true); else LB200_SEL_O(false);
@@ -706,7 +758,7 @@ int launch_force_ch(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & s
 // zero everything outside the interior (materialises "logically zero" halos of force / u)
 // ---------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB_MAX)
 zero_outside_kernel(const Lb200Geom g, int ncomp, double * __restrict__ data) {
   const int k0 = blockIdx.x*blockDim.x + threadIdx.x;
   const int j0 = blockIdx.y*blockDim.y + threadIdx.y;

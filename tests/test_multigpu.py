@@ -9,9 +9,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def ngpus():
+    # ask the driver, not torch: importing torch after libludwig_b200 has bound the system libnccl can fail
     try:
-        import torch
-        return torch.cuda.device_count()
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout
+        return sum(1 for line in out.splitlines() if line.startswith("GPU "))
     except Exception:
         return 0
 
