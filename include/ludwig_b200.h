@@ -164,6 +164,24 @@ enum lb200_kernel_class {
 int lb200_profile(lb200_t * ctx, int on);      /* clears accumulated timings */
 int lb200_profile_get(lb200_t * ctx, int kernel_class, double * total_ms, int * count);
 
+/* The x-slab exchange plan of one halo swap (pure host arithmetic, usable without a device): which
+ * ranks are the neighbours, which contiguous element ranges of each component leave this slab, and how
+ * the received planes are laid out in the staging areas the halo-shell kernel reads.  All offsets and
+ * counts are in doubles.  Replaces the send/recv region set-up of lb_halo_create / field_halo_create
+ * (src/lb_data.c:1183-1210, src/field.c:1329-1355) for the x direction. */
+typedef struct lb200_slab_plan_s {
+  int left, right;          /* neighbour ranks (periodic wrap) */
+  int has_lo, has_hi;       /* 0 at a non-periodic global boundary: nothing is exchanged there */
+  long long nsites;         /* component stride in the lattice array */
+  long long chunk;          /* depth * nall[Y] * nall[Z]: one component's boundary planes, contiguous */
+  long long off_lo;         /* first element of my planes i in [1, depth]        (sent to `left`) */
+  long long off_hi;         /* first element of my planes i in [N-depth+1, N]    (sent to `right`) */
+  long long halo_lo;        /* first element of my halo planes i in [1-depth, 0]     (filled from xlo) */
+  long long halo_hi;        /* first element of my halo planes i in [N+1, N+depth]   (filled from xhi) */
+  long long count;          /* ncomp * chunk: message size; staging layout is [comp][depth][y][z] */
+} lb200_slab_plan_t;
+int lb200_slab_plan(const lb200_options_t * options, int ncomp, int depth, lb200_slab_plan_t * plan);
+
 /* multi-GPU: attach an NCCL communicator (ncclComm_t, one rank per slab, rank == cart_rank) used
  * for the x-direction halo planes; replaces MPI_Isend/Irecv of lb_halo_post/field_halo_post
  * (src/lb_data.c:1317-1420, src/field.c:1412-1531). */

@@ -1,0 +1,313 @@
+/*
+ * ludwig_host.h -- C host layer with Ludwig's own object and function names for the hot path,
+ * implemented on top of the C-ABI in ludwig_b200.h (ludwig_b200/host/ludwig_host.c, linked into
+ * libludwig_b200.so).
+ *
+ * It mirrors the slice of the reference's host interface (ludwig-cf/ludwig v0.23.0) that the
+ * per-timestep path and its unit tests use: same function names, same argument order and meaning,
+ * same return convention (0 on success), same "host array is authoritative only after
+ * *_memcpy(..., tdpMemcpyDeviceToHost)" contract, same fatal-on-device-error behaviour
+ * (pe_fatal prints and aborts, reference src/pe.c:226-240).  Each declaration cites the reference
+ * declaration it mirrors (paths relative to the reference root).  Host arrays use the reference's
+ * -DADDR_SOA addressing (src/memory.h:182-195): lb->f[LB_ADDR(nsite, ndist, nvel, index, n, p)].
+ *
+ * Not mirrored (outside SURVEY.md section 8): run-time input parsing, I/O, statistics, colloids,
+ * walls, noise, Lees-Edwards planes (lees_edw_t exists with zero planes only), viscosity models.
+ */
+#ifndef LUDWIG_HOST_H
+#define LUDWIG_HOST_H
+
+#include "ludwig_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {X = 0, Y = 1, Z = 2};
+
+/* mpi_s/mpi.h: single process */
+typedef int MPI_Comm;
+#define MPI_COMM_WORLD 0
+
+/* target/target.h */
+typedef enum tdpMemcpyKind_enum {
+  tdpMemcpyHostToHost = 0, tdpMemcpyHostToDevice = 1, tdpMemcpyDeviceToHost = 2
+} tdpMemcpyKind;
+
+/* ---- pe: src/pe.h:20-43 ---------------------------------------------------------------- */
+typedef struct pe_s pe_t;
+typedef enum {PE_QUIET = 0, PE_VERBOSE, PE_OPTION_MAX} pe_enum_t;
+int pe_create(MPI_Comm parent, pe_enum_t flag, pe_t ** ppe);
+int pe_free(pe_t * pe);
+int pe_info(pe_t * pe, const char * fmt, ...);
+int pe_fatal(pe_t * pe, const char * fmt, ...);
+int pe_mpi_rank(pe_t * pe);
+int pe_mpi_size(pe_t * pe);
+
+/* ---- cs: src/coords.h:73-109 -------------------------------------------------------------- */
+typedef struct cs_s cs_t;
+int cs_create(pe_t * pe, cs_t ** pcs);
+int cs_free(cs_t * cs);
+int cs_init(cs_t * cs);
+int cs_ntotal_set(cs_t * cs, const int ntotal[3]);
+int cs_nhalo_set(cs_t * cs, int nhalo);
+int cs_periodicity_set(cs_t * cs, const int iper[3]);
+int cs_ntotal(cs_t * cs, int ntotal[3]);
+int cs_nlocal(cs_t * cs, int n[3]);
+int cs_nlocal_offset(cs_t * cs, int n[3]);
+int cs_nhalo(cs_t * cs, int * nhalo);
+int cs_nsites(cs_t * cs, int * nsites);
+int cs_nall(cs_t * cs, int nall[3]);
+int cs_periodic(cs_t * cs, int period[3]);
+int cs_index(cs_t * cs, int ic, int jc, int kc);
+int cs_strides(cs_t * cs, int * xs, int * ys, int * zs);
+int cs_cartsz(cs_t * cs, int cartsz[3]);
+int cs_cart_coords(cs_t * cs, int coords[3]);
+
+/* ---- physics: src/physics.h:20-52 (singleton, as in the reference) ------------------------- */
+typedef struct physics_s physics_t;
+int physics_create(pe_t * pe, physics_t ** phys);
+int physics_free(physics_t * phys);
+int physics_ref(physics_t ** phys);
+int physics_rho0_set(physics_t * phys, double rho0);
+int physics_eta_shear_set(physics_t * phys, double eta);
+int physics_eta_bulk_set(physics_t * phys, double zeta);
+int physics_fbody_set(physics_t * phys, double f[3]);
+int physics_mobility_set(physics_t * phys, double mobility);
+int physics_grad_mu_set(physics_t * phys, double gm[3]);
+int physics_rho0(physics_t * phys, double * rho0);
+int physics_eta_shear(physics_t * phys, double * eta);
+int physics_eta_bulk(physics_t * phys, double * eta);
+int physics_fbody(physics_t * phys, double f[3]);
+int physics_mobility(physics_t * phys, double * mobility);
+int physics_grad_mu(physics_t * phys, double gm[3]);
+
+/* ---- Lees-Edwards (zero planes only): src/leesedwards.h:26-29 ------------------------------ */
+typedef struct lees_edw_s lees_edw_t;
+typedef struct lees_edw_options_s {int nplanes; int type; int period; int nt0; double uy;} lees_edw_options_t;
+int lees_edw_create(pe_t * pe, cs_t * cs, const lees_edw_options_t * opts, lees_edw_t ** le);
+int lees_edw_free(lees_edw_t * le);
+int lees_edw_nplane_total(lees_edw_t * le);
+
+/* ---- memory.h addressing, SOA: src/memory.h:182-195 ---------------------------------------- */
+#define addr_rank0(nsites, index) (index)
+#define addr_rank1(nsites, na, index, ia) ((nsites)*(ia) + (index))
+#define addr_rank2(nsites, na, nb, index, ia, ib) ((nb)*(nsites)*(ia) + (nsites)*(ib) + (index))
+#define LB_ADDR(nsites, ndist, nvel, index, n, p) addr_rank2(nsites, ndist, nvel, index, n, p)
+
+/* ---- lb_t: src/lb_data.h:107-284, src/lb_data_options.h:21-47 ------------------------------- */
+typedef enum lb_relaxation_enum {LB_RELAXATION_M10, LB_RELAXATION_BGK, LB_RELAXATION_TRT} lb_relaxation_enum_t;
+typedef enum lb_halo_enum {LB_HALO_FULL = 1, LB_HALO_REDUCED = 2} lb_halo_enum_t;
+typedef enum lb_dist_enum_type {LB_RHO = 0, LB_PHI = 1} lb_dist_enum_t;
+
+typedef struct lb_data_options_s {
+  int ndim;
+  int nvel;
+  int ndist;
+  lb_relaxation_enum_t nrelax;
+  lb_halo_enum_t halo;
+  int reportimbalance;
+  int usefirsttouch;
+} lb_data_options_t;
+
+typedef struct lb_model_s {
+  int ndim;
+  int nvel;
+  signed char (* cv)[3];
+  double * wv;
+  double cs2;
+} lb_model_t;
+
+typedef struct lb_data_s lb_t;
+struct lb_data_s {
+  int ndim;
+  int nvel;
+  int ndist;
+  int nsite;
+  pe_t * pe;
+  cs_t * cs;
+  lb_model_t model;
+  double * f;                    /* host distributions, LB_ADDR addressing */
+  double * fprime;               /* not used on the host here */
+  lb_relaxation_enum_t nrelax;
+  lb_halo_enum_t haloscheme;
+  lb_data_options_t opts;
+  lb_t * target;
+};
+
+lb_data_options_t lb_data_options_default(void);
+lb_data_options_t lb_data_options_ndim_nvel_ndist(int ndim, int nvel, int ndist);
+int lb_data_create(pe_t * pe, cs_t * cs, const lb_data_options_t * opts, lb_t ** lb);
+int lb_free(lb_t * lb);
+int lb_memcpy(lb_t * lb, tdpMemcpyKind flag);
+int lb_halo(lb_t * lb);
+int lb_init_rest_f(lb_t * lb, double rho0);
+int lb_f(lb_t * lb, int index, int p, int n, double * f);
+int lb_f_set(lb_t * lb, int index, int p, int n, double f);
+int lb_0th_moment(lb_t * lb, int index, lb_dist_enum_t nd, double * rho);
+int lb_1st_moment(lb_t * lb, int index, lb_dist_enum_t nd, double g[3]);
+int lb_1st_moment_equilib_set(lb_t * lb, int index, double rho, double u[3]);
+int lb_collision_relaxation_set(lb_t * lb, lb_relaxation_enum_t nrelax);     /* src/collision.h:30 */
+
+/* ---- field_t: src/field.h:68-130, src/field_options.h ---------------------------------------- */
+typedef struct field_options_s {int ndata; int nhcomm; int haloscheme; int haloverbose; int usefirsttouch;} field_options_t;
+field_options_t field_options_default(void);
+field_options_t field_options_ndata_nhalo(int ndata, int nhalo);
+
+typedef struct field_s field_t;
+struct field_s {
+  int nf;
+  int nhcomm;
+  int nsites;
+  double * data;                 /* host data, addr_rank1(nsites, nf, index, n) */
+  char * name;
+  pe_t * pe;
+  cs_t * cs;
+  lees_edw_t * le;
+  field_options_t opts;
+  int b200_array;                /* which device array backs this field (LB200_PHI, LB200_U, ...) */
+  field_t * target;
+};
+
+int field_create(pe_t * pe, cs_t * cs, lees_edw_t * le, const char * name, const field_options_t * opts, field_t ** pobj);
+int field_free(field_t * obj);
+int field_memcpy(field_t * obj, tdpMemcpyKind flag);
+int field_halo(field_t * obj);
+int field_nf(field_t * obj, int * nop);
+int field_scalar(field_t * obj, int index, double * phi);
+int field_scalar_set(field_t * obj, int index, double phi);
+int field_vector(field_t * obj, int index, double p[3]);
+int field_vector_set(field_t * obj, int index, const double p[3]);
+
+/* ---- field_grad_t: src/field_grad.h:24-56, src/gradient_3d_27pt_fluid.h:20 ------------------- */
+typedef struct field_grad_s field_grad_t;
+typedef int (* grad_ft)(field_grad_t * fgrad);
+struct field_grad_s {
+  pe_t * pe;
+  field_t * field;
+  int nf;
+  int level;
+  int nsite;
+  double * grad;                 /* addr_rank2(nsite, nf, 3, index, n, ia) */
+  double * delsq;                /* addr_rank1(nsite, nf, index, n) */
+  grad_ft d2;
+  grad_ft d4;
+  field_grad_t * target;
+};
+
+int field_grad_create(pe_t * pe, field_t * f, int level, field_grad_t ** pobj);
+void field_grad_free(field_grad_t * obj);
+int field_grad_set(field_grad_t * obj, grad_ft d2, grad_ft d4);
+int field_grad_compute(field_grad_t * obj);
+int field_grad_memcpy(field_grad_t * obj, tdpMemcpyKind flag);
+int field_grad_scalar_grad(field_grad_t * obj, int index, double grad[3]);
+int field_grad_scalar_delsq(field_grad_t * obj, int index, double * delsq);
+int grad_3d_27pt_fluid_d2(field_grad_t * fg);
+
+/* ---- hydro_t: src/hydro.h:32-62, src/hydro_options.h ------------------------------------------ */
+typedef struct hydro_options_s {int nhcomm; field_options_t rho; field_options_t u; field_options_t force; field_options_t eta;} hydro_options_t;
+hydro_options_t hydro_options_default(void);
+hydro_options_t hydro_options_nhalo(int nhalo);
+
+typedef struct hydro_s hydro_t;
+struct hydro_s {
+  int nsite;
+  int nhcomm;
+  pe_t * pe;
+  cs_t * cs;
+  lees_edw_t * le;
+  field_t * rho;
+  field_t * u;
+  field_t * force;
+  field_t * eta;
+  hydro_t * target;
+};
+
+int hydro_create(pe_t * pe, cs_t * cs, lees_edw_t * le, const hydro_options_t * opts, hydro_t ** pobj);
+int hydro_free(hydro_t * obj);
+int hydro_memcpy(hydro_t * obj, tdpMemcpyKind flag);
+int hydro_u_halo(hydro_t * obj);
+int hydro_f_zero(hydro_t * obj, const double fzero[3]);
+int hydro_u_zero(hydro_t * obj, const double uzero[3]);
+int hydro_u(hydro_t * obj, int index, double u[3]);           /* src/hydro_impl.h */
+int hydro_u_set(hydro_t * obj, int index, const double u[3]);
+int hydro_f_local(hydro_t * obj, int index, double force[3]);
+int hydro_f_local_set(hydro_t * obj, int index, const double force[3]);
+int hydro_rho(hydro_t * obj, int index, double * rho);
+
+/* ---- map_t: src/map.h:26-63 ------------------------------------------------------------------ */
+enum map_status {MAP_FLUID = 0, MAP_BOUNDARY, MAP_COLLOID, MAP_STATUS_MAX};
+typedef struct map_options_s {int ndata; int is_porous_media;} map_options_t;
+map_options_t map_options_default(void);
+typedef struct map_s map_t;
+struct map_s {
+  int nsite;
+  pe_t * pe;
+  cs_t * cs;
+  char * status;
+  map_t * target;
+};
+int map_create(pe_t * pe, cs_t * cs, const map_options_t * options, map_t ** map);
+int map_free(map_t ** map);
+int map_memcpy(map_t * map, tdpMemcpyKind flag);
+int map_status(map_t * map, int index, int * status);
+int map_status_set(map_t * map, int index, int status);
+
+/* ---- free energy (symmetric): src/free_energy.h:36-80, src/symmetric.h:28-66 ------------------- */
+typedef struct fe_s fe_t;
+struct fe_s {int id; int use_stress_relaxation;};
+typedef struct fe_symm_param_s {double a; double b; double kappa; double c; double h;} fe_symm_param_t;
+typedef struct fe_symm_s fe_symm_t;
+struct fe_symm_s {
+  fe_t super;
+  pe_t * pe;
+  cs_t * cs;
+  fe_symm_param_t * param;
+  field_t * phi;
+  field_grad_t * dphi;
+  fe_symm_t * target;
+};
+int fe_symm_create(pe_t * pe, cs_t * cs, field_t * f, field_grad_t * grd, fe_symm_t ** p);
+int fe_symm_free(fe_symm_t * fe);
+int fe_symm_param_set(fe_symm_t * fe, fe_symm_param_t values);
+int fe_symm_param(fe_symm_t * fe, fe_symm_param_t * values);
+int fe_symm_fed(fe_symm_t * fe, int index, double * fed);     /* host arrays */
+int fe_symm_mu(fe_symm_t * fe, int index, double * mu);
+
+/* ---- force from the phi sector: src/phi_force_stress.h:26-39, src/phi_force.h:24, fe_force_method.h */
+typedef enum {
+  FE_FORCE_METHOD_INVALID, FE_FORCE_METHOD_NO_FORCE, FE_FORCE_METHOD_STRESS_DIVERGENCE, FE_FORCE_METHOD_PHI_GRADMU,
+  FE_FORCE_METHOD_PHI_GRADMU_CORRECTION, FE_FORCE_METHOD_RELAXATION_SYMM, FE_FORCE_METHOD_RELAXATION_ANTI,
+  FE_FORCE_METHOD_MAX
+} fe_force_method_enum_t;
+typedef struct pth_s pth_t;
+struct pth_s {pe_t * pe; cs_t * cs; int method; int nsites; pth_t * target;};
+typedef struct wall_s wall_t;          /* never dereferenced here: pass NULL (no walls in scope) */
+int pth_create(pe_t * pe, cs_t * cs, int method, pth_t ** pth);
+int pth_free(pth_t * pth);
+int phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t * wall, pth_t * pth, fe_t * fe,
+			  map_t * map, field_t * phi, hydro_t * hydro);
+
+/* ---- Cahn-Hilliard: src/phi_cahn_hilliard.h:38-56, src/advection.h:40-41 ---------------------- */
+typedef struct phi_ch_info_s {int conserve; int noise;} phi_ch_info_t;
+typedef struct phi_ch_s phi_ch_t;
+struct phi_ch_s {pe_t * pe; cs_t * cs; lees_edw_t * le; phi_ch_info_t info;};
+typedef struct noise_s noise_t;        /* pass NULL */
+typedef struct visc_s visc_t;          /* pass NULL */
+int phi_ch_create(pe_t * pe, cs_t * cs, lees_edw_t * le, phi_ch_info_t * info, phi_ch_t ** pch);
+int phi_ch_free(phi_ch_t * pch);
+int phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t * hydro, map_t * map, noise_t * noise);
+int advection_order_set(const int order);
+int advection_order(int * order);
+
+/* ---- collision and propagation: src/collision.h:27-28, src/propagation.h:21 ------------------- */
+int lb_collide(lb_t * lb, hydro_t * hydro, map_t * map, noise_t * noise, fe_t * fe, visc_t * visc);
+int lb_propagation(lb_t * lb);
+
+/* the device context behind a coordinate system (created on first device use) */
+lb200_t * cs_b200_context(cs_t * cs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

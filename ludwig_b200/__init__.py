@@ -5,10 +5,10 @@ ludwig_b200/csrc (CUDA) and ludwig_b200/host (C host layer with the reference's 
 This Python package is only a ctypes binding used by the tests and the benchmark; there is no
 CPU fallback: importing works anywhere, creating a context without a CUDA device raises.
 """
-from .capi import (Lb200, Lb200Error, CollideParam, SymmParam, Options, load_library, library_path,
+from .capi import (Lb200, Lb200Error, slab_plan, SlabPlan, CollideParam, SymmParam, Options, load_library, library_path,
                    F, PHI, U, RHO, FORCE, GRAD, DELSQ, MAP,
                    RELAX_M10, RELAX_BGK, RELAX_TRT, HALO_FULL, HALO_REDUCED, MATH_FAST, MATH_STRICT)
 
-__all__ = ["Lb200", "Lb200Error", "CollideParam", "SymmParam", "Options", "load_library", "library_path",
+__all__ = ["Lb200", "Lb200Error", "slab_plan", "SlabPlan", "CollideParam", "SymmParam", "Options", "load_library", "library_path",
            "F", "PHI", "U", "RHO", "FORCE", "GRAD", "DELSQ", "MAP",
            "RELAX_M10", "RELAX_BGK", "RELAX_TRT", "HALO_FULL", "HALO_REDUCED", "MATH_FAST", "MATH_STRICT"]

@@ -48,6 +48,29 @@ class SymmParam(C.Structure):
         return sp
 
 
+class SlabPlan(C.Structure):
+    _fields_ = [("left", C.c_int), ("right", C.c_int), ("has_lo", C.c_int), ("has_hi", C.c_int),
+                ("nsites", C.c_longlong), ("chunk", C.c_longlong), ("off_lo", C.c_longlong),
+                ("off_hi", C.c_longlong), ("halo_lo", C.c_longlong), ("halo_hi", C.c_longlong),
+                ("count", C.c_longlong)]
+
+
+def slab_plan(nlocal, nhalo, periodic, cart_size, cart_rank, ncomp, depth):
+    """lb200_slab_plan: the x-slab exchange plan (pure host arithmetic; works without a GPU)."""
+    lib = load_library()
+    o = Options()
+    o.nlocal[:] = nlocal
+    o.nhalo = nhalo
+    o.periodic[:] = periodic
+    o.nvel, o.ndist, o.halo_scheme = 19, 1, HALO_FULL
+    o.cart_size, o.cart_rank = cart_size, cart_rank
+    p = SlabPlan()
+    rc = lib.lb200_slab_plan(C.byref(o), ncomp, depth, C.byref(p))
+    if rc != 0:
+        raise Lb200Error(lib.lb200_last_error().decode())
+    return p
+
+
 def library_path():
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libludwig_b200.so")
 
@@ -85,6 +108,7 @@ def load_library():
     lib.lb200_stream.restype = C.c_void_p
     lib.lb200_profile.argtypes = [C.c_void_p, C.c_int]
     lib.lb200_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    lib.lb200_slab_plan.argtypes = [C.POINTER(Options), C.c_int, C.c_int, C.POINTER(SlabPlan)]
     lib.lb200_attach_nccl.argtypes = [C.c_void_p, C.c_void_p]
     lib.lb200_nccl_unique_id.argtypes = [C.c_void_p]
     lib.lb200_nccl_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]

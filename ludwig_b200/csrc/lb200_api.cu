@@ -539,6 +539,26 @@ static double * stage_ptr(lb200_t * c, double * base, const double * data) {
 static double * stage_lo(lb200_t * c, const double * data) { return stage_ptr(c, c->xlo, data); }
 static double * stage_hi(lb200_t * c, const double * data) { return stage_ptr(c, c->xhi, data); }
 
+int lb200_slab_plan(const lb200_options_t * o, int ncomp, int depth, lb200_slab_plan_t * p) {
+  if (o == nullptr || p == nullptr) return fail(LB200_EINVAL, "null argument");
+  if (depth < 1 || depth > o->nhalo || ncomp < 1) return fail(LB200_EINVAL, "bad depth/ncomp");
+  if (o->cart_size < 1 || o->cart_rank < 0 || o->cart_rank >= o->cart_size) return fail(LB200_EINVAL, "bad cart_size/cart_rank");
+  const long long nay = o->nlocal[1] + 2*o->nhalo, naz = o->nlocal[2] + 2*o->nhalo, nax = o->nlocal[0] + 2*o->nhalo;
+  const long long xs = nay*naz;
+  p->left = (o->cart_rank - 1 + o->cart_size) % o->cart_size;
+  p->right = (o->cart_rank + 1) % o->cart_size;
+  p->has_lo = (o->periodic[0] != 0) || o->cart_rank > 0;
+  p->has_hi = (o->periodic[0] != 0) || o->cart_rank < o->cart_size - 1;
+  p->nsites = nax*xs;
+  p->chunk = depth*xs;
+  p->off_lo = (long long) (1 + o->nhalo - 1)*xs;
+  p->off_hi = (long long) (o->nlocal[0] - depth + 1 + o->nhalo - 1)*xs;
+  p->halo_lo = (long long) (1 - depth + o->nhalo - 1)*xs;
+  p->halo_hi = (long long) (o->nlocal[0] + 1 + o->nhalo - 1)*xs;
+  p->count = ncomp*p->chunk;
+  return 0;
+}
+
 // ---- x-plane exchange between slabs (NCCL send/recv over NVLink) --------------------------------
 // Replaces MPI_Isend/Irecv/Waitall of lb_halo_post / field_halo_post.  For each component the
 // `depth` boundary planes at either end of the slab are contiguous in the SOA layout, so no pack
@@ -552,14 +572,15 @@ static int exchange_x(lb200_t * c, cudaStream_t st, const double * data, int nco
   if (c->nccl == nullptr) return fail(LB200_ECOMM, "cart_size > 1 but no NCCL communicator attached (lb200_attach_nccl)");
   ncclComm_t comm = (ncclComm_t) c->nccl;
   const Lb200Geom & g = c->g;
-  const int size = c->opt.cart_size, rank = c->opt.cart_rank;
-  const int left = (rank - 1 + size) % size;
-  const int right = (rank + 1) % size;
-  const size_t chunk = (size_t) depth*g.xs;
-  const size_t ns = (size_t) g.nsites;
+  lb200_slab_plan_t plan;
+  int prc = lb200_slab_plan(&c->opt, ncomp, depth, &plan);
+  if (prc != 0) return prc;
+  const int left = plan.left, right = plan.right;
+  const size_t chunk = (size_t) plan.chunk;
+  const size_t ns = (size_t) plan.nsites;
   // my top planes i in [N-d+1, N] go right (-> neighbour's xlo); my bottom planes i in [1, d] go left
-  const size_t off_hi = (size_t) (g.nl[0] - depth + 1 + g.nh - 1)*g.xs;
-  const size_t off_lo = (size_t) (1 + g.nh - 1)*g.xs;
+  const size_t off_hi = (size_t) plan.off_hi;
+  const size_t off_lo = (size_t) plan.off_lo;
   double * xlo = stage_lo(c, data);
   double * xhi = stage_hi(c, data);
 

@@ -1,0 +1,714 @@
+/*
+ * ludwig_host.c -- Ludwig's host-side names for the hot path on top of the lb200 C-ABI
+ * (declarations and reference citations: include/ludwig_host.h).
+ *
+ * One device context (lb200_t) per coordinate system, created at the first device operation from
+ * the objects registered with that cs_t by their constructors (lb_t, hydro_t, the order-parameter
+ * field_t, its field_grad_t, map_t) -- the reference likewise builds every object before the first
+ * *_memcpy(HostToDevice) (src/ludwig.c:202-429, 501-506).
+ */
+
+#include <assert.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ludwig_host.h"
+
+/* ---- pe ------------------------------------------------------------------------------------ */
+
+struct pe_s {int quiet; int nref;};
+
+int pe_create(MPI_Comm parent, pe_enum_t flag, pe_t ** ppe) {
+  pe_t * pe = (pe_t *) calloc(1, sizeof(pe_t));
+  (void) parent;
+  assert(ppe);
+  if (pe == NULL) return -1;
+  pe->quiet = (flag == PE_QUIET);
+  pe->nref = 1;
+  *ppe = pe;
+  return 0;
+}
+
+int pe_free(pe_t * pe) { free(pe); return 0; }
+int pe_mpi_rank(pe_t * pe) { (void) pe; return 0; }
+int pe_mpi_size(pe_t * pe) { (void) pe; return 1; }
+
+int pe_info(pe_t * pe, const char * fmt, ...) {
+  va_list args;
+  if (pe && pe->quiet) return 0;
+  va_start(args, fmt);
+  vprintf(fmt, args);
+  va_end(args);
+  return 0;
+}
+
+/* reference: print, then MPI_Abort (src/pe.c:226-240) */
+int pe_fatal(pe_t * pe, const char * fmt, ...) {
+  va_list args;
+  (void) pe;
+  printf("[0] ");
+  va_start(args, fmt);
+  vprintf(fmt, args);
+  va_end(args);
+  printf("[0] aborting\n");
+  fflush(stdout);
+  exit(1);
+  return 0;
+}
+
+/* ---- cs -------------------------------------------------------------------------------------- */
+
+struct cs_s {
+  pe_t * pe;
+  int ntotal[3];
+  int nlocal[3];
+  int noffset[3];
+  int nhalo;
+  int periodic[3];
+  int nall[3];
+  int nsites;
+  int initialised;
+  /* objects living on this coordinate system, and the device lattice behind them */
+  lb_t * lb;
+  hydro_t * hydro;
+  field_t * phi;
+  field_grad_t * phi_grad;
+  map_t * map;
+  lb200_t * ctx;
+};
+
+int cs_create(pe_t * pe, cs_t ** pcs) {
+  cs_t * cs = (cs_t *) calloc(1, sizeof(cs_t));
+  assert(pe);
+  assert(pcs);
+  if (cs == NULL) pe_fatal(pe, "calloc(cs_t) failed\n");
+  cs->pe = pe;
+  cs->ntotal[X] = cs->ntotal[Y] = cs->ntotal[Z] = 64;     /* reference defaults, src/coords.c:60-75 */
+  cs->periodic[X] = cs->periodic[Y] = cs->periodic[Z] = 1;
+  cs->nhalo = 1;
+  *pcs = cs;
+  return 0;
+}
+
+int cs_free(cs_t * cs) {
+  if (cs == NULL) return 0;
+  if (cs->ctx) lb200_free(cs->ctx);
+  free(cs);
+  return 0;
+}
+
+int cs_ntotal_set(cs_t * cs, const int ntotal[3]) { for (int a = 0; a < 3; a++) cs->ntotal[a] = ntotal[a]; return 0; }
+int cs_nhalo_set(cs_t * cs, int nhalo) { cs->nhalo = nhalo; return 0; }
+int cs_periodicity_set(cs_t * cs, const int iper[3]) { for (int a = 0; a < 3; a++) cs->periodic[a] = iper[a]; return 0; }
+
+int cs_init(cs_t * cs) {
+  assert(cs);
+  cs->nsites = 1;
+  for (int a = 0; a < 3; a++) {
+    cs->nlocal[a] = cs->ntotal[a];                         /* single process: src/coords.c:211-215 */
+    cs->noffset[a] = 0;
+    cs->nall[a] = cs->nlocal[a] + 2*cs->nhalo;
+    cs->nsites *= cs->nall[a];
+  }
+  cs->initialised = 1;
+  return 0;
+}
+
+int cs_ntotal(cs_t * cs, int n[3]) { for (int a = 0; a < 3; a++) n[a] = cs->ntotal[a]; return 0; }
+int cs_nlocal(cs_t * cs, int n[3]) { for (int a = 0; a < 3; a++) n[a] = cs->nlocal[a]; return 0; }
+int cs_nlocal_offset(cs_t * cs, int n[3]) { for (int a = 0; a < 3; a++) n[a] = cs->noffset[a]; return 0; }
+int cs_nall(cs_t * cs, int n[3]) { for (int a = 0; a < 3; a++) n[a] = cs->nall[a]; return 0; }
+int cs_periodic(cs_t * cs, int p[3]) { for (int a = 0; a < 3; a++) p[a] = cs->periodic[a]; return 0; }
+int cs_nhalo(cs_t * cs, int * nhalo) { *nhalo = cs->nhalo; return 0; }
+int cs_nsites(cs_t * cs, int * nsites) { *nsites = cs->nsites; return 0; }
+int cs_cartsz(cs_t * cs, int sz[3]) { (void) cs; sz[X] = sz[Y] = sz[Z] = 1; return 0; }
+int cs_cart_coords(cs_t * cs, int c[3]) { (void) cs; c[X] = c[Y] = c[Z] = 0; return 0; }
+
+/* src/coords.c:617-631 */
+int cs_index(cs_t * cs, int ic, int jc, int kc) {
+  return (ic + cs->nhalo - 1)*cs->nall[Y]*cs->nall[Z] + (jc + cs->nhalo - 1)*cs->nall[Z] + (kc + cs->nhalo - 1);
+}
+
+int cs_strides(cs_t * cs, int * xs, int * ys, int * zs) {
+  *xs = cs->nall[Y]*cs->nall[Z]; *ys = cs->nall[Z]; *zs = 1;
+  return 0;
+}
+
+lb200_t * cs_b200_context(cs_t * cs) {
+  assert(cs);
+  assert(cs->initialised);
+  if (cs->ctx == NULL) {
+    lb200_options_t o;
+    const char * math = getenv("LB200_MATH");
+    memset(&o, 0, sizeof(o));
+    for (int a = 0; a < 3; a++) { o.nlocal[a] = cs->nlocal[a]; o.periodic[a] = cs->periodic[a]; }
+    o.nhalo = cs->nhalo;
+    o.nvel = cs->lb ? cs->lb->nvel : 19;
+    o.ndist = cs->lb ? cs->lb->ndist : 1;
+    o.have_phi = (cs->phi != NULL);
+    o.halo_scheme = cs->lb ? (int) cs->lb->haloscheme : LB200_HALO_FULL;
+    o.math = (math && strcmp(math, "strict") == 0) ? LB200_MATH_STRICT : LB200_MATH_FAST;
+    o.device = -1;
+    o.cart_size = 1;
+    o.cart_rank = 0;
+    if (lb200_create(&o, &cs->ctx) != 0) pe_fatal(cs->pe, "lb200_create: %s\n", lb200_last_error());
+  }
+  return cs->ctx;
+}
+
+static void b200_check(pe_t * pe, int rc, const char * what) {
+  if (rc != 0) pe_fatal(pe, "%s: %s\n", what, lb200_last_error());
+}
+
+static int b200_kind(tdpMemcpyKind flag) {
+  return (flag == tdpMemcpyHostToDevice) ? LB200_HOST_TO_DEVICE : LB200_DEVICE_TO_HOST;
+}
+
+/* ---- physics (singleton) ---------------------------------------------------------------------- */
+
+struct physics_s {
+  double rho0, eta_shear, eta_bulk, fbody[3], mobility, grad_mu[3];
+};
+
+static physics_t * physics_static = NULL;
+
+int physics_create(pe_t * pe, physics_t ** phys) {
+  physics_t * p = (physics_t *) calloc(1, sizeof(physics_t));
+  if (p == NULL) pe_fatal(pe, "calloc(physics_t) failed\n");
+  p->rho0 = 1.0;                         /* reference defaults, src/physics.c:60-80 */
+  p->eta_shear = 1.0/6.0;
+  p->eta_bulk = 1.0/6.0;
+  physics_static = p;
+  *phys = p;
+  return 0;
+}
+
+int physics_free(physics_t * phys) { if (phys == physics_static) physics_static = NULL; free(phys); return 0; }
+int physics_ref(physics_t ** phys) { assert(physics_static); *phys = physics_static; return 0; }
+int physics_rho0_set(physics_t * p, double rho0) { p->rho0 = rho0; return 0; }
+int physics_eta_shear_set(physics_t * p, double eta) { p->eta_shear = eta; return 0; }
+int physics_eta_bulk_set(physics_t * p, double zeta) { p->eta_bulk = zeta; return 0; }
+int physics_fbody_set(physics_t * p, double f[3]) { for (int a = 0; a < 3; a++) p->fbody[a] = f[a]; return 0; }
+int physics_mobility_set(physics_t * p, double m) { p->mobility = m; return 0; }
+int physics_grad_mu_set(physics_t * p, double gm[3]) { for (int a = 0; a < 3; a++) p->grad_mu[a] = gm[a]; return 0; }
+int physics_rho0(physics_t * p, double * rho0) { *rho0 = p->rho0; return 0; }
+int physics_eta_shear(physics_t * p, double * eta) { *eta = p->eta_shear; return 0; }
+int physics_eta_bulk(physics_t * p, double * eta) { *eta = p->eta_bulk; return 0; }
+int physics_fbody(physics_t * p, double f[3]) { for (int a = 0; a < 3; a++) f[a] = p->fbody[a]; return 0; }
+int physics_mobility(physics_t * p, double * m) { *m = p->mobility; return 0; }
+int physics_grad_mu(physics_t * p, double gm[3]) { for (int a = 0; a < 3; a++) gm[a] = p->grad_mu[a]; return 0; }
+
+/* ---- Lees-Edwards: zero planes only ------------------------------------------------------------- */
+
+struct lees_edw_s {pe_t * pe; cs_t * cs; int nplanes;};
+
+int lees_edw_create(pe_t * pe, cs_t * cs, const lees_edw_options_t * opts, lees_edw_t ** ple) {
+  lees_edw_t * le = (lees_edw_t *) calloc(1, sizeof(lees_edw_t));
+  if (le == NULL) pe_fatal(pe, "calloc(lees_edw_t) failed\n");
+  if (opts && opts->nplanes != 0) pe_fatal(pe, "Lees-Edwards planes are outside this build (SURVEY 8f)\n");
+  le->pe = pe; le->cs = cs;
+  *ple = le;
+  return 0;
+}
+int lees_edw_free(lees_edw_t * le) { free(le); return 0; }
+int lees_edw_nplane_total(lees_edw_t * le) { return le ? le->nplanes : 0; }
+
+/* ---- lb_t -------------------------------------------------------------------------------------------- */
+
+static const signed char cv19_[19][3] = {
+  { 0,  0,  0},
+  { 1,  1,  0}, { 1,  0,  1}, { 1,  0,  0}, { 1,  0, -1}, { 1, -1,  0}, { 0,  1,  1},
+  { 0,  1,  0}, { 0,  1, -1}, { 0,  0,  1}, { 0,  0, -1}, { 0, -1,  1}, { 0, -1,  0},
+  { 0, -1, -1}, {-1,  1,  0}, {-1,  0,  1}, {-1,  0,  0}, {-1,  0, -1}, {-1, -1,  0}};
+static const signed char cv15_[15][3] = {
+  { 0,  0,  0},
+  { 1,  1,  1}, { 1,  1, -1}, { 1,  0,  0}, { 1, -1,  1}, { 1, -1, -1}, { 0,  1,  0},
+  { 0,  0,  1}, { 0,  0, -1}, { 0, -1,  0}, {-1,  1,  1}, {-1,  1, -1}, {-1,  0,  0},
+  {-1, -1,  1}, {-1, -1, -1}};
+
+static int lb_model_init(lb_model_t * m, int nvel) {
+  m->ndim = 3;
+  m->nvel = nvel;
+  m->cs2 = (1.0/3.0);
+  m->cv = (signed char (*)[3]) calloc(nvel, sizeof(signed char[3]));
+  m->wv = (double *) calloc(nvel, sizeof(double));
+  if (m->cv == NULL || m->wv == NULL) return -1;
+  if (nvel == 19 || nvel == 15) {
+    for (int p = 0; p < nvel; p++) {
+      int c1 = 0;
+      for (int a = 0; a < 3; a++) { m->cv[p][a] = (nvel == 19) ? cv19_[p][a] : cv15_[p][a]; c1 += abs(m->cv[p][a]); }
+      if (nvel == 19) m->wv[p] = (c1 == 0) ? 12.0/36.0 : (c1 == 1) ? 2.0/36.0 : 1.0/36.0;
+      else            m->wv[p] = (c1 == 0) ? 16.0/72.0 : (c1 == 1) ? 8.0/72.0 : 1.0/72.0;
+    }
+  }
+  else if (nvel == 27) {
+    int p = 1;
+    m->wv[0] = 64.0/216.0;
+    for (int i = -1; i <= 1; i++)
+      for (int j = -1; j <= 1; j++)
+	for (int k = -1; k <= 1; k++) {
+	  int c1 = abs(i) + abs(j) + abs(k);
+	  if (c1 == 0) continue;
+	  m->cv[p][X] = i; m->cv[p][Y] = j; m->cv[p][Z] = k;
+	  m->wv[p] = (c1 == 1) ? 16.0/216.0 : (c1 == 2) ? 4.0/216.0 : 1.0/216.0;
+	  p++;
+	}
+  }
+  else return -1;
+  return 0;
+}
+
+lb_data_options_t lb_data_options_default(void) {
+  lb_data_options_t o = {.ndim = 3, .nvel = 19, .ndist = 1, .nrelax = LB_RELAXATION_M10, .halo = LB_HALO_FULL,
+			 .reportimbalance = 0, .usefirsttouch = 0};
+  return o;
+}
+
+lb_data_options_t lb_data_options_ndim_nvel_ndist(int ndim, int nvel, int ndist) {
+  lb_data_options_t o = lb_data_options_default();
+  o.ndim = ndim; o.nvel = nvel; o.ndist = ndist;
+  return o;
+}
+
+int lb_data_create(pe_t * pe, cs_t * cs, const lb_data_options_t * opts, lb_t ** plb) {
+  lb_t * lb = (lb_t *) calloc(1, sizeof(lb_t));
+  assert(pe); assert(cs); assert(opts); assert(plb);
+  if (lb == NULL) pe_fatal(pe, "calloc(1, lb_t) failed\n");
+  if (opts->ndist != 1) pe_fatal(pe, "ndist = %d: the two-distribution model is outside this build (SURVEY 8f)\n", opts->ndist);
+  lb->pe = pe; lb->cs = cs;
+  lb->ndim = opts->ndim; lb->nvel = opts->nvel; lb->ndist = opts->ndist;
+  lb->nrelax = opts->nrelax; lb->haloscheme = opts->halo; lb->opts = *opts;
+  lb->nsite = cs->nsites;
+  if (lb_model_init(&lb->model, opts->nvel) != 0) pe_fatal(pe, "unsupported nvel %d\n", opts->nvel);
+  /* reference guard: src/lb_data.c:116-120 */
+  if ((long long) lb->nsite*lb->ndist*lb->nvel > 2147483647LL) pe_fatal(pe, "local lattice too large for int indexing\n");
+  lb->f = (double *) calloc((size_t) lb->nsite*lb->ndist*lb->nvel, sizeof(double));
+  if (lb->f == NULL) pe_fatal(pe, "calloc(lb->f) failed\n");
+  lb->target = lb;
+  cs->lb = lb;
+  *plb = lb;
+  return 0;
+}
+
+int lb_free(lb_t * lb) {
+  if (lb == NULL) return 0;
+  if (lb->cs && lb->cs->lb == lb) lb->cs->lb = NULL;
+  free(lb->model.cv); free(lb->model.wv); free(lb->f);
+  free(lb);
+  return 0;
+}
+
+int lb_memcpy(lb_t * lb, tdpMemcpyKind flag) {
+  b200_check(lb->pe, lb200_memcpy(cs_b200_context(lb->cs), LB200_F, lb->f, b200_kind(flag)), "lb_memcpy");
+  return 0;
+}
+
+int lb_halo(lb_t * lb) {
+  b200_check(lb->pe, lb200_lb_halo(cs_b200_context(lb->cs)), "lb_halo");
+  return 0;
+}
+
+int lb_propagation(lb_t * lb) {
+  b200_check(lb->pe, lb200_lb_propagation(cs_b200_context(lb->cs)), "lb_propagation");
+  return 0;
+}
+
+int lb_collision_relaxation_set(lb_t * lb, lb_relaxation_enum_t nrelax) { lb->nrelax = nrelax; return 0; }
+
+int lb_f(lb_t * lb, int index, int p, int n, double * f) {
+  *f = lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, n, p)];
+  return 0;
+}
+
+int lb_f_set(lb_t * lb, int index, int p, int n, double f) {
+  lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, n, p)] = f;
+  return 0;
+}
+
+int lb_0th_moment(lb_t * lb, int index, lb_dist_enum_t nd, double * rho) {
+  *rho = 0.0;
+  for (int p = 0; p < lb->nvel; p++) *rho += lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, nd, p)];
+  return 0;
+}
+
+int lb_1st_moment(lb_t * lb, int index, lb_dist_enum_t nd, double g[3]) {
+  for (int a = 0; a < 3; a++) g[a] = 0.0;
+  for (int p = 0; p < lb->nvel; p++)
+    for (int a = 0; a < 3; a++)
+      g[a] += lb->model.cv[p][a]*lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, nd, p)];
+  return 0;
+}
+
+/* src/lb_data.c:809-834 */
+int lb_1st_moment_equilib_set(lb_t * lb, int index, double rho, double u[3]) {
+  for (int p = 0; p < lb->model.nvel; p++) {
+    double cs2 = lb->model.cs2;
+    double rcs2 = 1.0/cs2;
+    double udotc = 0.0;
+    double sdotq = 0.0;
+    for (int ia = 0; ia < 3; ia++) {
+      udotc += u[ia]*lb->model.cv[p][ia];
+      for (int ib = 0; ib < 3; ib++) {
+	double dab = (ia == ib);
+	sdotq += (lb->model.cv[p][ia]*lb->model.cv[p][ib] - cs2*dab)*u[ia]*u[ib];
+      }
+    }
+    lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, LB_RHO, p)]
+      = rho*lb->model.wv[p]*(1.0 + rcs2*udotc + 0.5*rcs2*rcs2*sdotq);
+  }
+  return 0;
+}
+
+/* src/lb_data.c:659-680 */
+int lb_init_rest_f(lb_t * lb, double rho0) {
+  int nlocal[3];
+  cs_nlocal(lb->cs, nlocal);
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++) {
+	double u0[3] = {0.0, 0.0, 0.0};
+	lb_1st_moment_equilib_set(lb, cs_index(lb->cs, ic, jc, kc), rho0, u0);
+      }
+  return 0;
+}
+
+/* ---- field_t ------------------------------------------------------------------------------------------- */
+
+field_options_t field_options_default(void) { field_options_t o = {.ndata = 1, .nhcomm = 0}; return o; }
+field_options_t field_options_ndata_nhalo(int ndata, int nhalo) { field_options_t o = {.ndata = ndata, .nhcomm = nhalo}; return o; }
+
+static int field_create_tagged(pe_t * pe, cs_t * cs, lees_edw_t * le, const char * name,
+			       const field_options_t * opts, int tag, field_t ** pobj) {
+  field_t * obj = (field_t *) calloc(1, sizeof(field_t));
+  if (obj == NULL) pe_fatal(pe, "calloc(field_t) failed\n");
+  obj->nf = opts->ndata; obj->nhcomm = opts->nhcomm; obj->opts = *opts;
+  obj->pe = pe; obj->cs = cs; obj->le = le;
+  obj->nsites = cs->nsites;
+  obj->name = strdup(name);
+  obj->data = (double *) calloc((size_t) obj->nf*obj->nsites, sizeof(double));
+  if (obj->data == NULL) pe_fatal(pe, "calloc(field->data) failed\n");
+  obj->b200_array = tag;
+  obj->target = obj;
+  *pobj = obj;
+  return 0;
+}
+
+int field_create(pe_t * pe, cs_t * cs, lees_edw_t * le, const char * name, const field_options_t * opts, field_t ** pobj) {
+  int tag = -1;
+  assert(pe); assert(cs); assert(opts); assert(pobj);
+  /* the scalar order parameter of the symmetric free energy is the one device-backed user field */
+  if (opts->ndata == 1 && cs->phi == NULL) tag = LB200_PHI;
+  field_create_tagged(pe, cs, le, name, opts, tag, pobj);
+  if (tag == LB200_PHI) cs->phi = *pobj;
+  return 0;
+}
+
+int field_free(field_t * obj) {
+  if (obj == NULL) return 0;
+  if (obj->cs && obj->cs->phi == obj) obj->cs->phi = NULL;
+  free(obj->name); free(obj->data); free(obj);
+  return 0;
+}
+
+int field_memcpy(field_t * obj, tdpMemcpyKind flag) {
+  if (obj->b200_array < 0) return 0;
+  b200_check(obj->pe, lb200_memcpy(cs_b200_context(obj->cs), obj->b200_array, obj->data, b200_kind(flag)), "field_memcpy");
+  return 0;
+}
+
+int field_halo(field_t * obj) {
+  lb200_t * ctx = cs_b200_context(obj->cs);
+  if (obj->b200_array == LB200_PHI) b200_check(obj->pe, lb200_phi_halo(ctx), "field_halo");
+  else if (obj->b200_array == LB200_U) b200_check(obj->pe, lb200_hydro_u_halo(ctx), "field_halo");
+  else pe_fatal(obj->pe, "field_halo: field \"%s\" has no device halo in this build\n", obj->name);
+  return 0;
+}
+
+int field_nf(field_t * obj, int * nop) { *nop = obj->nf; return 0; }
+int field_scalar(field_t * obj, int index, double * phi) { *phi = obj->data[addr_rank1(obj->nsites, 1, index, 0)]; return 0; }
+int field_scalar_set(field_t * obj, int index, double phi) { obj->data[addr_rank1(obj->nsites, 1, index, 0)] = phi; return 0; }
+int field_vector(field_t * obj, int index, double p[3]) {
+  for (int a = 0; a < 3; a++) p[a] = obj->data[addr_rank1(obj->nsites, 3, index, a)];
+  return 0;
+}
+int field_vector_set(field_t * obj, int index, const double p[3]) {
+  for (int a = 0; a < 3; a++) obj->data[addr_rank1(obj->nsites, 3, index, a)] = p[a];
+  return 0;
+}
+
+/* ---- field_grad_t ------------------------------------------------------------------------------------------ */
+
+int field_grad_create(pe_t * pe, field_t * f, int level, field_grad_t ** pobj) {
+  field_grad_t * obj = (field_grad_t *) calloc(1, sizeof(field_grad_t));
+  if (obj == NULL) pe_fatal(pe, "calloc(field_grad_t) failed\n");
+  obj->pe = pe; obj->field = f; obj->nf = f->nf; obj->level = level; obj->nsite = f->nsites;
+  obj->grad = (double *) calloc((size_t) 3*obj->nf*obj->nsite, sizeof(double));
+  obj->delsq = (double *) calloc((size_t) obj->nf*obj->nsite, sizeof(double));
+  if (obj->grad == NULL || obj->delsq == NULL) pe_fatal(pe, "calloc(field_grad) failed\n");
+  obj->target = obj;
+  if (f->cs->phi == f) f->cs->phi_grad = obj;
+  *pobj = obj;
+  return 0;
+}
+
+void field_grad_free(field_grad_t * obj) {
+  if (obj == NULL) return;
+  if (obj->field && obj->field->cs && obj->field->cs->phi_grad == obj) obj->field->cs->phi_grad = NULL;
+  free(obj->grad); free(obj->delsq); free(obj);
+}
+
+int field_grad_set(field_grad_t * obj, grad_ft d2, grad_ft d4) { obj->d2 = d2; obj->d4 = d4; return 0; }
+
+/* src/field_grad.c:319-340 */
+int field_grad_compute(field_grad_t * obj) {
+  assert(obj);
+  assert(obj->d2);
+  obj->d2(obj);
+  if (obj->level >= 4) pe_fatal(obj->pe, "field_grad_compute: d4 is outside this build\n");
+  return 0;
+}
+
+int grad_3d_27pt_fluid_d2(field_grad_t * fg) {
+  b200_check(fg->pe, lb200_phi_grad_compute(cs_b200_context(fg->field->cs)), "grad_3d_27pt_fluid_d2");
+  return 0;
+}
+
+int field_grad_memcpy(field_grad_t * obj, tdpMemcpyKind flag) {
+  lb200_t * ctx = cs_b200_context(obj->field->cs);
+  b200_check(obj->pe, lb200_memcpy(ctx, LB200_GRAD, obj->grad, b200_kind(flag)), "field_grad_memcpy");
+  b200_check(obj->pe, lb200_memcpy(ctx, LB200_DELSQ, obj->delsq, b200_kind(flag)), "field_grad_memcpy");
+  return 0;
+}
+
+int field_grad_scalar_grad(field_grad_t * obj, int index, double grad[3]) {
+  for (int a = 0; a < 3; a++) grad[a] = obj->grad[addr_rank2(obj->nsite, 1, 3, index, 0, a)];
+  return 0;
+}
+int field_grad_scalar_delsq(field_grad_t * obj, int index, double * delsq) {
+  *delsq = obj->delsq[addr_rank1(obj->nsite, 1, index, 0)];
+  return 0;
+}
+
+/* ---- hydro_t -------------------------------------------------------------------------------------------------- */
+
+hydro_options_t hydro_options_nhalo(int nhalo) {
+  hydro_options_t o = {.nhcomm = nhalo, .rho = field_options_ndata_nhalo(1, nhalo), .u = field_options_ndata_nhalo(3, nhalo),
+		       .force = field_options_ndata_nhalo(3, nhalo), .eta = field_options_ndata_nhalo(1, nhalo)};
+  return o;
+}
+hydro_options_t hydro_options_default(void) { return hydro_options_nhalo(1); }
+
+int hydro_create(pe_t * pe, cs_t * cs, lees_edw_t * le, const hydro_options_t * opts, hydro_t ** pobj) {
+  hydro_t * obj = (hydro_t *) calloc(1, sizeof(hydro_t));
+  if (obj == NULL) pe_fatal(pe, "calloc(hydro) failed\n");
+  obj->pe = pe; obj->cs = cs; obj->le = le; obj->nhcomm = opts->nhcomm; obj->nsite = cs->nsites;
+  field_create_tagged(pe, cs, le, "rho", &opts->rho, LB200_RHO, &obj->rho);
+  field_create_tagged(pe, cs, le, "u", &opts->u, LB200_U, &obj->u);
+  field_create_tagged(pe, cs, le, "force", &opts->force, LB200_FORCE, &obj->force);
+  field_create_tagged(pe, cs, le, "eta", &opts->eta, -1, &obj->eta);
+  obj->target = obj;
+  cs->hydro = obj;
+  *pobj = obj;
+  return 0;
+}
+
+int hydro_free(hydro_t * obj) {
+  if (obj == NULL) return 0;
+  if (obj->cs && obj->cs->hydro == obj) obj->cs->hydro = NULL;
+  field_free(obj->rho); field_free(obj->u); field_free(obj->force); field_free(obj->eta);
+  free(obj);
+  return 0;
+}
+
+/* src/hydro.c:123-160: rho, u, force */
+int hydro_memcpy(hydro_t * obj, tdpMemcpyKind flag) {
+  field_memcpy(obj->rho, flag);
+  field_memcpy(obj->u, flag);
+  field_memcpy(obj->force, flag);
+  return 0;
+}
+
+int hydro_u_halo(hydro_t * obj) { return field_halo(obj->u); }
+
+int hydro_f_zero(hydro_t * obj, const double fzero[3]) {
+  if (fzero[X] != 0.0 || fzero[Y] != 0.0 || fzero[Z] != 0.0) pe_fatal(obj->pe, "hydro_f_zero: non-zero value not supported\n");
+  b200_check(obj->pe, lb200_hydro_f_zero(cs_b200_context(obj->cs)), "hydro_f_zero");
+  return 0;
+}
+
+int hydro_u_zero(hydro_t * obj, const double uzero[3]) {
+  if (uzero[X] != 0.0 || uzero[Y] != 0.0 || uzero[Z] != 0.0) pe_fatal(obj->pe, "hydro_u_zero: non-zero value not supported\n");
+  b200_check(obj->pe, lb200_hydro_u_zero(cs_b200_context(obj->cs)), "hydro_u_zero");
+  return 0;
+}
+
+int hydro_u(hydro_t * obj, int index, double u[3]) { return field_vector(obj->u, index, u); }
+int hydro_u_set(hydro_t * obj, int index, const double u[3]) { return field_vector_set(obj->u, index, u); }
+int hydro_f_local(hydro_t * obj, int index, double f[3]) { return field_vector(obj->force, index, f); }
+int hydro_f_local_set(hydro_t * obj, int index, const double f[3]) { return field_vector_set(obj->force, index, f); }
+int hydro_rho(hydro_t * obj, int index, double * rho) { return field_scalar(obj->rho, index, rho); }
+
+/* ---- map_t ------------------------------------------------------------------------------------------------------ */
+
+map_options_t map_options_default(void) { map_options_t o = {.ndata = 0, .is_porous_media = 0}; return o; }
+
+int map_create(pe_t * pe, cs_t * cs, const map_options_t * options, map_t ** pmap) {
+  map_t * map = (map_t *) calloc(1, sizeof(map_t));
+  (void) options;
+  if (map == NULL) pe_fatal(pe, "calloc(map_t) failed\n");
+  map->pe = pe; map->cs = cs; map->nsite = cs->nsites;
+  map->status = (char *) calloc(map->nsite, sizeof(char));     /* MAP_FLUID everywhere */
+  if (map->status == NULL) pe_fatal(pe, "calloc(map->status) failed\n");
+  map->target = map;
+  cs->map = map;
+  *pmap = map;
+  return 0;
+}
+
+int map_free(map_t ** pmap) {
+  map_t * map = *pmap;
+  if (map == NULL) return 0;
+  if (map->cs && map->cs->map == map) map->cs->map = NULL;
+  free(map->status); free(map);
+  *pmap = NULL;
+  return 0;
+}
+
+int map_memcpy(map_t * map, tdpMemcpyKind flag) {
+  double * tmp = (double *) malloc((size_t) map->nsite*sizeof(double));
+  if (tmp == NULL) pe_fatal(map->pe, "malloc failed\n");
+  if (flag == tdpMemcpyHostToDevice) for (int i = 0; i < map->nsite; i++) tmp[i] = (double) map->status[i];
+  b200_check(map->pe, lb200_memcpy(cs_b200_context(map->cs), LB200_MAP, tmp, b200_kind(flag)), "map_memcpy");
+  if (flag == tdpMemcpyDeviceToHost) for (int i = 0; i < map->nsite; i++) map->status[i] = (char) tmp[i];
+  free(tmp);
+  return 0;
+}
+
+int map_status(map_t * map, int index, int * status) { *status = (int) map->status[index]; return 0; }
+int map_status_set(map_t * map, int index, int status) { map->status[index] = (char) status; return 0; }
+
+/* ---- symmetric free energy ------------------------------------------------------------------------------------------ */
+
+int fe_symm_create(pe_t * pe, cs_t * cs, field_t * f, field_grad_t * grd, fe_symm_t ** p) {
+  fe_symm_t * fe = (fe_symm_t *) calloc(1, sizeof(fe_symm_t));
+  if (fe == NULL) pe_fatal(pe, "calloc(fe_symm_t) failed\n");
+  fe->param = (fe_symm_param_t *) calloc(1, sizeof(fe_symm_param_t));
+  fe->pe = pe; fe->cs = cs; fe->phi = f; fe->dphi = grd;
+  fe->super.id = 1;      /* FE_SYMMETRIC */
+  fe->target = fe;
+  *p = fe;
+  return 0;
+}
+int fe_symm_free(fe_symm_t * fe) { if (fe) { free(fe->param); free(fe); } return 0; }
+int fe_symm_param_set(fe_symm_t * fe, fe_symm_param_t values) { *fe->param = values; return 0; }
+int fe_symm_param(fe_symm_t * fe, fe_symm_param_t * values) { *values = *fe->param; return 0; }
+
+/* src/symmetric.c:284-299 (host arrays) */
+int fe_symm_fed(fe_symm_t * fe, int index, double * fed) {
+  double phi, dphi[3];
+  field_scalar(fe->phi, index, &phi);
+  field_grad_scalar_grad(fe->dphi, index, dphi);
+  *fed = (0.5*fe->param->a + 0.25*fe->param->b*phi*phi)*phi*phi
+    + 0.5*fe->param->kappa*(dphi[X]*dphi[X] + dphi[Y]*dphi[Y] + dphi[Z]*dphi[Z]);
+  return 0;
+}
+
+/* src/symmetric.c:307-319 */
+int fe_symm_mu(fe_symm_t * fe, int index, double * mu) {
+  double phi = fe->phi->data[addr_rank0(fe->phi->nsites, index)];
+  double delsq = fe->dphi->delsq[addr_rank0(fe->phi->nsites, index)];
+  *mu = fe->param->a*phi + fe->param->b*phi*phi*phi - fe->param->kappa*delsq;
+  return 0;
+}
+
+static void symm_param_from(fe_t * fe, lb200_symm_param_t * sp) {
+  fe_symm_t * fs = (fe_symm_t *) fe;
+  physics_t * phys = NULL;
+  memset(sp, 0, sizeof(*sp));
+  physics_ref(&phys);
+  sp->a = fs->param->a; sp->b = fs->param->b; sp->kappa = fs->param->kappa;
+  physics_mobility(phys, &sp->mobility);
+  physics_grad_mu(phys, sp->gradmu);
+  advection_order(&sp->adv_order);
+}
+
+/* ---- phi_force ---------------------------------------------------------------------------------------------------------- */
+
+int pth_create(pe_t * pe, cs_t * cs, int method, pth_t ** ppth) {
+  pth_t * pth = (pth_t *) calloc(1, sizeof(pth_t));
+  if (pth == NULL) pe_fatal(pe, "calloc(pth_t) failed\n");
+  pth->pe = pe; pth->cs = cs; pth->method = method; pth->nsites = cs->nsites;
+  pth->target = pth;
+  *ppth = pth;
+  return 0;
+}
+int pth_free(pth_t * pth) { free(pth); return 0; }
+
+/* src/phi_force.c:74-137 */
+int phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t * wall, pth_t * pth, fe_t * fe,
+			  map_t * map, field_t * phi, hydro_t * hydro) {
+  lb200_symm_param_t sp;
+  (void) map; (void) phi;
+  assert(pth);
+  if (hydro == NULL) return 0;
+  if (pth->method == FE_FORCE_METHOD_NO_FORCE) return 0;
+  if (wall != NULL) pe_fatal(pe, "phi_force_calculation: walls are outside this build\n");
+  if (le && lees_edw_nplane_total(le) > 0) pe_fatal(pe, "phi_force_calculation: LE planes are outside this build\n");
+  if (pth->method != FE_FORCE_METHOD_STRESS_DIVERGENCE) pe_fatal(pe, "Bad force method\n");
+  symm_param_from(fe, &sp);
+  b200_check(pe, lb200_phi_force_calculation(cs_b200_context(cs), &sp), "phi_force_calculation");
+  return 0;
+}
+
+/* ---- Cahn-Hilliard ---------------------------------------------------------------------------------------------------------- */
+
+static int advection_order_ = 1;     /* src/advection.c:74 */
+int advection_order_set(const int order) { advection_order_ = order; return 0; }
+int advection_order(int * order) { *order = advection_order_; return 0; }
+
+int phi_ch_create(pe_t * pe, cs_t * cs, lees_edw_t * le, phi_ch_info_t * info, phi_ch_t ** ppch) {
+  phi_ch_t * pch = (phi_ch_t *) calloc(1, sizeof(phi_ch_t));
+  if (pch == NULL) pe_fatal(pe, "calloc(phi_ch_t) failed\n");
+  if (info->conserve != 0) pe_fatal(pe, "cahn_hilliard_options_conserve != 0 is outside this build\n");
+  pch->pe = pe; pch->cs = cs; pch->le = le; pch->info = *info;
+  *ppch = pch;
+  return 0;
+}
+int phi_ch_free(phi_ch_t * pch) { free(pch); return 0; }
+
+/* src/phi_cahn_hilliard.c:213-288 */
+int phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t * hydro, map_t * map, noise_t * noise) {
+  lb200_symm_param_t sp;
+  (void) phi; (void) map;
+  assert(pch); assert(fe);
+  if (noise != NULL || pch->info.noise) pe_fatal(pch->pe, "phi_cahn_hilliard: noise is outside this build\n");
+  if (hydro == NULL) pe_fatal(pch->pe, "phi_cahn_hilliard: hydro == NULL is outside this build\n");
+  symm_param_from(fe, &sp);
+  b200_check(pch->pe, lb200_phi_cahn_hilliard(cs_b200_context(pch->cs), &sp), "phi_cahn_hilliard");
+  return 0;
+}
+
+/* ---- collision ------------------------------------------------------------------------------------------------------------------ */
+
+/* src/collision.c:143-162 with the per-call parameter refresh of :1163-1246 and :1906-1958 */
+int lb_collide(lb_t * lb, hydro_t * hydro, map_t * map, noise_t * noise, fe_t * fe, visc_t * visc) {
+  physics_t * phys = NULL;
+  lb200_collide_param_t cp;
+  (void) fe;
+  if (hydro == NULL) return 0;
+  assert(lb);
+  assert(map);
+  if (noise != NULL) pe_fatal(lb->pe, "lb_collide: fluctuations are outside this build\n");
+  if (visc != NULL) pe_fatal(lb->pe, "lb_collide: viscosity models are outside this build\n");
+  memset(&cp, 0, sizeof(cp));
+  physics_ref(&phys);
+  cp.nrelax = (int) lb->nrelax;
+  physics_rho0(phys, &cp.rho0);
+  physics_eta_shear(phys, &cp.eta_shear);
+  physics_eta_bulk(phys, &cp.eta_bulk);
+  physics_fbody(phys, cp.force_global);
+  b200_check(lb->pe, lb200_lb_collide(cs_b200_context(lb->cs), &cp), "lb_collide");
+  return 0;
+}
