@@ -159,7 +159,8 @@ enum lb200_kernel_class {
   LB200_K_HALO = 2,         /* halo shells incl. x-plane exchange */
   LB200_K_GRAD = 3,         /* 27-point gradient */
   LB200_K_FORCE_CH = 4,     /* stress-divergence force and/or Cahn-Hilliard update */
-  LB200_KCLASS_MAX = 5
+  LB200_K_PHI_SECTOR = 5,   /* gradient + force + Cahn-Hilliard in one sweep (lb200_step, all-fluid) */
+  LB200_KCLASS_MAX = 6
 };
 int lb200_profile(lb200_t * ctx, int on);      /* clears accumulated timings */
 int lb200_profile_get(lb200_t * ctx, int kernel_class, double * total_ms, int * count);

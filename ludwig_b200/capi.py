@@ -243,7 +243,7 @@ class Lb200:
             self.lb_halo()
             self.lb_propagation()
 
-    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch")
+    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch", "phi_sector")
 
     def profile(self, on=True):
         self._check(self.lib.lb200_profile(self.h, int(on)))

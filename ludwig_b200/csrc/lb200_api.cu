@@ -821,7 +821,8 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   // The three halo exchanges run on the comm stream, each overlapped with a compute kernel that does
   // not touch the array in flight:   phi(t+1) halo || collide(t);   f(t) and u(t) halos || grad(t+1),
   // force+CH(t+1).  Same operations on the same data as the serial order, so results are unchanged.
-  cudaStream_t S = c->stream, C = c->comm;
+  // (while per-kernel profiling is on, everything runs on one stream so that launch durations are clean)
+  cudaStream_t S = c->stream, C = c->profile ? c->stream : c->comm;
 
   // anything still pending on the main stream must be visible to the comm stream
   CUDA_TRY(cudaEventRecord(c->ev_main, S));
@@ -835,8 +836,11 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	if (rc != 0) return rc;
 	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
       }
+      // all-fluid lattices: gradient + force + Cahn-Hilliard in one sweep (LB200_PHI_SECTOR=0 disables)
+      static const int ps_enabled = getenv("LB200_PHI_SECTOR") ? atoi(getenv("LB200_PHI_SECTOR")) : 1;
+      const bool use_ps = ps_enabled && c->map_all_fluid;
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
-      {
+      if (!use_ps) {
 	ProfScope ps(c, LB200_K_GRAD);
 	c->launches += c->k->grad27(S, c->g, c->phi, c->grad, c->delsq);       // field_grad_compute
       }
@@ -850,11 +854,23 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	c->u_state = ARRAY_CLEAN;
       }
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
-      {
-	// phi_force_calculation + phi_cahn_hilliard
+      if (use_ps) {
+	// field_grad_compute + phi_force_calculation + phi_cahn_hilliard
+	ProfScope ps(c, LB200_K_PHI_SECTOR);
+	c->launches += c->k->phi_sector(S, c->g, sd, c->phi, c->u, c->grad, c->delsq, c->force, c->phinew);
+      }
+      else {
+	// phi_force_calculation + phi_cahn_hilliard: one sweep, or two lighter ones (LB200_SPLIT_FCH=1)
+	static const int split = getenv("LB200_SPLIT_FCH") ? atoi(getenv("LB200_SPLIT_FCH")) : 0;
 	ProfScope ps(c, LB200_K_FORCE_CH);
-	c->launches += c->k->force_ch(S, c->g, sd, 0, c->phi, c->grad, c->delsq, c->u,
-				      status_ptr(c), c->force, c->phinew);
+	if (split) {
+	  c->launches += c->k->phi_force(S, c->g, sd, 0, c->phi, c->grad, c->delsq, c->force);
+	  c->launches += c->k->cahn_hilliard(S, c->g, sd, c->phi, c->delsq, c->u, status_ptr(c), c->phinew);
+	}
+	else {
+	  c->launches += c->k->force_ch(S, c->g, sd, 0, c->phi, c->grad, c->delsq, c->u,
+					status_ptr(c), c->force, c->phinew);
+	}
       }
       c->force_state = INTERIOR_ONLY;
       double * t = c->phi; c->phi = c->phinew; c->phinew = t;

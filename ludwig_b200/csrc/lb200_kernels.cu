@@ -456,13 +456,14 @@ grad27_kernel(const Lb200Geom g, const double * __restrict__ field, double * __r
   P##_0m = field[(base)   -1]; P##_00 = field[(base)   ]; P##_0p = field[(base)   +1]; \
   P##_pm = field[(base)+ys-1]; P##_p0 = field[(base)+ys]; P##_pp = field[(base)+ys+1]
 
-  LB200_LOAD_PLANE(c, index - g.xs);
-  LB200_LOAD_PLANE(p, index);
+  // software pipeline: the plane two steps ahead (n_) is in flight while the current site is summed
+  double n_mm, n_m0, n_mp, n_0m, n_00, n_0p, n_pm, n_p0, n_pp;
+  LB200_LOAD_PLANE(m, index - g.xs);
+  LB200_LOAD_PLANE(c, index);
+  LB200_LOAD_PLANE(p, index + g.xs);
 
   for (int ic = ic0; ic <= ic1; ic++) {
-    m_mm = c_mm; m_m0 = c_m0; m_mp = c_mp; m_0m = c_0m; m_00 = c_00; m_0p = c_0p; m_pm = c_pm; m_p0 = c_p0; m_pp = c_pp;
-    c_mm = p_mm; c_m0 = p_m0; c_mp = p_mp; c_0m = p_0m; c_00 = p_00; c_0p = p_0p; c_pm = p_pm; c_p0 = p_p0; c_pp = p_pp;
-    LB200_LOAD_PLANE(p, index + g.xs);
+    if (ic < ic1) { LB200_LOAD_PLANE(n, index + 2*g.xs); }
 
     grad[0*ns + index] = 0.5*r9*
       (+ p_mm - m_mm + p_m0 - m_m0 + p_mp - m_mp
@@ -482,6 +483,12 @@ grad27_kernel(const Lb200Geom g, const double * __restrict__ field, double * __r
        + p_mm + p_m0 + p_mp + p_0m + p_00 + p_0p + p_pm + p_p0 + p_pp
        - 26.0*c_00);
     index += g.xs;
+
+    m_mm = c_mm; m_m0 = c_m0; m_mp = c_mp; m_0m = c_0m; m_00 = c_00; m_0p = c_0p; m_pm = c_pm; m_p0 = c_p0; m_pp = c_pp;
+    c_mm = p_mm; c_m0 = p_m0; c_mp = p_mp; c_0m = p_0m; c_00 = p_00; c_0p = p_0p; c_pm = p_pm; c_p0 = p_p0; c_pp = p_pp;
+    if (ic < ic1) {
+      p_mm = n_mm; p_m0 = n_m0; p_mp = n_mp; p_0m = n_0m; p_00 = n_00; p_0p = n_0p; p_pm = n_pm; p_p0 = n_p0; p_pp = n_pp;
+    }
   }
 #undef LB200_LOAD_PLANE
 }
@@ -755,6 +762,282 @@ int launch_force_ch(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & s
 }
 
 // ---------------------------------------------------------------------------------------------
+// The phi sector of a time step in one sweep: field_grad_compute + phi_force_calculation +
+// phi_cahn_hilliard (reference src/gradient_3d_27pt_fluid.c:219-363, src/symmetric.c:371-416,
+// src/phi_force_colloid.c:315-465, src/advection.c:946-1141, src/phi_cahn_hilliard.c:350-404,
+// 1018-1049, 1373-1397), same operations in the same order as the separate kernels above.
+//
+// A CTA owns a (PS_BY-2) x (PS_BZ-2) tile of (j,k) columns plus a one-site apron and marches along
+// x.  Per plane every thread (apron included) forms grad/delsq of ITS column from three phi planes
+// staged in shared memory, derives p0 and mu ONCE per site (the separate kernels recompute them at
+// all 7 stencil points), and publishes {p0, grad, mu, u_y, u_z} in shared memory for its y/z
+// neighbours; the x neighbours are the thread's own previous / next plane, kept in registers.
+// Global traffic per site: phi 8 + u 24 read, grad 24 + delsq 8 + force 24 + phi' 8 written
+// (vs 136 B for gradient + force/CH kernels), 4 global loads per thread per plane, all prefetched
+// one plane ahead, one __syncthreads per plane.
+// ---------------------------------------------------------------------------------------------
+
+constexpr int PS_BZ = 32;                 // threads along z (one warp)
+constexpr int PS_BY = 16;                 // threads along y
+constexpr int PS_NT = PS_BZ*PS_BY;        // 512
+constexpr int PS_TZ = PS_BZ - 2;          // interior columns per tile
+constexpr int PS_TY = PS_BY - 2;
+constexpr int PS_PZ = PS_BZ + 2;          // phi tile: block + one more ring
+constexpr int PS_PY = PS_BY + 2;
+constexpr int PS_PN = PS_PZ*PS_PY;        // 612
+constexpr int PS_XC = 32;                 // planes per x chunk
+
+struct PsShared {
+  double phi[4][PS_PN];                   // ring of phi planes
+  double g[2][5][PS_NT];                  // p0, gx, gy, gz, mu of plane i (double buffered)
+  double u[2][2][PS_NT];                  // u_y, u_z of plane i
+};
+
+__device__ __forceinline__ void ps_pcol(const Lb200SymmDev & sp, int B, double p0, double gx, double gy,
+					double gz, double p[3]) {
+  const double gb = (B == 0) ? gx : (B == 1) ? gy : gz;
+  const double d0 = (B == 0), d1 = (B == 1), d2 = (B == 2);
+  p[0] = p0*d0 + sp.kappa*gx*gb;
+  p[1] = p0*d1 + sp.kappa*gy*gb;
+  p[2] = p0*d2 + sp.kappa*gz*gb;
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(PS_NT, 1)
+phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __restrict__ phi,
+		  const double * __restrict__ u, double * __restrict__ grad,
+		  double * __restrict__ delsq, double * __restrict__ force,
+		  double * __restrict__ phinew) {
+
+  extern __shared__ __align__(16) unsigned char ps_smem_raw[];
+  PsShared & sm = *reinterpret_cast<PsShared *>(ps_smem_raw);
+
+  const int tz = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty*PS_BZ + tz;
+  const int kbase = blockIdx.x*PS_TZ;              // thread column (j,k) = (jbase + ty, kbase + tz)
+  const int jbase = blockIdx.y*PS_TY;
+  const int kc = kbase + tz, jc = jbase + ty;
+  const int i0 = 1 + blockIdx.z*PS_XC;
+  const int i1 = min(i0 + PS_XC - 1, g.nl[0]);
+  const int nh = g.nh;
+  const size_t ns = (size_t) g.nsites;
+  const int xs = g.xs, ys = g.ys;
+
+  const bool valid_g = (jc <= g.nl[1] + 1) && (kc <= g.nl[2] + 1);
+  const bool inner = (ty >= 1 && ty <= PS_TY && tz >= 1 && tz <= PS_TZ);
+  const bool out_site = inner && jc <= g.nl[1] && kc <= g.nl[2];
+  const bool own_g = valid_g && ((ty >= 1 && ty <= PS_TY) || (ty == 0 && jc == 0))
+    && ((tz >= 1 && tz <= PS_TZ) || (tz == 0 && kc == 0));
+
+  // clamp the column used for loads so that inactive threads stay inside the allocation
+  const int jl = min(jc, g.nl[1] + 1), kl = min(kc, g.nl[2] + 1);
+  const int col = (jl + nh - 1)*ys + (kl + nh - 1);       // + (i + nh - 1)*xs
+
+  // cooperative phi plane load: element e of the (PS_PY x PS_PZ) tile <-> (jbase-1+r, kbase-1+c)
+  const int e0 = tid, e1 = tid + PS_NT;
+  const int r0 = e0/PS_PZ, c0 = e0%PS_PZ;
+  const int r1 = e1/PS_PZ, c1 = e1%PS_PZ;
+  const int pj0 = min(jbase - 1 + r0, g.nl[1] + nh), pk0 = min(kbase - 1 + c0, g.nl[2] + nh);
+  const int pj1 = min(jbase - 1 + r1, g.nl[1] + nh), pk1 = min(kbase - 1 + c1, g.nl[2] + nh);
+  const int pcol0 = (pj0 + nh - 1)*ys + (pk0 + nh - 1);
+  const int pcol1 = (pj1 + nh - 1)*ys + (pk1 + nh - 1);
+  const bool has_e1 = (e1 < PS_PN);
+
+  const int istart = i0 - 2;
+
+  // prologue: planes istart, istart+1, istart+2 into the ring
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int ip = istart + d;
+    const int xo = (ip + nh - 1)*xs;
+    sm.phi[(ip + 4) & 3][e0] = phi[xo + pcol0];
+    if (has_e1) sm.phi[(ip + 4) & 3][e1] = phi[xo + pcol1];
+  }
+  double uxc = u[0*ns + (istart + nh - 1)*xs + col];
+  double uxp = u[0*ns + (istart + 1 + nh - 1)*xs + col];
+  double uxm = 0.0;
+  __syncthreads();
+
+  // own-column history
+  double gm_p0 = 0.0, gm_x = 0.0, gm_y = 0.0, gm_z = 0.0, gm_mu = 0.0;      // plane i-1
+  double gc_p0 = 0.0, gc_x = 0.0, gc_y = 0.0, gc_z = 0.0, gc_mu = 0.0;      // plane i
+  double phim1 = 0.0, phim2 = 0.0;                                        // phi(i-1), phi(i-2), own column
+
+  const int pc = (ty + 1)*PS_PZ + (tz + 1);        // own position in the phi tile
+
+  for (int i = istart; i <= i1; i++) {
+
+    // ---- 1. prefetch for the next plane-steps (consumed after the arithmetic below) ----
+    double pf0 = 0.0, pf1 = 0.0, uxn = 0.0, uyn = 0.0, uzn = 0.0;
+    if (i < i1) {
+      const int xo3 = (i + 3 + nh - 1)*xs;
+      pf0 = phi[xo3 + pcol0];
+      if (has_e1) pf1 = phi[xo3 + pcol1];
+      uxn = u[0*ns + (i + 2 + nh - 1)*xs + col];
+      uyn = u[1*ns + (i + 1 + nh - 1)*xs + col];
+      uzn = u[2*ns + (i + 1 + nh - 1)*xs + col];
+    }
+
+    // ---- 2. gradient of plane i+1 at the own column, from phi planes i, i+1, i+2 ----
+    const double * __restrict__ fm = sm.phi[(i + 4) & 3];
+    const double * __restrict__ fc = sm.phi[(i + 5) & 3];
+    const double * __restrict__ fp = sm.phi[(i + 6) & 3];
+    double gp_p0 = 0.0, gp_x = 0.0, gp_y = 0.0, gp_z = 0.0, gp_mu = 0.0;
+    if (valid_g) {
+      const double r9 = (1.0/9.0);
+      const double m_mm = fm[pc-PS_PZ-1], m_m0 = fm[pc-PS_PZ], m_mp = fm[pc-PS_PZ+1];
+      const double m_0m = fm[pc      -1], m_00 = fm[pc      ], m_0p = fm[pc      +1];
+      const double m_pm = fm[pc+PS_PZ-1], m_p0 = fm[pc+PS_PZ], m_pp = fm[pc+PS_PZ+1];
+      const double c_mm = fc[pc-PS_PZ-1], c_m0 = fc[pc-PS_PZ], c_mp = fc[pc-PS_PZ+1];
+      const double c_0m = fc[pc      -1], c_00 = fc[pc      ], c_0p = fc[pc      +1];
+      const double c_pm = fc[pc+PS_PZ-1], c_p0 = fc[pc+PS_PZ], c_pp = fc[pc+PS_PZ+1];
+      const double p_mm = fp[pc-PS_PZ-1], p_m0 = fp[pc-PS_PZ], p_mp = fp[pc-PS_PZ+1];
+      const double p_0m = fp[pc      -1], p_00 = fp[pc      ], p_0p = fp[pc      +1];
+      const double p_pm = fp[pc+PS_PZ-1], p_p0 = fp[pc+PS_PZ], p_pp = fp[pc+PS_PZ+1];
+
+      gp_x = 0.5*r9*
+	(+ p_mm - m_mm + p_m0 - m_m0 + p_mp - m_mp
+	 + p_0m - m_0m + p_00 - m_00 + p_0p - m_0p
+	 + p_pm - m_pm + p_p0 - m_p0 + p_pp - m_pp);
+      gp_y = 0.5*r9*
+	(+ m_pm - m_mm + m_p0 - m_m0 + m_pp - m_mp
+	 + c_pm - c_mm + c_p0 - c_m0 + c_pp - c_mp
+	 + p_pm - p_mm + p_p0 - p_m0 + p_pp - p_mp);
+      gp_z = 0.5*r9*
+	(+ m_mp - m_mm + m_0p - m_0m + m_pp - m_pm
+	 + c_mp - c_mm + c_0p - c_0m + c_pp - c_pm
+	 + p_mp - p_mm + p_0p - p_0m + p_pp - p_pm);
+      const double dsq = r9*
+	(+ m_mm + m_m0 + m_mp + m_0m + m_00 + m_0p + m_pm + m_p0 + m_pp
+	 + c_mm + c_m0 + c_mp + c_0m        + c_0p + c_pm + c_p0 + c_pp
+	 + p_mm + p_m0 + p_mp + p_0m + p_00 + p_0p + p_pm + p_p0 + p_pp
+	 - 26.0*c_00);
+
+      SiteFE sf;
+      sf.phi = c_00; sf.delsq = dsq; sf.gx = gp_x; sf.gy = gp_y; sf.gz = gp_z;
+      gp_p0 = symm_p0(sp, sf);
+      gp_mu = symm_mu(sp, c_00, dsq);
+
+      const int ig = i + 1;
+      const bool own_x = (ig >= i0 && ig <= i1) || (ig == 0 && i0 == 1) || (ig == g.nl[0] + 1 && i1 == g.nl[0]);
+      if (own_g && own_x) {
+	const int sidx = (ig + nh - 1)*xs + (jc + nh - 1)*ys + (kc + nh - 1);
+	grad[0*ns + sidx] = gp_x;
+	grad[1*ns + sidx] = gp_y;
+	grad[2*ns + sidx] = gp_z;
+	delsq[sidx] = dsq;
+      }
+    }
+    {
+      double (* gb)[PS_NT] = sm.g[(i + 1) & 1];
+      gb[0][tid] = gp_p0; gb[1][tid] = gp_x; gb[2][tid] = gp_y; gb[3][tid] = gp_z; gb[4][tid] = gp_mu;
+    }
+
+    // ---- 3. force and Cahn-Hilliard update of plane i ----
+    const double ph_c = fm[pc];
+    if (i >= i0 && out_site) {
+      const double (* gb)[PS_NT] = sm.g[i & 1];
+      const double (* ub)[PS_NT] = sm.u[i & 1];
+      const int s = (i + nh - 1)*xs + (jc + nh - 1)*ys + (kc + nh - 1);
+      const int typ = tid + PS_BZ, tym = tid - PS_BZ, tzp = tid + 1, tzm = tid - 1;
+
+      // force = - div P, accumulation order +x, -x, +y, -y, +z, -z
+      double fo[3], p0c[3], p1[3];
+      ps_pcol(sp, 0, gc_p0, gc_x, gc_y, gc_z, p0c);
+      ps_pcol(sp, 0, gp_p0, gp_x, gp_y, gp_z, p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] = -0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 0, gm_p0, gm_x, gm_y, gm_z, p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] += 0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 1, gc_p0, gc_x, gc_y, gc_z, p0c);
+      ps_pcol(sp, 1, gb[0][typ], gb[1][typ], gb[2][typ], gb[3][typ], p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] -= 0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 1, gb[0][tym], gb[1][tym], gb[2][tym], gb[3][tym], p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] += 0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 2, gc_p0, gc_x, gc_y, gc_z, p0c);
+      ps_pcol(sp, 2, gb[0][tzp], gb[1][tzp], gb[2][tzp], gb[3][tzp], p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] -= 0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 2, gb[0][tzm], gb[1][tzm], gb[2][tzm], gb[3][tzm], p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] += 0.5*(p1[a] + p0c[a]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) force[a*ns + s] = fo[a];
+
+      // Cahn-Hilliard: six face fluxes in registers, forward Euler
+      const double M = sp.mobility;
+      const double mu0 = gc_mu;
+      const double ph_xm = phim1, ph_xm2 = phim2, ph_xp = fc[pc], ph_xp2 = fp[pc];
+      const double ph_ym = fm[pc - PS_PZ], ph_yp = fm[pc + PS_PZ];
+      const double ph_zm = fm[pc - 1], ph_zp = fm[pc + 1];
+      double ph_ym2 = 0.0, ph_yp2 = 0.0, ph_zm2 = 0.0, ph_zp2 = 0.0;
+      if (ORDER == 3) {
+	ph_ym2 = fm[pc - 2*PS_PZ]; ph_yp2 = fm[pc + 2*PS_PZ];
+	ph_zm2 = fm[pc - 2];       ph_zp2 = fm[pc + 2];
+      }
+      const double uy_c = ub[0][tid], uy_ym = ub[0][tym], uy_yp = ub[0][typ];
+      const double uz_c = ub[1][tid], uz_zm = ub[1][tzm], uz_zp = ub[1][tzp];
+
+      double fw = adv_face<ORDER, true>(uxm, uxc, ph_xm2, ph_xm, ph_c, ph_xp);
+      fw -= M*(mu0 - gm_mu);
+      fw -= M*sp.gm[0];
+      double fe = adv_face<ORDER, false>(uxc, uxp, ph_xm, ph_c, ph_xp, ph_xp2);
+      fe -= M*(gp_mu - mu0);
+      fe -= M*sp.gm[0];
+      double fy = adv_face<ORDER, false>(uy_c, uy_yp, ph_ym, ph_c, ph_yp, ph_yp2);
+      fy -= M*(gb[4][typ] - mu0);
+      fy -= M*sp.gm[1];
+      double fym = adv_face<ORDER, false>(uy_ym, uy_c, ph_ym2, ph_ym, ph_c, ph_yp);
+      fym -= M*(mu0 - gb[4][tym]);
+      fym -= M*sp.gm[1];
+      double fz = adv_face<ORDER, false>(uz_c, uz_zp, ph_zm, ph_c, ph_zp, ph_zp2);
+      fz -= M*(gb[4][tzp] - mu0);
+      fz -= M*sp.gm[2];
+      double fzm = adv_face<ORDER, false>(uz_zm, uz_c, ph_zm2, ph_zm, ph_c, ph_zp);
+      fzm -= M*(mu0 - gb[4][tzm]);
+      fzm -= M*sp.gm[2];
+
+      double ph = ph_c;
+      ph -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
+      phinew[s] = ph;
+    }
+
+    // ---- 4. rotate the own-column history, publish the prefetched plane ----
+    gm_p0 = gc_p0; gm_x = gc_x; gm_y = gc_y; gm_z = gc_z; gm_mu = gc_mu;
+    gc_p0 = gp_p0; gc_x = gp_x; gc_y = gp_y; gc_z = gp_z; gc_mu = gp_mu;
+    phim2 = phim1; phim1 = ph_c;
+    uxm = uxc; uxc = uxp; uxp = uxn;
+    if (i < i1) {
+      sm.phi[(i + 7) & 3][e0] = pf0;                 // plane i+3 -> slot of plane i-1
+      if (has_e1) sm.phi[(i + 7) & 3][e1] = pf1;
+      sm.u[(i + 1) & 1][0][tid] = uyn;
+      sm.u[(i + 1) & 1][1][tid] = uzn;
+    }
+    __syncthreads();
+  }
+}
+
+int launch_phi_sector(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const double * phi,
+		      const double * u, double * grad, double * delsq, double * force, double * phinew) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(phi_sector_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(PsShared));
+    cudaFuncSetAttribute(phi_sector_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(PsShared));
+    cudaFuncSetAttribute(phi_sector_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(PsShared));
+    configured = true;
+  }
+  dim3 blk(PS_BZ, PS_BY, 1);
+  dim3 grd((g.nl[2] + 1 + PS_TZ - 1)/PS_TZ, (g.nl[1] + 1 + PS_TY - 1)/PS_TY, (g.nl[0] + PS_XC - 1)/PS_XC);
+  if (sp.order == 1)      phi_sector_kernel<1><<<grd, blk, sizeof(PsShared), st>>>(g, sp, phi, u, grad, delsq, force, phinew);
+  else if (sp.order == 2) phi_sector_kernel<2><<<grd, blk, sizeof(PsShared), st>>>(g, sp, phi, u, grad, delsq, force, phinew);
+  else                    phi_sector_kernel<3><<<grd, blk, sizeof(PsShared), st>>>(g, sp, phi, u, grad, delsq, force, phinew);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // zero everything outside the interior (materialises "logically zero" halos of force / u)
 // ---------------------------------------------------------------------------------------------
 
@@ -796,5 +1079,6 @@ const Lb200Kernels LB200_TABLE = {
   launch_phi_force,
   launch_cahn_hilliard,
   launch_force_ch,
+  launch_phi_sector,
   launch_zero_outside,
 };

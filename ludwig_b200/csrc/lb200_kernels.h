@@ -62,6 +62,10 @@ struct Lb200Kernels {
   int (*force_ch)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, int accumulate,
 		  const double * phi, const double * grad, const double * delsq, const double * u,
 		  const char * status, double * force, double * phinew);
+  // the whole phi sector of one time step in ONE sweep (all-fluid lattices): 27-point gradient (stored
+  // on [0,N+1]^3), chemical stress + force divergence, Cahn-Hilliard fluxes + update
+  int (*phi_sector)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, const double * phi,
+		    const double * u, double * grad, double * delsq, double * force, double * phinew);
   // zero everything outside the interior (ncomp components)
   int (*zero_outside)(cudaStream_t, const Lb200Geom &, int ncomp, double * data);
 };
