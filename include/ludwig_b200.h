@@ -147,6 +147,16 @@ int lb200_lb_propagation(lb200_t * ctx);
 int lb200_step(lb200_t * ctx, const lb200_collide_param_t * cp, const lb200_symm_param_t * sp,
 	       int nsteps);
 
+/* Execution knobs of lb200_step (results do not depend on them; the parity tests run both settings).
+ * Defaults come from the environment (LB200_WRAP, LB200_PHI_SECTOR), else 1. */
+enum lb200_knob {
+  LB200_KNOB_WRAP = 1,        /* 1: halo-free time steps on periodic lattices (periodic images are read from
+                               *    the interior; only the planes the kernels read cross NVLink)
+                               * 0: the reference's step structure with three halo swaps (phi, u, f) */
+  LB200_KNOB_PHI_SECTOR = 2   /* 1: gradient + force + Cahn-Hilliard in one sweep (all-fluid lattices) */
+};
+int lb200_set_knob(lb200_t * ctx, int knob, int value);
+
 /* number of kernels this library has launched on this context since creation */
 long long lb200_launch_count(const lb200_t * ctx);
 /* the context's CUDA stream (cudaStream_t) for event timing by the caller */

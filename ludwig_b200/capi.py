@@ -8,6 +8,7 @@ RELAX_M10, RELAX_BGK, RELAX_TRT = 0, 1, 2
 HALO_FULL, HALO_REDUCED = 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 H2D, D2H = 1, 2
+KNOB_WRAP, KNOB_PHI_SECTOR = 1, 2
 
 _NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1}
 
@@ -103,6 +104,7 @@ def load_library():
     lib.lb200_lb_collide.argtypes = [C.c_void_p, C.POINTER(CollideParam)]
     lib.lb200_step.argtypes = [C.c_void_p, C.POINTER(CollideParam), C.POINTER(SymmParam), C.c_int]
     lib.lb200_launch_count.argtypes = [C.c_void_p]
+    lib.lb200_set_knob.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.lb200_launch_count.restype = C.c_longlong
     lib.lb200_stream.argtypes = [C.c_void_p]
     lib.lb200_stream.restype = C.c_void_p
@@ -227,6 +229,10 @@ class Lb200:
 
     def step(self, cp, sp=None, nsteps=1):
         self._check(self.lib.lb200_step(self.h, C.byref(cp), C.byref(sp) if sp is not None else None, nsteps))
+
+    def set_knob(self, knob, value):
+        """lb200_set_knob: KNOB_WRAP (halo-free steps) / KNOB_PHI_SECTOR (one-sweep phi sector)."""
+        self._check(self.lib.lb200_set_knob(self.h, knob, int(value)))
 
     def step_api(self, cp, sp=None, nsteps=1):
         """The same time step through the individual reference-named entry points, in the

@@ -76,11 +76,16 @@ struct lb200_s {
   int u_halo_valid;
 
   int prop_pending;          // lb_propagation requested, not yet applied (fused into next collide)
+  int f_halo_stale;          // halo-free lb200_step: lb_halo(f) was folded into the kernels' reads and has
+                             // not been applied to the halo sites of f (done on demand with the propagation)
+  int wrap_x_valid;          // halo-free lb200_step on slabs: x-planes of phi, u_x, f already exchanged
   int force_state;           // ZeroState
   int u_state;
 
   long long launches;
   void * nccl;               // ncclComm_t
+  int knob_wrap;             // lb200_set_knob
+  int knob_phi_sector;
 
   // optional per-kernel-class timing with CUDA events on the launching stream
   int profile;
@@ -352,8 +357,18 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
 
   c->force_state = ARRAY_CLEAN;
   c->u_state = ARRAY_CLEAN;
+  c->knob_wrap = getenv("LB200_WRAP") ? atoi(getenv("LB200_WRAP")) : 1;
+  c->knob_phi_sector = getenv("LB200_PHI_SECTOR") ? atoi(getenv("LB200_PHI_SECTOR")) : 1;
   for (int i = 0; i < LB200_KCLASS_MAX; i++) c->ev[i] = new std::vector<cudaEvent_t>();
   *pctx = c;
+  return 0;
+}
+
+int lb200_set_knob(lb200_t * c, int knob, int value) {
+  if (c == nullptr) return fail(LB200_EINVAL, "null context");
+  if (knob == LB200_KNOB_WRAP) c->knob_wrap = (value != 0);
+  else if (knob == LB200_KNOB_PHI_SECTOR) c->knob_phi_sector = (value != 0);
+  else return fail(LB200_EINVAL, "unknown knob %d", knob);
   return 0;
 }
 
@@ -417,9 +432,22 @@ static const Lb200ModelDev * model_ptr(const lb200_t * c) { return c->unrolled19
 
 // ---- lazily applied operations --------------------------------------------------------------------
 
+static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int reduced, cudaStream_t st);
+
+// a halo-free lb200_step leaves "lb_halo(f); lb_propagation(f)" pending: apply the halo swap first
+static int ensure_f_halo(lb200_t * c) {
+  if (!c->f_halo_stale) return 0;
+  c->f_halo_stale = 0;
+  return halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED, nullptr);
+}
+
 // apply a pending lb_propagation as a stand-alone sweep (reference semantics, src/propagation.c)
 static int materialise_propagation(lb200_t * c) {
-  if (!c->prop_pending) return 0;
+  if (!c->prop_pending) { c->f_halo_stale = 0; return 0; }
+  {
+    int rc = ensure_f_halo(c);
+    if (rc != 0) return rc;
+  }
   {
     ProfScope ps(c, LB200_K_PROPAGATE);
     c->launches += c->k->propagate(c->stream, c->g, c->model_d, c->nvel, c->ndist, c->f, c->fprime);
@@ -500,6 +528,8 @@ static int do_memcpy(lb200_t * c, int array, double * host, int kind, int async)
     if (array == LB200_FORCE) c->force_state = ARRAY_CLEAN;
     if (array == LB200_U) { c->u_state = ARRAY_CLEAN; c->u_halo_valid = 0; }
     if (array == LB200_PHI) c->phi_halo_valid = 0;
+    if (array == LB200_F) c->f_halo_stale = 0;
+    c->wrap_x_valid = 0;
   }
 
   const size_t bytes = ncomp*(size_t) c->g.nsites*sizeof(double);
@@ -656,7 +686,7 @@ int lb200_nccl_comm_destroy(void * comm) {
 // ---- operators ------------------------------------------------------------------------------------
 
 #define CTX_ENTER(c) do { if ((c) == nullptr) return fail(LB200_EINVAL, "null context"); \
-  CUDA_TRY(cudaSetDevice((c)->device)); (c)->phi_halo_valid = 0; (c)->u_halo_valid = 0; } while (0)
+  CUDA_TRY(cudaSetDevice((c)->device)); (c)->phi_halo_valid = 0; (c)->u_halo_valid = 0; (c)->wrap_x_valid = 0; } while (0)
 #define CTX_LEAVE_SYNC(c) do { CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaStreamSynchronize((c)->stream)); return 0; } while (0)
 
 int lb200_hydro_f_zero(lb200_t * c) {
@@ -671,7 +701,7 @@ int lb200_hydro_u_zero(lb200_t * c) {
   return 0;
 }
 
-static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int reduced, cudaStream_t st = nullptr) {
+static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int reduced, cudaStream_t st) {
   if (st == nullptr) st = c->stream;
   ProfScope ps(c, LB200_K_HALO, st);
   int rc = exchange_x(c, st, data, ncomp, depth);
@@ -682,7 +712,7 @@ static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int redu
 
 static int u_halo_async(lb200_t * c) {
   if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
-  int rc = halo_field(c, c->u, 3, c->g.nh, 0);
+  int rc = halo_field(c, c->u, 3, c->g.nh, 0, nullptr);
   c->u_state = ARRAY_CLEAN;              // every halo site within nhalo has just been written
   return rc;
 }
@@ -697,7 +727,7 @@ int lb200_hydro_u_halo(lb200_t * c) {
 int lb200_phi_halo(lb200_t * c) {
   CTX_ENTER(c);
   if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
-  int rc = halo_field(c, c->phi, 1, c->g.nh, 0);
+  int rc = halo_field(c, c->phi, 1, c->g.nh, 0, nullptr);
   if (rc != 0) return rc;
   CTX_LEAVE_SYNC(c);
 }
@@ -749,12 +779,17 @@ int lb200_phi_cahn_hilliard(lb200_t * c, const lb200_symm_param_t * sp) {
   CTX_LEAVE_SYNC(c);
 }
 
-static int collide_async(lb200_t * c, const Lb200CollideDev & cd) {
+static int collide_async(lb200_t * c, const Lb200CollideDev & cd, const Lb200Geom * gwrap = nullptr) {
+  if (c->prop_pending && gwrap == nullptr) {
+    int rc = ensure_f_halo(c);
+    if (rc != 0) return rc;
+  }
   ProfScope ps(c, LB200_K_COLLIDE);
   const double * force = (c->force_state == ZERO_PENDING) ? nullptr : c->force;
   if (c->prop_pending) {
     // lb_propagation(t) fused with lb_collide(t+1): one read and one write of every population
-    c->launches += c->k->collide(c->stream, c->g, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime,
+    // (gwrap: lb_halo(t) folded in as well, the periodic images are read from the interior)
+    c->launches += c->k->collide(c->stream, gwrap ? *gwrap : c->g, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime,
 				 force, status_ptr(c), c->rho, c->u);
     double * t = c->f; c->f = c->fprime; c->fprime = t;
     c->prop_pending = 0;
@@ -780,7 +815,8 @@ int lb200_lb_collide(lb200_t * c, const lb200_collide_param_t * cp) {
 static int lb_halo_async(lb200_t * c) {
   int rc = materialise_propagation(c);
   if (rc != 0) return rc;
-  return halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED);
+  c->f_halo_stale = 0;
+  return halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED, nullptr);
 }
 
 int lb200_lb_halo(lb200_t * c) {
@@ -797,6 +833,196 @@ int lb200_lb_propagation(lb200_t * c) {
   c->prop_pending = 1;
   return 0;
 }
+
+// ---- halo-free whole time steps ---------------------------------------------------------------------
+// On a periodic lattice every halo site is the image of an interior site of the same GPU (y, z; x too
+// on one GPU), so the kernels of lb200_step read those images straight from the interior (Lb200Geom::wrap)
+// and the three halo sweeps of the reference step (field_halo(phi), hydro_u_halo, lb_halo: 26 pack
+// kernels + messages + unpack kernels each) disappear.  With x-slabs on several GPUs only what the next
+// kernels read crosses NVLink: 2 planes of phi, 1 plane of u_x and the populations with c_x = +-1
+// (5 of 19 for D3Q19) per direction, received directly in the halo planes.  Results on the interior are
+// those of the reference order; the halo sites of f are brought up to date on demand (f_halo_stale).
+
+struct XMsg { const double * send_hi; const double * send_lo; double * recv_lo; double * recv_hi; size_t count; };
+
+static int nccl_exchange(lb200_t * c, cudaStream_t st, const XMsg * m, int nm) {
+#ifdef LB200_NO_NCCL
+  return fail(LB200_ECOMM, "library built without NCCL");
+#else
+  if (c->nccl == nullptr) return fail(LB200_ECOMM, "cart_size > 1 but no NCCL communicator attached (lb200_attach_nccl)");
+  ncclComm_t comm = (ncclComm_t) c->nccl;
+  const int left = (c->opt.cart_rank - 1 + c->opt.cart_size) % c->opt.cart_size;
+  const int right = (c->opt.cart_rank + 1) % c->opt.cart_size;
+  ncclResult_t r = ncclGroupStart();
+  for (int i = 0; i < nm && r == ncclSuccess; i++) {
+    r = ncclSend(m[i].send_hi, m[i].count, ncclDouble, right, comm, st);
+    if (r == ncclSuccess) r = ncclSend(m[i].send_lo, m[i].count, ncclDouble, left, comm, st);
+    if (r == ncclSuccess) r = ncclRecv(m[i].recv_lo, m[i].count, ncclDouble, left, comm, st);
+    if (r == ncclSuccess) r = ncclRecv(m[i].recv_hi, m[i].count, ncclDouble, right, comm, st);
+  }
+  ncclResult_t r2 = ncclGroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess) {
+    return fail(LB200_ECOMM, "NCCL plane exchange: %s", ncclGetErrorString(r != ncclSuccess ? r : r2));
+  }
+  return 0;
+#endif
+}
+
+// planes of phi (depth nhalo) straight from the array into the neighbour's halo planes (contiguous: no staging)
+static int wrap_exchange_phi(lb200_t * c, cudaStream_t st) {
+  const Lb200Geom & g = c->g;
+  const size_t xs = (size_t) g.xs;
+  const int d = g.nh;
+  XMsg m;
+  m.send_hi = c->phi + (size_t) (g.nl[0] - d + g.nh)*xs;      // planes N-d+1 .. N
+  m.send_lo = c->phi + (size_t) g.nh*xs;                      // planes 1 .. d
+  m.recv_lo = c->phi + (size_t) (g.nh - d)*xs;                // planes 1-d .. 0
+  m.recv_hi = c->phi + (size_t) (g.nl[0] + g.nh)*xs;          // planes N+1 .. N+d
+  m.count = (size_t) d*xs;
+  ProfScope ps(c, LB200_K_HALO, st);
+  return nccl_exchange(c, st, &m, 1);
+}
+
+// after a collision: the populations moving in +x / -x of planes N / 1 and u_x of the same planes
+static int wrap_exchange_f_u(lb200_t * c, cudaStream_t st, int with_u) {
+  const Lb200Geom & g = c->g;
+  const size_t xs = (size_t) g.xs, ns = (size_t) g.nsites;
+  const int nv = c->nvel;
+  ProfScope ps(c, LB200_K_HALO, st);
+  // runs of consecutive populations with c_x = +1 (sent up) and c_x = -1 (sent down)
+  double * shi = c->shi, * slo = c->slo, * rlo = c->xlo, * rhi = c->xhi;
+  size_t nup = 0, ndn = 0;
+  for (int sign = 1; sign >= -1; sign -= 2) {
+    for (int p = 0; p < nv; ) {
+      if (c->model_h.cv[p][0] != sign) { p++; continue; }
+      int q = p;
+      while (q < nv && c->model_h.cv[q][0] == sign) q++;
+      const size_t plane = (size_t) ((sign > 0 ? g.nl[0] : 1) + g.nh - 1)*xs;
+      double * dst = (sign > 0) ? shi + nup*xs : slo + ndn*xs;
+      CUDA_TRY(cudaMemcpy2DAsync(dst, xs*sizeof(double), c->f + (size_t) p*ns + plane, ns*sizeof(double),
+				 xs*sizeof(double), q - p, cudaMemcpyDeviceToDevice, st));
+      if (sign > 0) nup += q - p; else ndn += q - p;
+      p = q;
+    }
+  }
+  if (nup != ndn) return fail(LB200_ESTATE, "velocity set not symmetric in x");
+  XMsg m[2];
+  m[0].send_hi = shi; m[0].send_lo = slo; m[0].recv_lo = rlo; m[0].recv_hi = rhi; m[0].count = nup*xs;
+  int nm = 1;
+  if (with_u) {
+    m[1].send_hi = c->u + (size_t) (g.nl[0] + g.nh - 1)*xs;   // u_x, plane N
+    m[1].send_lo = c->u + (size_t) g.nh*xs;                   // u_x, plane 1
+    m[1].recv_lo = c->u + (size_t) (g.nh - 1)*xs;             // plane 0
+    m[1].recv_hi = c->u + (size_t) (g.nl[0] + g.nh)*xs;       // plane N+1
+    m[1].count = xs;
+    nm = 2;
+  }
+  int rc = nccl_exchange(c, st, m, nm);
+  if (rc != 0) return rc;
+  // unpack: what came from the low neighbour are its c_x = +1 populations -> my plane 0; from the high
+  // neighbour its c_x = -1 populations -> my plane N+1
+  size_t kup = 0, kdn = 0;
+  for (int sign = 1; sign >= -1; sign -= 2) {
+    for (int p = 0; p < nv; ) {
+      if (c->model_h.cv[p][0] != sign) { p++; continue; }
+      int q = p;
+      while (q < nv && c->model_h.cv[q][0] == sign) q++;
+      const size_t plane = (size_t) ((sign > 0 ? 0 : g.nl[0] + 1) + g.nh - 1)*xs;
+      const double * src = (sign > 0) ? rlo + kup*xs : rhi + kdn*xs;
+      CUDA_TRY(cudaMemcpy2DAsync(c->f + (size_t) p*ns + plane, ns*sizeof(double), src, xs*sizeof(double),
+				 xs*sizeof(double), q - p, cudaMemcpyDeviceToDevice, st));
+      if (sign > 0) kup += q - p; else kdn += q - p;
+      p = q;
+    }
+  }
+  return 0;
+}
+
+static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev * sd, int nsteps) {
+  const int binary = (sd != nullptr);
+  const int remote = c->g.remote_x;
+  Lb200Geom gw = c->g;
+  gw.wrap[0] = !remote; gw.wrap[1] = 1; gw.wrap[2] = 1;
+  cudaStream_t S = c->stream, C = c->profile ? c->stream : c->comm;
+  int rc = 0;
+
+  if (remote) {
+    CUDA_TRY(cudaEventRecord(c->ev_main, S));
+    CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+    if (!c->wrap_x_valid) {
+      if (binary) {
+	if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+	CUDA_TRY(cudaEventRecord(c->ev_main, S));
+	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+	rc = wrap_exchange_phi(c, C);
+	if (rc != 0) return rc;
+      }
+      if (c->prop_pending || binary) {
+	rc = wrap_exchange_f_u(c, C, binary);
+	if (rc != 0) return rc;
+      }
+      CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+      CUDA_TRY(cudaEventRecord(c->ev_u, C));
+      CUDA_TRY(cudaEventRecord(c->ev_f, C));
+    }
+  }
+  if (c->u_state == ZERO_PENDING && binary) materialise_zero(c, c->u, &c->u_state);
+
+  for (int n = 0; n < nsteps; n++) {
+    c->force_state = ZERO_PENDING;                                       // hydro_f_zero
+    if (binary) {
+      if (remote) {
+	CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
+	CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
+      }
+      {
+	// field_halo(phi) + field_grad_compute + phi_force_calculation + phi_cahn_hilliard (hydro_u_halo inside)
+	ProfScope ps(c, LB200_K_PHI_SECTOR);
+	c->launches += c->k->phi_sector(S, gw, *sd, c->phi, c->u, c->grad, c->delsq, c->force, c->phinew);
+      }
+      c->force_state = INTERIOR_ONLY;
+      double * t = c->phi; c->phi = c->phinew; c->phinew = t;
+      if (remote) {
+	CUDA_TRY(cudaEventRecord(c->ev_main, S));
+	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+	rc = wrap_exchange_phi(c, C);                                    // overlaps the collision
+	if (rc != 0) return rc;
+	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+      }
+    }
+    c->u_state = ZERO_PENDING;                                           // hydro_u_zero
+    if (remote && c->prop_pending) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
+    if (!c->prop_pending) {
+      // first collision after an lb_memcpy / explicit propagation: in place, nothing to pull
+      rc = collide_async(c, cd, nullptr);
+    }
+    else {
+      rc = collide_async(c, cd, &gw);                                    // lb_halo + lb_propagation + lb_collide
+    }
+    if (rc != 0) return rc;
+    c->prop_pending = 1;                                                 // lb_halo; lb_propagation (lazy)
+    c->f_halo_stale = 1;
+    if (remote) {
+      CUDA_TRY(cudaEventRecord(c->ev_main, S));
+      CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+      rc = wrap_exchange_f_u(c, C, binary);
+      if (rc != 0) return rc;
+      CUDA_TRY(cudaEventRecord(c->ev_f, C));
+      CUDA_TRY(cudaEventRecord(c->ev_u, C));
+    }
+  }
+  c->phi_halo_valid = 0;
+  c->u_halo_valid = 0;
+  c->wrap_x_valid = 1;
+  if (remote) {
+    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
+    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
+    if (binary) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 
 // ---- whole time steps ---------------------------------------------------------------------------------
 // Order of operations of the reference driver (src/ludwig.c:528-860):
@@ -818,6 +1044,20 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   if (binary) symm_dev(c, sp, &sd);
   if (nsteps <= 0) return 0;
 
+  {
+    // Halo-free time steps (fully periodic lattices; binary fluid: all-fluid map, the one-sweep phi sector)
+    const int wrap_enabled = c->knob_wrap, ps_on = c->knob_phi_sector;
+    const Lb200Geom & g = c->g;
+    bool ok = wrap_enabled && g.per[0] && g.per[1] && g.per[2] && c->ndist == 1;
+    for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
+    if (binary) ok = ok && ps_on && c->map_all_fluid;
+    if (ok) return step_wrap(c, cd, binary ? &sd : nullptr, nsteps);
+  }
+  {
+    int rc2 = ensure_f_halo(c);
+    if (rc2 != 0) return rc2;
+  }
+
   // The three halo exchanges run on the comm stream, each overlapped with a compute kernel that does
   // not touch the array in flight:   phi(t+1) halo || collide(t);   f(t) and u(t) halos || grad(t+1),
   // force+CH(t+1).  Same operations on the same data as the serial order, so results are unchanged.
@@ -837,8 +1077,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
       }
       // all-fluid lattices: gradient + force + Cahn-Hilliard in one sweep (LB200_PHI_SECTOR=0 disables)
-      static const int ps_enabled = getenv("LB200_PHI_SECTOR") ? atoi(getenv("LB200_PHI_SECTOR")) : 1;
-      const bool use_ps = ps_enabled && c->map_all_fluid;
+      const bool use_ps = c->knob_phi_sector && c->map_all_fluid;
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
       if (!use_ps) {
 	ProfScope ps(c, LB200_K_GRAD);

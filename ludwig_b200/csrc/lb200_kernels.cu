@@ -112,7 +112,11 @@ __device__ __forceinline__ void relax_hydro(double * __restrict__ mode, const do
 // One thread per interior site.  PULL: read the 19 populations from the upwind neighbours of
 // fsrc (lb_propagation, src/propagation.c:153-200) and write the post-collision state to fdst,
 // so each population is read once and written once per time step.  !PULL: in-place collision.
-template <bool PULL, bool GHOST, bool HAS_FORCE, bool HAS_MAP, bool STREAM>
+// WRAP (whole time steps on periodic lattices, lb200_step): the periodic images are read straight from
+// the interior sites they mirror instead of from a halo shell filled by a separate kernel -- the halo
+// swap of lb_halo for the local dimensions costs nothing.  Dimensions with g.wrap[d] == 0 (x with
+// slab neighbours on other GPUs) still read the halo planes, which the exchange has filled.
+template <bool PULL, bool GHOST, bool HAS_FORCE, bool HAS_MAP, bool STREAM, bool WRAP>
 __global__ void __launch_bounds__(TPB_MAX)
 collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 		     const double * __restrict__ fsrc, double * __restrict__ fdst,
@@ -133,10 +137,29 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
   double u[3];
   double rho;
 
+  if (PULL && WRAP) {
+    // offset of the site one step DOWN (m) / UP (p) each axis, through the periodic boundary if need be
+    const int oxm = (g.wrap[0] && ic == 1)       ?  (g.nl[0] - 1)*g.xs : -g.xs;
+    const int oxp = (g.wrap[0] && ic == g.nl[0]) ? -(g.nl[0] - 1)*g.xs :  g.xs;
+    const int oym = (g.wrap[1] && jc == 1)       ?  (g.nl[1] - 1)*g.ys : -g.ys;
+    const int oyp = (g.wrap[1] && jc == g.nl[1]) ? -(g.nl[1] - 1)*g.ys :  g.ys;
+    const int ozm = (g.wrap[2] && kc == 1)       ?  (g.nl[2] - 1) : -1;
+    const int ozp = (g.wrap[2] && kc == g.nl[2]) ? -(g.nl[2] - 1) :  1;
 #pragma unroll
-  for (int p = 0; p < 19; p++) {
-    const int off = PULL ? (CV19[p][0]*g.xs + CV19[p][1]*g.ys + CV19[p][2]) : 0;
-    f[p] = fsrc[p*ns + (index - off)];
+    for (int p = 0; p < 19; p++) {
+      // population p arrives from the site at -c_p
+      const int off = (CV19[p][0] > 0 ? oxm : CV19[p][0] < 0 ? oxp : 0)
+	+ (CV19[p][1] > 0 ? oym : CV19[p][1] < 0 ? oyp : 0)
+	+ (CV19[p][2] > 0 ? ozm : CV19[p][2] < 0 ? ozp : 0);
+      f[p] = fsrc[p*ns + (index + off)];
+    }
+  }
+  else {
+#pragma unroll
+    for (int p = 0; p < 19; p++) {
+      const int off = PULL ? (CV19[p][0]*g.xs + CV19[p][1]*g.ys + CV19[p][2]) : 0;
+      f[p] = fsrc[p*ns + (index - off)];
+    }
   }
 
   if (HAS_MAP) {
@@ -175,7 +198,7 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 
 // Generic velocity set (D3Q15, D3Q27; also D3Q19 with the model matrices instead of the coded
 // constants): reference src/collision.c:335-342, 541-551.
-template <bool PULL>
+template <bool PULL, bool WRAP>
 __global__ void __launch_bounds__(TPB_MAX)
 collide_generic_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 		       const Lb200ModelDev * __restrict__ md,
@@ -198,9 +221,25 @@ collide_generic_kernel(const Lb200Geom g, const Lb200CollideDev cp,
   double u[3];
   double rho;
 
-  for (int p = 0; p < nvel; p++) {
-    const int off = PULL ? (md->cv[p][0]*g.xs + md->cv[p][1]*g.ys + md->cv[p][2]) : 0;
-    f[p] = fsrc[p*ns + (index - off)];
+  if (PULL && WRAP) {
+    int o[3][3];          // o[axis][1 - c]: offset of the site at -c along the axis
+    o[0][0] = (g.wrap[0] && ic == 1)       ?  (g.nl[0] - 1)*g.xs : -g.xs;
+    o[0][2] = (g.wrap[0] && ic == g.nl[0]) ? -(g.nl[0] - 1)*g.xs :  g.xs;
+    o[1][0] = (g.wrap[1] && jc == 1)       ?  (g.nl[1] - 1)*g.ys : -g.ys;
+    o[1][2] = (g.wrap[1] && jc == g.nl[1]) ? -(g.nl[1] - 1)*g.ys :  g.ys;
+    o[2][0] = (g.wrap[2] && kc == 1)       ?  (g.nl[2] - 1) : -1;
+    o[2][2] = (g.wrap[2] && kc == g.nl[2]) ? -(g.nl[2] - 1) :  1;
+    o[0][1] = o[1][1] = o[2][1] = 0;
+    for (int p = 0; p < nvel; p++) {
+      const int off = o[0][1 - md->cv[p][0]] + o[1][1 - md->cv[p][1]] + o[2][1 - md->cv[p][2]];
+      f[p] = fsrc[p*ns + (index + off)];
+    }
+  }
+  else {
+    for (int p = 0; p < nvel; p++) {
+      const int off = PULL ? (md->cv[p][0]*g.xs + md->cv[p][1]*g.ys + md->cv[p][2]) : 0;
+      f[p] = fsrc[p*ns + (index - off)];
+    }
   }
 
   if (status != nullptr && status[index] != 0) {
@@ -245,8 +284,10 @@ int launch_collide(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev &
 
   if (nvel == 19 && md == nullptr) {
     static const int stream_stores = tuned_flag("LB200_STCS", 1);
-#define LB200_GO(P, G, F, M) do { if (stream_stores && P) collide_d3q19_kernel<P, G, F, M, true><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u); \
-    else collide_d3q19_kernel<P, G, F, M, false><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u); } while (0)
+    const bool wrap = pull && (g.wrap[0] || g.wrap[1] || g.wrap[2]);
+#define LB200_GO(P, G, F, M) do { if (wrap && P) collide_d3q19_kernel<P, G, F, M, true, P><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u); \
+    else if (stream_stores && P) collide_d3q19_kernel<P, G, F, M, true, false><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u); \
+    else collide_d3q19_kernel<P, G, F, M, false, false><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u); } while (0)
 #define LB200_SEL_M(P, G, F) do { if (status) LB200_GO(P, G, F, true); else LB200_GO(P, G, F, false); } while (0)
 #define LB200_SEL_F(P, G) do { if (force) LB200_SEL_M(P, G, true); else LB200_SEL_M(P, G, false); } while (0)
 #define LB200_SEL_G(P) do { if (cp.ghost) LB200_SEL_F(P, true); else LB200_SEL_F(P, false); } while (0)
@@ -257,8 +298,10 @@ int launch_collide(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev &
 #undef LB200_SEL_G
   }
   else {
-    if (pull) collide_generic_kernel<true><<<grd, blk, 0, st>>>(g, cp, md, fsrc, fdst, force, status, rho, u);
-    else      collide_generic_kernel<false><<<grd, blk, 0, st>>>(g, cp, md, fsrc, fdst, force, status, rho, u);
+    const bool wrap = pull && (g.wrap[0] || g.wrap[1] || g.wrap[2]);
+    if (wrap)      collide_generic_kernel<true, true><<<grd, blk, 0, st>>>(g, cp, md, fsrc, fdst, force, status, rho, u);
+    else if (pull) collide_generic_kernel<true, false><<<grd, blk, 0, st>>>(g, cp, md, fsrc, fdst, force, status, rho, u);
+    else           collide_generic_kernel<false, false><<<grd, blk, 0, st>>>(g, cp, md, fsrc, fdst, force, status, rho, u);
   }
   return 1;
 }
@@ -785,13 +828,18 @@ constexpr int PS_TY = PS_BY - 2;
 constexpr int PS_PZ = PS_BZ + 2;          // phi tile: block + one more ring
 constexpr int PS_PY = PS_BY + 2;
 constexpr int PS_PN = PS_PZ*PS_PY;        // 612
-constexpr int PS_XC = 32;                 // planes per x chunk
 
 struct PsShared {
   double phi[4][PS_PN];                   // ring of phi planes
   double g[2][5][PS_NT];                  // p0, gx, gy, gz, mu of plane i (double buffered)
   double u[2][2][PS_NT];                  // u_y, u_z of plane i
 };
+
+// coordinate of the site that holds the value of (possibly halo) coordinate j: itself, or, when the
+// dimension is read through the periodic boundary (g.wrap), the interior site it is the image of
+__device__ __forceinline__ int ps_wrap(int j, int n, int w) {
+  return w ? (j < 1 ? j + n : (j > n ? j - n : j)) : j;
+}
 
 __device__ __forceinline__ void ps_pcol(const Lb200SymmDev & sp, int B, double p0, double gx, double gy,
 					double gz, double p[3]) {
@@ -804,7 +852,7 @@ __device__ __forceinline__ void ps_pcol(const Lb200SymmDev & sp, int B, double p
 
 template <int ORDER>
 __global__ void __launch_bounds__(PS_NT, 1)
-phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __restrict__ phi,
+phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc, const double * __restrict__ phi,
 		  const double * __restrict__ u, double * __restrict__ grad,
 		  double * __restrict__ delsq, double * __restrict__ force,
 		  double * __restrict__ phinew) {
@@ -817,8 +865,8 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __res
   const int kbase = blockIdx.x*PS_TZ;              // thread column (j,k) = (jbase + ty, kbase + tz)
   const int jbase = blockIdx.y*PS_TY;
   const int kc = kbase + tz, jc = jbase + ty;
-  const int i0 = 1 + blockIdx.z*PS_XC;
-  const int i1 = min(i0 + PS_XC - 1, g.nl[0]);
+  const int i0 = 1 + blockIdx.z*xc;
+  const int i1 = min(i0 + xc - 1, g.nl[0]);
   const int nh = g.nh;
   const size_t ns = (size_t) g.nsites;
   const int xs = g.xs, ys = g.ys;
@@ -830,15 +878,18 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __res
     && ((tz >= 1 && tz <= PS_TZ) || (tz == 0 && kc == 0));
 
   // clamp the column used for loads so that inactive threads stay inside the allocation
-  const int jl = min(jc, g.nl[1] + 1), kl = min(kc, g.nl[2] + 1);
+  const int jl = ps_wrap(min(jc, g.nl[1] + 1), g.nl[1], g.wrap[1]);
+  const int kl = ps_wrap(min(kc, g.nl[2] + 1), g.nl[2], g.wrap[2]);
   const int col = (jl + nh - 1)*ys + (kl + nh - 1);       // + (i + nh - 1)*xs
 
   // cooperative phi plane load: element e of the (PS_PY x PS_PZ) tile <-> (jbase-1+r, kbase-1+c)
   const int e0 = tid, e1 = tid + PS_NT;
   const int r0 = e0/PS_PZ, c0 = e0%PS_PZ;
   const int r1 = e1/PS_PZ, c1 = e1%PS_PZ;
-  const int pj0 = min(jbase - 1 + r0, g.nl[1] + nh), pk0 = min(kbase - 1 + c0, g.nl[2] + nh);
-  const int pj1 = min(jbase - 1 + r1, g.nl[1] + nh), pk1 = min(kbase - 1 + c1, g.nl[2] + nh);
+  const int pj0 = ps_wrap(min(jbase - 1 + r0, g.nl[1] + nh), g.nl[1], g.wrap[1]);
+  const int pk0 = ps_wrap(min(kbase - 1 + c0, g.nl[2] + nh), g.nl[2], g.wrap[2]);
+  const int pj1 = ps_wrap(min(jbase - 1 + r1, g.nl[1] + nh), g.nl[1], g.wrap[1]);
+  const int pk1 = ps_wrap(min(kbase - 1 + c1, g.nl[2] + nh), g.nl[2], g.wrap[2]);
   const int pcol0 = (pj0 + nh - 1)*ys + (pk0 + nh - 1);
   const int pcol1 = (pj1 + nh - 1)*ys + (pk1 + nh - 1);
   const bool has_e1 = (e1 < PS_PN);
@@ -849,12 +900,12 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __res
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     const int ip = istart + d;
-    const int xo = (ip + nh - 1)*xs;
+    const int xo = (ps_wrap(ip, g.nl[0], g.wrap[0]) + nh - 1)*xs;
     sm.phi[(ip + 4) & 3][e0] = phi[xo + pcol0];
     if (has_e1) sm.phi[(ip + 4) & 3][e1] = phi[xo + pcol1];
   }
-  double uxc = u[0*ns + (istart + nh - 1)*xs + col];
-  double uxp = u[0*ns + (istart + 1 + nh - 1)*xs + col];
+  double uxc = u[0*ns + (ps_wrap(istart, g.nl[0], g.wrap[0]) + nh - 1)*xs + col];
+  double uxp = u[0*ns + (ps_wrap(istart + 1, g.nl[0], g.wrap[0]) + nh - 1)*xs + col];
   double uxm = 0.0;
   __syncthreads();
 
@@ -870,12 +921,14 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __res
     // ---- 1. prefetch for the next plane-steps (consumed after the arithmetic below) ----
     double pf0 = 0.0, pf1 = 0.0, uxn = 0.0, uyn = 0.0, uzn = 0.0;
     if (i < i1) {
-      const int xo3 = (i + 3 + nh - 1)*xs;
+      const int xo3 = (ps_wrap(i + 3, g.nl[0], g.wrap[0]) + nh - 1)*xs;
+      const int xo2 = (ps_wrap(i + 2, g.nl[0], g.wrap[0]) + nh - 1)*xs;
+      const int xo1 = (ps_wrap(i + 1, g.nl[0], g.wrap[0]) + nh - 1)*xs;
       pf0 = phi[xo3 + pcol0];
       if (has_e1) pf1 = phi[xo3 + pcol1];
-      uxn = u[0*ns + (i + 2 + nh - 1)*xs + col];
-      uyn = u[1*ns + (i + 1 + nh - 1)*xs + col];
-      uzn = u[2*ns + (i + 1 + nh - 1)*xs + col];
+      uxn = u[0*ns + xo2 + col];
+      uyn = u[1*ns + xo1 + col];
+      uzn = u[2*ns + xo1 + col];
     }
 
     // ---- 2. gradient of plane i+1 at the own column, from phi planes i, i+1, i+2 ----
@@ -1020,20 +1073,291 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __res
   }
 }
 
+#ifndef LB200_STRICT
+// ---------------------------------------------------------------------------------------------
+// The same sweep for the FAST arithmetic mode (results within the stated FP64 tolerance of the
+// reference, not bit-identical): the exact kernel above is bound by instruction issue (ncu: 51 %
+// issue-active, 46 % FP64 pipe at 25 % occupancy, ~300 FP64 operations per site), so this version cuts the operation
+// count ~3x by re-associating, which the reference's summation order forbids in strict mode:
+//  * 27-point stencil from per-plane partial sums: B = 3x3 box sum, Cy / Cz = central differences of
+//    the row / column sums, kept in registers for three planes:
+//        d_x = (B(i+1) - B(i-1))/18,  d_y = (Cy(i-1) + Cy(i) + Cy(i+1))/18,  d_z likewise,
+//        delsq = (B(i-1) + B(i) + B(i+1) - 27 phi)/9                      (26 operations, 9 loads);
+//  * every site forms its stress tensor P once and publishes the five entries its y/z neighbours
+//    need; F_a = 1/2 sum_b [P_ab(-b) - P_ab(+b)]  (the centre-site terms of the reference's face
+//    averages cancel);
+//  * every face flux is computed once, by the site on its low side, and shared with the site on its
+//    high side (x: carried in registers along the march; y, z: through shared memory), so the phi
+//    update of plane n-1 is completed one plane-step after its fluxes.
+// One __syncthreads per plane; all shared buffers are double buffered.
+// ---------------------------------------------------------------------------------------------
+
+struct PfShared {
+  double phi[4][PS_PN];                   // ring of phi planes
+  double g[2][6][PS_NT];                  // Pxy, Pyy, Pyz, Pxz, Pzz, mu of a plane
+  double u[2][2][PS_NT];                  // u_y, u_z
+  double fl[2][2][PS_NT];                 // y and z face fluxes (face between the site and site+1)
+};
+
+// partial sums of one phi plane at the own column: B, Cy, Cz
+__device__ __forceinline__ void pf_plane_sums(const double * __restrict__ q, int pc, double & B,
+					      double & Cy, double & Cz) {
+  const double mm = q[pc-PS_PZ-1], m0 = q[pc-PS_PZ], mp = q[pc-PS_PZ+1];
+  const double zm = q[pc      -1], z0 = q[pc      ], zp = q[pc      +1];
+  const double pm = q[pc+PS_PZ-1], p0 = q[pc+PS_PZ], pp = q[pc+PS_PZ+1];
+  const double am = (mm + m0) + mp;
+  const double a0 = (zm + z0) + zp;
+  const double ap = (pm + p0) + pp;
+  B  = (am + a0) + ap;
+  Cy = ap - am;
+  Cz = ((mp - mm) + (zp - zm)) + (pp - pm);
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(PS_NT, 1)
+phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
+		       const double * __restrict__ phi, const double * __restrict__ u,
+		       double * __restrict__ grad, double * __restrict__ delsq,
+		       double * __restrict__ force, double * __restrict__ phinew) {
+
+  extern __shared__ __align__(16) unsigned char ps_smem_raw[];
+  PfShared & sm = *reinterpret_cast<PfShared *>(ps_smem_raw);
+
+  const int tz = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty*PS_BZ + tz;
+  const int kbase = blockIdx.x*PS_TZ;              // thread column (j,k) = (jbase + ty, kbase + tz)
+  const int jbase = blockIdx.y*PS_TY;
+  const int kc = kbase + tz, jc = jbase + ty;
+  const int i0 = 1 + blockIdx.z*xc;
+  const int i1 = min(i0 + xc - 1, g.nl[0]);
+  const int nh = g.nh;
+  const size_t ns = (size_t) g.nsites;
+  const int xs = g.xs, ys = g.ys;
+  const int wx = g.wrap[0], nlx = g.nl[0];
+
+  const bool valid_g = (jc <= g.nl[1] + 1) && (kc <= g.nl[2] + 1);
+  const bool inner = (ty >= 1 && ty <= PS_TY && tz >= 1 && tz <= PS_TZ);
+  const bool out_site = inner && jc <= g.nl[1] && kc <= g.nl[2];
+  const bool face_site = (ty <= PS_TY && tz <= PS_TZ);      // owns the faces towards j+1 and k+1
+  const bool own_g = valid_g && ((ty >= 1 && ty <= PS_TY) || (ty == 0 && jc == 0))
+    && ((tz >= 1 && tz <= PS_TZ) || (tz == 0 && kc == 0));
+
+  // column used for loads: clamped inside the allocation, through the periodic boundary if wrapping
+  const int jl = ps_wrap(min(jc, g.nl[1] + 1), g.nl[1], g.wrap[1]);
+  const int kl = ps_wrap(min(kc, g.nl[2] + 1), g.nl[2], g.wrap[2]);
+  const int col = (jl + nh - 1)*ys + (kl + nh - 1);
+  const int scol = (jc + nh - 1)*ys + (kc + nh - 1);       // column of the stores (never wrapped)
+
+  // cooperative phi plane load: element e of the (PS_PY x PS_PZ) tile <-> (jbase-1+r, kbase-1+c)
+  const int e0 = tid, e1 = tid + PS_NT;
+  const int r0 = e0/PS_PZ, c0 = e0%PS_PZ;
+  const int r1 = e1/PS_PZ, c1 = e1%PS_PZ;
+  const int pj0 = ps_wrap(min(jbase - 1 + r0, g.nl[1] + nh), g.nl[1], g.wrap[1]);
+  const int pk0 = ps_wrap(min(kbase - 1 + c0, g.nl[2] + nh), g.nl[2], g.wrap[2]);
+  const int pj1 = ps_wrap(min(jbase - 1 + r1, g.nl[1] + nh), g.nl[1], g.wrap[1]);
+  const int pk1 = ps_wrap(min(kbase - 1 + c1, g.nl[2] + nh), g.nl[2], g.wrap[2]);
+  const int pcol0 = (pj0 + nh - 1)*ys + (pk0 + nh - 1);
+  const int pcol1 = (pj1 + nh - 1)*ys + (pk1 + nh - 1);
+  const bool has_e1 = (e1 < PS_PN);
+
+  const int istart = i0 - 2;
+  const int pc = (ty + 1)*PS_PZ + (tz + 1);        // own position in the phi tile
+  const int typ = tid + PS_BZ, tym = tid - PS_BZ, tzp = tid + 1, tzm = tid - 1;
+
+  // prologue: planes istart, istart+1, istart+2 into the ring; u_y, u_z of plane i0 - 1 are not needed
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int ip = istart + d;
+    const int xo = (ps_wrap(ip, nlx, wx) + nh - 1)*xs;
+    sm.phi[(ip + 4) & 3][e0] = phi[xo + pcol0];
+    if (has_e1) sm.phi[(ip + 4) & 3][e1] = phi[xo + pcol1];
+  }
+  double uxc = 0.0;                                                          // u_x(n)
+  double uxp = u[0*ns + (ps_wrap(istart + 1, nlx, wx) + nh - 1)*xs + col];   // u_x(n+1)
+  __syncthreads();
+
+  // plane sums of planes n and n+1 (own column)
+  double Bm, Cym, Czm, Bc, Cyc, Czc;
+  pf_plane_sums(sm.phi[(istart + 4) & 3], pc, Bm, Cym, Czm);
+  pf_plane_sums(sm.phi[(istart + 5) & 3], pc, Bc, Cyc, Czc);
+
+  // own-column history
+  double gm_xx = 0.0, gm_xy = 0.0, gm_xz = 0.0;        // P_xa of plane n-1
+  double gc_xx = 0.0, gc_xy = 0.0, gc_xz = 0.0;        // P_xa of plane n
+  double gc_mu = 0.0;                                  // mu of plane n
+  double phim1 = 0.0;                                  // phi(n-1)
+  double fxm1 = 0.0, fxm2 = 0.0;                       // x-face fluxes (n-1 | n), (n-2 | n-1)
+  double fy_prev = 0.0, fz_prev = 0.0;                 // own y / z face fluxes of plane n-1
+
+  const double M = sp.mobility;
+  const double kappa = sp.kappa;
+  const double mg0 = M*sp.gm[0], mg1 = M*sp.gm[1], mg2 = M*sp.gm[2];
+  const double r9 = (1.0/9.0), r18 = 0.5*(1.0/9.0);
+
+  for (int n = istart; n <= i1 + 1; n++) {
+
+    // ---- 1. prefetch (consumed at the end of this plane-step) ----
+    double pf0 = 0.0, pf1 = 0.0, uxn = 0.0, uyn = 0.0, uzn = 0.0;
+    if (n < i1) {
+      const int xo3 = (ps_wrap(n + 3, nlx, wx) + nh - 1)*xs;
+      const int xo2 = (ps_wrap(n + 2, nlx, wx) + nh - 1)*xs;
+      const int xo1 = (ps_wrap(n + 1, nlx, wx) + nh - 1)*xs;
+      pf0 = phi[xo3 + pcol0];
+      if (has_e1) pf1 = phi[xo3 + pcol1];
+      uxn = u[0*ns + xo2 + col];
+      uyn = u[1*ns + xo1 + col];
+      uzn = u[2*ns + xo1 + col];
+    }
+
+    const double * __restrict__ fm = sm.phi[(n + 4) & 3];
+    const double * __restrict__ fc = sm.phi[(n + 5) & 3];
+    const double * __restrict__ fp = sm.phi[(n + 6) & 3];
+
+    // ---- 2. gradient, chemical potential and stress of plane n+1 at the own column ----
+    double gp_xx = 0.0, gp_xy = 0.0, gp_xz = 0.0, gp_mu = 0.0;
+    double Bp = 0.0, Cyp = 0.0, Czp = 0.0;
+    if (n <= i1) {
+      pf_plane_sums(fp, pc, Bp, Cyp, Czp);
+      const double ph = fc[pc];
+      const double gx = r18*(Bp - Bm);
+      const double gy = r18*((Cym + Cyc) + Cyp);
+      const double gz = r18*((Czm + Czc) + Czp);
+      const double dsq = r9*(((Bm + Bc) + Bp) - 27.0*ph);
+
+      const int ig = n + 1;
+      const bool own_x = (ig >= i0 && ig <= i1) || (ig == 0 && i0 == 1) || (ig == nlx + 1 && i1 == nlx);
+      if (own_g && own_x) {
+	const int sidx = (ig + nh - 1)*xs + scol;
+	grad[0*ns + sidx] = gx;
+	grad[1*ns + sidx] = gy;
+	grad[2*ns + sidx] = gz;
+	delsq[sidx] = dsq;
+      }
+
+      const double ph2 = ph*ph;
+      const double p0 = ph2*(0.5*sp.a + 0.75*sp.b*ph2) - kappa*(ph*dsq + 0.5*((gx*gx + gy*gy) + gz*gz));
+      gp_mu = ph*(sp.a + sp.b*ph2) - kappa*dsq;
+      const double kgx = kappa*gx, kgy = kappa*gy, kgz = kappa*gz;
+      gp_xx = p0 + kgx*gx; gp_xy = kgx*gy; gp_xz = kgx*gz;
+      double (* gb)[PS_NT] = sm.g[(n + 1) & 1];
+      gb[0][tid] = gp_xy;
+      gb[1][tid] = p0 + kgy*gy;
+      gb[2][tid] = kgy*gz;
+      gb[3][tid] = gp_xz;
+      gb[4][tid] = p0 + kgz*gz;
+      gb[5][tid] = gp_mu;
+    }
+
+    // ---- 3. plane n: x-face flux (n | n+1), force, y/z face fluxes ----
+    const double ph_c = fm[pc];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (n >= i0 - 1 && n <= i1 && face_site) {
+      fx = adv_face<ORDER, false>(uxc, uxp, phim1, ph_c, fc[pc], fp[pc]) - M*(gp_mu - gc_mu) - mg0;
+
+      if (n >= i0) {
+	const double (* gb)[PS_NT] = sm.g[n & 1];
+	const double (* ub)[PS_NT] = sm.u[n & 1];
+
+	if (out_site) {
+	  const int s = (n + nh - 1)*xs + scol;
+	  force[0*ns + s] = 0.5*(((gm_xx - gp_xx) + (gb[0][tym] - gb[0][typ])) + (gb[3][tzm] - gb[3][tzp]));
+	  force[1*ns + s] = 0.5*(((gm_xy - gp_xy) + (gb[1][tym] - gb[1][typ])) + (gb[2][tzm] - gb[2][tzp]));
+	  force[2*ns + s] = 0.5*(((gm_xz - gp_xz) + (gb[2][tym] - gb[2][typ])) + (gb[4][tzm] - gb[4][tzp]));
+	}
+
+	double ph_yp2 = 0.0, ph_zp2 = 0.0;
+	if (ORDER == 3) { ph_yp2 = fm[pc + 2*PS_PZ]; ph_zp2 = fm[pc + 2]; }
+	fy = adv_face<ORDER, false>(ub[0][tid], ub[0][typ], fm[pc - PS_PZ], ph_c, fm[pc + PS_PZ], ph_yp2)
+	  - M*(gb[5][typ] - gc_mu) - mg1;
+	fz = adv_face<ORDER, false>(ub[1][tid], ub[1][tzp], fm[pc - 1], ph_c, fm[pc + 1], ph_zp2)
+	  - M*(gb[5][tzp] - gc_mu) - mg2;
+	sm.fl[n & 1][0][tid] = fy;
+	sm.fl[n & 1][1][tid] = fz;
+      }
+    }
+
+    // ---- 4. phi update of plane n-1, whose y/z face fluxes were published one plane-step ago ----
+    if (n >= i0 + 1 && out_site) {
+      const double (* fl)[PS_NT] = sm.fl[(n - 1) & 1];
+      const int s = (n - 1 + nh - 1)*xs + scol;
+      phinew[s] = phim1 - (((fxm1 - fxm2) + (fy_prev - fl[0][tym])) + sp.wz*(fz_prev - fl[1][tzm]));
+    }
+
+    // ---- 5. rotate the own-column history, publish the prefetched plane ----
+    Bm = Bc; Cym = Cyc; Czm = Czc;
+    Bc = Bp; Cyc = Cyp; Czc = Czp;
+    gm_xx = gc_xx; gm_xy = gc_xy; gm_xz = gc_xz;
+    gc_xx = gp_xx; gc_xy = gp_xy; gc_xz = gp_xz;
+    gc_mu = gp_mu;
+    phim1 = ph_c;
+    fxm2 = fxm1; fxm1 = fx;
+    fy_prev = fy; fz_prev = fz;
+    uxc = uxp; uxp = uxn;
+    if (n < i1) {
+      sm.phi[(n + 7) & 3][e0] = pf0;                 // plane n+3 -> slot of plane n-1
+      if (has_e1) sm.phi[(n + 7) & 3][e1] = pf1;
+      sm.u[(n + 1) & 1][0][tid] = uyn;
+      sm.u[(n + 1) & 1][1][tid] = uzn;
+    }
+    __syncthreads();
+  }
+}
+#endif
+
+// Planes per x chunk: every chunk pays PS_XPRO extra plane-steps of pipeline fill, and the chunks are
+// scheduled in rounds of (SMs x resident CTAs), so pick the chunk count that minimises
+// rounds x (planes per chunk + fill).  256^3 on 148 SMs: 6 chunks of 43 planes = 1026 CTAs = 6.9 rounds.
+static int ps_pick_xc(const void * kernel, size_t smem, int tiles, int nx, int fill) {
+  static int nsm = 0;
+  if (nsm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+  }
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PS_NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const long long slots = (long long) nsm*per_sm;
+  const char * e = getenv("LB200_PS_XC");
+  if (e && atoi(e) > 0) return atoi(e);
+  long long best = -1;
+  int best_xc = nx;
+  for (int nchunk = 1; nchunk <= nx; nchunk++) {
+    const int xc = (nx + nchunk - 1)/nchunk;
+    if (xc < 8 && nchunk > 1) break;
+    const long long rounds = ((long long) tiles*((nx + xc - 1)/xc) + slots - 1)/slots;
+    const long long cost = rounds*(xc + fill);
+    if (best < 0 || cost < best) { best = cost; best_xc = xc; }
+  }
+  return best_xc;
+}
+
 int launch_phi_sector(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const double * phi,
 		      const double * u, double * grad, double * delsq, double * force, double * phinew) {
+  dim3 blk(PS_BZ, PS_BY, 1);
+  const int gz = (g.nl[2] + 1 + PS_TZ - 1)/PS_TZ, gy = (g.nl[1] + 1 + PS_TY - 1)/PS_TY;
+#ifdef LB200_STRICT
+#define LB200_PS_KERNEL phi_sector_kernel
+  const size_t smem = sizeof(PsShared);
+  const int fill = 3;
+#else
+#define LB200_PS_KERNEL phi_sector_fast_kernel
+  const size_t smem = sizeof(PfShared);
+  const int fill = 4;
+#endif
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(phi_sector_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(PsShared));
-    cudaFuncSetAttribute(phi_sector_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(PsShared));
-    cudaFuncSetAttribute(phi_sector_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(PsShared));
+    cudaFuncSetAttribute(LB200_PS_KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(LB200_PS_KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(LB200_PS_KERNEL<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     configured = true;
   }
-  dim3 blk(PS_BZ, PS_BY, 1);
-  dim3 grd((g.nl[2] + 1 + PS_TZ - 1)/PS_TZ, (g.nl[1] + 1 + PS_TY - 1)/PS_TY, (g.nl[0] + PS_XC - 1)/PS_XC);
-  if (sp.order == 1)      phi_sector_kernel<1><<<grd, blk, sizeof(PsShared), st>>>(g, sp, phi, u, grad, delsq, force, phinew);
-  else if (sp.order == 2) phi_sector_kernel<2><<<grd, blk, sizeof(PsShared), st>>>(g, sp, phi, u, grad, delsq, force, phinew);
-  else                    phi_sector_kernel<3><<<grd, blk, sizeof(PsShared), st>>>(g, sp, phi, u, grad, delsq, force, phinew);
+  const int xc = ps_pick_xc((const void *) LB200_PS_KERNEL<3>, smem, gz*gy, g.nl[0], fill);
+  dim3 grd(gz, gy, (g.nl[0] + xc - 1)/xc);
+  if (sp.order == 1)      LB200_PS_KERNEL<1><<<grd, blk, smem, st>>>(g, sp, xc, phi, u, grad, delsq, force, phinew);
+  else if (sp.order == 2) LB200_PS_KERNEL<2><<<grd, blk, smem, st>>>(g, sp, xc, phi, u, grad, delsq, force, phinew);
+  else                    LB200_PS_KERNEL<3><<<grd, blk, smem, st>>>(g, sp, xc, phi, u, grad, delsq, force, phinew);
+#undef LB200_PS_KERNEL
   return 1;
 }
 

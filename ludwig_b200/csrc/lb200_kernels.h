@@ -14,6 +14,7 @@ struct Lb200Geom {
   int has_lo;       // an x-neighbour exists on the low / high side (periodic or interior slab)
   int has_hi;
   int remote_x;     // 1: x-neighbours are other GPUs, their planes arrive in staging buffers
+  int wrap[3];      // 1: kernels read the periodic images of this dimension from the interior (no halo needed)
 };
 
 struct Lb200CollideDev {

@@ -186,12 +186,27 @@ def test_cahn_hilliard(order, math, solid):
         assert close_fast(got, rphi)
 
 
-@pytest.mark.parametrize("nlocal", [(16, 16, 16), (8, 12, 36)])
+# execution paths of a whole time step: the individual reference-named entry points; lb200_step halo-free
+# (default); lb200_step with the reference's three halo swaps; the same without the one-sweep phi sector
+STEP_PATHS = {"api": None, "fused": (1, 1), "fused_halos": (0, 1), "fused_halos_split": (0, 0)}
+
+
+def run_steps(sim, path, cp, sp, nsteps):
+    if STEP_PATHS[path] is None:
+        sim.step_api(cp, sp, nsteps)
+    else:
+        sim.set_knob(lb.KNOB_WRAP, STEP_PATHS[path][0])
+        sim.set_knob(lb.KNOB_PHI_SECTOR, STEP_PATHS[path][1])
+        sim.step(cp, sp, nsteps)
+
+
+@pytest.mark.parametrize("nlocal", [(16, 16, 16), (8, 12, 36), (4, 5, 67), (33, 4, 4)])
 @pytest.mark.parametrize("order", [1, 3])
-@pytest.mark.parametrize("path", ["api", "fused"])
+@pytest.mark.parametrize("path", list(STEP_PATHS))
 def test_binary_steps_strict_bit_exact(nlocal, order, path):
     """N whole binary-fluid time steps: CUDA (strict) == oracle, bit for bit, on f, phi, u, rho,
-    force, grad, delsq -- through the individual entry points and through the fused lb200_step."""
+    force, grad, delsq -- through the individual entry points and through the fused lb200_step
+    (halo-free and with halo swaps)."""
     nsteps = 6
     orc = Oracle(nlocal, nhalo=2)
     st = seeded_state(orc)
@@ -201,7 +216,7 @@ def test_binary_steps_strict_bit_exact(nlocal, order, path):
     with make_sim(orc, st) as sim:
         cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA, force=fg)
         sp = lb.SymmParam.make(adv_order=order, **BINARY)
-        (sim.step_api if path == "api" else sim.step)(cp, sp, nsteps)
+        run_steps(sim, path, cp, sp, nsteps)
         got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO),
                                           ("force", lb.FORCE), ("grad", lb.GRAD), ("delsq", lb.DELSQ))}
     orc.step(cpo, spo, 1, nsteps, st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
@@ -210,29 +225,40 @@ def test_binary_steps_strict_bit_exact(nlocal, order, path):
 
 
 @pytest.mark.parametrize("nrelax", [lb.RELAX_M10, lb.RELAX_TRT])
-def test_binary_steps_fast_tolerance(nrelax):
+@pytest.mark.parametrize("path", list(STEP_PATHS))
+@pytest.mark.parametrize("nlocal,order", [((16, 16, 16), 3), ((9, 31, 45), 3), ((20, 6, 8), 1), ((12, 12, 12), 2)])
+def test_binary_steps_fast_tolerance(nrelax, path, nlocal, order):
+    """Fast mode (FMA contraction; in the one-sweep phi sector also re-associated stencil sums, shared
+    face fluxes and the cancelled centre terms of the stress divergence): within 1e-12 relative of the
+    oracle after 20 steps on every field, intermediate ones (force, grad, delsq) included."""
     nsteps = 20
-    orc = Oracle((16, 16, 16), nhalo=2)
+    orc = Oracle(nlocal, nhalo=2)
     st = seeded_state(orc)
-    cpo = orc.collide_param(nrelax, 1.0, ETA)
-    spo = orc.symm_param(adv_order=3, **BINARY)
+    fg = (1e-6, -2e-6, 5e-7)
+    gm = (1e-5, -2e-5, 3e-5)
+    cpo = orc.collide_param(nrelax, 1.0, ETA, force=fg)
+    spo = orc.symm_param(adv_order=order, gradmu=gm, **BINARY)
     with make_sim(orc, st, math=lb.MATH_FAST) as sim:
-        sim.step(lb.CollideParam.make(nrelax, 1.0, ETA), lb.SymmParam.make(adv_order=3, **BINARY), nsteps)
-        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO))}
+        run_steps(sim, path, lb.CollideParam.make(nrelax, 1.0, ETA, force=fg),
+                  lb.SymmParam.make(adv_order=order, gradmu=gm, **BINARY), nsteps)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO),
+                                          ("force", lb.FORCE), ("grad", lb.GRAD), ("delsq", lb.DELSQ))}
     orc.step(cpo, spo, 1, nsteps, st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
     for k in got:
-        assert close_fast(orc.interior(got[k]), orc.interior(st[k])), k
+        assert close_fast(orc.interior(got[k]), orc.interior(st[k])), (k, rel_err(orc.interior(got[k]), orc.interior(st[k])))
 
 
 @pytest.mark.parametrize("nvel", [19, 15, 27])
 @pytest.mark.parametrize("reduced", [0, 1])
-def test_single_fluid_steps_strict_bit_exact(nvel, reduced):
+@pytest.mark.parametrize("wrap", [1, 0])
+def test_single_fluid_steps_strict_bit_exact(nvel, reduced, wrap):
     nsteps = 8
     orc = Oracle((12, 10, 34), nhalo=1, nvel=nvel)
     st = seeded_state(orc, binary=False)
     fg = (1e-6, 2e-6, 3e-6)
     cpo = orc.collide_param(lb.RELAX_BGK, 1.0, 0.1, force=fg)
     with make_sim(orc, st, have_phi=False, halo=lb.HALO_REDUCED if reduced else lb.HALO_FULL) as sim:
+        sim.set_knob(lb.KNOB_WRAP, wrap)
         sim.step(lb.CollideParam.make(lb.RELAX_BGK, 1.0, 0.1, force=fg), None, nsteps)
         gf, gu, gr = sim.get(lb.F), sim.get(lb.U), sim.get(lb.RHO)
     orc.step(cpo, None, 0, nsteps, st["f"], None, st["u"], st["rho"], st["force"], None, None, halo_reduced=reduced)
