@@ -1076,9 +1076,10 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc, const double
 #ifndef LB200_STRICT
 // ---------------------------------------------------------------------------------------------
 // The same sweep for the FAST arithmetic mode (results within the stated FP64 tolerance of the
-// reference, not bit-identical): the exact kernel above is bound by instruction issue (ncu: 51 %
-// issue-active, 46 % FP64 pipe at 25 % occupancy, ~300 FP64 operations per site), so this version cuts the operation
-// count ~3x by re-associating, which the reference's summation order forbids in strict mode:
+// reference, not bit-identical).  The exact kernel above is bound by instruction issue (ncu: 51 %
+// issue-active, 46 % FP64 pipe at 25 % occupancy, ~300 FP64 operations and ~670 instructions per
+// site), so this version cuts the operation count, which the reference's summation order forbids in
+// strict mode:
 //  * 27-point stencil from per-plane partial sums: B = 3x3 box sum, Cy / Cz = central differences of
 //    the row / column sums, kept in registers for three planes:
 //        d_x = (B(i+1) - B(i-1))/18,  d_y = (Cy(i-1) + Cy(i) + Cy(i+1))/18,  d_z likewise,
@@ -1088,15 +1089,48 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc, const double
 //    averages cancel);
 //  * every face flux is computed once, by the site on its low side, and shared with the site on its
 //    high side (x: carried in registers along the march; y, z: through shared memory), so the phi
-//    update of plane n-1 is completed one plane-step after its fluxes.
+//    update of plane n-1 is completed one plane-step after its fluxes;
+//  * the march is unrolled by the period of the shared-memory rings (4) for the steady-state planes
+//    of a chunk, so every shared-memory address is a per-thread base plus an immediate, and all the
+//    range tests of the pipeline fill / drain live in a generic step used for the first 3 and last
+//    4-7 planes only.
 // One __syncthreads per plane; all shared buffers are double buffered.
 // ---------------------------------------------------------------------------------------------
 
+constexpr int PF_RING = 6;                // phi planes in flight: n .. n+2 read, n+3 landed, n+4 in flight
 struct PfShared {
-  double phi[4][PS_PN];                   // ring of phi planes
+  double phi[PF_RING][PS_PN];             // ring of phi planes, slot = (plane - first plane) % 6
   double g[2][6][PS_NT];                  // Pxy, Pyy, Pyz, Pxz, Pzz, mu of a plane
-  double u[2][2][PS_NT];                  // u_y, u_z
+  double u[3][2][PS_NT];                  // u_y, u_z, slot = plane % 3
+  double ux[3][PS_NT];                    // u_x, slot = plane % 3
   double fl[2][2][PS_NT];                 // y and z face fluxes (face between the site and site+1)
+};
+
+// global -> shared without a register stop-over (LDGSTS): the prefetch distance of the march is two
+// plane-steps, more than the registers of this kernel could hold
+__device__ __forceinline__ void pf_cp_async8(double * smem_dst, const double * gsrc) {
+  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void pf_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void pf_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+struct PfRegs {                            // own-column history carried along the march (plane n = current)
+  double Bm, Cym, Czm, Bc, Cyc, Czc;      // plane sums of planes n, n+1
+  double gm_xx, gm_xy, gm_xz;             // P_xa of plane n-1
+  double gc_xx, gc_xy, gc_xz, gc_mu;      // P_xa, mu of plane n
+  double phim1;                           // phi(n-1)
+  double fxm1, fxm2;                      // x-face fluxes (n-1 | n), (n-2 | n-1)
+  double fy_prev, fz_prev;                // own y / z face fluxes of plane n-1
+  double uxc;                             // u_x(n)
+};
+
+struct PfK {                               // per-thread / per-CTA constants
+  int pc, tid, col, scol, pcol0, pcol1, e0, e1;
+  bool has_e1, valid_g, out_site, face_row, own_g;
+  int xs, ns, nh, nlx, wx, i0, i1;
+  double M, kappa, a, b, mg0, mg1, mg2, wz;
 };
 
 // partial sums of one phi plane at the own column: B, Cy, Cz
@@ -1113,6 +1147,138 @@ __device__ __forceinline__ void pf_plane_sums(const double * __restrict__ q, int
   Cz = ((mp - mm) + (zp - zm)) + (pp - pm);
 }
 
+// One plane-step of the march at plane n.  PH >= 0: steady state, PH = (n - first plane) % 6 known at
+// compile time, every stage active, no periodic wrap in x (planes n+1 .. n+4 inside the chunk).
+// PH < 0: generic (pipeline fill and drain).
+template <int ORDER, int PH>
+__device__ __forceinline__ void pf_step(PfShared & sm, PfRegs & r, const PfK & k, const int n,
+					const double * __restrict__ phi, const double * __restrict__ u,
+					double * __restrict__ grad, double * __restrict__ delsq,
+					double * __restrict__ force, double * __restrict__ phinew) {
+  constexpr bool STEADY = (PH >= 0);
+  const int q = STEADY ? PH : (n - (k.i0 - 2)) % 6;        // phase: plane n relative to the first plane
+  const int tid = k.tid, pc = k.pc;
+  const int typ = tid + PS_BZ, tym = tid - PS_BZ, tzp = tid + 1, tzm = tid - 1;
+  const double r9 = (1.0/9.0), r18 = 0.5*(1.0/9.0);
+
+  const bool do_grad = STEADY || (n <= k.i1);
+  const bool do_fx   = STEADY || (n >= k.i0 - 1 && n <= k.i1);
+  const bool do_full = STEADY || (n >= k.i0 && n <= k.i1);
+  const bool do_upd  = STEADY || (n >= k.i0 + 1);
+
+  // ---- 1. asynchronous prefetch, two plane-steps ahead: phi(n+4), u_x(n+3), u_y / u_z (n+2) ----
+  {
+    int xo2, xo3, xo4;
+    if (STEADY) {
+      xo2 = (n + 1 + k.nh)*k.xs; xo3 = xo2 + k.xs; xo4 = xo3 + k.xs;
+    }
+    else {
+      xo2 = (ps_wrap(n + 2, k.nlx, k.wx) + k.nh - 1)*k.xs;
+      xo3 = (ps_wrap(n + 3, k.nlx, k.wx) + k.nh - 1)*k.xs;
+      xo4 = (ps_wrap(n + 4, k.nlx, k.wx) + k.nh - 1)*k.xs;
+    }
+    if (STEADY || n + 4 <= k.i1 + 2) {
+      pf_cp_async8(&sm.phi[(q + 4) % 6][k.e0], phi + xo4 + k.pcol0);
+      if (k.has_e1) pf_cp_async8(&sm.phi[(q + 4) % 6][k.e1], phi + xo4 + k.pcol1);
+    }
+    if (STEADY || n + 3 <= k.i1 + 1) pf_cp_async8(&sm.ux[q % 3][tid], u + xo3 + k.col);
+    if (STEADY || n + 2 <= k.i1) {
+      pf_cp_async8(&sm.u[(q + 2) % 3][0][tid], u + k.ns + xo2 + k.col);
+      pf_cp_async8(&sm.u[(q + 2) % 3][1][tid], u + 2*k.ns + xo2 + k.col);
+    }
+    pf_cp_async_commit();
+  }
+
+  const double * __restrict__ fm = sm.phi[q];
+  const double * __restrict__ fc = sm.phi[(q + 1) % 6];
+  const double * __restrict__ fp = sm.phi[(q + 2) % 6];
+
+  // ---- 2. gradient, chemical potential and stress of plane n+1 at the own column ----
+  double gp_xx = 0.0, gp_xy = 0.0, gp_xz = 0.0, gp_mu = 0.0;
+  double Bp = 0.0, Cyp = 0.0, Czp = 0.0;
+  if (do_grad) {
+    pf_plane_sums(fp, pc, Bp, Cyp, Czp);
+    const double phc = fc[pc];
+    const double gx = r18*(Bp - r.Bm);
+    const double gy = r18*((r.Cym + r.Cyc) + Cyp);
+    const double gz = r18*((r.Czm + r.Czc) + Czp);
+    const double dsq = r9*(((r.Bm + r.Bc) + Bp) - 27.0*phc);
+
+    const int ig = n + 1;
+    const bool own_x = STEADY || (ig >= k.i0 && ig <= k.i1) || (ig == 0 && k.i0 == 1) || (ig == k.nlx + 1 && k.i1 == k.nlx);
+    if (k.own_g && own_x) {
+      const int sidx = (ig + k.nh - 1)*k.xs + k.scol;
+      grad[sidx] = gx;
+      grad[k.ns + sidx] = gy;
+      grad[2*k.ns + sidx] = gz;
+      delsq[sidx] = dsq;
+    }
+
+    const double ph2 = phc*phc;
+    const double p0 = ph2*(0.5*k.a + 0.75*k.b*ph2) - k.kappa*(phc*dsq + 0.5*((gx*gx + gy*gy) + gz*gz));
+    gp_mu = phc*(k.a + k.b*ph2) - k.kappa*dsq;
+    const double kgx = k.kappa*gx, kgy = k.kappa*gy, kgz = k.kappa*gz;
+    gp_xx = p0 + kgx*gx; gp_xy = kgx*gy; gp_xz = kgx*gz;
+    double (* gb)[PS_NT] = sm.g[(q + 1) & 1];
+    gb[0][tid] = gp_xy;
+    gb[1][tid] = p0 + kgy*gy;
+    gb[2][tid] = kgy*gz;
+    gb[3][tid] = gp_xz;
+    gb[4][tid] = p0 + kgz*gz;
+    gb[5][tid] = gp_mu;
+  }
+
+  // ---- 3. plane n: x-face flux (n | n+1), force, y/z face fluxes ----
+  // (rows 0 .. PS_TY own faces; lane PS_BZ-1 of those rows computes harmless values that nobody reads)
+  const double ph_c = fm[pc];
+  const double uxp = sm.ux[(q + 1) % 3][tid];               // u_x(n+1)
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  if (do_fx && k.face_row) {
+    fx = adv_face<ORDER, false>(r.uxc, uxp, r.phim1, ph_c, fc[pc], fp[pc]) - k.M*(gp_mu - r.gc_mu) - k.mg0;
+
+    if (do_full) {
+      const double (* gb)[PS_NT] = sm.g[q & 1];
+      const double (* ub)[PS_NT] = sm.u[q % 3];
+
+      if (k.out_site) {
+	const int s = (n + k.nh - 1)*k.xs + k.scol;
+	force[s]          = 0.5*(((r.gm_xx - gp_xx) + (gb[0][tym] - gb[0][typ])) + (gb[3][tzm] - gb[3][tzp]));
+	force[k.ns + s]   = 0.5*(((r.gm_xy - gp_xy) + (gb[1][tym] - gb[1][typ])) + (gb[2][tzm] - gb[2][tzp]));
+	force[2*k.ns + s] = 0.5*(((r.gm_xz - gp_xz) + (gb[2][tym] - gb[2][typ])) + (gb[4][tzm] - gb[4][tzp]));
+      }
+
+      double ph_yp2 = 0.0, ph_zp2 = 0.0;
+      if (ORDER == 3) { ph_yp2 = fm[pc + 2*PS_PZ]; ph_zp2 = fm[pc + 2]; }
+      fy = adv_face<ORDER, false>(ub[0][tid], ub[0][typ], fm[pc - PS_PZ], ph_c, fm[pc + PS_PZ], ph_yp2)
+	- k.M*(gb[5][typ] - r.gc_mu) - k.mg1;
+      fz = adv_face<ORDER, false>(ub[1][tid], ub[1][tzp], fm[pc - 1], ph_c, fm[pc + 1], ph_zp2)
+	- k.M*(gb[5][tzp] - r.gc_mu) - k.mg2;
+      sm.fl[q & 1][0][tid] = fy;
+      sm.fl[q & 1][1][tid] = fz;
+    }
+  }
+
+  // ---- 4. phi update of plane n-1, whose y/z face fluxes were published one plane-step ago ----
+  if (do_upd && k.out_site) {
+    const double (* fl)[PS_NT] = sm.fl[(q + 1) & 1];
+    const int s = (n - 1 + k.nh - 1)*k.xs + k.scol;
+    phinew[s] = r.phim1 - (((r.fxm1 - r.fxm2) + (r.fy_prev - fl[0][tym])) + k.wz*(r.fz_prev - fl[1][tzm]));
+  }
+
+  // ---- 5. rotate the own-column history; the prefetch issued ONE step ago must have landed ----
+  r.Bm = r.Bc; r.Cym = r.Cyc; r.Czm = r.Czc;
+  r.Bc = Bp; r.Cyc = Cyp; r.Czc = Czp;
+  r.gm_xx = r.gc_xx; r.gm_xy = r.gc_xy; r.gm_xz = r.gc_xz;
+  r.gc_xx = gp_xx; r.gc_xy = gp_xy; r.gc_xz = gp_xz;
+  r.gc_mu = gp_mu;
+  r.phim1 = ph_c;
+  r.fxm2 = r.fxm1; r.fxm1 = fx;
+  r.fy_prev = fy; r.fz_prev = fz;
+  r.uxc = uxp;
+  pf_cp_async_wait<1>();
+  __syncthreads();
+}
+
 template <int ORDER>
 __global__ void __launch_bounds__(PS_NT, 1)
 phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
@@ -1124,183 +1290,89 @@ phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
   PfShared & sm = *reinterpret_cast<PfShared *>(ps_smem_raw);
 
   const int tz = threadIdx.x, ty = threadIdx.y;
-  const int tid = ty*PS_BZ + tz;
   const int kbase = blockIdx.x*PS_TZ;              // thread column (j,k) = (jbase + ty, kbase + tz)
   const int jbase = blockIdx.y*PS_TY;
   const int kc = kbase + tz, jc = jbase + ty;
-  const int i0 = 1 + blockIdx.z*xc;
-  const int i1 = min(i0 + xc - 1, g.nl[0]);
-  const int nh = g.nh;
-  const size_t ns = (size_t) g.nsites;
-  const int xs = g.xs, ys = g.ys;
-  const int wx = g.wrap[0], nlx = g.nl[0];
+  const int nh = g.nh, ys = g.ys;
 
-  const bool valid_g = (jc <= g.nl[1] + 1) && (kc <= g.nl[2] + 1);
+  PfK k;
+  k.tid = ty*PS_BZ + tz;
+  k.pc = (ty + 1)*PS_PZ + (tz + 1);                // own position in the phi tile
+  k.xs = g.xs; k.ns = g.nsites; k.nh = nh; k.nlx = g.nl[0]; k.wx = g.wrap[0];
+  k.i0 = 1 + blockIdx.z*xc;
+  k.i1 = min(k.i0 + xc - 1, g.nl[0]);
+  k.M = sp.mobility; k.kappa = sp.kappa; k.a = sp.a; k.b = sp.b; k.wz = sp.wz;
+  k.mg0 = sp.mobility*sp.gm[0]; k.mg1 = sp.mobility*sp.gm[1]; k.mg2 = sp.mobility*sp.gm[2];
+
   const bool inner = (ty >= 1 && ty <= PS_TY && tz >= 1 && tz <= PS_TZ);
-  const bool out_site = inner && jc <= g.nl[1] && kc <= g.nl[2];
-  const bool face_site = (ty <= PS_TY && tz <= PS_TZ);      // owns the faces towards j+1 and k+1
-  const bool own_g = valid_g && ((ty >= 1 && ty <= PS_TY) || (ty == 0 && jc == 0))
+  k.valid_g = (jc <= g.nl[1] + 1) && (kc <= g.nl[2] + 1);
+  k.out_site = inner && jc <= g.nl[1] && kc <= g.nl[2];
+  k.face_row = (ty <= PS_TY);                      // rows that own faces towards j+1 / k+1
+  k.own_g = k.valid_g && ((ty >= 1 && ty <= PS_TY) || (ty == 0 && jc == 0))
     && ((tz >= 1 && tz <= PS_TZ) || (tz == 0 && kc == 0));
 
   // column used for loads: clamped inside the allocation, through the periodic boundary if wrapping
   const int jl = ps_wrap(min(jc, g.nl[1] + 1), g.nl[1], g.wrap[1]);
   const int kl = ps_wrap(min(kc, g.nl[2] + 1), g.nl[2], g.wrap[2]);
-  const int col = (jl + nh - 1)*ys + (kl + nh - 1);
-  const int scol = (jc + nh - 1)*ys + (kc + nh - 1);       // column of the stores (never wrapped)
+  k.col = (jl + nh - 1)*ys + (kl + nh - 1);
+  k.scol = (jc + nh - 1)*ys + (kc + nh - 1);       // column of the stores (never wrapped)
 
   // cooperative phi plane load: element e of the (PS_PY x PS_PZ) tile <-> (jbase-1+r, kbase-1+c)
-  const int e0 = tid, e1 = tid + PS_NT;
-  const int r0 = e0/PS_PZ, c0 = e0%PS_PZ;
-  const int r1 = e1/PS_PZ, c1 = e1%PS_PZ;
-  const int pj0 = ps_wrap(min(jbase - 1 + r0, g.nl[1] + nh), g.nl[1], g.wrap[1]);
-  const int pk0 = ps_wrap(min(kbase - 1 + c0, g.nl[2] + nh), g.nl[2], g.wrap[2]);
-  const int pj1 = ps_wrap(min(jbase - 1 + r1, g.nl[1] + nh), g.nl[1], g.wrap[1]);
-  const int pk1 = ps_wrap(min(kbase - 1 + c1, g.nl[2] + nh), g.nl[2], g.wrap[2]);
-  const int pcol0 = (pj0 + nh - 1)*ys + (pk0 + nh - 1);
-  const int pcol1 = (pj1 + nh - 1)*ys + (pk1 + nh - 1);
-  const bool has_e1 = (e1 < PS_PN);
-
-  const int istart = i0 - 2;
-  const int pc = (ty + 1)*PS_PZ + (tz + 1);        // own position in the phi tile
-  const int typ = tid + PS_BZ, tym = tid - PS_BZ, tzp = tid + 1, tzm = tid - 1;
-
-  // prologue: planes istart, istart+1, istart+2 into the ring; u_y, u_z of plane i0 - 1 are not needed
-#pragma unroll
-  for (int d = 0; d < 3; d++) {
-    const int ip = istart + d;
-    const int xo = (ps_wrap(ip, nlx, wx) + nh - 1)*xs;
-    sm.phi[(ip + 4) & 3][e0] = phi[xo + pcol0];
-    if (has_e1) sm.phi[(ip + 4) & 3][e1] = phi[xo + pcol1];
+  k.e0 = k.tid; k.e1 = k.tid + PS_NT;
+  {
+    const int r0 = k.e0/PS_PZ, c0 = k.e0%PS_PZ;
+    const int r1 = k.e1/PS_PZ, c1 = k.e1%PS_PZ;
+    const int pj0 = ps_wrap(min(jbase - 1 + r0, g.nl[1] + nh), g.nl[1], g.wrap[1]);
+    const int pk0 = ps_wrap(min(kbase - 1 + c0, g.nl[2] + nh), g.nl[2], g.wrap[2]);
+    const int pj1 = ps_wrap(min(jbase - 1 + r1, g.nl[1] + nh), g.nl[1], g.wrap[1]);
+    const int pk1 = ps_wrap(min(kbase - 1 + c1, g.nl[2] + nh), g.nl[2], g.wrap[2]);
+    k.pcol0 = (pj0 + nh - 1)*ys + (pk0 + nh - 1);
+    k.pcol1 = (pj1 + nh - 1)*ys + (pk1 + nh - 1);
+    k.has_e1 = (k.e1 < PS_PN);
   }
-  double uxc = 0.0;                                                          // u_x(n)
-  double uxp = u[0*ns + (ps_wrap(istart + 1, nlx, wx) + nh - 1)*xs + col];   // u_x(n+1)
+
+  const int istart = k.i0 - 2;
+
+  // prologue: phi planes istart .. istart+3 -> ring slots 0 .. 3; u_x(istart+1), u_x(istart+2) -> slots 1, 2;
+  // u_y, u_z (istart+1) -> slot 1.  (The first plane-step prefetches phi(istart+4), u_x(istart+3), u_y/u_z(istart+2).)
+#pragma unroll
+  for (int d = 0; d < 4; d++) {
+    const int xo = (ps_wrap(istart + d, k.nlx, k.wx) + nh - 1)*k.xs;
+    pf_cp_async8(&sm.phi[d][k.e0], phi + xo + k.pcol0);
+    if (k.has_e1) pf_cp_async8(&sm.phi[d][k.e1], phi + xo + k.pcol1);
+    if (d == 1 || d == 2) pf_cp_async8(&sm.ux[d][k.tid], u + xo + k.col);
+    if (d == 1) {
+      pf_cp_async8(&sm.u[1][0][k.tid], u + k.ns + xo + k.col);
+      pf_cp_async8(&sm.u[1][1][k.tid], u + 2*k.ns + xo + k.col);
+    }
+  }
+  pf_cp_async_commit();
+  pf_cp_async_wait<0>();
   __syncthreads();
 
-  // plane sums of planes n and n+1 (own column)
-  double Bm, Cym, Czm, Bc, Cyc, Czc;
-  pf_plane_sums(sm.phi[(istart + 4) & 3], pc, Bm, Cym, Czm);
-  pf_plane_sums(sm.phi[(istart + 5) & 3], pc, Bc, Cyc, Czc);
+  PfRegs r;
+  r.uxc = 0.0;                                     // u_x(n): not used before n = i0 - 1
+  pf_plane_sums(sm.phi[0], k.pc, r.Bm, r.Cym, r.Czm);
+  pf_plane_sums(sm.phi[1], k.pc, r.Bc, r.Cyc, r.Czc);
+  r.gm_xx = r.gm_xy = r.gm_xz = 0.0;
+  r.gc_xx = r.gc_xy = r.gc_xz = r.gc_mu = 0.0;
+  r.phim1 = 0.0;
+  r.fxm1 = r.fxm2 = r.fy_prev = r.fz_prev = 0.0;
 
-  // own-column history
-  double gm_xx = 0.0, gm_xy = 0.0, gm_xz = 0.0;        // P_xa of plane n-1
-  double gc_xx = 0.0, gc_xy = 0.0, gc_xz = 0.0;        // P_xa of plane n
-  double gc_mu = 0.0;                                  // mu of plane n
-  double phim1 = 0.0;                                  // phi(n-1)
-  double fxm1 = 0.0, fxm2 = 0.0;                       // x-face fluxes (n-1 | n), (n-2 | n-1)
-  double fy_prev = 0.0, fz_prev = 0.0;                 // own y / z face fluxes of plane n-1
-
-  const double M = sp.mobility;
-  const double kappa = sp.kappa;
-  const double mg0 = M*sp.gm[0], mg1 = M*sp.gm[1], mg2 = M*sp.gm[2];
-  const double r9 = (1.0/9.0), r18 = 0.5*(1.0/9.0);
-
-  for (int n = istart; n <= i1 + 1; n++) {
-
-    // ---- 1. prefetch (consumed at the end of this plane-step) ----
-    double pf0 = 0.0, pf1 = 0.0, uxn = 0.0, uyn = 0.0, uzn = 0.0;
-    if (n < i1) {
-      const int xo3 = (ps_wrap(n + 3, nlx, wx) + nh - 1)*xs;
-      const int xo2 = (ps_wrap(n + 2, nlx, wx) + nh - 1)*xs;
-      const int xo1 = (ps_wrap(n + 1, nlx, wx) + nh - 1)*xs;
-      pf0 = phi[xo3 + pcol0];
-      if (has_e1) pf1 = phi[xo3 + pcol1];
-      uxn = u[0*ns + xo2 + col];
-      uyn = u[1*ns + xo1 + col];
-      uzn = u[2*ns + xo1 + col];
-    }
-
-    const double * __restrict__ fm = sm.phi[(n + 4) & 3];
-    const double * __restrict__ fc = sm.phi[(n + 5) & 3];
-    const double * __restrict__ fp = sm.phi[(n + 6) & 3];
-
-    // ---- 2. gradient, chemical potential and stress of plane n+1 at the own column ----
-    double gp_xx = 0.0, gp_xy = 0.0, gp_xz = 0.0, gp_mu = 0.0;
-    double Bp = 0.0, Cyp = 0.0, Czp = 0.0;
-    if (n <= i1) {
-      pf_plane_sums(fp, pc, Bp, Cyp, Czp);
-      const double ph = fc[pc];
-      const double gx = r18*(Bp - Bm);
-      const double gy = r18*((Cym + Cyc) + Cyp);
-      const double gz = r18*((Czm + Czc) + Czp);
-      const double dsq = r9*(((Bm + Bc) + Bp) - 27.0*ph);
-
-      const int ig = n + 1;
-      const bool own_x = (ig >= i0 && ig <= i1) || (ig == 0 && i0 == 1) || (ig == nlx + 1 && i1 == nlx);
-      if (own_g && own_x) {
-	const int sidx = (ig + nh - 1)*xs + scol;
-	grad[0*ns + sidx] = gx;
-	grad[1*ns + sidx] = gy;
-	grad[2*ns + sidx] = gz;
-	delsq[sidx] = dsq;
-      }
-
-      const double ph2 = ph*ph;
-      const double p0 = ph2*(0.5*sp.a + 0.75*sp.b*ph2) - kappa*(ph*dsq + 0.5*((gx*gx + gy*gy) + gz*gz));
-      gp_mu = ph*(sp.a + sp.b*ph2) - kappa*dsq;
-      const double kgx = kappa*gx, kgy = kappa*gy, kgz = kappa*gz;
-      gp_xx = p0 + kgx*gx; gp_xy = kgx*gy; gp_xz = kgx*gz;
-      double (* gb)[PS_NT] = sm.g[(n + 1) & 1];
-      gb[0][tid] = gp_xy;
-      gb[1][tid] = p0 + kgy*gy;
-      gb[2][tid] = kgy*gz;
-      gb[3][tid] = gp_xz;
-      gb[4][tid] = p0 + kgz*gz;
-      gb[5][tid] = gp_mu;
-    }
-
-    // ---- 3. plane n: x-face flux (n | n+1), force, y/z face fluxes ----
-    const double ph_c = fm[pc];
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    if (n >= i0 - 1 && n <= i1 && face_site) {
-      fx = adv_face<ORDER, false>(uxc, uxp, phim1, ph_c, fc[pc], fp[pc]) - M*(gp_mu - gc_mu) - mg0;
-
-      if (n >= i0) {
-	const double (* gb)[PS_NT] = sm.g[n & 1];
-	const double (* ub)[PS_NT] = sm.u[n & 1];
-
-	if (out_site) {
-	  const int s = (n + nh - 1)*xs + scol;
-	  force[0*ns + s] = 0.5*(((gm_xx - gp_xx) + (gb[0][tym] - gb[0][typ])) + (gb[3][tzm] - gb[3][tzp]));
-	  force[1*ns + s] = 0.5*(((gm_xy - gp_xy) + (gb[1][tym] - gb[1][typ])) + (gb[2][tzm] - gb[2][tzp]));
-	  force[2*ns + s] = 0.5*(((gm_xz - gp_xz) + (gb[2][tym] - gb[2][typ])) + (gb[4][tzm] - gb[4][tzp]));
-	}
-
-	double ph_yp2 = 0.0, ph_zp2 = 0.0;
-	if (ORDER == 3) { ph_yp2 = fm[pc + 2*PS_PZ]; ph_zp2 = fm[pc + 2]; }
-	fy = adv_face<ORDER, false>(ub[0][tid], ub[0][typ], fm[pc - PS_PZ], ph_c, fm[pc + PS_PZ], ph_yp2)
-	  - M*(gb[5][typ] - gc_mu) - mg1;
-	fz = adv_face<ORDER, false>(ub[1][tid], ub[1][tzp], fm[pc - 1], ph_c, fm[pc + 1], ph_zp2)
-	  - M*(gb[5][tzp] - gc_mu) - mg2;
-	sm.fl[n & 1][0][tid] = fy;
-	sm.fl[n & 1][1][tid] = fz;
-      }
-    }
-
-    // ---- 4. phi update of plane n-1, whose y/z face fluxes were published one plane-step ago ----
-    if (n >= i0 + 1 && out_site) {
-      const double (* fl)[PS_NT] = sm.fl[(n - 1) & 1];
-      const int s = (n - 1 + nh - 1)*xs + scol;
-      phinew[s] = phim1 - (((fxm1 - fxm2) + (fy_prev - fl[0][tym])) + sp.wz*(fz_prev - fl[1][tzm]));
-    }
-
-    // ---- 5. rotate the own-column history, publish the prefetched plane ----
-    Bm = Bc; Cym = Cyc; Czm = Czc;
-    Bc = Bp; Cyc = Cyp; Czc = Czp;
-    gm_xx = gc_xx; gm_xy = gc_xy; gm_xz = gc_xz;
-    gc_xx = gp_xx; gc_xy = gp_xy; gc_xz = gp_xz;
-    gc_mu = gp_mu;
-    phim1 = ph_c;
-    fxm2 = fxm1; fxm1 = fx;
-    fy_prev = fy; fz_prev = fz;
-    uxc = uxp; uxp = uxn;
-    if (n < i1) {
-      sm.phi[(n + 7) & 3][e0] = pf0;                 // plane n+3 -> slot of plane n-1
-      if (has_e1) sm.phi[(n + 7) & 3][e1] = pf1;
-      sm.u[(n + 1) & 1][0][tid] = uyn;
-      sm.u[(n + 1) & 1][1][tid] = uzn;
-    }
-    __syncthreads();
+  int n = istart;
+  // pipeline fill: planes i0-2, i0-1, i0 (phases 0, 1, 2)
+  for (; n <= k.i0 && n <= k.i1 + 1; n++) pf_step<ORDER, -1>(sm, r, k, n, phi, u, grad, delsq, force, phinew);
+  // steady state: n >= i0+1 and n <= i1-4, phases 3, 4, 5, 0, 1, 2
+  for (; n + 5 <= k.i1 - 4; n += 6) {
+    pf_step<ORDER, 3>(sm, r, k, n,     phi, u, grad, delsq, force, phinew);
+    pf_step<ORDER, 4>(sm, r, k, n + 1, phi, u, grad, delsq, force, phinew);
+    pf_step<ORDER, 5>(sm, r, k, n + 2, phi, u, grad, delsq, force, phinew);
+    pf_step<ORDER, 0>(sm, r, k, n + 3, phi, u, grad, delsq, force, phinew);
+    pf_step<ORDER, 1>(sm, r, k, n + 4, phi, u, grad, delsq, force, phinew);
+    pf_step<ORDER, 2>(sm, r, k, n + 5, phi, u, grad, delsq, force, phinew);
   }
+  // remaining planes and pipeline drain
+  for (; n <= k.i1 + 1; n++) pf_step<ORDER, -1>(sm, r, k, n, phi, u, grad, delsq, force, phinew);
 }
 #endif
 
@@ -1343,7 +1415,7 @@ int launch_phi_sector(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
 #else
 #define LB200_PS_KERNEL phi_sector_fast_kernel
   const size_t smem = sizeof(PfShared);
-  const int fill = 4;
+  const int fill = 6;       // 4 extra plane-steps + the slower generic steps of fill and drain
 #endif
   static bool configured = false;
   if (!configured) {
