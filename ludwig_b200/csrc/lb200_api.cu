@@ -883,8 +883,23 @@ static int wrap_exchange_phi(lb200_t * c, cudaStream_t st) {
   return nccl_exchange(c, st, &m, 1);
 }
 
-// after a collision: the populations moving in +x / -x of planes N / 1 and u_x of the same planes
-static int wrap_exchange_f_u(lb200_t * c, cudaStream_t st, int with_u) {
+// after a collision: u_x of planes N / 1 (the only velocity the next phi sector reads across the slab
+// boundary), straight into the neighbour's halo planes -- first, because the phi sector waits for it
+static int wrap_exchange_ux(lb200_t * c, cudaStream_t st) {
+  const Lb200Geom & g = c->g;
+  const size_t xs = (size_t) g.xs;
+  XMsg m;
+  m.send_hi = c->u + (size_t) (g.nl[0] + g.nh - 1)*xs;   // u_x, plane N
+  m.send_lo = c->u + (size_t) g.nh*xs;                   // u_x, plane 1
+  m.recv_lo = c->u + (size_t) (g.nh - 1)*xs;             // plane 0
+  m.recv_hi = c->u + (size_t) (g.nl[0] + g.nh)*xs;       // plane N+1
+  m.count = xs;
+  ProfScope ps(c, LB200_K_HALO, st);
+  return nccl_exchange(c, st, &m, 1);
+}
+
+// ... and the populations moving in +x / -x of planes N / 1 (overlaps the phi sector)
+static int wrap_exchange_f(lb200_t * c, cudaStream_t st) {
   const Lb200Geom & g = c->g;
   const size_t xs = (size_t) g.xs, ns = (size_t) g.nsites;
   const int nv = c->nvel;
@@ -906,18 +921,9 @@ static int wrap_exchange_f_u(lb200_t * c, cudaStream_t st, int with_u) {
     }
   }
   if (nup != ndn) return fail(LB200_ESTATE, "velocity set not symmetric in x");
-  XMsg m[2];
-  m[0].send_hi = shi; m[0].send_lo = slo; m[0].recv_lo = rlo; m[0].recv_hi = rhi; m[0].count = nup*xs;
-  int nm = 1;
-  if (with_u) {
-    m[1].send_hi = c->u + (size_t) (g.nl[0] + g.nh - 1)*xs;   // u_x, plane N
-    m[1].send_lo = c->u + (size_t) g.nh*xs;                   // u_x, plane 1
-    m[1].recv_lo = c->u + (size_t) (g.nh - 1)*xs;             // plane 0
-    m[1].recv_hi = c->u + (size_t) (g.nl[0] + g.nh)*xs;       // plane N+1
-    m[1].count = xs;
-    nm = 2;
-  }
-  int rc = nccl_exchange(c, st, m, nm);
+  XMsg m;
+  m.send_hi = shi; m.send_lo = slo; m.recv_lo = rlo; m.recv_hi = rhi; m.count = nup*xs;
+  int rc = nccl_exchange(c, st, &m, 1);
   if (rc != 0) return rc;
   // unpack: what came from the low neighbour are its c_x = +1 populations -> my plane 0; from the high
   // neighbour its c_x = -1 populations -> my plane N+1
@@ -957,12 +963,16 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	rc = wrap_exchange_phi(c, C);
 	if (rc != 0) return rc;
       }
-      if (c->prop_pending || binary) {
-	rc = wrap_exchange_f_u(c, C, binary);
+      if (binary) {
+	rc = wrap_exchange_ux(c, C);
 	if (rc != 0) return rc;
       }
       CUDA_TRY(cudaEventRecord(c->ev_phi, C));
       CUDA_TRY(cudaEventRecord(c->ev_u, C));
+      if (c->prop_pending) {
+	rc = wrap_exchange_f(c, C);
+	if (rc != 0) return rc;
+      }
       CUDA_TRY(cudaEventRecord(c->ev_f, C));
     }
   }
@@ -1005,10 +1015,14 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     if (remote) {
       CUDA_TRY(cudaEventRecord(c->ev_main, S));
       CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
-      rc = wrap_exchange_f_u(c, C, binary);
+      if (binary) {
+	rc = wrap_exchange_ux(c, C);                                     // the next phi sector waits for this one only
+	if (rc != 0) return rc;
+	CUDA_TRY(cudaEventRecord(c->ev_u, C));
+      }
+      rc = wrap_exchange_f(c, C);                                        // overlaps the next phi sector
       if (rc != 0) return rc;
       CUDA_TRY(cudaEventRecord(c->ev_f, C));
-      CUDA_TRY(cudaEventRecord(c->ev_u, C));
     }
   }
   c->phi_halo_valid = 0;

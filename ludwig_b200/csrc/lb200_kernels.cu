@@ -1233,7 +1233,7 @@ __device__ __forceinline__ void pf_step(PfShared & sm, PfRegs & r, const PfK & k
   const double ph_c = fm[pc];
   const double uxp = sm.ux[(q + 1) % 3][tid];               // u_x(n+1)
   double fx = 0.0, fy = 0.0, fz = 0.0;
-  if (do_fx && k.face_row) {
+  if (STEADY || (do_fx && k.face_row)) {          // steady state: branch-free, one basic block for the scheduler
     fx = adv_face<ORDER, false>(r.uxc, uxp, r.phim1, ph_c, fc[pc], fp[pc]) - k.M*(gp_mu - r.gc_mu) - k.mg0;
 
     if (do_full) {

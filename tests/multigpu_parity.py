@@ -50,8 +50,11 @@ def main():
     sim.put(lb.F, slab(st["f"])); sim.put(lb.PHI, slab(st["phi"]))
     cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA, force=fg)
     sp = lb.SymmParam.make(adv_order=3, **BINARY)
-    sim.step(cp, sp, nsteps // 2)
-    sim.step_api(cp, sp, nsteps - nsteps // 2)          # both paths over the decomposed lattice
+    # every path over the decomposed lattice, and the hand-overs between them: halo-free lb200_step (only the
+    # planes the kernels read cross NVLink), the individual entry points (full halo swaps), lb200_step again
+    sim.step(cp, sp, 2)
+    sim.step_api(cp, sp, 2)
+    sim.step(cp, sp, nsteps - 4)
     mine = {k: np.ascontiguousarray(orc_l.interior(sim.get(a))) for k, a in
             (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO), ("force", lb.FORCE))}
     gathered = [None] * world
