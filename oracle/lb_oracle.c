@@ -826,3 +826,275 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
   free(str);
   free(flux);
 }
+
+/* ---- symmetric_lb: two-distribution binary fluid ------------------------------------------------
+ * phi_lb_to_field / phi_lb_from_field: src/phi_lb_coupler.c:39-137
+ * lb_collision_binary -> lb_collision_mrt2_site: src/collision.c:604-1013 (interior sites only, no
+ * status test, hydro->rho NOT written), relaxation rates from lb->param->rtau[]
+ * (src/collision.c:1163-1246), rtau2 = 2/(1 + 2M) (:1949-1950), thermodynamic stress fe_symm_str_v and
+ * chemical potential fe_symm_mu (src/symmetric.c:307-319, 371-416), order-parameter reprojection
+ * d3q19_mode2f_phi (src/collision.c:2856-3135) / generic loop (:974-1008).                          */
+
+void orc_phi_lb_to_field(const orc_geom_t * g, const orc_model_t * m, const double * f, double * phi) {
+  const size_t ns = (size_t) orc_nsites(g);
+  #pragma omp parallel for collapse(2) schedule(static)
+  for (int ic = 1; ic <= g->nlocal[X]; ic++)
+    for (int jc = 1; jc <= g->nlocal[Y]; jc++)
+      for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
+	int index = orc_index(g, ic, jc, kc);
+	double phi0 = 0.0;
+	for (int p = 0; p < m->nvel; p++) phi0 += f[(size_t) (m->nvel + p)*ns + index];
+	phi[index] = phi0;
+      }
+}
+
+void orc_phi_lb_from_field(const orc_geom_t * g, const orc_model_t * m, const double * phi, double * f) {
+  const size_t ns = (size_t) orc_nsites(g);
+  for (int ic = 1; ic <= g->nlocal[X]; ic++)
+    for (int jc = 1; jc <= g->nlocal[Y]; jc++)
+      for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
+	int index = orc_index(g, ic, jc, kc);
+	f[(size_t) (m->nvel + 0)*ns + index] = phi[index];
+	for (int p = 1; p < m->nvel; p++) f[(size_t) (m->nvel + p)*ns + index] = 0.0;
+      }
+}
+
+static void collide_binary_site(const orc_model_t * m, const orc_collide_param_t * cp,
+				const orc_symm_param_t * sp, double * fs, double * gs,
+				const double hforce[3], double phi, const double grad[3], double delsq,
+				double u_out[3]) {
+
+  const int nvel = m->nvel;
+  const int nhydro = 10;
+  const double cs2 = (1.0/3.0);
+  const double r3 = 1.0/3.0;
+  const signed char d[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  double mode[27];
+  double rho, rrho;
+  double u[3], s[3][3], seq[3][3], sth[3][3], sphi[3][3], force[3], jphi[3];
+  double rtau[27];
+  double tr_s, tr_seq, mu;
+
+  /* lb_collision_relaxation_times_set */
+  {
+    double rtau_shear = 1.0/(0.5 + cp->eta_shear/(cp->rho0*cs2));
+    double rtau_bulk  = 1.0/(0.5 + cp->eta_bulk/(cp->rho0*cs2));
+    for (int p = 0; p < 27; p++) rtau[p] = 0.0;
+    if (cp->nrelax == ORC_RELAX_M10) {
+      rtau[5] = rtau_shear; rtau[4] = rtau_bulk;
+      for (int p = nhydro; p < nvel; p++) rtau[p] = 1.0;
+    }
+    if (cp->nrelax == ORC_RELAX_BGK) {
+      for (int p = 0; p < nvel; p++) rtau[p] = rtau_shear;
+    }
+    if (cp->nrelax == ORC_RELAX_TRT) {
+      double tau = cp->eta_shear/(cp->rho0*cs2);
+      double rg = 0.5 + 2.0*tau/(tau + 3.0/8.0);
+      if (rg > 2.0) rg = 2.0;
+      rtau[5] = rtau_shear; rtau[4] = rtau_bulk;
+      if (nvel == 15) {
+	rtau[10] = rtau_shear; rtau[11] = rg; rtau[12] = rg; rtau[13] = rg; rtau[14] = rtau_shear;
+      }
+      if (nvel == 19) {
+	rtau[10] = rtau_shear; rtau[14] = rtau_shear; rtau[18] = rtau_shear;
+	rtau[11] = rg; rtau[12] = rg; rtau[13] = rg; rtau[15] = rg; rtau[16] = rg; rtau[17] = rg;
+      }
+    }
+  }
+
+  if (nvel == 19) {
+    for (int mm = 0; mm < 19; mm++) {
+      mode[mm] = 0.0;
+      for (int p = 0; p < 19; p++) {
+	if (d3q19_fwd[mm][p] != 0.0) mode[mm] += fs[p]*d3q19_fwd[mm][p];
+      }
+    }
+  }
+  else {
+    for (int mm = 0; mm < nvel; mm++) {
+      mode[mm] = 0.0;
+      for (int p = 0; p < nvel; p++) mode[mm] += m->ma[mm][p]*fs[p];
+    }
+  }
+
+  rho = mode[0];
+  for (int ia = 0; ia < 3; ia++) u[ia] = mode[1 + ia];
+  {
+    int k = 0;
+    for (int ia = 0; ia < 3; ia++)
+      for (int ib = ia; ib < 3; ib++) { s[ia][ib] = mode[4 + k]; k++; }
+    for (int ia = 1; ia < 3; ia++)
+      for (int ib = 0; ib < ia; ib++) s[ia][ib] = s[ib][ia];
+  }
+
+  rrho = 1.0/rho;
+  for (int ia = 0; ia < 3; ia++) {
+    force[ia] = cp->force_global[ia] + hforce[ia];
+    u[ia] = rrho*(u[ia] + 0.5*force[ia]);
+  }
+  for (int ia = 0; ia < 3; ia++) u_out[ia] = u[ia];
+
+  /* fe_symm_str_v */
+  {
+    double p0 = 0.5*sp->a*phi*phi + 0.75*sp->b*phi*phi*phi*phi - sp->kappa*phi*delsq
+      - 0.5*sp->kappa*(grad[X]*grad[X] + grad[Y]*grad[Y] + grad[Z]*grad[Z]);
+    for (int ia = 0; ia < 3; ia++)
+      for (int ib = 0; ib < 3; ib++) sth[ia][ib] = p0*d[ia][ib] + sp->kappa*grad[ia]*grad[ib];
+  }
+
+  tr_s = 0.0;
+  tr_seq = 0.0;
+  for (int ia = 0; ia < 3; ia++) {
+    for (int ib = 0; ib < 3; ib++) seq[ia][ib] = rho*u[ia]*u[ib] + sth[ia][ib];
+    tr_s   += s[ia][ia];
+    tr_seq += seq[ia][ia];
+  }
+  for (int ia = 0; ia < 3; ia++) {
+    s[ia][ia]   -= r3*tr_s;
+    seq[ia][ia] -= r3*tr_seq;
+  }
+  tr_s = tr_s - rtau[4]*(tr_s - tr_seq);
+
+  for (int ia = 0; ia < 3; ia++) {
+    for (int ib = 0; ib < 3; ib++) {
+      s[ia][ib] -= rtau[5]*(s[ia][ib] - seq[ia][ib]);
+      s[ia][ib] += d[ia][ib]*r3*tr_s;
+      s[ia][ib] += (2.0 - rtau[5])*(u[ia]*force[ib] + force[ia]*u[ib]);
+    }
+  }
+
+  for (int ia = 0; ia < 3; ia++) mode[1 + ia] += force[ia];
+  {
+    int k = 0;
+    for (int ia = 0; ia < 3; ia++)
+      for (int ib = ia; ib < 3; ib++) { mode[4 + k] = s[ia][ib] + 0.0; k++; }
+  }
+  for (int mm = nhydro; mm < nvel; mm++) {
+    mode[mm] = mode[mm] - rtau[mm]*(mode[mm] - 0.0) + 0.0;
+  }
+
+  if (nvel == 19) {
+    for (int p = 0; p < 19; p++) {
+      double ftmp = 0.0;
+      for (int mm = 0; mm < 19; mm++) {
+	if (d3q19_bwd[p][mm] != 0.0) ftmp += d3q19_bwd[p][mm]*mode[mm];
+      }
+      fs[p] = ftmp;
+    }
+  }
+  else {
+    for (int p = 0; p < nvel; p++) {
+      double ftmp = 0.0;
+      for (int mm = 0; mm < nvel; mm++) ftmp += m->mi[p][mm]*mode[mm];
+      fs[p] = ftmp;
+    }
+  }
+
+  /* the order parameter distribution */
+  mu = sp->a*phi + sp->b*phi*phi*phi - sp->kappa*delsq;
+  jphi[X] = 0.0; jphi[Y] = 0.0; jphi[Z] = 0.0;
+  for (int p = 1; p < nvel; p++)
+    for (int ia = 0; ia < 3; ia++) jphi[ia] += m->cv[p][ia]*gs[p];
+
+  {
+    const double rtau2 = 2.0/(1.0 + 2.0*sp->mobility);
+    for (int ia = 0; ia < 3; ia++) {
+      for (int ib = 0; ib < 3; ib++) sphi[ia][ib] = phi*u[ia]*u[ib] + mu*d[ia][ib];
+      jphi[ia] = jphi[ia] - rtau2*(jphi[ia] - phi*u[ia]);
+    }
+  }
+
+  if (nvel == 19) {
+    /* unrolled: only the non-zero terms, literal constants 2/3, -1/3, +-1 (src/collision.c:2856-3135) */
+    const double q23 = 6.6666666666666663e-01, q13 = -3.3333333333333331e-01;
+    for (int p = 0; p < 19; p++) {
+      double jdotc = 0.0, sphidotq = 0.0;
+      for (int ia = 0; ia < 3; ia++) {
+	if (m->cv[p][ia] > 0) jdotc += jphi[ia];
+	if (m->cv[p][ia] < 0) jdotc -= jphi[ia];
+      }
+      for (int ia = 0; ia < 3; ia++) {
+	for (int ib = 0; ib < 3; ib++) {
+	  int cc = m->cv[p][ia]*m->cv[p][ib];
+	  if (ia == ib) sphidotq += sphi[ia][ib]*(cc ? q23 : q13);
+	  else if (cc != 0) sphidotq += sphi[ia][ib]*(cc > 0 ? 1.0000000000000000e+00 : -1.0000000000000000e+00);
+	}
+      }
+      gs[p] = m->wv[p]*(jdotc*3.0 + sphidotq*(9.0/2.0));
+      if (p == 0) gs[p] = m->wv[p]*(jdotc*3.0 + sphidotq*(9.0/2.0)) + phi;
+    }
+  }
+  else {
+    for (int p = 0; p < nvel; p++) {
+      int dp0 = (p == 0);
+      double jdotc = 0.0, sphidotq = 0.0;
+      for (int ia = 0; ia < 3; ia++) {
+	jdotc += jphi[ia]*m->cv[p][ia];
+	for (int ib = 0; ib < 3; ib++) {
+	  sphidotq += sphi[ia][ib]*(m->cv[p][ia]*m->cv[p][ib] - cs2*d[ia][ib]);
+	}
+      }
+      gs[p] = m->wv[p]*(jdotc*3.0 + sphidotq*4.5) + phi*dp0;
+    }
+  }
+}
+
+void orc_collide_binary(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+			const orc_symm_param_t * sp, double * f, const double * force,
+			const double * phi, const double * grad, const double * delsq, double * u) {
+
+  const size_t ns = (size_t) orc_nsites(g);
+  const int nvel = m->nvel;
+
+  #pragma omp parallel for collapse(2) schedule(static)
+  for (int ic = 1; ic <= g->nlocal[X]; ic++) {
+    for (int jc = 1; jc <= g->nlocal[Y]; jc++) {
+      for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
+	int index = orc_index(g, ic, jc, kc);
+	double fs[27], gs[27], hf[3], gr[3], uu[3];
+	for (int p = 0; p < nvel; p++) {
+	  fs[p] = f[(size_t) p*ns + index];
+	  gs[p] = f[(size_t) (nvel + p)*ns + index];
+	}
+	for (int ia = 0; ia < 3; ia++) {
+	  hf[ia] = force[(size_t) ia*ns + index];
+	  gr[ia] = grad[(size_t) ia*ns + index];
+	}
+	collide_binary_site(m, cp, sp, fs, gs, hf, phi[index], gr, delsq[index], uu);
+	for (int p = 0; p < nvel; p++) {
+	  f[(size_t) p*ns + index] = fs[p];
+	  f[(size_t) (nvel + p)*ns + index] = gs[p];
+	}
+	for (int ia = 0; ia < 3; ia++) u[(size_t) ia*ns + index] = uu[ia];
+      }
+    }
+  }
+}
+
+/* nsteps of the symmetric_lb time step, reference order src/ludwig.c:528-860 with ndist == 2:
+ * hydro_f_zero; phi_lb_to_field; field_halo(phi); field_grad_compute; hydro_u_zero; lb_collide
+ * (binary); lb_halo; lb_propagation.  f holds both distributions. */
+void orc_step_lb2(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+		  const orc_symm_param_t * sp, int halo_reduced, int nsteps,
+		  double * f, double * phi, double * u, double * force, double * grad, double * delsq) {
+
+  const size_t ns = (size_t) orc_nsites(g);
+  const size_t nf = ns*2*m->nvel;
+  const double zero[3] = {0.0, 0.0, 0.0};
+  double * fprime = (double *) calloc(nf, sizeof(double));
+  assert(fprime);
+  memcpy(fprime, f, nf*sizeof(double));
+
+  for (int n = 0; n < nsteps; n++) {
+    orc_field_set(g, 3, force, zero);
+    orc_phi_lb_to_field(g, m, f, phi);
+    orc_field_halo(g, 1, phi);
+    orc_grad_27pt(g, phi, grad, delsq);
+    orc_field_set(g, 3, u, zero);
+    orc_collide_binary(g, m, cp, sp, f, force, phi, grad, delsq, u);
+    orc_lb_halo(g, m, 2, halo_reduced, f);
+    orc_propagation(g, m, 2, f, fprime);
+    memcpy(f, fprime, nf*sizeof(double));
+  }
+  free(fprime);
+}

@@ -100,6 +100,17 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
 	      double * f, double * phi, double * u, double * rho, double * force,
 	      double * grad, double * delsq);
 
+/* symmetric_lb (ndist = 2): f holds [LB_RHO dist | LB_PHI dist].  phi_lb_to_field / phi_lb_from_field
+ * (src/phi_lb_coupler.c:39-137), lb_collision_binary (src/collision.c:604-1013), whole steps. */
+void orc_phi_lb_to_field(const orc_geom_t * g, const orc_model_t * m, const double * f, double * phi);
+void orc_phi_lb_from_field(const orc_geom_t * g, const orc_model_t * m, const double * phi, double * f);
+void orc_collide_binary(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+			const orc_symm_param_t * sp, double * f, const double * force,
+			const double * phi, const double * grad, const double * delsq, double * u);
+void orc_step_lb2(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+		  const orc_symm_param_t * sp, int halo_reduced, int nsteps,
+		  double * f, double * phi, double * u, double * force, double * grad, double * delsq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,7 @@
 #include "wall.h"
 #include "fe_force_method.h"
 #include "noise.h"
+#include "phi_lb_coupler.h"
 
 typedef struct ref_cfg_s {
   int ntotal[3];
@@ -149,10 +150,17 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     fe_symm_create(s->pe, s->cs, s->phi, s->phi_grad, &s->fe);
     p.a = cfg->a; p.b = cfg->b; p.kappa = cfg->kappa;
     fe_symm_param_set(s->fe, p);
-    ch.conserve = cfg->conserve;
-    phi_ch_create(s->pe, s->cs, s->le, &ch, &s->pch);
-    pth_create(s->pe, s->cs, FE_FORCE_METHOD_STRESS_DIVERGENCE, &s->pth);
-    advection_order_set(cfg->adv_order);
+    if (cfg->ndist == 2) {
+      /* free_energy symmetric_lb (/root/reference/src/ludwig.c:1340-1383): order parameter carried by the
+       * second distribution, dynamics in lb_collision_binary, no explicit force */
+      pth_create(s->pe, s->cs, FE_FORCE_METHOD_NO_FORCE, &s->pth);
+    }
+    else {
+      ch.conserve = cfg->conserve;
+      phi_ch_create(s->pe, s->cs, s->le, &ch, &s->pch);
+      pth_create(s->pe, s->cs, FE_FORCE_METHOD_STRESS_DIVERGENCE, &s->pth);
+      advection_order_set(cfg->adv_order);
+    }
   }
   else {
     pth_create(s->pe, s->cs, FE_FORCE_METHOD_NO_FORCE, &s->pth);
@@ -284,6 +292,8 @@ int ref_collide(ref_sim_t * s) {
   return lb_collide(s->lb, s->hydro, s->map, NULL, (fe_t *) s->fe, NULL);
 }
 int ref_lb_halo(ref_sim_t * s) { return lb_halo(s->lb); }
+int ref_phi_lb_to_field(ref_sim_t * s) { return phi_lb_to_field(s->phi, s->lb); }
+int ref_phi_lb_from_field(ref_sim_t * s) { return phi_lb_from_field(s->phi, s->lb); }
 int ref_propagation(ref_sim_t * s) { return lb_propagation(s->lb); }
 
 /* One full time step in the reference driver's order (/root/reference/src/ludwig.c:528-860) */
@@ -291,7 +301,13 @@ int ref_propagation(ref_sim_t * s) { return lb_propagation(s->lb); }
 int ref_step(ref_sim_t * s, int nsteps) {
   for (int n = 0; n < nsteps; n++) {
     ref_hydro_f_zero(s);
-    if (s->phi) {
+    if (s->lb->ndist == 2) {
+      /* symmetric_lb: /root/reference/src/ludwig.c:551-571, 683-685 */
+      ref_phi_lb_to_field(s);
+      ref_phi_halo(s);
+      ref_grad_compute(s);
+    }
+    else if (s->phi) {
       ref_phi_halo(s);
       ref_grad_compute(s);
       ref_phi_force(s);

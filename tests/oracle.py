@@ -159,6 +159,21 @@ class Oracle:
     def phi_update(self, flux, phi):
         self.lib.orc_phi_update(C.byref(self.g), _p(flux), _p(phi))
 
+    # ---- symmetric_lb (two distributions: f is (2*nvel, nsites)) ------------------------------
+    def phi_lb_to_field(self, f, phi):
+        self.lib.orc_phi_lb_to_field(C.byref(self.g), C.byref(self.m), _p(f), _p(phi))
+
+    def phi_lb_from_field(self, phi, f):
+        self.lib.orc_phi_lb_from_field(C.byref(self.g), C.byref(self.m), _p(phi), _p(f))
+
+    def collide_binary(self, cp, sp, f, force, phi, grad, delsq, u):
+        self.lib.orc_collide_binary(C.byref(self.g), C.byref(self.m), C.byref(cp), C.byref(sp), _p(f), _p(force),
+                                    _p(phi), _p(grad), _p(delsq), _p(u))
+
+    def step_lb2(self, cp, sp, nsteps, f, phi, u, force, grad, delsq, halo_reduced=0):
+        self.lib.orc_step_lb2(C.byref(self.g), C.byref(self.m), C.byref(cp), C.byref(sp), halo_reduced, nsteps,
+                              _p(f), _p(phi), _p(u), _p(force), _p(grad), _p(delsq))
+
     def step(self, cp, sp, binary, nsteps, f, phi, u, rho, force, grad, delsq, halo_reduced=0):
         spp = C.byref(sp) if sp is not None else None
         args = [(_p(x) if x is not None else None) for x in (f, phi, u, rho, force, grad, delsq)]

@@ -46,7 +46,7 @@ def _lib(fast=False, nvel=19):
         lib.ref_time_steps.argtypes = [C.c_void_p, C.c_int]
         for name in ("ref_free", "ref_nsites", "ref_hydro_f_zero", "ref_hydro_u_zero", "ref_hydro_u_halo",
                      "ref_phi_halo", "ref_grad_compute", "ref_phi_force", "ref_cahn_hilliard",
-                     "ref_collide", "ref_lb_halo", "ref_propagation"):
+                     "ref_collide", "ref_lb_halo", "ref_propagation", "ref_phi_lb_to_field", "ref_phi_lb_from_field"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.ref_step.argtypes = [C.c_void_p, C.c_int]
         lib.ref_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]

@@ -79,3 +79,40 @@ def test_serial_dist_3du_log():
     orc.step(orc.collide_param(0, 1.0, 0.1), None, 0, 10, f, None, u, rho, force, None, None)
     assert momentum() == pytest.approx(expect, rel=1e-12)
     assert np.allclose(orc.interior(u)[0], 0.002, rtol=1e-13) and np.allclose(orc.interior(u)[2], 0.004, rtol=1e-13)
+
+
+def test_serial_spin_lb1_log():
+    """tests/regression/d3q19-short/serial-spin-lb1.{inp,log}: `free_energy symmetric_lb` (two distributions,
+    lb_collision_binary), 64^3, A = -B = -0.00625, K = 0.004, mobility 3.75, eta = 0.00625, nhalo = 1.
+    Log lines 78-83 (t = 0) and 91-104 (t = 10)."""
+    n = (64, 64, 64)
+    orc = Oracle(n, nhalo=1)
+    nv, ns = 19, orc.nsites
+    f = np.zeros((2 * nv, ns))
+    f[:nv] = equilibrium_f(n, 1)
+    phi = spinodal_phi(n, 1, 8361235, 0.0, 0.1)
+    orc.phi_lb_from_field(phi, f)                     # src/ludwig.c:402
+    z = lambda k: np.zeros((k, ns))
+    u, force, grad, delsq = z(3), z(3), z(3), z(1)
+    par = dict(a=-0.00625, b=0.00625, kappa=0.004, mobility=3.75)
+    sp = orc.symm_param(**par)
+    cp = orc.collide_param(0, 1.0, ETA)
+
+    orc.step_lb2(cp, sp, 10, f, phi, u, force, grad, delsq)
+
+    # the printed phi is recomputed from the distribution after the last propagation (src/ludwig.c:2416-2419);
+    # the free energy uses it with the gradients of the last step
+    phi_end = phi.copy()
+    orc.phi_lb_to_field(f, phi_end)
+    s = stats_scalar(orc, phi_end)
+    assert s[0] == approx(3.1484764e+00, 8) and s[1] == approx(1.2010484e-05, 8)
+    assert s[2] == approx(6.9606559e-04, 8)
+    assert s[3] == approx(-4.9172300e-02, 8) and s[4] == approx(4.9198035e-02, 8)
+    assert fed_density(orc, sp, phi_end, grad) == approx(-1.9246336785e-06, 11)
+    r = stats_scalar(orc, f[:nv].sum(axis=0, keepdims=True))
+    assert r[0] == approx(262144.00, 8)
+    assert r[3] == approx(0.99993867629, 11) and r[4] == approx(1.00004070448, 11)
+    ui = orc.interior(u)
+    for a, (lo, hi) in enumerate(((-1.1415683e-05, 1.1538576e-05), (-1.2562973e-05, 1.1995491e-05),
+                                  (-1.3597212e-05, 1.1403472e-05))):
+        assert ui[a].min() == approx(lo, 8) and ui[a].max() == approx(hi, 8)
