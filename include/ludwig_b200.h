@@ -135,6 +135,14 @@ int lb200_phi_force_calculation(lb200_t * ctx, const lb200_symm_param_t * sp);
 int lb200_phi_cahn_hilliard(lb200_t * ctx, const lb200_symm_param_t * sp);
 /* lb_collide (ndist = 1): src/collision.c:143-232, 253-593 */
 int lb200_lb_collide(lb200_t * ctx, const lb200_collide_param_t * cp);
+/* symmetric_lb (`free_energy symmetric_lb`, options.ndist = 2: array LB200_F holds [density | order parameter]
+ * distributions).  lb_collide with ndist == 2 -> lb_collision_binary: src/collision.c:157-159, 604-1013,
+ * 2856-3135; phi_lb_to_field / phi_lb_from_field: src/phi_lb_coupler.c:39-137.  lb200_step on such a context
+ * runs the symmetric_lb time step (src/ludwig.c:551-571, 683-685, 802-860). */
+int lb200_lb_collision_binary(lb200_t * ctx, const lb200_collide_param_t * cp, const lb200_symm_param_t * sp);
+int lb200_phi_lb_to_field(lb200_t * ctx);
+int lb200_phi_lb_from_field(lb200_t * ctx);
+
 /* lb_halo: src/lb_data.c:754-762, 1124-1477 */
 int lb200_lb_halo(lb200_t * ctx);
 /* lb_propagation: src/propagation.c:43-95, 153-240 */

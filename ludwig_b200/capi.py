@@ -103,6 +103,9 @@ def load_library():
     lib.lb200_phi_cahn_hilliard.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
     lib.lb200_lb_collide.argtypes = [C.c_void_p, C.POINTER(CollideParam)]
     lib.lb200_step.argtypes = [C.c_void_p, C.POINTER(CollideParam), C.POINTER(SymmParam), C.c_int]
+    lib.lb200_lb_collision_binary.argtypes = [C.c_void_p, C.POINTER(CollideParam), C.POINTER(SymmParam)]
+    lib.lb200_phi_lb_to_field.argtypes = [C.c_void_p]
+    lib.lb200_phi_lb_from_field.argtypes = [C.c_void_p]
     lib.lb200_launch_count.argtypes = [C.c_void_p]
     lib.lb200_set_knob.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.lb200_launch_count.restype = C.c_longlong
@@ -234,11 +237,29 @@ class Lb200:
         """lb200_set_knob: KNOB_WRAP (halo-free steps) / KNOB_PHI_SECTOR (one-sweep phi sector)."""
         self._check(self.lib.lb200_set_knob(self.h, knob, int(value)))
 
+    def lb_collision_binary(self, cp, sp):
+        self._check(self.lib.lb200_lb_collision_binary(self.h, C.byref(cp), C.byref(sp)))
+
+    def phi_lb_to_field(self):
+        self._check(self.lib.lb200_phi_lb_to_field(self.h))
+
+    def phi_lb_from_field(self):
+        self._check(self.lib.lb200_phi_lb_from_field(self.h))
+
     def step_api(self, cp, sp=None, nsteps=1):
         """The same time step through the individual reference-named entry points, in the
         reference driver's order (src/ludwig.c:528-860)."""
         for _ in range(nsteps):
             self.hydro_f_zero()
+            if self.ndist == 2:
+                self.phi_lb_to_field()
+                self.phi_halo()
+                self.phi_grad_compute()
+                self.hydro_u_zero()
+                self.lb_collision_binary(cp, sp)
+                self.lb_halo()
+                self.lb_propagation()
+                continue
             if sp is not None:
                 self.phi_halo()
                 self.phi_grad_compute()

@@ -204,6 +204,7 @@ static int model_init(int nvel, Lb200ModelDev * md) {
       ma[26][p] = 27.0*(cx*cx - cs2)*(cy*cy - cs2)*(cz*cz - cs2);
     }
   }
+  for (int p = 0; p < nvel; p++) md->wv[p] = wv[p];
   for (int m = 0; m < nvel; m++) {
     double wip = 0.0;
     for (int p = 0; p < nvel; p++) wip += wv[p]*md->ma[m][p]*md->ma[m][p];
@@ -262,6 +263,7 @@ static void symm_dev(const lb200_t * c, const lb200_symm_param_t * sp, Lb200Symm
   for (int a = 0; a < 3; a++) d->gm[a] = sp->gradmu[a];
   d->order = sp->adv_order;
   d->wz = (c->g.nl[2] == 1) ? 0.0 : 1.0;
+  d->rtau2 = 2.0/(1.0 + 2.0*sp->mobility);          // src/collision.c:1949-1950
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -277,9 +279,10 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   *pctx = nullptr;
   for (int a = 0; a < 3; a++) if (o->nlocal[a] < 1) return fail(LB200_EINVAL, "nlocal[%d] = %d", a, o->nlocal[a]);
   if (o->nhalo < 1 || o->nhalo > 3) return fail(LB200_EINVAL, "nhalo = %d", o->nhalo);
-  if (o->have_phi && o->nhalo < 2) return fail(LB200_EINVAL, "the symmetric FD route needs nhalo >= 2 (reference src/ludwig.c:1198)");
+  if (o->ndist != 1 && o->ndist != 2) return fail(LB200_EINVAL, "ndist = %d", o->ndist);
+  if (o->ndist == 2 && !o->have_phi) return fail(LB200_EINVAL, "ndist = 2 (symmetric_lb) needs have_phi (reference src/ludwig.c:1340-1383)");
+  if (o->have_phi && o->ndist == 1 && o->nhalo < 2) return fail(LB200_EINVAL, "the symmetric FD route needs nhalo >= 2 (reference src/ludwig.c:1198)");
   if (o->nvel != 15 && o->nvel != 19 && o->nvel != 27) return fail(LB200_EINVAL, "nvel = %d", o->nvel);
-  if (o->ndist != 1) return fail(LB200_EINVAL, "ndist = %d: only the single-distribution path is built (symmetric_lb is a 'next' row)", o->ndist);
   if (o->cart_size < 1 || o->cart_rank < 0 || o->cart_rank >= o->cart_size) return fail(LB200_EINVAL, "bad cart_size/cart_rank");
   if (o->halo_scheme != LB200_HALO_FULL && o->halo_scheme != LB200_HALO_REDUCED) return fail(LB200_EINVAL, "halo_scheme = %d", o->halo_scheme);
 
@@ -805,6 +808,7 @@ static int collide_async(lb200_t * c, const Lb200CollideDev & cd, const Lb200Geo
 int lb200_lb_collide(lb200_t * c, const lb200_collide_param_t * cp) {
   CTX_ENTER(c);
   if (cp == nullptr) return fail(LB200_EINVAL, "null parameters");
+  if (c->ndist == 2) return fail(LB200_ESTATE, "ndist = 2: the collision needs the free energy, call lb200_lb_collision_binary (reference lb_collide -> lb_collision_binary, src/collision.c:157-159)");
   Lb200CollideDev cd;
   int rc = collide_dev(c, cp, &cd);
   if (rc != 0) return rc;
@@ -831,6 +835,103 @@ int lb200_lb_propagation(lb200_t * c) {
   int rc = materialise_propagation(c);   // two propagations in a row: apply the first
   if (rc != 0) return rc;
   c->prop_pending = 1;
+  return 0;
+}
+
+// ---- symmetric_lb (ndist = 2) -------------------------------------------------------------------------
+
+// phi_lb_to_field, src/phi_lb_coupler.c:39-96.  With a propagation pending the sum runs over the pulled
+// populations (the state the reference's phi_lb_to_field sees after lb_propagation).
+static int phi_lb_to_field_async(lb200_t * c) {
+  if (c->prop_pending) {
+    int rc = ensure_f_halo(c);
+    if (rc != 0) return rc;
+  }
+  ProfScope ps(c, LB200_K_GRAD);
+  c->launches += c->k->phi_from_g(c->stream, c->g, c->model_d, c->prop_pending, c->f, c->phi);
+  return 0;
+}
+
+int lb200_phi_lb_to_field(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->ndist != 2) return fail(LB200_ESTATE, "phi_lb_to_field needs ndist = 2");
+  int rc = phi_lb_to_field_async(c);
+  if (rc != 0) return rc;
+  CTX_LEAVE_SYNC(c);
+}
+
+// phi_lb_from_field, src/phi_lb_coupler.c:98-137
+int lb200_phi_lb_from_field(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->ndist != 2) return fail(LB200_ESTATE, "phi_lb_from_field needs ndist = 2");
+  int rc = materialise_propagation(c);
+  if (rc != 0) return rc;
+  c->launches += c->k->phi_to_g(c->stream, c->g, c->nvel, c->phi, c->f);
+  CTX_LEAVE_SYNC(c);
+}
+
+static int collide_binary_async(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev & sd) {
+  if (c->prop_pending) {
+    int rc = ensure_f_halo(c);
+    if (rc != 0) return rc;
+  }
+  ProfScope ps(c, LB200_K_COLLIDE);
+  const double * force = (c->force_state == ZERO_PENDING) ? nullptr : c->force;
+  if (c->prop_pending) {
+    c->launches += c->k->collide_binary(c->stream, c->g, cd, sd, c->model_d, c->unrolled19, 1, c->f, c->fprime,
+					force, c->phi, c->grad, c->delsq, c->u);
+    double * t = c->f; c->f = c->fprime; c->fprime = t;
+    c->prop_pending = 0;
+  }
+  else {
+    c->launches += c->k->collide_binary(c->stream, c->g, cd, sd, c->model_d, c->unrolled19, 0, c->f, c->f,
+					force, c->phi, c->grad, c->delsq, c->u);
+  }
+  if (c->u_state == ZERO_PENDING) c->u_state = INTERIOR_ONLY;
+  return 0;
+}
+
+// lb_collide with ndist == 2 -> lb_collision_binary, src/collision.c:157-159, 604-1013
+int lb200_lb_collision_binary(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_param_t * sp) {
+  CTX_ENTER(c);
+  if (c->ndist != 2) return fail(LB200_ESTATE, "lb_collision_binary needs ndist = 2");
+  if (cp == nullptr || sp == nullptr) return fail(LB200_EINVAL, "null parameters");
+  Lb200CollideDev cd;
+  Lb200SymmDev sd;
+  int rc = collide_dev(c, cp, &cd);
+  if (rc != 0) return rc;
+  symm_dev(c, sp, &sd);
+  rc = collide_binary_async(c, cd, sd);
+  if (rc != 0) return rc;
+  CTX_LEAVE_SYNC(c);
+}
+
+// whole symmetric_lb time steps, reference order (src/ludwig.c:528-860 with ndist == 2): hydro_f_zero;
+// phi_lb_to_field; field_halo(phi); field_grad_compute; hydro_u_zero; lb_collide (binary); lb_halo;
+// lb_propagation.  The propagation is fused into the next phi_lb_to_field and collision (pull).
+static int step_lb2(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev & sd, int nsteps) {
+  int rc = 0;
+  for (int n = 0; n < nsteps; n++) {
+    c->force_state = ZERO_PENDING;
+    rc = phi_lb_to_field_async(c);
+    if (rc != 0) return rc;
+    rc = halo_field(c, c->phi, 1, c->g.nh, 0, nullptr);
+    if (rc != 0) return rc;
+    {
+      ProfScope ps(c, LB200_K_GRAD);
+      c->launches += c->k->grad27(c->stream, c->g, c->phi, c->grad, c->delsq);
+    }
+    c->u_state = ZERO_PENDING;
+    rc = collide_binary_async(c, cd, sd);
+    if (rc != 0) return rc;
+    rc = halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED, nullptr);
+    if (rc != 0) return rc;
+    c->prop_pending = 1;
+  }
+  c->phi_halo_valid = 0;
+  c->u_halo_valid = 0;
+  c->wrap_x_valid = 0;
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -1057,6 +1158,10 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   if (rc != 0) return rc;
   if (binary) symm_dev(c, sp, &sd);
   if (nsteps <= 0) return 0;
+  if (c->ndist == 2) {
+    if (!binary) return fail(LB200_EINVAL, "ndist = 2 needs the free-energy parameters");
+    return step_lb2(c, cd, sd, nsteps);
+  }
 
   {
     // Halo-free time steps (fully periodic lattices; binary fluid: all-fluid map, the one-sweep phi sector)

@@ -307,6 +307,282 @@ int launch_collide(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev &
 }
 
 // ---------------------------------------------------------------------------------------------
+// symmetric_lb: two distributions (reference `free_energy symmetric_lb`).
+//   phi_lb_to_field (src/phi_lb_coupler.c:39-96): phi = sum_p g_p, here optionally of the PULLED
+//     populations, i.e. of the state a pending lb_propagation would produce;
+//   lb_collision_binary -> lb_collision_mrt2_site (src/collision.c:604-1013): single-fluid collision with
+//     the thermodynamic stress fe_symm_str_v (src/symmetric.c:371-416) in the equilibrium stress, then the
+//     order-parameter distribution rebuilt from (phi, j_phi relaxed at rtau2 = 2/(1 + 2M), S_phi) by
+//     d3q19_mode2f_phi (src/collision.c:2856-3135: only the non-zero terms, literal constants) or the
+//     generic loop (:974-1008).  Interior sites, no status test, hydro->rho is not written (as the reference).
+// ---------------------------------------------------------------------------------------------
+
+template <bool PULL>
+__global__ void __launch_bounds__(TPB_MAX)
+phi_from_g_kernel(const Lb200Geom g, const Lb200ModelDev * __restrict__ md,
+		  const double * __restrict__ f, double * __restrict__ phi) {
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ic = 1 + blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+  const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+  const size_t ns = (size_t) g.nsites;
+  const int nvel = md->nvel;
+  double phi0 = 0.0;
+  for (int p = 0; p < nvel; p++) {
+    const int off = PULL ? (md->cv[p][0]*g.xs + md->cv[p][1]*g.ys + md->cv[p][2]) : 0;
+    phi0 += f[(size_t) (nvel + p)*ns + (index - off)];
+  }
+  phi[index] = phi0;
+}
+
+int launch_phi_from_g(cudaStream_t st, const Lb200Geom & g, const Lb200ModelDev * md, int pull,
+		      const double * f, double * phi) {
+  dim3 blk;
+  block_shape(g.nl[2], blk);
+  dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
+  if (pull) phi_from_g_kernel<true><<<grd, blk, 0, st>>>(g, md, f, phi);
+  else      phi_from_g_kernel<false><<<grd, blk, 0, st>>>(g, md, f, phi);
+  return 1;
+}
+
+__global__ void __launch_bounds__(TPB_MAX)
+phi_to_g_kernel(const Lb200Geom g, int nvel, const double * __restrict__ phi, double * __restrict__ f) {
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ic = 1 + blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+  const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+  const size_t ns = (size_t) g.nsites;
+  f[(size_t) nvel*ns + index] = phi[index];
+  for (int p = 1; p < nvel; p++) f[(size_t) (nvel + p)*ns + index] = 0.0;
+}
+
+int launch_phi_to_g(cudaStream_t st, const Lb200Geom & g, int nvel, const double * phi, double * f) {
+  dim3 blk;
+  block_shape(g.nl[2], blk);
+  dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
+  phi_to_g_kernel<<<grd, blk, 0, st>>>(g, nvel, phi, f);
+  return 1;
+}
+
+// hydrodynamic relaxation of the binary collision: equilibrium stress rho u u + P^th
+__device__ __forceinline__ void relax_hydro_binary(double * __restrict__ mode, const double force[3],
+						   const Lb200CollideDev & cp, const double sth[3][3],
+						   double u[3]) {
+  const double r3 = 1.0/3.0;
+  const double rho = mode[0];
+  const double rrho = 1.0/rho;
+  for (int ia = 0; ia < 3; ia++) u[ia] = rrho*(mode[1 + ia] + 0.5*force[ia]);
+
+  double s[3][3], seq[3][3];
+  s[0][0] = mode[4]; s[0][1] = mode[5]; s[0][2] = mode[6];
+  s[1][1] = mode[7]; s[1][2] = mode[8]; s[2][2] = mode[9];
+
+  double tr_s = 0.0, tr_seq = 0.0;
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) {
+#pragma unroll
+    for (int ib = ia; ib < 3; ib++) seq[ia][ib] = rho*u[ia]*u[ib] + sth[ia][ib];
+    tr_s   += s[ia][ia];
+    tr_seq += seq[ia][ia];
+  }
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) {
+    s[ia][ia]   -= r3*tr_s;
+    seq[ia][ia] -= r3*tr_seq;
+  }
+  tr_s = tr_s - cp.rtau_bulk*(tr_s - tr_seq);
+
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) {
+#pragma unroll
+    for (int ib = ia; ib < 3; ib++) {
+      s[ia][ib] -= cp.rtau*(s[ia][ib] - seq[ia][ib]);
+      if (ia == ib) s[ia][ib] += r3*tr_s;
+      s[ia][ib] += cp.tmr*(u[ia]*force[ib] + force[ia]*u[ib]);
+    }
+  }
+  for (int ia = 0; ia < 3; ia++) mode[1 + ia] += force[ia];
+  mode[4] = s[0][0]; mode[5] = s[0][1]; mode[6] = s[0][2];
+  mode[7] = s[1][1]; mode[8] = s[1][2]; mode[9] = s[2][2];
+}
+
+template <bool PULL, bool GHOST, bool UNROLLED19>
+__global__ void __launch_bounds__(TPB)
+collide_binary_kernel(const Lb200Geom g, const Lb200CollideDev cp, const Lb200SymmDev sp,
+		      const Lb200ModelDev * __restrict__ md,
+		      const double * __restrict__ fsrc, double * __restrict__ fdst,
+		      const double * __restrict__ hforce, const double * __restrict__ phi_,
+		      const double * __restrict__ grad, const double * __restrict__ delsq_,
+		      double * __restrict__ u_out) {
+
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ic = 1 + blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+
+  const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+  const size_t ns = (size_t) g.nsites;
+  const int nvel = UNROLLED19 ? 19 : md->nvel;
+
+  double force[3], u[3], gr[3], sth[3][3];
+  const double phi = phi_[index];
+  const double delsq = delsq_[index];
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) {
+    force[ia] = cp.fg[ia] + (hforce ? hforce[ia*ns + index] : 0.0);
+    gr[ia] = grad[ia*ns + index];
+  }
+  {
+    const double p0 = 0.5*sp.a*phi*phi + 0.75*sp.b*phi*phi*phi*phi - sp.kappa*phi*delsq
+      - 0.5*sp.kappa*(gr[0]*gr[0] + gr[1]*gr[1] + gr[2]*gr[2]);
+#pragma unroll
+    for (int ia = 0; ia < 3; ia++) {
+#pragma unroll
+      for (int ib = 0; ib < 3; ib++) sth[ia][ib] = p0*((ia == ib) ? 1.0 : 0.0) + sp.kappa*gr[ia]*gr[ib];
+    }
+  }
+
+  // ---- density distribution ----
+  if (UNROLLED19) {
+    double f[19], mode[19];
+#pragma unroll
+    for (int p = 0; p < 19; p++) {
+      const int off = PULL ? (CV19[p][0]*g.xs + CV19[p][1]*g.ys + CV19[p][2]) : 0;
+      f[p] = fsrc[p*ns + (index - off)];
+    }
+    d3q19_f2mode<GHOST>(f, mode);
+    relax_hydro_binary(mode, force, cp, sth, u);
+    if (GHOST) {
+#pragma unroll
+      for (int m = 10; m < 19; m++) mode[m] = mode[m] - cp.rtau_ghost[m]*(mode[m] - 0.0);
+    }
+    d3q19_mode2f<GHOST>(mode, f);
+#pragma unroll
+    for (int p = 0; p < 19; p++) fdst[p*ns + index] = f[p];
+  }
+  else {
+    double f[27], mode[27];
+    for (int p = 0; p < nvel; p++) {
+      const int off = PULL ? (md->cv[p][0]*g.xs + md->cv[p][1]*g.ys + md->cv[p][2]) : 0;
+      f[p] = fsrc[p*ns + (index - off)];
+    }
+    for (int m = 0; m < nvel; m++) {
+      double s = 0.0;
+      for (int p = 0; p < nvel; p++) s += md->ma[m][p]*f[p];
+      mode[m] = s;
+    }
+    relax_hydro_binary(mode, force, cp, sth, u);
+    for (int m = 10; m < nvel; m++) mode[m] = mode[m] - cp.rtau_ghost[m]*(mode[m] - 0.0);
+    for (int p = 0; p < nvel; p++) {
+      double s = 0.0;
+      for (int m = 0; m < nvel; m++) s += md->mi[p][m]*mode[m];
+      fdst[p*ns + index] = s;
+    }
+  }
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) u_out[ia*ns + index] = u[ia];
+
+  // ---- order-parameter distribution ----
+  const double mu = sp.a*phi + sp.b*phi*phi*phi - sp.kappa*delsq;
+  const double rtau2 = sp.rtau2;
+  double jphi[3] = {0.0, 0.0, 0.0};
+  double sphi[3][3];
+
+  if (UNROLLED19) {
+    double gp[19];
+#pragma unroll
+    for (int p = 0; p < 19; p++) {
+      const int off = PULL ? (CV19[p][0]*g.xs + CV19[p][1]*g.ys + CV19[p][2]) : 0;
+      gp[p] = fsrc[(19 + p)*ns + (index - off)];
+    }
+#pragma unroll
+    for (int p = 1; p < 19; p++) {
+#pragma unroll
+      for (int ia = 0; ia < 3; ia++) {
+	if (CV19[p][ia] > 0) jphi[ia] += gp[p];
+	if (CV19[p][ia] < 0) jphi[ia] += -gp[p];
+      }
+    }
+#pragma unroll
+    for (int ia = 0; ia < 3; ia++) {
+#pragma unroll
+      for (int ib = 0; ib < 3; ib++) sphi[ia][ib] = phi*u[ia]*u[ib] + mu*((ia == ib) ? 1.0 : 0.0);
+      jphi[ia] = jphi[ia] - rtau2*(jphi[ia] - phi*u[ia]);
+    }
+    const double q23 = 6.6666666666666663e-01, q13 = -3.3333333333333331e-01;
+#pragma unroll
+    for (int p = 0; p < 19; p++) {
+      double jdotc = 0.0, sphidotq = 0.0;
+#pragma unroll
+      for (int ia = 0; ia < 3; ia++) {
+	if (CV19[p][ia] > 0) jdotc += jphi[ia];
+	if (CV19[p][ia] < 0) jdotc -= jphi[ia];
+      }
+#pragma unroll
+      for (int ia = 0; ia < 3; ia++) {
+#pragma unroll
+	for (int ib = 0; ib < 3; ib++) {
+	  const int cc = CV19[p][ia]*CV19[p][ib];
+	  if (ia == ib) sphidotq += sphi[ia][ib]*(cc ? q23 : q13);
+	  else if (cc > 0) sphidotq += sphi[ia][ib]*1.0;
+	  else if (cc < 0) sphidotq += sphi[ia][ib]*-1.0;
+	}
+      }
+      const double w = (p == 0) ? (12.0/36.0) : ((CV19[p][0]*CV19[p][0] + CV19[p][1]*CV19[p][1] + CV19[p][2]*CV19[p][2] == 1) ? (2.0/36.0) : (1.0/36.0));
+      double v = w*(jdotc*3.0 + sphidotq*(9.0/2.0));
+      if (p == 0) v = v + phi;
+      fdst[(19 + p)*ns + index] = v;
+    }
+  }
+  else {
+    const double cs2 = (1.0/3.0);
+    double gp[27];
+    for (int p = 0; p < nvel; p++) {
+      const int off = PULL ? (md->cv[p][0]*g.xs + md->cv[p][1]*g.ys + md->cv[p][2]) : 0;
+      gp[p] = fsrc[(size_t) (nvel + p)*ns + (index - off)];
+    }
+    for (int p = 1; p < nvel; p++)
+      for (int ia = 0; ia < 3; ia++) jphi[ia] += md->cv[p][ia]*gp[p];
+    for (int ia = 0; ia < 3; ia++) {
+      for (int ib = 0; ib < 3; ib++) sphi[ia][ib] = phi*u[ia]*u[ib] + mu*((ia == ib) ? 1.0 : 0.0);
+      jphi[ia] = jphi[ia] - rtau2*(jphi[ia] - phi*u[ia]);
+    }
+    for (int p = 0; p < nvel; p++) {
+      const int dp0 = (p == 0);
+      double jdotc = 0.0, sphidotq = 0.0;
+      for (int ia = 0; ia < 3; ia++) {
+	jdotc += jphi[ia]*md->cv[p][ia];
+	for (int ib = 0; ib < 3; ib++) {
+	  sphidotq += sphi[ia][ib]*(md->cv[p][ia]*md->cv[p][ib] - cs2*((ia == ib) ? 1.0 : 0.0));
+	}
+      }
+      fdst[(size_t) (nvel + p)*ns + index] = md->wv[p]*(jdotc*3.0 + sphidotq*4.5) + phi*dp0;
+    }
+  }
+}
+
+int launch_collide_binary(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev & cp,
+			  const Lb200SymmDev & sp, const Lb200ModelDev * md, int unrolled19, int pull,
+			  const double * fsrc, double * fdst, const double * force, const double * phi,
+			  const double * grad, const double * delsq, double * u) {
+  dim3 blk;
+  block_shape_n(g.nl[2], TPB, blk);
+  dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
+#define LB200_GO(P, G, U) collide_binary_kernel<P, G, U><<<grd, blk, 0, st>>>(g, cp, sp, md, fsrc, fdst, force, phi, grad, delsq, u)
+  if (unrolled19) {
+    if (pull) { if (cp.ghost) LB200_GO(true, true, true); else LB200_GO(true, false, true); }
+    else      { if (cp.ghost) LB200_GO(false, true, true); else LB200_GO(false, false, true); }
+  }
+  else {
+    if (pull) LB200_GO(true, true, false); else LB200_GO(false, true, false);
+  }
+#undef LB200_GO
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // lb_propagation as a stand-alone sweep: reference src/propagation.c:153-200.
 // x in [1,N], every y,z of the allocation; y/z halo sites copy themselves.
 // ---------------------------------------------------------------------------------------------
@@ -1477,4 +1753,7 @@ const Lb200Kernels LB200_TABLE = {
   launch_force_ch,
   launch_phi_sector,
   launch_zero_outside,
+  launch_phi_from_g,
+  launch_phi_to_g,
+  launch_collide_binary,
 };

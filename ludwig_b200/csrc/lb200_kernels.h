@@ -31,11 +31,13 @@ struct Lb200SymmDev {
   double gm[3];
   int order;
   double wz;            // 0 if nlocal[Z] == 1
+  double rtau2;         // 2/(1 + 2 mobility): relaxation of the order-parameter flux (symmetric_lb)
 };
 
 struct Lb200ModelDev {       // generic (non-unrolled) model tables
   int nvel;
   signed char cv[27][3];
+  double wv[27];
   double ma[27][27];
   double mi[27][27];
 };
@@ -69,6 +71,15 @@ struct Lb200Kernels {
 		    const double * u, double * grad, double * delsq, double * force, double * phinew);
   // zero everything outside the interior (ncomp components)
   int (*zero_outside)(cudaStream_t, const Lb200Geom &, int ncomp, double * data);
+  // symmetric_lb (ndist = 2): phi = sum_p g_p (of the pulled populations if pull), g = (phi, 0, ..., 0),
+  // and the two-distribution collision (pull = 1: fdst <- collide(pull(fsrc)), else in place, fdst == fsrc)
+  int (*phi_from_g)(cudaStream_t, const Lb200Geom &, const Lb200ModelDev *, int pull, const double * f,
+		    double * phi);
+  int (*phi_to_g)(cudaStream_t, const Lb200Geom &, int nvel, const double * phi, double * f);
+  int (*collide_binary)(cudaStream_t, const Lb200Geom &, const Lb200CollideDev &, const Lb200SymmDev &,
+			const Lb200ModelDev *, int unrolled19, int pull, const double * fsrc, double * fdst,
+			const double * force, const double * phi, const double * grad, const double * delsq,
+			double * u);
 };
 
 extern const Lb200Kernels lb200_kernels_fast;
