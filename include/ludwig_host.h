@@ -298,6 +298,10 @@ int phi_ch_create(pe_t * pe, cs_t * cs, lees_edw_t * le, phi_ch_info_t * info, p
 int phi_ch_free(phi_ch_t * pch);
 int phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t * hydro, map_t * map, noise_t * noise);
 int advection_order_set(const int order);
+
+/* ---- symmetric_lb coupling: src/phi_lb_coupler.h (lb_collide dispatches on lb->ndist, src/collision.c:157-159) */
+int phi_lb_to_field(field_t * phi, lb_t * lb);
+int phi_lb_from_field(field_t * phi, lb_t * lb);
 int advection_order(int * order);
 
 /* ---- collision and propagation: src/collision.h:27-28, src/propagation.h:21 ------------------- */

@@ -131,6 +131,13 @@ int cs_index(cs_t * cs, int ic, int jc, int kc) {
   return (ic + cs->nhalo - 1)*cs->nall[Y]*cs->nall[Z] + (jc + cs->nhalo - 1)*cs->nall[Z] + (kc + cs->nhalo - 1);
 }
 
+static int cs_index_is_interior(cs_t * cs, int index) {
+  const int kc = index % cs->nall[Z] - cs->nhalo + 1;
+  const int jc = (index/cs->nall[Z]) % cs->nall[Y] - cs->nhalo + 1;
+  const int ic = index/(cs->nall[Y]*cs->nall[Z]) - cs->nhalo + 1;
+  return ic >= 1 && ic <= cs->nlocal[X] && jc >= 1 && jc <= cs->nlocal[Y] && kc >= 1 && kc <= cs->nlocal[Z];
+}
+
 int cs_strides(cs_t * cs, int * xs, int * ys, int * zs) {
   *xs = cs->nall[Y]*cs->nall[Z]; *ys = cs->nall[Z]; *zs = 1;
   return 0;
@@ -276,7 +283,7 @@ int lb_data_create(pe_t * pe, cs_t * cs, const lb_data_options_t * opts, lb_t **
   lb_t * lb = (lb_t *) calloc(1, sizeof(lb_t));
   assert(pe); assert(cs); assert(opts); assert(plb);
   if (lb == NULL) pe_fatal(pe, "calloc(1, lb_t) failed\n");
-  if (opts->ndist != 1) pe_fatal(pe, "ndist = %d: the two-distribution model is outside this build (SURVEY 8f)\n", opts->ndist);
+  if (opts->ndist != 1 && opts->ndist != 2) pe_fatal(pe, "ndist = %d\n", opts->ndist);
   lb->pe = pe; lb->cs = cs;
   lb->ndim = opts->ndim; lb->nvel = opts->nvel; lb->ndist = opts->ndist;
   lb->nrelax = opts->nrelax; lb->haloscheme = opts->halo; lb->opts = *opts;
@@ -696,7 +703,6 @@ int phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t * hydro,
 int lb_collide(lb_t * lb, hydro_t * hydro, map_t * map, noise_t * noise, fe_t * fe, visc_t * visc) {
   physics_t * phys = NULL;
   lb200_collide_param_t cp;
-  (void) fe;
   if (hydro == NULL) return 0;
   assert(lb);
   assert(map);
@@ -709,6 +715,32 @@ int lb_collide(lb_t * lb, hydro_t * hydro, map_t * map, noise_t * noise, fe_t * 
   physics_eta_shear(phys, &cp.eta_shear);
   physics_eta_bulk(phys, &cp.eta_bulk);
   physics_fbody(phys, cp.force_global);
+  if (lb->ndist == 2) {
+    /* lb_collision_binary(lb, hydro, noise, (fe_symm_t *) fe, visc), src/collision.c:157-159 */
+    lb200_symm_param_t sp;
+    if (fe == NULL) pe_fatal(lb->pe, "lb_collide: ndist = 2 needs the symmetric free energy\n");
+    symm_param_from(fe, &sp);
+    b200_check(lb->pe, lb200_lb_collision_binary(cs_b200_context(lb->cs), &cp, &sp), "lb_collision_binary");
+    return 0;
+  }
   b200_check(lb->pe, lb200_lb_collide(cs_b200_context(lb->cs), &cp), "lb_collide");
+  return 0;
+}
+
+/* src/phi_lb_coupler.c:39-137 */
+int phi_lb_to_field(field_t * phi, lb_t * lb) {
+  assert(phi); assert(lb);
+  b200_check(lb->pe, lb200_phi_lb_to_field(cs_b200_context(lb->cs)), "phi_lb_to_field");
+  return 0;
+}
+
+int phi_lb_from_field(field_t * phi, lb_t * lb) {
+  /* host operation in the reference too: move phi into the non-propagating population */
+  assert(phi); assert(lb);
+  for (int index = 0; index < lb->nsite; index++) {
+    if (!cs_index_is_interior(lb->cs, index)) continue;
+    lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, LB_PHI, 0)] = phi->data[addr_rank0(phi->nsites, index)];
+    for (int p = 1; p < lb->nvel; p++) lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, LB_PHI, p)] = 0.0;
+  }
   return 0;
 }

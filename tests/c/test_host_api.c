@@ -288,6 +288,102 @@ static void test_binary_step(int order, int nsteps, int strict) {
   map_free(&map); hydro_free(hydro); lb_free(lb); lees_edw_free(le); physics_free(phys); cs_free(cs);
 }
 
+/* `free_energy symmetric_lb`: two distributions, the calls of src/ludwig.c:528-860 with ndist == 2 */
+static void test_symmetric_lb(int nvel, int strict) {
+  cs_t * cs = NULL;
+  physics_t * phys = NULL;
+  lees_edw_t * le = NULL;
+  lb_t * lb = NULL;
+  hydro_t * hydro = NULL;
+  map_t * map = NULL;
+  field_t * phi = NULL;
+  field_grad_t * phi_grad = NULL;
+  fe_symm_t * fe = NULL;
+  int ntotal[3] = {8, 6, 34};
+  int nlocal[3], ns, nsteps = 5;
+  double fbody[3] = {1.0e-6, 2.0e-6, -1.0e-6};
+  const double zero[3] = {0.0, 0.0, 0.0};
+  unsigned int seed = 77;
+
+  cs_create(pe, &cs);
+  cs_nhalo_set(cs, 1);
+  cs_ntotal_set(cs, ntotal);
+  cs_init(cs);
+  cs_nlocal(cs, nlocal);
+  cs_nsites(cs, &ns);
+  physics_create(pe, &phys);
+  physics_eta_shear_set(phys, 0.00625);
+  physics_eta_bulk_set(phys, 0.00625);
+  physics_fbody_set(phys, fbody);
+  physics_mobility_set(phys, 3.75);
+  { lees_edw_options_t o = {0}; lees_edw_create(pe, cs, &o, &le); }
+  { lb_data_options_t o = lb_data_options_ndim_nvel_ndist(3, nvel, 2); lb_data_create(pe, cs, &o, &lb); }
+  { hydro_options_t o = hydro_options_default(); hydro_create(pe, cs, le, &o, &hydro); }
+  { map_options_t o = map_options_default(); map_create(pe, cs, &o, &map); }
+  { field_options_t o = field_options_ndata_nhalo(1, 1); field_create(pe, cs, le, "phi", &o, &phi); }
+  field_grad_create(pe, phi, 2, &phi_grad);
+  field_grad_set(phi_grad, grad_3d_27pt_fluid_d2, NULL);
+  fe_symm_create(pe, cs, phi, phi_grad, &fe);
+  { fe_symm_param_t p = {.a = -0.00625, .b = 0.00625, .kappa = 0.004}; fe_symm_param_set(fe, p); }
+
+  lb_init_rest_f(lb, 1.0);
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++)
+	field_scalar_set(phi, cs_index(cs, ic, jc, kc), 0.1*(frand(&seed) - 0.5));
+  phi_lb_from_field(phi, lb);                        /* src/ludwig.c:402 */
+
+  orc_geom_t g = {{nlocal[X], nlocal[Y], nlocal[Z]}, 1, {1, 1, 1}};
+  orc_model_t model;
+  orc_collide_param_t ocp = {ORC_RELAX_M10, 1.0, 0.00625, 0.00625, {fbody[0], fbody[1], fbody[2]}};
+  orc_symm_param_t osp = {-0.00625, 0.00625, 0.004, 3.75, {0.0, 0.0, 0.0}, 1};
+  double * of = malloc(sizeof(double)*2*nvel*ns), * ophi = calloc(ns, sizeof(double));
+  double * ou = calloc(3*ns, sizeof(double)), * oforce = calloc(3*ns, sizeof(double));
+  double * ograd = calloc(3*ns, sizeof(double)), * odelsq = calloc(ns, sizeof(double));
+  orc_model_create(nvel, &model);
+  memcpy(of, lb->f, sizeof(double)*2*nvel*ns);
+
+  lb_memcpy(lb, tdpMemcpyHostToDevice);
+  for (int n = 0; n < nsteps; n++) {
+    hydro_f_zero(hydro, zero);
+    phi_lb_to_field(phi, lb);
+    field_halo(phi);
+    field_grad_compute(phi_grad);
+    hydro_u_zero(hydro, zero);
+    lb_collide(lb, hydro, map, NULL, (fe_t *) fe, NULL);
+    lb_halo(lb);
+    lb_propagation(lb);
+  }
+  lb_memcpy(lb, tdpMemcpyDeviceToHost);
+  field_memcpy(phi, tdpMemcpyDeviceToHost);
+  hydro_memcpy(hydro, tdpMemcpyDeviceToHost);
+
+  orc_step_lb2(&g, &model, &ocp, &osp, 0, nsteps, of, ophi, ou, oforce, ograd, odelsq);
+
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++) {
+	int index = cs_index(cs, ic, jc, kc);
+	for (int n = 0; n < 2; n++)
+	  for (int p = 0; p < nvel; p++) {
+	    double a = lb->f[LB_ADDR(ns, 2, nvel, index, n, p)], b = of[(size_t) (n*nvel + p)*ns + index];
+	    if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-12*0.34 + 1e-14);
+	  }
+	{
+	  double a = phi->data[index], b = ophi[index];
+	  if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-12*0.05 + 1e-14);
+	}
+	for (int ia = 0; ia < 3; ia++) {
+	  double a = hydro->u->data[addr_rank1(ns, 3, index, ia)], b = ou[(size_t) ia*ns + index];
+	  if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-14);
+	}
+      }
+  printf("PASS test_symmetric_lb nvel=%d nsteps=%d %s\n", nvel, nsteps, strict ? "bit-exact" : "within tolerance");
+  free(of); free(ophi); free(ou); free(oforce); free(ograd); free(odelsq);
+  fe_symm_free(fe); field_grad_free(phi_grad); field_free(phi);
+  map_free(&map); hydro_free(hydro); lb_free(lb); lees_edw_free(le); physics_free(phys); cs_free(cs);
+}
+
 /* single-fluid collision + propagation steps, each relaxation scheme */
 static void test_single_fluid(int nvel, lb_relaxation_enum_t nrelax, int strict) {
   cs_t * cs = NULL;
@@ -374,6 +470,8 @@ int main(void) {
   test_single_fluid(27, LB_RELAXATION_M10, strict);
   test_binary_step(1, 5, strict);
   test_binary_step(3, 5, strict);
+  test_symmetric_lb(19, strict);
+  test_symmetric_lb(15, strict);
 
   pe_free(pe);
   printf("PASS test_host_api (%s)\n", strict ? "strict" : "fast");
