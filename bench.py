@@ -44,8 +44,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (started before the warm-up so
+    that the tool's own start-up time does not eat a short timed region; only samples whose timestamp
+    falls inside [mark_begin, mark_end] are reported, falling back to every sample taken under load)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -53,45 +55,68 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            # nvidia-smi needs ~1 s to produce its first line: wait for it so a short run is still sampled
+            t_end = time.time() + 5.0
+            while time.time() < t_end and os.path.getsize(self.path) == 0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 t = [x.strip() for x in line.split(",")]
-                if len(t) < 9:
+                if len(t) < 10:
                     continue
                 try:
-                    sm.append(float(t[1])); mx.append(float(t[2]))
+                    ts = datetime.datetime.strptime(t[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(t[2]), float(t[3]), float(t[4]), t[6:10]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1 + 0.02]
+        where = "timed region"
+        if not inside:
+            # very short timed region: every sample taken under load (warm-up included)
+            inside = [r for r in rows if r[3] > 300.0] or rows
+            where = "warm-up + timed region (under load)"
+        if inside:
+            sm = sorted(r[1] for r in inside)
+            reasons = set()
+            for r in inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in inside), reasons=sorted(reasons),
+                       samples=len(inside), window=where, power_w_max=max(r[3] for r in inside))
         return out
 
 
@@ -246,19 +271,21 @@ def run_ours(args, rank, local_rank, world):
         sim.memcpy_async(lb.RHO, h_rho.data_ptr(), D2H)
 
     # ---- device-resident timing: inputs in HBM before the timed region -------------------------------
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     upload()
     sim.sync()
     sim.step(cp, sp, args.warmup)
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     l0 = sim.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     sim.step(cp, sp, args.steps)
     e1.record(stream)
     barrier()
+    clocks.mark_end()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = sim.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
