@@ -28,6 +28,10 @@ CASES = {
     "single_d3q19_bgk_reduced": ("single", 19, (6, 5, 7), 6, dict(nrelax=1, reduced=1, fbody=(0.0, 0.0, 0.0))),
     "single_d3q15_trt": ("single", 15, (5, 6, 4), 6, dict(nrelax=2, reduced=0, fbody=(1e-6, 0.0, 0.0))),
     "single_d3q27_bgk": ("single", 27, (4, 5, 6), 6, dict(nrelax=1, reduced=0, fbody=(0.0, 2e-6, 0.0))),
+    # free_energy symmetric_lb: two distributions, lb_collision_binary
+    "symmlb_d3q19": ("symmlb", 19, (6, 7, 8), 5, dict(nrelax=0, reduced=0, fbody=(1e-6, -2e-6, 1e-6), mobility=3.75)),
+    "symmlb_d3q19_trt_reduced": ("symmlb", 19, (5, 6, 7), 4, dict(nrelax=2, reduced=1, fbody=(0.0, 0.0, 0.0), mobility=0.45)),
+    "symmlb_d3q15": ("symmlb", 15, (5, 5, 6), 4, dict(nrelax=0, reduced=0, fbody=(0.0, 1e-6, 0.0), mobility=3.75)),
 }
 
 
@@ -49,6 +53,20 @@ def main():
                     out[k] = s.get(w)
             out.update(nhalo=nhalo, adv_order=o["adv_order"], gradmu=np.array(o["gradmu"], dtype=float),
                        eta=0.00625, **BINARY)
+        elif kind == "symmlb":
+            nhalo = 1
+            par = dict(BINARY, mobility=o["mobility"])
+            with rh.RefSim(nlocal, nhalo=nhalo, nvel=nvel, ndist=2, have_phi=1, nrelax=o["nrelax"], eta_shear=0.00625,
+                           halo_reduced=o["reduced"], fbody=o["fbody"], **par) as s:
+                s.init_rest(1.0)
+                s.init_spinodal(8361235, 0.0, 0.1)
+                s.op("phi_lb_from_field")
+                out["f0"] = s.get(rh.REF_F)
+                s.step(nsteps)
+                for k, w in (("f", rh.REF_F), ("phi", rh.REF_PHI), ("u", rh.REF_U), ("grad", rh.REF_GRAD),
+                             ("delsq", rh.REF_DELSQ)):
+                    out[k] = s.get(w)
+            out.update(nhalo=nhalo, reduced=o["reduced"], eta=0.00625, **par)
         else:
             nhalo = 1
             with rh.RefSim(nlocal, nhalo=nhalo, nrelax=o["nrelax"], halo_reduced=o["reduced"], eta_shear=0.05,

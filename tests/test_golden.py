@@ -15,6 +15,13 @@ def run_oracle(g):
     orc = Oracle(g["nlocal"], nhalo=g["nhalo"], nvel=g["nvel"])
     z = lambda k: np.zeros((k, orc.nsites))
     st = dict(f=g["f0"].copy(), u=z(3), rho=z(1), force=z(3))
+    if g["kind"] == "symmlb":
+        st = dict(f=g["f0"].copy(), phi=z(1), u=z(3), grad=z(3), delsq=z(1))
+        cp = orc.collide_param(g["nrelax"], 1.0, g["eta"], force=tuple(g["fbody"]))
+        sp = orc.symm_param(g["a"], g["b"], g["kappa"], g["mobility"])
+        orc.step_lb2(cp, sp, g["nsteps"], st["f"], st["phi"], st["u"], z(3), st["grad"], st["delsq"],
+                     halo_reduced=g["reduced"])
+        return orc, st
     if g["kind"] == "binary":
         st.update(phi=g["phi0"].copy(), grad=z(3), delsq=z(1))
         cp = orc.collide_param(g["nrelax"], 1.0, g["eta"], force=tuple(g["fbody"]))
@@ -44,6 +51,20 @@ def test_cuda_reproduces_reference_golden(name, strict):
     g = golden_util.load(name)
     binary = g["kind"] == "binary"
     orc = Oracle(g["nlocal"], nhalo=g["nhalo"], nvel=g["nvel"])
+    if g["kind"] == "symmlb":
+        with lb.Lb200(g["nlocal"], nhalo=g["nhalo"], nvel=g["nvel"], ndist=2, have_phi=True,
+                      halo_scheme=lb.HALO_REDUCED if g["reduced"] else lb.HALO_FULL,
+                      math=lb.MATH_STRICT if strict else lb.MATH_FAST) as sim:
+            sim.put(lb.F, g["f0"])
+            sim.step(lb.CollideParam.make(g["nrelax"], 1.0, g["eta"], force=tuple(g["fbody"])),
+                     lb.SymmParam.make(g["a"], g["b"], g["kappa"], g["mobility"]), g["nsteps"])
+            for k, arr in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("grad", lb.GRAD), ("delsq", lb.DELSQ)):
+                got, ref = orc.interior(sim.get(arr)), orc.interior(g[k])
+                if strict:
+                    assert np.array_equal(got, ref), (name, k)
+                else:
+                    assert close_fast(got, ref), (name, k)
+        return
     with lb.Lb200(g["nlocal"], nhalo=g["nhalo"], nvel=g["nvel"], have_phi=binary,
                   halo_scheme=lb.HALO_REDUCED if g.get("reduced", 0) else lb.HALO_FULL,
                   math=lb.MATH_STRICT if strict else lb.MATH_FAST) as sim:
