@@ -62,7 +62,10 @@ enum lb200_array {
   LB200_FORCE = 4,          /* hydro->force       3 x nsites */
   LB200_GRAD = 5,           /* field_grad->grad   3 x nsites            src/field_grad.h:24-42 */
   LB200_DELSQ = 6,          /* field_grad->delsq  1 x nsites */
-  LB200_MAP = 7             /* map->status        1 x nsites, passed as double, 0 = MAP_FLUID  src/map.h:26-48 */
+  LB200_MAP = 7,            /* map->status        1 x nsites, passed as double, 0 = MAP_FLUID  src/map.h:26-48 */
+  LB200_GRAD_DELSQ = 8,     /* field_grad->grad_delsq  3 x nsites  (after lb200_phi_grad_compute_d4) */
+  LB200_DELSQ_DELSQ = 9,    /* field_grad->delsq_delsq 1 x nsites */
+  LB200_STR = 10            /* pth->str           9 x nsites, component ia*3 + ib (after lb200_pth_stress_compute) */
 };
 
 typedef struct lb200_options_s {
@@ -70,7 +73,7 @@ typedef struct lb200_options_s {
   int nhalo;                /* cs_nhalo: 1 (single fluid) or 2 (binary fluid FD route, src/ludwig.c:1198) */
   int periodic[3];          /* cs periodicity of the GLOBAL system */
   int nvel;                 /* 15, 19 or 27 (-D_D3Q15_/-D_D3Q19_/-D_D3Q27_, src/lb_data.h:30-42) */
-  int ndist;                /* 1 (2 = symmetric_lb: not yet supported -> LB200_EINVAL) */
+  int ndist;                /* 1, or 2 = symmetric_lb (needs have_phi; nhalo >= 1) */
   int have_phi;             /* allocate phi, grad, delsq (free_energy symmetric) */
   int halo_scheme;          /* enum lb200_halo_scheme */
   int math;                 /* enum lb200_math */
@@ -128,6 +131,14 @@ int lb200_phi_halo(lb200_t * ctx);
 /* field_grad_compute with d2 = grad_3d_27pt_fluid_d2: src/field_grad.c:319-340,
  * src/gradient_3d_27pt_fluid.c:76-99, 219-363 */
 int lb200_phi_grad_compute(lb200_t * ctx);
+/* field_grad level 4, d4 = grad_3d_27pt_fluid_d4 (src/gradient_3d_27pt_fluid.c:112-134): the same operator
+ * applied to delsq on [1-(nhalo-2), N+(nhalo-2)]^3 -> LB200_GRAD_DELSQ, LB200_DELSQ_DELSQ */
+int lb200_phi_grad_compute_d4(lb200_t * ctx);
+/* the two halves of phi_force_calculation as separate operators: pth_stress_compute
+ * (src/phi_force_stress.c:171-284, P stored in LB200_STR) and pth_force_fluid_driver
+ * (src/phi_force_colloid.c:274-465, force -= div P from the stored stress) */
+int lb200_pth_stress_compute(lb200_t * ctx, const lb200_symm_param_t * sp);
+int lb200_pth_force_fluid_driver(lb200_t * ctx);
 /* phi_force_calculation, stress-divergence method, fluid only: src/phi_force.c:74-137,
  * src/phi_force_stress.c:171-284, src/phi_force_colloid.c:274-465 */
 int lb200_phi_force_calculation(lb200_t * ctx, const lb200_symm_param_t * sp);

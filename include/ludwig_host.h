@@ -148,6 +148,7 @@ int lb_0th_moment(lb_t * lb, int index, lb_dist_enum_t nd, double * rho);
 int lb_1st_moment(lb_t * lb, int index, lb_dist_enum_t nd, double g[3]);
 int lb_1st_moment_equilib_set(lb_t * lb, int index, double rho, double u[3]);
 int lb_collision_relaxation_set(lb_t * lb, lb_relaxation_enum_t nrelax);     /* src/collision.h:30 */
+int lb_collide_param_commit(lb_t * lb);                                      /* src/lb_data.h:166 */
 
 /* ---- field_t: src/field.h:68-130, src/field_options.h ---------------------------------------- */
 typedef struct field_options_s {int ndata; int nhcomm; int haloscheme; int haloverbose; int usefirsttouch;} field_options_t;
@@ -173,6 +174,8 @@ int field_create(pe_t * pe, cs_t * cs, lees_edw_t * le, const char * name, const
 int field_free(field_t * obj);
 int field_memcpy(field_t * obj, tdpMemcpyKind flag);
 int field_halo(field_t * obj);
+typedef enum field_halo_enum {FIELD_HALO_HOST, FIELD_HALO_TARGET, FIELD_HALO_OPENMP} field_halo_enum_t;   /* src/field_options.h:22-24 */
+int field_halo_swap(field_t * obj, field_halo_enum_t flag);
 int field_nf(field_t * obj, int * nop);
 int field_scalar(field_t * obj, int index, double * phi);
 int field_scalar_set(field_t * obj, int index, double phi);
@@ -190,6 +193,9 @@ struct field_grad_s {
   int nsite;
   double * grad;                 /* addr_rank2(nsite, nf, 3, index, n, ia) */
   double * delsq;                /* addr_rank1(nsite, nf, index, n) */
+  double * grad_delsq;           /* level >= 4: addr_rank2(nsite, nf, 3, index, n, ia) */
+  double * delsq_delsq;          /* level >= 4 */
+  int d4_on_device;
   grad_ft d2;
   grad_ft d4;
   field_grad_t * target;
@@ -203,6 +209,7 @@ int field_grad_memcpy(field_grad_t * obj, tdpMemcpyKind flag);
 int field_grad_scalar_grad(field_grad_t * obj, int index, double grad[3]);
 int field_grad_scalar_delsq(field_grad_t * obj, int index, double * delsq);
 int grad_3d_27pt_fluid_d2(field_grad_t * fg);
+int grad_3d_27pt_fluid_d4(field_grad_t * fg);
 
 /* ---- hydro_t: src/hydro.h:32-62, src/hydro_options.h ------------------------------------------ */
 typedef struct hydro_options_s {int nhcomm; field_options_t rho; field_options_t u; field_options_t force; field_options_t eta;} hydro_options_t;
@@ -269,6 +276,7 @@ struct fe_symm_s {
 };
 int fe_symm_create(pe_t * pe, cs_t * cs, field_t * f, field_grad_t * grd, fe_symm_t ** p);
 int fe_symm_free(fe_symm_t * fe);
+int fe_symm_target(fe_symm_t * fe, fe_t ** target);
 int fe_symm_param_set(fe_symm_t * fe, fe_symm_param_t values);
 int fe_symm_param(fe_symm_t * fe, fe_symm_param_t * values);
 int fe_symm_fed(fe_symm_t * fe, int index, double * fed);     /* host arrays */
@@ -285,6 +293,8 @@ struct pth_s {pe_t * pe; cs_t * cs; int method; int nsites; pth_t * target;};
 typedef struct wall_s wall_t;          /* never dereferenced here: pass NULL (no walls in scope) */
 int pth_create(pe_t * pe, cs_t * cs, int method, pth_t ** pth);
 int pth_free(pth_t * pth);
+int pth_stress_compute(pth_t * pth, fe_t * fe);
+int pth_force_fluid_driver(pth_t * pth, hydro_t * hydro);
 int phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t * wall, pth_t * pth, fe_t * fe,
 			  map_t * map, field_t * phi, hydro_t * hydro);
 

@@ -3,14 +3,14 @@ import ctypes as C
 import os
 import numpy as np
 
-F, PHI, U, RHO, FORCE, GRAD, DELSQ, MAP = range(8)
+F, PHI, U, RHO, FORCE, GRAD, DELSQ, MAP, GRAD_DELSQ, DELSQ_DELSQ, STR = range(11)
 RELAX_M10, RELAX_BGK, RELAX_TRT = 0, 1, 2
 HALO_FULL, HALO_REDUCED = 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 H2D, D2H = 1, 2
 KNOB_WRAP, KNOB_PHI_SECTOR = 1, 2
 
-_NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1}
+_NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1, GRAD_DELSQ: 3, DELSQ_DELSQ: 1, STR: 9}
 
 
 class Lb200Error(RuntimeError):
@@ -96,8 +96,10 @@ def load_library():
     lib.lb200_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.lb200_memcpy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.lb200_memcpy_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.lb200_pth_stress_compute.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
     for name in ("lb200_sync", "lb200_hydro_f_zero", "lb200_hydro_u_zero", "lb200_hydro_u_halo",
-                 "lb200_phi_halo", "lb200_phi_grad_compute", "lb200_lb_halo", "lb200_lb_propagation"):
+                 "lb200_phi_halo", "lb200_phi_grad_compute", "lb200_lb_halo", "lb200_lb_propagation",
+                 "lb200_phi_grad_compute_d4", "lb200_pth_force_fluid_driver"):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.lb200_phi_force_calculation.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
     lib.lb200_phi_cahn_hilliard.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
@@ -214,6 +216,15 @@ class Lb200:
 
     def phi_grad_compute(self):
         self._check(self.lib.lb200_phi_grad_compute(self.h))
+
+    def phi_grad_compute_d4(self):
+        self._check(self.lib.lb200_phi_grad_compute_d4(self.h))
+
+    def pth_stress_compute(self, sp):
+        self._check(self.lib.lb200_pth_stress_compute(self.h, C.byref(sp)))
+
+    def pth_force_fluid_driver(self):
+        self._check(self.lib.lb200_pth_force_fluid_driver(self.h))
 
     def phi_force_calculation(self, sp):
         self._check(self.lib.lb200_phi_force_calculation(self.h, C.byref(sp)))

@@ -58,6 +58,9 @@ struct lb200_s {
   double * force;
   double * grad;
   double * delsq;
+  double * grad_delsq;       // field_grad level 4 (grad_3d_27pt_fluid_d4), allocated on first use
+  double * delsq_delsq;
+  double * str;              // pth->str (9 x nsites), allocated on first use of lb200_pth_stress_compute
   char * status;             // device copy of map->status, nullptr if all fluid
   int map_all_fluid;
 
@@ -407,6 +410,7 @@ int lb200_free(lb200_t * c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->f); cudaFree(c->fprime); cudaFree(c->u); cudaFree(c->rho); cudaFree(c->force);
   cudaFree(c->phi); cudaFree(c->phinew); cudaFree(c->grad); cudaFree(c->delsq);
+  cudaFree(c->grad_delsq); cudaFree(c->delsq_delsq); cudaFree(c->str);
   cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->slo); cudaFree(c->shi); cudaFree(c->model_d);
   for (int i = 0; i < LB200_KCLASS_MAX; i++) {
     if (c->ev[i]) { for (cudaEvent_t e : *c->ev[i]) cudaEventDestroy(e); delete c->ev[i]; }
@@ -483,6 +487,9 @@ static int array_info(lb200_t * c, int array, double ** dev, size_t * ncomp) {
   case LB200_FORCE: *dev = c->force; *ncomp = 3; break;
   case LB200_GRAD:  *dev = c->grad;  *ncomp = 3; break;
   case LB200_DELSQ: *dev = c->delsq; *ncomp = 1; break;
+  case LB200_GRAD_DELSQ:  *dev = c->grad_delsq;  *ncomp = 3; break;
+  case LB200_DELSQ_DELSQ: *dev = c->delsq_delsq; *ncomp = 1; break;
+  case LB200_STR:   *dev = c->str;   *ncomp = 9; break;
   default: return fail(LB200_EINVAL, "unknown array id %d", array);
   }
   if (*dev == nullptr) return fail(LB200_ESTATE, "array %d is not allocated in this context (have_phi = 0?)", array);
@@ -740,7 +747,7 @@ int lb200_phi_grad_compute(lb200_t * c) {
   if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
   {
     ProfScope ps(c, LB200_K_GRAD);
-    c->launches += c->k->grad27(c->stream, c->g, c->phi, c->grad, c->delsq);
+    c->launches += c->k->grad27(c->stream, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);
   }
   CTX_LEAVE_SYNC(c);
 }
@@ -751,6 +758,49 @@ static int phi_force_async(lb200_t * c, const Lb200SymmDev & sd) {
   c->launches += c->k->phi_force(c->stream, c->g, sd, accumulate, c->phi, c->grad, c->delsq, c->force);
   if (c->force_state == ZERO_PENDING) c->force_state = INTERIOR_ONLY;
   return 0;
+}
+
+// grad_3d_27pt_fluid_d4, src/gradient_3d_27pt_fluid.c:112-134: the same operator applied to delsq
+int lb200_phi_grad_compute_d4(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  if (c->g.nh < 2) return fail(LB200_ESTATE, "grad_3d_27pt_fluid_d4 needs nhalo >= 2 (reference asserts nhalo - 2 >= 0)");
+  if (c->grad_delsq == nullptr) {
+    if (alloc_d(&c->grad_delsq, (size_t) 3*c->g.nsites) != 0 || alloc_d(&c->delsq_delsq, (size_t) c->g.nsites) != 0) return LB200_ECUDA;
+  }
+  {
+    ProfScope ps(c, LB200_K_GRAD);
+    c->launches += c->k->grad27(c->stream, c->g, c->g.nh - 2, c->delsq, c->grad_delsq, c->delsq_delsq);
+  }
+  CTX_LEAVE_SYNC(c);
+}
+
+// pth_stress_compute, src/phi_force_stress.c:171-217 (fe_symm_str_v per site)
+int lb200_pth_stress_compute(lb200_t * c, const lb200_symm_param_t * sp) {
+  CTX_ENTER(c);
+  if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  if (sp == nullptr) return fail(LB200_EINVAL, "null parameters");
+  if (c->str == nullptr && alloc_d(&c->str, (size_t) 9*c->g.nsites) != 0) return LB200_ECUDA;
+  Lb200SymmDev sd;
+  symm_dev(c, sp, &sd);
+  {
+    ProfScope ps(c, LB200_K_FORCE_CH);
+    c->launches += c->k->stress(c->stream, c->g, sd, c->phi, c->grad, c->delsq, c->str);
+  }
+  CTX_LEAVE_SYNC(c);
+}
+
+// pth_force_fluid_driver, src/phi_force_colloid.c:274-301, 315-465
+int lb200_pth_force_fluid_driver(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->str == nullptr) return fail(LB200_ESTATE, "no stress: call lb200_pth_stress_compute first");
+  {
+    const int accumulate = (c->force_state != ZERO_PENDING);
+    ProfScope ps(c, LB200_K_FORCE_CH);
+    c->launches += c->k->force_from_stress(c->stream, c->g, accumulate, c->str, c->force);
+    if (c->force_state == ZERO_PENDING) c->force_state = INTERIOR_ONLY;
+  }
+  CTX_LEAVE_SYNC(c);
 }
 
 int lb200_phi_force_calculation(lb200_t * c, const lb200_symm_param_t * sp) {
@@ -919,7 +969,7 @@ static int step_lb2(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev 
     if (rc != 0) return rc;
     {
       ProfScope ps(c, LB200_K_GRAD);
-      c->launches += c->k->grad27(c->stream, c->g, c->phi, c->grad, c->delsq);
+      c->launches += c->k->grad27(c->stream, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);
     }
     c->u_state = ZERO_PENDING;
     rc = collide_binary_async(c, cd, sd);
@@ -1200,7 +1250,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
       if (!use_ps) {
 	ProfScope ps(c, LB200_K_GRAD);
-	c->launches += c->k->grad27(S, c->g, c->phi, c->grad, c->delsq);       // field_grad_compute
+	c->launches += c->k->grad27(S, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);       // field_grad_compute
       }
       if (!c->u_halo_valid) {                                            // hydro_u_halo
 	if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);

@@ -748,9 +748,8 @@ int launch_halo(cudaStream_t st, const Lb200Geom & g, const Lb200ModelDev * md, 
 constexpr int GRAD_XC = 16;
 
 __global__ void __launch_bounds__(TPB)
-grad27_kernel(const Lb200Geom g, const double * __restrict__ field, double * __restrict__ grad,
+grad27_kernel(const Lb200Geom g, const int ne, const double * __restrict__ field, double * __restrict__ grad,
 	      double * __restrict__ delsq) {
-  const int ne = g.nh - 1;
   const int ey = g.nl[1] + 2*ne, ez = g.nl[2] + 2*ne;
   const int q = blockIdx.x*blockDim.x + threadIdx.x;
   if (q >= ey*ez) return;
@@ -812,12 +811,13 @@ grad27_kernel(const Lb200Geom g, const double * __restrict__ field, double * __r
 #undef LB200_LOAD_PLANE
 }
 
-int launch_grad27(cudaStream_t st, const Lb200Geom & g, const double * phi, double * grad,
+// ne: the operator is applied on [1-ne, N+ne]^3 (nhalo - 1 for grad/delsq of phi, src/gradient_3d_27pt_fluid.c:91-95;
+// nhalo - 2 for the same operator applied to delsq, grad_3d_27pt_fluid_d4 :112-134)
+int launch_grad27(cudaStream_t st, const Lb200Geom & g, int ne, const double * phi, double * grad,
 		  double * delsq) {
-  const int ne = g.nh - 1;
   const int ex = g.nl[0] + 2*ne, ey = g.nl[1] + 2*ne, ez = g.nl[2] + 2*ne;
   dim3 grd((ey*ez + TPB - 1)/TPB, (ex + GRAD_XC - 1)/GRAD_XC, 1);
-  grad27_kernel<<<grd, TPB, 0, st>>>(g, phi, grad, delsq);
+  grad27_kernel<<<grd, TPB, 0, st>>>(g, ne, phi, grad, delsq);
   return 1;
 }
 
@@ -886,6 +886,85 @@ __device__ __forceinline__ void site_force(const Lb200SymmDev & sp, const SiteFE
   for (int a = 0; a < 3; a++) fo[a] -= 0.5*(p1[a] + p0c[a]);
   symm_pcol<2>(sp, zm, p1);
   for (int a = 0; a < 3; a++) fo[a] += 0.5*(p1[a] + p0c[a]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The two halves of phi_force_calculation as separate operators, for callers that use them
+// directly: pth_stress_compute (src/phi_force_stress.c:171-284: P_ab stored for x in [0, N+1] and
+// EVERY y, z of the allocation) and pth_force_fluid_driver (src/phi_force_colloid.c:274-465:
+// force -= divergence of the stored P).  lb200_phi_force_calculation / lb200_step never store P.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(TPB_MAX)
+stress_symm_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __restrict__ phi,
+		   const double * __restrict__ grad, const double * __restrict__ delsq,
+		   double * __restrict__ str) {
+  const int k0 = blockIdx.x*blockDim.x + threadIdx.x;       // 0 .. nall[2]-1
+  const int j0 = blockIdx.y*blockDim.y + threadIdx.y;
+  const int i0 = blockIdx.z + g.nh - 1;                     // ic = 0 .. N+1
+  if (k0 >= g.nall[2] || j0 >= g.nall[1]) return;
+  const int index = (i0*g.nall[1] + j0)*g.nall[2] + k0;
+  const size_t ns = (size_t) g.nsites;
+  SiteFE s = load_fe(phi, grad, delsq, ns, index);
+  const double p0 = symm_p0(sp, s);
+  const double gr[3] = {s.gx, s.gy, s.gz};
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) {
+#pragma unroll
+    for (int ib = 0; ib < 3; ib++) {
+      str[(size_t) (ia*3 + ib)*ns + index] = p0*((ia == ib) ? 1.0 : 0.0) + sp.kappa*gr[ia]*gr[ib];
+    }
+  }
+}
+
+template <bool ACCUM>
+__global__ void __launch_bounds__(TPB_MAX)
+force_from_stress_kernel(const Lb200Geom g, const double * __restrict__ str, double * __restrict__ force) {
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ic = 1 + blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+  const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+  const size_t ns = (size_t) g.nsites;
+  const int off[6] = {+g.xs, -g.xs, +g.ys, -g.ys, +1, -1};
+  double fo[3];
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    const int ib = d/2;
+    const int index1 = index + off[d];
+#pragma unroll
+    for (int ia = 0; ia < 3; ia++) {
+      const double p1 = str[(size_t) (ia*3 + ib)*ns + index1];
+      const double p0 = str[(size_t) (ia*3 + ib)*ns + index];
+      if (d == 0)          fo[ia]  = -0.5*(p1 + p0);
+      else if (d % 2 == 1) fo[ia] += 0.5*(p1 + p0);
+      else                 fo[ia] -= 0.5*(p1 + p0);
+    }
+  }
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) {
+    if (ACCUM) force[ia*ns + index] += fo[ia];
+    else       force[ia*ns + index] = fo[ia];
+  }
+}
+
+int launch_stress(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const double * phi,
+		  const double * grad, const double * delsq, double * str) {
+  dim3 blk;
+  block_shape(g.nall[2], blk);
+  dim3 grd((g.nall[2] + blk.x - 1)/blk.x, (g.nall[1] + blk.y - 1)/blk.y, g.nl[0] + 2);
+  stress_symm_kernel<<<grd, blk, 0, st>>>(g, sp, phi, grad, delsq, str);
+  return 1;
+}
+
+int launch_force_from_stress(cudaStream_t st, const Lb200Geom & g, int accumulate, const double * str,
+			     double * force) {
+  dim3 blk;
+  block_shape(g.nl[2], blk);
+  dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
+  if (accumulate) force_from_stress_kernel<true><<<grd, blk, 0, st>>>(g, str, force);
+  else            force_from_stress_kernel<false><<<grd, blk, 0, st>>>(g, str, force);
+  return 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1756,4 +1835,6 @@ const Lb200Kernels LB200_TABLE = {
   launch_phi_from_g,
   launch_phi_to_g,
   launch_collide_binary,
+  launch_stress,
+  launch_force_from_stress,
 };

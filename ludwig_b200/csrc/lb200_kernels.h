@@ -54,7 +54,7 @@ struct Lb200Kernels {
   // halo shell of depth d for ncomp components; reduced != 0 only for distributions (needs cv)
   int (*halo)(cudaStream_t, const Lb200Geom &, const Lb200ModelDev *, int ncomp, int depth,
 	      int reduced, double * data, const double * xlo, const double * xhi);
-  int (*grad27)(cudaStream_t, const Lb200Geom &, const double * phi, double * grad, double * delsq);
+  int (*grad27)(cudaStream_t, const Lb200Geom &, int ne, const double * phi, double * grad, double * delsq);
   // force = [force +] -div P(phi, grad, delsq)   (accumulate = 0: plain store)
   int (*phi_force)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, int accumulate,
 		   const double * phi, const double * grad, const double * delsq, double * force);
@@ -80,6 +80,10 @@ struct Lb200Kernels {
 			const Lb200ModelDev *, int unrolled19, int pull, const double * fsrc, double * fdst,
 			const double * force, const double * phi, const double * grad, const double * delsq,
 			double * u);
+  // pth_stress_compute / pth_force_fluid_driver as separate operators (P stored: 9 x nsites)
+  int (*stress)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, const double * phi, const double * grad,
+		const double * delsq, double * str);
+  int (*force_from_stress)(cudaStream_t, const Lb200Geom &, int accumulate, const double * str, double * force);
 };
 
 extern const Lb200Kernels lb200_kernels_fast;

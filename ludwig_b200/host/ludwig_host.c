@@ -433,6 +433,12 @@ int field_halo(field_t * obj) {
   return 0;
 }
 
+/* src/field.c:1541-1560: the swap with an explicit scheme; one device scheme here */
+int field_halo_swap(field_t * obj, field_halo_enum_t flag) {
+  (void) flag;
+  return field_halo(obj);
+}
+
 int field_nf(field_t * obj, int * nop) { *nop = obj->nf; return 0; }
 int field_scalar(field_t * obj, int index, double * phi) { *phi = obj->data[addr_rank1(obj->nsites, 1, index, 0)]; return 0; }
 int field_scalar_set(field_t * obj, int index, double phi) { obj->data[addr_rank1(obj->nsites, 1, index, 0)] = phi; return 0; }
@@ -454,6 +460,12 @@ int field_grad_create(pe_t * pe, field_t * f, int level, field_grad_t ** pobj) {
   obj->grad = (double *) calloc((size_t) 3*obj->nf*obj->nsite, sizeof(double));
   obj->delsq = (double *) calloc((size_t) obj->nf*obj->nsite, sizeof(double));
   if (obj->grad == NULL || obj->delsq == NULL) pe_fatal(pe, "calloc(field_grad) failed\n");
+  if (level >= 4) {
+    /* src/field_grad.c:112-135 */
+    obj->grad_delsq = (double *) calloc((size_t) 3*obj->nf*obj->nsite, sizeof(double));
+    obj->delsq_delsq = (double *) calloc((size_t) obj->nf*obj->nsite, sizeof(double));
+    if (obj->grad_delsq == NULL || obj->delsq_delsq == NULL) pe_fatal(pe, "calloc(field_grad d4) failed\n");
+  }
   obj->target = obj;
   if (f->cs->phi == f) f->cs->phi_grad = obj;
   *pobj = obj;
@@ -463,7 +475,7 @@ int field_grad_create(pe_t * pe, field_t * f, int level, field_grad_t ** pobj) {
 void field_grad_free(field_grad_t * obj) {
   if (obj == NULL) return;
   if (obj->field && obj->field->cs && obj->field->cs->phi_grad == obj) obj->field->cs->phi_grad = NULL;
-  free(obj->grad); free(obj->delsq); free(obj);
+  free(obj->grad); free(obj->delsq); free(obj->grad_delsq); free(obj->delsq_delsq); free(obj);
 }
 
 int field_grad_set(field_grad_t * obj, grad_ft d2, grad_ft d4) { obj->d2 = d2; obj->d4 = d4; return 0; }
@@ -473,7 +485,10 @@ int field_grad_compute(field_grad_t * obj) {
   assert(obj);
   assert(obj->d2);
   obj->d2(obj);
-  if (obj->level >= 4) pe_fatal(obj->pe, "field_grad_compute: d4 is outside this build\n");
+  if (obj->level >= 4) {
+    assert(obj->d4);
+    obj->d4(obj);
+  }
   return 0;
 }
 
@@ -482,10 +497,21 @@ int grad_3d_27pt_fluid_d2(field_grad_t * fg) {
   return 0;
 }
 
+/* src/gradient_3d_27pt_fluid.c:112-134 */
+int grad_3d_27pt_fluid_d4(field_grad_t * fg) {
+  b200_check(fg->pe, lb200_phi_grad_compute_d4(cs_b200_context(fg->field->cs)), "grad_3d_27pt_fluid_d4");
+  fg->d4_on_device = 1;
+  return 0;
+}
+
 int field_grad_memcpy(field_grad_t * obj, tdpMemcpyKind flag) {
   lb200_t * ctx = cs_b200_context(obj->field->cs);
   b200_check(obj->pe, lb200_memcpy(ctx, LB200_GRAD, obj->grad, b200_kind(flag)), "field_grad_memcpy");
   b200_check(obj->pe, lb200_memcpy(ctx, LB200_DELSQ, obj->delsq, b200_kind(flag)), "field_grad_memcpy");
+  if (obj->level >= 4 && obj->d4_on_device && flag == tdpMemcpyDeviceToHost) {
+    b200_check(obj->pe, lb200_memcpy(ctx, LB200_GRAD_DELSQ, obj->grad_delsq, b200_kind(flag)), "field_grad_memcpy");
+    b200_check(obj->pe, lb200_memcpy(ctx, LB200_DELSQ_DELSQ, obj->delsq_delsq, b200_kind(flag)), "field_grad_memcpy");
+  }
   return 0;
 }
 
@@ -608,6 +634,12 @@ int fe_symm_create(pe_t * pe, cs_t * cs, field_t * f, field_grad_t * grd, fe_sym
   *p = fe;
   return 0;
 }
+/* src/symmetric.c:160-170: the device-side object; parameters travel with every call here, so the host object is it */
+int fe_symm_target(fe_symm_t * fe, fe_t ** target) { *target = (fe_t *) fe->target; return 0; }
+
+/* src/lb_data.c:585-600: constants are passed to the kernels with every launch; nothing to commit */
+int lb_collide_param_commit(lb_t * lb) { assert(lb); return 0; }
+
 int fe_symm_free(fe_symm_t * fe) { if (fe) { free(fe->param); free(fe); } return 0; }
 int fe_symm_param_set(fe_symm_t * fe, fe_symm_param_t values) { *fe->param = values; return 0; }
 int fe_symm_param(fe_symm_t * fe, fe_symm_param_t * values) { *values = *fe->param; return 0; }
@@ -652,6 +684,22 @@ int pth_create(pe_t * pe, cs_t * cs, int method, pth_t ** ppth) {
   return 0;
 }
 int pth_free(pth_t * pth) { free(pth); return 0; }
+
+/* src/phi_force_stress.c:171-217 */
+int pth_stress_compute(pth_t * pth, fe_t * fe) {
+  lb200_symm_param_t sp;
+  assert(pth); assert(fe);
+  symm_param_from(fe, &sp);
+  b200_check(pth->pe, lb200_pth_stress_compute(cs_b200_context(pth->cs), &sp), "pth_stress_compute");
+  return 0;
+}
+
+/* src/phi_force_colloid.c:274-301 */
+int pth_force_fluid_driver(pth_t * pth, hydro_t * hydro) {
+  assert(pth); assert(hydro);
+  b200_check(pth->pe, lb200_pth_force_fluid_driver(cs_b200_context(pth->cs)), "pth_force_fluid_driver");
+  return 0;
+}
 
 /* src/phi_force.c:74-137 */
 int phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t * wall, pth_t * pth, fe_t * fe,

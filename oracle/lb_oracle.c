@@ -451,10 +451,15 @@ void orc_collide(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
 /* ---- 27-point gradient: src/gradient_3d_27pt_fluid.c:76-99 (extent), :219-363 (stencil) --- */
 
 void orc_grad_27pt(const orc_geom_t * g, const double * phi, double * grad, double * delsq) {
+  orc_grad_27pt_ne(g, g->nhalo - 1, phi, grad, delsq);
+}
+
+/* the operator on [1-nextra, N+nextra]^3: nextra = nhalo - 1 for d2 (:91-95); grad_3d_27pt_fluid_d4 (:112-134)
+ * applies it to delsq with nextra = nhalo - 2 to produce grad_delsq, delsq_delsq */
+void orc_grad_27pt_ne(const orc_geom_t * g, int nextra, const double * phi, double * grad, double * delsq) {
 
   int nall[3];
   const size_t ns = (size_t) orc_nsites(g);
-  const int nextra = g->nhalo - 1;
   const double r9 = (1.0/9.0);
   orc_nall(g, nall);
   const int ys = nall[Z];

@@ -80,6 +80,7 @@ void orc_collide(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
 		 double * f, const double * force, double * rho, double * u);
 
 void orc_grad_27pt(const orc_geom_t * g, const double * phi, double * grad, double * delsq);
+void orc_grad_27pt_ne(const orc_geom_t * g, int nextra, const double * field, double * grad, double * delsq);
 void orc_stress_symm(const orc_geom_t * g, const orc_symm_param_t * sp, const double * phi,
 		     const double * grad, const double * delsq, double * str);
 void orc_force_divergence(const orc_geom_t * g, const double * str, double * force);

@@ -66,6 +66,7 @@ typedef struct ref_cfg_s {
   double a, b, kappa;
   double mobility;
   double gradmu[3];
+  int grad_level;      /* 0/2: field_grad level 2; 4: also grad_delsq, delsq_delsq (grad_3d_27pt_fluid_d4) */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -87,7 +88,8 @@ typedef struct ref_sim_s {
 } ref_sim_t;
 
 enum {REF_F = 0, REF_PHI = 1, REF_U = 2, REF_RHO = 3, REF_FORCE = 4,
-      REF_GRAD = 5, REF_DELSQ = 6, REF_STR = 7, REF_FLUX = 8, REF_MAP = 9};
+      REF_GRAD = 5, REF_DELSQ = 6, REF_STR = 7, REF_FLUX = 8, REF_MAP = 9,
+      REF_GRAD_DELSQ = 10, REF_DELSQ_DELSQ = 11};
 
 static int mpi_up = 0;
 
@@ -145,7 +147,7 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     phi_ch_info_t ch = {0};
     fe_symm_param_t p = {0};
     field_create(s->pe, s->cs, s->le, "phi", &opts, &s->phi);
-    field_grad_create(s->pe, s->phi, 2, &s->phi_grad);
+    field_grad_create(s->pe, s->phi, cfg->grad_level == 4 ? 4 : 2, &s->phi_grad);
     field_grad_set(s->phi_grad, grad_3d_27pt_fluid_d2, grad_3d_27pt_fluid_d4);
     fe_symm_create(s->pe, s->cs, s->phi, s->phi_grad, &s->fe);
     p.a = cfg->a; p.b = cfg->b; p.kappa = cfg->kappa;
@@ -246,6 +248,13 @@ static int ref_copy(ref_sim_t * s, int what, double * buf, int put) {
   case REF_DELSQ:
     for (int i = 0; i < ns; i++) XFER(s->phi_grad->delsq[addr_rank1(ns, 1, i, 0)], i);
     break;
+  case REF_GRAD_DELSQ:
+    for (int a = 0; a < 3; a++)
+      for (int i = 0; i < ns; i++) XFER(s->phi_grad->grad_delsq[addr_rank2(ns, 1, 3, i, 0, a)], (size_t) a*ns + i);
+    break;
+  case REF_DELSQ_DELSQ:
+    for (int i = 0; i < ns; i++) XFER(s->phi_grad->delsq_delsq[addr_rank1(ns, 1, i, 0)], i);
+    break;
   case REF_STR:
     for (int a = 0; a < 3; a++)
       for (int b = 0; b < 3; b++)
@@ -281,6 +290,9 @@ int ref_hydro_u_zero(ref_sim_t * s) { double z[3] = {0.0, 0.0, 0.0}; return hydr
 int ref_hydro_u_halo(ref_sim_t * s) { return hydro_u_halo(s->hydro); }
 int ref_phi_halo(ref_sim_t * s) { return field_halo(s->phi); }
 int ref_grad_compute(ref_sim_t * s) { return field_grad_compute(s->phi_grad); }
+int ref_grad_d4(ref_sim_t * s) { return grad_3d_27pt_fluid_d4(s->phi_grad); }
+int ref_pth_stress_compute(ref_sim_t * s) { return pth_stress_compute(s->pth, (fe_t *) s->fe); }
+int ref_pth_force_fluid_driver(ref_sim_t * s) { return pth_force_fluid_driver(s->pth, s->hydro); }
 int ref_phi_force(ref_sim_t * s) {
   return phi_force_calculation(s->pe, s->cs, s->le, s->wall, s->pth, (fe_t *) s->fe, s->map,
 			       s->phi, s->hydro);

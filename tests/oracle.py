@@ -137,6 +137,10 @@ class Oracle:
     def grad_27pt(self, phi, grad, delsq):
         self.lib.orc_grad_27pt(C.byref(self.g), _p(phi), _p(grad), _p(delsq))
 
+    def grad_27pt_d4(self, delsq, grad_delsq, delsq_delsq):
+        """grad_3d_27pt_fluid_d4: the same operator on delsq, region nhalo - 2."""
+        self.lib.orc_grad_27pt_ne(C.byref(self.g), self.nhalo - 2, _p(delsq), _p(grad_delsq), _p(delsq_delsq))
+
     def stress_symm(self, sp, phi, grad, delsq, str_):
         self.lib.orc_stress_symm(C.byref(self.g), C.byref(sp), _p(phi), _p(grad), _p(delsq), _p(str_))
 

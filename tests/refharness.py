@@ -8,9 +8,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "..", "oracle", "_ref", "libludwig_ref.so")
 REF_FAST_SO = os.path.join(HERE, "..", "oracle", "_ref", "libludwig_ref_fast.so")
 
-REF_F, REF_PHI, REF_U, REF_RHO, REF_FORCE, REF_GRAD, REF_DELSQ, REF_STR, REF_FLUX, REF_MAP = range(10)
+REF_F, REF_PHI, REF_U, REF_RHO, REF_FORCE, REF_GRAD, REF_DELSQ, REF_STR, REF_FLUX, REF_MAP, \
+    REF_GRAD_DELSQ, REF_DELSQ_DELSQ = range(12)
 NCOMP = {REF_PHI: 1, REF_U: 3, REF_RHO: 1, REF_FORCE: 3, REF_GRAD: 3, REF_DELSQ: 1,
-         REF_STR: 9, REF_FLUX: 4, REF_MAP: 1}
+         REF_STR: 9, REF_FLUX: 4, REF_MAP: 1, REF_GRAD_DELSQ: 3, REF_DELSQ_DELSQ: 1}
 
 
 class RefCfg(C.Structure):
@@ -20,7 +21,8 @@ class RefCfg(C.Structure):
                 ("conserve", C.c_int),
                 ("rho0", C.c_double), ("eta_shear", C.c_double), ("eta_bulk", C.c_double),
                 ("fbody", C.c_double * 3), ("a", C.c_double), ("b", C.c_double),
-                ("kappa", C.c_double), ("mobility", C.c_double), ("gradmu", C.c_double * 3)]
+                ("kappa", C.c_double), ("mobility", C.c_double), ("gradmu", C.c_double * 3),
+                ("grad_level", C.c_int)]
 
 
 def _so(fast=False, nvel=19):
@@ -46,7 +48,8 @@ def _lib(fast=False, nvel=19):
         lib.ref_time_steps.argtypes = [C.c_void_p, C.c_int]
         for name in ("ref_free", "ref_nsites", "ref_hydro_f_zero", "ref_hydro_u_zero", "ref_hydro_u_halo",
                      "ref_phi_halo", "ref_grad_compute", "ref_phi_force", "ref_cahn_hilliard",
-                     "ref_collide", "ref_lb_halo", "ref_propagation", "ref_phi_lb_to_field", "ref_phi_lb_from_field"):
+                     "ref_collide", "ref_lb_halo", "ref_propagation", "ref_phi_lb_to_field", "ref_phi_lb_from_field", "ref_grad_d4", "ref_pth_stress_compute",
+                     "ref_pth_force_fluid_driver"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.ref_step.argtypes = [C.c_void_p, C.c_int]
         lib.ref_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -66,7 +69,7 @@ class RefSim:
     def __init__(self, ntotal, nhalo=1, periodic=(1, 1, 1), ndist=1, nrelax=0, ghost_off=0,
                  halo_reduced=0, have_phi=0, adv_order=1, conserve=0, rho0=1.0, eta_shear=1.0 / 6.0,
                  eta_bulk=None, fbody=(0, 0, 0), a=0.0, b=0.0, kappa=0.0, mobility=0.0,
-                 gradmu=(0, 0, 0), fast=False, nvel=19):
+                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2):
         self.lib = _lib(fast, nvel)
         cfg = RefCfg()
         cfg.ntotal[:] = ntotal
@@ -79,6 +82,7 @@ class RefSim:
         cfg.fbody[:] = fbody
         cfg.a, cfg.b, cfg.kappa, cfg.mobility = a, b, kappa, mobility
         cfg.gradmu[:] = gradmu
+        cfg.grad_level = grad_level
         self.cfg = cfg
         self.h = self.lib.ref_create(C.byref(cfg))
         self.nsites = self.lib.ref_nsites(self.h)

@@ -12,7 +12,7 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 def declared_functions(header):
     src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(?:int|long long|void \*|const char \*|double)\s*\**\s*((?:lb200|lb|field|hydro|phi|pth|fe|cs|pe|physics|map)_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:int|long long|void \*|const char \*|double)\s*\**\s*((?:lb200|lb|field|hydro|phi|pth|fe|cs|pe|physics|map|grad|advection|lees_edw)_\w+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():

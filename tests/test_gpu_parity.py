@@ -124,6 +124,51 @@ def test_gradient_bit_exact(nlocal):
         assert np.array_equal(sim.get(lb.DELSQ), delsq)
 
 
+def test_gradient_d4_bit_exact():
+    """grad_3d_27pt_fluid_d4: the 27-point operator applied to delsq on [1-(nhalo-2), N+(nhalo-2)]^3."""
+    orc = Oracle((6, 7, 35), nhalo=3)
+    rng = np.random.default_rng(12)
+    delsq = rng.random((1, orc.nsites)) - 0.5
+    gd, dd = np.zeros((3, orc.nsites)), np.zeros((1, orc.nsites))
+    orc.grad_27pt_d4(delsq, gd, dd)
+    with lb.Lb200(orc.nlocal, nhalo=3, have_phi=True, math=lb.MATH_STRICT) as sim:
+        sim.put(lb.DELSQ, delsq)
+        sim.phi_grad_compute_d4()
+        assert np.array_equal(orc.region(sim.get(lb.GRAD_DELSQ), 1), orc.region(gd, 1))
+        assert np.array_equal(orc.region(sim.get(lb.DELSQ_DELSQ), 1), orc.region(dd, 1))
+    with lb.Lb200((4, 4, 4), nhalo=1, nvel=19, ndist=2, have_phi=True) as sim:
+        with pytest.raises(lb.Lb200Error):
+            sim.phi_grad_compute_d4()
+
+
+@pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST])
+def test_pth_stress_then_force_driver(math):
+    """pth_stress_compute (P stored on x in [0, N+1], every y, z) + pth_force_fluid_driver as separate operators."""
+    orc = Oracle((6, 7, 34), nhalo=2)
+    rng = np.random.default_rng(13)
+    phi = 0.1 * (rng.random((1, orc.nsites)) - 0.5)
+    grad = 0.05 * (rng.random((3, orc.nsites)) - 0.5)
+    delsq = 0.1 * (rng.random((1, orc.nsites)) - 0.5)
+    force0 = 1e-4 * (rng.random((3, orc.nsites)) - 0.5)
+    spo = orc.symm_param(**BINARY)
+    strs = np.zeros((9, orc.nsites)); force = force0.copy()
+    orc.stress_symm(spo, phi, grad, delsq, strs)
+    orc.force_divergence(strs, force)
+    with lb.Lb200(orc.nlocal, nhalo=2, have_phi=True, math=math) as sim:
+        with pytest.raises(lb.Lb200Error):
+            sim.pth_force_fluid_driver()
+        sim.put(lb.PHI, phi); sim.put(lb.GRAD, grad); sim.put(lb.DELSQ, delsq); sim.put(lb.FORCE, force0)
+        sim.pth_stress_compute(lb.SymmParam.make(**BINARY))
+        gs = sim.get(lb.STR)
+        sim.pth_force_fluid_driver()
+        gf = sim.get(lb.FORCE)
+    v = lambda a: a.reshape((-1,) + orc.nall)[:, 1:-1]
+    if math == lb.MATH_STRICT:
+        assert np.array_equal(v(gs), v(strs)) and np.array_equal(orc.interior(gf), orc.interior(force))
+    else:
+        assert close_fast(v(gs), v(strs)) and close_fast(orc.interior(gf), orc.interior(force))
+
+
 @pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST])
 def test_phi_force(math):
     orc = Oracle((6, 7, 34), nhalo=2)

@@ -311,3 +311,42 @@ def test_symmetric_lb_steps(nvel, reduced):
     got = dict(f=f, phi=phi, u=u, grad=grad, delsq=delsq)
     for k in ref:
         assert np.array_equal(orc.interior(got[k]), orc.interior(ref[k])), k
+
+
+def test_gradient_d4():
+    """grad_3d_27pt_fluid_d4 (src/gradient_3d_27pt_fluid.c:112-134): the operator applied to delsq, nhalo = 3."""
+    nlocal, nhalo = (5, 6, 7), 3
+    orc = Oracle(nlocal, nhalo=nhalo)
+    rng = np.random.default_rng(60)
+    with rh.RefSim(nlocal, nhalo=nhalo, have_phi=1, grad_level=4, **BINARY) as s:
+        fill_random(s, orc, rh.REF_PHI, rng, 1.0, -0.5)
+        delsq = fill_random(s, orc, rh.REF_DELSQ, rng, 1.0, -0.5)
+        s.op("grad_d4")
+        ref_gd, ref_dd = s.get(rh.REF_GRAD_DELSQ), s.get(rh.REF_DELSQ_DELSQ)
+    gd, dd = np.zeros((3, orc.nsites)), np.zeros((1, orc.nsites))
+    orc.grad_27pt_d4(delsq, gd, dd)
+    assert np.array_equal(orc.region(gd, 1), orc.region(ref_gd, 1))
+    assert np.array_equal(orc.region(dd, 1), orc.region(ref_dd, 1))
+
+
+def test_pth_stress_then_force_driver():
+    """pth_stress_compute + pth_force_fluid_driver called separately == the oracle's two operators."""
+    nlocal, nhalo = (6, 5, 7), 2
+    orc = Oracle(nlocal, nhalo=nhalo)
+    rng = np.random.default_rng(61)
+    with rh.RefSim(nlocal, nhalo=nhalo, have_phi=1, **BINARY) as s:
+        phi = fill_random(s, orc, rh.REF_PHI, rng, 0.1, -0.5)
+        grad = fill_random(s, orc, rh.REF_GRAD, rng, 0.05, -0.5)
+        delsq = fill_random(s, orc, rh.REF_DELSQ, rng, 0.1, -0.5)
+        force = fill_random(s, orc, rh.REF_FORCE, rng, 1e-4, -0.5)
+        s.op("pth_stress_compute")
+        ref_str = s.get(rh.REF_STR)
+        s.op("pth_force_fluid_driver")
+        ref_force = s.get(rh.REF_FORCE)
+    strs = np.zeros((9, orc.nsites))
+    orc.stress_symm(orc.symm_param(**BINARY), phi, grad, delsq, strs)
+    # stored for x in [0, N+1], every y, z of the allocation
+    v = lambda a: a.reshape((-1,) + orc.nall)[:, nhalo - 1:-(nhalo - 1)]
+    assert np.array_equal(v(strs), v(ref_str))
+    orc.force_divergence(strs, force)
+    assert np.array_equal(orc.interior(force), orc.interior(ref_force))
