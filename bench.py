@@ -360,6 +360,8 @@ def run_ours(args, rank, local_rank, world):
                                    "x-planes over NVLink when sharded",
                        "lattice_per_gpu": list(nlocal), "decomposition": f"{world}_1_1 x-slabs",
                        "math": "strict" if args.strict else "fast(fma)",
+                       "x_plane_exchange": {0: "none (one GPU)", 1: "NCCL send/recv on a second stream",
+                                            2: "NVLink peer stores from inside the kernels + flags"}[sim.exchange_mode()],
                        "l2": "inputs (2.8 GB of lattice state per sweep) exceed the 126 MB L2; no flush needed",
                        "e2e_protocol": "pinned-host f+phi -> device, K steps, phi+u+rho -> pinned host "
                                        "(the reference's own lb_memcpy/field_memcpy usage, src/ludwig.c:501-506, 985)"},

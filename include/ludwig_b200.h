@@ -172,9 +172,15 @@ enum lb200_knob {
   LB200_KNOB_WRAP = 1,        /* 1: halo-free time steps on periodic lattices (periodic images are read from
                                *    the interior; only the planes the kernels read cross NVLink)
                                * 0: the reference's step structure with three halo swaps (phi, u, f) */
-  LB200_KNOB_PHI_SECTOR = 2   /* 1: gradient + force + Cahn-Hilliard in one sweep (all-fluid lattices) */
+  LB200_KNOB_PHI_SECTOR = 2,  /* 1: gradient + force + Cahn-Hilliard in one sweep (all-fluid lattices) */
+  LB200_KNOB_PEER = 3         /* 1: x-slab neighbours exchange planes by NVLink peer stores from inside the kernels
+                               *    (cudaIpc-mapped arrays + one flag per kernel); 0: NCCL send/recv.  Must be set
+                               *    identically on every rank.  Default LB200_PEER, else 1 */
 };
 int lb200_set_knob(lb200_t * ctx, int knob, int value);
+/* how lb200_step exchanges x-planes on this context: 0 = single GPU, 1 = NCCL send/recv, 2 = peer stores
+ * (meaningful after the first lb200_step, which sets the mapping up collectively) */
+int lb200_exchange_mode(const lb200_t * ctx);
 
 /* number of kernels this library has launched on this context since creation */
 long long lb200_launch_count(const lb200_t * ctx);

@@ -8,7 +8,7 @@ RELAX_M10, RELAX_BGK, RELAX_TRT = 0, 1, 2
 HALO_FULL, HALO_REDUCED = 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 H2D, D2H = 1, 2
-KNOB_WRAP, KNOB_PHI_SECTOR = 1, 2
+KNOB_WRAP, KNOB_PHI_SECTOR, KNOB_PEER = 1, 2, 3
 
 _NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1, GRAD_DELSQ: 3, DELSQ_DELSQ: 1, STR: 9}
 
@@ -110,6 +110,7 @@ def load_library():
     lib.lb200_phi_lb_from_field.argtypes = [C.c_void_p]
     lib.lb200_launch_count.argtypes = [C.c_void_p]
     lib.lb200_set_knob.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.lb200_exchange_mode.argtypes = [C.c_void_p]
     lib.lb200_launch_count.restype = C.c_longlong
     lib.lb200_stream.argtypes = [C.c_void_p]
     lib.lb200_stream.restype = C.c_void_p
@@ -294,6 +295,10 @@ class Lb200:
             self._check(self.lib.lb200_profile_get(self.h, i, C.byref(t), C.byref(n)))
             out[name] = (t.value, n.value)
         return out
+
+    def exchange_mode(self):
+        """0 single GPU, 1 NCCL send/recv, 2 NVLink peer stores from inside the kernels."""
+        return int(self.lib.lb200_exchange_mode(self.h))
 
     def launch_count(self):
         return int(self.lib.lb200_launch_count(self.h))

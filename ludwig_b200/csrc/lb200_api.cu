@@ -5,6 +5,7 @@
 // the reference's host code does, and launches the kernels in lb200_kernels.cu.
 
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <cstdarg>
@@ -36,6 +37,15 @@ static int fail(int code, const char * fmt, ...) {
   return fail(LB200_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); } while (0)
 
 enum ZeroState {ARRAY_CLEAN = 0, ZERO_PENDING = 1, INTERIOR_ONLY = 2};
+enum {SRC_NONE = 0, SRC_EVENT = 1, SRC_FLAG = 2};
+enum {FLAG_PS_LO = 0, FLAG_PS_HI = 1, FLAG_COL_LO = 2, FLAG_COL_HI = 3, FLAG_COUNT = 16};
+
+struct PeerLink {            // one neighbour's arrays, in ITS allocation order
+  double * f[2];
+  double * phi[2];
+  double * u[2];
+  unsigned int * flags;
+};
 
 struct lb200_s {
   lb200_options_t opt;
@@ -89,6 +99,20 @@ struct lb200_s {
   void * nccl;               // ncclComm_t
   int knob_wrap;             // lb200_set_knob
   int knob_phi_sector;
+  int knob_peer;
+
+  // peer-store exchange of lb200_step on x-slabs: the neighbours' arrays mapped into this process (cudaIpc)
+  int peer_state;            // 0: not set up yet, 1: active, -1: unavailable (NCCL exchange instead)
+  double * f_alloc[2], * phi_alloc[2], * u_alloc[2];   // my buffers in allocation order (the neighbours swap in lockstep)
+  double * u2;               // second velocity buffer: the collision writes the one the neighbours' phi sector is not reading
+  unsigned int * flags;      // [0] phi sector done on the low / [1] high neighbour, [2] collision low / [3] high
+  int * spin_err;
+  PeerLink lo, hi;
+  void * mapped[14];         // everything opened with cudaIpcOpenMemHandle
+  int nmapped;
+  unsigned int n_ps, n_col;  // producer kernels run with peer stores (identical on every rank)
+  int phi_src, u_src, f_src; // how the boundary data the next consumer needs arrives: SRC_*
+  void * wait_value32;       // cuStreamWaitValue32, if the driver has it
 
   // optional per-kernel-class timing with CUDA events on the launching stream
   int profile;
@@ -365,6 +389,10 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   c->u_state = ARRAY_CLEAN;
   c->knob_wrap = getenv("LB200_WRAP") ? atoi(getenv("LB200_WRAP")) : 1;
   c->knob_phi_sector = getenv("LB200_PHI_SECTOR") ? atoi(getenv("LB200_PHI_SECTOR")) : 1;
+  c->knob_peer = getenv("LB200_PEER") ? atoi(getenv("LB200_PEER")) : 1;
+  c->f_alloc[0] = c->f; c->f_alloc[1] = c->fprime;
+  c->phi_alloc[0] = c->phi; c->phi_alloc[1] = c->phinew;
+  c->u_alloc[0] = c->u; c->u_alloc[1] = nullptr;
   for (int i = 0; i < LB200_KCLASS_MAX; i++) c->ev[i] = new std::vector<cudaEvent_t>();
   *pctx = c;
   return 0;
@@ -374,6 +402,7 @@ int lb200_set_knob(lb200_t * c, int knob, int value) {
   if (c == nullptr) return fail(LB200_EINVAL, "null context");
   if (knob == LB200_KNOB_WRAP) c->knob_wrap = (value != 0);
   else if (knob == LB200_KNOB_PHI_SECTOR) c->knob_phi_sector = (value != 0);
+  else if (knob == LB200_KNOB_PEER) { c->knob_peer = (value != 0); c->wrap_x_valid = 0; }
   else return fail(LB200_EINVAL, "unknown knob %d", knob);
   return 0;
 }
@@ -408,9 +437,11 @@ int lb200_free(lb200_t * c) {
   if (c == nullptr) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaFree(c->f); cudaFree(c->fprime); cudaFree(c->u); cudaFree(c->rho); cudaFree(c->force);
+  cudaFree(c->f); cudaFree(c->fprime); cudaFree(c->u_alloc[0] ? c->u_alloc[0] : c->u); cudaFree(c->u_alloc[1]); cudaFree(c->rho); cudaFree(c->force);
   cudaFree(c->phi); cudaFree(c->phinew); cudaFree(c->grad); cudaFree(c->delsq);
   cudaFree(c->grad_delsq); cudaFree(c->delsq_delsq); cudaFree(c->str);
+  for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
+  cudaFree(c->flags); cudaFree(c->spin_err);
   cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->slo); cudaFree(c->shi); cudaFree(c->model_d);
   for (int i = 0; i < LB200_KCLASS_MAX; i++) {
     if (c->ev[i]) { for (cudaEvent_t e : *c->ev[i]) cudaEventDestroy(e); delete c->ev[i]; }
@@ -985,6 +1016,128 @@ static int step_lb2(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev 
   return 0;
 }
 
+// ---- peer-store exchange: set-up (collective over the NCCL communicator, first lb200_step only) --------------
+// Every rank exports its two distribution buffers, two phi buffers, two velocity buffers and its flag words
+// with cudaIpcGetMemHandle; the handles are all-gathered and each rank maps its two neighbours' arrays.
+// From then on the kernels of lb200_step store their boundary planes directly in the neighbour's halo planes
+// (Lb200Geom::peer_*) and the only other traffic is one 4-byte flag per kernel and neighbour.
+
+static int peer_setup(lb200_t * c) {
+  if (c->peer_state != 0) return 0;
+  c->peer_state = -1;
+#ifdef LB200_NO_NCCL
+  return 0;
+#else
+  if (!c->g.remote_x || c->nccl == nullptr || c->opt.cart_size < 2) return 0;
+  ncclComm_t comm = (ncclComm_t) c->nccl;
+  const int P = c->opt.cart_size, rank = c->opt.cart_rank;
+  const int left = (rank - 1 + P) % P, right = (rank + 1) % P;
+  const size_t ns = (size_t) c->g.nsites;
+  enum {NH = 7};
+  int ok = 1;
+
+  if (alloc_d(&c->u2, 3*ns) != 0) return LB200_ECUDA;
+  c->u_alloc[0] = c->u; c->u_alloc[1] = c->u2;
+  // (a whole 2 MiB granule: an exported allocation exposes the granule it lives in)
+  CUDA_TRY(cudaMalloc((void **) &c->flags, (size_t) 2 << 20));
+  CUDA_TRY(cudaMemset(c->flags, 0, FLAG_COUNT*sizeof(unsigned int)));
+  CUDA_TRY(cudaMalloc((void **) &c->spin_err, sizeof(int)));
+  CUDA_TRY(cudaMemset(c->spin_err, 0, sizeof(int)));
+
+  void * mine[NH] = {c->f_alloc[0], c->f_alloc[1], c->phi_alloc[0], c->phi_alloc[1], c->u_alloc[0], c->u_alloc[1], c->flags};
+  std::vector<cudaIpcMemHandle_t> hs(NH), all((size_t) NH*P);
+  for (int i = 0; i < NH; i++) {
+    if (mine[i] == nullptr) { memset(&hs[i], 0, sizeof(hs[i])); continue; }      // single fluid: no phi
+    if (cudaIpcGetMemHandle(&hs[i], mine[i]) != cudaSuccess) { cudaGetLastError(); ok = 0; memset(&hs[i], 0, sizeof(hs[i])); }
+  }
+  char * dsend = nullptr, * drecv = nullptr;
+  const size_t nb = NH*sizeof(cudaIpcMemHandle_t);
+  CUDA_TRY(cudaMalloc((void **) &dsend, nb + sizeof(int)));
+  CUDA_TRY(cudaMalloc((void **) &drecv, (nb + sizeof(int))*P));
+  CUDA_TRY(cudaMemcpyAsync(dsend, hs.data(), nb, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(dsend + nb, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (ncclAllGather(dsend, drecv, nb + sizeof(int), ncclChar, comm, c->stream) != ncclSuccess) {
+    return fail(LB200_ECOMM, "ncclAllGather of the IPC handles failed");
+  }
+  std::vector<char> raw((nb + sizeof(int))*P);
+  CUDA_TRY(cudaMemcpyAsync(raw.data(), drecv, raw.size(), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < P; r++) {
+    int okr = 0;
+    memcpy(&all[(size_t) r*NH], raw.data() + (size_t) r*(nb + sizeof(int)), nb);
+    memcpy(&okr, raw.data() + (size_t) r*(nb + sizeof(int)) + nb, sizeof(int));
+    ok = ok && okr;
+  }
+
+  // map the neighbours (the same rank on both sides when P == 2: map once)
+  auto map_rank = [&](int r, PeerLink * L) -> int {
+    void * ptr[NH];
+    for (int i = 0; i < NH; i++) {
+      ptr[i] = nullptr;
+      if (mine[i] == nullptr) continue;
+      if (cudaIpcOpenMemHandle(&ptr[i], all[(size_t) r*NH + i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+	cudaGetLastError();
+	return 0;
+      }
+      c->mapped[c->nmapped++] = ptr[i];
+    }
+    L->f[0] = (double *) ptr[0]; L->f[1] = (double *) ptr[1];
+    L->phi[0] = (double *) ptr[2]; L->phi[1] = (double *) ptr[3];
+    L->u[0] = (double *) ptr[4]; L->u[1] = (double *) ptr[5];
+    L->flags = (unsigned int *) ptr[6];
+    return 1;
+  };
+  int mapped_ok = ok;
+  if (mapped_ok) mapped_ok = map_rank(left, &c->lo);
+  if (mapped_ok) { if (right == left) c->hi = c->lo; else mapped_ok = map_rank(right, &c->hi); }
+
+  // every rank must reach the same verdict
+  {
+    int * dflag = (int *) dsend;
+    CUDA_TRY(cudaMemcpyAsync(dflag, &mapped_ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (ncclAllReduce(dflag, dflag, 1, ncclInt, ncclMin, comm, c->stream) != ncclSuccess) {
+      return fail(LB200_ECOMM, "ncclAllReduce of the peer set-up verdict failed");
+    }
+    CUDA_TRY(cudaMemcpyAsync(&mapped_ok, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(dsend); cudaFree(drecv);
+
+  {
+    // stream memory operations for the consumer side of the flags (the polling kernel is the fallback)
+    void * fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess
+	&& q == cudaDriverEntryPointSuccess && getenv("LB200_SPIN_WAIT") == nullptr) c->wait_value32 = fn;
+    else cudaGetLastError();
+  }
+  c->peer_state = mapped_ok ? 1 : -1;
+  return 0;
+#endif
+}
+
+int lb200_exchange_mode(const lb200_t * c) {
+  if (c == nullptr || !c->g.remote_x) return 0;
+  return (c->peer_state == 1 && c->knob_peer) ? 2 : 1;
+}
+
+typedef int (* wait_value32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+
+// wait until the neighbours on both sides have signalled `value` on the flag pair (lo, hi)
+static int flags_wait(lb200_t * c, cudaStream_t st, int ilo, unsigned int value) {
+  for (int i = ilo; i <= ilo + 1; i++) {
+    if (c->wait_value32 != nullptr) {
+      // CU_STREAM_WAIT_VALUE_GEQ = 0: (int32_t)(*addr - value) >= 0
+      int r = ((wait_value32_fn) c->wait_value32)(st, (unsigned long long) (uintptr_t) (c->flags + i), value, 0u);
+      if (r != 0) return fail(LB200_ECUDA, "cuStreamWaitValue32 failed (%d)", r);
+    }
+    else {
+      c->launches += c->k->spin_wait(st, c->flags + i, value, 20000, c->spin_err);
+    }
+  }
+  return 0;
+}
+
 // ---- halo-free whole time steps ---------------------------------------------------------------------
 // On a periodic lattice every halo site is the image of an interior site of the same GPU (y, z; x too
 // on one GPU), so the kernels of lb200_step read those images straight from the interior (Lb200Geom::wrap)
@@ -1095,6 +1248,15 @@ static int wrap_exchange_f(lb200_t * c, cudaStream_t st) {
   return 0;
 }
 
+static int idx2(const double * ptr, double * const alloc[2]) { return (ptr == alloc[0]) ? 0 : 1; }
+
+// make the boundary data of one kind available to the next kernel on S
+static int src_wait(lb200_t * c, cudaStream_t S, int src, cudaEvent_t ev, int flag_lo, unsigned int value) {
+  if (src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, ev, 0));
+  else if (src == SRC_FLAG) return flags_wait(c, S, flag_lo, value);
+  return 0;
+}
+
 static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev * sd, int nsteps) {
   const int binary = (sd != nullptr);
   const int remote = c->g.remote_x;
@@ -1104,9 +1266,18 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   int rc = 0;
 
   if (remote) {
+    rc = peer_setup(c);                  // collective, does something the first time only
+    if (rc != 0) return rc;
+  }
+  // peer stores from inside the kernels + flags instead of NCCL messages
+  const bool peer = remote && c->peer_state == 1 && c->knob_peer;
+
+  if (remote) {
     CUDA_TRY(cudaEventRecord(c->ev_main, S));
     CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
     if (!c->wrap_x_valid) {
+      // The state did not come out of a previous lb200_step: one round of messages brings the planes the
+      // first kernels read (and orders this step after whatever the neighbours were doing before).
       if (binary) {
 	if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
 	CUDA_TRY(cudaEventRecord(c->ev_main, S));
@@ -1114,10 +1285,8 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	rc = wrap_exchange_phi(c, C);
 	if (rc != 0) return rc;
       }
-      if (binary) {
-	rc = wrap_exchange_ux(c, C);
-	if (rc != 0) return rc;
-      }
+      rc = wrap_exchange_ux(c, C);
+      if (rc != 0) return rc;
       CUDA_TRY(cudaEventRecord(c->ev_phi, C));
       CUDA_TRY(cudaEventRecord(c->ev_u, C));
       if (c->prop_pending) {
@@ -1125,6 +1294,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	if (rc != 0) return rc;
       }
       CUDA_TRY(cudaEventRecord(c->ev_f, C));
+      c->phi_src = c->u_src = c->f_src = SRC_EVENT;
     }
   }
   if (c->u_state == ZERO_PENDING && binary) materialise_zero(c, c->u, &c->u_state);
@@ -1133,9 +1303,12 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     c->force_state = ZERO_PENDING;                                       // hydro_f_zero
     if (binary) {
       if (remote) {
-	CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
-	CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
+	rc = src_wait(c, S, c->phi_src, c->ev_phi, FLAG_PS_LO, c->n_ps);
+	if (rc == 0) rc = src_wait(c, S, c->u_src, c->ev_u, FLAG_COL_LO, c->n_col);
+	if (rc != 0) return rc;
       }
+      gw.peer_phi_lo = peer ? c->lo.phi[idx2(c->phinew, c->phi_alloc)] : nullptr;
+      gw.peer_phi_hi = peer ? c->hi.phi[idx2(c->phinew, c->phi_alloc)] : nullptr;
       {
 	// field_halo(phi) + field_grad_compute + phi_force_calculation + phi_cahn_hilliard (hydro_u_halo inside)
 	ProfScope ps(c, LB200_K_PHI_SECTOR);
@@ -1143,27 +1316,61 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       }
       c->force_state = INTERIOR_ONLY;
       double * t = c->phi; c->phi = c->phinew; c->phinew = t;
-      if (remote) {
+      if (peer) {
+	// the new phi planes are already in the neighbours' halo planes: tell them
+	c->n_ps++;
+	c->launches += c->k->signal(S, c->hi.flags + FLAG_PS_LO, c->lo.flags + FLAG_PS_HI, c->n_ps);
+	c->phi_src = SRC_FLAG;
+      }
+      else if (remote) {
 	CUDA_TRY(cudaEventRecord(c->ev_main, S));
 	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
 	rc = wrap_exchange_phi(c, C);                                    // overlaps the collision
 	if (rc != 0) return rc;
 	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+	c->phi_src = SRC_EVENT;
       }
     }
     c->u_state = ZERO_PENDING;                                           // hydro_u_zero
-    if (remote && c->prop_pending) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
-    if (!c->prop_pending) {
-      // first collision after an lb_memcpy / explicit propagation: in place, nothing to pull
-      rc = collide_async(c, cd, nullptr);
+    if (remote) {
+      rc = src_wait(c, S, c->f_src, c->ev_f, FLAG_COL_LO, c->n_col);
+      if (rc != 0) return rc;
     }
-    else {
-      rc = collide_async(c, cd, &gw);                                    // lb_halo + lb_propagation + lb_collide
+    {
+      // lb_halo + lb_propagation + lb_collide (in place the first time after an lb_memcpy / explicit propagation)
+      double * u_out = c->u;
+      if (peer) {
+	// the neighbours' phi sector may still be reading the u_x plane it got last step: write the other buffer
+	u_out = (c->u == c->u_alloc[0]) ? c->u_alloc[1] : c->u_alloc[0];
+	const double * fdst = c->prop_pending ? c->fprime : c->f;
+	gw.peer_f_lo = c->lo.f[idx2(fdst, c->f_alloc)];
+	gw.peer_f_hi = c->hi.f[idx2(fdst, c->f_alloc)];
+	gw.peer_u_lo = binary ? c->lo.u[idx2(u_out, c->u_alloc)] : nullptr;
+	gw.peer_u_hi = binary ? c->hi.u[idx2(u_out, c->u_alloc)] : nullptr;
+      }
+      ProfScope ps(c, LB200_K_COLLIDE);
+      const double * force = (c->force_state == ZERO_PENDING) ? nullptr : c->force;
+      if (c->prop_pending) {
+	c->launches += c->k->collide(S, gw, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, force, status_ptr(c), c->rho, u_out);
+	double * t = c->f; c->f = c->fprime; c->fprime = t;
+	c->prop_pending = 0;
+      }
+      else {
+	Lb200Geom gi = c->g;                                             // in place: no pull, but the peer stores
+	gi.peer_f_lo = gw.peer_f_lo; gi.peer_f_hi = gw.peer_f_hi; gi.peer_u_lo = gw.peer_u_lo; gi.peer_u_hi = gw.peer_u_hi;
+	c->launches += c->k->collide(S, gi, cd, model_ptr(c), c->nvel, 0, c->f, c->f, force, status_ptr(c), c->rho, u_out);
+      }
+      c->u = u_out;
+      c->u_state = INTERIOR_ONLY;
     }
-    if (rc != 0) return rc;
     c->prop_pending = 1;                                                 // lb_halo; lb_propagation (lazy)
     c->f_halo_stale = 1;
-    if (remote) {
+    if (peer) {
+      c->n_col++;
+      c->launches += c->k->signal(S, c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
+      c->f_src = c->u_src = SRC_FLAG;
+    }
+    else if (remote) {
       CUDA_TRY(cudaEventRecord(c->ev_main, S));
       CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
       if (binary) {
@@ -1174,20 +1381,21 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       rc = wrap_exchange_f(c, C);                                        // overlaps the next phi sector
       if (rc != 0) return rc;
       CUDA_TRY(cudaEventRecord(c->ev_f, C));
+      c->f_src = c->u_src = SRC_EVENT;
     }
   }
   c->phi_halo_valid = 0;
   c->u_halo_valid = 0;
   c->wrap_x_valid = 1;
   if (remote) {
-    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
-    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
-    if (binary) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
+    // rejoin: whatever is still in flight on the comm stream is ordered before what follows on the main stream
+    if (c->f_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
+    if (c->u_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
+    if (binary && c->phi_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
-
 
 // ---- whole time steps ---------------------------------------------------------------------------------
 // Order of operations of the reference driver (src/ludwig.c:528-860):

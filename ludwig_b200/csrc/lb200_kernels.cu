@@ -169,6 +169,14 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 #pragma unroll
 	for (int p = 0; p < 19; p++) fdst[p*ns + index] = f[p];
       }
+      if (ic == 1 && g.peer_f_lo != nullptr) {
+#pragma unroll
+	for (int p = 0; p < 19; p++) if (CV19[p][0] < 0) g.peer_f_lo[p*ns + (size_t) index + (size_t) g.nl[0]*g.xs] = f[p];
+      }
+      if (ic == g.nl[0] && g.peer_f_hi != nullptr) {
+#pragma unroll
+	for (int p = 0; p < 19; p++) if (CV19[p][0] > 0) g.peer_f_hi[p*ns + (size_t) index - (size_t) g.nl[0]*g.xs] = f[p];
+      }
       return;
     }
   }
@@ -194,6 +202,21 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
   rho_out[index] = rho;
 #pragma unroll
   for (int ia = 0; ia < 3; ia++) u_out[ia*ns + index] = u[ia];
+
+  // boundary planes straight into the neighbour GPUs' halo planes (NVLink peer stores): what their next
+  // pull-collision and phi sector read from this slab (block-uniform branches, 2 of N planes)
+  if (ic == 1 && g.peer_f_lo != nullptr) {
+    const size_t dst = (size_t) index + (size_t) g.nl[0]*g.xs;            // my plane 1 -> its plane N+1
+#pragma unroll
+    for (int p = 0; p < 19; p++) if (CV19[p][0] < 0) g.peer_f_lo[p*ns + dst] = f[p];
+    if (g.peer_u_lo != nullptr) g.peer_u_lo[dst] = u[0];
+  }
+  if (ic == g.nl[0] && g.peer_f_hi != nullptr) {
+    const size_t dst = (size_t) index - (size_t) g.nl[0]*g.xs;            // my plane N -> its plane 0
+#pragma unroll
+    for (int p = 0; p < 19; p++) if (CV19[p][0] > 0) g.peer_f_hi[p*ns + dst] = f[p];
+    if (g.peer_u_hi != nullptr) g.peer_u_hi[dst] = u[0];
+  }
 }
 
 // Generic velocity set (D3Q15, D3Q27; also D3Q19 with the model matrices instead of the coded
@@ -246,6 +269,10 @@ collide_generic_kernel(const Lb200Geom g, const Lb200CollideDev cp,
     if (PULL) {
       for (int p = 0; p < nvel; p++) fdst[p*ns + index] = f[p];
     }
+    for (int p = 0; p < nvel; p++) {
+      if (ic == 1 && g.peer_f_lo != nullptr && md->cv[p][0] < 0) g.peer_f_lo[p*ns + (size_t) index + (size_t) g.nl[0]*g.xs] = f[p];
+      if (ic == g.nl[0] && g.peer_f_hi != nullptr && md->cv[p][0] > 0) g.peer_f_hi[p*ns + (size_t) index - (size_t) g.nl[0]*g.xs] = f[p];
+    }
     return;
   }
 
@@ -263,14 +290,19 @@ collide_generic_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 
   for (int m = 10; m < nvel; m++) mode[m] = mode[m] - cp.rtau_ghost[m]*(mode[m] - 0.0);
 
+  const bool to_lo = (ic == 1 && g.peer_f_lo != nullptr), to_hi = (ic == g.nl[0] && g.peer_f_hi != nullptr);
   for (int p = 0; p < nvel; p++) {
     double s = 0.0;
     for (int m = 0; m < nvel; m++) s += md->mi[p][m]*mode[m];
     fdst[p*ns + index] = s;
+    if (to_lo && md->cv[p][0] < 0) g.peer_f_lo[p*ns + (size_t) index + (size_t) g.nl[0]*g.xs] = s;
+    if (to_hi && md->cv[p][0] > 0) g.peer_f_hi[p*ns + (size_t) index - (size_t) g.nl[0]*g.xs] = s;
   }
 
   rho_out[index] = rho;
   for (int ia = 0; ia < 3; ia++) u_out[ia*ns + index] = u[ia];
+  if (to_lo && g.peer_u_lo != nullptr) g.peer_u_lo[(size_t) index + (size_t) g.nl[0]*g.xs] = u[0];
+  if (to_hi && g.peer_u_hi != nullptr) g.peer_u_hi[(size_t) index - (size_t) g.nl[0]*g.xs] = u[0];
 }
 
 int launch_collide(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev & cp,
@@ -1411,6 +1443,9 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc, const double
       double ph = ph_c;
       ph -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
       phinew[s] = ph;
+      // the planes the neighbour GPUs' next phi sector reads, straight into their halo planes
+      if (g.peer_phi_lo != nullptr && i <= nh) g.peer_phi_lo[(size_t) s + (size_t) g.nl[0]*xs] = ph;
+      if (g.peer_phi_hi != nullptr && i > g.nl[0] - nh) g.peer_phi_hi[(size_t) s - (size_t) g.nl[0]*xs] = ph;
     }
 
     // ---- 4. rotate the own-column history, publish the prefetched plane ----
@@ -1486,6 +1521,7 @@ struct PfK {                               // per-thread / per-CTA constants
   bool has_e1, valid_g, out_site, face_row, own_g;
   int xs, ns, nh, nlx, wx, i0, i1;
   double M, kappa, a, b, mg0, mg1, mg2, wz;
+  double * peer_lo, * peer_hi;            // neighbour GPUs' phi' arrays (nullptr: none)
 };
 
 // partial sums of one phi plane at the own column: B, Cy, Cz
@@ -1617,7 +1653,11 @@ __device__ __forceinline__ void pf_step(PfShared & sm, PfRegs & r, const PfK & k
   if (do_upd && k.out_site) {
     const double (* fl)[PS_NT] = sm.fl[(q + 1) & 1];
     const int s = (n - 1 + k.nh - 1)*k.xs + k.scol;
-    phinew[s] = r.phim1 - (((r.fxm1 - r.fxm2) + (r.fy_prev - fl[0][tym])) + k.wz*(r.fz_prev - fl[1][tzm]));
+    const double phn = r.phim1 - (((r.fxm1 - r.fxm2) + (r.fy_prev - fl[0][tym])) + k.wz*(r.fz_prev - fl[1][tzm]));
+    phinew[s] = phn;
+    // the planes the neighbour GPUs' next phi sector reads, straight into their halo planes
+    if (k.peer_lo != nullptr && n - 1 <= k.nh) k.peer_lo[(size_t) s + (size_t) k.nlx*k.xs] = phn;
+    if (k.peer_hi != nullptr && n - 1 > k.nlx - k.nh) k.peer_hi[(size_t) s - (size_t) k.nlx*k.xs] = phn;
   }
 
   // ---- 5. rotate the own-column history; the prefetch issued ONE step ago must have landed ----
@@ -1657,6 +1697,7 @@ phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
   k.i0 = 1 + blockIdx.z*xc;
   k.i1 = min(k.i0 + xc - 1, g.nl[0]);
   k.M = sp.mobility; k.kappa = sp.kappa; k.a = sp.a; k.b = sp.b; k.wz = sp.wz;
+  k.peer_lo = g.peer_phi_lo; k.peer_hi = g.peer_phi_hi;
   k.mg0 = sp.mobility*sp.gm[0]; k.mg1 = sp.mobility*sp.gm[1]; k.mg2 = sp.mobility*sp.gm[2];
 
   const bool inner = (ty >= 1 && ty <= PS_TY && tz >= 1 && tz <= PS_TZ);
@@ -1789,6 +1830,46 @@ int launch_phi_sector(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cross-GPU flags of the peer-store exchange.  The signal runs in stream order after the producing
+// kernel, whose peer stores are therefore complete and visible system-wide; the consumer waits with a
+// stream memory operation (cuStreamWaitValue32) or, where that is unavailable, with this polling kernel.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void signal_kernel(unsigned int * a, unsigned int * b, unsigned int value) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (a != nullptr) *((volatile unsigned int *) a) = value;
+    if (b != nullptr) *((volatile unsigned int *) b) = value;
+    __threadfence_system();
+  }
+}
+
+__global__ void spin_wait_kernel(const unsigned int * flag, unsigned int value, long long timeout_ns, int * err) {
+  if (threadIdx.x == 0) {
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    // (int) difference: the counters wrap around after 2^32 exchanges
+    while ((int) (*((volatile const unsigned int *) flag) - value) < 0) {
+      long long t1;
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) { *err = 1; break; }
+    }
+    __threadfence_system();
+  }
+}
+
+int launch_signal(cudaStream_t st, unsigned int * a, unsigned int * b, unsigned int value) {
+  signal_kernel<<<1, 32, 0, st>>>(a, b, value);
+  return 1;
+}
+
+int launch_spin_wait(cudaStream_t st, const unsigned int * flag, unsigned int value, int timeout_ms, int * err) {
+  spin_wait_kernel<<<1, 32, 0, st>>>(flag, value, (long long) timeout_ms*1000000LL, err);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // zero everything outside the interior (materialises "logically zero" halos of force / u)
 // ---------------------------------------------------------------------------------------------
 
@@ -1837,4 +1918,6 @@ const Lb200Kernels LB200_TABLE = {
   launch_collide_binary,
   launch_stress,
   launch_force_from_stress,
+  launch_signal,
+  launch_spin_wait,
 };

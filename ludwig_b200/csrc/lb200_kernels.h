@@ -15,6 +15,14 @@ struct Lb200Geom {
   int has_hi;
   int remote_x;     // 1: x-neighbours are other GPUs, their planes arrive in staging buffers
   int wrap[3];      // 1: kernels read the periodic images of this dimension from the interior (no halo needed)
+  // Peer stores (x-slabs on several GPUs, lb200_step): the neighbour GPUs' arrays, mapped into this process
+  // (cudaIpc over NVLink).  A kernel that produces a boundary plane also stores it in the halo plane of the
+  // neighbour that will read it: collide -> populations with c_x = -1 / +1 and u_x of planes 1 / N into the
+  // low / high neighbour's destination buffers; phi sector -> the new phi of planes 1..nh / N-nh+1..N.
+  // nullptr: no peer store.
+  double * peer_f_lo, * peer_f_hi;
+  double * peer_u_lo, * peer_u_hi;
+  double * peer_phi_lo, * peer_phi_hi;
 };
 
 struct Lb200CollideDev {
@@ -84,6 +92,11 @@ struct Lb200Kernels {
   int (*stress)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, const double * phi, const double * grad,
 		const double * delsq, double * str);
   int (*force_from_stress)(cudaStream_t, const Lb200Geom &, int accumulate, const double * str, double * force);
+  // cross-GPU flags of the peer-store exchange: *a = *b = value after everything earlier in the stream
+  // (either pointer may be nullptr); wait until *flag >= value (fallback when stream memory operations are
+  // not available), giving up after ~timeout_ms with *err = 1
+  int (*signal)(cudaStream_t, unsigned int * a, unsigned int * b, unsigned int value);
+  int (*spin_wait)(cudaStream_t, const unsigned int * flag, unsigned int value, int timeout_ms, int * err);
 };
 
 extern const Lb200Kernels lb200_kernels_fast;

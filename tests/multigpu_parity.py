@@ -27,6 +27,8 @@ def main():
     nxl, ny, nz = 6, 10, 34
     periodic = (1, 1, 1) if len(sys.argv) < 2 else tuple(int(c) for c in sys.argv[1])
     reduced = 0 if len(sys.argv) < 3 else int(sys.argv[2])
+    peer = 1 if len(sys.argv) < 4 else int(sys.argv[3])
+    binary = 1 if len(sys.argv) < 5 else int(sys.argv[4])
     nglobal = (nxl * world, ny, nz)
     nhalo = 2
     orc_g = Oracle(nglobal, nhalo=nhalo, periodic=periodic)
@@ -47,23 +49,38 @@ def main():
     ids = [sim.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     sim.nccl_init(ids[0], world, rank)
+    sim.set_knob(lb.KNOB_PEER, peer)
     sim.put(lb.F, slab(st["f"])); sim.put(lb.PHI, slab(st["phi"]))
     cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA, force=fg)
     sp = lb.SymmParam.make(adv_order=3, **BINARY)
     # every path over the decomposed lattice, and the hand-overs between them: halo-free lb200_step (only the
     # planes the kernels read cross NVLink), the individual entry points (full halo swaps), lb200_step again
+    if not binary:
+        sp = None
     sim.step(cp, sp, 2)
+    mode = sim.exchange_mode()
     sim.step_api(cp, sp, 2)
     sim.step(cp, sp, nsteps - 4)
+    fully_periodic = all(periodic)
+    if rank == 0:
+        print(f"exchange mode of lb200_step: {mode} (0 single, 1 NCCL, 2 peer stores); requested peer={peer}", flush=True)
+    if fully_periodic and peer and os.environ.get("LB200_ALLOW_NO_PEER") is None:
+        assert mode == 2, "peer-store exchange was requested but could not be set up"
     mine = {k: np.ascontiguousarray(orc_l.interior(sim.get(a))) for k, a in
             (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO), ("force", lb.FORCE))}
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     ok = True
     if rank == 0:
-        orc_g.step(orc_g.collide_param(0, 1.0, ETA, force=fg), orc_g.symm_param(adv_order=3, **BINARY), 1, nsteps,
-                   st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"], halo_reduced=reduced)
+        if binary:
+            orc_g.step(orc_g.collide_param(0, 1.0, ETA, force=fg), orc_g.symm_param(adv_order=3, **BINARY), 1, nsteps,
+                       st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"], halo_reduced=reduced)
+        else:
+            orc_g.step(orc_g.collide_param(0, 1.0, ETA, force=fg), None, 0, nsteps,
+                       st["f"], None, st["u"], st["rho"], st["force"], None, None, halo_reduced=reduced)
         for k in mine:
+            if not binary and k in ("phi", "force"):
+                continue
             full = np.concatenate([g[k] for g in gathered], axis=1)
             same = np.array_equal(full, orc_g.interior(st[k]))
             print(f"multigpu parity world={world} periodic={periodic} reduced={reduced} {k}: {'OK' if same else 'MISMATCH'}", flush=True)

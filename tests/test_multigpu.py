@@ -18,16 +18,19 @@ def ngpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("periodic,reduced", [("111", 0), ("011", 0), ("111", 1)])
-def test_slab_decomposition_matches_single_domain_oracle(periodic, reduced):
+@pytest.mark.parametrize("periodic,reduced,peer,binary", [("111", 0, 1, 1), ("111", 0, 0, 1), ("011", 0, 1, 1), ("111", 1, 1, 1),
+                                                         ("111", 0, 1, 0), ("111", 0, 0, 0)])
+def test_slab_decomposition_matches_single_domain_oracle(periodic, reduced, peer, binary):
+    """x-slabs on 2 (4) GPUs == the undecomposed oracle, bit for bit, with the planes of lb200_step travelling by
+    NVLink peer stores from inside the kernels (peer = 1) or by NCCL send/recv (peer = 0); binary and single fluid."""
     n = ngpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(HERE, "multigpu_parity.py"),
-           periodic, str(reduced)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           periodic, str(reduced), str(peer), str(binary)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0
     assert "MISMATCH" not in r.stdout and "OK" in r.stdout
