@@ -218,6 +218,28 @@ typedef struct lb200_slab_plan_s {
 } lb200_slab_plan_t;
 int lb200_slab_plan(const lb200_options_t * options, int ncomp, int depth, lb200_slab_plan_t * plan);
 
+/* What lb200_step moves between x-slabs in halo-free mode (pure host arithmetic): per array only the components
+ * and planes the NEXT kernel reads across the slab boundary -- y/z images are read in-kernel from the interior.
+ * `up` goes to the high neighbour (my top planes -> its low halo planes), `down` to the low neighbour.
+ * With the peer-store exchange a kernel adds `peer_shift` (down) or subtracts it (up) to the index of a boundary
+ * site to get the index of its image in the neighbour's array. */
+enum lb200_step_array {LB200_STEP_PHI = 0, LB200_STEP_UX = 1, LB200_STEP_F = 2};
+typedef struct lb200_step_plan_s {
+  int left, right;          /* neighbour ranks */
+  int depth;                /* planes per direction: nhalo for phi, 1 for u_x and f */
+  int ncomp_up, ncomp_down; /* components travelling up / down */
+  int comp_up[27];          /* f: populations with c_x = +1; phi, u_x: component 0 */
+  int comp_down[27];        /* f: populations with c_x = -1 */
+  long long nsites;         /* component stride */
+  long long chunk;          /* depth * nall[Y] * nall[Z] */
+  long long src_up;         /* first element of my planes [N-depth+1, N] */
+  long long dst_up;         /* first element of the receiver's halo planes [1-depth, 0] */
+  long long src_down;       /* first element of my planes [1, depth] */
+  long long dst_down;       /* first element of the receiver's halo planes [N+1, N+depth] */
+  long long peer_shift;     /* nlocal[X] * nall[Y] * nall[Z] */
+} lb200_step_plan_t;
+int lb200_step_plan(const lb200_options_t * options, int step_array, lb200_step_plan_t * plan);
+
 /* multi-GPU: attach an NCCL communicator (ncclComm_t, one rank per slab, rank == cart_rank) used
  * for the x-direction halo planes; replaces MPI_Isend/Irecv of lb_halo_post/field_halo_post
  * (src/lb_data.c:1317-1420, src/field.c:1412-1531). */

@@ -56,6 +56,32 @@ class SlabPlan(C.Structure):
                 ("count", C.c_longlong)]
 
 
+class StepPlan(C.Structure):
+    _fields_ = [("left", C.c_int), ("right", C.c_int), ("depth", C.c_int), ("ncomp_up", C.c_int), ("ncomp_down", C.c_int),
+                ("comp_up", C.c_int * 27), ("comp_down", C.c_int * 27), ("nsites", C.c_longlong), ("chunk", C.c_longlong),
+                ("src_up", C.c_longlong), ("dst_up", C.c_longlong), ("src_down", C.c_longlong),
+                ("dst_down", C.c_longlong), ("peer_shift", C.c_longlong)]
+
+
+STEP_PHI, STEP_UX, STEP_F = 0, 1, 2
+
+
+def step_plan(nlocal, nhalo, cart_size, cart_rank, what, nvel=19):
+    """lb200_step_plan: what lb200_step moves between x-slabs in halo-free mode (works without a GPU)."""
+    lib = load_library()
+    o = Options()
+    o.nlocal[:] = nlocal
+    o.nhalo = nhalo
+    o.periodic[:] = (1, 1, 1)
+    o.nvel, o.ndist, o.halo_scheme = nvel, 1, HALO_FULL
+    o.cart_size, o.cart_rank = cart_size, cart_rank
+    p = StepPlan()
+    rc = lib.lb200_step_plan(C.byref(o), what, C.byref(p))
+    if rc != 0:
+        raise Lb200Error(lib.lb200_last_error().decode())
+    return p
+
+
 def slab_plan(nlocal, nhalo, periodic, cart_size, cart_rank, ncomp, depth):
     """lb200_slab_plan: the x-slab exchange plan (pure host arithmetic; works without a GPU)."""
     lib = load_library()
@@ -117,6 +143,7 @@ def load_library():
     lib.lb200_profile.argtypes = [C.c_void_p, C.c_int]
     lib.lb200_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.lb200_slab_plan.argtypes = [C.POINTER(Options), C.c_int, C.c_int, C.POINTER(SlabPlan)]
+    lib.lb200_step_plan.argtypes = [C.POINTER(Options), C.c_int, C.POINTER(StepPlan)]
     lib.lb200_attach_nccl.argtypes = [C.c_void_p, C.c_void_p]
     lib.lb200_nccl_unique_id.argtypes = [C.c_void_p]
     lib.lb200_nccl_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]

@@ -630,6 +630,37 @@ int lb200_slab_plan(const lb200_options_t * o, int ncomp, int depth, lb200_slab_
   return 0;
 }
 
+int lb200_step_plan(const lb200_options_t * o, int what, lb200_step_plan_t * p) {
+  if (o == nullptr || p == nullptr) return fail(LB200_EINVAL, "null argument");
+  if (o->cart_size < 1 || o->cart_rank < 0 || o->cart_rank >= o->cart_size) return fail(LB200_EINVAL, "bad cart_size/cart_rank");
+  if (what != LB200_STEP_PHI && what != LB200_STEP_UX && what != LB200_STEP_F) return fail(LB200_EINVAL, "unknown step array %d", what);
+  memset(p, 0, sizeof(*p));
+  const long long nay = o->nlocal[1] + 2*o->nhalo, naz = o->nlocal[2] + 2*o->nhalo, nax = o->nlocal[0] + 2*o->nhalo;
+  const long long xs = nay*naz;
+  p->left = (o->cart_rank - 1 + o->cart_size) % o->cart_size;
+  p->right = (o->cart_rank + 1) % o->cart_size;
+  p->depth = (what == LB200_STEP_PHI) ? o->nhalo : 1;
+  p->nsites = nax*xs;
+  p->chunk = p->depth*xs;
+  p->src_up = (long long) (o->nlocal[0] - p->depth + o->nhalo)*xs;
+  p->dst_up = (long long) (o->nhalo - p->depth)*xs;
+  p->src_down = (long long) o->nhalo*xs;
+  p->dst_down = (long long) (o->nlocal[0] + o->nhalo)*xs;
+  p->peer_shift = (long long) o->nlocal[0]*xs;
+  if (what == LB200_STEP_F) {
+    Lb200ModelDev md;
+    if (model_init(o->nvel, &md) != 0) return fail(LB200_EINVAL, "nvel = %d", o->nvel);
+    for (int q = 0; q < o->nvel; q++) {
+      if (md.cv[q][0] > 0) p->comp_up[p->ncomp_up++] = q;
+      if (md.cv[q][0] < 0) p->comp_down[p->ncomp_down++] = q;
+    }
+  }
+  else {
+    p->ncomp_up = p->ncomp_down = 1;
+  }
+  return 0;
+}
+
 // ---- x-plane exchange between slabs (NCCL send/recv over NVLink) --------------------------------
 // Replaces MPI_Isend/Irecv/Waitall of lb_halo_post / field_halo_post.  For each component the
 // `depth` boundary planes at either end of the slab are contiguous in the SOA layout, so no pack
@@ -1202,49 +1233,49 @@ static int wrap_exchange_ux(lb200_t * c, cudaStream_t st) {
   return nccl_exchange(c, st, &m, 1);
 }
 
-// ... and the populations moving in +x / -x of planes N / 1 (overlaps the phi sector)
+// ... and the populations moving in +x / -x of planes N / 1 (overlaps the phi sector); what travels is
+// lb200_step_plan(LB200_STEP_F): runs of consecutive populations are gathered / scattered with one strided copy
 static int wrap_exchange_f(lb200_t * c, cudaStream_t st) {
-  const Lb200Geom & g = c->g;
-  const size_t xs = (size_t) g.xs, ns = (size_t) g.nsites;
-  const int nv = c->nvel;
-  ProfScope ps(c, LB200_K_HALO, st);
-  // runs of consecutive populations with c_x = +1 (sent up) and c_x = -1 (sent down)
-  double * shi = c->shi, * slo = c->slo, * rlo = c->xlo, * rhi = c->xhi;
-  size_t nup = 0, ndn = 0;
-  for (int sign = 1; sign >= -1; sign -= 2) {
-    for (int p = 0; p < nv; ) {
-      if (c->model_h.cv[p][0] != sign) { p++; continue; }
-      int q = p;
-      while (q < nv && c->model_h.cv[q][0] == sign) q++;
-      const size_t plane = (size_t) ((sign > 0 ? g.nl[0] : 1) + g.nh - 1)*xs;
-      double * dst = (sign > 0) ? shi + nup*xs : slo + ndn*xs;
-      CUDA_TRY(cudaMemcpy2DAsync(dst, xs*sizeof(double), c->f + (size_t) p*ns + plane, ns*sizeof(double),
-				 xs*sizeof(double), q - p, cudaMemcpyDeviceToDevice, st));
-      if (sign > 0) nup += q - p; else ndn += q - p;
-      p = q;
-    }
-  }
-  if (nup != ndn) return fail(LB200_ESTATE, "velocity set not symmetric in x");
-  XMsg m;
-  m.send_hi = shi; m.send_lo = slo; m.recv_lo = rlo; m.recv_hi = rhi; m.count = nup*xs;
-  int rc = nccl_exchange(c, st, &m, 1);
+  const size_t ns = (size_t) c->g.nsites;
+  lb200_step_plan_t pl;
+  int rc = lb200_step_plan(&c->opt, LB200_STEP_F, &pl);
   if (rc != 0) return rc;
-  // unpack: what came from the low neighbour are its c_x = +1 populations -> my plane 0; from the high
-  // neighbour its c_x = -1 populations -> my plane N+1
-  size_t kup = 0, kdn = 0;
-  for (int sign = 1; sign >= -1; sign -= 2) {
-    for (int p = 0; p < nv; ) {
-      if (c->model_h.cv[p][0] != sign) { p++; continue; }
-      int q = p;
-      while (q < nv && c->model_h.cv[q][0] == sign) q++;
-      const size_t plane = (size_t) ((sign > 0 ? 0 : g.nl[0] + 1) + g.nh - 1)*xs;
-      const double * src = (sign > 0) ? rlo + kup*xs : rhi + kdn*xs;
-      CUDA_TRY(cudaMemcpy2DAsync(c->f + (size_t) p*ns + plane, ns*sizeof(double), src, xs*sizeof(double),
-				 xs*sizeof(double), q - p, cudaMemcpyDeviceToDevice, st));
-      if (sign > 0) kup += q - p; else kdn += q - p;
-      p = q;
+  if (pl.ncomp_up != pl.ncomp_down) return fail(LB200_ESTATE, "velocity set not symmetric in x");
+  const size_t chunk = (size_t) pl.chunk;
+  ProfScope ps(c, LB200_K_HALO, st);
+  double * shi = c->shi, * slo = c->slo, * rlo = c->xlo, * rhi = c->xhi;
+
+  // dir 0: up (my plane N -> staging -> the high neighbour's plane 0), dir 1: down
+  auto strided = [&](int dir, bool pack) -> int {
+    const int * comp = dir == 0 ? pl.comp_up : pl.comp_down;
+    const int ncomp = dir == 0 ? pl.ncomp_up : pl.ncomp_down;
+    for (int a = 0; a < ncomp; ) {
+      int b = a;
+      while (b + 1 < ncomp && comp[b + 1] == comp[b] + 1) b++;
+      const int nrun = b - a + 1;
+      if (pack) {
+	double * dst = (dir == 0 ? shi : slo) + (size_t) a*chunk;
+	const double * src = c->f + (size_t) comp[a]*ns + (size_t) (dir == 0 ? pl.src_up : pl.src_down);
+	CUDA_TRY(cudaMemcpy2DAsync(dst, chunk*sizeof(double), src, ns*sizeof(double), chunk*sizeof(double), nrun,
+				   cudaMemcpyDeviceToDevice, st));
+      }
+      else {
+	// what arrives from the LOW neighbour are its `up` components -> my low halo plane; from the high one its `down`
+	const double * src = (dir == 0 ? rlo : rhi) + (size_t) a*chunk;
+	double * dst = c->f + (size_t) comp[a]*ns + (size_t) (dir == 0 ? pl.dst_up : pl.dst_down);
+	CUDA_TRY(cudaMemcpy2DAsync(dst, ns*sizeof(double), src, chunk*sizeof(double), chunk*sizeof(double), nrun,
+				   cudaMemcpyDeviceToDevice, st));
+      }
+      a = b + 1;
     }
-  }
+    return 0;
+  };
+  if ((rc = strided(0, true)) != 0 || (rc = strided(1, true)) != 0) return rc;
+  XMsg m;
+  m.send_hi = shi; m.send_lo = slo; m.recv_lo = rlo; m.recv_hi = rhi; m.count = (size_t) pl.ncomp_up*chunk;
+  rc = nccl_exchange(c, st, &m, 1);
+  if (rc != 0) return rc;
+  if ((rc = strided(0, false)) != 0 || (rc = strided(1, false)) != 0) return rc;
   return 0;
 }
 

@@ -129,3 +129,112 @@ def test_slab_plan_values():
     assert (q.has_lo, q.has_hi) == (1, 0) and q.chunk == 2 * 260 * 260 and q.off_hi == 256 * 260 * 260
     with pytest.raises(lb.Lb200Error):
         lb.slab_plan((8, 8, 8), 1, (1, 1, 1), 2, 0, 1, 2)      # depth > nhalo
+
+
+# ---- the halo-free time step of lb200_step on x-slabs: only what lb200_step_plan lists crosses the slab boundary ----
+
+def step_exchange(a, what, nlocal, nhalo, world, rank, nvel=19):
+    """Boundary planes of canonical array a -> the neighbours' halo planes, exactly the components and planes of
+    lb200_step_plan (the peer-store kernels and the NCCL path of lb200_step move precisely these)."""
+    import ludwig_b200 as lb
+    p = lb.step_plan(nlocal, nhalo, world, rank, what, nvel=nvel)
+    flat = a.reshape(a.shape[0], -1)
+    assert flat.shape[1] == p.nsites
+    up, down = list(p.comp_up[:p.ncomp_up]), list(p.comp_down[:p.ncomp_down])
+    assert p.dst_down - p.src_down == p.peer_shift and p.src_up - p.dst_up == p.peer_shift
+    send_up = torch.from_numpy(np.ascontiguousarray(flat[up, p.src_up:p.src_up + p.chunk]))
+    send_dn = torch.from_numpy(np.ascontiguousarray(flat[down, p.src_down:p.src_down + p.chunk]))
+    recv_lo, recv_hi = torch.empty_like(send_up), torch.empty_like(send_dn)
+    reqs = [dist.isend(send_up, p.right, tag=11), dist.isend(send_dn, p.left, tag=12),
+            dist.irecv(recv_lo, p.left, tag=11), dist.irecv(recv_hi, p.right, tag=12)]
+    for r in reqs:
+        r.wait()
+    nall = tuple(n + 2 * nhalo for n in nlocal)
+    h = nhalo
+    for buf, comps, off in ((recv_lo, up, p.dst_up), (recv_hi, down, p.dst_down)):
+        st = buf.numpy().reshape(len(comps), p.depth, nall[1], nall[2])
+        # the kernels read the y/z images of the received planes from their interior: emulate by wrapping the rims
+        wrapped = np.pad(st[:, :, h:-h, h:-h], ((0, 0), (0, 0), (h, h), (h, h)), mode="wrap")
+        flat[comps, off:off + p.chunk] = wrapped.reshape(len(comps), -1)
+
+
+def worker_halo_free(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ludwig_b200 as lb
+    from oracle import Oracle
+    nxl, ny, nz, nhalo, nsteps = 4, 5, 6, 2, 4
+    nglobal = (nxl * world, ny, nz)
+    og = Oracle(nglobal, nhalo=nhalo)
+    st = seeded_state(og, seed=34)
+    ol = Oracle((nxl, ny, nz), nhalo=nhalo, periodic=(0, 1, 1))
+
+    def slab(a):
+        v = a.reshape((-1,) + og.nall)
+        out = np.zeros((v.shape[0],) + ol.nall)
+        out[:, nhalo:nhalo + nxl] = v[:, nhalo + rank * nxl:nhalo + (rank + 1) * nxl]
+        return out.reshape(v.shape[0], -1)
+
+    f, phi = slab(st["f"]), slab(st["phi"])
+    z = lambda k: np.zeros((k, ol.nsites))
+    u, rho, force, grad, delsq, strs, flux = z(3), z(1), z(3), z(3), z(1), z(9), z(4)
+    fp = f.copy()
+    fg = (1e-6, -2e-6, 5e-7)
+    cp = ol.collide_param(0, 1.0, ETA, force=fg)
+    sp = ol.symm_param(adv_order=3, **BINARY)
+    n3 = (nxl, ny, nz)
+    for _ in range(nsteps):
+        force[...] = 0.0
+        ol.field_halo(phi)                                   # y/z images (in-kernel wrap on the GPU); x: nothing
+        step_exchange(phi, lb.STEP_PHI, n3, nhalo, world, rank)
+        ol.grad_27pt(phi, grad, delsq)
+        ol.stress_symm(sp, phi, grad, delsq, strs)
+        ol.force_divergence(strs, force)
+        ol.field_halo(u)
+        step_exchange(u, lb.STEP_UX, n3, nhalo, world, rank)  # u_x only, one plane
+        ol.advection(3, u, phi, flux); ol.flux_mu(sp, phi, delsq, flux); ol.flux_mu_ext(sp, flux)
+        ol.phi_update(flux, phi)
+        u[...] = 0.0
+        ol.collide(cp, f, force, rho, u)
+        ol.lb_halo(f)
+        step_exchange(f, lb.STEP_F, n3, nhalo, world, rank)   # 5 of 19 populations per direction
+        ol.propagation(f, fp)
+        f, fp = fp, f
+    mine = {k: np.ascontiguousarray(ol.interior(a)) for k, a in (("f", f), ("phi", phi), ("u", u), ("rho", rho))}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    if rank == 0:
+        og.step(og.collide_param(0, 1.0, ETA, force=fg), og.symm_param(adv_order=3, **BINARY), 1, nsteps,
+                st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+        ok = all(np.array_equal(np.concatenate([g[k] for g in gathered], axis=1), og.interior(st[k])) for k in mine)
+        ret.put(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_free_step_plan_is_sufficient_and_bit_exact(world):
+    """Only 2 planes of phi, 1 plane of u_x and the populations with c_x = +-1 cross the slab boundary per step and
+    direction (lb200_step_plan); the decomposed run still equals the undecomposed oracle bit for bit."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29700 + world * 7
+    procs = [ctx.Process(target=worker_halo_free, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) is True
+
+
+def test_step_plan_values():
+    import ludwig_b200 as lb
+    p = lb.step_plan((256, 256, 256), 2, 8, 3, lb.STEP_F)
+    assert (p.left, p.right, p.depth) == (2, 4, 1)
+    assert list(p.comp_up[:p.ncomp_up]) == [1, 2, 3, 4, 5] and list(p.comp_down[:p.ncomp_down]) == [14, 15, 16, 17, 18]
+    xs = 260 * 260
+    assert (p.src_up, p.dst_up, p.src_down, p.dst_down, p.peer_shift) == (257 * xs, 1 * xs, 2 * xs, 258 * xs, 256 * xs)
+    q = lb.step_plan((64, 256, 256), 2, 8, 0, lb.STEP_PHI)
+    assert (q.left, q.right, q.depth, q.chunk) == (7, 1, 2, 2 * xs) and (q.src_up, q.dst_up) == (64 * xs, 0)
+    r = lb.step_plan((8, 8, 8), 1, 2, 1, lb.STEP_F, nvel=27)
+    assert r.ncomp_up == 9 and r.ncomp_down == 9
