@@ -23,10 +23,24 @@ static void orc_nall(const orc_geom_t * g, int nall[3]) {
   for (int a = 0; a < 3; a++) nall[a] = g->nlocal[a] + 2*g->nhalo;
 }
 
-int orc_nsites(const orc_geom_t * g) {
+int orc_nsites_lb(const orc_geom_t * g) {
   int nall[3];
   orc_nall(g, nall);
   return nall[X]*nall[Y]*nall[Z];
+}
+
+/* lees_edw_nsites, src/leesedwards.c:485-495 (== cs_nsites without planes) */
+int orc_nsites(const orc_geom_t * g) {
+  int nall[3];
+  orc_nall(g, nall);
+  return (nall[X] + 2*g->nhalo*g->le_nplanes)*nall[Y]*nall[Z];
+}
+
+/* index offset of the x-neighbour di planes away, through the LE buffer region if a plane is crossed
+ * (lees_edw_ic_to_buff, src/leesedwards.c:1030-1065); di*xs without planes */
+static int xoff(const orc_geom_t * g, int ic, int di, int xs) {
+  if (g->le_nplanes == 0) return di*xs;
+  return (orc_le_ic_to_buff(g, ic, di) - ic)*xs;
 }
 
 int orc_index(const orc_geom_t * g, int ic, int jc, int kc) {
@@ -176,7 +190,7 @@ void orc_propagation(const orc_geom_t * g, const orc_model_t * m, int ndist,
 		     const double * f, double * fprime) {
   int nall[3];
   const int nh = g->nhalo;
-  const size_t ns = (size_t) orc_nsites(g);
+  const size_t ns = (size_t) orc_nsites_lb(g);
   orc_nall(g, nall);
   const int ys = nall[Z];
   const int xs = nall[Y]*nall[Z];
@@ -230,7 +244,7 @@ static void halo_limits(const orc_geom_t * g, int depth, const int c[3], lim_t *
 
 void orc_lb_halo(const orc_geom_t * g, const orc_model_t * m, int ndist, int reduced, double * f) {
 
-  const size_t ns = (size_t) orc_nsites(g);
+  const size_t ns = (size_t) orc_nsites_lb(g);
 
   for (int cx = -1; cx <= 1; cx++) {
     for (int cy = -1; cy <= 1; cy++) {
@@ -425,7 +439,8 @@ void orc_collide(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
 		 const char * status, int include_halo,
 		 double * f, const double * force, double * rho, double * u) {
 
-  const size_t ns = (size_t) orc_nsites(g);
+  const size_t ns = (size_t) orc_nsites(g);         /* hydro arrays */
+  const size_t nsf = (size_t) orc_nsites_lb(g);     /* distributions */
   const int nh = include_halo ? g->nhalo : 0;
 
   #pragma omp parallel for collapse(2) schedule(static)
@@ -437,10 +452,10 @@ void orc_collide(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
 	double hf[3];
 	double r, uu[3];
 	if (status && status[index] != ORC_MAP_FLUID) continue;
-	for (int p = 0; p < m->nvel; p++) fs[p] = f[(size_t) p*ns + index];
+	for (int p = 0; p < m->nvel; p++) fs[p] = f[(size_t) p*nsf + index];
 	for (int ia = 0; ia < 3; ia++) hf[ia] = force[(size_t) ia*ns + index];
 	collide_site(m, cp, fs, hf, &r, uu);
-	for (int p = 0; p < m->nvel; p++) f[(size_t) p*ns + index] = fs[p];
+	for (int p = 0; p < m->nvel; p++) f[(size_t) p*nsf + index] = fs[p];
 	rho[index] = r;
 	for (int ia = 0; ia < 3; ia++) u[(size_t) ia*ns + index] = uu[ia];
       }
@@ -471,8 +486,8 @@ void orc_grad_27pt_ne(const orc_geom_t * g, int nextra, const double * phi, doub
     for (int jc = 1 - nextra; jc <= g->nlocal[Y] + nextra; jc++) {
       for (int kc = 1 - nextra; kc <= g->nlocal[Z] + nextra; kc++) {
 	int index = orc_index(g, ic, jc, kc);
-	int indexm1 = index - xs;
-	int indexp1 = index + xs;
+	int indexm1 = index + xoff(g, ic, -1, xs);        /* lees_edw_ic_to_buff, :250-253 */
+	int indexp1 = index + xoff(g, ic, +1, xs);
 
 	grad[0*ns + index] = 0.5*r9*
 	  (+ field[indexp1-ys-1] - field[indexm1-ys-1]
@@ -615,14 +630,17 @@ void orc_advection(const orc_geom_t * g, int order, const double * u, const doub
 	int index0 = orc_index(g, ic, jc, kc);
 	double u0[3] = {u[0*ns + index0], u[1*ns + index0], u[2*ns + index0]};
 	double uf;
+	/* x-neighbours through lees_edw_ic_to_buff (src/advection.c:559-560, 792-795, 988-991) */
+	const int xm1 = xoff(g, ic, -1, xs), xp1 = xoff(g, ic, +1, xs);
+	const int xm2 = xoff(g, ic, -2, xs), xp2 = xoff(g, ic, +2, xs);
 
 	if (order == 1) {
 	  int index1, index;
-	  index1 = index0 - xs;
+	  index1 = index0 + xm1;
 	  uf = 0.5*(u0[X] + u[0*ns + index1]);
 	  index = index0; if (uf > 0.0) index = index1;
 	  fw[index0] = uf*phi[index];
-	  index1 = index0 + xs;
+	  index1 = index0 + xp1;
 	  uf = 0.5*(u0[X] + u[0*ns + index1]);
 	  index = index0; if (uf < 0.0) index = index1;
 	  fe[index0] = uf*phi[index];
@@ -637,9 +655,9 @@ void orc_advection(const orc_geom_t * g, int order, const double * u, const doub
 	}
 	else if (order == 2) {
 	  int index1;
-	  index1 = index0 - xs;
+	  index1 = index0 + xm1;
 	  fw[index0] = 0.5*(u0[X] + u[0*ns + index1])*1*0.5*(phi[index1] + phi[index0]);
-	  index1 = index0 + xs;
+	  index1 = index0 + xp1;
 	  fe[index0] = 0.5*(u0[X] + u[0*ns + index1])*1*0.5*(phi[index0] + phi[index1]);
 	  index1 = index0 + ys;
 	  fy[index0] = 0.5*(u0[Y] + u[1*ns + index1])*1*0.5*(phi[index0] + phi[index1]);
@@ -648,13 +666,13 @@ void orc_advection(const orc_geom_t * g, int order, const double * u, const doub
 	}
 	else {
 	  /* west: index2 = -2, index1 = -1, index3 = +1 */
-	  uf = 0.5*1*(u0[X] + u[0*ns + index0 - xs]);
-	  if (uf > 0.0) fw[index0] = adv3(uf, phi[index0 - 2*xs], phi[index0 - xs], phi[index0]);
-	  else          fw[index0] = adv3(uf, phi[index0 + xs], phi[index0], phi[index0 - xs]);
+	  uf = 0.5*1*(u0[X] + u[0*ns + index0 + xm1]);
+	  if (uf > 0.0) fw[index0] = adv3(uf, phi[index0 + xm2], phi[index0 + xm1], phi[index0]);
+	  else          fw[index0] = adv3(uf, phi[index0 + xp1], phi[index0], phi[index0 + xm1]);
 	  /* east */
-	  uf = 0.5*1*(u0[X] + u[0*ns + index0 + xs]);
-	  if (uf < 0.0) fe[index0] = adv3(uf, phi[index0 + 2*xs], phi[index0 + xs], phi[index0]);
-	  else          fe[index0] = adv3(uf, phi[index0 - xs], phi[index0], phi[index0 + xs]);
+	  uf = 0.5*1*(u0[X] + u[0*ns + index0 + xp1]);
+	  if (uf < 0.0) fe[index0] = adv3(uf, phi[index0 + xp2], phi[index0 + xp1], phi[index0]);
+	  else          fe[index0] = adv3(uf, phi[index0 + xm1], phi[index0], phi[index0 + xp1]);
 	  /* y */
 	  uf = 0.5*1*(u0[Y] + u[1*ns + index0 + ys]);
 	  if (uf < 0.0) fy[index0] = adv3(uf, phi[index0 + 2*ys], phi[index0 + ys], phi[index0]);
@@ -691,9 +709,9 @@ void orc_flux_mu(const orc_geom_t * g, const orc_symm_param_t * sp, const double
 	int index0 = orc_index(g, ic, jc, kc);
 	double mu0 = symm_mu(sp, phi[index0], delsq[index0]);
 	double mu1;
-	mu1 = symm_mu(sp, phi[index0 - xs], delsq[index0 - xs]);
+	mu1 = symm_mu(sp, phi[index0 + xoff(g, ic, -1, xs)], delsq[index0 + xoff(g, ic, -1, xs)]);   /* :369-370 */
 	flux[0*ns + index0] -= mobility*(mu0 - mu1);
-	mu1 = symm_mu(sp, phi[index0 + xs], delsq[index0 + xs]);
+	mu1 = symm_mu(sp, phi[index0 + xoff(g, ic, +1, xs)], delsq[index0 + xoff(g, ic, +1, xs)]);
 	flux[1*ns + index0] -= mobility*(mu1 - mu0);
 	mu1 = symm_mu(sp, phi[index0 + ys], delsq[index0 + ys]);
 	flux[2*ns + index0] -= mobility*(mu1 - mu0);

@@ -30,6 +30,9 @@ typedef struct orc_geom_s {
   int nlocal[3];
   int nhalo;
   int periodic[3];
+  int le_nplanes;        /* Lees-Edwards planes (0 = none): hydro / field arrays then carry
+			  * nxbuffer = 2*nhalo*le_nplanes extra x-planes after the high x halo
+			  * (lees_edw_nsites, src/leesedwards.c:485-495); lb->f never does (src/lb_data.c:102-115) */
 } orc_geom_t;
 
 typedef struct orc_model_s {
@@ -60,7 +63,8 @@ typedef struct orc_symm_param_s {
   int adv_order;         /* 1, 2, 3 */
 } orc_symm_param_t;
 
-int orc_nsites(const orc_geom_t * g);
+int orc_nsites(const orc_geom_t * g);          /* hydro, fields, gradients, fluxes: with the LE buffer planes */
+int orc_nsites_lb(const orc_geom_t * g);       /* distributions, map: cs_nsites */
 int orc_index(const orc_geom_t * g, int ic, int jc, int kc);
 
 int orc_model_create(int nvel, orc_model_t * model);
@@ -111,6 +115,45 @@ void orc_collide_binary(const orc_geom_t * g, const orc_model_t * m, const orc_c
 void orc_step_lb2(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
 		  const orc_symm_param_t * sp, int halo_reduced, int nsteps,
 		  double * f, double * phi, double * u, double * force, double * grad, double * delsq);
+
+/* ---- Lees-Edwards sliding periodic boundaries, oracle/lb_oracle_le.c -----------------
+ * Steady shear, single domain in y (as the x-slab decomposition of the product).  `t` arguments are the
+ * reference's physics_control_time() = t_start + t_current - 1 (src/physics.c:622-630) unless stated. */
+typedef struct orc_le_s {
+  double uy;             /* plane speed (lees_edw_options_t.uy) */
+  double time0;          /* reference time nt0 (src/leesedwards.c:262) */
+} orc_le_t;
+
+int orc_le_nxbuffer(const orc_geom_t * g);
+int orc_le_plane_location(const orc_geom_t * g, int np);
+int orc_le_ic_to_buff(const orc_geom_t * g, int ic, int di);
+int orc_le_ibuff_to_real(const orc_geom_t * g, int ib);
+double orc_le_buffer_displacement(const orc_geom_t * g, const orc_le_t * le, int ib, double t);
+/* field_leesedwards (src/field.c:418-510): buffer planes <- 4-point Lagrange interpolation; uses time t */
+void orc_le_field(const orc_geom_t * g, const orc_le_t * le, double t, int nf, double * data);
+/* hydro_lees_edwards (src/hydro.c:350-440): linear interpolation + velocity jump; the reference calls the
+ * displacement with t + 1 (src/hydro.c:401): pass t, the + 1 is applied inside.  nhcomm = z extent */
+void orc_le_hydro(const orc_geom_t * g, const orc_le_t * le, double t, int nhcomm, double * u);
+/* grad_3d_27pt_fluid_le (src/gradient_3d_27pt_fluid.c:375-651): gradients in the buffer region */
+void orc_le_grad_buffer(const orc_geom_t * g, int nextra, const double * field, double * grad, double * delsq);
+/* phi_force_flux (src/phi_force.c:289-345, 360-473, 595-673): flux form of the force with the per-plane fix */
+void orc_le_phi_force(const orc_geom_t * g, const orc_symm_param_t * sp, const double * phi,
+		      const double * grad, const double * delsq, double * force);
+/* phi_ch_le_fix_fluxes (src/phi_cahn_hilliard.c:613-745) */
+void orc_le_fix_fluxes(const orc_geom_t * g, const orc_le_t * le, double t, double * flux);
+/* lb_data_apply_le_boundary_conditions (src/model_le.c:78-180, 264-345, 358-400, 584-640); tstep = the integer
+ * time step physics_control_timestep() */
+void orc_le_lb_bc(const orc_geom_t * g, const orc_model_t * m, const orc_le_t * le, double tstep,
+		  int ndist, double * f);
+/* lb_le_init_shear_profile (src/model_le.c:652-714) */
+void orc_le_init_shear_profile(const orc_geom_t * g, const orc_model_t * m, const orc_le_t * le,
+			       double rho0, double eta, double * f);
+/* whole steps with planes (src/ludwig.c:528-860); tcurrent0 = physics t_current before the first step
+ * (t_start = 0); on return the caller's clock is tcurrent0 + nsteps */
+void orc_le_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+		 const orc_symm_param_t * sp, const orc_le_t * le, int tcurrent0, int nsteps,
+		 double * f, double * phi, double * u, double * rho, double * force,
+		 double * grad, double * delsq);
 
 #ifdef __cplusplus
 }

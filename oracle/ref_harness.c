@@ -47,6 +47,7 @@
 #include "fe_force_method.h"
 #include "noise.h"
 #include "phi_lb_coupler.h"
+#include "model_le.h"
 
 typedef struct ref_cfg_s {
   int ntotal[3];
@@ -67,6 +68,8 @@ typedef struct ref_cfg_s {
   double mobility;
   double gradmu[3];
   int grad_level;      /* 0/2: field_grad level 2; 4: also grad_delsq, delsq_delsq (grad_3d_27pt_fluid_d4) */
+  int le_nplanes;      /* N_LE_plane: number of Lees-Edwards planes (0 = none) */
+  double le_uy;        /* LE_plane_vel (steady shear) */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -84,7 +87,8 @@ typedef struct ref_sim_s {
   fe_symm_t * fe;
   pth_t * pth;
   phi_ch_t * pch;
-  int nsites;
+  int nsites;          /* cs_nsites: lb->f, map */
+  int nsites_le;       /* lees_edw_nsites: hydro, fields, gradients, fluxes (== nsites without planes) */
 } ref_sim_t;
 
 enum {REF_F = 0, REF_PHI = 1, REF_U = 2, REF_RHO = 3, REF_FORCE = 4,
@@ -126,7 +130,16 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     physics_grad_mu_set(s->phys, gm); }
 
   { lees_edw_options_t opts = {0};
-    lees_edw_create(s->pe, s->cs, &opts, &s->le); }
+    if (cfg->le_nplanes > 0) {
+      /* /root/reference/src/leesedwards_rt.c: N_LE_plane, LE_plane_vel, steady shear, nt0 = 0 */
+      opts.nplanes = cfg->le_nplanes;
+      opts.type = LE_SHEAR_TYPE_STEADY;
+      opts.uy = cfg->le_uy;
+      opts.nt0 = 0;
+      physics_control_init_time(s->phys, 0, 1000000);
+    }
+    lees_edw_create(s->pe, s->cs, &opts, &s->le);
+    lees_edw_nsites(s->le, &s->nsites_le); }
 
   { lb_data_options_t opts = lb_data_options_ndim_nvel_ndist(NDIM, NVEL, cfg->ndist);
     opts.nrelax = (lb_relaxation_enum_t) cfg->nrelax;
@@ -190,6 +203,7 @@ void ref_free(ref_sim_t * s) {
 }
 
 int ref_nsites(ref_sim_t * s) { return s->nsites; }
+int ref_nsites_le(ref_sim_t * s) { return s->nsites_le; }
 int ref_nvel(void) { return NVEL; }
 
 /* --- initial conditions through the reference's own routines --------------------------- */
@@ -216,7 +230,7 @@ int ref_init_spinodal(ref_sim_t * s, int seed, double phi0, double amp) {
 
 static int ref_copy(ref_sim_t * s, int what, double * buf, int put) {
 
-  const int ns = s->nsites;
+  const int ns = (what == REF_F || what == REF_MAP || what == REF_STR) ? s->nsites : s->nsites_le;
 
 #define XFER(hostexpr, k) do { if (put) (hostexpr) = buf[(k)]; else buf[(k)] = (hostexpr); } while (0)
 
@@ -308,10 +322,20 @@ int ref_phi_lb_to_field(ref_sim_t * s) { return phi_lb_to_field(s->phi, s->lb); 
 int ref_phi_lb_from_field(ref_sim_t * s) { return phi_lb_from_field(s->phi, s->lb); }
 int ref_propagation(ref_sim_t * s) { return lb_propagation(s->lb); }
 
+/* Lees-Edwards: the pieces of field_grad_compute / phi_cahn_hilliard / the LB boundary condition that the
+ * planes add (/root/reference/src/field.c:418-510, src/hydro.c:350-440, src/model_le.c:78-180) */
+int ref_le_field(ref_sim_t * s) { return field_leesedwards(s->phi); }
+int ref_le_hydro(ref_sim_t * s) { return hydro_lees_edwards(s->hydro); }
+int ref_le_lb_bc(ref_sim_t * s) { return lb_data_apply_le_boundary_conditions(s->lb, s->le); }
+int ref_le_init_shear_profile(ref_sim_t * s) { return lb_le_init_shear_profile(s->lb, s->le); }
+int ref_next_step(ref_sim_t * s) { return physics_control_next_step(s->phys); }
+int ref_timestep(ref_sim_t * s) { return physics_control_timestep(s->phys); }
+
 /* One full time step in the reference driver's order (/root/reference/src/ludwig.c:528-860) */
 
 int ref_step(ref_sim_t * s, int nsteps) {
   for (int n = 0; n < nsteps; n++) {
+    if (s->cfg.le_nplanes > 0) physics_control_next_step(s->phys);
     ref_hydro_f_zero(s);
     if (s->lb->ndist == 2) {
       /* symmetric_lb: /root/reference/src/ludwig.c:551-571, 683-685 */
@@ -327,6 +351,7 @@ int ref_step(ref_sim_t * s, int nsteps) {
     }
     ref_hydro_u_zero(s);
     ref_collide(s);
+    if (s->cfg.le_nplanes > 0) ref_le_lb_bc(s);       /* /root/reference/src/ludwig.c:817-819 */
     ref_lb_halo(s);
     ref_propagation(s);
   }

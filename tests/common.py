@@ -16,7 +16,7 @@ def seeded_state(orc, seed=7, binary=True, u_amp=0.01, phi_amp=0.05):
     ux = u_amp * np.sin(2 * np.pi * y)
     uy = u_amp * np.sin(2 * np.pi * z)
     uz = u_amp * np.sin(2 * np.pi * x)
-    f = np.zeros((orc.nvel, ns))
+    f = np.zeros((orc.nvel, orc.nsites_lb))      # distributions never carry the LE buffer planes
     fi = orc.interior(f)
     for p in range(orc.nvel):
         cu = orc.cv[p, 0] * ux + orc.cv[p, 1] * uy + orc.cv[p, 2] * uz

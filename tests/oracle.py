@@ -12,17 +12,22 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
 
 def build(force=False):
     src = os.path.join(ORACLE_DIR, "lb_oracle.c")
-    deps = [src, os.path.join(ORACLE_DIR, "lb_oracle.h"), os.path.join(ORACLE_DIR, "d3q19_tables.h")]
+    src_le = os.path.join(ORACLE_DIR, "lb_oracle_le.c")
+    deps = [src, src_le, os.path.join(ORACLE_DIR, "lb_oracle.h"), os.path.join(ORACLE_DIR, "d3q19_tables.h")]
     if (not force and os.path.exists(ORACLE_SO)
             and all(os.path.getmtime(ORACLE_SO) >= os.path.getmtime(d) for d in deps)):
         return ORACLE_SO
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-Wall",
-                           "-o", ORACLE_SO, src, "-lm"])
+                           "-o", ORACLE_SO, src, src_le, "-lm"])
     return ORACLE_SO
 
 
 class Geom(C.Structure):
-    _fields_ = [("nlocal", C.c_int * 3), ("nhalo", C.c_int), ("periodic", C.c_int * 3)]
+    _fields_ = [("nlocal", C.c_int * 3), ("nhalo", C.c_int), ("periodic", C.c_int * 3), ("le_nplanes", C.c_int)]
+
+
+class LeParam(C.Structure):
+    _fields_ = [("uy", C.c_double), ("time0", C.c_double)]
 
 
 class Model(C.Structure):
@@ -60,16 +65,23 @@ def _p(a):
 class Oracle:
     """Stateless operator set bound to one geometry + model."""
 
-    def __init__(self, nlocal, nhalo=1, periodic=(1, 1, 1), nvel=19):
+    def __init__(self, nlocal, nhalo=1, periodic=(1, 1, 1), nvel=19, le_nplanes=0, le_uy=0.0):
         self.lib = lib()
         self.g = Geom()
         self.g.nlocal[:] = nlocal
         self.g.nhalo = nhalo
         self.g.periodic[:] = periodic
+        self.g.le_nplanes = le_nplanes
         self.nlocal = tuple(nlocal)
         self.nhalo = nhalo
         self.nall = tuple(n + 2 * nhalo for n in nlocal)
-        self.nsites = int(np.prod(self.nall))
+        self.nsites_lb = int(np.prod(self.nall))              # distributions, map (cs_nsites)
+        # hydro / field arrays carry 2*nhalo buffer x-planes per Lees-Edwards plane (lees_edw_nsites)
+        self.le_nplanes = le_nplanes
+        self.nxbuffer = 2 * nhalo * le_nplanes
+        self.nsites = (self.nall[0] + self.nxbuffer) * self.nall[1] * self.nall[2]
+        self.le = LeParam(le_uy, 0.0)
+        self.lib.orc_le_buffer_displacement.restype = C.c_double
         self.m = Model()
         rc = self.lib.orc_model_create(nvel, C.byref(self.m))
         assert rc == 0
@@ -81,14 +93,20 @@ class Oracle:
     def interior(self, a):
         """View of the interior of a (ncomp, nsites) canonical array as (ncomp, Nx, Ny, Nz)."""
         h = self.nhalo
-        v = a.reshape((-1,) + self.nall)
+        v = a.reshape((a.shape[0], -1) + self.nall[1:])       # x extent: nall[0] (+ LE buffer planes)
         return v[:, h:h + self.nlocal[0], h:h + self.nlocal[1], h:h + self.nlocal[2]]
 
     def region(self, a, extra):
         """View of [1-extra, N+extra]^3."""
         h = self.nhalo - extra
-        v = a.reshape((-1,) + self.nall)
+        v = a.reshape((a.shape[0], -1) + self.nall[1:])
         return v[:, h:self.nall[0] - h, h:self.nall[1] - h, h:self.nall[2] - h]
+
+    def buffer(self, a, extra=0):
+        """View of the Lees-Edwards buffer planes of a field array, y/z in [1-extra, N+extra]."""
+        h = self.nhalo - extra
+        v = a.reshape((a.shape[0], -1) + self.nall[1:])
+        return v[:, self.nall[0]:, h:self.nall[1] - h, h:self.nall[2] - h]
 
     def collide_param(self, nrelax=0, rho0=1.0, eta_shear=1.0 / 6.0, eta_bulk=None, force=(0, 0, 0)):
         cp = CollideParam()
@@ -105,7 +123,7 @@ class Oracle:
 
     def equilibrium(self, rho, u):
         """f_p = rho w_p (1 + 3 u.c + 4.5 (cc - 1/3 I):uu), reference src/lb_data.c:809-834 (same op order)."""
-        f = np.zeros((self.nvel, self.nsites))
+        f = np.zeros((self.nvel, self.nsites_lb))
         cs2 = 1.0 / 3.0
         rcs2 = 1.0 / cs2
         for p in range(self.nvel):
@@ -162,6 +180,39 @@ class Oracle:
 
     def phi_update(self, flux, phi):
         self.lib.orc_phi_update(C.byref(self.g), _p(flux), _p(phi))
+
+    # ---- Lees-Edwards (oracle/lb_oracle_le.c) ---------------------------------------------------
+    def le_plane_location(self, p):
+        return self.lib.orc_le_plane_location(C.byref(self.g), p)
+
+    def le_ic_to_buff(self, ic, di):
+        return self.lib.orc_le_ic_to_buff(C.byref(self.g), ic, di)
+
+    def le_field(self, t, a):
+        self.lib.orc_le_field(C.byref(self.g), C.byref(self.le), C.c_double(t), a.shape[0], _p(a))
+
+    def le_hydro(self, t, u, nhcomm=1):
+        self.lib.orc_le_hydro(C.byref(self.g), C.byref(self.le), C.c_double(t), nhcomm, _p(u))
+
+    def le_grad_buffer(self, phi, grad, delsq):
+        self.lib.orc_le_grad_buffer(C.byref(self.g), self.nhalo - 1, _p(phi), _p(grad), _p(delsq))
+
+    def le_phi_force(self, sp, phi, grad, delsq, force):
+        self.lib.orc_le_phi_force(C.byref(self.g), C.byref(sp), _p(phi), _p(grad), _p(delsq), _p(force))
+
+    def le_fix_fluxes(self, t, flux):
+        self.lib.orc_le_fix_fluxes(C.byref(self.g), C.byref(self.le), C.c_double(t), _p(flux))
+
+    def le_lb_bc(self, tstep, f, ndist=1):
+        self.lib.orc_le_lb_bc(C.byref(self.g), C.byref(self.m), C.byref(self.le), C.c_double(tstep), ndist, _p(f))
+
+    def le_init_shear_profile(self, rho0, eta, f):
+        self.lib.orc_le_init_shear_profile(C.byref(self.g), C.byref(self.m), C.byref(self.le), C.c_double(rho0),
+                                           C.c_double(eta), _p(f))
+
+    def le_step(self, cp, sp, tcurrent0, nsteps, f, phi, u, rho, force, grad, delsq):
+        self.lib.orc_le_step(C.byref(self.g), C.byref(self.m), C.byref(cp), C.byref(sp), C.byref(self.le),
+                             tcurrent0, nsteps, _p(f), _p(phi), _p(u), _p(rho), _p(force), _p(grad), _p(delsq))
 
     # ---- symmetric_lb (two distributions: f is (2*nvel, nsites)) ------------------------------
     def phi_lb_to_field(self, f, phi):

@@ -22,7 +22,7 @@ class RefCfg(C.Structure):
                 ("rho0", C.c_double), ("eta_shear", C.c_double), ("eta_bulk", C.c_double),
                 ("fbody", C.c_double * 3), ("a", C.c_double), ("b", C.c_double),
                 ("kappa", C.c_double), ("mobility", C.c_double), ("gradmu", C.c_double * 3),
-                ("grad_level", C.c_int)]
+                ("grad_level", C.c_int), ("le_nplanes", C.c_int), ("le_uy", C.c_double)]
 
 
 def _so(fast=False, nvel=19):
@@ -49,7 +49,8 @@ def _lib(fast=False, nvel=19):
         for name in ("ref_free", "ref_nsites", "ref_hydro_f_zero", "ref_hydro_u_zero", "ref_hydro_u_halo",
                      "ref_phi_halo", "ref_grad_compute", "ref_phi_force", "ref_cahn_hilliard",
                      "ref_collide", "ref_lb_halo", "ref_propagation", "ref_phi_lb_to_field", "ref_phi_lb_from_field", "ref_grad_d4", "ref_pth_stress_compute",
-                     "ref_pth_force_fluid_driver"):
+                     "ref_pth_force_fluid_driver", "ref_nsites_le", "ref_le_field", "ref_le_hydro", "ref_le_lb_bc",
+                     "ref_le_init_shear_profile", "ref_next_step", "ref_timestep"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.ref_step.argtypes = [C.c_void_p, C.c_int]
         lib.ref_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -69,7 +70,7 @@ class RefSim:
     def __init__(self, ntotal, nhalo=1, periodic=(1, 1, 1), ndist=1, nrelax=0, ghost_off=0,
                  halo_reduced=0, have_phi=0, adv_order=1, conserve=0, rho0=1.0, eta_shear=1.0 / 6.0,
                  eta_bulk=None, fbody=(0, 0, 0), a=0.0, b=0.0, kappa=0.0, mobility=0.0,
-                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2):
+                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2, le_nplanes=0, le_uy=0.0):
         self.lib = _lib(fast, nvel)
         cfg = RefCfg()
         cfg.ntotal[:] = ntotal
@@ -83,9 +84,11 @@ class RefSim:
         cfg.a, cfg.b, cfg.kappa, cfg.mobility = a, b, kappa, mobility
         cfg.gradmu[:] = gradmu
         cfg.grad_level = grad_level
+        cfg.le_nplanes, cfg.le_uy = le_nplanes, le_uy
         self.cfg = cfg
         self.h = self.lib.ref_create(C.byref(cfg))
         self.nsites = self.lib.ref_nsites(self.h)
+        self.nsites_le = self.lib.ref_nsites_le(self.h)      # hydro / field arrays carry the LE buffer planes
         self.ndist = ndist
         self.nvel = nvel
 
@@ -102,7 +105,8 @@ class RefSim:
 
     def get(self, what):
         n = self.ndist * self.nvel if what == REF_F else NCOMP[what]
-        out = np.empty((n, self.nsites), dtype=np.float64)
+        ns = self.nsites if what in (REF_F, REF_MAP, REF_STR) else self.nsites_le
+        out = np.empty((n, ns), dtype=np.float64)
         rc = self.lib.ref_get(self.h, what, out.ctypes.data)
         assert rc == 0
         return out

@@ -1,0 +1,168 @@
+"""Lees-Edwards planes: the CPU restatement oracle/lb_oracle_le.c pinned bit-for-bit to the
+UNMODIFIED reference compiled from /root/reference (oracle/_ref), operator by operator and over whole time
+steps, and to the printed statistics of the reference's own regression logs serial-le3d-st5/6/7.log."""
+import numpy as np
+import pytest
+
+import refharness as R
+from oracle import Oracle, stats_scalar, fed_density
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="reference library oracle/_ref not built")
+
+FE = dict(a=-0.0625, b=0.0625, kappa=0.04, mobility=0.15)     # serial-le3d-st*.inp
+ETA = 0.1
+UY = 0.05
+
+
+def make(n, nplanes, order, uy=UY):
+    ref = R.RefSim(n, nhalo=2, have_phi=1, adv_order=order, eta_shear=ETA, le_nplanes=nplanes, le_uy=uy, **FE)
+    orc = Oracle(n, nhalo=2, le_nplanes=nplanes, le_uy=uy)
+    assert ref.nsites == orc.nsites_lb and ref.nsites_le == orc.nsites
+    return ref, orc
+
+
+def test_le_geometry():
+    """plane locations and the x -> buffer map against the reference's formulae at the regression size"""
+    orc = Oracle((32, 8, 8), nhalo=2, le_nplanes=2)
+    assert [orc.le_plane_location(p) for p in range(2)] == [8, 24]
+    # crossing plane 0 (between x = 8 and 9): buffer planes start at x = N + nhalo + 1 = 35
+    assert orc.le_ic_to_buff(8, +1) == 37 and orc.le_ic_to_buff(8, +2) == 38 and orc.le_ic_to_buff(7, +2) == 37
+    assert orc.le_ic_to_buff(9, -1) == 36 and orc.le_ic_to_buff(9, -2) == 35 and orc.le_ic_to_buff(10, -2) == 36
+    assert orc.le_ic_to_buff(7, +1) == 8 and orc.le_ic_to_buff(10, -1) == 9 and orc.le_ic_to_buff(8, -1) == 7
+
+
+@pytest.mark.parametrize("n,nplanes", [((16, 8, 6), 1), ((16, 12, 8), 2), ((24, 7, 5), 2)])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_le_operators_vs_reference(n, nplanes, order):
+    """every Lees-Edwards operator, same inputs, bit for bit, at a time with a fractional displacement"""
+    ref, orc = make(n, nplanes, order)
+    with ref:
+        rng = np.random.default_rng(5)
+        ref.init_spinodal(13, 0.0, 0.05)
+        ref.op("le_init_shear_profile")
+        f = ref.get(R.REF_F)
+        f0 = np.zeros_like(f)
+        orc.le_init_shear_profile(1.0, ETA, f0)
+        assert np.array_equal(orc.interior(f0), orc.interior(f))
+        # a non-equilibrium perturbation so that every moment is exercised
+        orc.interior(f)[...] *= 1.0 + 1e-3 * (rng.random(orc.interior(f).shape) - 0.5)
+        ref.set(R.REF_F, f)
+        u = np.zeros((3, orc.nsites))
+        orc.interior(u)[...] = 0.02 * (rng.random((3,) + tuple(n)) - 0.5)
+        ref.set(R.REF_U, u)
+        for _ in range(7):
+            ref.op("next_step")                       # t_current = 7: time = 6, displacement 0.3 / 0.35
+        tstep = float(ref.op("timestep"))
+        time = tstep - 1.0
+        sp = orc.symm_param(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order)
+
+        # field_halo + field_grad_compute (field_leesedwards + d2 + buffer-region gradients)
+        phi = ref.get(R.REF_PHI)
+        ref.op("phi_halo"); ref.op("grad_compute")
+        grad = np.zeros((3, orc.nsites)); delsq = np.zeros((1, orc.nsites))
+        orc.field_halo(phi); orc.le_field(time, phi); orc.grad_27pt(phi, grad, delsq); orc.le_grad_buffer(phi, grad, delsq)
+        assert np.array_equal(phi, ref.get(R.REF_PHI))
+        rg, rd = ref.get(R.REF_GRAD), ref.get(R.REF_DELSQ)
+        assert np.array_equal(orc.region(grad, 1), orc.region(rg, 1)) and np.array_equal(orc.region(delsq, 1), orc.region(rd, 1))
+        # buffer planes the stencils read: one either side of each plane (nextra = 1), y/z in [0, N+1]
+        for p in range(nplanes):
+            for x in (orc.le_ic_to_buff(orc.le_plane_location(p), 1), orc.le_ic_to_buff(orc.le_plane_location(p) + 1, -1)):
+                xb = x - 1 + 2            # array plane index of x coordinate
+                sl = lambda a: a.reshape((a.shape[0], -1) + orc.nall[1:])[:, xb, 1:-1, 1:-1]
+                assert np.array_equal(sl(grad), sl(rg)) and np.array_equal(sl(delsq), sl(rd))
+
+        # phi_force_calculation (flux form with the per-plane correction)
+        ref.op("hydro_f_zero"); ref.op("phi_force")
+        force = np.zeros((3, orc.nsites))
+        orc.le_phi_force(sp, phi, rg, rd, force)
+        assert np.array_equal(orc.interior(force), orc.interior(ref.get(R.REF_FORCE)))
+
+        # phi_cahn_hilliard: u halo, hydro_lees_edwards, fluxes, fix, update
+        ref.op("cahn_hilliard")
+        orc.field_halo(u); orc.le_hydro(time, u)
+        ru = ref.get(R.REF_U)
+        sel = lambda a: a.reshape((3, -1) + orc.nall[1:])[:, :, :, 1:-1]           # nhcomm = 1 in z
+        assert np.array_equal(sel(u), sel(ru))
+        flux = np.zeros((4, orc.nsites))
+        orc.advection(order, u, phi, flux); orc.flux_mu(sp, phi, rd, flux); orc.flux_mu_ext(sp, flux)
+        orc.le_fix_fluxes(time, flux)
+        rflux = ref.get(R.REF_FLUX)
+        assert np.array_equal(orc.interior(flux), orc.interior(rflux))
+        orc.phi_update(flux, phi)
+        assert np.array_equal(orc.interior(phi), orc.interior(ref.get(R.REF_PHI)))
+
+        # lb_data_apply_le_boundary_conditions
+        ref.op("le_lb_bc")
+        orc.le_lb_bc(tstep, f)
+        assert np.array_equal(orc.interior(f), orc.interior(ref.get(R.REF_F)))
+
+
+@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 8, 8), 1, 3), ((24, 8, 6), 2, 2)])
+def test_le_steps_vs_reference(n, nplanes, order):
+    ref, orc = make(n, nplanes, order)
+    with ref:
+        ref.init_spinodal(13, 0.0, 0.05)
+        ref.op("le_init_shear_profile")
+        f = ref.get(R.REF_F); phi = ref.get(R.REF_PHI)
+        z = lambda k: np.zeros((k, orc.nsites))
+        u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+        nsteps = 12
+        ref.step(nsteps)
+        cp = orc.collide_param(0, 1.0, ETA)
+        sp = orc.symm_param(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order)
+        orc.le_step(cp, sp, 0, nsteps, f, phi, u, rho, force, grad, delsq)
+        for name, a, what in (("f", f, R.REF_F), ("phi", phi, R.REF_PHI), ("u", u, R.REF_U), ("rho", rho, R.REF_RHO),
+                              ("force", force, R.REF_FORCE), ("grad", grad, R.REF_GRAD), ("delsq", delsq, R.REF_DELSQ)):
+            assert np.array_equal(orc.interior(a), orc.interior(ref.get(what))), name
+
+
+# ---- printed statistics of the reference's own regression logs after 10 steps ---------------------------------
+# tests/regression/d3q19-short/serial-le3d-st5/6/7.{inp,log}: 32^3, 2 planes, LE_plane_vel 0.05, LE_init_profile 1,
+# viscosity 0.1, A = -B = -0.0625, K = 0.04, mobility 0.15, 27pt gradient, advection order 1/2/3, seed 7361237
+
+LOGS = {
+    1: dict(var=2.7954511e-04, lo=-4.3686720e-02, hi=4.4289983e-02, fed=-6.9311730666e-06,
+            rlo=0.99989690503, rhi=1.00007666257, momy=6.3814249e-04,
+            umin=(-3.9221844e-05, -2.3463878e-02, -3.2254803e-05), umax=(3.4178658e-05, 2.3465547e-02, 3.5110536e-05)),
+    2: dict(var=3.3067606e-04, lo=-4.4644770e-02, hi=4.9068268e-02, fed=-8.3656830360e-06,
+            rlo=0.99990337027, rhi=1.00008437211, momy=8.0471915e-04,
+            umin=(-4.6114452e-05, -2.3467741e-02, -3.3157493e-05), umax=(3.9185154e-05, 2.3468327e-02, 3.6566756e-05)),
+    3: dict(var=3.0000123e-04, lo=-4.4451160e-02, hi=4.6772004e-02, fed=-7.4768699749e-06,
+            rlo=0.99989939996, rhi=1.00007990713, momy=6.7440881e-04,
+            umin=(-3.9757187e-05, -2.3465114e-02, -3.2556760e-05), umax=(3.5246929e-05, 2.3466305e-02, 3.5961973e-05)),
+}
+
+
+def approx(v, digits):
+    return pytest.approx(v, rel=0.5 * 10.0 ** (1 - digits), abs=1e-30)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_serial_le3d_logs(order):
+    from ludwig_b200.initial import spinodal_phi
+    n = (32, 32, 32)
+    orc = Oracle(n, nhalo=2, le_nplanes=2, le_uy=UY)
+    phi = np.zeros((1, orc.nsites))
+    phi[:, :orc.nsites_lb] = spinodal_phi(n, 2, 7361237, 0.0, 0.1)
+    f = np.zeros((19, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f)
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+    cp = orc.collide_param(0, 1.0, ETA)
+    sp = orc.symm_param(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order)
+    s0 = stats_scalar(orc, phi)
+    assert s0[0] == approx(-1.5507344e+00, 8)
+    orc.le_step(cp, sp, 0, 10, f, phi, u, rho, force, grad, delsq)
+    L = LOGS[order]
+    s = stats_scalar(orc, phi)
+    assert s[0] == approx(-1.5507344e+00, 7) and s[2] == approx(L["var"], 8)
+    assert s[3] == approx(L["lo"], 8) and s[4] == approx(L["hi"], 8)
+    assert fed_density(orc, sp, phi, grad) == approx(L["fed"], 11)
+    r = stats_scalar(orc, f.sum(axis=0, keepdims=True))
+    assert r[0] == approx(32768.00, 8) and r[3] == approx(L["rlo"], 11) and r[4] == approx(L["rhi"], 11)
+    fi = orc.interior(f)
+    momy = float((fi * orc.cv[:, 1, None, None, None]).sum())
+    assert momy == approx(L["momy"], 7)
+    ui = orc.interior(u)
+    for a in range(3):
+        assert ui[a].min() == approx(L["umin"][a], 8) and ui[a].max() == approx(L["umax"][a], 8)
