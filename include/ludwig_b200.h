@@ -81,6 +81,15 @@ typedef struct lb200_options_s {
   /* x-slab domain decomposition across the GPUs of one box (cs "grid Px_1_1", src/coords.c:151-201) */
   int cart_size;            /* number of slabs (1 = single GPU) */
   int cart_rank;            /* this slab */
+  /* Lees-Edwards sliding periodic planes, lees_edw_options_t (src/lees_edwards_options.h:31-38): steady shear.
+   * N_LE_plane planes in the GLOBAL system, equally spaced in x at (p + 1/2) Lx / nplanes (src/leesedwards.c:
+   * 245-257, 615-634); must divide evenly over the slabs and lie further than nhalo from a slab boundary
+   * (lees_edw_checks, :433-470).  With planes, every array except LB200_F and LB200_MAP carries
+   * 2*nhalo*(planes in this slab) buffer x-planes after the high x halo, as the reference's
+   * (lees_edw_nsites, :485-495): lb200_nsites() counts them, lb200_nsites_lb() does not. */
+  int le_nplanes;           /* 0 = none */
+  double le_uy;             /* LE_plane_vel */
+  int le_nt0;               /* reference time step (lees_edw_options_t.nt0, usually 0) */
 } lb200_options_t;
 
 /* lb_collide_param_t / collide_param_t as seen by the collision: src/lb_data.h:59-76,
@@ -111,7 +120,8 @@ int lb200_create(const lb200_options_t * options, lb200_t ** ctx);
 /* lb_free / hydro_free / field_free: src/lb_data.c:251-296 */
 int lb200_free(lb200_t * ctx);
 
-int lb200_nsites(const lb200_t * ctx);
+int lb200_nsites(const lb200_t * ctx);        /* hydro / field arrays (with the Lees-Edwards buffer planes, if any) */
+int lb200_nsites_lb(const lb200_t * ctx);     /* LB200_F, LB200_MAP: cs_nsites */
 /* device pointer of an array in its current (device) layout; for zero-copy interop */
 int lb200_device_ptr(lb200_t * ctx, int array, void ** ptr);
 
@@ -154,6 +164,28 @@ int lb200_lb_collision_binary(lb200_t * ctx, const lb200_collide_param_t * cp, c
 int lb200_phi_lb_to_field(lb200_t * ctx);
 int lb200_phi_lb_from_field(lb200_t * ctx);
 
+/* ---- Lees-Edwards planes (options.le_nplanes > 0) ----------------------------------------------------------
+ * The plane displacement is uy * time; like the reference (physics_control_next_step / _timestep / _time,
+ * src/physics.c:600-647) the context keeps t_start and the step counter t_current: lb200_step advances
+ * t_current by one at the start of every step; a host driving the individual entry points sets it.
+ * With planes present
+ *   lb200_phi_grad_compute       = field_leesedwards + d2 + grad_3d_27pt_fluid_le   (src/field_grad.c:319-340)
+ *   lb200_phi_force_calculation  = phi_force_flux: flux form + per-plane correction  (src/phi_force.c:91-97, 289-673)
+ *   lb200_phi_cahn_hilliard      = ... hydro_lees_edwards ... phi_ch_le_fix_fluxes    (src/phi_cahn_hilliard.c:213-288)
+ *   lb200_step                   = the reference step with lb_data_apply_le_boundary_conditions after the collision
+ * all on the device (the reference's GPU build runs them on the host with whole-array copies). */
+int lb200_physics_control_time_set(lb200_t * ctx, int t_start, int t_current);
+int lb200_physics_control_timestep(const lb200_t * ctx);
+/* field_leesedwards(phi): src/field.c:418-510;  hydro_lees_edwards: src/hydro.c:350-440 */
+int lb200_field_leesedwards(lb200_t * ctx);
+int lb200_hydro_lees_edwards(lb200_t * ctx);
+/* lb_data_apply_le_boundary_conditions: src/model_le.c:78-180 */
+int lb200_lb_le_apply_boundary_conditions(lb200_t * ctx);
+/* lees_edw_plane_location (local x of plane np of this slab) and lees_edw_ic_to_buff: src/leesedwards.c:615-634,
+ * 1030-1065; pure host arithmetic on the options */
+int lb200_le_plane_location(const lb200_options_t * options, int np);
+int lb200_le_ic_to_buff(const lb200_options_t * options, int ic, int di);
+
 /* lb_halo: src/lb_data.c:754-762, 1124-1477 */
 int lb200_lb_halo(lb200_t * ctx);
 /* lb_propagation: src/propagation.c:43-95, 153-240 */
@@ -195,7 +227,8 @@ enum lb200_kernel_class {
   LB200_K_GRAD = 3,         /* 27-point gradient */
   LB200_K_FORCE_CH = 4,     /* stress-divergence force and/or Cahn-Hilliard update */
   LB200_K_PHI_SECTOR = 5,   /* gradient + force + Cahn-Hilliard in one sweep (lb200_step, all-fluid) */
-  LB200_KCLASS_MAX = 6
+  LB200_K_LE = 6,           /* Lees-Edwards: buffer interpolation, plane patches, plane-crossing populations */
+  LB200_KCLASS_MAX = 7
 };
 int lb200_profile(lb200_t * ctx, int on);      /* clears accumulated timings */
 int lb200_profile_get(lb200_t * ctx, int kernel_class, double * total_ms, int * count);
@@ -208,7 +241,7 @@ int lb200_profile_get(lb200_t * ctx, int kernel_class, double * total_ms, int * 
 typedef struct lb200_slab_plan_s {
   int left, right;          /* neighbour ranks (periodic wrap) */
   int has_lo, has_hi;       /* 0 at a non-periodic global boundary: nothing is exchanged there */
-  long long nsites;         /* component stride in the lattice array */
+  long long nsites;         /* component stride in the lattice array (with the Lees-Edwards buffer planes) */
   long long chunk;          /* depth * nall[Y] * nall[Z]: one component's boundary planes, contiguous */
   long long off_lo;         /* first element of my planes i in [1, depth]        (sent to `left`) */
   long long off_hi;         /* first element of my planes i in [N-depth+1, N]    (sent to `right`) */

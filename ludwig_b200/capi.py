@@ -21,7 +21,8 @@ class Options(C.Structure):
     _fields_ = [("nlocal", C.c_int * 3), ("nhalo", C.c_int), ("periodic", C.c_int * 3),
                 ("nvel", C.c_int), ("ndist", C.c_int), ("have_phi", C.c_int),
                 ("halo_scheme", C.c_int), ("math", C.c_int), ("device", C.c_int),
-                ("cart_size", C.c_int), ("cart_rank", C.c_int)]
+                ("cart_size", C.c_int), ("cart_rank", C.c_int),
+                ("le_nplanes", C.c_int), ("le_uy", C.c_double), ("le_nt0", C.c_int)]
 
 
 class CollideParam(C.Structure):
@@ -119,13 +120,19 @@ def load_library():
     lib.lb200_create.argtypes = [C.POINTER(Options), C.POINTER(C.c_void_p)]
     lib.lb200_free.argtypes = [C.c_void_p]
     lib.lb200_nsites.argtypes = [C.c_void_p]
+    lib.lb200_nsites_lb.argtypes = [C.c_void_p]
+    lib.lb200_physics_control_time_set.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.lb200_physics_control_timestep.argtypes = [C.c_void_p]
+    lib.lb200_le_plane_location.argtypes = [C.POINTER(Options), C.c_int]
+    lib.lb200_le_ic_to_buff.argtypes = [C.POINTER(Options), C.c_int, C.c_int]
     lib.lb200_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.lb200_memcpy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.lb200_memcpy_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.lb200_pth_stress_compute.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
     for name in ("lb200_sync", "lb200_hydro_f_zero", "lb200_hydro_u_zero", "lb200_hydro_u_halo",
                  "lb200_phi_halo", "lb200_phi_grad_compute", "lb200_lb_halo", "lb200_lb_propagation",
-                 "lb200_phi_grad_compute_d4", "lb200_pth_force_fluid_driver"):
+                 "lb200_phi_grad_compute_d4", "lb200_pth_force_fluid_driver", "lb200_field_leesedwards",
+                 "lb200_hydro_lees_edwards", "lb200_lb_le_apply_boundary_conditions"):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.lb200_phi_force_calculation.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
     lib.lb200_phi_cahn_hilliard.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
@@ -156,7 +163,8 @@ class Lb200:
     """One device-resident lattice (the lb_t / hydro_t / field_t / field_grad_t / map_t device sides)."""
 
     def __init__(self, nlocal, nhalo=1, periodic=(1, 1, 1), nvel=19, ndist=1, have_phi=False,
-                 halo_scheme=HALO_FULL, math=MATH_FAST, device=-1, cart_size=1, cart_rank=0):
+                 halo_scheme=HALO_FULL, math=MATH_FAST, device=-1, cart_size=1, cart_rank=0,
+                 le_nplanes=0, le_uy=0.0, le_nt0=0):
         self.lib = load_library()
         o = Options()
         o.nlocal[:] = nlocal
@@ -165,13 +173,15 @@ class Lb200:
         o.nvel, o.ndist, o.have_phi = nvel, ndist, int(bool(have_phi))
         o.halo_scheme, o.math, o.device = halo_scheme, math, device
         o.cart_size, o.cart_rank = cart_size, cart_rank
+        o.le_nplanes, o.le_uy, o.le_nt0 = le_nplanes, le_uy, le_nt0
         self.options = o
         self.h = C.c_void_p()
         self._check(self.lib.lb200_create(C.byref(o), C.byref(self.h)))
         self.nlocal = tuple(nlocal)
         self.nhalo = nhalo
         self.nall = tuple(n + 2 * nhalo for n in nlocal)
-        self.nsites = self.lib.lb200_nsites(self.h)
+        self.nsites = self.lib.lb200_nsites(self.h)          # hydro / field arrays (with Lees-Edwards buffer planes)
+        self.nsites_lb = self.lib.lb200_nsites_lb(self.h)    # F, MAP
         self.nvel, self.ndist = nvel, ndist
         self._nccl = None
 
@@ -203,13 +213,17 @@ class Lb200:
     def ncomp(self, array):
         return self.nvel * self.ndist if array == F else _NCOMP[array]
 
+    def host_nsites(self, array):
+        return self.nsites_lb if array in (F, MAP) else self.nsites
+
     def put(self, array, host):
         host = np.ascontiguousarray(host, dtype=np.float64)
-        assert host.size == self.ncomp(array) * self.nsites, (host.shape, self.ncomp(array), self.nsites)
+        ns = self.host_nsites(array)
+        assert host.size == self.ncomp(array) * ns, (host.shape, self.ncomp(array), ns)
         self._check(self.lib.lb200_memcpy(self.h, array, host.ctypes.data, H2D))
 
     def get(self, array):
-        out = np.empty((self.ncomp(array), self.nsites), dtype=np.float64)
+        out = np.empty((self.ncomp(array), self.host_nsites(array)), dtype=np.float64)
         self._check(self.lib.lb200_memcpy(self.h, array, out.ctypes.data, D2H))
         return out
 
@@ -223,7 +237,7 @@ class Lb200:
 
     def interior(self, a):
         h = self.nhalo
-        v = a.reshape((-1,) + self.nall)
+        v = a.reshape((a.shape[0], -1) + self.nall[1:])        # x extent: nall[0] (+ Lees-Edwards buffer planes)
         return v[:, h:h + self.nlocal[0], h:h + self.nlocal[1], h:h + self.nlocal[2]]
 
     # ---- operators (names follow the reference entry points) ------------------------------------
@@ -244,6 +258,22 @@ class Lb200:
 
     def phi_grad_compute(self):
         self._check(self.lib.lb200_phi_grad_compute(self.h))
+
+    # Lees-Edwards planes
+    def physics_control_time_set(self, t_start, t_current):
+        self._check(self.lib.lb200_physics_control_time_set(self.h, t_start, t_current))
+
+    def physics_control_timestep(self):
+        return self.lib.lb200_physics_control_timestep(self.h)
+
+    def field_leesedwards(self):
+        self._check(self.lib.lb200_field_leesedwards(self.h))
+
+    def hydro_lees_edwards(self):
+        self._check(self.lib.lb200_hydro_lees_edwards(self.h))
+
+    def lb_le_apply_boundary_conditions(self):
+        self._check(self.lib.lb200_lb_le_apply_boundary_conditions(self.h))
 
     def phi_grad_compute_d4(self):
         self._check(self.lib.lb200_phi_grad_compute_d4(self.h))

@@ -114,6 +114,20 @@ struct lb200_s {
   int phi_src, u_src, f_src; // how the boundary data the next consumer needs arrives: SRC_*
   void * wait_value32;       // cuStreamWaitValue32, if the driver has it
 
+  // Lees-Edwards planes (options.le_nplanes > 0)
+  Lb200LeDev le;             // planes of this slab
+  int nxbuf;                 // buffer x-planes appended to every hydro / field array
+  int nsites_lb;             // nall[0]*nall[1]*nall[2]: host stride of LB200_F / LB200_MAP
+  int t_start, t_current;    // physics_control_* (src/physics.c:600-647)
+  int * le_trip;             // device: (x-1, x, x+1) plane triples of the gradient patch
+  int le_ntrip;
+  int * le_xlist;            // device: the x-planes within nhalo of a plane (force / Cahn-Hilliard patch)
+  int le_nxlist;
+  double * le_term;          // 3*nplane*Ny*Nz: summands of the per-plane force flux correction
+  double * le_fcor;          // 3*nplane
+  double * le_chx;           // 2*nplane*Ny*Nz: raw Cahn-Hilliard x-face fluxes either side of the planes
+  double * le_sbuf;          // 2*nplane*ndist*nprop*Ny*Nz: re-projected plane-crossing populations
+
   // optional per-kernel-class timing with CUDA events on the launching stream
   int profile;
   std::vector<cudaEvent_t> * ev[LB200_KCLASS_MAX];   // pairs (start, stop)
@@ -301,6 +315,175 @@ static int alloc_d(double ** p, size_t n) {
   return 0;
 }
 
+// ---- Lees-Edwards planes: host-side geometry (reference src/leesedwards.c) ---------------------------------
+
+static int le_nplane_local(const lb200_options_t * o) {
+  return (o->le_nplanes > 0 && o->cart_size > 0) ? o->le_nplanes/o->cart_size : 0;
+}
+
+// lees_edw_plane_location, src/leesedwards.c:615-634: dx_sep = ntotal[X]/nplanetotal, dx_min = dx_sep/2 (:256-257)
+int lb200_le_plane_location(const lb200_options_t * o, int np) {
+  if (o == nullptr || o->le_nplanes <= 0) return fail(LB200_EINVAL, "no Lees-Edwards planes");
+  const int npl = le_nplane_local(o);
+  if (np < 0 || np >= npl) return fail(LB200_EINVAL, "plane %d of %d", np, npl);
+  const double dx_sep = 1.0*(o->nlocal[0]*o->cart_size)/o->le_nplanes;
+  const double dx_min = 0.5*dx_sep;
+  const int offset = o->cart_rank*o->nlocal[0];
+  const int nplane_offset = o->cart_rank*npl;
+  int ix = dx_min + (np + nplane_offset)*dx_sep - offset;
+  return ix;
+}
+
+// lees_edw_ic_to_buff, src/leesedwards.c:1030-1065
+int lb200_le_ic_to_buff(const lb200_options_t * o, int ic, int di) {
+  if (o == nullptr) return fail(LB200_EINVAL, "null argument");
+  const int npl = le_nplane_local(o);
+  if (npl > 0) {
+    const int nh = o->nhalo;
+    int p = ic/(o->nlocal[0]/npl);
+    p = p < 0 ? 0 : (p > npl - 1 ? npl - 1 : p);
+    int ip = lb200_le_plane_location(o, p) - (nh - 1);
+    if (di > 0 && (ic >= ip && ic < ip + nh) && (ic + di >= ip + nh)) return o->nlocal[0] + (1 + 2*p)*nh + (ic - ip + 1) + di;
+    ip = lb200_le_plane_location(o, p) + 1;
+    if (di < 0 && (ic >= ip && ic < ip + nh) && (ic + di < ip)) return o->nlocal[0] + (2 + 2*p)*nh + (ic - ip + 1) + di;
+  }
+  return ic + di;
+}
+
+// lees_edw_init / lees_edw_init_tables / lees_edw_checks: src/leesedwards.c:233-279, 384-470
+static int le_setup(lb200_t * c) {
+  const lb200_options_t * o = &c->opt;
+  memset(&c->le, 0, sizeof(c->le));
+  c->nxbuf = 0;
+  if (o->le_nplanes < 0) return fail(LB200_EINVAL, "le_nplanes = %d", o->le_nplanes);
+  if (o->le_nplanes == 0) return 0;
+  const int ntotal_x = o->nlocal[0]*o->cart_size;
+  if (ntotal_x % o->le_nplanes) return fail(LB200_EINVAL, "Number of planes must divide system size (src/leesedwards.c:249-253)");
+  if (o->le_nplanes % o->cart_size) return fail(LB200_EINVAL, "Must have a uniform number of planes per process (src/leesedwards.c:463-468)");
+  const int npl = o->le_nplanes/o->cart_size;
+  if (npl > LB200_LE_MAXPLANES) return fail(LB200_EINVAL, "more than %d planes per slab", LB200_LE_MAXPLANES);
+  if (!o->periodic[1]) return fail(LB200_EINVAL, "Lees-Edwards planes need a periodic y direction");
+  c->le.nplane = npl;
+  c->le.xblock = o->nlocal[0]/npl;
+  c->le.uy = o->le_uy;
+  for (int p = 0; p < npl; p++) {
+    const int ic = lb200_le_plane_location(o, p);
+    if (ic <= o->nhalo || ic > o->nlocal[0] - o->nhalo) return fail(LB200_EINVAL, "Wall at domain boundary (lees_edw_checks, src/leesedwards.c:449-460)");
+    c->le.loc[p] = ic;
+  }
+  c->nxbuf = 2*o->nhalo*npl;
+  return 0;
+}
+
+static int le_alloc(lb200_t * c) {
+  const lb200_options_t * o = &c->opt;
+  const int npl = c->le.nplane, nh = o->nhalo;
+  const size_t nyz = (size_t) o->nlocal[1]*o->nlocal[2];
+  int nprop = 0;
+  for (int p = 1; p < c->nvel; p++) if (c->model_h.cv[p][0] == 1) nprop++;
+  c->le.nprop = nprop;
+
+  // gradient patch: the real planes either side of each plane and the nextra = nhalo - 1 buffer planes beyond
+  // (grad_3d_27pt_fluid_le, src/gradient_3d_27pt_fluid.c:421-425, 535-541)
+  std::vector<int> trip, xl;
+  const int ne = nh - 1;
+  for (int p = 0; p < npl; p++) {
+    const int ic = c->le.loc[p];
+    trip.insert(trip.end(), {ic - 1, ic, lb200_le_ic_to_buff(o, ic, +1)});
+    trip.insert(trip.end(), {lb200_le_ic_to_buff(o, ic + 1, -1), ic + 1, ic + 2});
+    for (int n = 1; n <= ne; n++) {
+      trip.insert(trip.end(), {lb200_le_ic_to_buff(o, ic, n - 1), lb200_le_ic_to_buff(o, ic, n), lb200_le_ic_to_buff(o, ic, n + 1)});
+      trip.insert(trip.end(), {lb200_le_ic_to_buff(o, ic + 1, -n - 1), lb200_le_ic_to_buff(o, ic + 1, -n), lb200_le_ic_to_buff(o, ic + 1, -n + 1)});
+    }
+    // force / Cahn-Hilliard patch of the fused fast path: every plane whose stencil (+-2 in x, or +-1 of a
+    // site whose gradient was patched) crosses the plane
+    for (int x = ic - nh + 1; x <= ic + nh; x++) xl.push_back(x);
+  }
+  c->le_ntrip = (int) trip.size()/3;
+  c->le_nxlist = (int) xl.size();
+  if (cudaMalloc((void **) &c->le_trip, trip.size()*sizeof(int)) != cudaSuccess) return -1;
+  if (cudaMalloc((void **) &c->le_xlist, xl.size()*sizeof(int)) != cudaSuccess) return -1;
+  if (cudaMemcpy(c->le_trip, trip.data(), trip.size()*sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  if (cudaMemcpy(c->le_xlist, xl.data(), xl.size()*sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  int rc = 0;
+  rc |= alloc_d(&c->le_term, (size_t) 3*npl*nyz);
+  rc |= alloc_d(&c->le_fcor, (size_t) 3*npl);
+  rc |= alloc_d(&c->le_chx, (size_t) 2*npl*nyz);
+  rc |= alloc_d(&c->le_sbuf, (size_t) 2*npl*c->ndist*nprop*nyz);
+  return rc;
+}
+
+// physics_control_time, src/physics.c:622-630
+static double le_time(const lb200_t * c) { return 1.0*(c->t_start + c->t_current - 1.0); }
+
+// lees_edw_buffer_displacement (steady shear), src/leesedwards.c:649-673, for a buffer with jump sign duy
+static double le_buffer_displacement(const lb200_t * c, int duy, double t) {
+  if (t < 0.0) t = 0.0;
+  const double tle = t - 1.0*c->opt.le_nt0;
+  return tle*c->opt.le_uy*duy;
+}
+
+// field_leesedwards (src/field.c:466-470, 492-497): 4-point Lagrange weights in the reference's evaluation order
+static void le_interp_cubic(const lb200_t * c, Lb200LeInterp * ip) {
+  const double r6 = (1.0/6.0);
+  const double ltot_y = 1.0*c->g.nl[1];
+  for (int s = 0; s < 2; s++) {
+    double dy = le_buffer_displacement(c, s ? +1 : -1, le_time(c) + 0.0);
+    dy = fmod(dy, ltot_y);
+    const int jdy = (int) floor(dy);
+    const double fr = 1.0 - (dy - jdy);
+    ip->jdy[s] = jdy;
+    ip->w[s][0] = r6*fr*(fr-1.0)*(fr-2.0);
+    ip->w[s][1] = 0.5*(fr*fr-1.0)*(fr-2.0);
+    ip->w[s][2] = 0.5*fr*(fr+1.0)*(fr-2.0);
+    ip->w[s][3] = r6*fr*(fr*fr-1.0);
+  }
+}
+
+// hydro_lees_edwards (src/hydro.c:398-404): the displacement is taken at time + 1
+static void le_interp_linear(const lb200_t * c, Lb200LeInterp * ip) {
+  const double ltot_y = 1.0*c->g.nl[1];
+  memset(ip, 0, sizeof(*ip));
+  for (int s = 0; s < 2; s++) {
+    double dy = le_buffer_displacement(c, s ? +1 : -1, le_time(c) + 1.0);
+    dy = fmod(dy, ltot_y);
+    const int jdy = (int) floor(dy);
+    const double fr = dy - jdy;
+    ip->jdy[s] = jdy;
+    ip->w[s][0] = fr;
+    ip->w[s][1] = 1.0 - fr;
+  }
+}
+
+// phi_ch_le_fix_fluxes (src/phi_cahn_hilliard.c:667-671, 692-696): lees_edw_plane_dy = time*uy, looked at from
+// below (+dy) and from above (-dy); and the force flux normaliser (src/phi_force.c:647)
+static void le_fix_param(const lb200_t * c, Lb200LeFix * fx) {
+  const double ltot_y = 1.0*c->g.nl[1], ltot_z = 1.0*c->g.nl[2];
+  const double dy0 = le_time(c)*c->opt.le_uy;
+  for (int s = 0; s < 2; s++) {
+    double dy = fmod(s ? -dy0 : +dy0, ltot_y);
+    const int jdy = (int) floor(dy);
+    fx->jdy[s] = jdy;
+    fx->fr[s] = dy - jdy;
+  }
+  fx->ra = 0.5/(ltot_y*ltot_z);
+}
+
+// lb_data_apply_le_boundary_conditions (src/model_le.c:106-110, 375-380, 612-616): displacement of buffer
+// ib = nhalo (jump +uy) at t = the time STEP, seen by the populations going up (cx = +1) and down (cx = -1)
+static void le_lb_param(const lb200_t * c, Lb200LeFix * fx) {
+  const double ltot_y = 1.0*c->g.nl[1];
+  const double dy_le = le_buffer_displacement(c, +1, 1.0*c->t_current);
+  for (int s = 0; s < 2; s++) {
+    const int cx = 1 - 2*s;
+    double dy = fmod(dy_le*cx, ltot_y);
+    const int jdy = (int) floor(dy);
+    fx->jdy[s] = jdy;
+    fx->fr[s] = dy - jdy;
+  }
+  fx->ra = 0.0;
+}
+
 int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   if (o == nullptr || pctx == nullptr) return fail(LB200_EINVAL, "null argument");
   *pctx = nullptr;
@@ -340,7 +523,9 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   g.nh = o->nhalo;
   g.ys = g.nall[2];
   g.xs = g.nall[1]*g.nall[2];
-  const long long ns = (long long) g.nall[0]*g.nall[1]*g.nall[2];
+  if (le_setup(c) != 0) { delete c; return LB200_EINVAL; }
+  c->nsites_lb = g.nall[0]*g.nall[1]*g.nall[2];
+  const long long ns = (long long) (g.nall[0] + c->nxbuf)*g.nall[1]*g.nall[2];
   if (ns*c->nvel*c->ndist > 2147483647LL) {
     delete c;
     return fail(LB200_EINVAL, "nsites*nvel exceeds INT_MAX (reference guard src/lb_data.c:116-120)");
@@ -380,6 +565,7 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
     rc |= alloc_d(&c->slo, c->stage_doubles);
     rc |= alloc_d(&c->shi, c->stage_doubles);
   }
+  if (rc == 0 && c->le.nplane > 0) rc = le_alloc(c);
   if (rc != 0) { lb200_free(c); return LB200_ECUDA; }
   CUDA_TRY(cudaMalloc((void **) &c->status, nsz));
   CUDA_TRY(cudaMemset(c->status, 0, nsz));
@@ -440,6 +626,7 @@ int lb200_free(lb200_t * c) {
   cudaFree(c->f); cudaFree(c->fprime); cudaFree(c->u_alloc[0] ? c->u_alloc[0] : c->u); cudaFree(c->u_alloc[1]); cudaFree(c->rho); cudaFree(c->force);
   cudaFree(c->phi); cudaFree(c->phinew); cudaFree(c->grad); cudaFree(c->delsq);
   cudaFree(c->grad_delsq); cudaFree(c->delsq_delsq); cudaFree(c->str);
+  cudaFree(c->le_trip); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
   for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
   cudaFree(c->flags); cudaFree(c->spin_err);
   cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->slo); cudaFree(c->shi); cudaFree(c->model_d);
@@ -455,6 +642,7 @@ int lb200_free(lb200_t * c) {
 }
 
 int lb200_nsites(const lb200_t * c) { return c ? c->g.nsites : LB200_EINVAL; }
+int lb200_nsites_lb(const lb200_t * c) { return c ? c->nsites_lb : LB200_EINVAL; }
 long long lb200_launch_count(const lb200_t * c) { return c ? c->launches : 0; }
 void * lb200_stream(lb200_t * c) { return c ? (void *) c->stream : nullptr; }
 
@@ -534,7 +722,8 @@ static int do_memcpy(lb200_t * c, int array, double * host, int kind, int async)
 
   if (array == LB200_MAP) {
     // status is exchanged as doubles at this interface and held as bytes on the device
-    const size_t ns = (size_t) c->g.nsites;
+    // (map->status has cs_nsites entries, a prefix of the device array when there are Lees-Edwards buffer planes)
+    const size_t ns = (size_t) c->nsites_lb;
     std::vector<char> tmp(ns);
     if (kind == LB200_HOST_TO_DEVICE) {
       int all_fluid = 1;
@@ -574,7 +763,13 @@ static int do_memcpy(lb200_t * c, int array, double * host, int kind, int async)
   }
 
   const size_t bytes = ncomp*(size_t) c->g.nsites*sizeof(double);
-  if (kind == LB200_HOST_TO_DEVICE) {
+  if (array == LB200_F && c->nxbuf > 0) {
+    // lb->f has cs_nsites per population on the host (src/lb_data.c:102-115), the device arrays share one stride
+    const size_t hpitch = (size_t) c->nsites_lb*sizeof(double), dpitch = (size_t) c->g.nsites*sizeof(double);
+    if (kind == LB200_HOST_TO_DEVICE) CUDA_TRY(cudaMemcpy2DAsync(dev, dpitch, host, hpitch, hpitch, ncomp, cudaMemcpyHostToDevice, c->stream));
+    else                              CUDA_TRY(cudaMemcpy2DAsync(host, hpitch, dev, dpitch, hpitch, ncomp, cudaMemcpyDeviceToHost, c->stream));
+  }
+  else if (kind == LB200_HOST_TO_DEVICE) {
     CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
   }
   else {
@@ -620,7 +815,7 @@ int lb200_slab_plan(const lb200_options_t * o, int ncomp, int depth, lb200_slab_
   p->right = (o->cart_rank + 1) % o->cart_size;
   p->has_lo = (o->periodic[0] != 0) || o->cart_rank > 0;
   p->has_hi = (o->periodic[0] != 0) || o->cart_rank < o->cart_size - 1;
-  p->nsites = nax*xs;
+  p->nsites = (nax + 2*o->nhalo*le_nplane_local(o))*xs;
   p->chunk = depth*xs;
   p->off_lo = (long long) (1 + o->nhalo - 1)*xs;
   p->off_hi = (long long) (o->nlocal[0] - depth + 1 + o->nhalo - 1)*xs;
@@ -640,7 +835,7 @@ int lb200_step_plan(const lb200_options_t * o, int what, lb200_step_plan_t * p) 
   p->left = (o->cart_rank - 1 + o->cart_size) % o->cart_size;
   p->right = (o->cart_rank + 1) % o->cart_size;
   p->depth = (what == LB200_STEP_PHI) ? o->nhalo : 1;
-  p->nsites = nax*xs;
+  p->nsites = (nax + 2*o->nhalo*le_nplane_local(o))*xs;
   p->chunk = p->depth*xs;
   p->src_up = (long long) (o->nlocal[0] - p->depth + o->nhalo)*xs;
   p->dst_up = (long long) (o->nhalo - p->depth)*xs;
@@ -804,18 +999,111 @@ int lb200_phi_halo(lb200_t * c) {
   CTX_LEAVE_SYNC(c);
 }
 
+// field_leesedwards, src/field.c:418-510
+static int le_field_async(lb200_t * c, double * phi) {
+  if (c->le.nplane == 0) return 0;
+  Lb200LeInterp ip;
+  le_interp_cubic(c, &ip);
+  ProfScope ps(c, LB200_K_LE);
+  c->launches += c->k->le_interp(c->stream, c->g, c->le, ip, 1, 1, c->g.nh, phi);
+  return 0;
+}
+
+// hydro_lees_edwards, src/hydro.c:350-440
+static int le_hydro_async(lb200_t * c) {
+  if (c->le.nplane == 0) return 0;
+  Lb200LeInterp ip;
+  le_interp_linear(c, &ip);
+  ProfScope ps(c, LB200_K_LE);
+  c->launches += c->k->le_interp(c->stream, c->g, c->le, ip, 0, 3, c->g.nh, c->u);
+  return 0;
+}
+
+// grad_3d_27pt_fluid_d2 with planes: the two real planes next to each plane again, through the buffer planes,
+// and the buffer planes themselves (src/gradient_3d_27pt_fluid.c:94-95, 250-253, 375-651)
+static int le_grad_async(lb200_t * c) {
+  if (c->le.nplane == 0) return 0;
+  ProfScope ps(c, LB200_K_LE);
+  c->launches += c->k->le_grad_planes(c->stream, c->g, c->g.nh - 1, c->le_ntrip, c->le_trip, c->phi, c->grad, c->delsq);
+  return 0;
+}
+
 int lb200_phi_grad_compute(lb200_t * c) {
   CTX_ENTER(c);
   if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  le_field_async(c, c->phi);              // field_grad_compute -> field_leesedwards, src/field_grad.c:324
   {
     ProfScope ps(c, LB200_K_GRAD);
     c->launches += c->k->grad27(c->stream, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);
   }
+  le_grad_async(c);
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_field_leesedwards(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  le_field_async(c, c->phi);
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_hydro_lees_edwards(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+  le_hydro_async(c);
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_physics_control_time_set(lb200_t * c, int t_start, int t_current) {
+  if (c == nullptr) return fail(LB200_EINVAL, "null context");
+  c->t_start = t_start;
+  c->t_current = t_current;
+  return 0;
+}
+
+int lb200_physics_control_timestep(const lb200_t * c) { return c ? c->t_current : LB200_EINVAL; }
+
+// phi_force_flux / phi_cahn_hilliard with planes: the generic kernels of lb200_le.cuh on nx planes
+// (xlist == nullptr: the whole lattice)
+static int le_force_ch_async(lb200_t * c, const Lb200SymmDev & sd, int nx, const int * xlist, int do_force, int do_ch,
+			     int accumulate, double * phinew) {
+  Lb200LeFix fx;
+  le_fix_param(c, &fx);
+  ProfScope ps(c, LB200_K_LE);
+  if (do_force) c->launches += c->k->le_force_prep(c->stream, c->g, c->le, sd, c->phi, c->grad, c->delsq, c->le_term, c->le_fcor);
+  if (do_ch)    c->launches += c->k->le_ch_prep(c->stream, c->g, c->le, sd, c->phi, c->delsq, c->u, status_ptr(c), c->le_chx);
+  c->launches += c->k->le_force_ch(c->stream, c->g, c->le, sd, fx, nx, xlist, do_force, do_ch, accumulate, c->phi, c->grad,
+				   c->delsq, c->u, status_ptr(c), c->le_fcor, c->le_chx, c->force, phinew);
+  return 0;
+}
+
+// lb_data_apply_le_boundary_conditions, src/model_le.c:78-180 (in place on the post-collision distributions)
+static int le_lb_bc_async(lb200_t * c) {
+  if (c->le.nplane == 0) return 0;
+  Lb200LeFix fx;
+  le_lb_param(c, &fx);
+  ProfScope ps(c, LB200_K_LE);
+  c->launches += c->k->le_lb_bc(c->stream, c->g, c->le, fx, c->model_d, c->ndist, c->f, c->le_sbuf);
+  return 0;
+}
+
+int lb200_lb_le_apply_boundary_conditions(lb200_t * c) {
+  CTX_ENTER(c);
+  int rc = materialise_propagation(c);
+  if (rc != 0) return rc;
+  le_lb_bc_async(c);
+  c->f_halo_stale = 0;
   CTX_LEAVE_SYNC(c);
 }
 
 static int phi_force_async(lb200_t * c, const Lb200SymmDev & sd) {
   const int accumulate = (c->force_state != ZERO_PENDING);
+  if (c->le.nplane > 0) {
+    // "Must use the flux method for LE planes", src/phi_force.c:91-97
+    le_force_ch_async(c, sd, c->g.nl[0], nullptr, 1, 0, accumulate, nullptr);
+    if (c->force_state == ZERO_PENDING) c->force_state = INTERIOR_ONLY;
+    return 0;
+  }
   ProfScope ps(c, LB200_K_FORCE_CH);
   c->launches += c->k->phi_force(c->stream, c->g, sd, accumulate, c->phi, c->grad, c->delsq, c->force);
   if (c->force_state == ZERO_PENDING) c->force_state = INTERIOR_ONLY;
@@ -827,6 +1115,7 @@ int lb200_phi_grad_compute_d4(lb200_t * c) {
   CTX_ENTER(c);
   if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
   if (c->g.nh < 2) return fail(LB200_ESTATE, "grad_3d_27pt_fluid_d4 needs nhalo >= 2 (reference asserts nhalo - 2 >= 0)");
+  if (c->le.nplane > 0) return fail(LB200_ESTATE, "grad_3d_27pt_fluid_d4 with Lees-Edwards planes is not implemented");
   if (c->grad_delsq == nullptr) {
     if (alloc_d(&c->grad_delsq, (size_t) 3*c->g.nsites) != 0 || alloc_d(&c->delsq_delsq, (size_t) c->g.nsites) != 0) return LB200_ECUDA;
   }
@@ -886,7 +1175,11 @@ int lb200_phi_cahn_hilliard(lb200_t * c, const lb200_symm_param_t * sp) {
   if (rc != 0) return rc;
   // phinew holds phi everywhere (halo included) so that the swap keeps the reference's view
   CUDA_TRY(cudaMemcpyAsync(c->phinew, c->phi, (size_t) c->g.nsites*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  {
+  if (c->le.nplane > 0) {
+    le_hydro_async(c);                    // hydro_lees_edwards, src/phi_cahn_hilliard.c:230
+    le_force_ch_async(c, sd, c->g.nl[0], nullptr, 0, 1, 0, c->phinew);
+  }
+  else {
     ProfScope ps(c, LB200_K_FORCE_CH);
     c->launches += c->k->cahn_hilliard(c->stream, c->g, sd, c->phi, c->delsq, c->u, status_ptr(c), c->phinew);
   }
@@ -1428,6 +1721,66 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   return 0;
 }
 
+// ---- whole time steps with Lees-Edwards planes -----------------------------------------------------------------
+// Reference order (src/ludwig.c:528-860 with ludwig->le): hydro_f_zero; field_halo(phi); field_grad_compute
+// (field_leesedwards + d2 + buffer-region gradients); phi_force_calculation (flux form); phi_cahn_hilliard
+// (hydro_u_halo, hydro_lees_edwards, fluxes, phi_ch_le_fix_fluxes, update); hydro_u_zero; lb_collide;
+// lb_data_apply_le_boundary_conditions; lb_halo; lb_propagation.
+//   strict: the reference's operations everywhere (flux-form force on the whole lattice): bit-identical.
+//   fast  : the one-sweep phi-sector kernel for the bulk, then the planes whose stencils cross a Lees-Edwards
+//           plane (2*nhalo per plane) are redone by the generic plane kernels through the buffer planes.
+static int step_le(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev & sd, int nsteps) {
+  cudaStream_t S = c->stream;
+  const Lb200Geom & g = c->g;
+  int rc = ensure_f_halo(c);
+  if (rc != 0) return rc;
+  const bool fused = (c->opt.math == LB200_MATH_FAST) && c->knob_phi_sector && c->map_all_fluid;
+
+  for (int n = 0; n < nsteps; n++) {
+    c->t_current += 1;                                                   // physics_control_next_step
+    c->force_state = ZERO_PENDING;                                       // hydro_f_zero
+    rc = halo_field(c, c->phi, 1, g.nh, 0, S);                           // field_halo(phi)
+    if (rc != 0) return rc;
+    le_field_async(c, c->phi);                                           // field_leesedwards
+    if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+    rc = halo_field(c, c->u, 3, g.nh, 0, S);                             // hydro_u_halo
+    if (rc != 0) return rc;
+    c->u_state = ARRAY_CLEAN;
+    le_hydro_async(c);                                                   // hydro_lees_edwards
+    if (fused) {
+      {
+	ProfScope ps(c, LB200_K_PHI_SECTOR);
+	c->launches += c->k->phi_sector(S, g, sd, c->phi, c->u, c->grad, c->delsq, c->force, c->phinew);
+      }
+      le_grad_async(c);
+      le_force_ch_async(c, sd, c->le_nxlist, c->le_xlist, 1, 1, 0, c->phinew);
+    }
+    else {
+      {
+	ProfScope ps(c, LB200_K_GRAD);
+	c->launches += c->k->grad27(S, g, g.nh - 1, c->phi, c->grad, c->delsq);
+      }
+      le_grad_async(c);
+      le_force_ch_async(c, sd, g.nl[0], nullptr, 1, 1, 0, c->phinew);
+    }
+    c->force_state = INTERIOR_ONLY;
+    { double * t = c->phi; c->phi = c->phinew; c->phinew = t; }
+    c->u_state = ZERO_PENDING;                                           // hydro_u_zero
+    rc = collide_async(c, cd);                                           // (lb_propagation +) lb_collide
+    if (rc != 0) return rc;
+    le_lb_bc_async(c);                                                   // lb_data_apply_le_boundary_conditions
+    rc = halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED, S);   // lb_halo
+    if (rc != 0) return rc;
+    c->prop_pending = 1;                                                 // lb_propagation (lazy)
+    c->f_halo_stale = 0;
+  }
+  c->phi_halo_valid = 0;
+  c->u_halo_valid = 0;
+  c->wrap_x_valid = 0;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // ---- whole time steps ---------------------------------------------------------------------------------
 // Order of operations of the reference driver (src/ludwig.c:528-860):
 //   hydro_f_zero; field_halo(phi); field_grad_compute; phi_force_calculation; phi_cahn_hilliard
@@ -1447,6 +1800,10 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   if (rc != 0) return rc;
   if (binary) symm_dev(c, sp, &sd);
   if (nsteps <= 0) return 0;
+  if (c->le.nplane > 0) {
+    if (!binary || c->ndist != 1) return fail(LB200_EINVAL, "Lees-Edwards planes: lb200_step is implemented for the binary-fluid FD route (ndist = 1, free_energy symmetric)");
+    return step_le(c, cd, sd, nsteps);
+  }
   if (c->ndist == 2) {
     if (!binary) return fail(LB200_EINVAL, "ndist = 2 needs the free-energy parameters");
     return step_lb2(c, cd, sd, nsteps);

@@ -1894,6 +1894,8 @@ int launch_zero_outside(cudaStream_t st, const Lb200Geom & g, int ncomp, double 
   return 1;
 }
 
+#include "lb200_le.cuh"
+
 }  // anonymous namespace
 }  // namespace lb200_fast / lb200_strict
 
@@ -1920,4 +1922,10 @@ const Lb200Kernels LB200_TABLE = {
   launch_force_from_stress,
   launch_signal,
   launch_spin_wait,
+  launch_le_interp,
+  launch_le_grad_planes,
+  launch_le_force_prep,
+  launch_le_ch_prep,
+  launch_le_force_ch,
+  launch_le_lb_bc,
 };

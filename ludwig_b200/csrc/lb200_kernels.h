@@ -25,6 +25,30 @@ struct Lb200Geom {
   double * peer_phi_lo, * peer_phi_hi;
 };
 
+// Lees-Edwards planes (reference src/leesedwards.c).  Field arrays of an LE context carry 2*nh*nplane buffer
+// x-planes after the high x halo (Lb200Geom::nsites counts them; nall[0] does not).
+constexpr int LB200_LE_MAXPLANES = 16;
+struct Lb200LeDev {
+  int nplane;           // planes in this slab (0: none)
+  int xblock;           // nl[0]/nplane
+  int nprop;            // populations with c_x = +1 (= those with c_x = -1)
+  int loc[LB200_LE_MAXPLANES];   // plane p lies between local x = loc[p] and loc[p] + 1
+  double uy;            // plane speed
+};
+// displacement of the buffer planes, formed on the host as the reference does (fmod, floor):
+// index 0: buffers with velocity jump -uy, 1: +uy.  Cubic (phi): w = the four Lagrange weights;
+// linear (u): w[0] = fr, w[1] = 1 - fr
+struct Lb200LeInterp {
+  int jdy[2];
+  double w[2][4];
+};
+// index 0: the side below a plane (c_x = +1 populations / east face flux), 1: above
+struct Lb200LeFix {
+  int jdy[2];
+  double fr[2];
+  double ra;            // 0.5/(Ly Lz), force flux correction
+};
+
 struct Lb200CollideDev {
   double fg[3];         // force_global
   double rtau;          // 1/tau_shear
@@ -97,6 +121,24 @@ struct Lb200Kernels {
   // not available), giving up after ~timeout_ms with *err = 1
   int (*signal)(cudaStream_t, unsigned int * a, unsigned int * b, unsigned int value);
   int (*spin_wait)(cudaStream_t, const unsigned int * flag, unsigned int value, int timeout_ms, int * err);
+  // Lees-Edwards planes (lb200_le.cuh): buffer planes of a field (cubic: phi, linear + jump: u), the 27-point
+  // gradient on (x-1, x, x+1) plane triples, the flux-form force with its per-plane correction, the
+  // Cahn-Hilliard x-face fluxes either side of a plane, force and/or Cahn-Hilliard on a list of x-planes,
+  // and the re-projection + displacement + interpolation of the plane-crossing populations
+  int (*le_interp)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200LeInterp &, int cubic,
+		   int ncomp, int zext, double * data);
+  int (*le_grad_planes)(cudaStream_t, const Lb200Geom &, int ne, int ntrip, const int * trip, const double * phi,
+			double * grad, double * delsq);
+  int (*le_force_prep)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200SymmDev &, const double * phi,
+		       const double * grad, const double * delsq, double * term, double * fcor);
+  int (*le_ch_prep)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200SymmDev &, const double * phi,
+		    const double * delsq, const double * u, const char * status, double * chx);
+  int (*le_force_ch)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200SymmDev &, const Lb200LeFix &,
+		     int nx, const int * xlist, int do_force, int do_ch, int accumulate, const double * phi,
+		     const double * grad, const double * delsq, const double * u, const char * status,
+		     const double * fcor, const double * chx, double * force, double * phinew);
+  int (*le_lb_bc)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200LeFix &, const Lb200ModelDev *,
+		  int ndist, double * f, double * sbuf);
 };
 
 extern const Lb200Kernels lb200_kernels_fast;

@@ -1,0 +1,165 @@
+"""Lees-Edwards planes on the GPU, through the C-ABI, against the CPU oracle
+(oracle/lb_oracle_le.c, pinned bit-for-bit to the compiled reference and to serial-le3d-st5/6/7.log in
+tests/test_le_oracle.py) on identical inputs.
+
+Bar: LB200_MATH_STRICT bit-exact for every operator and for whole time steps; LB200_MATH_FAST (FMA contraction,
+fused phi sector for the bulk + plane patches) within 1e-12 relative (absolute floor 1e-14) after N steps."""
+import numpy as np
+import pytest
+
+import ludwig_b200 as lb
+from common import close_fast
+from ludwig_b200.initial import spinodal_phi
+from oracle import Oracle, fed_density, stats_scalar
+
+pytestmark = pytest.mark.gpu
+
+FE = dict(a=-0.0625, b=0.0625, kappa=0.04, mobility=0.15)     # serial-le3d-st*.inp
+ETA = 0.1
+UY = 0.05
+
+
+def le_state(orc, seed=11, amp=0.05):
+    """shear-profile distributions with a non-equilibrium perturbation, noisy phi and u (interior; halos zero)"""
+    rng = np.random.default_rng(seed)
+    n = orc.nlocal
+    f = np.zeros((orc.nvel, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f)
+    orc.interior(f)[...] *= 1.0 + 1e-3 * (rng.random(orc.interior(f).shape) - 0.5)
+    phi = np.zeros((1, orc.nsites))
+    orc.interior(phi)[0] = amp * (rng.random(n) - 0.5)
+    u = np.zeros((3, orc.nsites))
+    orc.interior(u)[...] = 0.02 * (rng.random((3,) + tuple(n)) - 0.5)
+    return f, phi, u
+
+
+def make(n, nplanes, order, math, nvel=19):
+    orc = Oracle(n, nhalo=2, le_nplanes=nplanes, le_uy=UY, nvel=nvel)
+    sim = lb.Lb200(n, nhalo=2, nvel=nvel, have_phi=True, math=math, le_nplanes=nplanes, le_uy=UY)
+    assert sim.nsites == orc.nsites and sim.nsites_lb == orc.nsites_lb
+    sp_o = orc.symm_param(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order)
+    sp_g = lb.SymmParam.make(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order)
+    return orc, sim, sp_o, sp_g
+
+
+def test_le_geometry_host():
+    """lb200_le_plane_location / lb200_le_ic_to_buff (pure host arithmetic) against the oracle's (= the reference's)"""
+    lib = lb.load_library()
+    import ctypes as C
+    for n, npl in (((32, 8, 8), 2), ((16, 4, 4), 1), ((48, 4, 4), 4)):
+        orc = Oracle(n, nhalo=2, le_nplanes=npl)
+        o = lb.capi.Options()
+        o.nlocal[:] = n
+        o.nhalo, o.cart_size, o.cart_rank, o.le_nplanes = 2, 1, 0, npl
+        for p in range(npl):
+            assert lib.lb200_le_plane_location(C.byref(o), p) == orc.le_plane_location(p)
+        for ic in range(1, n[0] + 1):
+            for di in (-2, -1, 1, 2):
+                assert lib.lb200_le_ic_to_buff(C.byref(o), ic, di) == orc.le_ic_to_buff(ic, di), (ic, di)
+
+
+@pytest.mark.parametrize("n,nplanes", [((16, 8, 6), 1), ((16, 12, 40), 2), ((24, 7, 5), 2)])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_le_operators_strict_bit_exact(n, nplanes, order):
+    orc, sim, sp_o, sp_g = make(n, nplanes, order, lb.MATH_STRICT)
+    with sim:
+        f, phi, u = le_state(orc)
+        tcur = 8                                   # time = 7: displacements 0.35 / 0.4, fractional
+        time, tstep = tcur - 1.0, float(tcur)
+        sim.physics_control_time_set(0, tcur)
+        sim.put(lb.F, f); sim.put(lb.PHI, phi); sim.put(lb.U, u)
+
+        # field_halo + field_grad_compute
+        sim.phi_halo(); sim.phi_grad_compute()
+        grad = np.zeros((3, orc.nsites)); delsq = np.zeros((1, orc.nsites))
+        orc.field_halo(phi); orc.le_field(time, phi); orc.grad_27pt(phi, grad, delsq); orc.le_grad_buffer(phi, grad, delsq)
+        assert np.array_equal(sim.get(lb.PHI), phi)                       # buffer planes included
+        gg, gd = sim.get(lb.GRAD), sim.get(lb.DELSQ)
+        assert np.array_equal(orc.region(gg, 1), orc.region(grad, 1)) and np.array_equal(orc.region(gd, 1), orc.region(delsq, 1))
+        for p in range(nplanes):
+            for x in (orc.le_ic_to_buff(orc.le_plane_location(p), 1), orc.le_ic_to_buff(orc.le_plane_location(p) + 1, -1)):
+                sl = lambda a: a.reshape((a.shape[0], -1) + orc.nall[1:])[:, x + 1, 1:-1, 1:-1]
+                assert np.array_equal(sl(gg), sl(grad)) and np.array_equal(sl(gd), sl(delsq))
+
+        # phi_force_calculation: flux form + per-plane correction
+        sim.hydro_f_zero(); sim.phi_force_calculation(sp_g)
+        force = np.zeros((3, orc.nsites))
+        orc.le_phi_force(sp_o, phi, grad, delsq, force)
+        assert np.array_equal(orc.interior(sim.get(lb.FORCE)), orc.interior(force))
+
+        # phi_cahn_hilliard: u halo, hydro_lees_edwards, fluxes, flux fix, update
+        sim.phi_cahn_hilliard(sp_g)
+        orc.field_halo(u); orc.le_hydro(time, u, nhcomm=2)
+        assert np.array_equal(sim.get(lb.U), u)
+        flux = np.zeros((4, orc.nsites))
+        orc.advection(order, u, phi, flux); orc.flux_mu(sp_o, phi, delsq, flux); orc.flux_mu_ext(sp_o, flux)
+        orc.le_fix_fluxes(time, flux); orc.phi_update(flux, phi)
+        assert np.array_equal(orc.interior(sim.get(lb.PHI)), orc.interior(phi))
+
+        # lb_data_apply_le_boundary_conditions
+        sim.lb_le_apply_boundary_conditions()
+        orc.le_lb_bc(tstep, f)
+        assert np.array_equal(orc.interior(sim.get(lb.F)), orc.interior(f))
+
+
+@pytest.mark.parametrize("nvel", [15, 27])
+def test_le_lb_bc_other_models(nvel):
+    """the plane-crossing re-projection for the other velocity sets (5 / 9 crossing populations per side)"""
+    n, npl = (16, 9, 7), 2
+    orc = Oracle(n, nhalo=1, le_nplanes=npl, le_uy=UY, nvel=nvel)
+    rng = np.random.default_rng(3)
+    f = np.zeros((nvel, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f)
+    orc.interior(f)[...] *= 1.0 + 1e-3 * (rng.random(orc.interior(f).shape) - 0.5)
+    with lb.Lb200(n, nhalo=1, nvel=nvel, math=lb.MATH_STRICT, le_nplanes=npl, le_uy=UY) as sim:
+        sim.physics_control_time_set(0, 13)
+        sim.put(lb.F, f)
+        sim.lb_le_apply_boundary_conditions()
+        got = sim.get(lb.F)
+    orc.le_lb_bc(13.0, f)
+    assert np.array_equal(orc.interior(got), orc.interior(f))
+
+
+def _run_steps(n, nplanes, order, math, nsteps, seed=13):
+    orc, sim, sp_o, sp_g = make(n, nplanes, order, math)
+    f = np.zeros((19, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f)
+    phi = np.zeros((1, orc.nsites))
+    phi[:, :orc.nsites_lb] = spinodal_phi(n, 2, seed, 0.0, 0.1)
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+    with sim:
+        sim.put(lb.F, f); sim.put(lb.PHI, phi)
+        sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), sp_g, nsteps)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO),
+                                          ("force", lb.FORCE), ("grad", lb.GRAD), ("delsq", lb.DELSQ))}
+        assert sim.physics_control_timestep() == nsteps
+    orc.le_step(orc.collide_param(0, 1.0, ETA), sp_o, 0, nsteps, f, phi, u, rho, force, grad, delsq)
+    want = dict(f=f, phi=phi, u=u, rho=rho, force=force, grad=grad, delsq=delsq)
+    return orc, sp_o, got, want
+
+
+@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 8, 40), 1, 3), ((24, 8, 6), 2, 2), ((32, 32, 32), 2, 3)])
+def test_le_steps_strict_bit_exact(n, nplanes, order):
+    orc, sp, got, want = _run_steps(n, nplanes, order, lb.MATH_STRICT, 12)
+    for k in want:
+        assert np.array_equal(orc.interior(got[k]), orc.interior(want[k])), k
+
+
+@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 16, 40), 1, 3), ((24, 16, 16), 2, 2), ((32, 32, 32), 2, 3)])
+def test_le_steps_fast_tolerance(n, nplanes, order):
+    orc, sp, got, want = _run_steps(n, nplanes, order, lb.MATH_FAST, 20)
+    for k in want:
+        assert close_fast(orc.interior(got[k]), orc.interior(want[k])), (k, np.abs(orc.interior(got[k]) - orc.interior(want[k])).max())
+
+
+def test_serial_le3d_st7_log_on_gpu():
+    """the reference's own regression answer (tests/regression/d3q19-short/serial-le3d-st7.log, advection order 3)
+    from the CUDA path in fast mode: printed statistics to the printed digits"""
+    orc, sp, got, want = _run_steps((32, 32, 32), 2, 3, lb.MATH_FAST, 10, seed=7361237)
+    approx = lambda v, d: pytest.approx(v, rel=0.5 * 10.0 ** (1 - d), abs=1e-30)
+    s = stats_scalar(orc, got["phi"])
+    assert s[2] == approx(3.0000123e-04, 8) and s[3] == approx(-4.4451160e-02, 8) and s[4] == approx(4.6772004e-02, 8)
+    assert fed_density(orc, sp, got["phi"], got["grad"]) == approx(-7.4768699749e-06, 10)
+    ui = orc.interior(got["u"])
+    assert ui[1].min() == approx(-2.3465114e-02, 8) and ui[1].max() == approx(2.3466305e-02, 8)
