@@ -224,8 +224,9 @@ def run_ours(args, rank, local_rank, world):
         nlocal = (2 * n // world, n, n)
     local_sites = float(nlocal[0]) * nlocal[1] * nlocal[2]
     nhalo = 2
+    # --le P: Lees-Edwards sheared binary fluid (BASELINE config 5), P planes per GPU, plane speed 0.05
     sim = lb.Lb200(nlocal, nhalo=nhalo, have_phi=True, math=lb.MATH_STRICT if args.strict else lb.MATH_FAST,
-                   device=local_rank, cart_size=world, cart_rank=rank)
+                   device=local_rank, cart_size=world, cart_rank=rank, le_nplanes=args.le * world, le_uy=0.05)
     if world > 1:
         ids = [sim.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -234,7 +235,7 @@ def run_ours(args, rank, local_rank, world):
     ns = sim.nsites
     nall = sim.nall
     # pinned host state (the reference's host arrays: lb->f, phi->data, hydro->u, hydro->rho)
-    h_f = torch.empty((19, ns), dtype=torch.float64, pin_memory=True)
+    h_f = torch.empty((19, sim.nsites_lb), dtype=torch.float64, pin_memory=True)
     h_phi = torch.empty((1, ns), dtype=torch.float64, pin_memory=True)
     h_u = torch.empty((3, ns), dtype=torch.float64, pin_memory=True)
     h_rho = torch.empty((1, ns), dtype=torch.float64, pin_memory=True)
@@ -243,8 +244,8 @@ def run_ours(args, rank, local_rank, world):
     for p in range(19):
         fv[p, :] = wv[p]                         # rho = 1, u = 0 equilibrium
     rng = np.random.default_rng(8361235 + rank)
-    pv = h_phi.numpy().reshape(nall)
-    pv[...] = 0.0
+    h_phi.numpy()[...] = 0.0
+    pv = h_phi.numpy()[0, :sim.nsites_lb].reshape(nall)
     pv[nhalo:-nhalo, nhalo:-nhalo, nhalo:-nhalo] = 0.05 * (rng.random(nlocal) - 0.5)
 
     cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA)
@@ -336,7 +337,7 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_ms = max_over_ranks(max(t0.elapsed_time(t1), wall * 1e3))
     e2e = sites_total * args.steps / (e2e_ms * 1e-3) / 1e6
-    h2d = (19 + 1) * ns * 8 / args.steps
+    h2d = (19 * sim.nsites_lb + ns) * 8 / args.steps
     d2h = (1 + 3 + 1) * ns * 8 / args.steps
 
     cpu = None
@@ -359,6 +360,8 @@ def run_ours(args, rank, local_rank, world):
                                    "+ MRT(M10) pull-stream-collide; periodic images read in-kernel (halo-free), "
                                    "x-planes over NVLink when sharded",
                        "lattice_per_gpu": list(nlocal), "decomposition": f"{world}_1_1 x-slabs",
+                       "lees_edwards": (f"{args.le * world} planes, plane speed 0.05 (steady shear): reference-structured step with "
+                                        "halo kernels + plane patches (not the halo-free path)" if args.le else "none"),
                        "math": "strict" if args.strict else "fast(fma)",
                        "x_plane_exchange": {0: "none (one GPU)", 1: "NCCL send/recv on a second stream",
                                             2: "NVLink peer stores from inside the kernels + flags"}[sim.exchange_mode()],
@@ -400,6 +403,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=128, help="edge of the CPU-baseline sample lattice")
     ap.add_argument("--strict", action="store_true", help="bit-exact arithmetic mode (no FMA contraction)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--le", type=int, default=0, help="Lees-Edwards planes per GPU (0: none, the headline workload)")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: a fixed (2*size) x size x size lattice over all GPUs (default: weak, size^3 per GPU)")
     args = ap.parse_args()

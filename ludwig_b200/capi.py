@@ -318,7 +318,11 @@ class Lb200:
     def step_api(self, cp, sp=None, nsteps=1):
         """The same time step through the individual reference-named entry points, in the
         reference driver's order (src/ludwig.c:528-860)."""
+        le = self.options.le_nplanes > 0
         for _ in range(nsteps):
+            if le:
+                # physics_control_next_step: the plane displacement is a function of the step counter
+                self.physics_control_time_set(0, self.physics_control_timestep() + 1)
             self.hydro_f_zero()
             if self.ndist == 2:
                 self.phi_lb_to_field()
@@ -336,10 +340,12 @@ class Lb200:
                 self.phi_cahn_hilliard(sp)
             self.hydro_u_zero()
             self.lb_collide(cp)
+            if le:
+                self.lb_le_apply_boundary_conditions()      # src/ludwig.c:817-819
             self.lb_halo()
             self.lb_propagation()
 
-    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch", "phi_sector")
+    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch", "phi_sector", "le")
 
     def profile(self, on=True):
         self._check(self.lib.lb200_profile(self.h, int(on)))

@@ -1000,31 +1000,33 @@ int lb200_phi_halo(lb200_t * c) {
 }
 
 // field_leesedwards, src/field.c:418-510
-static int le_field_async(lb200_t * c, double * phi) {
+static int le_field_async(lb200_t * c, double * phi, const Lb200Geom * gw = nullptr) {
   if (c->le.nplane == 0) return 0;
   Lb200LeInterp ip;
   le_interp_cubic(c, &ip);
   ProfScope ps(c, LB200_K_LE);
-  c->launches += c->k->le_interp(c->stream, c->g, c->le, ip, 1, 1, c->g.nh, phi);
+  c->launches += c->k->le_interp(c->stream, gw ? *gw : c->g, c->le, ip, 1, 1, c->g.nh, phi);
   return 0;
 }
 
 // hydro_lees_edwards, src/hydro.c:350-440
-static int le_hydro_async(lb200_t * c) {
+static int le_hydro_async(lb200_t * c, const Lb200Geom * gw = nullptr) {
   if (c->le.nplane == 0) return 0;
   Lb200LeInterp ip;
   le_interp_linear(c, &ip);
   ProfScope ps(c, LB200_K_LE);
-  c->launches += c->k->le_interp(c->stream, c->g, c->le, ip, 0, 3, c->g.nh, c->u);
+  c->launches += c->k->le_interp(c->stream, gw ? *gw : c->g, c->le, ip, 0, 3, c->g.nh, c->u);
   return 0;
 }
 
 // grad_3d_27pt_fluid_d2 with planes: the two real planes next to each plane again, through the buffer planes,
 // and the buffer planes themselves (src/gradient_3d_27pt_fluid.c:94-95, 250-253, 375-651)
-static int le_grad_async(lb200_t * c) {
+static int le_grad_async(lb200_t * c, const Lb200Geom * gw = nullptr) {
   if (c->le.nplane == 0) return 0;
   ProfScope ps(c, LB200_K_LE);
-  c->launches += c->k->le_grad_planes(c->stream, c->g, c->g.nh - 1, c->le_ntrip, c->le_trip, c->phi, c->grad, c->delsq);
+  // halo-free steps: every reader takes its y / z neighbours from the interior, so only interior (j, k) are needed
+  const int ne = (gw && gw->wrap[1] && gw->wrap[2]) ? 0 : c->g.nh - 1;
+  c->launches += c->k->le_grad_planes(c->stream, gw ? *gw : c->g, ne, c->le_ntrip, c->le_trip, c->phi, c->grad, c->delsq);
   return 0;
 }
 
@@ -1066,13 +1068,14 @@ int lb200_physics_control_timestep(const lb200_t * c) { return c ? c->t_current 
 // phi_force_flux / phi_cahn_hilliard with planes: the generic kernels of lb200_le.cuh on nx planes
 // (xlist == nullptr: the whole lattice)
 static int le_force_ch_async(lb200_t * c, const Lb200SymmDev & sd, int nx, const int * xlist, int do_force, int do_ch,
-			     int accumulate, double * phinew) {
+			     int accumulate, double * phinew, const Lb200Geom * gw = nullptr) {
   Lb200LeFix fx;
   le_fix_param(c, &fx);
+  const Lb200Geom & g = gw ? *gw : c->g;
   ProfScope ps(c, LB200_K_LE);
-  if (do_force) c->launches += c->k->le_force_prep(c->stream, c->g, c->le, sd, c->phi, c->grad, c->delsq, c->le_term, c->le_fcor);
-  if (do_ch)    c->launches += c->k->le_ch_prep(c->stream, c->g, c->le, sd, c->phi, c->delsq, c->u, status_ptr(c), c->le_chx);
-  c->launches += c->k->le_force_ch(c->stream, c->g, c->le, sd, fx, nx, xlist, do_force, do_ch, accumulate, c->phi, c->grad,
+  if (do_force) c->launches += c->k->le_force_prep(c->stream, g, c->le, sd, c->phi, c->grad, c->delsq, c->le_term, c->le_fcor);
+  if (do_ch)    c->launches += c->k->le_ch_prep(c->stream, g, c->le, sd, c->phi, c->delsq, c->u, status_ptr(c), c->le_chx);
+  c->launches += c->k->le_force_ch(c->stream, g, c->le, sd, fx, nx, xlist, do_force, do_ch, accumulate, c->phi, c->grad,
 				   c->delsq, c->u, status_ptr(c), c->le_fcor, c->le_chx, c->force, phinew);
   return 0;
 }
@@ -1623,7 +1626,9 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   }
   if (c->u_state == ZERO_PENDING && binary) materialise_zero(c, c->u, &c->u_state);
 
+  const bool le = (c->le.nplane > 0);
   for (int n = 0; n < nsteps; n++) {
+    c->t_current += 1;                                                   // physics_control_next_step
     c->force_state = ZERO_PENDING;                                       // hydro_f_zero
     if (binary) {
       if (remote) {
@@ -1633,10 +1638,22 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       }
       gw.peer_phi_lo = peer ? c->lo.phi[idx2(c->phinew, c->phi_alloc)] : nullptr;
       gw.peer_phi_hi = peer ? c->hi.phi[idx2(c->phinew, c->phi_alloc)] : nullptr;
+      if (le) {
+	// field_leesedwards, hydro_lees_edwards: the buffer planes, from interior columns (no halo needed)
+	le_field_async(c, c->phi, &gw);
+	le_hydro_async(c, &gw);
+      }
       {
 	// field_halo(phi) + field_grad_compute + phi_force_calculation + phi_cahn_hilliard (hydro_u_halo inside)
 	ProfScope ps(c, LB200_K_PHI_SECTOR);
 	c->launches += c->k->phi_sector(S, gw, *sd, c->phi, c->u, c->grad, c->delsq, c->force, c->phinew);
+      }
+      if (le) {
+	// the 2*nhalo planes per Lees-Edwards plane whose stencils cross it, redone through the buffer planes
+	Lb200Geom gl = gw;                 // no peer stores from the patch kernels (they never touch boundary planes)
+	gl.peer_phi_lo = gl.peer_phi_hi = nullptr;
+	le_grad_async(c, &gl);
+	le_force_ch_async(c, *sd, c->le_nxlist, c->le_xlist, 1, 1, 0, c->phinew, &gl);
       }
       c->force_state = INTERIOR_ONLY;
       double * t = c->phi; c->phi = c->phinew; c->phinew = t;
@@ -1687,6 +1704,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       c->u = u_out;
       c->u_state = INTERIOR_ONLY;
     }
+    if (le) le_lb_bc_async(c);                                           // lb_data_apply_le_boundary_conditions
     c->prop_pending = 1;                                                 // lb_halo; lb_propagation (lazy)
     c->f_halo_stale = 1;
     if (peer) {
@@ -1802,6 +1820,14 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   if (nsteps <= 0) return 0;
   if (c->le.nplane > 0) {
     if (!binary || c->ndist != 1) return fail(LB200_EINVAL, "Lees-Edwards planes: lb200_step is implemented for the binary-fluid FD route (ndist = 1, free_energy symmetric)");
+    // fast mode on a fully periodic all-fluid lattice: the halo-free step with plane patches, provided every plane
+    // patch (and its +-2 stencil) stays clear of the slab boundary planes that the neighbours exchange
+    const Lb200Geom & g = c->g;
+    bool ok = (c->opt.math == LB200_MATH_FAST) && c->knob_wrap && c->knob_phi_sector && c->map_all_fluid
+      && g.per[0] && g.per[1] && g.per[2];
+    for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
+    for (int p = 0; p < c->le.nplane; p++) ok = ok && (c->le.loc[p] - g.nh - 1 >= 1) && (c->le.loc[p] + g.nh + 2 <= g.nl[0]);
+    if (ok) return step_wrap(c, cd, &sd, nsteps);
     return step_le(c, cd, sd, nsteps);
   }
   if (c->ndist == 2) {

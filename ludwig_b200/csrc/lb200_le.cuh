@@ -24,7 +24,19 @@ __device__ __forceinline__ int le_x(const Lb200LeDev & le, const Lb200Geom & g, 
     ip = le.loc[p] + 1;
     if (di < 0 && ic >= ip && ic < ip + nh && ic + di < ip) return g.nl[0] + (2 + 2*p)*nh + (ic - ip + 1) + di;
   }
-  return ic + di;
+  int x = ic + di;
+  if (g.wrap[0]) { if (x < 1) x += g.nl[0]; else if (x > g.nl[0]) x -= g.nl[0]; }
+  return x;
+}
+
+// Halo-free steps (Lb200Geom::wrap): the periodic images in y / z are read from the interior sites they mirror
+__device__ __forceinline__ int le_wy(const Lb200Geom & g, int j) {
+  if (g.wrap[1]) { if (j < 1) j += g.nl[1]; else if (j > g.nl[1]) j -= g.nl[1]; }
+  return j;
+}
+__device__ __forceinline__ int le_wz(const Lb200Geom & g, int k) {
+  if (g.wrap[2]) { if (k < 1) k += g.nl[2]; else if (k > g.nl[2]) k -= g.nl[2]; }
+  return k;
 }
 
 __device__ __forceinline__ int le_index(const Lb200Geom & g, int ic, int jc, int kc) {
@@ -55,6 +67,7 @@ le_interp_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, const
   const int ny = g.nl[1];
   const size_t ns = (size_t) g.nsites;
   const int dst = le_index(g, g.nl[0] + nh + 1 + ib, jc, kc);
+  const int ks = le_wz(g, kc);                             // source column (its z halo may be stale in halo-free steps)
 
   if (CUBIC) {
     const int j0 = 1 + (jc - jdy - 3 + 2*ny) % ny;
@@ -64,8 +77,8 @@ le_interp_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, const
     const double w0 = ip.w[sgn][0], w1 = ip.w[sgn][1], w2 = ip.w[sgn][2], w3 = ip.w[sgn][3];
     for (int n = 0; n < ncomp; n++) {
       const double * d = data + n*ns;
-      data[n*ns + dst] = - w0*d[le_index(g, ic, j0, kc)] + w1*d[le_index(g, ic, j1, kc)]
-	- w2*d[le_index(g, ic, j2, kc)] + w3*d[le_index(g, ic, j3, kc)];
+      data[n*ns + dst] = - w0*d[le_index(g, ic, j0, ks)] + w1*d[le_index(g, ic, j1, ks)]
+	- w2*d[le_index(g, ic, j2, ks)] + w3*d[le_index(g, ic, j3, ks)];
     }
   }
   else {
@@ -75,7 +88,7 @@ le_interp_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, const
     for (int n = 0; n < ncomp; n++) {
       const double * d = data + n*ns;
       const double ule = (n == 1) ? le.uy*(sgn ? 1 : -1) : 0.0;
-      data[n*ns + dst] = ule + d[le_index(g, ic, j1, kc)]*fr + d[le_index(g, ic, j2, kc)]*omfr;
+      data[n*ns + dst] = ule + d[le_index(g, ic, j1, ks)]*fr + d[le_index(g, ic, j2, ks)]*omfr;
     }
   }
 }
@@ -107,21 +120,21 @@ le_grad_planes_kernel(const Lb200Geom g, const int ne, const int * __restrict__ 
   const int jc = 1 - ne + q/ez;
   const int kc = 1 - ne + q%ez;
   const int xm = trip[3*blockIdx.y + 0], xc = trip[3*blockIdx.y + 1], xp = trip[3*blockIdx.y + 2];
-  const int ys = g.ys;
   const size_t ns = (size_t) g.nsites;
   const double r9 = (1.0/9.0);
-  const int im = le_index(g, xm, jc, kc), index = le_index(g, xc, jc, kc), ipl = le_index(g, xp, jc, kc);
+  const int index = le_index(g, xc, jc, kc);
+  const int jm = le_wy(g, jc - 1), jp = le_wy(g, jc + 1), km = le_wz(g, kc - 1), kp = le_wz(g, kc + 1);
 
   double m_mm, m_m0, m_mp, m_0m, m_00, m_0p, m_pm, m_p0, m_pp;
   double c_mm, c_m0, c_mp, c_0m, c_00, c_0p, c_pm, c_p0, c_pp;
   double p_mm, p_m0, p_mp, p_0m, p_00, p_0p, p_pm, p_p0, p_pp;
-#define LB200_LOAD_PLANE(P, base) \
-  P##_mm = field[(base)-ys-1]; P##_m0 = field[(base)-ys]; P##_mp = field[(base)-ys+1]; \
-  P##_0m = field[(base)   -1]; P##_00 = field[(base)   ]; P##_0p = field[(base)   +1]; \
-  P##_pm = field[(base)+ys-1]; P##_p0 = field[(base)+ys]; P##_pp = field[(base)+ys+1]
-  LB200_LOAD_PLANE(m, im);
-  LB200_LOAD_PLANE(c, index);
-  LB200_LOAD_PLANE(p, ipl);
+#define LB200_LOAD_PLANE(P, X) \
+  P##_mm = field[le_index(g, X, jm, km)]; P##_m0 = field[le_index(g, X, jm, kc)]; P##_mp = field[le_index(g, X, jm, kp)]; \
+  P##_0m = field[le_index(g, X, jc, km)]; P##_00 = field[le_index(g, X, jc, kc)]; P##_0p = field[le_index(g, X, jc, kp)]; \
+  P##_pm = field[le_index(g, X, jp, km)]; P##_p0 = field[le_index(g, X, jp, kc)]; P##_pp = field[le_index(g, X, jp, kp)]
+  LB200_LOAD_PLANE(m, xm);
+  LB200_LOAD_PLANE(c, xc);
+  LB200_LOAD_PLANE(p, xp);
 #undef LB200_LOAD_PLANE
 
   grad[0*ns + index] = 0.5*r9*
@@ -281,10 +294,11 @@ le_force_ch_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, con
   if (kc > g.nl[2] || jc > g.nl[1]) return;
 
   const size_t ns = (size_t) g.nsites;
-  const int ys = g.ys;
   const int s = le_index(g, ic, jc, kc);
   const int sxm = le_index(g, le_x(le, g, ic, -1), jc, kc);
   const int sxp = le_index(g, le_x(le, g, ic, +1), jc, kc);
+  const int sym = le_index(g, ic, le_wy(g, jc - 1), kc), syp = le_index(g, ic, le_wy(g, jc + 1), kc);
+  const int szm = le_index(g, ic, jc, le_wz(g, kc - 1)), szp = le_index(g, ic, jc, le_wz(g, kc + 1));
 
   // which plane (if any) this site touches: below (ic == loc) or above (ic == loc + 1)
   int pl = -1, side = -1;
@@ -297,10 +311,10 @@ le_force_ch_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, con
     const SiteFE s0 = load_fe(phi, grad, delsq, ns, s);
     const SiteFE xm = load_fe(phi, grad, delsq, ns, sxm);
     const SiteFE xp = load_fe(phi, grad, delsq, ns, sxp);
-    const SiteFE ym = load_fe(phi, grad, delsq, ns, s - ys);
-    const SiteFE yp = load_fe(phi, grad, delsq, ns, s + ys);
-    const SiteFE zm = load_fe(phi, grad, delsq, ns, s - 1);
-    const SiteFE zp = load_fe(phi, grad, delsq, ns, s + 1);
+    const SiteFE ym = load_fe(phi, grad, delsq, ns, sym);
+    const SiteFE yp = load_fe(phi, grad, delsq, ns, syp);
+    const SiteFE zm = load_fe(phi, grad, delsq, ns, szm);
+    const SiteFE zp = load_fe(phi, grad, delsq, ns, szp);
     double p0[3], p1[3], fluxe[3], fluxw[3], fluxy[3], fluxym[3], fluxz[3], fluxzm[3];
     symm_pcol<0>(sp, s0, p0);
     symm_pcol<0>(sp, xm, p1);
@@ -330,18 +344,21 @@ le_force_ch_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, con
   if (DO_CH) {
     const double M = sp.mobility;
     const double ph_c = phi[s];
-    const double ph_ym = phi[s - ys], ph_yp = phi[s + ys], ph_zm = phi[s - 1], ph_zp = phi[s + 1];
+    const double ph_ym = phi[sym], ph_yp = phi[syp], ph_zm = phi[szm], ph_zp = phi[szp];
     const double d_c = delsq[s];
     const double mu0 = symm_mu(sp, ph_c, d_c);
     double ph_ym2 = 0.0, ph_yp2 = 0.0, ph_zm2 = 0.0, ph_zp2 = 0.0;
-    if (ORDER == 3) { ph_ym2 = phi[s - 2*ys]; ph_yp2 = phi[s + 2*ys]; ph_zm2 = phi[s - 2]; ph_zp2 = phi[s + 2]; }
-    const double uy_c = u[1*ns + s], uy_ym = u[1*ns + s - ys], uy_yp = u[1*ns + s + ys];
-    const double uz_c = u[2*ns + s], uz_zm = u[2*ns + s - 1],  uz_zp = u[2*ns + s + 1];
+    if (ORDER == 3) {
+      ph_ym2 = phi[le_index(g, ic, le_wy(g, jc - 2), kc)]; ph_yp2 = phi[le_index(g, ic, le_wy(g, jc + 2), kc)];
+      ph_zm2 = phi[le_index(g, ic, jc, le_wz(g, kc - 2))]; ph_zp2 = phi[le_index(g, ic, jc, le_wz(g, kc + 2))];
+    }
+    const double uy_c = u[1*ns + s], uy_ym = u[1*ns + sym], uy_yp = u[1*ns + syp];
+    const double uz_c = u[2*ns + s], uz_zm = u[2*ns + szm], uz_zp = u[2*ns + szp];
     double mk = 1.0, mkyp = 1.0, mkym = 1.0, mkzp = 1.0, mkzm = 1.0;
     if (status) {
       mk = (status[s] == 0);
-      mkym = (status[s - ys] == 0); mkyp = (status[s + ys] == 0);
-      mkzm = (status[s - 1] == 0);  mkzp = (status[s + 1] == 0);
+      mkym = (status[sym] == 0); mkyp = (status[syp] == 0);
+      mkzm = (status[szm] == 0); mkzp = (status[szp] == 0);
     }
 
     double fw = le_ch_xflux<ORDER, true>(g, le, sp, phi, delsq, u, status, ic, jc, kc);
@@ -361,19 +378,19 @@ le_force_ch_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, con
     }
 
     double fy = adv_face<ORDER, false>(uy_c, uy_yp, ph_ym, ph_c, ph_yp, ph_yp2);
-    fy -= M*(symm_mu(sp, ph_yp, delsq[s + ys]) - mu0);
+    fy -= M*(symm_mu(sp, ph_yp, delsq[syp]) - mu0);
     fy -= M*sp.gm[1];
     if (status) fy *= mk*mkyp;
     double fym = adv_face<ORDER, false>(uy_ym, uy_c, ph_ym2, ph_ym, ph_c, ph_yp);
-    fym -= M*(mu0 - symm_mu(sp, ph_ym, delsq[s - ys]));
+    fym -= M*(mu0 - symm_mu(sp, ph_ym, delsq[sym]));
     fym -= M*sp.gm[1];
     if (status) fym *= mkym*mk;
     double fz = adv_face<ORDER, false>(uz_c, uz_zp, ph_zm, ph_c, ph_zp, ph_zp2);
-    fz -= M*(symm_mu(sp, ph_zp, delsq[s + 1]) - mu0);
+    fz -= M*(symm_mu(sp, ph_zp, delsq[szp]) - mu0);
     fz -= M*sp.gm[2];
     if (status) fz *= mk*mkzp;
     double fzm = adv_face<ORDER, false>(uz_zm, uz_c, ph_zm2, ph_zm, ph_c, ph_zp);
-    fzm -= M*(mu0 - symm_mu(sp, ph_zm, delsq[s - 1]));
+    fzm -= M*(mu0 - symm_mu(sp, ph_zm, delsq[szm]));
     fzm -= M*sp.gm[2];
     if (status) fzm *= mkzm*mk;
 

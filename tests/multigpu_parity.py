@@ -29,23 +29,30 @@ def main():
     reduced = 0 if len(sys.argv) < 3 else int(sys.argv[2])
     peer = 1 if len(sys.argv) < 4 else int(sys.argv[3])
     binary = 1 if len(sys.argv) < 5 else int(sys.argv[4])
+    le = 0 if len(sys.argv) < 6 else int(sys.argv[5])          # Lees-Edwards planes per slab (plane speed 0.05)
+    if le:
+        nxl = 8*le
     nglobal = (nxl * world, ny, nz)
     nhalo = 2
-    orc_g = Oracle(nglobal, nhalo=nhalo, periodic=periodic)
+    orc_g = Oracle(nglobal, nhalo=nhalo, periodic=periodic, le_nplanes=le*world, le_uy=0.05)
     st = seeded_state(orc_g, seed=21)
     fg = (1e-6, -2e-6, 5e-7)
 
-    # my slab of the initial state
-    orc_l = Oracle((nxl, ny, nz), nhalo=nhalo)
+    # my slab of the initial state (field arrays of a Lees-Edwards run carry buffer planes: zero here, rebuilt
+    # from the interior every step)
+    orc_l = Oracle((nxl, ny, nz), nhalo=nhalo, le_nplanes=le, le_uy=0.05)
     def slab(a):
-        v = a.reshape((-1,) + orc_g.nall)
-        out = np.zeros((v.shape[0],) + orc_l.nall)
+        v = a.reshape((a.shape[0], -1) + orc_g.nall[1:])
+        is_field = le and a.shape[1] == orc_g.nsites          # distributions never carry buffer planes
+        nxa = orc_l.nall[0] + (orc_l.nxbuffer if is_field else 0)
+        out = np.zeros((v.shape[0], nxa) + orc_l.nall[1:])
         x0 = rank * nxl
         out[:, nhalo:nhalo + nxl] = v[:, nhalo + x0:nhalo + x0 + nxl]
         return out.reshape(v.shape[0], -1)
 
     sim = lb.Lb200((nxl, ny, nz), nhalo=nhalo, periodic=periodic, have_phi=True, math=lb.MATH_STRICT, device=local,
-                   halo_scheme=lb.HALO_REDUCED if reduced else lb.HALO_FULL, cart_size=world, cart_rank=rank)
+                   halo_scheme=lb.HALO_REDUCED if reduced else lb.HALO_FULL, cart_size=world, cart_rank=rank,
+                   le_nplanes=le*world, le_uy=0.05)
     ids = [sim.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     sim.nccl_init(ids[0], world, rank)
@@ -72,7 +79,10 @@ def main():
     dist.all_gather_object(gathered, mine)
     ok = True
     if rank == 0:
-        if binary:
+        if le:
+            orc_g.le_step(orc_g.collide_param(0, 1.0, ETA, force=fg), orc_g.symm_param(adv_order=3, **BINARY), 0, nsteps,
+                          st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+        elif binary:
             orc_g.step(orc_g.collide_param(0, 1.0, ETA, force=fg), orc_g.symm_param(adv_order=3, **BINARY), 1, nsteps,
                        st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"], halo_reduced=reduced)
         else:

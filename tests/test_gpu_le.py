@@ -120,7 +120,7 @@ def test_le_lb_bc_other_models(nvel):
     assert np.array_equal(orc.interior(got), orc.interior(f))
 
 
-def _run_steps(n, nplanes, order, math, nsteps, seed=13):
+def _run_steps(n, nplanes, order, math, nsteps, seed=13, wrap=1):
     orc, sim, sp_o, sp_g = make(n, nplanes, order, math)
     f = np.zeros((19, orc.nsites_lb))
     orc.le_init_shear_profile(1.0, ETA, f)
@@ -129,6 +129,7 @@ def _run_steps(n, nplanes, order, math, nsteps, seed=13):
     z = lambda k: np.zeros((k, orc.nsites))
     u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
     with sim:
+        sim.set_knob(lb.KNOB_WRAP, wrap)
         sim.put(lb.F, f); sim.put(lb.PHI, phi)
         sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), sp_g, nsteps)
         got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO),
@@ -146,9 +147,14 @@ def test_le_steps_strict_bit_exact(n, nplanes, order):
         assert np.array_equal(orc.interior(got[k]), orc.interior(want[k])), k
 
 
-@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 16, 40), 1, 3), ((24, 16, 16), 2, 2), ((32, 32, 32), 2, 3)])
-def test_le_steps_fast_tolerance(n, nplanes, order):
-    orc, sp, got, want = _run_steps(n, nplanes, order, lb.MATH_FAST, 20)
+@pytest.mark.parametrize("wrap", [1, 0])
+@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 16, 40), 1, 3), ((24, 16, 16), 2, 2), ((32, 32, 32), 2, 3),
+                                             ((12, 16, 16), 2, 3)])
+def test_le_steps_fast_tolerance(n, nplanes, order, wrap):
+    """wrap = 1: the halo-free step (periodic images read in-kernel) with the plane patches; wrap = 0 (and the last
+    shape, whose planes sit too close to the x boundary for the halo-free step): the reference's step structure with
+    halo kernels, fused phi sector for the bulk + plane patches"""
+    orc, sp, got, want = _run_steps(n, nplanes, order, lb.MATH_FAST, 20, wrap=wrap)
     for k in want:
         assert close_fast(orc.interior(got[k]), orc.interior(want[k])), (k, np.abs(orc.interior(got[k]) - orc.interior(want[k])).max())
 

@@ -34,3 +34,21 @@ def test_slab_decomposition_matches_single_domain_oracle(periodic, reduced, peer
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0
     assert "MISMATCH" not in r.stdout and "OK" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("le", [1, 2])
+def test_lees_edwards_slabs_match_single_domain_oracle(le):
+    """Lees-Edwards sheared binary fluid (BASELINE config 5) on x-slabs, `le` planes per GPU: lb200_step and the
+    individual entry points over 2 (4) GPUs == the undecomposed Lees-Edwards oracle, bit for bit."""
+    n = ngpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29535", os.path.join(HERE, "multigpu_parity.py"),
+           "111", "0", "0", "1", str(le)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+    assert "MISMATCH" not in r.stdout and "OK" in r.stdout
