@@ -15,7 +15,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(HERE, ".."))
 
 import ludwig_b200 as lb  # noqa: E402
-from common import BINARY, ETA, seeded_state  # noqa: E402
+from common import BINARY, ETA, close_fast, seeded_state  # noqa: E402
 from oracle import Oracle  # noqa: E402
 
 
@@ -30,6 +30,7 @@ def main():
     peer = 1 if len(sys.argv) < 4 else int(sys.argv[3])
     binary = 1 if len(sys.argv) < 5 else int(sys.argv[4])
     le = 0 if len(sys.argv) < 6 else int(sys.argv[5])          # Lees-Edwards planes per slab (plane speed 0.05)
+    fast = 0 if len(sys.argv) < 7 else int(sys.argv[6])        # 1: LB200_MATH_FAST, compared within tolerance
     if le:
         nxl = 8*le
     nglobal = (nxl * world, ny, nz)
@@ -50,7 +51,7 @@ def main():
         out[:, nhalo:nhalo + nxl] = v[:, nhalo + x0:nhalo + x0 + nxl]
         return out.reshape(v.shape[0], -1)
 
-    sim = lb.Lb200((nxl, ny, nz), nhalo=nhalo, periodic=periodic, have_phi=True, math=lb.MATH_STRICT, device=local,
+    sim = lb.Lb200((nxl, ny, nz), nhalo=nhalo, periodic=periodic, have_phi=True, math=lb.MATH_FAST if fast else lb.MATH_STRICT, device=local,
                    halo_scheme=lb.HALO_REDUCED if reduced else lb.HALO_FULL, cart_size=world, cart_rank=rank,
                    le_nplanes=le*world, le_uy=0.05)
     ids = [sim.nccl_unique_id() if rank == 0 else None]
@@ -92,7 +93,7 @@ def main():
             if not binary and k in ("phi", "force"):
                 continue
             full = np.concatenate([g[k] for g in gathered], axis=1)
-            same = np.array_equal(full, orc_g.interior(st[k]))
+            same = close_fast(full, orc_g.interior(st[k])) if fast else np.array_equal(full, orc_g.interior(st[k]))
             print(f"multigpu parity world={world} periodic={periodic} reduced={reduced} {k}: {'OK' if same else 'MISMATCH'}", flush=True)
             ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")
