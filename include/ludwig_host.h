@@ -81,13 +81,31 @@ int physics_eta_bulk(physics_t * phys, double * eta);
 int physics_fbody(physics_t * phys, double f[3]);
 int physics_mobility(physics_t * phys, double * mobility);
 int physics_grad_mu(physics_t * phys, double gm[3]);
+/* time control, src/physics.c:600-670: the Lees-Edwards plane displacement is a function of these */
+int physics_control_init_time(physics_t * phys, int nstart, int nstep);
+int physics_control_next_step(physics_t * phys);
+int physics_control_timestep(physics_t * phys);
+int physics_control_time(physics_t * phys, double * t);
 
-/* ---- Lees-Edwards (zero planes only): src/leesedwards.h:26-29 ------------------------------ */
+/* ---- Lees-Edwards planes, steady shear: src/leesedwards.h:26-83, src/lees_edwards_options.h:23-38 ----------
+ * Create the lees_edw_t straight after cs_init (as src/ludwig.c does): the device lattice of the coordinate
+ * system is laid out with the buffer planes of the planes it finds. */
 typedef struct lees_edw_s lees_edw_t;
+typedef enum lees_edw_enum {LE_SHEAR_TYPE_INVALID, LE_SHEAR_TYPE_STEADY, LE_SHEAR_TYPE_OSCILLATORY} lees_edw_enum_t;
 typedef struct lees_edw_options_s {int nplanes; int type; int period; int nt0; double uy;} lees_edw_options_t;
 int lees_edw_create(pe_t * pe, cs_t * cs, const lees_edw_options_t * opts, lees_edw_t ** le);
 int lees_edw_free(lees_edw_t * le);
 int lees_edw_nplane_total(lees_edw_t * le);
+int lees_edw_nplane_local(lees_edw_t * le);
+int lees_edw_plane_uy(lees_edw_t * le, double * uy);
+int lees_edw_nxbuffer(lees_edw_t * le, int * nxb);
+int lees_edw_nsites(lees_edw_t * le, int * nsites);
+int lees_edw_index(lees_edw_t * le, int ic, int jc, int kc);
+int lees_edw_plane_location(lees_edw_t * le, int plane);
+int lees_edw_ic_to_buff(lees_edw_t * le, int ic, int di);
+int lees_edw_ibuff_to_real(lees_edw_t * le, int ib);
+int lees_edw_shear_rate(lees_edw_t * le, double * gammadot);
+int lees_edw_steady_uy(lees_edw_t * le, int ic, double * uy);
 
 /* ---- memory.h addressing, SOA: src/memory.h:182-195 ---------------------------------------- */
 #define addr_rank0(nsites, index) (index)
@@ -147,6 +165,9 @@ int lb_f_set(lb_t * lb, int index, int p, int n, double f);
 int lb_0th_moment(lb_t * lb, int index, lb_dist_enum_t nd, double * rho);
 int lb_1st_moment(lb_t * lb, int index, lb_dist_enum_t nd, double g[3]);
 int lb_1st_moment_equilib_set(lb_t * lb, int index, double rho, double u[3]);
+/* src/model_le.h: plane-crossing populations after the collision; steady shear profile initial condition */
+int lb_data_apply_le_boundary_conditions(lb_t * lb, lees_edw_t * le);
+int lb_le_init_shear_profile(lb_t * lb, lees_edw_t * le);
 int lb_collision_relaxation_set(lb_t * lb, lb_relaxation_enum_t nrelax);     /* src/collision.h:30 */
 int lb_collide_param_commit(lb_t * lb);                                      /* src/lb_data.h:166 */
 
@@ -176,6 +197,7 @@ int field_memcpy(field_t * obj, tdpMemcpyKind flag);
 int field_halo(field_t * obj);
 typedef enum field_halo_enum {FIELD_HALO_HOST, FIELD_HALO_TARGET, FIELD_HALO_OPENMP} field_halo_enum_t;   /* src/field_options.h:22-24 */
 int field_halo_swap(field_t * obj, field_halo_enum_t flag);
+int field_leesedwards(field_t * obj);                                        /* src/field.h:106 */
 int field_nf(field_t * obj, int * nop);
 int field_scalar(field_t * obj, int index, double * phi);
 int field_scalar_set(field_t * obj, int index, double phi);
@@ -234,6 +256,7 @@ int hydro_create(pe_t * pe, cs_t * cs, lees_edw_t * le, const hydro_options_t * 
 int hydro_free(hydro_t * obj);
 int hydro_memcpy(hydro_t * obj, tdpMemcpyKind flag);
 int hydro_u_halo(hydro_t * obj);
+int hydro_lees_edwards(hydro_t * obj);                                       /* src/hydro.h:57 */
 int hydro_f_zero(hydro_t * obj, const double fzero[3]);
 int hydro_u_zero(hydro_t * obj, const double uzero[3]);
 int hydro_u(hydro_t * obj, int index, double u[3]);           /* src/hydro_impl.h */

@@ -76,6 +76,7 @@ struct cs_s {
   field_t * phi;
   field_grad_t * phi_grad;
   map_t * map;
+  lees_edw_t * le;
   lb200_t * ctx;
 };
 
@@ -143,6 +144,9 @@ int cs_strides(cs_t * cs, int * xs, int * ys, int * zs) {
   return 0;
 }
 
+static void b200_le_options(cs_t * cs, lb200_options_t * o);
+static void b200_time_sync(cs_t * cs);
+
 lb200_t * cs_b200_context(cs_t * cs) {
   assert(cs);
   assert(cs->initialised);
@@ -160,6 +164,7 @@ lb200_t * cs_b200_context(cs_t * cs) {
     o.device = -1;
     o.cart_size = 1;
     o.cart_rank = 0;
+    b200_le_options(cs, &o);
     if (lb200_create(&o, &cs->ctx) != 0) pe_fatal(cs->pe, "lb200_create: %s\n", lb200_last_error());
   }
   return cs->ctx;
@@ -177,6 +182,7 @@ static int b200_kind(tdpMemcpyKind flag) {
 
 struct physics_s {
   double rho0, eta_shear, eta_bulk, fbody[3], mobility, grad_mu[3];
+  int t_start, nsteps, t_current;
 };
 
 static physics_t * physics_static = NULL;
@@ -207,20 +213,94 @@ int physics_fbody(physics_t * p, double f[3]) { for (int a = 0; a < 3; a++) f[a]
 int physics_mobility(physics_t * p, double * m) { *m = p->mobility; return 0; }
 int physics_grad_mu(physics_t * p, double gm[3]) { for (int a = 0; a < 3; a++) gm[a] = p->grad_mu[a]; return 0; }
 
-/* ---- Lees-Edwards: zero planes only ------------------------------------------------------------- */
+/* src/physics.c:600-670 */
+int physics_control_init_time(physics_t * p, int nstart, int nstep) { p->t_start = nstart; p->nsteps = nstep; p->t_current = nstart; return 0; }
+int physics_control_next_step(physics_t * p) { p->t_current += 1; return (p->t_start + p->nsteps - p->t_current + 1); }
+int physics_control_timestep(physics_t * p) { return p->t_current; }
+int physics_control_time(physics_t * p, double * t) { *t = 1.0*(p->t_start + p->t_current - 1.0); return 0; }
 
-struct lees_edw_s {pe_t * pe; cs_t * cs; int nplanes;};
+/* ---- Lees-Edwards planes (steady shear): src/leesedwards.c -------------------------------------- */
+
+struct lees_edw_s {pe_t * pe; cs_t * cs; lees_edw_options_t opts; lb200_options_t o;};
+
+/* the plane / buffer arithmetic is the library's (lb200_le_plane_location, lb200_le_ic_to_buff) */
+static void le_fill_options(cs_t * cs, const lees_edw_options_t * opts, lb200_options_t * o) {
+  memset(o, 0, sizeof(*o));
+  for (int a = 0; a < 3; a++) { o->nlocal[a] = cs->nlocal[a]; o->periodic[a] = cs->periodic[a]; }
+  o->nhalo = cs->nhalo;
+  o->cart_size = 1;
+  o->le_nplanes = opts->nplanes; o->le_uy = opts->uy; o->le_nt0 = opts->nt0;
+}
 
 int lees_edw_create(pe_t * pe, cs_t * cs, const lees_edw_options_t * opts, lees_edw_t ** ple) {
   lees_edw_t * le = (lees_edw_t *) calloc(1, sizeof(lees_edw_t));
   if (le == NULL) pe_fatal(pe, "calloc(lees_edw_t) failed\n");
-  if (opts && opts->nplanes != 0) pe_fatal(pe, "Lees-Edwards planes are outside this build (SURVEY 8f)\n");
   le->pe = pe; le->cs = cs;
+  if (opts) le->opts = *opts;
+  if (le->opts.nplanes > 0) {
+    if (cs->ctx != NULL) pe_fatal(pe, "lees_edw_create: create the planes before the first device use of the coordinate system\n");
+    if (le->opts.type == LE_SHEAR_TYPE_OSCILLATORY) pe_fatal(pe, "Oscillatory shear is outside this build\n");
+    if (cs->ntotal[X] % le->opts.nplanes) pe_fatal(pe, "Number of planes must divide system size\n");     /* :249-253 */
+    le_fill_options(cs, &le->opts, &le->o);
+    for (int p = 0; p < le->opts.nplanes; p++) {
+      int ic = lb200_le_plane_location(&le->o, p);
+      if (ic <= cs->nhalo || ic > cs->nlocal[X] - cs->nhalo) pe_fatal(pe, "Wall at domain boundary\n");    /* :449-460 */
+    }
+    cs->le = le;
+  }
+  else {
+    le_fill_options(cs, &le->opts, &le->o);
+  }
   *ple = le;
   return 0;
 }
-int lees_edw_free(lees_edw_t * le) { free(le); return 0; }
-int lees_edw_nplane_total(lees_edw_t * le) { return le ? le->nplanes : 0; }
+int lees_edw_free(lees_edw_t * le) { if (le && le->cs && le->cs->le == le) le->cs->le = NULL; free(le); return 0; }
+int lees_edw_nplane_total(lees_edw_t * le) { return le ? le->opts.nplanes : 0; }
+int lees_edw_nplane_local(lees_edw_t * le) { return le ? le->opts.nplanes : 0; }
+int lees_edw_plane_uy(lees_edw_t * le, double * uy) { *uy = le->opts.uy; return 0; }
+int lees_edw_nxbuffer(lees_edw_t * le, int * nxb) { *nxb = 2*le->cs->nhalo*le->opts.nplanes; return 0; }
+int lees_edw_nsites(lees_edw_t * le, int * nsites) {
+  cs_t * cs = le->cs;
+  *nsites = (cs->nall[X] + 2*cs->nhalo*le->opts.nplanes)*cs->nall[Y]*cs->nall[Z];        /* :485-495 */
+  return 0;
+}
+int lees_edw_index(lees_edw_t * le, int ic, int jc, int kc) { return cs_index(le->cs, ic, jc, kc); }    /* :783-798 */
+int lees_edw_plane_location(lees_edw_t * le, int np) { return lb200_le_plane_location(&le->o, np); }
+int lees_edw_ic_to_buff(lees_edw_t * le, int ic, int di) { return lb200_le_ic_to_buff(&le->o, ic, di); }
+int lees_edw_ibuff_to_real(lees_edw_t * le, int ib) {                                                   /* :1008-1022 */
+  const int nh = le->cs->nhalo;
+  return lees_edw_plane_location(le, ib/(2*nh)) - (nh - 1) + ib % (2*nh);
+}
+int lees_edw_shear_rate(lees_edw_t * le, double * gammadot) {                                           /* :759-769 */
+  *gammadot = le->opts.uy*le->opts.nplanes/(1.0*le->cs->ntotal[X]);
+  return 0;
+}
+int lees_edw_steady_uy(lees_edw_t * le, int ic, double * uy) {                                          /* :508-533 */
+  const double dx_sep = 1.0*le->cs->ntotal[X]/le->opts.nplanes, dx_min = 0.5*dx_sep;
+  double gammadot, xglobal = le->cs->noffset[X] + (double) ic - 0.5;
+  int nplane = (int) ((dx_min + xglobal)/dx_sep);
+  lees_edw_shear_rate(le, &gammadot);
+  *uy = xglobal*gammadot - le->opts.uy*nplane;
+  return 0;
+}
+
+static void b200_le_options(cs_t * cs, lb200_options_t * o) {
+  if (cs->le == NULL) return;
+  o->le_nplanes = cs->le->opts.nplanes; o->le_uy = cs->le->opts.uy; o->le_nt0 = cs->le->opts.nt0;
+}
+
+/* the device context keeps its own copy of the step counter (the reference's kernels read the singleton) */
+static void b200_time_sync(cs_t * cs) {
+  if (cs->le == NULL || physics_static == NULL) return;
+  b200_check(cs->pe, lb200_physics_control_time_set(cs_b200_context(cs), physics_static->t_start, physics_static->t_current),
+	     "physics_control_time");
+}
+
+static int le_nsites_or(cs_t * cs, lees_edw_t * le) {
+  int ns = cs->nsites;
+  if (le && le->opts.nplanes > 0) lees_edw_nsites(le, &ns);
+  return ns;
+}
 
 /* ---- lb_t -------------------------------------------------------------------------------------------- */
 
@@ -322,6 +402,51 @@ int lb_propagation(lb_t * lb) {
   return 0;
 }
 
+/* src/model_le.c:78-180 */
+int lb_data_apply_le_boundary_conditions(lb_t * lb, lees_edw_t * le) {
+  assert(lb); assert(le);
+  if (lees_edw_nplane_total(le) == 0) return 0;
+  b200_time_sync(lb->cs);
+  b200_check(lb->pe, lb200_lb_le_apply_boundary_conditions(cs_b200_context(lb->cs)), "lb_data_apply_le_boundary_conditions");
+  return 0;
+}
+
+/* src/model_le.c:652-714: host distributions consistent with a steady linear shear profile */
+int lb_le_init_shear_profile(lb_t * lb, lees_edw_t * le) {
+  physics_t * phys = NULL;
+  int nlocal[3];
+  double rho0, eta, u[3] = {0.0, 0.0, 0.0}, gradu[3][3] = {{0.0}};
+  const double cs2 = lb->model.cs2, rcs2 = 1.0/cs2;
+  assert(lb); assert(le);
+  physics_ref(&phys);
+  physics_rho0(phys, &rho0);
+  physics_eta_shear(phys, &eta);
+  cs_nlocal(lb->cs, nlocal);
+  lees_edw_shear_rate(le, &gradu[X][Y]);
+  for (int ic = 1; ic <= nlocal[X]; ic++) {
+    lees_edw_steady_uy(le, ic, &u[Y]);
+    for (int jc = 1; jc <= nlocal[Y]; jc++) {
+      for (int kc = 1; kc <= nlocal[Z]; kc++) {
+	int index = cs_index(lb->cs, ic, jc, kc);
+	for (int p = 0; p < lb->nvel; p++) {
+	  double f, cdotu = 0.0, sdotq = 0.0;
+	  for (int i = 0; i < 3; i++) {
+	    cdotu += lb->model.cv[p][i]*u[i];
+	    for (int j = 0; j < 3; j++) {
+	      double dij = (i == j);
+	      double qij = lb->model.cv[p][i]*lb->model.cv[p][j] - cs2*dij;
+	      sdotq += (rho0*u[i]*u[j] - eta*gradu[i][j])*qij;
+	    }
+	  }
+	  f = lb->model.wv[p]*(rho0 + rcs2*rho0*cdotu + 0.5*rcs2*rcs2*sdotq);
+	  lb_f_set(lb, index, p, 0, f);
+	}
+      }
+    }
+  }
+  return 0;
+}
+
 int lb_collision_relaxation_set(lb_t * lb, lb_relaxation_enum_t nrelax) { lb->nrelax = nrelax; return 0; }
 
 int lb_f(lb_t * lb, int index, int p, int n, double * f) {
@@ -392,7 +517,7 @@ static int field_create_tagged(pe_t * pe, cs_t * cs, lees_edw_t * le, const char
   if (obj == NULL) pe_fatal(pe, "calloc(field_t) failed\n");
   obj->nf = opts->ndata; obj->nhcomm = opts->nhcomm; obj->opts = *opts;
   obj->pe = pe; obj->cs = cs; obj->le = le;
-  obj->nsites = cs->nsites;
+  obj->nsites = le_nsites_or(cs, le);                 /* src/field.c:196-197 */
   obj->name = strdup(name);
   obj->data = (double *) calloc((size_t) obj->nf*obj->nsites, sizeof(double));
   if (obj->data == NULL) pe_fatal(pe, "calloc(field->data) failed\n");
@@ -430,6 +555,15 @@ int field_halo(field_t * obj) {
   if (obj->b200_array == LB200_PHI) b200_check(obj->pe, lb200_phi_halo(ctx), "field_halo");
   else if (obj->b200_array == LB200_U) b200_check(obj->pe, lb200_hydro_u_halo(ctx), "field_halo");
   else pe_fatal(obj->pe, "field_halo: field \"%s\" has no device halo in this build\n", obj->name);
+  return 0;
+}
+
+/* src/field.c:418-510 */
+int field_leesedwards(field_t * obj) {
+  if (obj->le == NULL || lees_edw_nplane_total(obj->le) == 0) return 0;
+  if (obj->b200_array != LB200_PHI) pe_fatal(obj->pe, "field_leesedwards: field \"%s\" is not device backed\n", obj->name);
+  b200_time_sync(obj->cs);
+  b200_check(obj->pe, lb200_field_leesedwards(cs_b200_context(obj->cs)), "field_leesedwards");
   return 0;
 }
 
@@ -493,6 +627,7 @@ int field_grad_compute(field_grad_t * obj) {
 }
 
 int grad_3d_27pt_fluid_d2(field_grad_t * fg) {
+  b200_time_sync(fg->field->cs);       /* with planes: field_leesedwards + d2 + grad_3d_27pt_fluid_le on the device */
   b200_check(fg->pe, lb200_phi_grad_compute(cs_b200_context(fg->field->cs)), "grad_3d_27pt_fluid_d2");
   return 0;
 }
@@ -536,7 +671,7 @@ hydro_options_t hydro_options_default(void) { return hydro_options_nhalo(1); }
 int hydro_create(pe_t * pe, cs_t * cs, lees_edw_t * le, const hydro_options_t * opts, hydro_t ** pobj) {
   hydro_t * obj = (hydro_t *) calloc(1, sizeof(hydro_t));
   if (obj == NULL) pe_fatal(pe, "calloc(hydro) failed\n");
-  obj->pe = pe; obj->cs = cs; obj->le = le; obj->nhcomm = opts->nhcomm; obj->nsite = cs->nsites;
+  obj->pe = pe; obj->cs = cs; obj->le = le; obj->nhcomm = opts->nhcomm; obj->nsite = le_nsites_or(cs, le);
   field_create_tagged(pe, cs, le, "rho", &opts->rho, LB200_RHO, &obj->rho);
   field_create_tagged(pe, cs, le, "u", &opts->u, LB200_U, &obj->u);
   field_create_tagged(pe, cs, le, "force", &opts->force, LB200_FORCE, &obj->force);
@@ -564,6 +699,14 @@ int hydro_memcpy(hydro_t * obj, tdpMemcpyKind flag) {
 }
 
 int hydro_u_halo(hydro_t * obj) { return field_halo(obj->u); }
+
+/* src/hydro.c:350-440 */
+int hydro_lees_edwards(hydro_t * obj) {
+  if (obj->le == NULL || lees_edw_nplane_total(obj->le) == 0) return 0;
+  b200_time_sync(obj->cs);
+  b200_check(obj->pe, lb200_hydro_lees_edwards(cs_b200_context(obj->cs)), "hydro_lees_edwards");
+  return 0;
+}
 
 int hydro_f_zero(hydro_t * obj, const double fzero[3]) {
   if (fzero[X] != 0.0 || fzero[Y] != 0.0 || fzero[Z] != 0.0) pe_fatal(obj->pe, "hydro_f_zero: non-zero value not supported\n");
@@ -710,7 +853,7 @@ int phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t * wall, 
   if (hydro == NULL) return 0;
   if (pth->method == FE_FORCE_METHOD_NO_FORCE) return 0;
   if (wall != NULL) pe_fatal(pe, "phi_force_calculation: walls are outside this build\n");
-  if (le && lees_edw_nplane_total(le) > 0) pe_fatal(pe, "phi_force_calculation: LE planes are outside this build\n");
+  (void) le;                       /* with planes the library uses the flux form, src/phi_force.c:91-97 */
   if (pth->method != FE_FORCE_METHOD_STRESS_DIVERGENCE) pe_fatal(pe, "Bad force method\n");
   symm_param_from(fe, &sp);
   b200_check(pe, lb200_phi_force_calculation(cs_b200_context(cs), &sp), "phi_force_calculation");
@@ -741,6 +884,7 @@ int phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t * hydro,
   if (noise != NULL || pch->info.noise) pe_fatal(pch->pe, "phi_cahn_hilliard: noise is outside this build\n");
   if (hydro == NULL) pe_fatal(pch->pe, "phi_cahn_hilliard: hydro == NULL is outside this build\n");
   symm_param_from(fe, &sp);
+  b200_time_sync(pch->cs);
   b200_check(pch->pe, lb200_phi_cahn_hilliard(cs_b200_context(pch->cs), &sp), "phi_cahn_hilliard");
   return 0;
 }

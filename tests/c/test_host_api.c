@@ -384,6 +384,127 @@ static void test_symmetric_lb(int nvel, int strict) {
   map_free(&map); hydro_free(hydro); lb_free(lb); lees_edw_free(le); physics_free(phys); cs_free(cs);
 }
 
+/* Lees-Edwards sheared binary fluid through the reference's entry points (src/ludwig.c:528-860 with planes:
+ * tests/regression/d3q19-short/serial-le3d-st7.inp at a smaller size) vs the Lees-Edwards oracle */
+static void test_lees_edwards_step(int order, int nplanes, int nsteps, int strict) {
+  cs_t * cs = NULL;
+  physics_t * phys = NULL;
+  lees_edw_t * le = NULL;
+  lb_t * lb = NULL;
+  hydro_t * hydro = NULL;
+  map_t * map = NULL;
+  field_t * phi = NULL;
+  field_grad_t * phi_grad = NULL;
+  fe_symm_t * fe = NULL;
+  pth_t * pth = NULL;
+  phi_ch_t * pch = NULL;
+  int ntotal[3] = {16, 12, 10};
+  int nlocal[3], ns, nsle;
+  unsigned int seed = 777;
+  const double zero[3] = {0.0, 0.0, 0.0};
+  const double uy = 0.05, eta = 0.1;
+
+  cs_create(pe, &cs);
+  cs_nhalo_set(cs, 2);
+  cs_ntotal_set(cs, ntotal);
+  cs_init(cs);
+  cs_nlocal(cs, nlocal);
+  cs_nsites(cs, &ns);
+  physics_create(pe, &phys);
+  physics_eta_shear_set(phys, eta);
+  physics_eta_bulk_set(phys, eta);
+  physics_mobility_set(phys, 0.15);
+  physics_control_init_time(phys, 0, nsteps);
+  { lees_edw_options_t o = {.nplanes = nplanes, .type = LE_SHEAR_TYPE_STEADY, .nt0 = 0, .uy = uy}; lees_edw_create(pe, cs, &o, &le); }
+  lees_edw_nsites(le, &nsle);
+  test_assert(nsle == (nlocal[X] + 4 + 4*nplanes)*(nlocal[Y] + 4)*(nlocal[Z] + 4));
+  test_assert(lees_edw_plane_location(le, 0) == nlocal[X]/(2*nplanes));
+  test_assert(lees_edw_ic_to_buff(le, lees_edw_plane_location(le, 0), +1) == nlocal[X] + 2 + 1 + 2);
+  { lb_data_options_t o = lb_data_options_ndim_nvel_ndist(3, 19, 1); lb_data_create(pe, cs, &o, &lb); }
+  { hydro_options_t o = hydro_options_default(); hydro_create(pe, cs, le, &o, &hydro); }
+  { map_options_t o = map_options_default(); map_create(pe, cs, &o, &map); }
+  { field_options_t o = field_options_ndata_nhalo(1, 2); field_create(pe, cs, le, "phi", &o, &phi); }
+  test_assert(phi->nsites == nsle && hydro->nsite == nsle && lb->nsite == ns);
+  field_grad_create(pe, phi, 2, &phi_grad);
+  field_grad_set(phi_grad, grad_3d_27pt_fluid_d2, NULL);
+  fe_symm_create(pe, cs, phi, phi_grad, &fe);
+  { fe_symm_param_t p = {.a = -0.0625, .b = 0.0625, .kappa = 0.04}; fe_symm_param_set(fe, p); }
+  { phi_ch_info_t o = {0}; phi_ch_create(pe, cs, le, &o, &pch); }
+  pth_create(pe, cs, FE_FORCE_METHOD_STRESS_DIVERGENCE, &pth);
+  advection_order_set(order);
+
+  lb_le_init_shear_profile(lb, le);
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++)
+	field_scalar_set(phi, cs_index(cs, ic, jc, kc), 0.1*(frand(&seed) - 0.5));
+
+  orc_geom_t g = {{nlocal[X], nlocal[Y], nlocal[Z]}, 2, {1, 1, 1}, nplanes};
+  orc_le_t ole = {uy, 0.0};
+  orc_model_t model;
+  orc_collide_param_t ocp = {ORC_RELAX_M10, 1.0, eta, eta, {0.0, 0.0, 0.0}};
+  orc_symm_param_t osp = {-0.0625, 0.0625, 0.04, 0.15, {0.0, 0.0, 0.0}, order};
+  double * of = malloc(sizeof(double)*19*ns), * ophi = malloc(sizeof(double)*nsle);
+  double * ou = calloc(3*nsle, sizeof(double)), * orho = calloc(nsle, sizeof(double)), * oforce = calloc(3*nsle, sizeof(double));
+  double * ograd = calloc(3*nsle, sizeof(double)), * odelsq = calloc(nsle, sizeof(double));
+  orc_model_create(19, &model);
+  test_assert(orc_nsites(&g) == nsle && orc_nsites_lb(&g) == ns);
+  /* the host initial condition is the reference's (oracle restatement of lb_le_init_shear_profile) */
+  orc_le_init_shear_profile(&g, &model, &ole, 1.0, eta, of);
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++)
+	for (int p = 0; p < 19; p++) test_assert(of[(size_t) p*ns + cs_index(cs, ic, jc, kc)] == lb->f[LB_ADDR(ns, 1, 19, cs_index(cs, ic, jc, kc), 0, p)]);
+  memcpy(of, lb->f, sizeof(double)*19*ns);
+  memcpy(ophi, phi->data, sizeof(double)*nsle);
+
+  map_memcpy(map, tdpMemcpyHostToDevice);
+  lb_memcpy(lb, tdpMemcpyHostToDevice);
+  field_memcpy(phi, tdpMemcpyHostToDevice);
+  while (physics_control_next_step(phys)) {
+    hydro_f_zero(hydro, zero);
+    field_halo(phi);
+    field_grad_compute(phi_grad);
+    phi_force_calculation(pe, cs, le, NULL, pth, (fe_t *) fe, map, phi, hydro);
+    phi_cahn_hilliard(pch, (fe_t *) fe, phi, hydro, map, NULL);
+    hydro_u_zero(hydro, zero);
+    lb_collide(lb, hydro, map, NULL, (fe_t *) fe, NULL);
+    lb_data_apply_le_boundary_conditions(lb, le);
+    lb_halo(lb);
+    lb_propagation(lb);
+  }
+  test_assert(physics_control_timestep(phys) == nsteps + 1);     /* the loop test advances once more, as in the reference */
+  lb_memcpy(lb, tdpMemcpyDeviceToHost);
+  field_memcpy(phi, tdpMemcpyDeviceToHost);
+  hydro_memcpy(hydro, tdpMemcpyDeviceToHost);
+
+  orc_le_step(&g, &model, &ocp, &osp, &ole, 0, nsteps, of, ophi, ou, orho, oforce, ograd, odelsq);
+
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++) {
+	int index = lees_edw_index(le, ic, jc, kc);
+	for (int p = 0; p < 19; p++) {
+	  double a = lb->f[LB_ADDR(ns, 1, 19, index, 0, p)], b = of[(size_t) p*ns + index];
+	  if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-12*0.34 + 1e-14);
+	}
+	{
+	  double a = phi->data[index], b = ophi[index];
+	  if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-12*0.05 + 1e-14);
+	}
+	for (int ia = 0; ia < 3; ia++) {
+	  double a = hydro->u->data[addr_rank1(nsle, 3, index, ia)], b = ou[(size_t) ia*nsle + index];
+	  if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-12*0.03 + 1e-14);
+	}
+      }
+  printf("PASS test_lees_edwards_step order=%d planes=%d nsteps=%d %s\n", order, nplanes, nsteps,
+	 strict ? "bit-exact" : "within tolerance");
+
+  free(of); free(ophi); free(ou); free(orho); free(oforce); free(ograd); free(odelsq);
+  pth_free(pth); phi_ch_free(pch); fe_symm_free(fe); field_grad_free(phi_grad); field_free(phi);
+  map_free(&map); hydro_free(hydro); lb_free(lb); lees_edw_free(le); physics_free(phys); cs_free(cs);
+}
+
 /* single-fluid collision + propagation steps, each relaxation scheme */
 static void test_single_fluid(int nvel, lb_relaxation_enum_t nrelax, int strict) {
   cs_t * cs = NULL;
@@ -472,6 +593,8 @@ int main(void) {
   test_binary_step(3, 5, strict);
   test_symmetric_lb(19, strict);
   test_symmetric_lb(15, strict);
+  test_lees_edwards_step(3, 2, 6, strict);
+  test_lees_edwards_step(1, 1, 6, strict);
 
   pe_free(pe);
   printf("PASS test_host_api (%s)\n", strict ? "strict" : "fast");
