@@ -70,3 +70,46 @@ def equilibrium_f(nlocal, nhalo, rho=1.0, u=(0.0, 0.0, 0.0), out=None):
         out[p, nhalo:nhalo + nlocal[0], nhalo:nhalo + nlocal[1], nhalo:nhalo + nlocal[2]] = \
             rho * WV19[p] * (1.0 + rcs2 * udotc + 0.5 * rcs2 * rcs2 * sdotq)
     return out.reshape(19, -1)
+
+
+def lc_uniaxial_q(nlocal, nhalo, director, amplitude):
+    """Q_ab = A/2 (3 n_a n_b - d_ab) on the interior for a director field n (3, Nx, Ny, Nz) (reference
+    fe_lc_q_uniaxial, src/blue_phase.c:1406-1418); compressed (XX, XY, XZ, YY, YZ), shape (5, nsites)."""
+    nall = tuple(n + 2 * nhalo for n in nlocal)
+    out = np.zeros((5,) + nall)
+    n = np.broadcast_to(np.asarray(director, dtype=np.float64), (3,) + tuple(nlocal))
+    sl = (slice(nhalo, nhalo + nlocal[0]), slice(nhalo, nhalo + nlocal[1]), slice(nhalo, nhalo + nlocal[2]))
+    for c, (a, b) in enumerate(((0, 0), (0, 1), (0, 2), (1, 1), (1, 2))):
+        d = 1.0 if a == b else 0.0
+        out[(c,) + sl] = 0.5 * amplitude * (3.0 * n[a] * n[b] - d)
+    return out.reshape(5, -1)
+
+
+def lc_twist_q(nlocal, nhalo, q0, amplitude, axis=2, noffset=(0, 0, 0)):
+    """`lc_q_initialisation twist` (= cholesteric along z): n = (cos q0 z, sin q0 z, 0) (reference
+    blue_phase_twist_init, src/blue_phase_init.c:763-823; x: n = (0, cos q0 x, sin q0 x); y: n = (cos q0 y, 0, -sin q0 y))."""
+    import math
+    n = np.zeros((3,) + tuple(nlocal))
+    coord = np.arange(1, nlocal[axis] + 1, dtype=np.float64) + noffset[axis]
+    c = np.array([math.cos(q0 * x) for x in coord])
+    s = np.array([math.sin(q0 * x) for x in coord])
+    shape = [1, 1, 1]
+    shape[axis] = -1
+    c, s = c.reshape(shape), s.reshape(shape)
+    if axis == 2:
+        n[0], n[1] = c, s
+    elif axis == 0:
+        n[1], n[2] = c, s
+    else:
+        n[0], n[2] = c, -s
+    return lc_uniaxial_q(nlocal, nhalo, n, amplitude)
+
+
+def lc_nematic_q(nlocal, nhalo, director, amplitude):
+    """`lc_q_initialisation nematic`: uniform uniaxial nematic along the (normalised) director
+    (reference blue_phase_nematic_init, src/blue_phase_init.c:836-880)."""
+    import math
+    d = [float(x) for x in director]
+    norm = math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+    n = np.array([x / norm for x in d]).reshape(3, 1, 1, 1)
+    return lc_uniaxial_q(nlocal, nhalo, n, amplitude)

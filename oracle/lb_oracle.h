@@ -155,6 +155,33 @@ void orc_le_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
 		 double * f, double * phi, double * u, double * rho, double * force,
 		 double * grad, double * delsq);
 
+/* ---- liquid crystal: Landau-de Gennes Q tensor + Beris-Edwards, oracle/lb_oracle_lc.c ----
+ * q[n*ns + i], n = XX, XY, XZ, YY, YZ; qgrad[(n*3 + a)*ns + i]; qdelsq[n*ns + i]; str[(a*3 + b)*ns + i];
+ * flux[(face*5 + n)*ns + i], face = w, e, y, z.  Redshift 1, no activity / noise / colloids. */
+typedef struct orc_lc_param_s {
+  double a0, q0, gamma, kappa0, kappa1, xi;   /* fe_lc_param_t, src/blue_phase.h:52-75 */
+  double Gamma;                               /* beris_edw_param_t.gamma: rotational diffusion constant */
+  double epsilon;                             /* dielectric anisotropy (as stored: includes 1/12pi) */
+  double e0[3];                               /* external electric field */
+} orc_lc_param_t;
+
+void orc_grad_7pt(const orc_geom_t * g, int nf, const double * field, double * grad, double * delsq);
+void orc_lc_compute_h(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3], double dsq[3][3], double h[3][3]);
+double orc_lc_compute_fed(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3]);
+void orc_lc_compute_stress(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3], double h[3][3], double s[3][3]);
+void orc_lc_stress(const orc_geom_t * g, const orc_lc_param_t * p, const double * q, const double * grad,
+		   const double * delsq, double * str);
+void orc_lc_mol_field(const orc_geom_t * g, const orc_lc_param_t * p, const double * q, const double * grad,
+		      const double * delsq, double * h);
+double orc_lc_fed_sum(const orc_geom_t * g, const orc_lc_param_t * p, const double * q, const double * grad);
+void orc_advection_nf(const orc_geom_t * g, int order, int nf, const double * u, const double * field, double * flux);
+void orc_beris_edw_update(const orc_geom_t * g, double xi, double Gamma, const double * u, const double * h,
+			  const double * flux, double * q);
+void orc_lc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+		 const orc_lc_param_t * p, int adv_order, int nsteps,
+		 double * f, double * q, double * u, double * rho, double * force,
+		 double * qgrad, double * qdelsq);
+
 #ifdef __cplusplus
 }
 #endif

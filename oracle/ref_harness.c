@@ -48,6 +48,11 @@
 #include "noise.h"
 #include "phi_lb_coupler.h"
 #include "model_le.h"
+#include "blue_phase.h"
+#include "blue_phase_init.h"
+#include "blue_phase_beris_edwards.h"
+#include "gradient_3d_7pt_fluid.h"
+#include "colloids.h"
 
 typedef struct ref_cfg_s {
   int ntotal[3];
@@ -70,6 +75,12 @@ typedef struct ref_cfg_s {
   int grad_level;      /* 0/2: field_grad level 2; 4: also grad_delsq, delsq_delsq (grad_3d_27pt_fluid_d4) */
   int le_nplanes;      /* N_LE_plane: number of Lees-Edwards planes (0 = none) */
   double le_uy;        /* LE_plane_vel (steady shear) */
+  /* free_energy lc_blue_phase (have_phi = 0): Landau-de Gennes Q tensor + Beris-Edwards, 7-point gradient */
+  int have_q;
+  double lc_a0, lc_q0, lc_gamma, lc_kappa0, lc_kappa1, lc_xi;
+  double lc_Gamma;     /* rotational diffusion constant (beris_edw_param_t.gamma) */
+  double lc_epsilon;   /* dielectric anisotropy as stored in fe_lc_param_t (includes the 1/12pi) */
+  double lc_e0[3];     /* external electric field */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -87,13 +98,19 @@ typedef struct ref_sim_s {
   fe_symm_t * fe;
   pth_t * pth;
   phi_ch_t * pch;
+  field_t * q;
+  field_grad_t * q_grad;
+  fe_lc_t * fe_lc;
+  beris_edw_t * be;
+  colloids_info_t * cinfo;
   int nsites;          /* cs_nsites: lb->f, map */
   int nsites_le;       /* lees_edw_nsites: hydro, fields, gradients, fluxes (== nsites without planes) */
 } ref_sim_t;
 
 enum {REF_F = 0, REF_PHI = 1, REF_U = 2, REF_RHO = 3, REF_FORCE = 4,
       REF_GRAD = 5, REF_DELSQ = 6, REF_STR = 7, REF_FLUX = 8, REF_MAP = 9,
-      REF_GRAD_DELSQ = 10, REF_DELSQ_DELSQ = 11};
+      REF_GRAD_DELSQ = 10, REF_DELSQ_DELSQ = 11,
+      REF_Q = 12, REF_QGRAD = 13, REF_QDELSQ = 14, REF_H = 15};
 
 static int mpi_up = 0;
 
@@ -177,6 +194,30 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
       advection_order_set(cfg->adv_order);
     }
   }
+  else if (cfg->have_q) {
+    /* /root/reference/src/ludwig.c:1598-1666, src/blue_phase_rt.c:50-410 */
+    field_options_t opts = field_options_ndata_nhalo(NQAB, cfg->nhalo);
+    fe_lc_param_t p = {0};
+    beris_edw_param_t bp = {0};
+    int ncell[3] = {2, 2, 2};
+    field_create(s->pe, s->cs, s->le, "q", &opts, &s->q);
+    field_grad_create(s->pe, s->q, 2, &s->q_grad);
+    field_grad_set(s->q_grad, grad_3d_7pt_fluid_d2, grad_3d_7pt_fluid_d4);
+    fe_lc_create(s->pe, s->cs, s->le, s->q, s->q_grad, &s->fe_lc);
+    p.a0 = cfg->lc_a0; p.q0 = cfg->lc_q0; p.gamma = cfg->lc_gamma;
+    p.kappa0 = cfg->lc_kappa0; p.kappa1 = cfg->lc_kappa1; p.xi = cfg->lc_xi;
+    p.redshift = 1.0; p.rredshift = 1.0;
+    p.epsilon = cfg->lc_epsilon;
+    p.e0[0] = cfg->lc_e0[0]; p.e0[1] = cfg->lc_e0[1]; p.e0[2] = cfg->lc_e0[2];
+    p.coswt = 1.0;
+    fe_lc_param_set(s->fe_lc, &p);
+    beris_edw_create(s->pe, s->cs, s->le, &s->be);
+    bp.xi = cfg->lc_xi; bp.gamma = cfg->lc_Gamma;
+    beris_edw_param_set(s->be, &bp);
+    pth_create(s->pe, s->cs, FE_FORCE_METHOD_STRESS_DIVERGENCE, &s->pth);
+    advection_order_set(cfg->adv_order);
+    colloids_info_create(s->pe, s->cs, ncell, &s->cinfo);
+  }
   else {
     pth_create(s->pe, s->cs, FE_FORCE_METHOD_NO_FORCE, &s->pth);
   }
@@ -186,6 +227,11 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
 
 void ref_free(ref_sim_t * s) {
   if (s == NULL) return;
+  if (s->cinfo) colloids_info_free(s->cinfo);
+  if (s->be) beris_edw_free(s->be);
+  if (s->fe_lc) fe_lc_free(s->fe_lc);
+  if (s->q_grad) field_grad_free(s->q_grad);
+  if (s->q) field_free(s->q);
   if (s->pch) phi_ch_free(s->pch);
   if (s->pth) pth_free(s->pth);
   if (s->fe) fe_symm_free(s->fe);
@@ -282,6 +328,34 @@ static int ref_copy(ref_sim_t * s, int what, double * buf, int put) {
       XFER(s->pch->flux->fz[addr_rank0(ns, i)], (size_t) 3*ns + i);
     }
     break;
+  case REF_Q:
+    for (int n = 0; n < NQAB; n++)
+      for (int i = 0; i < ns; i++) XFER(s->q->data[addr_rank1(ns, NQAB, i, n)], (size_t) n*ns + i);
+    break;
+  case REF_QGRAD:
+    for (int n = 0; n < NQAB; n++)
+      for (int a = 0; a < 3; a++)
+	for (int i = 0; i < ns; i++) XFER(s->q_grad->grad[addr_rank2(ns, NQAB, 3, i, n, a)], (size_t) (n*3 + a)*ns + i);
+    break;
+  case REF_QDELSQ:
+    for (int n = 0; n < NQAB; n++)
+      for (int i = 0; i < ns; i++) XFER(s->q_grad->delsq[addr_rank1(ns, NQAB, i, n)], (size_t) n*ns + i);
+    break;
+  case REF_H:
+    /* the molecular field through the reference's public per-site function (the stored copy is private to
+     * blue_phase_beris_edwards.c); read only */
+    if (put) return -1;
+    for (int i = 0; i < ns; i++) {
+      int nall[3], nlocal[3], nh;
+      cs_nlocal(s->cs, nlocal); cs_nhalo(s->cs, &nh);
+      for (int a2 = 0; a2 < 3; a2++) nall[a2] = nlocal[a2] + 2*nh;
+      int kc = i % nall[Z] - nh + 1, jc = (i/nall[Z]) % nall[Y] - nh + 1, ic = i/(nall[Y]*nall[Z]) - nh + 1;
+      double h[3][3] = {{0.0}};
+      if (ic >= 1 && ic <= nlocal[X] && jc >= 1 && jc <= nlocal[Y] && kc >= 1 && kc <= nlocal[Z]) fe_lc_mol_field(s->fe_lc, i, h);
+      buf[(size_t) 0*ns + i] = h[X][X]; buf[(size_t) 1*ns + i] = h[X][Y]; buf[(size_t) 2*ns + i] = h[X][Z];
+      buf[(size_t) 3*ns + i] = h[Y][Y]; buf[(size_t) 4*ns + i] = h[Y][Z];
+    }
+    break;
   case REF_MAP:
     for (int i = 0; i < ns; i++) {
       if (put) s->map->status[i] = (char) buf[i]; else buf[i] = (double) s->map->status[i];
@@ -308,8 +382,43 @@ int ref_grad_d4(ref_sim_t * s) { return grad_3d_27pt_fluid_d4(s->phi_grad); }
 int ref_pth_stress_compute(ref_sim_t * s) { return pth_stress_compute(s->pth, (fe_t *) s->fe); }
 int ref_pth_force_fluid_driver(ref_sim_t * s) { return pth_force_fluid_driver(s->pth, s->hydro); }
 int ref_phi_force(ref_sim_t * s) {
-  return phi_force_calculation(s->pe, s->cs, s->le, s->wall, s->pth, (fe_t *) s->fe, s->map,
+  fe_t * fe = s->fe_lc ? (fe_t *) s->fe_lc : (fe_t *) s->fe;
+  return phi_force_calculation(s->pe, s->cs, s->le, s->wall, s->pth, fe, s->map,
 			       s->phi, s->hydro);
+}
+/* liquid crystal: /root/reference/src/ludwig.c:579-586, 769-779 */
+int ref_q_halo(ref_sim_t * s) { return field_halo(s->q); }
+int ref_q_grad_compute(ref_sim_t * s) { return field_grad_compute(s->q_grad); }
+int ref_lc_stress_compute(ref_sim_t * s) { return pth_stress_compute(s->pth, (fe_t *) s->fe_lc); }
+int ref_beris_edw_update(ref_sim_t * s) {
+  return beris_edw_update(s->be, (fe_t *) s->fe_lc, s->q, s->q_grad, s->hydro, s->cinfo, s->map, NULL);
+}
+int ref_lc_twist_init(ref_sim_t * s, int helical_axis, double amplitude) {
+  fe_lc_param_t p;
+  fe_lc_param(s->fe_lc, &p);
+  p.amplitude0 = amplitude;
+  return blue_phase_twist_init(s->cs, &p, s->q, helical_axis);
+}
+int ref_lc_o8m_init(ref_sim_t * s, double amplitude) {
+  fe_lc_param_t p;
+  double angles[3] = {0.0, 0.0, 0.0};
+  fe_lc_param(s->fe_lc, &p);
+  p.amplitude0 = amplitude;
+  return blue_phase_O8M_init(s->cs, &p, s->q, angles);
+}
+/* total free energy density sum over the interior (stats_free_energy_density, src/stats_free_energy.c:76-134) */
+double ref_lc_fed_sum(ref_sim_t * s) {
+  int nlocal[3];
+  double sum = 0.0;
+  cs_nlocal(s->cs, nlocal);
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++) {
+	double fed;
+	fe_lc_fed(s->fe_lc, cs_index(s->cs, ic, jc, kc), &fed);
+	sum += fed;
+      }
+  return sum;
 }
 int ref_cahn_hilliard(ref_sim_t * s) {
   return phi_cahn_hilliard(s->pch, (fe_t *) s->fe, s->phi, s->hydro, s->map, NULL);
@@ -348,6 +457,13 @@ int ref_step(ref_sim_t * s, int nsteps) {
       ref_grad_compute(s);
       ref_phi_force(s);
       ref_cahn_hilliard(s);
+    }
+    else if (s->q) {
+      ref_q_halo(s);
+      ref_q_grad_compute(s);
+      ref_phi_force(s);
+      ref_hydro_u_halo(s);
+      ref_beris_edw_update(s);
     }
     ref_hydro_u_zero(s);
     ref_collide(s);

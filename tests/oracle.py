@@ -13,17 +13,24 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
 def build(force=False):
     src = os.path.join(ORACLE_DIR, "lb_oracle.c")
     src_le = os.path.join(ORACLE_DIR, "lb_oracle_le.c")
-    deps = [src, src_le, os.path.join(ORACLE_DIR, "lb_oracle.h"), os.path.join(ORACLE_DIR, "d3q19_tables.h")]
+    src_lc = os.path.join(ORACLE_DIR, "lb_oracle_lc.c")
+    deps = [src, src_le, src_lc, os.path.join(ORACLE_DIR, "lb_oracle.h"), os.path.join(ORACLE_DIR, "d3q19_tables.h")]
     if (not force and os.path.exists(ORACLE_SO)
             and all(os.path.getmtime(ORACLE_SO) >= os.path.getmtime(d) for d in deps)):
         return ORACLE_SO
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-Wall",
-                           "-o", ORACLE_SO, src, src_le, "-lm"])
+                           "-o", ORACLE_SO, src, src_le, src_lc, "-lm"])
     return ORACLE_SO
 
 
 class Geom(C.Structure):
     _fields_ = [("nlocal", C.c_int * 3), ("nhalo", C.c_int), ("periodic", C.c_int * 3), ("le_nplanes", C.c_int)]
+
+
+class LcParam(C.Structure):
+    _fields_ = [("a0", C.c_double), ("q0", C.c_double), ("gamma", C.c_double), ("kappa0", C.c_double),
+                ("kappa1", C.c_double), ("xi", C.c_double), ("Gamma", C.c_double), ("epsilon", C.c_double),
+                ("e0", C.c_double * 3)]
 
 
 class LeParam(C.Structure):
@@ -213,6 +220,36 @@ class Oracle:
     def le_step(self, cp, sp, tcurrent0, nsteps, f, phi, u, rho, force, grad, delsq):
         self.lib.orc_le_step(C.byref(self.g), C.byref(self.m), C.byref(cp), C.byref(sp), C.byref(self.le),
                              tcurrent0, nsteps, _p(f), _p(phi), _p(u), _p(rho), _p(force), _p(grad), _p(delsq))
+
+    # ---- liquid crystal (oracle/lb_oracle_lc.c) ----------------------------------------------------
+    def lc_param(self, a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon=0.0, e0=(0.0, 0.0, 0.0)):
+        p = LcParam()
+        p.a0, p.q0, p.gamma, p.kappa0, p.kappa1, p.xi, p.Gamma, p.epsilon = a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon
+        p.e0[:] = e0
+        return p
+
+    def grad_7pt(self, field, grad, delsq):
+        self.lib.orc_grad_7pt(C.byref(self.g), field.shape[0], _p(field), _p(grad), _p(delsq))
+
+    def lc_stress(self, p, q, qgrad, qdelsq, str_):
+        self.lib.orc_lc_stress(C.byref(self.g), C.byref(p), _p(q), _p(qgrad), _p(qdelsq), _p(str_))
+
+    def lc_mol_field(self, p, q, qgrad, qdelsq, h):
+        self.lib.orc_lc_mol_field(C.byref(self.g), C.byref(p), _p(q), _p(qgrad), _p(qdelsq), _p(h))
+
+    def lc_fed_sum(self, p, q, qgrad):
+        self.lib.orc_lc_fed_sum.restype = C.c_double
+        return self.lib.orc_lc_fed_sum(C.byref(self.g), C.byref(p), _p(q), _p(qgrad))
+
+    def advection_nf(self, order, u, field, flux):
+        self.lib.orc_advection_nf(C.byref(self.g), order, field.shape[0], _p(u), _p(field), _p(flux))
+
+    def beris_edw_update(self, p, u, h, flux, q):
+        self.lib.orc_beris_edw_update(C.byref(self.g), C.c_double(p.xi), C.c_double(p.Gamma), _p(u), _p(h), _p(flux), _p(q))
+
+    def lc_step(self, cp, p, adv_order, nsteps, f, q, u, rho, force, qgrad, qdelsq):
+        self.lib.orc_lc_step(C.byref(self.g), C.byref(self.m), C.byref(cp), C.byref(p), adv_order, nsteps,
+                             _p(f), _p(q), _p(u), _p(rho), _p(force), _p(qgrad), _p(qdelsq))
 
     # ---- symmetric_lb (two distributions: f is (2*nvel, nsites)) ------------------------------
     def phi_lb_to_field(self, f, phi):

@@ -9,9 +9,10 @@ REF_SO = os.path.join(HERE, "..", "oracle", "_ref", "libludwig_ref.so")
 REF_FAST_SO = os.path.join(HERE, "..", "oracle", "_ref", "libludwig_ref_fast.so")
 
 REF_F, REF_PHI, REF_U, REF_RHO, REF_FORCE, REF_GRAD, REF_DELSQ, REF_STR, REF_FLUX, REF_MAP, \
-    REF_GRAD_DELSQ, REF_DELSQ_DELSQ = range(12)
+    REF_GRAD_DELSQ, REF_DELSQ_DELSQ, REF_Q, REF_QGRAD, REF_QDELSQ, REF_H = range(16)
 NCOMP = {REF_PHI: 1, REF_U: 3, REF_RHO: 1, REF_FORCE: 3, REF_GRAD: 3, REF_DELSQ: 1,
-         REF_STR: 9, REF_FLUX: 4, REF_MAP: 1, REF_GRAD_DELSQ: 3, REF_DELSQ_DELSQ: 1}
+         REF_STR: 9, REF_FLUX: 4, REF_MAP: 1, REF_GRAD_DELSQ: 3, REF_DELSQ_DELSQ: 1,
+         REF_Q: 5, REF_QGRAD: 15, REF_QDELSQ: 5, REF_H: 5}
 
 
 class RefCfg(C.Structure):
@@ -22,7 +23,10 @@ class RefCfg(C.Structure):
                 ("rho0", C.c_double), ("eta_shear", C.c_double), ("eta_bulk", C.c_double),
                 ("fbody", C.c_double * 3), ("a", C.c_double), ("b", C.c_double),
                 ("kappa", C.c_double), ("mobility", C.c_double), ("gradmu", C.c_double * 3),
-                ("grad_level", C.c_int), ("le_nplanes", C.c_int), ("le_uy", C.c_double)]
+                ("grad_level", C.c_int), ("le_nplanes", C.c_int), ("le_uy", C.c_double),
+                ("have_q", C.c_int), ("lc_a0", C.c_double), ("lc_q0", C.c_double), ("lc_gamma", C.c_double),
+                ("lc_kappa0", C.c_double), ("lc_kappa1", C.c_double), ("lc_xi", C.c_double), ("lc_Gamma", C.c_double),
+                ("lc_epsilon", C.c_double), ("lc_e0", C.c_double * 3)]
 
 
 def _so(fast=False, nvel=19):
@@ -50,7 +54,8 @@ def _lib(fast=False, nvel=19):
                      "ref_phi_halo", "ref_grad_compute", "ref_phi_force", "ref_cahn_hilliard",
                      "ref_collide", "ref_lb_halo", "ref_propagation", "ref_phi_lb_to_field", "ref_phi_lb_from_field", "ref_grad_d4", "ref_pth_stress_compute",
                      "ref_pth_force_fluid_driver", "ref_nsites_le", "ref_le_field", "ref_le_hydro", "ref_le_lb_bc",
-                     "ref_le_init_shear_profile", "ref_next_step", "ref_timestep"):
+                     "ref_le_init_shear_profile", "ref_next_step", "ref_timestep", "ref_q_halo", "ref_q_grad_compute",
+                     "ref_lc_stress_compute", "ref_beris_edw_update"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.ref_step.argtypes = [C.c_void_p, C.c_int]
         lib.ref_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -58,6 +63,10 @@ def _lib(fast=False, nvel=19):
         lib.ref_init_rest.argtypes = [C.c_void_p, C.c_double]
         lib.ref_init_uniform_u.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double * 3)]
         lib.ref_init_spinodal.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        lib.ref_lc_twist_init.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        lib.ref_lc_o8m_init.argtypes = [C.c_void_p, C.c_double]
+        lib.ref_lc_fed_sum.argtypes = [C.c_void_p]
+        lib.ref_lc_fed_sum.restype = C.c_double
         lib.ref_nvel.restype = C.c_int
         assert lib.ref_nvel() == nvel
         _libs[key] = lib
@@ -70,7 +79,7 @@ class RefSim:
     def __init__(self, ntotal, nhalo=1, periodic=(1, 1, 1), ndist=1, nrelax=0, ghost_off=0,
                  halo_reduced=0, have_phi=0, adv_order=1, conserve=0, rho0=1.0, eta_shear=1.0 / 6.0,
                  eta_bulk=None, fbody=(0, 0, 0), a=0.0, b=0.0, kappa=0.0, mobility=0.0,
-                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2, le_nplanes=0, le_uy=0.0):
+                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2, le_nplanes=0, le_uy=0.0, lc=None):
         self.lib = _lib(fast, nvel)
         cfg = RefCfg()
         cfg.ntotal[:] = ntotal
@@ -85,6 +94,13 @@ class RefSim:
         cfg.gradmu[:] = gradmu
         cfg.grad_level = grad_level
         cfg.le_nplanes, cfg.le_uy = le_nplanes, le_uy
+        if lc is not None:
+            # liquid crystal: dict(a0, q0, gamma, kappa0, kappa1, xi, Gamma[, epsilon, e0])
+            cfg.have_q = 1
+            cfg.lc_a0, cfg.lc_q0, cfg.lc_gamma = lc["a0"], lc["q0"], lc["gamma"]
+            cfg.lc_kappa0, cfg.lc_kappa1, cfg.lc_xi, cfg.lc_Gamma = lc["kappa0"], lc["kappa1"], lc["xi"], lc["Gamma"]
+            cfg.lc_epsilon = lc.get("epsilon", 0.0)
+            cfg.lc_e0[:] = lc.get("e0", (0.0, 0.0, 0.0))
         self.cfg = cfg
         self.h = self.lib.ref_create(C.byref(cfg))
         self.nsites = self.lib.ref_nsites(self.h)
@@ -124,6 +140,15 @@ class RefSim:
 
     def init_spinodal(self, seed, phi0, amp):
         self.lib.ref_init_spinodal(self.h, seed, phi0, amp)
+
+    def lc_twist_init(self, axis, amplitude):
+        self.lib.ref_lc_twist_init(self.h, axis, amplitude)
+
+    def lc_o8m_init(self, amplitude):
+        self.lib.ref_lc_o8m_init(self.h, amplitude)
+
+    def lc_fed_sum(self):
+        return self.lib.ref_lc_fed_sum(self.h)
 
     def op(self, name):
         return getattr(self.lib, "ref_" + name)(self.h)
