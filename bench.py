@@ -393,6 +393,133 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# secondary workload (BASELINE config 4): liquid-crystal blue phase / cholesteric, 128^3 per GPU
+# ------------------------------------------------------------------------------------------------------
+
+LC = dict(a0=0.01, q0=0.19635, gamma=3.0, kappa0=0.000648456, kappa1=0.000648456, xi=0.7, Gamma=0.5)   # pmpi08-chol-s01.inp
+LC_B_ALG = {"stress": 40.0 + 72.0, "force_be": 72.0 + 40.0 + 24.0 + 24.0 + 40.0, "collide": 360.0}
+
+
+def run_lc(args, local_rank):
+    """python bench.py --lc [--size 128]: Landau-de Gennes Q tensor + Beris-Edwards coupled to D3Q19,
+    cholesteric twist initial state (tests/regression/d3q19/pmpi08-chol-s01.inp parameters, advection order 3)."""
+    import numpy as np
+    import torch
+    import ludwig_b200 as lb
+    from ludwig_b200.initial import lc_twist_q
+
+    torch.cuda.set_device(local_rank)
+    n = args.size
+    nlocal = (n, n, n)
+    sim = lb.Lb200(nlocal, nhalo=2, have_q=True, math=lb.MATH_STRICT if args.strict else lb.MATH_FAST, device=local_rank)
+    ns = sim.nsites
+    h_f = torch.empty((19, ns), dtype=torch.float64, pin_memory=True)
+    h_q = torch.empty((5, ns), dtype=torch.float64, pin_memory=True)
+    h_u = torch.empty((3, ns), dtype=torch.float64, pin_memory=True)
+    wv = np.array([12.0] + [2.0 if sum(abs(c) for c in cv) == 1 else 1.0 for cv in CV19[1:]]) / 36.0
+    for p in range(19):
+        h_f.numpy()[p, :] = wv[p]
+    rng = np.random.default_rng(8361235)
+    h_q.numpy()[...] = lc_twist_q(nlocal, 2, LC["q0"], 1.0 / 3.0, 2)
+    sim.interior(h_q.numpy())[...] += 0.01 * (rng.random((5,) + nlocal) - 0.5)
+    cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, 0.1)
+    lc = lb.LcParam.make(adv_order=3, **LC)
+    stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local_rank))
+    H2D, D2H = 1, 2
+
+    def upload():
+        sim.memcpy_async(lb.F, h_f.data_ptr(), H2D)
+        sim.memcpy_async(lb.Q, h_q.data_ptr(), H2D)
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    upload()
+    sim.sync()
+    sim.step_lc(cp, lc, args.warmup)
+    sim.sync()
+    clocks.mark_begin()
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.step_lc(cp, lc, args.steps)
+    e1.record(stream)
+    sim.sync()
+    clocks.mark_end()
+    ms = e0.elapsed_time(e1)
+    launches = sim.launch_count() - l0
+    clk = clocks.stop()
+    sites = float(n) ** 3
+    mlups = sites * args.steps / (ms * 1e-3) / 1e6
+
+    sim.profile(True)
+    sim.step_lc(cp, lc, min(args.steps, 20))
+    sim.sync()
+    prof = sim.profile_get()
+    sim.profile(False)
+    kernels = {k: {"ms_per_launch": (t / c if c else None), "launches": c} for k, (t, c) in prof.items() if c}
+    peak, peak_src = measured_peaks()
+
+    def gbs(key, alg):
+        t = kernels.get(key, {}).get("ms_per_launch")
+        return alg * sites / (t * 1e-3) / 1e9 if t else None
+
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    t0.record(stream)
+    upload()
+    sim.step_lc(cp, lc, args.steps)
+    sim.memcpy_async(lb.Q, h_q.data_ptr(), D2H)
+    sim.memcpy_async(lb.U, h_u.data_ptr(), D2H)
+    t1.record(stream)
+    sim.sync()
+    e2e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0) * 1e3)
+    q_sum = float(np.nansum(sim.interior(h_q.numpy())[0]))
+
+    cpu = None
+    if not args.no_cpu:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import refharness
+            nsamp = 64
+            if refharness.available(fast=True):
+                os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+                ref = refharness.RefSim((nsamp,) * 3, nhalo=2, adv_order=3, eta_shear=0.1, fast=True, lc=LC)
+                ref.init_rest(1.0); ref.lc_twist_init(2, 1.0 / 3.0)
+                ref.step(1)
+                t = ref.time_steps(3) / 3
+                ref.close()
+                cpu = {"value": nsamp ** 3 / t / 1e6, "unit": "MLUPS", "cores": os.cpu_count() or 1, "kind": "reference",
+                       "sample": f"3 full liquid-crystal time steps of a {nsamp}^3 lattice after 1 warm-up step"}
+        except Exception as exc:
+            cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "reference", "sample": f"failed: {exc}"}
+
+    b_step = LC_B_ALG["stress"] + LC_B_ALG["force_be"] + LC_B_ALG["collide"]
+    line = {
+        "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"D3Q19 + liquid crystal (Landau-de Gennes Q tensor, Beris-Edwards, 7pt gradient, advection order 3), "
+                               f"{n}^3 on one GPU, cholesteric twist + noise (pmpi08-chol-s01.inp parameters); halo-free steps",
+                   "lattice_per_gpu": list(nlocal), "math": "strict" if args.strict else "fast(fma)",
+                   "l2": f"lattice state per step {b_step * sites / 1e9:.2f} GB vs 126 MB L2"},
+        "roofline": {"bound": "hbm", "kernel": "collide_d3q19 (pull-stream + MRT collision)",
+                     "achieved": gbs("collide", LC_B_ALG["collide"]), "peak": peak, "unit": "GB/s",
+                     "frac": (gbs("collide", LC_B_ALG["collide"]) or 0.0) / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_site": LC_B_ALG["collide"],
+                     "lc_stress": {"algorithmic_bytes_per_site": LC_B_ALG["stress"], "achieved": gbs("lc_stress", LC_B_ALG["stress"])},
+                     "lc_force_be": {"algorithmic_bytes_per_site": LC_B_ALG["force_be"], "achieved": gbs("lc_be", LC_B_ALG["force_be"])},
+                     "whole_step": {"algorithmic_bytes_per_site": b_step, "achieved": mlups * 1e6 * b_step / 1e9,
+                                    "frac": mlups * 1e6 * b_step / 1e9 / peak}},
+        "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
+        "e2e": {"value": sites * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS",
+                "h2d_bytes_per_step": (19 + 5) * ns * 8 / args.steps, "d2h_bytes_per_step": (5 + 3) * ns * 8 / args.steps},
+        "gpu_launches": launches, "check": {"qxx_sum": q_sum},
+    }
+    print(json.dumps(line), flush=True)
+    sim.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -403,6 +530,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=128, help="edge of the CPU-baseline sample lattice")
     ap.add_argument("--strict", action="store_true", help="bit-exact arithmetic mode (no FMA contraction)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lc", action="store_true", help="secondary workload: liquid crystal (BASELINE config 4), --size 128 unless given")
     ap.add_argument("--le", type=int, default=0, help="Lees-Edwards planes per GPU (0: none, the headline workload)")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: a fixed (2*size) x size x size lattice over all GPUs (default: weak, size^3 per GPU)")
@@ -416,6 +544,11 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.lc:
+        if "--size" not in sys.argv:
+            args.size = 128
+        run_lc(args, local_rank)
         return
     if world == 1 and args.gpus > 1:
         # not under torchrun: launch ourselves one process per GPU

@@ -65,7 +65,10 @@ enum lb200_array {
   LB200_MAP = 7,            /* map->status        1 x nsites, passed as double, 0 = MAP_FLUID  src/map.h:26-48 */
   LB200_GRAD_DELSQ = 8,     /* field_grad->grad_delsq  3 x nsites  (after lb200_phi_grad_compute_d4) */
   LB200_DELSQ_DELSQ = 9,    /* field_grad->delsq_delsq 1 x nsites */
-  LB200_STR = 10            /* pth->str           9 x nsites, component ia*3 + ib (after lb200_pth_stress_compute) */
+  LB200_STR = 10,           /* pth->str           9 x nsites, component ia*3 + ib (after lb200_pth_stress_compute) */
+  LB200_Q = 11,             /* field "q"          5 x nsites: Q_xx, Q_xy, Q_xz, Q_yy, Q_yz   src/field.h, NQAB */
+  LB200_QGRAD = 12,         /* field_grad(q)->grad   15 x nsites, component n*3 + ia (after lb200_q_grad_compute) */
+  LB200_QDELSQ = 13         /* field_grad(q)->delsq   5 x nsites */
 };
 
 typedef struct lb200_options_s {
@@ -90,6 +93,9 @@ typedef struct lb200_options_s {
   int le_nplanes;           /* 0 = none */
   double le_uy;             /* LE_plane_vel */
   int le_nt0;               /* reference time step (lees_edw_options_t.nt0, usually 0) */
+  /* free_energy lc_blue_phase (src/ludwig.c:1598-1666): the tensor order parameter q (5 components, nhalo >= 2).
+   * Exclusive with have_phi; one GPU (cart_size == 1) and no Lees-Edwards planes in this round. */
+  int have_q;
 } lb200_options_t;
 
 /* lb_collide_param_t / collide_param_t as seen by the collision: src/lb_data.h:59-76,
@@ -110,6 +116,19 @@ typedef struct lb200_symm_param_s {
   double gradmu[3];         /* physics grad_mu (external chemical potential gradient) */
   int adv_order;            /* fd_advection_scheme_order 1, 2 or 3 */
 } lb200_symm_param_t;
+
+/* fe_lc_param_t + beris_edw_param_t as the liquid-crystal kernels see them (src/blue_phase.h:52-75,
+ * src/blue_phase_beris_edwards.h:30-37); redshift 1, no activity, no noise */
+typedef struct lb200_lc_param_s {
+  double a0, q0, gamma;     /* lc_a0, lc_q0, lc_gamma */
+  double kappa0, kappa1;    /* lc_kappa0, lc_kappa1 (as the reference, its vectorised molecular field and free-energy
+                             * density use kappa0 for both: src/blue_phase.c:1934, 2119-2120) */
+  double xi;                /* lc_xi: flow-aligning parameter */
+  double Gamma;             /* lc_Gamma: rotational diffusion constant */
+  double epsilon;           /* lc_dielectric_anisotropy / (12 pi), as stored by fe_lc_param_set (src/blue_phase.c:249-252) */
+  double e0[3];             /* electric_e0 */
+  int adv_order;            /* fd_advection_scheme_order 1, 2 or 3 */
+} lb200_lc_param_t;
 
 const char * lb200_last_error(void);
 int lb200_version(void);
@@ -186,6 +205,26 @@ int lb200_lb_le_apply_boundary_conditions(lb200_t * ctx);
 int lb200_le_plane_location(const lb200_options_t * options, int np);
 int lb200_le_ic_to_buff(const lb200_options_t * options, int ic, int di);
 
+/* ---- liquid crystal (options.have_q) ------------------------------------------------------------------------
+ * field_halo(q): src/field.c:371-404;  field_grad_compute(q_grad) with d2 = grad_3d_7pt_fluid_d2
+ * (src/gradient_3d_7pt_fluid.c:76-99, 231-300) -> LB200_QGRAD, LB200_QDELSQ (the stress and the Beris-Edwards kernels
+ * below do not need these arrays: they rebuild the gradients from Q in registers) */
+int lb200_q_halo(lb200_t * ctx);
+int lb200_q_grad_compute(lb200_t * ctx);
+/* pth_stress_compute with fe_lc_stress_v (src/phi_force_stress.c:171-284, src/blue_phase.c:1737-1800, 2279-2775)
+ * -> LB200_STR; follow with lb200_pth_force_fluid_driver.  lb200_lc_force_calculation = phi_force_calculation
+ * for this free energy (both, src/phi_force.c:100-110) */
+int lb200_lc_stress_compute(lb200_t * ctx, const lb200_lc_param_t * lc);
+int lb200_lc_force_calculation(lb200_t * ctx, const lb200_lc_param_t * lc);
+/* beris_edw_update (hydro present, no colloids, no noise): advection_x + beris_edw_h_driver + beris_edw_update_driver,
+ * src/blue_phase_beris_edwards.c:266-296, 538-850, 942-985.  The caller has done hydro_u_halo (src/ludwig.c:771-773). */
+int lb200_beris_edw_update(lb200_t * ctx, const lb200_lc_param_t * lc);
+/* nsteps whole liquid-crystal time steps (src/ludwig.c:528-860 with ludwig->q): hydro_f_zero; field_halo(q);
+ * field_grad_compute; phi_force_calculation; hydro_u_halo; beris_edw_update; hydro_u_zero; lb_collide; lb_halo;
+ * lb_propagation -- three sweeps per step (stress; force + Beris-Edwards; pull-stream + collide), halo-free on
+ * periodic lattices.  Asynchronous like lb200_step. */
+int lb200_step_lc(lb200_t * ctx, const lb200_collide_param_t * cp, const lb200_lc_param_t * lc, int nsteps);
+
 /* lb_halo: src/lb_data.c:754-762, 1124-1477 */
 int lb200_lb_halo(lb200_t * ctx);
 /* lb_propagation: src/propagation.c:43-95, 153-240 */
@@ -228,7 +267,9 @@ enum lb200_kernel_class {
   LB200_K_FORCE_CH = 4,     /* stress-divergence force and/or Cahn-Hilliard update */
   LB200_K_PHI_SECTOR = 5,   /* gradient + force + Cahn-Hilliard in one sweep (lb200_step, all-fluid) */
   LB200_K_LE = 6,           /* Lees-Edwards: buffer interpolation, plane patches, plane-crossing populations */
-  LB200_KCLASS_MAX = 7
+  LB200_K_LC_STRESS = 7,    /* liquid crystal: gradients + molecular field + stress */
+  LB200_K_LC_BE = 8,        /* liquid crystal: force divergence + Beris-Edwards update */
+  LB200_KCLASS_MAX = 9
 };
 int lb200_profile(lb200_t * ctx, int on);      /* clears accumulated timings */
 int lb200_profile_get(lb200_t * ctx, int kernel_class, double * total_ms, int * count);

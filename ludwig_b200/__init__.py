@@ -5,12 +5,12 @@ ludwig_b200/csrc (CUDA) and ludwig_b200/host (C host layer with the reference's 
 This Python package is only a ctypes binding used by the tests and the benchmark; there is no
 CPU fallback: importing works anywhere, creating a context without a CUDA device raises.
 """
-from .capi import (Lb200, Lb200Error, slab_plan, SlabPlan, step_plan, StepPlan, STEP_PHI, STEP_UX, STEP_F, CollideParam, SymmParam, Options, load_library, library_path,
-                   F, PHI, U, RHO, FORCE, GRAD, DELSQ, MAP, GRAD_DELSQ, DELSQ_DELSQ, STR,
+from .capi import (Lb200, Lb200Error, slab_plan, SlabPlan, step_plan, StepPlan, STEP_PHI, STEP_UX, STEP_F, CollideParam, SymmParam, LcParam, Options, load_library, library_path,
+                   F, PHI, U, RHO, FORCE, GRAD, DELSQ, MAP, GRAD_DELSQ, DELSQ_DELSQ, STR, Q, QGRAD, QDELSQ,
                    RELAX_M10, RELAX_BGK, RELAX_TRT, HALO_FULL, HALO_REDUCED, MATH_FAST, MATH_STRICT,
                    KNOB_WRAP, KNOB_PHI_SECTOR, KNOB_PEER)
 
-__all__ = ["Lb200", "Lb200Error", "slab_plan", "SlabPlan", "step_plan", "StepPlan", "STEP_PHI", "STEP_UX", "STEP_F", "CollideParam", "SymmParam", "Options", "load_library", "library_path",
-           "F", "PHI", "U", "RHO", "FORCE", "GRAD", "DELSQ", "MAP", "GRAD_DELSQ", "DELSQ_DELSQ", "STR",
+__all__ = ["Lb200", "Lb200Error", "slab_plan", "SlabPlan", "step_plan", "StepPlan", "STEP_PHI", "STEP_UX", "STEP_F", "CollideParam", "SymmParam", "LcParam", "Options", "load_library", "library_path",
+           "F", "PHI", "U", "RHO", "FORCE", "GRAD", "DELSQ", "MAP", "GRAD_DELSQ", "DELSQ_DELSQ", "STR", "Q", "QGRAD", "QDELSQ",
            "RELAX_M10", "RELAX_BGK", "RELAX_TRT", "HALO_FULL", "HALO_REDUCED", "MATH_FAST", "MATH_STRICT",
            "KNOB_WRAP", "KNOB_PHI_SECTOR", "KNOB_PEER"]

@@ -3,14 +3,15 @@ import ctypes as C
 import os
 import numpy as np
 
-F, PHI, U, RHO, FORCE, GRAD, DELSQ, MAP, GRAD_DELSQ, DELSQ_DELSQ, STR = range(11)
+F, PHI, U, RHO, FORCE, GRAD, DELSQ, MAP, GRAD_DELSQ, DELSQ_DELSQ, STR, Q, QGRAD, QDELSQ = range(14)
 RELAX_M10, RELAX_BGK, RELAX_TRT = 0, 1, 2
 HALO_FULL, HALO_REDUCED = 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 H2D, D2H = 1, 2
 KNOB_WRAP, KNOB_PHI_SECTOR, KNOB_PEER = 1, 2, 3
 
-_NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1, GRAD_DELSQ: 3, DELSQ_DELSQ: 1, STR: 9}
+_NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1, GRAD_DELSQ: 3, DELSQ_DELSQ: 1, STR: 9,
+          Q: 5, QGRAD: 15, QDELSQ: 5}
 
 
 class Lb200Error(RuntimeError):
@@ -22,7 +23,7 @@ class Options(C.Structure):
                 ("nvel", C.c_int), ("ndist", C.c_int), ("have_phi", C.c_int),
                 ("halo_scheme", C.c_int), ("math", C.c_int), ("device", C.c_int),
                 ("cart_size", C.c_int), ("cart_rank", C.c_int),
-                ("le_nplanes", C.c_int), ("le_uy", C.c_double), ("le_nt0", C.c_int)]
+                ("le_nplanes", C.c_int), ("le_uy", C.c_double), ("le_nt0", C.c_int), ("have_q", C.c_int)]
 
 
 class CollideParam(C.Structure):
@@ -48,6 +49,20 @@ class SymmParam(C.Structure):
         sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order = a, b, kappa, mobility, adv_order
         sp.gradmu[:] = gradmu
         return sp
+
+
+class LcParam(C.Structure):
+    _fields_ = [("a0", C.c_double), ("q0", C.c_double), ("gamma", C.c_double), ("kappa0", C.c_double),
+                ("kappa1", C.c_double), ("xi", C.c_double), ("Gamma", C.c_double), ("epsilon", C.c_double),
+                ("e0", C.c_double * 3), ("adv_order", C.c_int)]
+
+    @classmethod
+    def make(cls, a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon=0.0, e0=(0.0, 0.0, 0.0), adv_order=1):
+        p = cls()
+        p.a0, p.q0, p.gamma, p.kappa0, p.kappa1, p.xi, p.Gamma, p.epsilon = a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon
+        p.e0[:] = e0
+        p.adv_order = adv_order
+        return p
 
 
 class SlabPlan(C.Structure):
@@ -132,8 +147,12 @@ def load_library():
     for name in ("lb200_sync", "lb200_hydro_f_zero", "lb200_hydro_u_zero", "lb200_hydro_u_halo",
                  "lb200_phi_halo", "lb200_phi_grad_compute", "lb200_lb_halo", "lb200_lb_propagation",
                  "lb200_phi_grad_compute_d4", "lb200_pth_force_fluid_driver", "lb200_field_leesedwards",
-                 "lb200_hydro_lees_edwards", "lb200_lb_le_apply_boundary_conditions"):
+                 "lb200_hydro_lees_edwards", "lb200_lb_le_apply_boundary_conditions", "lb200_q_halo", "lb200_q_grad_compute"):
         getattr(lib, name).argtypes = [C.c_void_p]
+    lib.lb200_lc_stress_compute.argtypes = [C.c_void_p, C.POINTER(LcParam)]
+    lib.lb200_lc_force_calculation.argtypes = [C.c_void_p, C.POINTER(LcParam)]
+    lib.lb200_beris_edw_update.argtypes = [C.c_void_p, C.POINTER(LcParam)]
+    lib.lb200_step_lc.argtypes = [C.c_void_p, C.POINTER(CollideParam), C.POINTER(LcParam), C.c_int]
     lib.lb200_phi_force_calculation.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
     lib.lb200_phi_cahn_hilliard.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
     lib.lb200_lb_collide.argtypes = [C.c_void_p, C.POINTER(CollideParam)]
@@ -164,7 +183,7 @@ class Lb200:
 
     def __init__(self, nlocal, nhalo=1, periodic=(1, 1, 1), nvel=19, ndist=1, have_phi=False,
                  halo_scheme=HALO_FULL, math=MATH_FAST, device=-1, cart_size=1, cart_rank=0,
-                 le_nplanes=0, le_uy=0.0, le_nt0=0):
+                 le_nplanes=0, le_uy=0.0, le_nt0=0, have_q=False):
         self.lib = load_library()
         o = Options()
         o.nlocal[:] = nlocal
@@ -174,6 +193,7 @@ class Lb200:
         o.halo_scheme, o.math, o.device = halo_scheme, math, device
         o.cart_size, o.cart_rank = cart_size, cart_rank
         o.le_nplanes, o.le_uy, o.le_nt0 = le_nplanes, le_uy, le_nt0
+        o.have_q = int(bool(have_q))
         self.options = o
         self.h = C.c_void_p()
         self._check(self.lib.lb200_create(C.byref(o), C.byref(self.h)))
@@ -258,6 +278,40 @@ class Lb200:
 
     def phi_grad_compute(self):
         self._check(self.lib.lb200_phi_grad_compute(self.h))
+
+    # liquid crystal
+    def q_halo(self):
+        self._check(self.lib.lb200_q_halo(self.h))
+
+    def q_grad_compute(self):
+        self._check(self.lib.lb200_q_grad_compute(self.h))
+
+    def lc_stress_compute(self, lc):
+        self._check(self.lib.lb200_lc_stress_compute(self.h, C.byref(lc)))
+
+    def lc_force_calculation(self, lc):
+        self._check(self.lib.lb200_lc_force_calculation(self.h, C.byref(lc)))
+
+    def beris_edw_update(self, lc):
+        self._check(self.lib.lb200_beris_edw_update(self.h, C.byref(lc)))
+
+    def step_lc(self, cp, lc, nsteps=1):
+        self._check(self.lib.lb200_step_lc(self.h, C.byref(cp), C.byref(lc), nsteps))
+
+    def step_lc_api(self, cp, lc, nsteps=1):
+        """The liquid-crystal step through the individual entry points, reference driver order (src/ludwig.c:528-860)."""
+        for _ in range(nsteps):
+            self.hydro_f_zero()
+            self.q_halo()
+            self.q_grad_compute()
+            self.lc_stress_compute(lc)
+            self.pth_force_fluid_driver()
+            self.hydro_u_halo()
+            self.beris_edw_update(lc)
+            self.hydro_u_zero()
+            self.lb_collide(cp)
+            self.lb_halo()
+            self.lb_propagation()
 
     # Lees-Edwards planes
     def physics_control_time_set(self, t_start, t_current):
@@ -345,7 +399,7 @@ class Lb200:
             self.lb_halo()
             self.lb_propagation()
 
-    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch", "phi_sector", "le")
+    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch", "phi_sector", "le", "lc_stress", "lc_be")
 
     def profile(self, on=True):
         self._check(self.lib.lb200_profile(self.h, int(on)))

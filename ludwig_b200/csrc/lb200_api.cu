@@ -71,6 +71,10 @@ struct lb200_s {
   double * grad_delsq;       // field_grad level 4 (grad_3d_27pt_fluid_d4), allocated on first use
   double * delsq_delsq;
   double * str;              // pth->str (9 x nsites), allocated on first use of lb200_pth_stress_compute
+  double * q;                // liquid crystal: Q (5 x nsites) and its update target
+  double * qnew;
+  double * qgrad;            // 15 x nsites, allocated on first use of lb200_q_grad_compute
+  double * qdelsq;           // 5 x nsites
   char * status;             // device copy of map->status, nullptr if all fluid
   int map_all_fluid;
 
@@ -494,6 +498,9 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   if (o->have_phi && o->ndist == 1 && o->nhalo < 2) return fail(LB200_EINVAL, "the symmetric FD route needs nhalo >= 2 (reference src/ludwig.c:1198)");
   if (o->nvel != 15 && o->nvel != 19 && o->nvel != 27) return fail(LB200_EINVAL, "nvel = %d", o->nvel);
   if (o->cart_size < 1 || o->cart_rank < 0 || o->cart_rank >= o->cart_size) return fail(LB200_EINVAL, "bad cart_size/cart_rank");
+  if (o->have_q && (o->have_phi || o->ndist != 1)) return fail(LB200_EINVAL, "have_q (lc_blue_phase) excludes have_phi / ndist = 2");
+  if (o->have_q && o->nhalo < 2) return fail(LB200_EINVAL, "the liquid crystal needs nhalo >= 2 (reference src/ludwig.c:1605)");
+  if (o->have_q && (o->cart_size != 1 || o->le_nplanes != 0)) return fail(LB200_EINVAL, "have_q: one GPU and no Lees-Edwards planes in this build");
   if (o->halo_scheme != LB200_HALO_FULL && o->halo_scheme != LB200_HALO_REDUCED) return fail(LB200_EINVAL, "halo_scheme = %d", o->halo_scheme);
 
   int ndev = 0;
@@ -556,6 +563,11 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
     rc |= alloc_d(&c->phinew, nsz);
     rc |= alloc_d(&c->grad, nsz*3);
     rc |= alloc_d(&c->delsq, nsz);
+  }
+  if (o->have_q) {
+    rc |= alloc_d(&c->q, nsz*5);
+    rc |= alloc_d(&c->qnew, nsz*5);
+    rc |= alloc_d(&c->str, nsz*9);
   }
   if (g.remote_x) {
     // staging: nvel planes of depth 1 (f) | 3 components of depth nhalo (u) | nhalo planes (phi)
@@ -626,6 +638,7 @@ int lb200_free(lb200_t * c) {
   cudaFree(c->f); cudaFree(c->fprime); cudaFree(c->u_alloc[0] ? c->u_alloc[0] : c->u); cudaFree(c->u_alloc[1]); cudaFree(c->rho); cudaFree(c->force);
   cudaFree(c->phi); cudaFree(c->phinew); cudaFree(c->grad); cudaFree(c->delsq);
   cudaFree(c->grad_delsq); cudaFree(c->delsq_delsq); cudaFree(c->str);
+  cudaFree(c->q); cudaFree(c->qnew); cudaFree(c->qgrad); cudaFree(c->qdelsq);
   cudaFree(c->le_trip); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
   for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
   cudaFree(c->flags); cudaFree(c->spin_err);
@@ -709,6 +722,9 @@ static int array_info(lb200_t * c, int array, double ** dev, size_t * ncomp) {
   case LB200_GRAD_DELSQ:  *dev = c->grad_delsq;  *ncomp = 3; break;
   case LB200_DELSQ_DELSQ: *dev = c->delsq_delsq; *ncomp = 1; break;
   case LB200_STR:   *dev = c->str;   *ncomp = 9; break;
+  case LB200_Q:      *dev = c->q;      *ncomp = 5; break;
+  case LB200_QGRAD:  *dev = c->qgrad;  *ncomp = 15; break;
+  case LB200_QDELSQ: *dev = c->qdelsq; *ncomp = 5; break;
   default: return fail(LB200_EINVAL, "unknown array id %d", array);
   }
   if (*dev == nullptr) return fail(LB200_ESTATE, "array %d is not allocated in this context (have_phi = 0?)", array);
@@ -1735,6 +1751,166 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     if (c->u_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
     if (binary && c->phi_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
   }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- liquid crystal (options.have_q): lb200_lc.cuh ---------------------------------------------------------------
+
+static int lc_dev(lb200_t * c, const lb200_lc_param_t * lc, Lb200LcDev * d) {
+  if (c->q == nullptr) return fail(LB200_ESTATE, "no q in this context (options.have_q)");
+  if (lc == nullptr) return fail(LB200_EINVAL, "null parameters");
+  if (lc->adv_order < 1 || lc->adv_order > 3) return fail(LB200_EINVAL, "advection order %d: device kernels exist for 1-3", lc->adv_order);
+  if (!c->map_all_fluid) return fail(LB200_ESTATE, "liquid crystal: all-fluid lattices only in this build");
+  d->a0 = lc->a0; d->q0 = lc->q0; d->gamma = lc->gamma; d->kappa0 = lc->kappa0; d->kappa1 = lc->kappa1; d->xi = lc->xi;
+  d->Gamma = lc->Gamma; d->epsilon = lc->epsilon;
+  for (int a = 0; a < 3; a++) d->e0[a] = lc->e0[a];
+  d->order = lc->adv_order;
+  return 0;
+}
+
+int lb200_q_halo(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->q == nullptr) return fail(LB200_ESTATE, "no q in this context");
+  int rc = halo_field(c, c->q, 5, c->g.nh, 0, nullptr);
+  if (rc != 0) return rc;
+  CTX_LEAVE_SYNC(c);
+}
+
+// field_grad_compute(q_grad), d2 = grad_3d_7pt_fluid_d2: [1 - (nhalo - 1), N + nhalo - 1]^3
+int lb200_q_grad_compute(lb200_t * c) {
+  CTX_ENTER(c);
+  if (c->q == nullptr) return fail(LB200_ESTATE, "no q in this context");
+  if (c->qgrad == nullptr) {
+    if (alloc_d(&c->qgrad, (size_t) 15*c->g.nsites) != 0 || alloc_d(&c->qdelsq, (size_t) 5*c->g.nsites) != 0) return LB200_ECUDA;
+  }
+  {
+    ProfScope ps(c, LB200_K_GRAD);
+    c->launches += c->k->grad7(c->stream, c->g, c->g.nh - 1, 5, c->q, c->qgrad, c->qdelsq);
+  }
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_lc_stress_compute(lb200_t * c, const lb200_lc_param_t * lc) {
+  CTX_ENTER(c);
+  Lb200LcDev d;
+  int rc = lc_dev(c, lc, &d);
+  if (rc != 0) return rc;
+  {
+    ProfScope ps(c, LB200_K_LC_STRESS);
+    c->launches += c->k->lc_stress(c->stream, c->g, d, 1, c->q, c->str);
+  }
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_lc_force_calculation(lb200_t * c, const lb200_lc_param_t * lc) {
+  CTX_ENTER(c);
+  Lb200LcDev d;
+  int rc = lc_dev(c, lc, &d);
+  if (rc != 0) return rc;
+  {
+    ProfScope ps(c, LB200_K_LC_STRESS);
+    c->launches += c->k->lc_stress(c->stream, c->g, d, 1, c->q, c->str);
+  }
+  {
+    const int accumulate = (c->force_state != ZERO_PENDING);
+    ProfScope ps(c, LB200_K_LC_BE);
+    c->launches += c->k->lc_force_be(c->stream, c->g, d, 1, 0, accumulate, c->q, c->str, c->u, c->force, nullptr);
+    if (c->force_state == ZERO_PENDING) c->force_state = INTERIOR_ONLY;
+  }
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_beris_edw_update(lb200_t * c, const lb200_lc_param_t * lc) {
+  CTX_ENTER(c);
+  Lb200LcDev d;
+  int rc = lc_dev(c, lc, &d);
+  if (rc != 0) return rc;
+  if (c->u_state != ARRAY_CLEAN) materialise_zero(c, c->u, &c->u_state);
+  // qnew holds q everywhere (halo included) so that the swap keeps the reference's view of the array
+  CUDA_TRY(cudaMemcpyAsync(c->qnew, c->q, (size_t) 5*c->g.nsites*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  {
+    ProfScope ps(c, LB200_K_LC_BE);
+    c->launches += c->k->lc_force_be(c->stream, c->g, d, 0, 1, 0, c->q, nullptr, c->u, nullptr, c->qnew);
+  }
+  { double * t = c->q; c->q = c->qnew; c->qnew = t; }
+  CTX_LEAVE_SYNC(c);
+}
+
+int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_param_t * lc, int nsteps) {
+  if (c == nullptr) return fail(LB200_EINVAL, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (cp == nullptr) return fail(LB200_EINVAL, "null collision parameters");
+  Lb200CollideDev cd;
+  Lb200LcDev d;
+  int rc = collide_dev(c, cp, &cd);
+  if (rc != 0) return rc;
+  rc = lc_dev(c, lc, &d);
+  if (rc != 0) return rc;
+  if (nsteps <= 0) return 0;
+  cudaStream_t S = c->stream;
+  const Lb200Geom & g = c->g;
+  bool wrap = c->knob_wrap && g.per[0] && g.per[1] && g.per[2];
+  for (int a = 0; a < 3; a++) wrap = wrap && (g.nl[a] >= 2*g.nh);
+  Lb200Geom gw = c->g;
+  if (wrap) gw.wrap[0] = gw.wrap[1] = gw.wrap[2] = 1;
+  if (!wrap) {
+    rc = ensure_f_halo(c);
+    if (rc != 0) return rc;
+  }
+  if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+
+  for (int n = 0; n < nsteps; n++) {
+    c->force_state = ZERO_PENDING;                                       // hydro_f_zero
+    if (!wrap) {
+      rc = halo_field(c, c->q, 5, g.nh, 0, S);                           // field_halo(q)
+      if (rc != 0) return rc;
+    }
+    {
+      // field_grad_compute + pth_stress_compute: gradients in registers, only the stress is stored
+      ProfScope ps(c, LB200_K_LC_STRESS);
+      c->launches += c->k->lc_stress(S, gw, d, wrap ? 0 : 1, c->q, c->str);
+    }
+    if (!wrap) {
+      if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+      rc = halo_field(c, c->u, 3, g.nh, 0, S);                           // hydro_u_halo
+      if (rc != 0) return rc;
+      c->u_state = ARRAY_CLEAN;
+    }
+    {
+      // pth_force_fluid_driver + beris_edw_update
+      ProfScope ps(c, LB200_K_LC_BE);
+      c->launches += c->k->lc_force_be(S, gw, d, 1, 1, 0, c->q, c->str, c->u, c->force, c->qnew);
+    }
+    c->force_state = INTERIOR_ONLY;
+    { double * t = c->q; c->q = c->qnew; c->qnew = t; }
+    c->u_state = ZERO_PENDING;                                           // hydro_u_zero
+    if (wrap) {
+      ProfScope ps(c, LB200_K_COLLIDE);
+      if (c->prop_pending) {
+	c->launches += c->k->collide(S, gw, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, c->u);
+	double * t = c->f; c->f = c->fprime; c->fprime = t;
+	c->prop_pending = 0;
+      }
+      else {
+	c->launches += c->k->collide(S, c->g, cd, model_ptr(c), c->nvel, 0, c->f, c->f, c->force, status_ptr(c), c->rho, c->u);
+      }
+      c->u_state = INTERIOR_ONLY;
+      c->prop_pending = 1;                                               // lb_halo; lb_propagation (lazy)
+      c->f_halo_stale = 1;
+    }
+    else {
+      rc = collide_async(c, cd);
+      if (rc != 0) return rc;
+      rc = halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED, S);   // lb_halo
+      if (rc != 0) return rc;
+      c->prop_pending = 1;
+      c->f_halo_stale = 0;
+    }
+  }
+  c->phi_halo_valid = 0;
+  c->u_halo_valid = 0;
+  c->wrap_x_valid = 0;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -1895,6 +1895,7 @@ int launch_zero_outside(cudaStream_t st, const Lb200Geom & g, int ncomp, double 
 }
 
 #include "lb200_le.cuh"
+#include "lb200_lc.cuh"
 
 }  // anonymous namespace
 }  // namespace lb200_fast / lb200_strict
@@ -1928,4 +1929,7 @@ const Lb200Kernels LB200_TABLE = {
   launch_le_ch_prep,
   launch_le_force_ch,
   launch_le_lb_bc,
+  launch_grad7,
+  launch_lc_stress,
+  launch_lc_force_be,
 };

@@ -49,6 +49,15 @@ struct Lb200LeFix {
   double ra;            // 0.5/(Ly Lz), force flux correction
 };
 
+// liquid crystal (fe_lc_param_t + beris_edw_param_t, src/blue_phase.h:52-75, src/blue_phase_beris_edwards.h:30-37)
+struct Lb200LcDev {
+  double a0, q0, gamma, kappa0, kappa1, xi;
+  double Gamma;         // rotational diffusion constant
+  double epsilon;       // dielectric anisotropy, already divided by 12 pi
+  double e0[3];
+  int order;            // advection order 1..3
+};
+
 struct Lb200CollideDev {
   double fg[3];         // force_global
   double rtau;          // 1/tau_shear
@@ -139,6 +148,12 @@ struct Lb200Kernels {
 		     const double * fcor, const double * chx, double * force, double * phinew);
   int (*le_lb_bc)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200LeFix &, const Lb200ModelDev *,
 		  int ndist, double * f, double * sbuf);
+  // liquid crystal (lb200_lc.cuh): 7-point gradient arrays of nf components on [1-ne, N+ne]^3; the stress from the
+  // 7-point star of Q; force from the stored stress and / or the Beris-Edwards update in one sweep
+  int (*grad7)(cudaStream_t, const Lb200Geom &, int ne, int nf, const double * field, double * grad, double * delsq);
+  int (*lc_stress)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int ne, const double * q, double * str);
+  int (*lc_force_be)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int do_force, int do_be, int accumulate,
+		     const double * q, const double * str, const double * u, double * force, double * qnew);
 };
 
 extern const Lb200Kernels lb200_kernels_fast;
