@@ -401,7 +401,7 @@ LC = dict(a0=0.01, q0=0.19635, gamma=3.0, kappa0=0.000648456, kappa1=0.000648456
 LC_B_ALG = {"stress": 40.0 + 72.0, "force_be": 72.0 + 40.0 + 24.0 + 24.0 + 40.0, "collide": 360.0}
 
 
-def run_lc(args, local_rank):
+def run_lc(args, rank, local_rank, world):
     """python bench.py --lc [--size 128]: Landau-de Gennes Q tensor + Beris-Edwards coupled to D3Q19,
     cholesteric twist initial state (tests/regression/d3q19/pmpi08-chol-s01.inp parameters, advection order 3)."""
     import numpy as np
@@ -409,10 +409,32 @@ def run_lc(args, local_rank):
     import ludwig_b200 as lb
     from ludwig_b200.initial import lc_twist_q
 
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     n = args.size
     nlocal = (n, n, n)
-    sim = lb.Lb200(nlocal, nhalo=2, have_q=True, math=lb.MATH_STRICT if args.strict else lb.MATH_FAST, device=local_rank)
+    sim = lb.Lb200(nlocal, nhalo=2, have_q=True, math=lb.MATH_STRICT if args.strict else lb.MATH_FAST, device=local_rank,
+                   cart_size=world, cart_rank=rank)
+    if world > 1:
+        ids = [sim.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sim.nccl_init(ids[0], world, rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sim.sync()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     ns = sim.nsites
     h_f = torch.empty((19, ns), dtype=torch.float64, pin_memory=True)
     h_q = torch.empty((5, ns), dtype=torch.float64, pin_memory=True)
@@ -420,7 +442,7 @@ def run_lc(args, local_rank):
     wv = np.array([12.0] + [2.0 if sum(abs(c) for c in cv) == 1 else 1.0 for cv in CV19[1:]]) / 36.0
     for p in range(19):
         h_f.numpy()[p, :] = wv[p]
-    rng = np.random.default_rng(8361235)
+    rng = np.random.default_rng(8361235 + rank)
     h_q.numpy()[...] = lc_twist_q(nlocal, 2, LC["q0"], 1.0 / 3.0, 2)
     sim.interior(h_q.numpy())[...] += 0.01 * (rng.random((5,) + nlocal) - 0.5)
     cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, 0.1)
@@ -433,24 +455,25 @@ def run_lc(args, local_rank):
         sim.memcpy_async(lb.Q, h_q.data_ptr(), H2D)
 
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if rank == 0:
+        clocks.start()
     upload()
     sim.sync()
     sim.step_lc(cp, lc, args.warmup)
-    sim.sync()
+    barrier()
     clocks.mark_begin()
     l0 = sim.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     sim.step_lc(cp, lc, args.steps)
     e1.record(stream)
-    sim.sync()
+    barrier()
     clocks.mark_end()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = sim.launch_count() - l0
-    clk = clocks.stop()
+    clk = clocks.stop() if rank == 0 else None
     sites = float(n) ** 3
-    mlups = sites * args.steps / (ms * 1e-3) / 1e6
+    mlups = sites * world * args.steps / (ms * 1e-3) / 1e6
 
     sim.profile(True)
     sim.step_lc(cp, lc, min(args.steps, 20))
@@ -464,6 +487,7 @@ def run_lc(args, local_rank):
         t = kernels.get(key, {}).get("ms_per_launch")
         return alg * sites / (t * 1e-3) / 1e9 if t else None
 
+    barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     t0.record(stream)
@@ -473,11 +497,13 @@ def run_lc(args, local_rank):
     sim.memcpy_async(lb.U, h_u.data_ptr(), D2H)
     t1.record(stream)
     sim.sync()
-    e2e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0) * 1e3)
+    wall = (time.perf_counter() - w0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(max(t0.elapsed_time(t1), wall))
     q_sum = float(np.nansum(sim.interior(h_q.numpy())[0]))
 
     cpu = None
-    if not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import refharness
@@ -495,12 +521,17 @@ def run_lc(args, local_rank):
             cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "reference", "sample": f"failed: {exc}"}
 
     b_step = LC_B_ALG["stress"] + LC_B_ALG["force_be"] + LC_B_ALG["collide"]
+    if rank != 0:
+        sim.close()
+        dist.destroy_process_group()
+        return
     line = {
-        "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"D3Q19 + liquid crystal (Landau-de Gennes Q tensor, Beris-Edwards, 7pt gradient, advection order 3), "
-                               f"{n}^3 on one GPU, cholesteric twist + noise (pmpi08-chol-s01.inp parameters); halo-free steps",
+                               f"{n}^3 per GPU, cholesteric twist + noise (pmpi08-chol-s01.inp parameters); "
+                               + ("halo-free steps" if world == 1 else f"{world}_1_1 x-slabs, halo kernels + NCCL x-planes of q, u, f"),
                    "lattice_per_gpu": list(nlocal), "math": "strict" if args.strict else "fast(fma)",
                    "l2": f"lattice state per step {b_step * sites / 1e9:.2f} GB vs 126 MB L2"},
         "roofline": {"bound": "hbm", "kernel": "collide_d3q19 (pull-stream + MRT collision)",
@@ -509,15 +540,17 @@ def run_lc(args, local_rank):
                      "algorithmic_bytes_per_site": LC_B_ALG["collide"],
                      "lc_stress": {"algorithmic_bytes_per_site": LC_B_ALG["stress"], "achieved": gbs("lc_stress", LC_B_ALG["stress"])},
                      "lc_force_be": {"algorithmic_bytes_per_site": LC_B_ALG["force_be"], "achieved": gbs("lc_be", LC_B_ALG["force_be"])},
-                     "whole_step": {"algorithmic_bytes_per_site": b_step, "achieved": mlups * 1e6 * b_step / 1e9,
-                                    "frac": mlups * 1e6 * b_step / 1e9 / peak}},
+                     "whole_step": {"algorithmic_bytes_per_site": b_step, "achieved": mlups / world * 1e6 * b_step / 1e9,
+                                    "frac": mlups / world * 1e6 * b_step / 1e9 / peak}},
         "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
-        "e2e": {"value": sites * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS",
+        "e2e": {"value": sites * world * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS",
                 "h2d_bytes_per_step": (19 + 5) * ns * 8 / args.steps, "d2h_bytes_per_step": (5 + 3) * ns * 8 / args.steps},
         "gpu_launches": launches, "check": {"qxx_sum": q_sum},
     }
     print(json.dumps(line), flush=True)
     sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():
@@ -545,10 +578,10 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
-    if args.lc:
+    if args.lc and not (world == 1 and args.gpus > 1):
         if "--size" not in sys.argv:
             args.size = 128
-        run_lc(args, local_rank)
+        run_lc(args, rank, local_rank, world)
         return
     if world == 1 and args.gpus > 1:
         # not under torchrun: launch ourselves one process per GPU

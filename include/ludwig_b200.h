@@ -94,7 +94,8 @@ typedef struct lb200_options_s {
   double le_uy;             /* LE_plane_vel */
   int le_nt0;               /* reference time step (lees_edw_options_t.nt0, usually 0) */
   /* free_energy lc_blue_phase (src/ludwig.c:1598-1666): the tensor order parameter q (5 components, nhalo >= 2).
-   * Exclusive with have_phi; one GPU (cart_size == 1) and no Lees-Edwards planes in this round. */
+   * Exclusive with have_phi; no Lees-Edwards planes in this round.  x-slabs (cart_size > 1) exchange the x-planes
+   * of q (depth nhalo), u and f over NCCL. */
   int have_q;
 } lb200_options_t;
 

@@ -500,7 +500,7 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   if (o->cart_size < 1 || o->cart_rank < 0 || o->cart_rank >= o->cart_size) return fail(LB200_EINVAL, "bad cart_size/cart_rank");
   if (o->have_q && (o->have_phi || o->ndist != 1)) return fail(LB200_EINVAL, "have_q (lc_blue_phase) excludes have_phi / ndist = 2");
   if (o->have_q && o->nhalo < 2) return fail(LB200_EINVAL, "the liquid crystal needs nhalo >= 2 (reference src/ludwig.c:1605)");
-  if (o->have_q && (o->cart_size != 1 || o->le_nplanes != 0)) return fail(LB200_EINVAL, "have_q: one GPU and no Lees-Edwards planes in this build");
+  if (o->have_q && o->le_nplanes != 0) return fail(LB200_EINVAL, "have_q: no Lees-Edwards planes in this build");
   if (o->halo_scheme != LB200_HALO_FULL && o->halo_scheme != LB200_HALO_REDUCED) return fail(LB200_EINVAL, "halo_scheme = %d", o->halo_scheme);
 
   int ndev = 0;
@@ -571,7 +571,8 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   }
   if (g.remote_x) {
     // staging: nvel planes of depth 1 (f) | 3 components of depth nhalo (u) | nhalo planes (phi)
-    c->stage_doubles = (size_t) c->nvel*c->ndist*g.xs + (size_t) 3*g.nh*g.xs + (size_t) g.nh*g.xs;
+    c->stage_doubles = (size_t) c->nvel*c->ndist*g.xs + (size_t) 3*g.nh*g.xs + (size_t) g.nh*g.xs
+      + (o->have_q ? (size_t) 5*g.nh*g.xs : 0);
     rc |= alloc_d(&c->xlo, c->stage_doubles);
     rc |= alloc_d(&c->xhi, c->stage_doubles);
     rc |= alloc_d(&c->slo, c->stage_doubles);
@@ -816,6 +817,7 @@ static double * stage_ptr(lb200_t * c, double * base, const double * data) {
   const size_t xs = (size_t) c->g.xs;
   if (data == c->u) return base + (size_t) c->nvel*c->ndist*xs;
   if (data == c->phi || data == c->phinew) return base + (size_t) c->nvel*c->ndist*xs + (size_t) 3*c->g.nh*xs;
+  if (c->q != nullptr && (data == c->q || data == c->qnew)) return base + (size_t) c->nvel*c->ndist*xs + (size_t) 4*c->g.nh*xs;
   return base;
 }
 static double * stage_lo(lb200_t * c, const double * data) { return stage_ptr(c, c->xlo, data); }
@@ -1850,7 +1852,8 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
   if (nsteps <= 0) return 0;
   cudaStream_t S = c->stream;
   const Lb200Geom & g = c->g;
-  bool wrap = c->knob_wrap && g.per[0] && g.per[1] && g.per[2];
+  // halo-free on one GPU; x-slabs use the reference's structure (halo kernels + NCCL x-planes of q, u, f)
+  bool wrap = c->knob_wrap && g.per[0] && g.per[1] && g.per[2] && !g.remote_x;
   for (int a = 0; a < 3; a++) wrap = wrap && (g.nl[a] >= 2*g.nh);
   Lb200Geom gw = c->g;
   if (wrap) gw.wrap[0] = gw.wrap[1] = gw.wrap[2] = 1;

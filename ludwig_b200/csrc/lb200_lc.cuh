@@ -16,6 +16,12 @@
 // fe_lc_compute_stress_v, src/blue_phase.c:1908-2775; beris_edw_kernel_v, src/blue_phase_beris_edwards.c:538-850),
 // including their use of kappa1 = kappa0 in the molecular field and the free-energy density.
 
+#ifndef LC_BE_MINB
+#define LC_BE_MINB 4
+#endif
+#ifndef LC_ST_MINB
+#define LC_ST_MINB 4
+#endif
 __device__ constexpr int LC_D[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
 __device__ constexpr int LC_E[3][3][3] = {{{0, 0, 0}, {0, 0, 1}, {0, -1, 0}},
 					   {{0, 0, -1}, {0, 0, 0}, {1, 0, 0}},
@@ -278,7 +284,7 @@ int launch_grad7(cudaStream_t st, const Lb200Geom & g, int ne, int nf, const dou
 // stress on [1-ne, N+ne]^3 (ne = 1 when the divergence reads halo sites, 0 in halo-free steps)
 // ---------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, LC_ST_MINB)
 lc_stress_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, int ne, const double * __restrict__ qf,
 		 double * __restrict__ str) {
   const int kc = 1 - ne + blockIdx.x*blockDim.x + threadIdx.x;
@@ -312,7 +318,7 @@ int launch_lc_stress(cudaStream_t st, const Lb200Geom & g, const Lb200LcDev & p,
 // ---------------------------------------------------------------------------------------------
 
 template <bool DO_FORCE, bool DO_BE, int ORDER>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, LC_BE_MINB)
 lc_force_be_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, const int accumulate,
 		   const double * __restrict__ qf, const double * __restrict__ str, const double * __restrict__ u,
 		   double * __restrict__ force, double * __restrict__ qnew) {

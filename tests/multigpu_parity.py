@@ -19,6 +19,56 @@ from common import BINARY, ETA, close_fast, seeded_state  # noqa: E402
 from oracle import Oracle  # noqa: E402
 
 
+LC = dict(a0=0.01, q0=0.19635, gamma=3.0, kappa0=0.000648456, kappa1=0.0008, xi=0.7, Gamma=0.5)
+
+
+def main_lc(rank, world, local):
+    """liquid crystal on x-slabs (strict) == the undecomposed liquid-crystal oracle, bit for bit"""
+    from ludwig_b200.initial import equilibrium_f, lc_twist_q
+    nxl, ny, nz, nhalo, nsteps = 6, 10, 34, 2, 6
+    n = (nxl * world, ny, nz)
+    orc_g = Oracle(n, nhalo=nhalo)
+    orc_l = Oracle((nxl, ny, nz), nhalo=nhalo)
+    rng = np.random.default_rng(5)
+    q = lc_twist_q(n, nhalo, LC["q0"], 1.0 / 3.0, 0)
+    orc_g.interior(q)[...] += 0.02 * (rng.random(orc_g.interior(q).shape) - 0.5)
+    f = equilibrium_f(n, nhalo)
+
+    def slab(a):
+        v = a.reshape((a.shape[0],) + orc_g.nall)
+        out = np.zeros((v.shape[0],) + orc_l.nall)
+        out[:, nhalo:nhalo + nxl] = v[:, nhalo + rank * nxl:nhalo + (rank + 1) * nxl]
+        return out.reshape(v.shape[0], -1)
+
+    sim = lb.Lb200((nxl, ny, nz), nhalo=nhalo, have_q=True, math=lb.MATH_STRICT, device=local, cart_size=world, cart_rank=rank)
+    ids = [sim.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    sim.nccl_init(ids[0], world, rank)
+    sim.put(lb.F, slab(f)); sim.put(lb.Q, slab(q))
+    cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, 0.1)
+    pg = lb.LcParam.make(adv_order=3, **LC)
+    sim.step_lc(cp, pg, 2); sim.step_lc_api(cp, pg, 2); sim.step_lc(cp, pg, nsteps - 4)
+    mine = {k: np.ascontiguousarray(orc_l.interior(sim.get(a))) for k, a in (("f", lb.F), ("q", lb.Q), ("u", lb.U), ("force", lb.FORCE))}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    ok = True
+    if rank == 0:
+        z = lambda k: np.zeros((k, orc_g.nsites))
+        u, rho, force, qgrad, qdelsq = z(3), z(1), z(3), z(15), z(5)
+        orc_g.lc_step(orc_g.collide_param(0, 1.0, 0.1), orc_g.lc_param(**LC), 3, nsteps, f, q, u, rho, force, qgrad, qdelsq)
+        want = dict(f=f, q=q, u=u, force=force)
+        for k in mine:
+            full = np.concatenate([g[k] for g in gathered], axis=1)
+            same = np.array_equal(full, orc_g.interior(want[k]))
+            print(f"multigpu liquid-crystal parity world={world} {k}: {'OK' if same else 'MISMATCH'}", flush=True)
+            ok = ok and same
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    sim.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -31,6 +81,8 @@ def main():
     binary = 1 if len(sys.argv) < 5 else int(sys.argv[4])
     le = 0 if len(sys.argv) < 6 else int(sys.argv[5])          # Lees-Edwards planes per slab (plane speed 0.05)
     fast = 0 if len(sys.argv) < 7 else int(sys.argv[6])        # 1: LB200_MATH_FAST, compared within tolerance
+    if len(sys.argv) >= 8 and int(sys.argv[7]):
+        return main_lc(rank, world, local)
     if le:
         nxl = 8*le
     nglobal = (nxl * world, ny, nz)
