@@ -1800,7 +1800,7 @@ int lb200_lc_stress_compute(lb200_t * c, const lb200_lc_param_t * lc) {
   if (rc != 0) return rc;
   {
     ProfScope ps(c, LB200_K_LC_STRESS);
-    c->launches += c->k->lc_stress(c->stream, c->g, d, 1, c->q, c->str);
+    c->launches += c->k->lc_stress(c->stream, c->g, d, 1, 1, c->q, c->str);
   }
   CTX_LEAVE_SYNC(c);
 }
@@ -1812,7 +1812,7 @@ int lb200_lc_force_calculation(lb200_t * c, const lb200_lc_param_t * lc) {
   if (rc != 0) return rc;
   {
     ProfScope ps(c, LB200_K_LC_STRESS);
-    c->launches += c->k->lc_stress(c->stream, c->g, d, 1, c->q, c->str);
+    c->launches += c->k->lc_stress(c->stream, c->g, d, 1, 1, c->q, c->str);
   }
   {
     const int accumulate = (c->force_state != ZERO_PENDING);
@@ -1839,6 +1839,25 @@ int lb200_beris_edw_update(lb200_t * c, const lb200_lc_param_t * lc) {
   CTX_LEAVE_SYNC(c);
 }
 
+// `depth` boundary x-planes of every component of a field straight into the neighbours' halo planes (each component's
+// planes are contiguous: no staging), one NCCL group
+static int wrap_exchange_field(lb200_t * c, cudaStream_t st, double * data, int ncomp, int depth) {
+  const Lb200Geom & g = c->g;
+  const size_t xs = (size_t) g.xs, ns = (size_t) g.nsites;
+  XMsg m[8];
+  if (ncomp > 8) return fail(LB200_EINVAL, "wrap_exchange_field: ncomp = %d", ncomp);
+  for (int n = 0; n < ncomp; n++) {
+    double * a = data + n*ns;
+    m[n].send_hi = a + (size_t) (g.nl[0] - depth + g.nh)*xs;
+    m[n].send_lo = a + (size_t) g.nh*xs;
+    m[n].recv_lo = a + (size_t) (g.nh - depth)*xs;
+    m[n].recv_hi = a + (size_t) (g.nl[0] + g.nh)*xs;
+    m[n].count = (size_t) depth*xs;
+  }
+  ProfScope ps(c, LB200_K_HALO, st);
+  return nccl_exchange(c, st, m, ncomp);
+}
+
 int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_param_t * lc, int nsteps) {
   if (c == nullptr) return fail(LB200_EINVAL, "null context");
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1850,18 +1869,32 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
   rc = lc_dev(c, lc, &d);
   if (rc != 0) return rc;
   if (nsteps <= 0) return 0;
-  cudaStream_t S = c->stream;
   const Lb200Geom & g = c->g;
-  // halo-free on one GPU; x-slabs use the reference's structure (halo kernels + NCCL x-planes of q, u, f)
-  bool wrap = c->knob_wrap && g.per[0] && g.per[1] && g.per[2] && !g.remote_x;
+  // halo-free steps on periodic lattices: every y / z (one GPU: also x) periodic image is read in-kernel; x-slabs
+  // exchange only the x-planes the kernels read (q: nhalo, u: 1, f: the populations crossing) over NCCL on the comm
+  // stream, overlapped with the kernels that do not need them.  Otherwise the reference's structure with halo kernels.
+  bool wrap = c->knob_wrap && g.per[0] && g.per[1] && g.per[2];
   for (int a = 0; a < 3; a++) wrap = wrap && (g.nl[a] >= 2*g.nh);
+  const bool remote = wrap && g.remote_x;
+  cudaStream_t S = c->stream, C = (remote && !c->profile) ? c->comm : c->stream;
   Lb200Geom gw = c->g;
-  if (wrap) gw.wrap[0] = gw.wrap[1] = gw.wrap[2] = 1;
+  if (wrap) { gw.wrap[0] = !g.remote_x; gw.wrap[1] = gw.wrap[2] = 1; }
   if (!wrap) {
     rc = ensure_f_halo(c);
     if (rc != 0) return rc;
   }
   if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+  if (remote) {
+    // bring the planes the first kernels read (the state did not come out of a previous halo-free step)
+    CUDA_TRY(cudaEventRecord(c->ev_main, S));
+    CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+    if ((rc = wrap_exchange_field(c, C, c->q, 5, g.nh)) != 0) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+    if ((rc = wrap_exchange_field(c, C, c->u, 3, 1)) != 0) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_u, C));
+    if (c->prop_pending && (rc = wrap_exchange_f(c, C)) != 0) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_f, C));
+  }
 
   for (int n = 0; n < nsteps; n++) {
     c->force_state = ZERO_PENDING;                                       // hydro_f_zero
@@ -1869,10 +1902,11 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
       rc = halo_field(c, c->q, 5, g.nh, 0, S);                           // field_halo(q)
       if (rc != 0) return rc;
     }
+    if (remote) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
     {
       // field_grad_compute + pth_stress_compute: gradients in registers, only the stress is stored
       ProfScope ps(c, LB200_K_LC_STRESS);
-      c->launches += c->k->lc_stress(S, gw, d, wrap ? 0 : 1, c->q, c->str);
+      c->launches += c->k->lc_stress(S, gw, d, (!wrap || remote) ? 1 : 0, wrap ? 0 : 1, c->q, c->str);
     }
     if (!wrap) {
       if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
@@ -1880,27 +1914,53 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
       if (rc != 0) return rc;
       c->u_state = ARRAY_CLEAN;
     }
+    if (remote) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
     {
       // pth_force_fluid_driver + beris_edw_update
+      // two sweeps (default; the 64-register force gather runs at high occupancy on its own: 1.19 vs 1.52 ms at 256^3) or one (LB200_LC_SPLIT=0)
+      static const int split = getenv("LB200_LC_SPLIT") ? atoi(getenv("LB200_LC_SPLIT")) : 1;
       ProfScope ps(c, LB200_K_LC_BE);
-      c->launches += c->k->lc_force_be(S, gw, d, 1, 1, 0, c->q, c->str, c->u, c->force, c->qnew);
+      if (split) {
+	c->launches += c->k->lc_force_be(S, gw, d, 1, 0, 0, c->q, c->str, c->u, c->force, c->qnew);
+	c->launches += c->k->lc_force_be(S, gw, d, 0, 1, 0, c->q, c->str, c->u, c->force, c->qnew);
+      }
+      else {
+	c->launches += c->k->lc_force_be(S, gw, d, 1, 1, 0, c->q, c->str, c->u, c->force, c->qnew);
+      }
     }
     c->force_state = INTERIOR_ONLY;
     { double * t = c->q; c->q = c->qnew; c->qnew = t; }
+    if (remote) {
+      CUDA_TRY(cudaEventRecord(c->ev_main, S));
+      CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+      if ((rc = wrap_exchange_field(c, C, c->q, 5, g.nh)) != 0) return rc;      // overlaps the collision
+      CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+    }
     c->u_state = ZERO_PENDING;                                           // hydro_u_zero
     if (wrap) {
-      ProfScope ps(c, LB200_K_COLLIDE);
-      if (c->prop_pending) {
-	c->launches += c->k->collide(S, gw, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, c->u);
-	double * t = c->f; c->f = c->fprime; c->fprime = t;
-	c->prop_pending = 0;
-      }
-      else {
-	c->launches += c->k->collide(S, c->g, cd, model_ptr(c), c->nvel, 0, c->f, c->f, c->force, status_ptr(c), c->rho, c->u);
+      if (remote) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
+      {
+	ProfScope ps(c, LB200_K_COLLIDE);
+	if (c->prop_pending) {
+	  c->launches += c->k->collide(S, gw, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, c->u);
+	  double * t = c->f; c->f = c->fprime; c->fprime = t;
+	  c->prop_pending = 0;
+	}
+	else {
+	  c->launches += c->k->collide(S, c->g, cd, model_ptr(c), c->nvel, 0, c->f, c->f, c->force, status_ptr(c), c->rho, c->u);
+	}
       }
       c->u_state = INTERIOR_ONLY;
       c->prop_pending = 1;                                               // lb_halo; lb_propagation (lazy)
       c->f_halo_stale = 1;
+      if (remote) {
+	CUDA_TRY(cudaEventRecord(c->ev_main, S));
+	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+	if ((rc = wrap_exchange_field(c, C, c->u, 3, 1)) != 0) return rc;       // the next Beris-Edwards sweep waits for this
+	CUDA_TRY(cudaEventRecord(c->ev_u, C));
+	if ((rc = wrap_exchange_f(c, C)) != 0) return rc;                       // overlaps the next two LC sweeps
+	CUDA_TRY(cudaEventRecord(c->ev_f, C));
+      }
     }
     else {
       rc = collide_async(c, cd);
@@ -1910,6 +1970,11 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
       c->prop_pending = 1;
       c->f_halo_stale = 0;
     }
+  }
+  if (remote) {
+    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
+    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
+    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
   }
   c->phi_halo_valid = 0;
   c->u_halo_valid = 0;

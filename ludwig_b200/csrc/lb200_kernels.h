@@ -151,7 +151,7 @@ struct Lb200Kernels {
   // liquid crystal (lb200_lc.cuh): 7-point gradient arrays of nf components on [1-ne, N+ne]^3; the stress from the
   // 7-point star of Q; force from the stored stress and / or the Beris-Edwards update in one sweep
   int (*grad7)(cudaStream_t, const Lb200Geom &, int ne, int nf, const double * field, double * grad, double * delsq);
-  int (*lc_stress)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int ne, const double * q, double * str);
+  int (*lc_stress)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int nex, int ne, const double * q, double * str);
   int (*lc_force_be)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int do_force, int do_be, int accumulate,
 		     const double * q, const double * str, const double * u, double * force, double * qnew);
 };
