@@ -337,6 +337,22 @@ int phi_lb_to_field(field_t * phi, lb_t * lb);
 int phi_lb_from_field(field_t * phi, lb_t * lb);
 int advection_order(int * order);
 
+/* ---- on-disk formats: src/lb_data.c:1533-1575, 1716-1830, src/field.c:896-930, 1633-1740,
+ * src/io_subfile.c:186-204, src/io_metadata.c.  One file per quantity and time step, "<stub>-%9.9d.001-001": the
+ * interior sites in (ic, jc, kc) order with kc fastest, one binary record per site (distributions: ndist*nvel
+ * doubles in (n, p) order; fields: nf doubles), plus "<stub>-metadata.001-001" (JSON, written once).  Files are
+ * byte-identical with the reference's default (mpiio, binary, single file) output, so either code restarts from
+ * the other's. */
+typedef struct io_event_s {int unused;} io_event_t;
+int lb_write_buf(const lb_t * lb, int index, char * buf);
+int lb_read_buf(lb_t * lb, int index, const char * buf);
+int lb_io_write(lb_t * lb, int timestep, io_event_t * event);
+int lb_io_read(lb_t * lb, int timestep, io_event_t * event);
+int field_write_buf(field_t * field, int index, char * buf);
+int field_read_buf(field_t * field, int index, const char * buf);
+int field_io_write(field_t * field, int timestep, io_event_t * event);
+int field_io_read(field_t * field, int timestep, io_event_t * event);
+
 /* ---- collision and propagation: src/collision.h:27-28, src/propagation.h:21 ------------------- */
 int lb_collide(lb_t * lb, hydro_t * hydro, map_t * map, noise_t * noise, fe_t * fe, visc_t * visc);
 int lb_propagation(lb_t * lb);

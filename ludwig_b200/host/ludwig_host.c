@@ -889,6 +889,171 @@ int phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t * hydro,
   return 0;
 }
 
+
+/* ---- on-disk formats --------------------------------------------------------------------------------------- */
+
+/* src/io_subfile.c:186-204 (one file: index 0 of 1) */
+static void io_file_name(const char * stub, int it, char * filename, size_t bufsz) {
+  snprintf(filename, bufsz, "%s-%9.9d.%3.3d-%3.3d", stub, it, 1, 1);
+}
+
+/* the reference's metadata file for the default options (mode mpiio, binary records, one file): same text */
+static int io_metadata_write_default(cs_t * cs, const char * stub, int count) {
+  char filename[BUFSIZ];
+  FILE * fp = NULL;
+  int nplanes = cs->le ? lees_edw_nplane_total(cs->le) : 0;
+  snprintf(filename, BUFSIZ, "%s-metadata.%3.3d-%3.3d", stub, 1, 1);
+  fp = fopen(filename, "w");
+  if (fp == NULL) return -1;
+  fprintf(fp, "{\n\t\"coords\":\t{\n\t\t\"options\":\t{\n");
+  fprintf(fp, "\t\t\t\"System size (total)\":\t[%d, %d, %d],\n", cs->ntotal[X], cs->ntotal[Y], cs->ntotal[Z]);
+  fprintf(fp, "\t\t\t\"Periodic boundaries\":\t[%d, %d, %d],\n", cs->periodic[X], cs->periodic[Y], cs->periodic[Z]);
+  fprintf(fp, "\t\t\t\"Left-end limit Lmin\":\t[0.5, 0.5, 0.5]\n\t\t},\n");
+  fprintf(fp, "\t\t\"lees_edwards\":\t{\n\t\t\t\"Number of planes\":\t%d", nplanes);
+  if (nplanes > 0) {
+    /* lees_edw_opts_to_json, src/lees_edwards_options.c; numbers as cJSON prints them (%1.15g, else %1.17g) */
+    char num[64];
+    double back = 0.0;
+    snprintf(num, sizeof(num), "%1.15g", cs->le->opts.uy);
+    if (sscanf(num, "%lg", &back) != 1 || back != cs->le->opts.uy) snprintf(num, sizeof(num), "%1.17g", cs->le->opts.uy);
+    fprintf(fp, ",\n\t\t\t\"Shear type\":\t\"STEADY\",\n\t\t\t\"Reference time\":\t%d,\n\t\t\t\"Plane speed\":\t%s",
+	    cs->le->opts.nt0, num);
+  }
+  fprintf(fp, "\n\t\t}\n\t},\n");
+  fprintf(fp, "\t\"io_options\":\t{\n\t\t\"Mode\":\t\"mpiio\",\n\t\t\"Record format\":\t\"binary\",\n\t\t\"Metadata version\":\t3,\n"
+	  "\t\t\"Report\":\tfalse,\n\t\t\"Asynchronous\":\tfalse,\n\t\t\"Compression level\":\t0,\n\t\t\"I/O grid\":\t[1, 1, 1]\n\t},\n");
+  fprintf(fp, "\t\"io_element\":\t{\n\t\t\"MPI_Datatype\":\t\"MPI_DOUBLE\",\n\t\t\"Size (bytes)\":\t8,\n\t\t\"Count\":\t%d,\n"
+	  "\t\t\"Endianness\":\t\"LITTLE_ENDIAN\"\n\t},\n", count);
+  fprintf(fp, "\t\"io_subfile\":\t{\n\t\t\"Number of files\":\t1,\n\t\t\"File index\":\t0,\n\t\t\"Topology\":\t[1, 1, 1],\n"
+	  "\t\t\"Coordinate\":\t[0, 0, 0],\n\t\t\"Data ndims\":\t3,\n\t\t\"File size (sites)\":\t[%d, %d, %d],\n"
+	  "\t\t\"File offset (sites)\":\t[0, 0, 0]\n\t}\n}", cs->nlocal[X], cs->nlocal[Y], cs->nlocal[Z]);
+  fclose(fp);
+  return 0;
+}
+
+/* src/lb_data.c:1533-1575 */
+int lb_write_buf(const lb_t * lb, int index, char * buf) {
+  for (int n = 0; n < lb->ndist; n++) {
+    size_t sz = lb->nvel*sizeof(double);
+    double data[27];
+    for (int p = 0; p < lb->nvel; p++) data[p] = lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, n, p)];
+    memcpy(buf + n*sz, data, sz);
+  }
+  return 0;
+}
+
+int lb_read_buf(lb_t * lb, int index, const char * buf) {
+  for (int n = 0; n < lb->ndist; n++) {
+    size_t sz = lb->nvel*sizeof(double);
+    double data[27];
+    memcpy(data, buf + n*sz, sz);
+    for (int p = 0; p < lb->nvel; p++) lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, n, p)] = data[p];
+  }
+  return 0;
+}
+
+/* src/field.c:896-930 */
+int field_write_buf(field_t * field, int index, char * buf) {
+  double array[9];
+  for (int n = 0; n < field->nf; n++) array[n] = field->data[addr_rank1(field->nsites, field->nf, index, n)];
+  memcpy(buf, array, field->nf*sizeof(double));
+  return 0;
+}
+
+int field_read_buf(field_t * field, int index, const char * buf) {
+  double array[9];
+  memcpy(array, buf, field->nf*sizeof(double));
+  for (int n = 0; n < field->nf; n++) field->data[addr_rank1(field->nsites, field->nf, index, n)] = array[n];
+  return 0;
+}
+
+/* the aggregator: interior sites in (ic, jc, kc) order (cs_limits, src/lb_data.c:1646-1673, src/field.c:1590-1625) */
+static int io_file_transfer(cs_t * cs, const char * filename, size_t szelement, int write,
+			    void * obj, int (* wbuf)(void *, int, char *), int (* rbuf)(void *, int, const char *)) {
+  const size_t nsite = (size_t) cs->nlocal[X]*cs->nlocal[Y]*cs->nlocal[Z];
+  char * buf = (char *) malloc(nsite*szelement);
+  FILE * fp = NULL;
+  size_t ib = 0, nio;
+  if (buf == NULL) return -1;
+  if (!write) {
+    fp = fopen(filename, "rb");
+    if (fp == NULL) { free(buf); return -1; }
+    nio = fread(buf, szelement, nsite, fp);
+    fclose(fp);
+    if (nio != nsite) { free(buf); return -1; }
+  }
+  for (int ic = 1; ic <= cs->nlocal[X]; ic++)
+    for (int jc = 1; jc <= cs->nlocal[Y]; jc++)
+      for (int kc = 1; kc <= cs->nlocal[Z]; kc++) {
+	int index = cs_index(cs, ic, jc, kc);
+	if (write) wbuf(obj, index, buf + ib*szelement); else rbuf(obj, index, buf + ib*szelement);
+	ib++;
+      }
+  if (write) {
+    fp = fopen(filename, "wb");
+    if (fp == NULL) { free(buf); return -1; }
+    nio = fwrite(buf, szelement, nsite, fp);
+    fclose(fp);
+    if (nio != nsite) { free(buf); return -1; }
+  }
+  free(buf);
+  return 0;
+}
+
+static int lb_wbuf_(void * o, int index, char * buf) { return lb_write_buf((const lb_t *) o, index, buf); }
+static int lb_rbuf_(void * o, int index, const char * buf) { return lb_read_buf((lb_t *) o, index, buf); }
+static int field_wbuf_(void * o, int index, char * buf) { return field_write_buf((field_t *) o, index, buf); }
+static int field_rbuf_(void * o, int index, const char * buf) { return field_read_buf((field_t *) o, index, buf); }
+
+/* src/lb_data.c:1716-1830.  The device copy is brought to the host first (and pushed back after a read) when the
+ * lattice has one; a host-only lb_t (no device use yet) is written / read as it stands. */
+int lb_io_write(lb_t * lb, int timestep, io_event_t * event) {
+  char filename[BUFSIZ];
+  (void) event;
+  if (lb->cs->ctx) lb_memcpy(lb, tdpMemcpyDeviceToHost);
+  if (io_metadata_write_default(lb->cs, "dist", lb->ndist*lb->nvel) != 0) pe_fatal(lb->pe, "Could not write dist metadata\n");
+  io_file_name("dist", timestep, filename, BUFSIZ);
+  if (io_file_transfer(lb->cs, filename, sizeof(double)*lb->ndist*lb->nvel, 1, lb, lb_wbuf_, lb_rbuf_) != 0) {
+    pe_fatal(lb->pe, "Error: could not write distribution file: %s\n", filename);
+  }
+  return 0;
+}
+
+int lb_io_read(lb_t * lb, int timestep, io_event_t * event) {
+  char filename[BUFSIZ];
+  (void) event;
+  io_file_name("dist", timestep, filename, BUFSIZ);
+  if (io_file_transfer(lb->cs, filename, sizeof(double)*lb->ndist*lb->nvel, 0, lb, lb_wbuf_, lb_rbuf_) != 0) {
+    pe_fatal(lb->pe, "Error: could not read distribuiion file: %s\n", filename);
+  }
+  if (lb->cs->ctx) lb_memcpy(lb, tdpMemcpyHostToDevice);
+  return 0;
+}
+
+/* src/field.c:1633-1740 */
+int field_io_write(field_t * field, int timestep, io_event_t * event) {
+  char filename[BUFSIZ];
+  (void) event;
+  if (field->cs->ctx && field->b200_array >= 0) field_memcpy(field, tdpMemcpyDeviceToHost);
+  if (io_metadata_write_default(field->cs, field->name, field->nf) != 0) pe_fatal(field->pe, "Could not write %s metadata\n", field->name);
+  io_file_name(field->name, timestep, filename, BUFSIZ);
+  if (io_file_transfer(field->cs, filename, sizeof(double)*field->nf, 1, field, field_wbuf_, field_rbuf_) != 0) {
+    pe_fatal(field->pe, "Error: could not write file: %s\n", filename);
+  }
+  return 0;
+}
+
+int field_io_read(field_t * field, int timestep, io_event_t * event) {
+  char filename[BUFSIZ];
+  (void) event;
+  io_file_name(field->name, timestep, filename, BUFSIZ);
+  if (io_file_transfer(field->cs, filename, sizeof(double)*field->nf, 0, field, field_wbuf_, field_rbuf_) != 0) {
+    pe_fatal(field->pe, "Error: could not read file: %s\n", filename);
+  }
+  if (field->cs->ctx && field->b200_array >= 0) field_memcpy(field, tdpMemcpyHostToDevice);
+  return 0;
+}
+
 /* ---- collision ------------------------------------------------------------------------------------------------------------------ */
 
 /* src/collision.c:143-162 with the per-call parameter refresh of :1163-1246 and :1906-1958 */

@@ -53,6 +53,7 @@
 #include "blue_phase_beris_edwards.h"
 #include "gradient_3d_7pt_fluid.h"
 #include "colloids.h"
+#include "io_event.h"
 
 typedef struct ref_cfg_s {
   int ntotal[3];
@@ -439,6 +440,20 @@ int ref_le_lb_bc(ref_sim_t * s) { return lb_data_apply_le_boundary_conditions(s-
 int ref_le_init_shear_profile(ref_sim_t * s) { return lb_le_init_shear_profile(s->lb, s->le); }
 int ref_next_step(ref_sim_t * s) { return physics_control_next_step(s->phys); }
 int ref_timestep(ref_sim_t * s) { return physics_control_timestep(s->phys); }
+
+/* on-disk formats: the reference's own writers / readers, files land in the current directory
+ * as dist-%9.9d.001-001, phi-%9.9d.001-001, q-%9.9d.001-001 (+ their .meta JSON): src/lb_data.c:1716-1830,
+ * src/field.c:1633-1740, src/io_subfile.c:186-204 */
+int ref_lb_io_write(ref_sim_t * s, int timestep) { io_event_t ev = {0}; return lb_io_write(s->lb, timestep, &ev); }
+int ref_lb_io_read(ref_sim_t * s, int timestep) { io_event_t ev = {0}; return lb_io_read(s->lb, timestep, &ev); }
+int ref_field_io_write(ref_sim_t * s, int timestep) {
+  io_event_t ev = {0};
+  return field_io_write(s->q ? s->q : s->phi, timestep, &ev);
+}
+int ref_field_io_read(ref_sim_t * s, int timestep) {
+  io_event_t ev = {0};
+  return field_io_read(s->q ? s->q : s->phi, timestep, &ev);
+}
 
 /* One full time step in the reference driver's order (/root/reference/src/ludwig.c:528-860) */
 

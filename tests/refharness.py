@@ -63,6 +63,8 @@ def _lib(fast=False, nvel=19):
         lib.ref_init_rest.argtypes = [C.c_void_p, C.c_double]
         lib.ref_init_uniform_u.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double * 3)]
         lib.ref_init_spinodal.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        for name in ("ref_lb_io_write", "ref_lb_io_read", "ref_field_io_write", "ref_field_io_read"):
+            getattr(lib, name).argtypes = [C.c_void_p, C.c_int]
         lib.ref_lc_twist_init.argtypes = [C.c_void_p, C.c_int, C.c_double]
         lib.ref_lc_o8m_init.argtypes = [C.c_void_p, C.c_double]
         lib.ref_lc_fed_sum.argtypes = [C.c_void_p]
@@ -149,6 +151,10 @@ class RefSim:
 
     def lc_fed_sum(self):
         return self.lib.ref_lc_fed_sum(self.h)
+
+    def io(self, name, timestep):
+        """lb_io_write / lb_io_read / field_io_write / field_io_read in the current directory"""
+        return getattr(self.lib, "ref_" + name)(self.h, timestep)
 
     def op(self, name):
         return getattr(self.lib, "ref_" + name)(self.h)
