@@ -337,6 +337,50 @@ int phi_lb_to_field(field_t * phi, lb_t * lb);
 int phi_lb_from_field(field_t * phi, lb_t * lb);
 int advection_order(int * order);
 
+/* ---- liquid crystal: src/blue_phase.h:32-75, src/blue_phase_beris_edwards.h:27-50, src/blue_phase_init.h,
+ * src/gradient_3d_7pt_fluid.h.  The tensor order parameter is the field_t "q" created with ndata = NQAB. -------- */
+#define NQAB 5
+enum {XX = 0, XY = 1, XZ = 2, YY = 3, YZ = 4};
+typedef struct fe_lc_param_s {
+  double a0, q0, gamma, kappa0, kappa1;
+  double xi, zeta0, zeta1, zeta2;
+  double redshift, rredshift;
+  double epsilon;
+  double amplitude0;
+  double e0[3];
+  double coswt;
+  int is_redshift_updated;
+  int is_active;
+} fe_lc_param_t;
+typedef struct fe_lc_s fe_lc_t;
+struct fe_lc_s {
+  fe_t super;
+  pe_t * pe;
+  cs_t * cs;
+  fe_lc_param_t * param;
+  field_t * q;
+  field_grad_t * dq;
+  fe_lc_t * target;
+};
+int fe_lc_create(pe_t * pe, cs_t * cs, lees_edw_t * le, field_t * q, field_grad_t * dq, fe_lc_t ** fe);
+int fe_lc_free(fe_lc_t * fe);
+int fe_lc_param_set(fe_lc_t * fe, const fe_lc_param_t * values);      /* epsilon *= 1/12pi, as the reference */
+int fe_lc_param(fe_lc_t * fe, fe_lc_param_t * vals);
+int fe_lc_q_uniaxial(fe_lc_param_t * param, const double n[3], double q[3][3]);
+int field_tensor(field_t * obj, int index, double q[3][3]);
+int field_tensor_set(field_t * obj, int index, double q[3][3]);
+int blue_phase_twist_init(cs_t * cs, fe_lc_param_t * param, field_t * fq, int helical_axis);
+int grad_3d_7pt_fluid_d2(field_grad_t * fg);
+
+typedef struct beris_edw_param_s {double xi; double gamma; int noise; double var;} beris_edw_param_t;
+typedef struct beris_edw_s beris_edw_t;
+typedef struct colloids_info_s colloids_info_t;   /* never dereferenced here: pass NULL (no colloids in scope) */
+int beris_edw_create(pe_t * pe, cs_t * cs, lees_edw_t * le, beris_edw_t ** pobj);
+int beris_edw_free(beris_edw_t * be);
+int beris_edw_param_set(beris_edw_t * be, beris_edw_param_t * values);
+int beris_edw_update(beris_edw_t * be, fe_t * fe, field_t * fq, field_grad_t * fq_grad, hydro_t * hydro,
+		     colloids_info_t * cinfo, map_t * map, noise_t * noise);
+
 /* ---- on-disk formats: src/lb_data.c:1533-1575, 1716-1830, src/field.c:896-930, 1633-1740,
  * src/io_subfile.c:186-204, src/io_metadata.c.  One file per quantity and time step, "<stub>-%9.9d.001-001": the
  * interior sites in (ic, jc, kc) order with kc fastest, one binary record per site (distributions: ndist*nvel

@@ -9,6 +9,7 @@
  */
 
 #include <assert.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -77,6 +78,8 @@ struct cs_s {
   field_grad_t * phi_grad;
   map_t * map;
   lees_edw_t * le;
+  field_t * q;              /* liquid crystal: the tensor order parameter */
+  field_grad_t * q_grad;
   lb200_t * ctx;
 };
 
@@ -144,6 +147,8 @@ int cs_strides(cs_t * cs, int * xs, int * ys, int * zs) {
   return 0;
 }
 
+struct beris_edw_s {pe_t * pe; cs_t * cs; lees_edw_t * le; beris_edw_param_t param;};
+enum {FE_LC_ID = 1000};   /* tag of the liquid-crystal free energy in fe_t.id (the reference's enum value is not part of this interface) */
 static void b200_le_options(cs_t * cs, lb200_options_t * o);
 static void b200_time_sync(cs_t * cs);
 
@@ -159,6 +164,8 @@ lb200_t * cs_b200_context(cs_t * cs) {
     o.nvel = cs->lb ? cs->lb->nvel : 19;
     o.ndist = cs->lb ? cs->lb->ndist : 1;
     o.have_phi = (cs->phi != NULL);
+    o.have_q = (cs->q != NULL);
+    if (o.have_q && o.have_phi) pe_fatal(cs->pe, "a scalar order parameter and the Q tensor on one lattice are outside this build\n");
     o.halo_scheme = cs->lb ? (int) cs->lb->haloscheme : LB200_HALO_FULL;
     o.math = (math && strcmp(math, "strict") == 0) ? LB200_MATH_STRICT : LB200_MATH_FAST;
     o.device = -1;
@@ -532,14 +539,17 @@ int field_create(pe_t * pe, cs_t * cs, lees_edw_t * le, const char * name, const
   assert(pe); assert(cs); assert(opts); assert(pobj);
   /* the scalar order parameter of the symmetric free energy is the one device-backed user field */
   if (opts->ndata == 1 && cs->phi == NULL) tag = LB200_PHI;
+  if (opts->ndata == NQAB && cs->q == NULL) tag = LB200_Q;          /* the liquid-crystal tensor order parameter */
   field_create_tagged(pe, cs, le, name, opts, tag, pobj);
   if (tag == LB200_PHI) cs->phi = *pobj;
+  if (tag == LB200_Q) cs->q = *pobj;
   return 0;
 }
 
 int field_free(field_t * obj) {
   if (obj == NULL) return 0;
   if (obj->cs && obj->cs->phi == obj) obj->cs->phi = NULL;
+  if (obj->cs && obj->cs->q == obj) obj->cs->q = NULL;
   free(obj->name); free(obj->data); free(obj);
   return 0;
 }
@@ -554,6 +564,7 @@ int field_halo(field_t * obj) {
   lb200_t * ctx = cs_b200_context(obj->cs);
   if (obj->b200_array == LB200_PHI) b200_check(obj->pe, lb200_phi_halo(ctx), "field_halo");
   else if (obj->b200_array == LB200_U) b200_check(obj->pe, lb200_hydro_u_halo(ctx), "field_halo");
+  else if (obj->b200_array == LB200_Q) b200_check(obj->pe, lb200_q_halo(ctx), "field_halo");
   else pe_fatal(obj->pe, "field_halo: field \"%s\" has no device halo in this build\n", obj->name);
   return 0;
 }
@@ -602,6 +613,7 @@ int field_grad_create(pe_t * pe, field_t * f, int level, field_grad_t ** pobj) {
   }
   obj->target = obj;
   if (f->cs->phi == f) f->cs->phi_grad = obj;
+  if (f->cs->q == f) f->cs->q_grad = obj;
   *pobj = obj;
   return 0;
 }
@@ -639,7 +651,20 @@ int grad_3d_27pt_fluid_d4(field_grad_t * fg) {
   return 0;
 }
 
+/* src/gradient_3d_7pt_fluid.c:76-99 */
+int grad_3d_7pt_fluid_d2(field_grad_t * fg) {
+  if (fg->field->b200_array != LB200_Q) pe_fatal(fg->pe, "grad_3d_7pt_fluid_d2: only the Q tensor field is device backed\n");
+  b200_check(fg->pe, lb200_q_grad_compute(cs_b200_context(fg->field->cs)), "grad_3d_7pt_fluid_d2");
+  return 0;
+}
+
 int field_grad_memcpy(field_grad_t * obj, tdpMemcpyKind flag) {
+  if (obj->field->b200_array == LB200_Q) {
+    lb200_t * cq = cs_b200_context(obj->field->cs);
+    b200_check(obj->pe, lb200_memcpy(cq, LB200_QGRAD, obj->grad, b200_kind(flag)), "field_grad_memcpy");
+    b200_check(obj->pe, lb200_memcpy(cq, LB200_QDELSQ, obj->delsq, b200_kind(flag)), "field_grad_memcpy");
+    return 0;
+  }
   lb200_t * ctx = cs_b200_context(obj->field->cs);
   b200_check(obj->pe, lb200_memcpy(ctx, LB200_GRAD, obj->grad, b200_kind(flag)), "field_grad_memcpy");
   b200_check(obj->pe, lb200_memcpy(ctx, LB200_DELSQ, obj->delsq, b200_kind(flag)), "field_grad_memcpy");
@@ -829,9 +854,18 @@ int pth_create(pe_t * pe, cs_t * cs, int method, pth_t ** ppth) {
 int pth_free(pth_t * pth) { free(pth); return 0; }
 
 /* src/phi_force_stress.c:171-217 */
+static void lc_param_from(fe_t * fe, const struct beris_edw_s * be, lb200_lc_param_t * lc);
+
 int pth_stress_compute(pth_t * pth, fe_t * fe) {
   lb200_symm_param_t sp;
   assert(pth); assert(fe);
+  if (fe->id == FE_LC_ID) {
+    /* fe->func->stress_v == fe_lc_stress_v, src/phi_force_stress.c:256-284 */
+    lb200_lc_param_t lc;
+    lc_param_from(fe, NULL, &lc);
+    b200_check(pth->pe, lb200_lc_stress_compute(cs_b200_context(pth->cs), &lc), "pth_stress_compute");
+    return 0;
+  }
   symm_param_from(fe, &sp);
   b200_check(pth->pe, lb200_pth_stress_compute(cs_b200_context(pth->cs), &sp), "pth_stress_compute");
   return 0;
@@ -855,6 +889,12 @@ int phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t * wall, 
   if (wall != NULL) pe_fatal(pe, "phi_force_calculation: walls are outside this build\n");
   (void) le;                       /* with planes the library uses the flux form, src/phi_force.c:91-97 */
   if (pth->method != FE_FORCE_METHOD_STRESS_DIVERGENCE) pe_fatal(pe, "Bad force method\n");
+  if (fe->id == FE_LC_ID) {
+    lb200_lc_param_t lc;
+    lc_param_from(fe, NULL, &lc);
+    b200_check(pe, lb200_lc_force_calculation(cs_b200_context(cs), &lc), "phi_force_calculation");
+    return 0;
+  }
   symm_param_from(fe, &sp);
   b200_check(pe, lb200_phi_force_calculation(cs_b200_context(cs), &sp), "phi_force_calculation");
   return 0;
@@ -889,6 +929,113 @@ int phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t * hydro,
   return 0;
 }
 
+
+/* ---- liquid crystal -------------------------------------------------------------------------------------------- */
+
+int field_tensor(field_t * obj, int index, double q[3][3]) {           /* src/field.c: compressed XX XY XZ YY YZ */
+  const double * d = obj->data;
+  const int ns = obj->nsites;
+  q[X][X] = d[addr_rank1(ns, NQAB, index, XX)]; q[X][Y] = d[addr_rank1(ns, NQAB, index, XY)];
+  q[X][Z] = d[addr_rank1(ns, NQAB, index, XZ)]; q[Y][X] = q[X][Y];
+  q[Y][Y] = d[addr_rank1(ns, NQAB, index, YY)]; q[Y][Z] = d[addr_rank1(ns, NQAB, index, YZ)];
+  q[Z][X] = q[X][Z]; q[Z][Y] = q[Y][Z]; q[Z][Z] = 0.0 - q[X][X] - q[Y][Y];
+  return 0;
+}
+
+int field_tensor_set(field_t * obj, int index, double q[3][3]) {
+  double * d = obj->data;
+  const int ns = obj->nsites;
+  d[addr_rank1(ns, NQAB, index, XX)] = q[X][X]; d[addr_rank1(ns, NQAB, index, XY)] = q[X][Y];
+  d[addr_rank1(ns, NQAB, index, XZ)] = q[X][Z]; d[addr_rank1(ns, NQAB, index, YY)] = q[Y][Y];
+  d[addr_rank1(ns, NQAB, index, YZ)] = q[Y][Z];
+  return 0;
+}
+
+int fe_lc_create(pe_t * pe, cs_t * cs, lees_edw_t * le, field_t * q, field_grad_t * dq, fe_lc_t ** pfe) {
+  fe_lc_t * fe = (fe_lc_t *) calloc(1, sizeof(fe_lc_t));
+  (void) le;
+  if (fe == NULL) pe_fatal(pe, "calloc(fe_lc_t) failed\n");
+  fe->param = (fe_lc_param_t *) calloc(1, sizeof(fe_lc_param_t));
+  if (fe->param == NULL) pe_fatal(pe, "calloc(fe_lc_param_t) failed\n");
+  fe->pe = pe; fe->cs = cs; fe->q = q; fe->dq = dq;
+  fe->super.id = FE_LC_ID;
+  fe->param->redshift = 1.0; fe->param->rredshift = 1.0; fe->param->coswt = 1.0;
+  fe->target = fe;
+  *pfe = fe;
+  return 0;
+}
+int fe_lc_free(fe_lc_t * fe) { if (fe) { free(fe->param); free(fe); } return 0; }
+
+/* src/blue_phase.c:241-258 */
+int fe_lc_param_set(fe_lc_t * fe, const fe_lc_param_t * values) {
+  const double pi = 3.1415926535897932385;           /* PI_DOUBLE, src/util.h */
+  *fe->param = *values;
+  fe->param->epsilon *= (1.0/(12.0*pi));
+  if (fe->param->redshift != 1.0 || fe->param->is_redshift_updated) pe_fatal(fe->pe, "liquid crystal: redshift != 1 is outside this build\n");
+  if (fe->param->is_active) pe_fatal(fe->pe, "liquid crystal: active stress is outside this build\n");
+  fe->param->rredshift = 1.0;
+  if (fe->param->coswt == 0.0) fe->param->coswt = 1.0;
+  return 0;
+}
+int fe_lc_param(fe_lc_t * fe, fe_lc_param_t * vals) { *vals = *fe->param; return 0; }
+
+/* src/blue_phase.c:1406-1418 */
+int fe_lc_q_uniaxial(fe_lc_param_t * param, const double n[3], double q[3][3]) {
+  for (int ia = 0; ia < 3; ia++)
+    for (int ib = 0; ib < 3; ib++) q[ia][ib] = 0.5*param->amplitude0*(3.0*n[ia]*n[ib] - (ia == ib));
+  return 0;
+}
+
+/* src/blue_phase_init.c:763-823 */
+int blue_phase_twist_init(cs_t * cs, fe_lc_param_t * param, field_t * fq, int helical_axis) {
+  double n[3] = {0.0, 0.0, 0.0}, q[3][3];
+  const double q0 = param->q0;
+  for (int ic = 1; ic <= cs->nlocal[X]; ic++) {
+    if (helical_axis == X) { double x = cs->noffset[X] + ic; n[Y] = cos(q0*x); n[Z] = sin(q0*x); }
+    for (int jc = 1; jc <= cs->nlocal[Y]; jc++) {
+      if (helical_axis == Y) { double y = cs->noffset[Y] + jc; n[X] = cos(q0*y); n[Z] = -sin(q0*y); }
+      for (int kc = 1; kc <= cs->nlocal[Z]; kc++) {
+	if (helical_axis == Z) { double z = cs->noffset[Z] + kc; n[X] = cos(q0*z); n[Y] = sin(q0*z); }
+	fe_lc_q_uniaxial(param, n, q);
+	field_tensor_set(fq, cs_index(cs, ic, jc, kc), q);
+      }
+    }
+  }
+  return 0;
+}
+
+int beris_edw_create(pe_t * pe, cs_t * cs, lees_edw_t * le, beris_edw_t ** pobj) {
+  beris_edw_t * be = (beris_edw_t *) calloc(1, sizeof(beris_edw_t));
+  if (be == NULL) pe_fatal(pe, "calloc(beris_edw_t) failed\n");
+  be->pe = pe; be->cs = cs; be->le = le;
+  *pobj = be;
+  return 0;
+}
+int beris_edw_free(beris_edw_t * be) { free(be); return 0; }
+int beris_edw_param_set(beris_edw_t * be, beris_edw_param_t * values) { be->param = *values; return 0; }
+
+static void lc_param_from(fe_t * fe, const beris_edw_t * be, lb200_lc_param_t * lc) {
+  const fe_lc_param_t * p = ((fe_lc_t *) fe)->param;
+  memset(lc, 0, sizeof(*lc));
+  lc->a0 = p->a0; lc->q0 = p->q0; lc->gamma = p->gamma; lc->kappa0 = p->kappa0; lc->kappa1 = p->kappa1; lc->xi = p->xi;
+  lc->epsilon = p->epsilon;
+  for (int a = 0; a < 3; a++) lc->e0[a] = p->e0[a]*p->coswt;
+  lc->Gamma = be ? be->param.gamma : 0.0;
+  lc->adv_order = advection_order_;
+}
+
+/* src/blue_phase_beris_edwards.c:266-296 */
+int beris_edw_update(beris_edw_t * be, fe_t * fe, field_t * fq, field_grad_t * fq_grad, hydro_t * hydro,
+		     colloids_info_t * cinfo, map_t * map, noise_t * noise) {
+  lb200_lc_param_t lc;
+  (void) fq; (void) fq_grad; (void) map;
+  if (hydro == NULL) pe_fatal(be->pe, "beris_edw_update: hydro == NULL is outside this build\n");
+  if (cinfo != NULL) pe_fatal(be->pe, "beris_edw_update: colloids are outside this build\n");
+  if (noise != NULL || be->param.noise) pe_fatal(be->pe, "beris_edw_update: noise is outside this build\n");
+  lc_param_from(fe, be, &lc);
+  b200_check(be->pe, lb200_beris_edw_update(cs_b200_context(be->cs), &lc), "beris_edw_update");
+  return 0;
+}
 
 /* ---- on-disk formats --------------------------------------------------------------------------------------- */
 

@@ -505,6 +505,118 @@ static void test_lees_edwards_step(int order, int nplanes, int nsteps, int stric
   map_free(&map); hydro_free(hydro); lb_free(lb); lees_edw_free(le); physics_free(phys); cs_free(cs);
 }
 
+/* liquid crystal (Q tensor + Beris-Edwards) through the reference's entry points (src/ludwig.c:528-860 with ludwig->q:
+ * tests/regression/d3q19/pmpi08-chol-s01.inp at a smaller size) vs the liquid-crystal oracle */
+static void test_liquid_crystal_step(int order, int nsteps, int strict) {
+  cs_t * cs = NULL;
+  physics_t * phys = NULL;
+  lees_edw_t * le = NULL;
+  lb_t * lb = NULL;
+  hydro_t * hydro = NULL;
+  map_t * map = NULL;
+  field_t * q = NULL;
+  field_grad_t * q_grad = NULL;
+  fe_lc_t * fe = NULL;
+  beris_edw_t * be = NULL;
+  pth_t * pth = NULL;
+  int ntotal[3] = {10, 8, 12};
+  int nlocal[3], ns;
+  unsigned int seed = 4321;
+  const double zero[3] = {0.0, 0.0, 0.0};
+  const double eta = 0.1;
+  fe_lc_param_t p = {.a0 = 0.01, .q0 = 0.19635, .gamma = 3.0, .kappa0 = 0.000648456, .kappa1 = 0.0008, .xi = 0.7,
+		     .redshift = 1.0, .rredshift = 1.0, .amplitude0 = 0.333333333333333, .coswt = 1.0};
+  beris_edw_param_t bp = {.xi = 0.7, .gamma = 0.5};
+
+  cs_create(pe, &cs);
+  cs_nhalo_set(cs, 2);
+  cs_ntotal_set(cs, ntotal);
+  cs_init(cs);
+  cs_nlocal(cs, nlocal);
+  cs_nsites(cs, &ns);
+  physics_create(pe, &phys);
+  physics_eta_shear_set(phys, eta);
+  physics_eta_bulk_set(phys, eta);
+  { lees_edw_options_t o = {0}; lees_edw_create(pe, cs, &o, &le); }
+  { lb_data_options_t o = lb_data_options_ndim_nvel_ndist(3, 19, 1); lb_data_create(pe, cs, &o, &lb); }
+  { hydro_options_t o = hydro_options_nhalo(2); hydro_create(pe, cs, le, &o, &hydro); }
+  { map_options_t o = map_options_default(); map_create(pe, cs, &o, &map); }
+  { field_options_t o = field_options_ndata_nhalo(NQAB, 2); field_create(pe, cs, le, "q", &o, &q); }
+  field_grad_create(pe, q, 2, &q_grad);
+  field_grad_set(q_grad, grad_3d_7pt_fluid_d2, NULL);
+  fe_lc_create(pe, cs, le, q, q_grad, &fe);
+  fe_lc_param_set(fe, &p);
+  beris_edw_create(pe, cs, le, &be);
+  beris_edw_param_set(be, &bp);
+  pth_create(pe, cs, FE_FORCE_METHOD_STRESS_DIVERGENCE, &pth);
+  advection_order_set(order);
+
+  lb_init_rest_f(lb, 1.0);
+  blue_phase_twist_init(cs, &p, q, Z);
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++)
+	for (int n = 0; n < NQAB; n++) q->data[addr_rank1(ns, NQAB, cs_index(cs, ic, jc, kc), n)] += 0.02*(frand(&seed) - 0.5);
+
+  orc_geom_t g = {{nlocal[X], nlocal[Y], nlocal[Z]}, 2, {1, 1, 1}, 0};
+  orc_model_t model;
+  orc_collide_param_t ocp = {ORC_RELAX_M10, 1.0, eta, eta, {0.0, 0.0, 0.0}};
+  orc_lc_param_t olc = {p.a0, p.q0, p.gamma, p.kappa0, p.kappa1, p.xi, bp.gamma, 0.0, {0.0, 0.0, 0.0}};
+  double * of = malloc(sizeof(double)*19*ns), * oq = malloc(sizeof(double)*NQAB*ns);
+  double * ou = calloc(3*ns, sizeof(double)), * orho = calloc(ns, sizeof(double)), * oforce = calloc(3*ns, sizeof(double));
+  double * ograd = calloc(15*ns, sizeof(double)), * odelsq = calloc(5*ns, sizeof(double));
+  orc_model_create(19, &model);
+  memcpy(of, lb->f, sizeof(double)*19*ns);
+  memcpy(oq, q->data, sizeof(double)*NQAB*ns);
+
+  map_memcpy(map, tdpMemcpyHostToDevice);
+  lb_memcpy(lb, tdpMemcpyHostToDevice);
+  field_memcpy(q, tdpMemcpyHostToDevice);
+  for (int n = 0; n < nsteps; n++) {
+    hydro_f_zero(hydro, zero);
+    field_halo(q);
+    field_grad_compute(q_grad);
+    phi_force_calculation(pe, cs, le, NULL, pth, (fe_t *) fe, map, NULL, hydro);
+    hydro_u_halo(hydro);
+    beris_edw_update(be, (fe_t *) fe, q, q_grad, hydro, NULL, map, NULL);
+    hydro_u_zero(hydro, zero);
+    lb_collide(lb, hydro, map, NULL, (fe_t *) fe, NULL);
+    lb_halo(lb);
+    lb_propagation(lb);
+  }
+  lb_memcpy(lb, tdpMemcpyDeviceToHost);
+  field_memcpy(q, tdpMemcpyDeviceToHost);
+  hydro_memcpy(hydro, tdpMemcpyDeviceToHost);
+
+  orc_lc_step(&g, &model, &ocp, &olc, order, nsteps, of, oq, ou, orho, oforce, ograd, odelsq);
+
+  double umax = 0.0;
+  for (int ic = 1; ic <= nlocal[X]; ic++)
+    for (int jc = 1; jc <= nlocal[Y]; jc++)
+      for (int kc = 1; kc <= nlocal[Z]; kc++) {
+	int index = cs_index(cs, ic, jc, kc);
+	for (int p1 = 0; p1 < 19; p1++) {
+	  double a = lb->f[LB_ADDR(ns, 1, 19, index, 0, p1)], b = of[(size_t) p1*ns + index];
+	  if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-12*0.34 + 1e-14);
+	}
+	for (int n = 0; n < NQAB; n++) {
+	  double a = q->data[addr_rank1(ns, NQAB, index, n)], b = oq[(size_t) n*ns + index];
+	  if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-12*0.34 + 1e-14);
+	}
+	for (int ia = 0; ia < 3; ia++) {
+	  double a = hydro->u->data[addr_rank1(ns, 3, index, ia)], b = ou[(size_t) ia*ns + index];
+	  if (strict) test_assert(a == b); else test_assert(fabs(a - b) <= 1e-14);
+	  if (fabs(b) > umax) umax = fabs(b);
+	}
+      }
+  test_assert(umax > 1e-9);
+  printf("PASS test_liquid_crystal_step order=%d nsteps=%d %s\n", order, nsteps, strict ? "bit-exact" : "within tolerance");
+
+  free(of); free(oq); free(ou); free(orho); free(oforce); free(ograd); free(odelsq);
+  pth_free(pth); beris_edw_free(be); fe_lc_free(fe); field_grad_free(q_grad); field_free(q);
+  map_free(&map); hydro_free(hydro); lb_free(lb); lees_edw_free(le); physics_free(phys); cs_free(cs);
+}
+
 /* single-fluid collision + propagation steps, each relaxation scheme */
 static void test_single_fluid(int nvel, lb_relaxation_enum_t nrelax, int strict) {
   cs_t * cs = NULL;
@@ -595,6 +707,8 @@ int main(void) {
   test_symmetric_lb(15, strict);
   test_lees_edwards_step(3, 2, 6, strict);
   test_lees_edwards_step(1, 1, 6, strict);
+  test_liquid_crystal_step(3, 6, strict);
+  test_liquid_crystal_step(1, 6, strict);
 
   pe_free(pe);
   printf("PASS test_host_api (%s)\n", strict ? "strict" : "fast");
