@@ -591,6 +591,7 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   c->knob_peer = getenv("LB200_PEER") ? atoi(getenv("LB200_PEER")) : 1;
   c->f_alloc[0] = c->f; c->f_alloc[1] = c->fprime;
   c->phi_alloc[0] = c->phi; c->phi_alloc[1] = c->phinew;
+  if (o->have_q) { c->phi_alloc[0] = c->q; c->phi_alloc[1] = c->qnew; }     // the order-parameter slots of the peer links carry Q
   c->u_alloc[0] = c->u; c->u_alloc[1] = nullptr;
   for (int i = 0; i < LB200_KCLASS_MAX; i++) c->ev[i] = new std::vector<cudaEvent_t>();
   *pctx = c;
@@ -1858,6 +1859,46 @@ static int wrap_exchange_field(lb200_t * c, cudaStream_t st, double * data, int 
   return nccl_exchange(c, st, m, ncomp);
 }
 
+// Peer copies of boundary x-planes (x-slabs, liquid-crystal step): `ncomp` consecutive components starting at `comp0`,
+// `depth` planes, from my array `src` straight into the halo planes of the neighbours' arrays (cudaIpc-mapped, NVLink),
+// as strided device-to-device copies on the comm stream -- no SM is taken from the compute kernels (the NCCL send/recv
+// kernels they replace compete with 0.1 ms sweeps for SMs).  up != 0: my planes [N-d+1, N] -> the high neighbour's
+// planes [1-d, 0]; down != 0: my planes [1, d] -> the low neighbour's planes [N+1, N+d].
+static int peer_copy_planes(lb200_t * c, cudaStream_t st, const double * src, double * dst_lo, double * dst_hi,
+			    int comp0, int ncomp, int depth, int up, int down) {
+  const Lb200Geom & g = c->g;
+  const size_t xs = (size_t) g.xs, ns = (size_t) g.nsites;
+  const size_t width = (size_t) depth*xs*sizeof(double), pitch = ns*sizeof(double);
+  if (up) {
+    CUDA_TRY(cudaMemcpy2DAsync(dst_hi + comp0*ns + (size_t) (g.nh - depth)*xs, pitch,
+			       src + comp0*ns + (size_t) (g.nl[0] - depth + g.nh)*xs, pitch, width, ncomp, cudaMemcpyDeviceToDevice, st));
+  }
+  if (down) {
+    CUDA_TRY(cudaMemcpy2DAsync(dst_lo + comp0*ns + (size_t) (g.nl[0] + g.nh)*xs, pitch,
+			       src + comp0*ns + (size_t) g.nh*xs, pitch, width, ncomp, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+// the populations moving in +x go up, those moving in -x go down (runs of consecutive populations: one copy each)
+static int peer_copy_f(lb200_t * c, cudaStream_t st, const double * f, double * dst_lo, double * dst_hi) {
+  lb200_step_plan_t pl;
+  int rc = lb200_step_plan(&c->opt, LB200_STEP_F, &pl);
+  if (rc != 0) return rc;
+  for (int dir = 0; dir < 2; dir++) {
+    const int * comp = dir == 0 ? pl.comp_up : pl.comp_down;
+    const int ncomp = dir == 0 ? pl.ncomp_up : pl.ncomp_down;
+    for (int a = 0; a < ncomp; ) {
+      int b = a;
+      while (b + 1 < ncomp && comp[b + 1] == comp[b] + 1) b++;
+      rc = peer_copy_planes(c, st, f, dst_lo, dst_hi, comp[a], b - a + 1, 1, dir == 0, dir == 1);
+      if (rc != 0) return rc;
+      a = b + 1;
+    }
+  }
+  return 0;
+}
+
 int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_param_t * lc, int nsteps) {
   if (c == nullptr) return fail(LB200_EINVAL, "null context");
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1871,11 +1912,17 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
   if (nsteps <= 0) return 0;
   const Lb200Geom & g = c->g;
   // halo-free steps on periodic lattices: every y / z (one GPU: also x) periodic image is read in-kernel; x-slabs
-  // exchange only the x-planes the kernels read (q: nhalo, u: 1, f: the populations crossing) over NCCL on the comm
-  // stream, overlapped with the kernels that do not need them.  Otherwise the reference's structure with halo kernels.
+  // exchange only the x-planes the kernels read (q: nhalo, u: 1, f: the populations crossing) on the comm stream,
+  // overlapped with the kernels that do not need them -- as peer copies into the neighbours' mapped arrays with one
+  // flag per exchange (default), or NCCL send/recv.  Otherwise the reference's structure with halo kernels.
   bool wrap = c->knob_wrap && g.per[0] && g.per[1] && g.per[2];
   for (int a = 0; a < 3; a++) wrap = wrap && (g.nl[a] >= 2*g.nh);
   const bool remote = wrap && g.remote_x;
+  if (remote) {
+    rc = peer_setup(c);                  // collective, does something the first time only
+    if (rc != 0) return rc;
+  }
+  const bool peer = remote && c->peer_state == 1 && c->knob_peer;
   cudaStream_t S = c->stream, C = (remote && !c->profile) ? c->comm : c->stream;
   Lb200Geom gw = c->g;
   if (wrap) { gw.wrap[0] = !g.remote_x; gw.wrap[1] = gw.wrap[2] = 1; }
@@ -1884,8 +1931,10 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
     if (rc != 0) return rc;
   }
   if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+  int q_src = SRC_NONE, u_src = SRC_NONE, f_src = SRC_NONE;
   if (remote) {
-    // bring the planes the first kernels read (the state did not come out of a previous halo-free step)
+    // bring the planes the first kernels read (the state did not come out of a previous halo-free step); this round
+    // of messages also orders this call after whatever the neighbours were doing before
     CUDA_TRY(cudaEventRecord(c->ev_main, S));
     CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
     if ((rc = wrap_exchange_field(c, C, c->q, 5, g.nh)) != 0) return rc;
@@ -1894,6 +1943,7 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
     CUDA_TRY(cudaEventRecord(c->ev_u, C));
     if (c->prop_pending && (rc = wrap_exchange_f(c, C)) != 0) return rc;
     CUDA_TRY(cudaEventRecord(c->ev_f, C));
+    q_src = u_src = f_src = SRC_EVENT;
   }
 
   for (int n = 0; n < nsteps; n++) {
@@ -1902,7 +1952,7 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
       rc = halo_field(c, c->q, 5, g.nh, 0, S);                           // field_halo(q)
       if (rc != 0) return rc;
     }
-    if (remote) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
+    if (remote && (rc = src_wait(c, S, q_src, c->ev_phi, FLAG_PS_LO, c->n_ps)) != 0) return rc;
     {
       // field_grad_compute + pth_stress_compute: gradients in registers, only the stress is stored
       ProfScope ps(c, LB200_K_LC_STRESS);
@@ -1914,10 +1964,10 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
       if (rc != 0) return rc;
       c->u_state = ARRAY_CLEAN;
     }
-    if (remote) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
+    if (remote && (rc = src_wait(c, S, u_src, c->ev_u, FLAG_COL_LO, c->n_col)) != 0) return rc;
     {
-      // pth_force_fluid_driver + beris_edw_update
-      // two sweeps (default; the 64-register force gather runs at high occupancy on its own: 1.19 vs 1.52 ms at 256^3) or one (LB200_LC_SPLIT=0)
+      // pth_force_fluid_driver + beris_edw_update: two sweeps (default; the 64-register force gather runs at high
+      // occupancy on its own: 1.19 vs 1.52 ms at 256^3) or one (LB200_LC_SPLIT=0)
       static const int split = getenv("LB200_LC_SPLIT") ? atoi(getenv("LB200_LC_SPLIT")) : 1;
       ProfScope ps(c, LB200_K_LC_BE);
       if (split) {
@@ -1931,35 +1981,62 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
     c->force_state = INTERIOR_ONLY;
     { double * t = c->q; c->q = c->qnew; c->qnew = t; }
     if (remote) {
+      // the new q planes travel while the collision runs
       CUDA_TRY(cudaEventRecord(c->ev_main, S));
       CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
-      if ((rc = wrap_exchange_field(c, C, c->q, 5, g.nh)) != 0) return rc;      // overlaps the collision
-      CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+      if (peer) {
+	const int iq = idx2(c->q, c->phi_alloc);
+	ProfScope ps(c, LB200_K_HALO, C);
+	if ((rc = peer_copy_planes(c, C, c->q, c->lo.phi[iq], c->hi.phi[iq], 0, 5, g.nh, 1, 1)) != 0) return rc;
+	c->n_ps++;
+	c->launches += c->k->signal(C, c->hi.flags + FLAG_PS_LO, c->lo.flags + FLAG_PS_HI, c->n_ps);
+	q_src = SRC_FLAG;
+      }
+      else {
+	if ((rc = wrap_exchange_field(c, C, c->q, 5, g.nh)) != 0) return rc;
+	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+	q_src = SRC_EVENT;
+      }
     }
     c->u_state = ZERO_PENDING;                                           // hydro_u_zero
     if (wrap) {
-      if (remote) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
+      if (remote && (rc = src_wait(c, S, f_src, c->ev_f, FLAG_COL_LO, c->n_col)) != 0) return rc;
+      // with peer copies the neighbours may still be reading the u planes they got last step: write the other buffer
+      double * u_out = peer ? ((c->u == c->u_alloc[0]) ? c->u_alloc[1] : c->u_alloc[0]) : c->u;
       {
 	ProfScope ps(c, LB200_K_COLLIDE);
 	if (c->prop_pending) {
-	  c->launches += c->k->collide(S, gw, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, c->u);
+	  c->launches += c->k->collide(S, gw, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, u_out);
 	  double * t = c->f; c->f = c->fprime; c->fprime = t;
 	  c->prop_pending = 0;
 	}
 	else {
-	  c->launches += c->k->collide(S, c->g, cd, model_ptr(c), c->nvel, 0, c->f, c->f, c->force, status_ptr(c), c->rho, c->u);
+	  c->launches += c->k->collide(S, c->g, cd, model_ptr(c), c->nvel, 0, c->f, c->f, c->force, status_ptr(c), c->rho, u_out);
 	}
       }
+      c->u = u_out;
       c->u_state = INTERIOR_ONLY;
       c->prop_pending = 1;                                               // lb_halo; lb_propagation (lazy)
       c->f_halo_stale = 1;
       if (remote) {
 	CUDA_TRY(cudaEventRecord(c->ev_main, S));
 	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
-	if ((rc = wrap_exchange_field(c, C, c->u, 3, 1)) != 0) return rc;       // the next Beris-Edwards sweep waits for this
-	CUDA_TRY(cudaEventRecord(c->ev_u, C));
-	if ((rc = wrap_exchange_f(c, C)) != 0) return rc;                       // overlaps the next two LC sweeps
-	CUDA_TRY(cudaEventRecord(c->ev_f, C));
+	if (peer) {
+	  const int iu = idx2(c->u, c->u_alloc), jf = idx2(c->f, c->f_alloc);
+	  ProfScope ps(c, LB200_K_HALO, C);
+	  if ((rc = peer_copy_planes(c, C, c->u, c->lo.u[iu], c->hi.u[iu], 0, 3, 1, 1, 1)) != 0) return rc;
+	  if ((rc = peer_copy_f(c, C, c->f, c->lo.f[jf], c->hi.f[jf])) != 0) return rc;
+	  c->n_col++;
+	  c->launches += c->k->signal(C, c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
+	  u_src = f_src = SRC_FLAG;
+	}
+	else {
+	  if ((rc = wrap_exchange_field(c, C, c->u, 3, 1)) != 0) return rc;       // the next Beris-Edwards sweep waits for this
+	  CUDA_TRY(cudaEventRecord(c->ev_u, C));
+	  if ((rc = wrap_exchange_f(c, C)) != 0) return rc;                       // overlaps the next two LC sweeps
+	  CUDA_TRY(cudaEventRecord(c->ev_f, C));
+	  u_src = f_src = SRC_EVENT;
+	}
       }
     }
     else {
@@ -1972,9 +2049,12 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
     }
   }
   if (remote) {
+    // rejoin: what is still in flight on the comm stream (it reads this rank's boundary planes) is ordered before
+    // whatever follows on the main stream, and the planes the neighbours sent have arrived
+    CUDA_TRY(cudaEventRecord(c->ev_f, C));
     CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
-    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
-    CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
+    if (q_src == SRC_FLAG && (rc = flags_wait(c, S, FLAG_PS_LO, c->n_ps)) != 0) return rc;
+    if (f_src == SRC_FLAG && (rc = flags_wait(c, S, FLAG_COL_LO, c->n_col)) != 0) return rc;
   }
   c->phi_halo_valid = 0;
   c->u_halo_valid = 0;
