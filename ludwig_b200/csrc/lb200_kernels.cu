@@ -400,6 +400,178 @@ collide_model_kernel(const Lb200Geom g, const Lb200CollideDev cp, const __grid_c
   if (to_hi && g.peer_u_hi != nullptr) g.peer_u_hi[(size_t) index - (size_t) g.nl[0]*g.xs] = u[0];
 }
 
+#ifndef LB200_STRICT
+// ---------------------------------------------------------------------------------------------
+// D3Q27, fast mode: the reference's D3Q27 basis (src/lb_d3q27.c:100-190) is the complete tensor-product Hermite basis
+// m_abc = k_abc sum_p h_a(c_px) h_b(c_py) h_c(c_pz) f_p with h_0 = 1, h_1 = c, h_2 = c^2 - 1/3 and k = 1, 3, 9, 27 for
+// polynomial order per axis (see D27_MODE), so both projections factorise into three passes of 3-point transforms:
+// 2 x 243 multiply-adds per site instead of the 2 x 729 of the dense matrix products (which make the generic kernel
+// FP64-bound: 4.9 GLUPS).  Same relaxation as every other collision kernel; within 1e-12 of the dense form (tested).
+// The back projection uses mi[p][m] = w_p N_m ma[m][p], N_m = 1/(k_m^2 n_a n_b n_c), n = (1, 1/3, 2/9), w_p = w(c_x) w(c_y) w(c_z).
+// ---------------------------------------------------------------------------------------------
+
+// population index of velocity (i, j, k): rest first, then i, j, k ascending with the rest skipped (src/lb_d3q27.h:26-32)
+__host__ __device__ constexpr int d27_p(int i, int j, int k) {
+  const int lin = (i + 1)*9 + (j + 1)*3 + (k + 1);          // 0..26, the rest velocity at 13
+  return (lin == 13) ? 0 : (lin < 13 ? lin + 1 : lin);
+}
+// mode m of the reference <-> polynomial orders (a, b, c) along x, y, z and scale k (src/lb_d3q27.c:160-186)
+__device__ constexpr int D27_MODE[27][4] = {
+  {0, 0, 0, 1}, {1, 0, 0, 1}, {0, 1, 0, 1}, {0, 0, 1, 1},
+  {2, 0, 0, 1}, {1, 1, 0, 1}, {1, 0, 1, 1}, {0, 2, 0, 1}, {0, 1, 1, 1}, {0, 0, 2, 1},
+  {2, 1, 0, 3}, {2, 0, 1, 3}, {0, 2, 1, 3}, {1, 2, 0, 3}, {1, 0, 2, 3}, {0, 1, 2, 3},
+  {1, 1, 1, 1},
+  {2, 2, 0, 9}, {0, 2, 2, 9}, {2, 0, 2, 9},
+  {2, 1, 1, 9}, {1, 2, 1, 9}, {1, 1, 2, 9},
+  {2, 2, 1, 9}, {1, 2, 2, 9}, {2, 1, 2, 9},
+  {2, 2, 2, 27}};
+
+// forward 3-point transform along one axis: values at c = -1, 0, +1 -> orders 0, 1, 2
+__device__ __forceinline__ void d27_fwd(double fm, double f0, double fp, double & t0, double & t1, double & t2) {
+  const double s = fm + fp;
+  t0 = s + f0;
+  t1 = fp - fm;
+  t2 = (2.0/3.0)*s - (1.0/3.0)*f0;
+}
+// transposed transform with the 1-d weights w(0) = 2/3, w(+-1) = 1/6 folded in
+__device__ __forceinline__ void d27_bwd(double t0, double t1, double t2, double & fm, double & f0, double & fp) {
+  const double e = t0 + (2.0/3.0)*t2;
+  fm = (1.0/6.0)*(e - t1);
+  fp = (1.0/6.0)*(e + t1);
+  f0 = (2.0/3.0)*(t0 - (1.0/3.0)*t2);
+}
+
+template <bool PULL, bool WRAP>
+__global__ void __launch_bounds__(TPB_MAX)
+collide_d3q27_sep_kernel(const Lb200Geom g, const Lb200CollideDev cp,
+			 const double * __restrict__ fsrc, double * __restrict__ fdst,
+			 const double * __restrict__ hforce, const char * __restrict__ status,
+			 double * __restrict__ rho_out, double * __restrict__ u_out) {
+
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ic = 1 + blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+
+  const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+  const size_t ns = (size_t) g.nsites;
+
+  // offsets of the site one step down / up each axis (through the periodic boundary in halo-free steps)
+  int om[3], op[3];
+  om[0] = (WRAP && g.wrap[0] && ic == 1)       ?  (g.nl[0] - 1)*g.xs : -g.xs;
+  op[0] = (WRAP && g.wrap[0] && ic == g.nl[0]) ? -(g.nl[0] - 1)*g.xs :  g.xs;
+  om[1] = (WRAP && g.wrap[1] && jc == 1)       ?  (g.nl[1] - 1)*g.ys : -g.ys;
+  op[1] = (WRAP && g.wrap[1] && jc == g.nl[1]) ? -(g.nl[1] - 1)*g.ys :  g.ys;
+  om[2] = (WRAP && g.wrap[2] && kc == 1)       ?  (g.nl[2] - 1) : -1;
+  op[2] = (WRAP && g.wrap[2] && kc == g.nl[2]) ? -(g.nl[2] - 1) :  1;
+
+  double f[3][3][3];                     // f[i+1][j+1][k+1], velocity (i, j, k)
+#pragma unroll
+  for (int i = -1; i <= 1; i++)
+#pragma unroll
+    for (int j = -1; j <= 1; j++)
+#pragma unroll
+      for (int k = -1; k <= 1; k++) {
+	// population (i, j, k) arrives from the site at -(i, j, k)
+	const int off = PULL ? ((i > 0 ? om[0] : i < 0 ? op[0] : 0) + (j > 0 ? om[1] : j < 0 ? op[1] : 0) + (k > 0 ? om[2] : k < 0 ? op[2] : 0)) : 0;
+	f[i + 1][j + 1][k + 1] = fsrc[d27_p(i, j, k)*ns + (index + off)];
+      }
+
+  const bool to_lo = (ic == 1 && g.peer_f_lo != nullptr), to_hi = (ic == g.nl[0] && g.peer_f_hi != nullptr);
+
+  if (status != nullptr && status[index] != 0) {
+#pragma unroll
+    for (int i = -1; i <= 1; i++)
+#pragma unroll
+      for (int j = -1; j <= 1; j++)
+#pragma unroll
+	for (int k = -1; k <= 1; k++) {
+	  const int p = d27_p(i, j, k);
+	  const double v = f[i + 1][j + 1][k + 1];
+	  if (PULL) fdst[p*ns + index] = v;
+	  if (to_lo && i < 0) g.peer_f_lo[p*ns + (size_t) index + (size_t) g.nl[0]*g.xs] = v;
+	  if (to_hi && i > 0) g.peer_f_hi[p*ns + (size_t) index - (size_t) g.nl[0]*g.xs] = v;
+	}
+    return;
+  }
+
+  // forward: z, then y, then x
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) d27_fwd(f[i][j][0], f[i][j][1], f[i][j][2], f[i][j][0], f[i][j][1], f[i][j][2]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) d27_fwd(f[i][0][k], f[i][1][k], f[i][2][k], f[i][0][k], f[i][1][k], f[i][2][k]);
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) d27_fwd(f[0][j][k], f[1][j][k], f[2][j][k], f[0][j][k], f[1][j][k], f[2][j][k]);
+
+  double mode[27];
+#pragma unroll
+  for (int m = 0; m < 27; m++) mode[m] = (double) D27_MODE[m][3]*f[D27_MODE[m][0]][D27_MODE[m][1]][D27_MODE[m][2]];
+
+  double force[3], u[3], rho;
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) force[ia] = cp.fg[ia] + (hforce ? hforce[ia*ns + index] : 0.0);
+  relax_hydro(mode, force, cp, rho, u);
+#pragma unroll
+  for (int m = 10; m < 27; m++) mode[m] = mode[m] - cp.rtau_ghost[m]*(mode[m] - 0.0);
+
+  // back: N_m k_m mode_m into the (a, b, c) cube, then x, y, z with the weights folded in
+  const double nn[3] = {1.0, 3.0, 4.5};                  // 1/n_a, n = (1, 1/3, 2/9)
+#pragma unroll
+  for (int m = 0; m < 27; m++) {
+    const int a = D27_MODE[m][0], b = D27_MODE[m][1], c = D27_MODE[m][2];
+    f[a][b][c] = mode[m]*(nn[a]*nn[b]*nn[c]/(double) D27_MODE[m][3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) d27_bwd(f[0][j][k], f[1][j][k], f[2][j][k], f[0][j][k], f[1][j][k], f[2][j][k]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) d27_bwd(f[i][0][k], f[i][1][k], f[i][2][k], f[i][0][k], f[i][1][k], f[i][2][k]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) d27_bwd(f[i][j][0], f[i][j][1], f[i][j][2], f[i][j][0], f[i][j][1], f[i][j][2]);
+
+#pragma unroll
+  for (int i = -1; i <= 1; i++)
+#pragma unroll
+    for (int j = -1; j <= 1; j++)
+#pragma unroll
+      for (int k = -1; k <= 1; k++) {
+	const int p = d27_p(i, j, k);
+	const double v = f[i + 1][j + 1][k + 1];
+	store_f<PULL>(fdst + p*ns + index, v);
+	if (to_lo && i < 0) g.peer_f_lo[p*ns + (size_t) index + (size_t) g.nl[0]*g.xs] = v;
+	if (to_hi && i > 0) g.peer_f_hi[p*ns + (size_t) index - (size_t) g.nl[0]*g.xs] = v;
+      }
+
+  rho_out[index] = rho;
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) u_out[ia*ns + index] = u[ia];
+  if (to_lo && g.peer_u_lo != nullptr) g.peer_u_lo[(size_t) index + (size_t) g.nl[0]*g.xs] = u[0];
+  if (to_hi && g.peer_u_hi != nullptr) g.peer_u_hi[(size_t) index - (size_t) g.nl[0]*g.xs] = u[0];
+}
+
+// the separable form assumes the velocity ordering above: check the model tables once
+static bool d27_ordering_ok(const Lb200ModelDev & mh) {
+  for (int i = -1; i <= 1; i++)
+    for (int j = -1; j <= 1; j++)
+      for (int k = -1; k <= 1; k++) {
+	const int p = d27_p(i, j, k);
+	if (mh.cv[p][0] != i || mh.cv[p][1] != j || mh.cv[p][2] != k) return false;
+      }
+  return true;
+}
+#endif
+
 // host copy of the model tables of a velocity set (deterministic per nvel), fetched once from the device copy
 static const Lb200ModelDev * host_model(const Lb200ModelDev * md_dev, int nvel) {
   static Lb200ModelDev cache[3];
@@ -442,6 +614,15 @@ int launch_collide(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev &
     dim3 blk2;
     block_shape_n(g.nl[2], 128, blk2);
     dim3 grd2((g.nl[2] + blk2.x - 1)/blk2.x, (g.nl[1] + blk2.y - 1)/blk2.y, g.nl[0]);
+#ifndef LB200_STRICT
+    static const int sep27 = tuned_flag("LB200_D3Q27_SEPARABLE", 1);
+    if (nvel == 27 && sep27 && d27_ordering_ok(mh)) {
+      if (wrap)      collide_d3q27_sep_kernel<true, true><<<grd2, blk2, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u);
+      else if (pull) collide_d3q27_sep_kernel<true, false><<<grd2, blk2, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u);
+      else           collide_d3q27_sep_kernel<false, false><<<grd2, blk2, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u);
+      return 1;
+    }
+#endif
 #define LB200_GO(N) do { \
     if (wrap)      collide_model_kernel<N, true, true><<<grd2, blk2, 0, st>>>(g, cp, mh, fsrc, fdst, force, status, rho, u); \
     else if (pull) collide_model_kernel<N, true, false><<<grd2, blk2, 0, st>>>(g, cp, mh, fsrc, fdst, force, status, rho, u); \
