@@ -115,7 +115,7 @@ typedef struct lb200_symm_param_s {
   double a, b, kappa;       /* symmetric free energy A, B, kappa */
   double mobility;          /* physics mobility */
   double gradmu[3];         /* physics grad_mu (external chemical potential gradient) */
-  int adv_order;            /* fd_advection_scheme_order 1, 2 or 3 */
+  int adv_order;            /* fd_advection_scheme_order 1-4 (src/advection.c:453-468; order 5 needs a 3-deep halo: not built) */
 } lb200_symm_param_t;
 
 /* fe_lc_param_t + beris_edw_param_t as the liquid-crystal kernels see them (src/blue_phase.h:52-75,
@@ -128,7 +128,7 @@ typedef struct lb200_lc_param_s {
   double Gamma;             /* lc_Gamma: rotational diffusion constant */
   double epsilon;           /* lc_dielectric_anisotropy / (12 pi), as stored by fe_lc_param_set (src/blue_phase.c:249-252) */
   double e0[3];             /* electric_e0 */
-  int adv_order;            /* fd_advection_scheme_order 1, 2 or 3 */
+  int adv_order;            /* fd_advection_scheme_order 1-4 (src/advection.c:453-468; order 5 needs a 3-deep halo: not built) */
 } lb200_lc_param_t;
 
 const char * lb200_last_error(void);

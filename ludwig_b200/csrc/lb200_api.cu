@@ -1190,7 +1190,7 @@ int lb200_phi_cahn_hilliard(lb200_t * c, const lb200_symm_param_t * sp) {
   CTX_ENTER(c);
   if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
   if (sp == nullptr) return fail(LB200_EINVAL, "null parameters");
-  if (sp->adv_order < 1 || sp->adv_order > 3) return fail(LB200_EINVAL, "advection order %d: device kernels exist for 1-3 (reference src/advection.c:456-480)", sp->adv_order);
+  if (sp->adv_order < 1 || sp->adv_order > 4) return fail(LB200_EINVAL, "advection order %d: device kernels exist for 1-4 (reference src/advection.c:456-480)", sp->adv_order);
   Lb200SymmDev sd;
   symm_dev(c, sp, &sd);
   int rc = u_halo_async(c);               // hydro_u_halo inside phi_cahn_hilliard, src/phi_cahn_hilliard.c:229
@@ -1763,7 +1763,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 static int lc_dev(lb200_t * c, const lb200_lc_param_t * lc, Lb200LcDev * d) {
   if (c->q == nullptr) return fail(LB200_ESTATE, "no q in this context (options.have_q)");
   if (lc == nullptr) return fail(LB200_EINVAL, "null parameters");
-  if (lc->adv_order < 1 || lc->adv_order > 3) return fail(LB200_EINVAL, "advection order %d: device kernels exist for 1-3", lc->adv_order);
+  if (lc->adv_order < 1 || lc->adv_order > 4) return fail(LB200_EINVAL, "advection order %d: device kernels exist for 1-4", lc->adv_order);
   if (!c->map_all_fluid) return fail(LB200_ESTATE, "liquid crystal: all-fluid lattices only in this build");
   d->a0 = lc->a0; d->q0 = lc->q0; d->gamma = lc->gamma; d->kappa0 = lc->kappa0; d->kappa1 = lc->kappa1; d->xi = lc->xi;
   d->Gamma = lc->Gamma; d->epsilon = lc->epsilon;
@@ -2076,7 +2076,7 @@ static int step_le(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev &
   const Lb200Geom & g = c->g;
   int rc = ensure_f_halo(c);
   if (rc != 0) return rc;
-  const bool fused = (c->opt.math == LB200_MATH_FAST) && c->knob_phi_sector && c->map_all_fluid;
+  const bool fused = (c->opt.math == LB200_MATH_FAST) && c->knob_phi_sector && c->map_all_fluid && sd.order <= 3;
 
   for (int n = 0; n < nsteps; n++) {
     c->t_current += 1;                                                   // physics_control_next_step
@@ -2135,7 +2135,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   CUDA_TRY(cudaSetDevice(c->device));
   if (cp == nullptr) return fail(LB200_EINVAL, "null collision parameters");
   const int binary = (sp != nullptr && c->phi != nullptr);
-  if (binary && (sp->adv_order < 1 || sp->adv_order > 3)) return fail(LB200_EINVAL, "advection order %d", sp->adv_order);
+  if (binary && (sp->adv_order < 1 || sp->adv_order > 4)) return fail(LB200_EINVAL, "advection order %d", sp->adv_order);
   Lb200CollideDev cd;
   Lb200SymmDev sd;
   int rc = collide_dev(c, cp, &cd);
@@ -2148,7 +2148,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     // patch (and its +-2 stencil) stays clear of the slab boundary planes that the neighbours exchange
     const Lb200Geom & g = c->g;
     bool ok = (c->opt.math == LB200_MATH_FAST) && c->knob_wrap && c->knob_phi_sector && c->map_all_fluid
-      && g.per[0] && g.per[1] && g.per[2];
+      && g.per[0] && g.per[1] && g.per[2] && sd.order <= 3;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
     for (int p = 0; p < c->le.nplane; p++) ok = ok && (c->le.loc[p] - g.nh - 1 >= 1) && (c->le.loc[p] + g.nh + 2 <= g.nl[0]);
     if (ok) return step_wrap(c, cd, &sd, nsteps);
@@ -2165,7 +2165,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     const Lb200Geom & g = c->g;
     bool ok = wrap_enabled && g.per[0] && g.per[1] && g.per[2] && c->ndist == 1;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
-    if (binary) ok = ok && ps_on && c->map_all_fluid;
+    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3;      // the one-sweep phi sector exists for orders 1-3
     if (ok) return step_wrap(c, cd, binary ? &sd : nullptr, nsteps);
   }
   {
@@ -2192,7 +2192,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
       }
       // all-fluid lattices: gradient + force + Cahn-Hilliard in one sweep (LB200_PHI_SECTOR=0 disables)
-      const bool use_ps = c->knob_phi_sector && c->map_all_fluid;
+      const bool use_ps = c->knob_phi_sector && c->map_all_fluid && sd.order <= 3;
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
       if (!use_ps) {
 	ProfScope ps(c, LB200_K_GRAD);

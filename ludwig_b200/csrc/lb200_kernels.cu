@@ -1324,6 +1324,13 @@ __device__ __forceinline__ double adv_face(double u_lo, double u_hi, double pm1,
   else if (ORDER == 2) {
     return 0.5*(u_lo + u_hi)*1.0*0.5*(plo + phi_);
   }
+  else if (ORDER == 4) {
+    // four-point central interpolation, reference advection_le_4th (src/advection.c:1153-1262)
+    const double a1 = (1.0/16.0);
+    const double a2 = (9.0/16.0);
+    const double uf = 0.5*(u_lo + u_hi);
+    return uf*(- a1*pm1 + a2*plo + a2*phi_ - a1*pp1);
+  }
   else {
     const double a1 = -0.213933;
     const double a2 =  0.927865;
@@ -1371,7 +1378,7 @@ force_ch_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __restr
   double ux_c = 0.0, ux_xm = 0.0, ux_xp = 0.0, uy_c = 0.0, uy_ym = 0.0, uy_yp = 0.0;
   double uz_c = 0.0, uz_zm = 0.0, uz_zp = 0.0;
   if (DO_CH) {
-    if (ORDER == 3) {
+    if (ORDER >= 3) {
       ph_xm2 = phi[s - 2*xs]; ph_xp2 = phi[s + 2*xs];
       ph_ym2 = phi[s - 2*ys]; ph_yp2 = phi[s + 2*ys];
       ph_zm2 = phi[s - 2];    ph_zp2 = phi[s + 2];
@@ -1464,7 +1471,7 @@ int launch_force_ch_t(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
     else if (minb == 3) force_ch_kernel<DO_FORCE, DO_CH, A, O, M, 3><<<grd, blk, 0, st>>>(g, sp, phi, grad, delsq, u, status, force, phinew); \
     else                force_ch_kernel<DO_FORCE, DO_CH, A, O, M, 4><<<grd, blk, 0, st>>>(g, sp, phi, grad, delsq, u, status, force, phinew); } while (0)
 #define LB200_SEL_M(A, O) do { if (status) LB200_GO(A, O, true); else LB200_GO(A, O, false); } while (0)
-#define LB200_SEL_O(A) do { if (sp.order == 1) LB200_SEL_M(A, 1); else if (sp.order == 2) LB200_SEL_M(A, 2); else LB200_SEL_M(A, 3); } while (0)
+#define LB200_SEL_O(A) do { if (sp.order == 1) LB200_SEL_M(A, 1); else if (sp.order == 2) LB200_SEL_M(A, 2); else if (sp.order == 4) LB200_SEL_M(A, 4); else LB200_SEL_M(A, 3); } while (0)
   if (accumulate) LB200_SEL_O(true); else LB200_SEL_O(false);
 #undef LB200_GO
 #undef LB200_SEL_M

@@ -527,7 +527,7 @@ lc_force_be_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, cons
     const double uy_c = u[1*ns + s], uy_m = u[1*ns + sym], uy_p = u[1*ns + syp];
     const double uz_c = u[2*ns + s], uz_m = u[2*ns + szm], uz_p = u[2*ns + szp];
     int sxm2 = s, sxp2 = s, sym2 = s, syp2 = s, szm2 = s, szp2 = s;
-    if (ORDER == 3) {
+    if (ORDER >= 3) {
       sxm2 = lc_nbr(g, ic - 2, jc, kc); sxp2 = lc_nbr(g, ic + 2, jc, kc);
       sym2 = lc_nbr(g, ic, jc - 2, kc); syp2 = lc_nbr(g, ic, jc + 2, kc);
       szm2 = lc_nbr(g, ic, jc, kc - 2); szp2 = lc_nbr(g, ic, jc, kc + 2);
@@ -539,7 +539,7 @@ lc_force_be_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, cons
       const double f0 = f[s];
       const double fxm = f[sxm], fxp = f[sxp], fym = f[sym], fyp = f[syp], fzm = f[szm], fzp = f[szp];
       double fxm2 = 0.0, fxp2 = 0.0, fym2 = 0.0, fyp2 = 0.0, fzm2 = 0.0, fzp2 = 0.0;
-      if (ORDER == 3) { fxm2 = f[sxm2]; fxp2 = f[sxp2]; fym2 = f[sym2]; fyp2 = f[syp2]; fzm2 = f[szm2]; fzp2 = f[szp2]; }
+      if (ORDER >= 3) { fxm2 = f[sxm2]; fxp2 = f[sxp2]; fym2 = f[sym2]; fyp2 = f[syp2]; fzm2 = f[szm2]; fzp2 = f[szp2]; }
       const double fw  = adv_face<ORDER, true>(ux_m, ux_c, fxm2, fxm, f0, fxp);
       const double fe  = adv_face<ORDER, false>(ux_c, ux_p, fxm, f0, fxp, fxp2);
       const double fy  = adv_face<ORDER, false>(uy_c, uy_p, fym, f0, fyp, fyp2);
@@ -568,7 +568,7 @@ lc_force_be_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, cons
     const double uy_c = u[1*ns + s], uy_m = u[1*ns + sym], uy_p = u[1*ns + syp];
     const double uz_c = u[2*ns + s], uz_m = u[2*ns + szm], uz_p = u[2*ns + szp];
     int sxm2 = s, sxp2 = s, sym2 = s, syp2 = s, szm2 = s, szp2 = s;
-    if (ORDER == 3) {
+    if (ORDER >= 3) {
       sxm2 = lc_nbr(g, ic - 2, jc, kc); sxp2 = lc_nbr(g, ic + 2, jc, kc);
       sym2 = lc_nbr(g, ic, jc - 2, kc); syp2 = lc_nbr(g, ic, jc + 2, kc);
       szm2 = lc_nbr(g, ic, jc, kc - 2); szp2 = lc_nbr(g, ic, jc, kc + 2);
@@ -580,7 +580,7 @@ lc_force_be_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, cons
       const double f0 = f[s];
       const double fxm = f[sxm], fxp = f[sxp], fym = f[sym], fyp = f[syp], fzm = f[szm], fzp = f[szp];
       double fxm2 = 0.0, fxp2 = 0.0, fym2 = 0.0, fyp2 = 0.0, fzm2 = 0.0, fzp2 = 0.0;
-      if (ORDER == 3) { fxm2 = f[sxm2]; fxp2 = f[sxp2]; fym2 = f[sym2]; fyp2 = f[syp2]; fzm2 = f[szm2]; fzp2 = f[szp2]; }
+      if (ORDER >= 3) { fxm2 = f[sxm2]; fxp2 = f[sxp2]; fym2 = f[sym2]; fyp2 = f[syp2]; fzm2 = f[szm2]; fzp2 = f[szp2]; }
       c[n] = f0;
       gx[n] = 0.5*(fxp - fxm);
       gy[n] = 0.5*(fyp - fym);
@@ -647,7 +647,7 @@ int launch_lc_force_be(cudaStream_t st, const Lb200Geom & g, const Lb200LcDev & 
   lc_block_shape(g.nl[2], blk);
   dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
 #define LB200_GO(F, B, O) lc_force_be_kernel<F, B, O><<<grd, blk, 0, st>>>(g, p, accumulate, q, str, u, force, qnew)
-#define LB200_SEL_O(F, B) do { if (p.order == 1) LB200_GO(F, B, 1); else if (p.order == 2) LB200_GO(F, B, 2); else LB200_GO(F, B, 3); } while (0)
+#define LB200_SEL_O(F, B) do { if (p.order == 1) LB200_GO(F, B, 1); else if (p.order == 2) LB200_GO(F, B, 2); else if (p.order == 4) LB200_GO(F, B, 4); else LB200_GO(F, B, 3); } while (0)
   if (do_force && do_be) LB200_SEL_O(true, true);
   else if (do_force)     LB200_GO(true, false, 1);
   else                   LB200_SEL_O(false, true);

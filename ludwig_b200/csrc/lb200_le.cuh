@@ -241,14 +241,14 @@ __device__ __forceinline__ double le_ch_xflux(const Lb200Geom & g, const Lb200Le
   const double mu0 = symm_mu(sp, ph_c, delsq[s]);
   double fx;
   if (WEST) {
-    const double ph_xm2 = (ORDER == 3) ? phi[le_index(g, le_x(le, g, ic, -2), jc, kc)] : 0.0;
+    const double ph_xm2 = (ORDER >= 3) ? phi[le_index(g, le_x(le, g, ic, -2), jc, kc)] : 0.0;
     fx = adv_face<ORDER, true>(u[sm1], u[s], ph_xm2, ph_xm, ph_c, ph_xp);
     fx -= sp.mobility*(mu0 - symm_mu(sp, ph_xm, delsq[sm1]));
     fx -= sp.mobility*sp.gm[0];
     if (status) fx *= (double) (status[s] == 0)*(double) (status[s - g.xs] == 0);
   }
   else {
-    const double ph_xp2 = (ORDER == 3) ? phi[le_index(g, le_x(le, g, ic, +2), jc, kc)] : 0.0;
+    const double ph_xp2 = (ORDER >= 3) ? phi[le_index(g, le_x(le, g, ic, +2), jc, kc)] : 0.0;
     fx = adv_face<ORDER, false>(u[s], u[sp1], ph_xm, ph_c, ph_xp, ph_xp2);
     fx -= sp.mobility*(symm_mu(sp, ph_xp, delsq[sp1]) - mu0);
     fx -= sp.mobility*sp.gm[0];
@@ -348,7 +348,7 @@ le_force_ch_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, con
     const double d_c = delsq[s];
     const double mu0 = symm_mu(sp, ph_c, d_c);
     double ph_ym2 = 0.0, ph_yp2 = 0.0, ph_zm2 = 0.0, ph_zp2 = 0.0;
-    if (ORDER == 3) {
+    if (ORDER >= 3) {
       ph_ym2 = phi[le_index(g, ic, le_wy(g, jc - 2), kc)]; ph_yp2 = phi[le_index(g, ic, le_wy(g, jc + 2), kc)];
       ph_zm2 = phi[le_index(g, ic, jc, le_wz(g, kc - 2))]; ph_zp2 = phi[le_index(g, ic, jc, le_wz(g, kc + 2))];
     }
@@ -419,6 +419,7 @@ int launch_le_ch_prep(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & l
   dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, 2*le.nplane);
   if (sp.order == 1)      le_ch_xflux_kernel<1><<<grd, blk, 0, st>>>(g, le, sp, phi, delsq, u, status, chx);
   else if (sp.order == 2) le_ch_xflux_kernel<2><<<grd, blk, 0, st>>>(g, le, sp, phi, delsq, u, status, chx);
+  else if (sp.order == 4) le_ch_xflux_kernel<4><<<grd, blk, 0, st>>>(g, le, sp, phi, delsq, u, status, chx);
   else                    le_ch_xflux_kernel<3><<<grd, blk, 0, st>>>(g, le, sp, phi, delsq, u, status, chx);
   return 1;
 }
@@ -431,7 +432,7 @@ int launch_le_force_ch(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & 
   block_shape_n(g.nl[2], TPB, blk);
   dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, nx);
 #define LB200_GO(F, C, O) le_force_ch_kernel<F, C, O><<<grd, blk, 0, st>>>(g, le, sp, fix, xlist, accumulate, phi, grad, delsq, u, status, fcor, chx, force, phinew)
-#define LB200_SEL_O(F, C) do { if (sp.order == 1) LB200_GO(F, C, 1); else if (sp.order == 2) LB200_GO(F, C, 2); else LB200_GO(F, C, 3); } while (0)
+#define LB200_SEL_O(F, C) do { if (sp.order == 1) LB200_GO(F, C, 1); else if (sp.order == 2) LB200_GO(F, C, 2); else if (sp.order == 4) LB200_GO(F, C, 4); else LB200_GO(F, C, 3); } while (0)
   if (do_force && do_ch) LB200_SEL_O(true, true);
   else if (do_force)     LB200_GO(true, false, 1);
   else                   LB200_SEL_O(false, true);

@@ -664,6 +664,19 @@ void orc_advection(const orc_geom_t * g, int order, const double * u, const doub
 	  index1 = index0 + 1;
 	  fz[index0] = 0.5*(u0[Z] + u[2*ns + index1])*1*0.5*(phi[index0] + phi[index1]);
 	}
+	else if (order == 4) {
+	  /* advection_le_4th, src/advection.c:1153-1262: four-point central interpolation */
+	  const double a1 = (1.0/16.0);
+	  const double a2 = (9.0/16.0);
+	  uf = 0.5*(u0[X] + u[0*ns + index0 + xm1]);
+	  fw[index0] = uf*(- a1*phi[index0 + xm2] + a2*phi[index0 + xm1] + a2*phi[index0] - a1*phi[index0 + xp1]);
+	  uf = 0.5*(u0[X] + u[0*ns + index0 + xp1]);
+	  fe[index0] = uf*(- a1*phi[index0 + xm1] + a2*phi[index0] + a2*phi[index0 + xp1] - a1*phi[index0 + xp2]);
+	  uf = 0.5*(u0[Y] + u[1*ns + index0 + ys]);
+	  fy[index0] = uf*(- a1*phi[index0 - ys] + a2*phi[index0] + a2*phi[index0 + ys] - a1*phi[index0 + 2*ys]);
+	  uf = 0.5*(u0[Z] + u[2*ns + index0 + 1]);
+	  fz[index0] = uf*(- a1*phi[index0 - 1] + a2*phi[index0] + a2*phi[index0 + 1] - a1*phi[index0 + 2]);
+	}
 	else {
 	  /* west: index2 = -2, index1 = -1, index3 = +1 */
 	  uf = 0.5*1*(u0[X] + u[0*ns + index0 + xm1]);

@@ -331,6 +331,13 @@ void orc_advection_nf(const orc_geom_t * g, int order, int nf, const double * u,
 	      if (face == 0) fl[i0] = 0.5*(u0[X] + u[0*ns + i1])*1*0.5*(f[i1] + f[i0]);
 	      else           fl[i0] = 0.5*(u0[comp[face]] + u[comp[face]*ns + i1])*1*0.5*(f[i0] + f[i1]);
 	    }
+	    else if (order == 4) {
+	      /* advection_le_4th, src/advection.c:1153-1262 */
+	      const double a1 = (1.0/16.0), a2 = (9.0/16.0);
+	      uf = 0.5*(u0[comp[face]] + u[comp[face]*ns + i1]);
+	      if (face == 0) fl[i0] = uf*(- a1*f[i0 + 2*o] + a2*f[i0 + o] + a2*f[i0] - a1*f[i0 - o]);
+	      else           fl[i0] = uf*(- a1*f[i0 - o] + a2*f[i0] + a2*f[i0 + o] - a1*f[i0 + 2*o]);
+	    }
 	    else {
 	      uf = 0.5*1*(u0[comp[face]] + u[comp[face]*ns + i1]);
 	      if (face == 0) {

@@ -33,7 +33,7 @@ def state(orc, lc, seed=17, axis=2):
 
 @pytest.mark.parametrize("n", [(8, 6, 10), (12, 12, 40)])
 @pytest.mark.parametrize("lc", [CHOL, FLD], ids=["chol", "field"])
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_lc_operators_strict_bit_exact(n, lc, order):
     orc = Oracle(n, nhalo=2)
     p = orc.lc_param(**lc)
@@ -90,7 +90,7 @@ def _run(n, lc, order, math, nsteps, path):
 
 
 @pytest.mark.parametrize("path", ["wrap", "halo", "api", "mixed"])
-@pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 40), FLD, 1), ((10, 12, 6), FLD, 2)])
+@pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 40), FLD, 1), ((10, 12, 6), FLD, 2), ((8, 10, 12), CHOL, 4)])
 def test_lc_steps_strict_bit_exact(n, lc, order, path):
     orc, got, want = _run(n, lc, order, lb.MATH_STRICT, 10, path)
     for k in want:
@@ -99,7 +99,7 @@ def test_lc_steps_strict_bit_exact(n, lc, order, path):
 
 
 @pytest.mark.parametrize("path", ["wrap", "halo"])
-@pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 40), FLD, 1), ((32, 32, 32), CHOL, 2)])
+@pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 40), FLD, 1), ((32, 32, 32), CHOL, 2), ((8, 10, 12), CHOL, 4)])
 def test_lc_steps_fast_tolerance(n, lc, order, path):
     orc, got, want = _run(n, lc, order, lb.MATH_FAST, 20, path)
     for k in want:

@@ -59,7 +59,7 @@ def test_le_geometry_host():
 
 
 @pytest.mark.parametrize("n,nplanes", [((16, 8, 6), 1), ((16, 12, 40), 2), ((24, 7, 5), 2)])
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_le_operators_strict_bit_exact(n, nplanes, order):
     orc, sim, sp_o, sp_g = make(n, nplanes, order, lb.MATH_STRICT)
     with sim:
@@ -140,7 +140,7 @@ def _run_steps(n, nplanes, order, math, nsteps, seed=13, wrap=1):
     return orc, sp_o, got, want
 
 
-@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 8, 40), 1, 3), ((24, 8, 6), 2, 2), ((32, 32, 32), 2, 3)])
+@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 8, 40), 1, 3), ((24, 8, 6), 2, 2), ((32, 32, 32), 2, 3), ((16, 10, 8), 2, 4)])
 def test_le_steps_strict_bit_exact(n, nplanes, order):
     orc, sp, got, want = _run_steps(n, nplanes, order, lb.MATH_STRICT, 12)
     for k in want:
@@ -149,7 +149,7 @@ def test_le_steps_strict_bit_exact(n, nplanes, order):
 
 @pytest.mark.parametrize("wrap", [1, 0])
 @pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 16, 40), 1, 3), ((24, 16, 16), 2, 2), ((32, 32, 32), 2, 3),
-                                             ((12, 16, 16), 2, 3)])
+                                             ((12, 16, 16), 2, 3), ((16, 16, 16), 2, 4)])
 def test_le_steps_fast_tolerance(n, nplanes, order, wrap):
     """wrap = 1: the halo-free step (periodic images read in-kernel) with the plane patches; wrap = 0 (and the last
     shape, whose planes sit too close to the x boundary for the halo-free step): the reference's step structure with

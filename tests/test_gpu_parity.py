@@ -196,7 +196,7 @@ def test_phi_force(math):
         assert close_fast(got, force) and close_fast(got2, force2)
 
 
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 @pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST])
 @pytest.mark.parametrize("solid", [0, 1])
 def test_cahn_hilliard(order, math, solid):
@@ -246,7 +246,7 @@ def run_steps(sim, path, cp, sp, nsteps):
 
 
 @pytest.mark.parametrize("nlocal", [(16, 16, 16), (8, 12, 36), (4, 5, 67), (33, 4, 4)])
-@pytest.mark.parametrize("order", [1, 3])
+@pytest.mark.parametrize("order", [1, 3, 4])
 @pytest.mark.parametrize("path", list(STEP_PATHS))
 def test_binary_steps_strict_bit_exact(nlocal, order, path):
     """N whole binary-fluid time steps: CUDA (strict) == oracle, bit for bit, on f, phi, u, rho,
@@ -271,7 +271,7 @@ def test_binary_steps_strict_bit_exact(nlocal, order, path):
 
 @pytest.mark.parametrize("nrelax", [lb.RELAX_M10, lb.RELAX_TRT])
 @pytest.mark.parametrize("path", list(STEP_PATHS))
-@pytest.mark.parametrize("nlocal,order", [((16, 16, 16), 3), ((9, 31, 45), 3), ((20, 6, 8), 1), ((12, 12, 12), 2)])
+@pytest.mark.parametrize("nlocal,order", [((16, 16, 16), 3), ((9, 31, 45), 3), ((20, 6, 8), 1), ((12, 12, 12), 2), ((12, 10, 14), 4)])
 def test_binary_steps_fast_tolerance(nrelax, path, nlocal, order):
     """Fast mode (FMA contraction; in the one-sweep phi sector also re-associated stencil sums, shared
     face fluxes and the cancelled centre terms of the stress divergence): within 1e-12 relative of the

@@ -27,7 +27,7 @@ def make(n, lc, order):
 
 @pytest.mark.parametrize("n", [(8, 6, 10), (12, 12, 12)])
 @pytest.mark.parametrize("lc", [CHOL, FLD], ids=["chol", "field"])
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_lc_operators_vs_reference(n, lc, order):
     ref, orc, p = make(n, lc, order)
     with ref:
@@ -79,7 +79,7 @@ def test_lc_operators_vs_reference(n, lc, order):
         assert np.array_equal(orc.interior(q), orc.interior(ref.get(R.REF_Q)))
 
 
-@pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 16), FLD, 1), ((10, 12, 6), FLD, 2)])
+@pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 16), FLD, 1), ((10, 12, 6), FLD, 2), ((8, 10, 12), CHOL, 4)])
 def test_lc_steps_vs_reference(n, lc, order):
     ref, orc, p = make(n, lc, order)
     with ref:

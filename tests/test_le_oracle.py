@@ -32,7 +32,7 @@ def test_le_geometry():
 
 
 @pytest.mark.parametrize("n,nplanes", [((16, 8, 6), 1), ((16, 12, 8), 2), ((24, 7, 5), 2)])
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_le_operators_vs_reference(n, nplanes, order):
     """every Lees-Edwards operator, same inputs, bit for bit, at a time with a fractional displacement"""
     ref, orc = make(n, nplanes, order)
@@ -97,7 +97,7 @@ def test_le_operators_vs_reference(n, nplanes, order):
         assert np.array_equal(orc.interior(f), orc.interior(ref.get(R.REF_F)))
 
 
-@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 8, 8), 1, 3), ((24, 8, 6), 2, 2)])
+@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 1), ((16, 8, 8), 1, 3), ((24, 8, 6), 2, 2), ((16, 10, 8), 2, 4)])
 def test_le_steps_vs_reference(n, nplanes, order):
     ref, orc = make(n, nplanes, order)
     with ref:

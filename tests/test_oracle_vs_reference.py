@@ -105,7 +105,7 @@ def test_gradient_stress_force_fluxes():
     orc = Oracle(nlocal, nhalo=2)
     rng = np.random.default_rng(5)
     gm = (1e-4, -2e-4, 3e-4)
-    for order in (1, 2, 3):
+    for order in (1, 2, 3, 4):
         with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=order, eta_shear=ETA, gradmu=gm, **BINARY) as s:
             phi = fill_random(s, orc, rh.REF_PHI, rng, scale=0.1, shift=-0.5)
             u = fill_random(s, orc, rh.REF_U, rng, scale=0.05, shift=-0.5)
@@ -164,7 +164,7 @@ def test_no_flux_mask_with_solid_sites():
     assert np.array_equal(orc.interior(phi), orc.interior(ref_phi))
 
 
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 @pytest.mark.parametrize("nlocal", [(12, 10, 8), (16, 16, 16)])
 def test_binary_time_steps(order, nlocal):
     nsteps = 8
