@@ -232,6 +232,9 @@ def run_ours(args, rank, local_rank, world):
         dist.broadcast_object_list(ids, src=0)
         sim.nccl_init(ids[0], world, rank)
 
+    if args.pipe >= 2 and world == 1:
+        sim.set_knob(lb.KNOB_PIPE_SMS, args.pipe_sms)
+        sim.set_knob(lb.KNOB_PIPE, args.pipe)
     ns = sim.nsites
     nall = sim.nall
     # pinned host state (the reference's host arrays: lb->f, phi->data, hydro->u, hydro->rho)
@@ -365,6 +368,8 @@ def run_ours(args, rank, local_rank, world):
                        "math": "strict" if args.strict else "fast(fma)",
                        "x_plane_exchange": {0: "none (one GPU)", 1: "NCCL send/recv on a second stream",
                                             2: "NVLink peer stores from inside the kernels + flags"}[sim.exchange_mode()],
+                       "slab_pipeline": (lambda st: {"slabs": args.pipe, "mode": {1: "green contexts", 2: "priority streams"}.get(st[0], "off"),
+                                                     "sms_phi_sector": st[1][0], "sms_collide": st[1][1]})(sim.pipe_state()),
                        "l2": "inputs (2.8 GB of lattice state per sweep) exceed the 126 MB L2; no flush needed",
                        "e2e_protocol": "pinned-host f+phi -> device, K steps, phi+u+rho -> pinned host "
                                        "(the reference's own lb_memcpy/field_memcpy usage, src/ludwig.c:501-506, 985)"},
@@ -563,6 +568,10 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=128, help="edge of the CPU-baseline sample lattice")
     ap.add_argument("--strict", action="store_true", help="bit-exact arithmetic mode (no FMA contraction)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pipe", type=int, default=int(os.environ.get("LB200_PIPE", "0")),
+                    help="slab pipeline of the single-GPU step: x-slabs (0: off; LB200_KNOB_PIPE)")
+    ap.add_argument("--pipe-sms", type=int, default=int(os.environ.get("LB200_PIPE_SMS", "56")),
+                    help="SMs of the phi-sector partition (LB200_KNOB_PIPE_SMS)")
     ap.add_argument("--lc", action="store_true", help="secondary workload: liquid crystal (BASELINE config 4), --size 128 unless given")
     ap.add_argument("--le", type=int, default=0, help="Lees-Edwards planes per GPU (0: none, the headline workload)")
     ap.add_argument("--strong", action="store_true",

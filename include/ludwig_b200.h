@@ -245,11 +245,22 @@ enum lb200_knob {
                                *    the interior; only the planes the kernels read cross NVLink)
                                * 0: the reference's step structure with three halo swaps (phi, u, f) */
   LB200_KNOB_PHI_SECTOR = 2,  /* 1: gradient + force + Cahn-Hilliard in one sweep (all-fluid lattices) */
-  LB200_KNOB_PEER = 3         /* 1: x-slab neighbours exchange planes by NVLink peer stores from inside the kernels
+  LB200_KNOB_PEER = 3,        /* 1: x-slab neighbours exchange planes by NVLink peer stores from inside the kernels
                                *    (cudaIpc-mapped arrays + one flag per kernel); 0: NCCL send/recv.  Must be set
                                *    identically on every rank.  Default LB200_PEER, else 1 */
+  LB200_KNOB_PIPE = 4,        /* S >= 2: slab pipeline of the single-GPU binary-fluid step -- the lattice is cut into S
+                               *    x-slabs and the two kernels of a step run CONCURRENTLY on disjoint SM partitions
+                               *    (CUDA green contexts), the collision of slab s next to the phi sector of the slabs
+                               *    after it (same operations on the same data: results unchanged).  0: off.
+                               *    Default LB200_PIPE, else 0 */
+  LB200_KNOB_PIPE_SMS = 5     /* SMs provisioned for the phi-sector partition (rounded up to the device's partition
+                               *    granularity, 8 on sm_100); the collision gets the rest.  Default LB200_PIPE_SMS, else 56.
+                               *    Must be set before the first pipelined step */
 };
 int lb200_set_knob(lb200_t * ctx, int knob, int value);
+/* slab pipeline of this context: 0 = not used yet, 1 = green contexts (sms[0] / sms[1] = SMs of the phi-sector /
+ * collision partition), 2 = two priority streams sharing every SM (no partition API), -1 = unavailable */
+int lb200_pipe_state(const lb200_t * ctx, int sms[2]);
 /* how lb200_step exchanges x-planes on this context: 0 = single GPU, 1 = NCCL send/recv, 2 = peer stores
  * (meaningful after the first lb200_step, which sets the mapping up collectively) */
 int lb200_exchange_mode(const lb200_t * ctx);

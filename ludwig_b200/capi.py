@@ -8,7 +8,7 @@ RELAX_M10, RELAX_BGK, RELAX_TRT = 0, 1, 2
 HALO_FULL, HALO_REDUCED = 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 H2D, D2H = 1, 2
-KNOB_WRAP, KNOB_PHI_SECTOR, KNOB_PEER = 1, 2, 3
+KNOB_WRAP, KNOB_PHI_SECTOR, KNOB_PEER, KNOB_PIPE, KNOB_PIPE_SMS = 1, 2, 3, 4, 5
 
 _NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1, GRAD_DELSQ: 3, DELSQ_DELSQ: 1, STR: 9,
           Q: 5, QGRAD: 15, QDELSQ: 5}
@@ -163,6 +163,7 @@ def load_library():
     lib.lb200_launch_count.argtypes = [C.c_void_p]
     lib.lb200_set_knob.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.lb200_exchange_mode.argtypes = [C.c_void_p]
+    lib.lb200_pipe_state.argtypes = [C.c_void_p, C.POINTER(C.c_int * 2)]
     lib.lb200_launch_count.restype = C.c_longlong
     lib.lb200_stream.argtypes = [C.c_void_p]
     lib.lb200_stream.restype = C.c_void_p
@@ -416,6 +417,12 @@ class Lb200:
     def exchange_mode(self):
         """0 single GPU, 1 NCCL send/recv, 2 NVLink peer stores from inside the kernels."""
         return int(self.lib.lb200_exchange_mode(self.h))
+
+    def pipe_state(self):
+        """(state, (phi-sector SMs, collision SMs)): 0 not used, 1 green-context SM partitions, 2 priority streams."""
+        sms = (C.c_int * 2)()
+        st = int(self.lib.lb200_pipe_state(self.h, C.byref(sms)))
+        return st, (int(sms[0]), int(sms[1]))
 
     def launch_count(self):
         return int(self.lib.lb200_launch_count(self.h))

@@ -13,6 +13,7 @@
 #include <new>
 #include <vector>
 
+#include <cuda.h>             // types of the driver's green-context API (entry points through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #ifndef LB200_NO_NCCL
 #include <nccl.h>
@@ -46,6 +47,8 @@ struct PeerLink {            // one neighbour's arrays, in ITS allocation order
   double * u[2];
   unsigned int * flags;
 };
+
+enum { LB200_PIPE_MAXS = 16 };
 
 struct lb200_s {
   lb200_options_t opt;
@@ -104,6 +107,15 @@ struct lb200_s {
   int knob_wrap;             // lb200_set_knob
   int knob_phi_sector;
   int knob_peer;
+  int knob_pipe;             // slab pipeline of lb200_step: number of x-slabs (0: off)
+  int knob_pipe_sms;         // SMs of the phi-sector partition (the collision gets the rest)
+
+  // slab pipeline (step_pipe): the two kernels of a binary-fluid step on disjoint SM partitions (green contexts)
+  int pipe_state;            // 0: not set up, 1: green contexts, 2: plain priority streams, -1: unavailable
+  cudaStream_t pipe_a, pipe_b;            // phi sector / collision
+  cudaEvent_t pipe_ev_ps[LB200_PIPE_MAXS], pipe_ev_c[LB200_PIPE_MAXS], pipe_ev_join[2];
+  void * pipe_gctx[2];       // CUgreenCtx
+  int pipe_sm[2];            // SMs provisioned for the phi sector / the collision
 
   // peer-store exchange of lb200_step on x-slabs: the neighbours' arrays mapped into this process (cudaIpc)
   int peer_state;            // 0: not set up yet, 1: active, -1: unavailable (NCCL exchange instead)
@@ -316,6 +328,9 @@ static void symm_dev(const lb200_t * c, const lb200_symm_param_t * sp, Lb200Symm
 static int alloc_d(double ** p, size_t n) {
   CUDA_TRY(cudaMalloc((void **) p, n*sizeof(double)));
   CUDA_TRY(cudaMemset(*p, 0, n*sizeof(double)));
+  // cudaMemset on device memory returns before the fill has run, on the legacy stream, which is not ordered with
+  // the contexts' non-blocking streams: without this wait the fill can land after the first upload / kernel
+  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
   return 0;
 }
 
@@ -407,8 +422,11 @@ static int le_alloc(lb200_t * c) {
   c->le_nxlist = (int) xl.size();
   if (cudaMalloc((void **) &c->le_trip, trip.size()*sizeof(int)) != cudaSuccess) return -1;
   if (cudaMalloc((void **) &c->le_xlist, xl.size()*sizeof(int)) != cudaSuccess) return -1;
-  if (cudaMemcpy(c->le_trip, trip.data(), trip.size()*sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
-  if (cudaMemcpy(c->le_xlist, xl.data(), xl.size()*sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  // on the context's own (non-blocking) stream, which orders them before every kernel of this context: a legacy-stream
+  // cudaMemcpy from pageable memory may return before the DMA has landed and is not ordered with c->stream
+  if (cudaMemcpyAsync(c->le_trip, trip.data(), trip.size()*sizeof(int), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -1;
+  if (cudaMemcpyAsync(c->le_xlist, xl.data(), xl.size()*sizeof(int), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
   int rc = 0;
   rc |= alloc_d(&c->le_term, (size_t) 3*npl*nyz);
   rc |= alloc_d(&c->le_fcor, (size_t) 3*npl);
@@ -544,7 +562,8 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
 
   if (model_init(c->nvel, &c->model_h) != 0) { delete c; return fail(LB200_EINVAL, "model"); }
   CUDA_TRY(cudaMalloc((void **) &c->model_d, sizeof(Lb200ModelDev)));
-  CUDA_TRY(cudaMemcpy(c->model_d, &c->model_h, sizeof(Lb200ModelDev), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpyAsync(c->model_d, &c->model_h, sizeof(Lb200ModelDev), cudaMemcpyHostToDevice, c->stream));   // ordered before every kernel
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->unrolled19 = (c->nvel == 19);
   {
     const char * e = getenv("LB200_GENERIC_D3Q19");     // model matrices instead of coded constants
@@ -581,7 +600,8 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   if (rc == 0 && c->le.nplane > 0) rc = le_alloc(c);
   if (rc != 0) { lb200_free(c); return LB200_ECUDA; }
   CUDA_TRY(cudaMalloc((void **) &c->status, nsz));
-  CUDA_TRY(cudaMemset(c->status, 0, nsz));
+  CUDA_TRY(cudaMemsetAsync(c->status, 0, nsz, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->map_all_fluid = 1;
 
   c->force_state = ARRAY_CLEAN;
@@ -589,6 +609,8 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   c->knob_wrap = getenv("LB200_WRAP") ? atoi(getenv("LB200_WRAP")) : 1;
   c->knob_phi_sector = getenv("LB200_PHI_SECTOR") ? atoi(getenv("LB200_PHI_SECTOR")) : 1;
   c->knob_peer = getenv("LB200_PEER") ? atoi(getenv("LB200_PEER")) : 1;
+  c->knob_pipe = getenv("LB200_PIPE") ? atoi(getenv("LB200_PIPE")) : 0;
+  c->knob_pipe_sms = getenv("LB200_PIPE_SMS") ? atoi(getenv("LB200_PIPE_SMS")) : 56;
   c->f_alloc[0] = c->f; c->f_alloc[1] = c->fprime;
   c->phi_alloc[0] = c->phi; c->phi_alloc[1] = c->phinew;
   if (o->have_q) { c->phi_alloc[0] = c->q; c->phi_alloc[1] = c->qnew; }     // the order-parameter slots of the peer links carry Q
@@ -603,6 +625,11 @@ int lb200_set_knob(lb200_t * c, int knob, int value) {
   if (knob == LB200_KNOB_WRAP) c->knob_wrap = (value != 0);
   else if (knob == LB200_KNOB_PHI_SECTOR) c->knob_phi_sector = (value != 0);
   else if (knob == LB200_KNOB_PEER) { c->knob_peer = (value != 0); c->wrap_x_valid = 0; }
+  else if (knob == LB200_KNOB_PIPE) c->knob_pipe = (value < 0) ? 0 : (value > LB200_PIPE_MAXS ? LB200_PIPE_MAXS : value);
+  else if (knob == LB200_KNOB_PIPE_SMS) {
+    if (c->pipe_state != 0) return fail(LB200_ESTATE, "the SM partitions of the slab pipeline are already provisioned");
+    c->knob_pipe_sms = value;
+  }
   else return fail(LB200_EINVAL, "unknown knob %d", knob);
   return 0;
 }
@@ -633,6 +660,8 @@ int lb200_profile_get(lb200_t * c, int kclass, double * total_ms, int * count) {
   return 0;
 }
 
+static void pipe_teardown(lb200_t * c);
+
 int lb200_free(lb200_t * c) {
   if (c == nullptr) return 0;
   cudaSetDevice(c->device);
@@ -648,6 +677,7 @@ int lb200_free(lb200_t * c) {
   for (int i = 0; i < LB200_KCLASS_MAX; i++) {
     if (c->ev[i]) { for (cudaEvent_t e : *c->ev[i]) cudaEventDestroy(e); delete c->ev[i]; }
   }
+  pipe_teardown(c);
   cudaStreamSynchronize(c->comm);
   cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_phi); cudaEventDestroy(c->ev_u); cudaEventDestroy(c->ev_f);
   cudaStreamDestroy(c->comm);
@@ -1389,6 +1419,7 @@ static int peer_setup(lb200_t * c) {
   CUDA_TRY(cudaMemset(c->flags, 0, FLAG_COUNT*sizeof(unsigned int)));
   CUDA_TRY(cudaMalloc((void **) &c->spin_err, sizeof(int)));
   CUDA_TRY(cudaMemset(c->spin_err, 0, sizeof(int)));
+  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
 
   void * mine[NH] = {c->f_alloc[0], c->f_alloc[1], c->phi_alloc[0], c->phi_alloc[1], c->u_alloc[0], c->u_alloc[1], c->flags};
   std::vector<cudaIpcMemHandle_t> hs(NH), all((size_t) NH*P);
@@ -1754,6 +1785,228 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     if (c->u_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
     if (binary && c->phi_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
   }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+
+// ---- slab pipeline of the single-GPU binary-fluid step (LB200_KNOB_PIPE) ----------------------------------------
+// The two kernels of a step bound on different resources: the collision on HBM bandwidth with most issue slots
+// idle, the phi sector on shared-memory instruction issue with half the bandwidth idle (profiles/).  They depend
+// on each other only through neighbouring x-planes:
+//   phi_sector(n, slab s) reads u(n-1) of slabs s-1, s, s+1 and overwrites force on slab s   -> after collide(n-1, s-1 .. s+1)
+//   collide(n, slab s)    reads force(n) of slab s                                           -> after phi_sector(n, s)
+// (phi, f: each is produced and consumed on one stream, in order; u is double-buffered.)  So with the lattice cut
+// into S x-slabs, stream A runs the phi sector slab by slab and stream B the collision slab by slab, linked by
+// one event per slab, and the phi sector of step n+1 runs next to the collision of step n.  Each stream belongs
+// to a green context with its own SM partition, so that neither kernel's CTAs queue behind the other's.
+
+typedef CUresult (*fn_cuDeviceGet_t)(CUdevice *, int);
+typedef CUresult (*fn_cuDeviceGetDevResource_t)(CUdevice, CUdevResource *, CUdevResourceType);
+typedef CUresult (*fn_cuDevSmResourceSplitByCount_t)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *,
+						     unsigned int, unsigned int);
+typedef CUresult (*fn_cuDevResourceGenerateDesc_t)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+typedef CUresult (*fn_cuGreenCtxCreate_t)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+typedef CUresult (*fn_cuGreenCtxStreamCreate_t)(CUstream *, CUgreenCtx, unsigned int, int);
+typedef CUresult (*fn_cuGreenCtxDestroy_t)(CUgreenCtx);
+
+template <class F> static bool driver_entry(const char * name, F * fn) {
+  void * p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+    cudaGetLastError();
+    return false;
+  }
+  *fn = (F) p;
+  return true;
+}
+
+// two green contexts: >= knob_pipe_sms SMs for the phi sector, the remaining SMs for the collision
+static bool pipe_green(lb200_t * c) {
+  fn_cuDeviceGet_t dev_get; fn_cuDeviceGetDevResource_t get_res; fn_cuDevSmResourceSplitByCount_t split;
+  fn_cuDevResourceGenerateDesc_t gen_desc; fn_cuGreenCtxCreate_t gctx_create; fn_cuGreenCtxStreamCreate_t gstream;
+  fn_cuGreenCtxDestroy_t gctx_destroy;
+  if (!driver_entry("cuDeviceGet", &dev_get) || !driver_entry("cuDeviceGetDevResource", &get_res)
+      || !driver_entry("cuDevSmResourceSplitByCount", &split) || !driver_entry("cuDevResourceGenerateDesc", &gen_desc)
+      || !driver_entry("cuGreenCtxCreate", &gctx_create) || !driver_entry("cuGreenCtxStreamCreate", &gstream)
+      || !driver_entry("cuGreenCtxDestroy", &gctx_destroy)) return false;
+  CUdevice dev;
+  CUdevResource all, part[2];
+  unsigned int ngroups = 1;
+  memset(&all, 0, sizeof(all)); memset(part, 0, sizeof(part));
+  if (dev_get(&dev, c->device) != CUDA_SUCCESS) return false;
+  if (get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+  const int want = c->knob_pipe_sms;
+  if (want < 8 || want + 8 > (int) all.sm.smCount) return false;
+  if (split(&part[0], &ngroups, &all, &part[1], 0, (unsigned int) want) != CUDA_SUCCESS || ngroups != 1) return false;
+  if (part[0].sm.smCount == 0 || part[1].sm.smCount == 0) return false;
+  CUgreenCtx g[2] = {nullptr, nullptr};
+  CUstream st[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; i++) {
+    CUdevResourceDesc desc = nullptr;
+    if (gen_desc(&desc, &part[i], 1) != CUDA_SUCCESS || gctx_create(&g[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS
+	|| gstream(&st[i], g[i], CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+      for (int j = 0; j <= i; j++) { if (st[j]) cudaStreamDestroy((cudaStream_t) st[j]); if (g[j]) gctx_destroy(g[j]); }
+      cudaGetLastError();
+      return false;
+    }
+  }
+  c->pipe_a = (cudaStream_t) st[0]; c->pipe_b = (cudaStream_t) st[1];
+  c->pipe_gctx[0] = g[0]; c->pipe_gctx[1] = g[1];
+  c->pipe_sm[0] = (int) part[0].sm.smCount; c->pipe_sm[1] = (int) part[1].sm.smCount;
+  return true;
+}
+
+static void pipe_teardown(lb200_t * c) {
+  if (c->pipe_state <= 0) return;
+  cudaStreamSynchronize(c->pipe_a); cudaStreamSynchronize(c->pipe_b);
+  for (int i = 0; i < LB200_PIPE_MAXS; i++) { cudaEventDestroy(c->pipe_ev_ps[i]); cudaEventDestroy(c->pipe_ev_c[i]); }
+  cudaEventDestroy(c->pipe_ev_join[0]); cudaEventDestroy(c->pipe_ev_join[1]);
+  cudaStreamDestroy(c->pipe_a); cudaStreamDestroy(c->pipe_b);
+  fn_cuGreenCtxDestroy_t gctx_destroy;
+  if (c->pipe_state == 1 && driver_entry("cuGreenCtxDestroy", &gctx_destroy)) {
+    gctx_destroy((CUgreenCtx) c->pipe_gctx[0]); gctx_destroy((CUgreenCtx) c->pipe_gctx[1]);
+  }
+  c->pipe_state = 0;
+}
+
+static int pipe_setup(lb200_t * c) {
+  if (c->pipe_state != 0) return 0;
+  const char * e = getenv("LB200_PIPE_GREEN");
+  const bool try_green = (e == nullptr) || atoi(e) != 0;
+  if (try_green && pipe_green(c)) {
+    // a kernel of this library's module must launch on a green-context stream and events must link the two
+    // partitions: check once, and fall back to plain streams if the driver refuses
+    c->pipe_state = 1;
+    unsigned int * scratch = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool ok = cudaMalloc((void **) &scratch, 2*sizeof(unsigned int)) == cudaSuccess
+      && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {
+      c->k->signal(c->pipe_a, scratch, scratch + 1, 1u);
+      ok = cudaGetLastError() == cudaSuccess && cudaEventRecord(ev, c->pipe_a) == cudaSuccess
+	&& cudaStreamWaitEvent(c->pipe_b, ev, 0) == cudaSuccess;
+      if (ok) { c->k->signal(c->pipe_b, scratch, scratch + 1, 2u); ok = cudaGetLastError() == cudaSuccess; }
+      ok = ok && cudaStreamSynchronize(c->pipe_b) == cudaSuccess && cudaStreamSynchronize(c->pipe_a) == cudaSuccess;
+    }
+    if (ev) cudaEventDestroy(ev);
+    cudaFree(scratch);
+    if (!ok) {
+      cudaGetLastError();
+      cudaStreamDestroy(c->pipe_a); cudaStreamDestroy(c->pipe_b);
+      fn_cuGreenCtxDestroy_t gctx_destroy;
+      if (driver_entry("cuGreenCtxDestroy", &gctx_destroy)) { gctx_destroy((CUgreenCtx) c->pipe_gctx[0]); gctx_destroy((CUgreenCtx) c->pipe_gctx[1]); }
+      c->pipe_state = 0;
+    }
+  }
+  if (c->pipe_state == 0) {
+    // no partition API: two streams, the phi sector (one CTA needs a whole SM's registers) at the higher priority
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->pipe_a, cudaStreamNonBlocking, hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->pipe_b, cudaStreamNonBlocking, lo));
+    c->pipe_sm[0] = c->pipe_sm[1] = 0;
+    c->pipe_state = 2;
+  }
+  for (int i = 0; i < LB200_PIPE_MAXS; i++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&c->pipe_ev_ps[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->pipe_ev_c[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&c->pipe_ev_join[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->pipe_ev_join[1], cudaEventDisableTiming));
+  if (c->u_alloc[1] == nullptr) {
+    if (alloc_d(&c->u2, (size_t) 3*c->g.nsites) != 0) return LB200_ECUDA;
+    c->u_alloc[0] = c->u; c->u_alloc[1] = c->u2;
+  }
+  return 0;
+}
+
+int lb200_pipe_state(const lb200_t * c, int sms[2]) {
+  if (c == nullptr) return LB200_EINVAL;
+  if (sms != nullptr) { sms[0] = c->pipe_sm[0]; sms[1] = c->pipe_sm[1]; }
+  return c->pipe_state;
+}
+
+static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev * sd, int nsteps);
+
+static bool pipe_eligible(const lb200_t * c, int nsteps) {
+  const Lb200Geom & g = c->g;
+  return c->knob_pipe >= 2 && !g.remote_x && c->le.nplane == 0 && c->nvel == 19 && c->unrolled19 && c->ndist == 1
+    && c->map_all_fluid && nsteps >= 2 && g.nl[0] >= 8*c->knob_pipe && c->pipe_state >= 0
+    && !c->profile;          // per-kernel timing wants each kernel alone on the device
+}
+
+static int step_pipe(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev & sd, int nsteps) {
+  int rc = pipe_setup(c);
+  if (rc != 0) return rc;
+  // the first step after an upload (in-place collision, u = 0 to materialise) takes the serial path
+  if (!c->prop_pending || c->u_state == ZERO_PENDING || c->u_state == ARRAY_CLEAN) {
+    rc = step_wrap(c, cd, &sd, 1);
+    if (rc != 0) return rc;
+    nsteps -= 1;
+  }
+  if (nsteps <= 0) return 0;
+
+  const int S = c->knob_pipe;
+  Lb200Geom gw = c->g;
+  gw.wrap[0] = gw.wrap[1] = gw.wrap[2] = 1;
+  cudaStream_t A = c->pipe_a, B = c->pipe_b;
+  int x0[LB200_PIPE_MAXS + 1];
+  for (int s = 0; s <= S; s++) x0[s] = (int) (((long long) s*gw.nl[0])/S);
+  static const int chunks_per_slab = getenv("LB200_PIPE_CHUNKS") ? atoi(getenv("LB200_PIPE_CHUNKS")) : 1;
+
+  CUDA_TRY(cudaEventRecord(c->ev_main, c->stream));
+  CUDA_TRY(cudaStreamWaitEvent(A, c->ev_main, 0));
+  CUDA_TRY(cudaStreamWaitEvent(B, c->ev_main, 0));
+
+  bool linked = false;          // pipe_ev_c[] hold the collisions of the previous pipelined step
+  for (int n = 0; n < nsteps; n++) {
+    c->t_current += 1;
+    double * u_in = c->u;
+    double * u_out = (c->u == c->u_alloc[0]) ? c->u_alloc[1] : c->u_alloc[0];
+    for (int s = 0; s < S; s++) {
+      if (linked) {
+	const int sm = (s + S - 1) % S, sp = (s + 1) % S;
+	CUDA_TRY(cudaStreamWaitEvent(A, c->pipe_ev_c[s], 0));
+	CUDA_TRY(cudaStreamWaitEvent(A, c->pipe_ev_c[sm], 0));
+	if (sp != sm) CUDA_TRY(cudaStreamWaitEvent(A, c->pipe_ev_c[sp], 0));
+      }
+      Lb200Geom gs = gw;
+      gs.xoff = x0[s]; gs.xcnt = x0[s + 1] - x0[s];
+      gs.xchunk = (chunks_per_slab >= 1) ? (gs.xcnt + chunks_per_slab - 1)/chunks_per_slab : 0;
+      {
+	ProfScope ps(c, LB200_K_PHI_SECTOR, A);
+	c->launches += c->k->phi_sector(A, gs, sd, c->phi, u_in, c->grad, c->delsq, c->force, c->phinew);
+      }
+      CUDA_TRY(cudaEventRecord(c->pipe_ev_ps[s], A));
+    }
+    { double * t = c->phi; c->phi = c->phinew; c->phinew = t; }
+    for (int s = 0; s < S; s++) {
+      CUDA_TRY(cudaStreamWaitEvent(B, c->pipe_ev_ps[s], 0));
+      Lb200Geom gs = gw;
+      gs.xoff = x0[s]; gs.xcnt = x0[s + 1] - x0[s];
+      {
+	ProfScope ps(c, LB200_K_COLLIDE, B);
+	c->launches += c->k->collide(B, gs, cd, nullptr, 19, 1, c->f, c->fprime, c->force, nullptr, c->rho, u_out);
+      }
+      CUDA_TRY(cudaEventRecord(c->pipe_ev_c[s], B));
+    }
+    { double * t = c->f; c->f = c->fprime; c->fprime = t; }
+    c->u = u_out;
+    linked = true;
+  }
+  c->force_state = INTERIOR_ONLY;
+  c->u_state = INTERIOR_ONLY;
+  c->prop_pending = 1;
+  c->f_halo_stale = 1;
+  c->phi_halo_valid = 0;
+  c->u_halo_valid = 0;
+  c->wrap_x_valid = 1;
+  // rejoin the context's stream
+  CUDA_TRY(cudaEventRecord(c->pipe_ev_join[0], A));
+  CUDA_TRY(cudaEventRecord(c->pipe_ev_join[1], B));
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->pipe_ev_join[0], 0));
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->pipe_ev_join[1], 0));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -2166,6 +2419,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     bool ok = wrap_enabled && g.per[0] && g.per[1] && g.per[2] && c->ndist == 1;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
     if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3;      // the one-sweep phi sector exists for orders 1-3
+    if (ok && binary && pipe_eligible(c, nsteps)) return step_pipe(c, cd, sd, nsteps);
     if (ok) return step_wrap(c, cd, binary ? &sd : nullptr, nsteps);
   }
   {

@@ -117,7 +117,7 @@ __device__ __forceinline__ void relax_hydro(double * __restrict__ mode, const do
 // swap of lb_halo for the local dimensions costs nothing.  Dimensions with g.wrap[d] == 0 (x with
 // slab neighbours on other GPUs) still read the halo planes, which the exchange has filled.
 template <bool PULL, bool GHOST, bool HAS_FORCE, bool HAS_MAP, bool STREAM, bool WRAP>
-__global__ void __launch_bounds__(TPB_MAX)
+__global__ void __launch_bounds__(TPB_MAX, GHOST ? 3 : 4)
 collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 		     const double * __restrict__ fsrc, double * __restrict__ fdst,
 		     const double * __restrict__ hforce, const char * __restrict__ status,
@@ -125,7 +125,7 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 
   const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
   const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
-  const int ic = 1 + blockIdx.z;
+  const int ic = 1 + g.xoff + blockIdx.z;
   if (kc > g.nl[2] || jc > g.nl[1]) return;
 
   const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
@@ -594,6 +594,7 @@ int launch_collide(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev &
   dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
 
   if (nvel == 19 && md == nullptr) {
+    if (g.xcnt > 0) grd.z = g.xcnt;                 // slab pipeline: planes xoff+1 .. xoff+xcnt
     static const int stream_stores = tuned_flag("LB200_STCS", 1);
     const bool wrap = pull && (g.wrap[0] || g.wrap[1] || g.wrap[2]);
 #define LB200_GO(P, G, F, M) do { if (wrap && P) collide_d3q19_kernel<P, G, F, M, true, P><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, status, rho, u); \
@@ -1560,8 +1561,8 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc, const double
   const int kbase = blockIdx.x*PS_TZ;              // thread column (j,k) = (jbase + ty, kbase + tz)
   const int jbase = blockIdx.y*PS_TY;
   const int kc = kbase + tz, jc = jbase + ty;
-  const int i0 = 1 + blockIdx.z*xc;
-  const int i1 = min(i0 + xc - 1, g.nl[0]);
+  const int i0 = 1 + g.xoff + blockIdx.z*xc;
+  const int i1 = min(i0 + xc - 1, g.xcnt > 0 ? g.xoff + g.xcnt : g.nl[0]);
   const int nh = g.nh;
   const size_t ns = (size_t) g.nsites;
   const int xs = g.xs, ys = g.ys;
@@ -2002,8 +2003,8 @@ phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
   k.tid = ty*PS_BZ + tz;
   k.pc = (ty + 1)*PS_PZ + (tz + 1);                // own position in the phi tile
   k.xs = g.xs; k.ns = g.nsites; k.nh = nh; k.nlx = g.nl[0]; k.wx = g.wrap[0];
-  k.i0 = 1 + blockIdx.z*xc;
-  k.i1 = min(k.i0 + xc - 1, g.nl[0]);
+  k.i0 = 1 + g.xoff + blockIdx.z*xc;
+  k.i1 = min(k.i0 + xc - 1, g.xcnt > 0 ? g.xoff + g.xcnt : g.nl[0]);
   k.M = sp.mobility; k.kappa = sp.kappa; k.a = sp.a; k.b = sp.b; k.wz = sp.wz;
   k.peer_lo = g.peer_phi_lo; k.peer_hi = g.peer_phi_hi;
   k.mg0 = sp.mobility*sp.gm[0]; k.mg1 = sp.mobility*sp.gm[1]; k.mg2 = sp.mobility*sp.gm[2];
@@ -2128,8 +2129,9 @@ int launch_phi_sector(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
     cudaFuncSetAttribute(LB200_PS_KERNEL<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     configured = true;
   }
-  const int xc = ps_pick_xc((const void *) LB200_PS_KERNEL<3>, smem, gz*gy, g.nl[0], fill);
-  dim3 grd(gz, gy, (g.nl[0] + xc - 1)/xc);
+  const int nx = (g.xcnt > 0) ? g.xcnt : g.nl[0];
+  const int xc = (g.xchunk > 0) ? g.xchunk : ps_pick_xc((const void *) LB200_PS_KERNEL<3>, smem, gz*gy, nx, fill);
+  dim3 grd(gz, gy, (nx + xc - 1)/xc);
   if (sp.order == 1)      LB200_PS_KERNEL<1><<<grd, blk, smem, st>>>(g, sp, xc, phi, u, grad, delsq, force, phinew);
   else if (sp.order == 2) LB200_PS_KERNEL<2><<<grd, blk, smem, st>>>(g, sp, xc, phi, u, grad, delsq, force, phinew);
   else                    LB200_PS_KERNEL<3><<<grd, blk, smem, st>>>(g, sp, xc, phi, u, grad, delsq, force, phinew);

@@ -23,6 +23,10 @@ struct Lb200Geom {
   double * peer_f_lo, * peer_f_hi;
   double * peer_u_lo, * peer_u_hi;
   double * peer_phi_lo, * peer_phi_hi;
+  // x sub-range of one launch (the slab pipeline of lb200_step, collide_d3q19 and the phi-sector kernels only):
+  // planes xoff+1 .. xoff+xcnt; xcnt == 0: all of 1 .. nl[0].  xchunk > 0: planes per phi-sector CTA (0: chosen
+  // from the SM count).
+  int xoff, xcnt, xchunk;
 };
 
 // Lees-Edwards planes (reference src/leesedwards.c).  Field arrays of an LE context carry 2*nh*nplane buffer

@@ -293,6 +293,42 @@ def test_binary_steps_fast_tolerance(nrelax, path, nlocal, order):
         assert close_fast(orc.interior(got[k]), orc.interior(st[k])), (k, rel_err(orc.interior(got[k]), orc.interior(st[k])))
 
 
+@pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+@pytest.mark.parametrize("nlocal,nslab,order,green", [((32, 12, 20), 2, 3, 1), ((24, 16, 16), 3, 1, 1), ((40, 8, 36), 4, 2, 1),
+                                                      ((32, 12, 20), 3, 3, 0)])
+def test_binary_steps_slab_pipeline(nlocal, nslab, order, green, math, monkeypatch):
+    """LB200_KNOB_PIPE: the phi sector and the collision of consecutive x-slabs (and of consecutive steps) run
+    concurrently on two SM partitions (green contexts; green = 0: two priority streams).  Same operations on the
+    same data as the serial step: strict mode stays bit-identical to the oracle, fast mode within tolerance; steps
+    issued in two calls so that the pipeline is entered both after an upload and from a pipelined state."""
+    monkeypatch.setenv("LB200_PIPE_GREEN", str(green))
+    orc = Oracle(nlocal, nhalo=2)
+    st = seeded_state(orc)
+    fg = (1e-6, -2e-6, 5e-7)
+    cpo = orc.collide_param(lb.RELAX_M10, 1.0, ETA, force=fg)
+    spo = orc.symm_param(adv_order=order, **BINARY)
+    with make_sim(orc, st, math=math) as sim:
+        sim.set_knob(lb.KNOB_PIPE, nslab)
+        sim.set_knob(lb.KNOB_PIPE_SMS, 48)
+        cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA, force=fg)
+        sp = lb.SymmParam.make(adv_order=order, **BINARY)
+        sim.step(cp, sp, 7)
+        sim.step(cp, sp, 5)
+        state, sms = sim.pipe_state()
+        assert state == (1 if green else 2), (state, sms)
+        if green:
+            assert sms[0] >= 48 and sms[1] >= 8
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO),
+                                          ("force", lb.FORCE), ("grad", lb.GRAD), ("delsq", lb.DELSQ))}
+    orc.step(cpo, spo, 1, 12, st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    for k in got:
+        a, b = orc.interior(got[k]), orc.interior(st[k])
+        if math == lb.MATH_STRICT:
+            assert np.array_equal(a, b), k
+        else:
+            assert close_fast(a, b), (k, rel_err(a, b))
+
+
 @pytest.mark.parametrize("nvel", [19, 15, 27])
 @pytest.mark.parametrize("reduced", [0, 1])
 @pytest.mark.parametrize("wrap", [1, 0])
