@@ -232,6 +232,8 @@ def run_ours(args, rank, local_rank, world):
         dist.broadcast_object_list(ids, src=0)
         sim.nccl_init(ids[0], world, rank)
 
+    if args.f32:
+        sim.set_knob(lb.KNOB_F32, 1)
     if args.pipe >= 2 and world == 1:
         sim.set_knob(lb.KNOB_PIPE_SMS, args.pipe_sms)
         sim.set_knob(lb.KNOB_PIPE, args.pipe)
@@ -312,7 +314,9 @@ def run_ours(args, rank, local_rank, world):
     kernels = {k: {"ms_per_launch": (t / c if c else None), "launches": c} for k, (t, c) in prof.items()}
     peak, peak_src = measured_peaks()
     col_ms = kernels["collide"]["ms_per_launch"]
-    ach = B_ALG["collide"] * local_sites / (col_ms * 1e-3) / 1e9 if col_ms else None
+    b_col = 208.0 if args.f32 else B_ALG["collide"]            # f32 storage: 19 x 4 x 2 + 56
+    b_step = B_ALG["step_binary"] - (B_ALG["collide"] - b_col)
+    ach = b_col * local_sites / (col_ms * 1e-3) / 1e9 if col_ms else None
     ps_ms = kernels.get("phi_sector", {}).get("ms_per_launch")
     ps_alg = B_ALG["grad"] + B_ALG["force_ch"]            # SURVEY 8(d) sweeps A + B, done here in one kernel
     ps_ach = ps_alg * local_sites / (ps_ms * 1e-3) / 1e9 if ps_ms else None
@@ -321,7 +325,7 @@ def run_ours(args, rank, local_rank, world):
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("collide_bytes_per_launch_256")
-            if nlocal != (256, 256, 256):
+            if nlocal != (256, 256, 256) or args.f32:
                 traffic = None
         except Exception:
             traffic = None
@@ -357,7 +361,7 @@ def run_ours(args, rank, local_rank, world):
         line = {
             "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64 arithmetic, f32 storage of the distributions" if args.f32 else "f64", "data": "synthetic",
             "config": {"workload": f"D3Q19 symmetric binary fluid (spinodal decomposition), {nlocal[0]}x{nlocal[1]}x{nlocal[2]} per GPU, "
                                    "27pt phi gradient + stress-divergence force + Cahn-Hilliard (advection order 3) "
                                    "+ MRT(M10) pull-stream-collide; periodic images read in-kernel (halo-free), "
@@ -368,6 +372,8 @@ def run_ours(args, rank, local_rank, world):
                        "math": "strict" if args.strict else "fast(fma)",
                        "x_plane_exchange": {0: "none (one GPU)", 1: "NCCL send/recv on a second stream",
                                             2: "NVLink peer stores from inside the kernels + flags"}[sim.exchange_mode()],
+                       "distribution_storage": ("f32 (float(f_p - w_p), FP64 arithmetic; LB200_KNOB_F32: error bound in "
+                                                "tests/test_gpu_parity.py::test_f32_storage_error_bound)" if args.f32 else "f64"),
                        "slab_pipeline": (lambda st: {"slabs": args.pipe, "mode": {1: "green contexts", 2: "priority streams"}.get(st[0], "off"),
                                                      "sms_phi_sector": st[1][0], "sms_collide": st[1][1]})(sim.pipe_state()),
                        "l2": "inputs (2.8 GB of lattice state per sweep) exceed the 126 MB L2; no flush needed",
@@ -376,14 +382,14 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": "collide_d3q19 (pull-stream + MRT collision)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak if ach else None),
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_site": B_ALG["collide"],
+                         "algorithmic_bytes_per_site": b_col,
                          "second_kernel": {"kernel": "phi_sector (27pt gradient + stress-divergence force + Cahn-Hilliard)",
                                            "algorithmic_bytes_per_site": ps_alg, "achieved": ps_ach,
                                            "frac": (ps_ach / peak if ps_ach else None),
                                            "note": "issue/latency-bound FP64 stencil, not HBM-bound (ncu: profiles/)"},
-                         "whole_step": {"algorithmic_bytes_per_site": B_ALG["step_binary"],
-                                        "achieved": mlups / world * 1e6 * B_ALG["step_binary"] / 1e9,
-                                        "frac": mlups / world * 1e6 * B_ALG["step_binary"] / 1e9 / peak}},
+                         "whole_step": {"algorithmic_bytes_per_site": b_step,
+                                        "achieved": mlups / world * 1e6 * b_step / 1e9,
+                                        "frac": mlups / world * 1e6 * b_step / 1e9 / peak}},
             "kernels": kernels,
             "cpu_baseline": cpu,
             "clocks": clk,
@@ -568,6 +574,8 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=128, help="edge of the CPU-baseline sample lattice")
     ap.add_argument("--strict", action="store_true", help="bit-exact arithmetic mode (no FMA contraction)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--f32", action="store_true", help="FP32 storage of the distributions inside lb200_step (LB200_KNOB_F32); "
+                    "a separate mode with a stated error bound, not the FP64 headline")
     ap.add_argument("--pipe", type=int, default=int(os.environ.get("LB200_PIPE", "0")),
                     help="slab pipeline of the single-GPU step: x-slabs (0: off; LB200_KNOB_PIPE)")
     ap.add_argument("--pipe-sms", type=int, default=int(os.environ.get("LB200_PIPE_SMS", "56")),

@@ -253,9 +253,16 @@ enum lb200_knob {
                                *    (CUDA green contexts), the collision of slab s next to the phi sector of the slabs
                                *    after it (same operations on the same data: results unchanged).  0: off.
                                *    Default LB200_PIPE, else 0 */
-  LB200_KNOB_PIPE_SMS = 5     /* SMs provisioned for the phi-sector partition (rounded up to the device's partition
+  LB200_KNOB_PIPE_SMS = 5,    /* SMs provisioned for the phi-sector partition (rounded up to the device's partition
                                *    granularity, 8 on sm_100); the collision gets the rest.  Default LB200_PIPE_SMS, else 56.
                                *    Must be set before the first pipelined step */
+  LB200_KNOB_F32 = 6          /* 1: FP32 STORAGE of the D3Q19 distributions inside lb200_step (single GPU, halo-free path,
+                               *    no planes): the two distribution arrays hold float(f_p - w_p) for the steps of one
+                               *    call, arithmetic stays FP64, LB200_F is converted on entry and back on exit.  Not
+                               *    the reference's arithmetic: each population is rounded once per step with relative
+                               *    error <= 2^-24 of its deviation from the rest weight w_p (bound and measured
+                               *    errors: DESIGN.md, tests/test_gpu_parity.py::test_f32_storage_error_bound).
+                               *    208 instead of 360 bytes per site and step.  Default LB200_F32, else 0 */
 };
 int lb200_set_knob(lb200_t * ctx, int knob, int value);
 /* slab pipeline of this context: 0 = not used yet, 1 = green contexts (sms[0] / sms[1] = SMs of the phi-sector /

@@ -107,6 +107,8 @@ struct lb200_s {
   int knob_wrap;             // lb200_set_knob
   int knob_phi_sector;
   int knob_peer;
+  int knob_f32;              // FP32 storage of the distributions inside lb200_step (0: off)
+  float * f32[2];            // float(f_p - w_p), allocated on first use
   int knob_pipe;             // slab pipeline of lb200_step: number of x-slabs (0: off)
   int knob_pipe_sms;         // SMs of the phi-sector partition (the collision gets the rest)
 
@@ -610,6 +612,7 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   c->knob_phi_sector = getenv("LB200_PHI_SECTOR") ? atoi(getenv("LB200_PHI_SECTOR")) : 1;
   c->knob_peer = getenv("LB200_PEER") ? atoi(getenv("LB200_PEER")) : 1;
   c->knob_pipe = getenv("LB200_PIPE") ? atoi(getenv("LB200_PIPE")) : 0;
+  c->knob_f32 = getenv("LB200_F32") ? atoi(getenv("LB200_F32")) : 0;
   c->knob_pipe_sms = getenv("LB200_PIPE_SMS") ? atoi(getenv("LB200_PIPE_SMS")) : 56;
   c->f_alloc[0] = c->f; c->f_alloc[1] = c->fprime;
   c->phi_alloc[0] = c->phi; c->phi_alloc[1] = c->phinew;
@@ -625,6 +628,7 @@ int lb200_set_knob(lb200_t * c, int knob, int value) {
   if (knob == LB200_KNOB_WRAP) c->knob_wrap = (value != 0);
   else if (knob == LB200_KNOB_PHI_SECTOR) c->knob_phi_sector = (value != 0);
   else if (knob == LB200_KNOB_PEER) { c->knob_peer = (value != 0); c->wrap_x_valid = 0; }
+  else if (knob == LB200_KNOB_F32) c->knob_f32 = (value != 0);
   else if (knob == LB200_KNOB_PIPE) c->knob_pipe = (value < 0) ? 0 : (value > LB200_PIPE_MAXS ? LB200_PIPE_MAXS : value);
   else if (knob == LB200_KNOB_PIPE_SMS) {
     if (c->pipe_state != 0) return fail(LB200_ESTATE, "the SM partitions of the slab pipeline are already provisioned");
@@ -672,6 +676,7 @@ int lb200_free(lb200_t * c) {
   cudaFree(c->q); cudaFree(c->qnew); cudaFree(c->qgrad); cudaFree(c->qdelsq);
   cudaFree(c->le_trip); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
   for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
+  cudaFree(c->f32[0]); cudaFree(c->f32[1]);
   cudaFree(c->flags); cudaFree(c->spin_err);
   cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->slo); cudaFree(c->shi); cudaFree(c->model_d);
   for (int i = 0; i < LB200_KCLASS_MAX; i++) {
@@ -1677,6 +1682,13 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   if (c->u_state == ZERO_PENDING && binary) materialise_zero(c, c->u, &c->u_state);
 
   const bool le = (c->le.nplane > 0);
+  // FP32 storage of the distributions for the steps of this call (LB200_KNOB_F32; single GPU, D3Q19, no planes)
+  const bool f32 = c->knob_f32 && !remote && !le && c->nvel == 19 && c->unrolled19 && c->ndist == 1 && c->map_all_fluid;
+  int f32_cur = -1;                                                      // >= 0: the state lives in c->f32[f32_cur]
+  if (f32 && c->f32[0] == nullptr) {
+    CUDA_TRY(cudaMalloc((void **) &c->f32[0], (size_t) 19*c->g.nsites*sizeof(float)));
+    CUDA_TRY(cudaMalloc((void **) &c->f32[1], (size_t) 19*c->g.nsites*sizeof(float)));
+  }
   for (int n = 0; n < nsteps; n++) {
     c->t_current += 1;                                                   // physics_control_next_step
     c->force_state = ZERO_PENDING;                                       // hydro_f_zero
@@ -1739,9 +1751,17 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	gw.peer_u_lo = binary ? c->lo.u[idx2(u_out, c->u_alloc)] : nullptr;
 	gw.peer_u_hi = binary ? c->hi.u[idx2(u_out, c->u_alloc)] : nullptr;
       }
+      if (f32 && c->prop_pending && f32_cur < 0) {
+	c->launches += c->k->f_convert(S, c->g, 1, c->f, c->f32[0]);
+	f32_cur = 0;
+      }
       ProfScope ps(c, LB200_K_COLLIDE);
       const double * force = (c->force_state == ZERO_PENDING) ? nullptr : c->force;
-      if (c->prop_pending) {
+      if (f32 && c->prop_pending) {
+	c->launches += c->k->collide_f32(S, gw, cd, c->f32[f32_cur], c->f32[1 - f32_cur], force, c->rho, u_out);
+	f32_cur = 1 - f32_cur;
+      }
+      else if (c->prop_pending) {
 	c->launches += c->k->collide(S, gw, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, force, status_ptr(c), c->rho, u_out);
 	double * t = c->f; c->f = c->fprime; c->fprime = t;
 	c->prop_pending = 0;
@@ -1776,6 +1796,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       c->f_src = c->u_src = SRC_EVENT;
     }
   }
+  if (f32_cur >= 0) c->launches += c->k->f_convert(S, c->g, 0, c->f, c->f32[f32_cur]);   // back to the FP64 array
   c->phi_halo_valid = 0;
   c->u_halo_valid = 0;
   c->wrap_x_valid = 1;

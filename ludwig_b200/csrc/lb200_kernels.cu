@@ -219,6 +219,111 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// FP32 STORAGE of the distributions (not the reference's arithmetic: an
+// opt-in mode with a stated error bound).  Inside lb200_step the two distribution arrays hold
+// d_p = float(f_p - w_p), the deviation from the rest-state weights, so the 24-bit significand is spent on
+// the O(Ma) part of f_p; every load widens to FP64 and adds w_p back, the collision itself is the FP64
+// collision above, every store rounds f_p - w_p to float once.  Rounding per population per step:
+// <= 2^-24 |f_p - w_p|.  Bytes per site: 19 x 4 x 2 + 56 = 208 instead of 360.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ constexpr double w19(int p) {
+  return (CV19[p][0]*CV19[p][0] + CV19[p][1]*CV19[p][1] + CV19[p][2]*CV19[p][2] == 0) ? (12.0/36.0)
+    : (CV19[p][0]*CV19[p][0] + CV19[p][1]*CV19[p][1] + CV19[p][2]*CV19[p][2] == 1) ? (2.0/36.0) : (1.0/36.0);
+}
+
+__global__ void __launch_bounds__(TPB_MAX)
+f_convert_kernel(size_t ns, int to_f32, double * __restrict__ f64, float * __restrict__ f32) {
+  const size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+#pragma unroll
+  for (int p = 0; p < 19; p++) {
+    if (to_f32) f32[p*ns + i] = (float) (f64[p*ns + i] - w19(p));
+    else        f64[p*ns + i] = w19(p) + (double) f32[p*ns + i];
+  }
+}
+
+int launch_f_convert(cudaStream_t st, const Lb200Geom & g, int to_f32, double * f64, float * f32) {
+  const size_t ns = (size_t) g.nsites;
+  f_convert_kernel<<<(unsigned int) ((ns + TPB_MAX - 1)/TPB_MAX), TPB_MAX, 0, st>>>(ns, to_f32, f64, f32);
+  return 1;
+}
+
+template <bool GHOST, bool HAS_FORCE>
+__global__ void __launch_bounds__(TPB_MAX, GHOST ? 3 : 4)
+collide_d3q19_f32_kernel(const Lb200Geom g, const Lb200CollideDev cp,
+			 const float * __restrict__ fsrc, float * __restrict__ fdst,
+			 const double * __restrict__ hforce,
+			 double * __restrict__ rho_out, double * __restrict__ u_out) {
+
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ic = 1 + blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+
+  const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+  const size_t ns = (size_t) g.nsites;
+
+  double f[19];
+  double mode[19];
+  double force[3];
+  double u[3];
+  double rho;
+
+  // pull, periodic images read from the interior (as collide_d3q19_kernel<PULL, ..., WRAP>)
+  const int oxm = (ic == 1)       ?  (g.nl[0] - 1)*g.xs : -g.xs;
+  const int oxp = (ic == g.nl[0]) ? -(g.nl[0] - 1)*g.xs :  g.xs;
+  const int oym = (jc == 1)       ?  (g.nl[1] - 1)*g.ys : -g.ys;
+  const int oyp = (jc == g.nl[1]) ? -(g.nl[1] - 1)*g.ys :  g.ys;
+  const int ozm = (kc == 1)       ?  (g.nl[2] - 1) : -1;
+  const int ozp = (kc == g.nl[2]) ? -(g.nl[2] - 1) :  1;
+#pragma unroll
+  for (int p = 0; p < 19; p++) {
+    const int off = (CV19[p][0] > 0 ? oxm : CV19[p][0] < 0 ? oxp : 0)
+      + (CV19[p][1] > 0 ? oym : CV19[p][1] < 0 ? oyp : 0)
+      + (CV19[p][2] > 0 ? ozm : CV19[p][2] < 0 ? ozp : 0);
+    f[p] = w19(p) + (double) fsrc[p*ns + (index + off)];
+  }
+
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) {
+    force[ia] = HAS_FORCE ? (cp.fg[ia] + hforce[ia*ns + index]) : (cp.fg[ia] + 0.0);
+  }
+
+  d3q19_f2mode<GHOST>(f, mode);
+  relax_hydro(mode, force, cp, rho, u);
+  if (GHOST) {
+#pragma unroll
+    for (int m = 10; m < 19; m++) mode[m] = mode[m] - cp.rtau_ghost[m]*(mode[m] - 0.0);
+  }
+  d3q19_mode2f<GHOST>(mode, f);
+
+#pragma unroll
+  for (int p = 0; p < 19; p++) __stcs(fdst + p*ns + index, (float) (f[p] - w19(p)));
+
+  rho_out[index] = rho;
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) u_out[ia*ns + index] = u[ia];
+}
+
+int launch_collide_f32(cudaStream_t st, const Lb200Geom & g, const Lb200CollideDev & cp, const float * fsrc,
+		       float * fdst, const double * force, double * rho, double * u) {
+  dim3 blk;
+  block_shape_n(g.nl[2], 256, blk);
+  dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
+  if (cp.ghost) {
+    if (force) collide_d3q19_f32_kernel<true, true><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, rho, u);
+    else       collide_d3q19_f32_kernel<true, false><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, rho, u);
+  }
+  else {
+    if (force) collide_d3q19_f32_kernel<false, true><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, rho, u);
+    else       collide_d3q19_f32_kernel<false, false><<<grd, blk, 0, st>>>(g, cp, fsrc, fdst, force, rho, u);
+  }
+  return 1;
+}
+
 // Generic velocity set (D3Q15, D3Q27; also D3Q19 with the model matrices instead of the coded
 // constants): reference src/collision.c:335-342, 541-551.
 template <bool PULL, bool WRAP>
@@ -2242,4 +2347,6 @@ const Lb200Kernels LB200_TABLE = {
   launch_grad7,
   launch_lc_stress,
   launch_lc_force_be,
+  launch_f_convert,
+  launch_collide_f32,
 };

@@ -158,6 +158,12 @@ struct Lb200Kernels {
   int (*lc_stress)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int nex, int ne, const double * q, double * str);
   int (*lc_force_be)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int do_force, int do_be, int accumulate,
 		     const double * q, const double * str, const double * u, double * force, double * qnew);
+  // FP32 storage of the D3Q19 distributions inside lb200_step (LB200_KNOB_F32): the arrays hold float(f_p - w_p),
+  // arithmetic stays FP64.  to_f32 != 0: f32 <- f64, else f64 <- f32 (every site of the allocation);
+  // collide_f32: pull-stream (periodic images from the interior) + collision, f32 in / f32 out
+  int (*f_convert)(cudaStream_t, const Lb200Geom &, int to_f32, double * f64, float * f32);
+  int (*collide_f32)(cudaStream_t, const Lb200Geom &, const Lb200CollideDev &, const float * fsrc, float * fdst,
+		     const double * force, double * rho, double * u);
 };
 
 extern const Lb200Kernels lb200_kernels_fast;

@@ -329,6 +329,49 @@ def test_binary_steps_slab_pipeline(nlocal, nslab, order, green, math, monkeypat
             assert close_fast(a, b), (k, rel_err(a, b))
 
 
+def f32_errors(nlocal, nrelax, math, nsteps, binary=True, u_amp=0.01):
+    """(errors, scales) of the FP32-storage mode against the FP64 oracle after nsteps steps"""
+    orc = Oracle(nlocal, nhalo=2)
+    st = seeded_state(orc, binary=binary, u_amp=u_amp)
+    fg = (1e-6, -2e-6, 5e-7)
+    cpo = orc.collide_param(nrelax, 1.0, ETA, force=fg)
+    spo = orc.symm_param(adv_order=3, **BINARY) if binary else None
+    arrays = (("f", lb.F), ("u", lb.U), ("rho", lb.RHO)) + ((("phi", lb.PHI),) if binary else ())
+    with make_sim(orc, st, math=math, have_phi=binary) as sim:
+        sim.set_knob(lb.KNOB_F32, 1)
+        cp = lb.CollideParam.make(nrelax, 1.0, ETA, force=fg)
+        sp = lb.SymmParam.make(adv_order=3, **BINARY) if binary else None
+        sim.step(cp, sp, nsteps // 2)
+        sim.step(cp, sp, nsteps - nsteps // 2)         # two calls: FP64 -> FP32 -> FP64 -> FP32 -> FP64
+        got = {k: sim.get(a) for k, a in arrays}
+    if binary:
+        orc.step(cpo, spo, 1, nsteps, st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    else:
+        orc.step(cpo, None, 0, nsteps, st["f"], None, st["u"], st["rho"], st["force"], None, None)
+    err = {k: float(np.abs(orc.interior(got[k]) - orc.interior(st[k])).max()) for k in got}
+    dev = float(np.abs(orc.interior(st["f"]) - orc.wv[:, None, None, None]).max())
+    scale = {k: float(np.abs(orc.interior(st[k])).max()) for k in got}
+    return err, dev, scale
+
+
+@pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+@pytest.mark.parametrize("nlocal,nrelax,binary,u_amp", [((24, 20, 16), lb.RELAX_M10, True, 0.01), ((16, 16, 40), lb.RELAX_TRT, True, 0.01),
+                                                        ((20, 12, 24), lb.RELAX_BGK, False, 0.05)])
+def test_f32_storage_error_bound(nlocal, nrelax, binary, u_amp, math):
+    """LB200_KNOB_F32 (FP32 storage with a stated bound).  The arrays hold float(f_p - w_p); one rounding
+    per population per step of at most 2^-24 |f_p - w_p|.  Stated bound after N steps, with D = max |f_p - w_p|:
+    |df_p| <= N 2^-23 D (worst-case linear accumulation, factor 2 of margin), |du_a| <= 10 x that (u = sum_p c_pa f_p / rho,
+    10 populations with c_pa != 0), |drho| <= 19 x that, phi (advected by u) to 1e-6 relative.  The mode is not bit-exact
+    and not within the 1e-12 FP64 tolerance: it is an opt-in storage format, off by default."""
+    nsteps = 40
+    err, dev, scale = f32_errors(nlocal, nrelax, math, nsteps, binary=binary, u_amp=u_amp)
+    bound = nsteps * 2.0 ** -23 * dev
+    assert 0.0 < err["f"] <= bound, (err, bound)          # > 0: the mode really stored floats
+    assert err["u"] <= 10 * bound and err["rho"] <= 19 * bound, (err, bound)
+    if binary:
+        assert err["phi"] <= 1e-6 * scale["phi"], (err, scale)
+
+
 @pytest.mark.parametrize("nvel", [19, 15, 27])
 @pytest.mark.parametrize("reduced", [0, 1])
 @pytest.mark.parametrize("wrap", [1, 0])
