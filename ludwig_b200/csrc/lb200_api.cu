@@ -107,6 +107,7 @@ struct lb200_s {
   int knob_wrap;             // lb200_set_knob
   int knob_phi_sector;
   int knob_peer;
+  int knob_lazy_diag;        // rho / grad / delsq stored by the last step of an lb200_step call only (LB200_LAZY_DIAG, default 1)
   int knob_f32;              // FP32 storage of the distributions inside lb200_step (0: off)
   float * f32[2];            // float(f_p - w_p), allocated on first use
   int knob_pipe;             // slab pipeline of lb200_step: number of x-slabs (0: off)
@@ -613,6 +614,7 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   c->knob_peer = getenv("LB200_PEER") ? atoi(getenv("LB200_PEER")) : 1;
   c->knob_pipe = getenv("LB200_PIPE") ? atoi(getenv("LB200_PIPE")) : 0;
   c->knob_f32 = getenv("LB200_F32") ? atoi(getenv("LB200_F32")) : 0;
+  c->knob_lazy_diag = getenv("LB200_LAZY_DIAG") ? atoi(getenv("LB200_LAZY_DIAG")) : 1;
   c->knob_pipe_sms = getenv("LB200_PIPE_SMS") ? atoi(getenv("LB200_PIPE_SMS")) : 56;
   c->f_alloc[0] = c->f; c->f_alloc[1] = c->fprime;
   c->phi_alloc[0] = c->phi; c->phi_alloc[1] = c->phinew;
@@ -1692,6 +1694,9 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   for (int n = 0; n < nsteps; n++) {
     c->t_current += 1;                                                   // physics_control_next_step
     c->force_state = ZERO_PENDING;                                       // hydro_f_zero
+    // hydro->rho, grad and delsq are read by nobody inside the step (the Lees-Edwards patches excepted, which read grad
+    // and delsq): only the last step of the call stores them
+    gw.skip_diag = (c->knob_lazy_diag && !le && n < nsteps - 1) ? 1 : 0;
     if (binary) {
       if (remote) {
 	rc = src_wait(c, S, c->phi_src, c->ev_phi, FLAG_PS_LO, c->n_ps);
@@ -1993,6 +1998,7 @@ static int step_pipe(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	if (sp != sm) CUDA_TRY(cudaStreamWaitEvent(A, c->pipe_ev_c[sp], 0));
       }
       Lb200Geom gs = gw;
+      gs.skip_diag = (c->knob_lazy_diag && n < nsteps - 1) ? 1 : 0;
       gs.xoff = x0[s]; gs.xcnt = x0[s + 1] - x0[s];
       gs.xchunk = (chunks_per_slab >= 1) ? (gs.xcnt + chunks_per_slab - 1)/chunks_per_slab : 0;
       {
@@ -2005,6 +2011,7 @@ static int step_pipe(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     for (int s = 0; s < S; s++) {
       CUDA_TRY(cudaStreamWaitEvent(B, c->pipe_ev_ps[s], 0));
       Lb200Geom gs = gw;
+      gs.skip_diag = (c->knob_lazy_diag && n < nsteps - 1) ? 1 : 0;
       gs.xoff = x0[s]; gs.xcnt = x0[s + 1] - x0[s];
       {
 	ProfScope ps(c, LB200_K_COLLIDE, B);
@@ -2280,6 +2287,7 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
       {
 	ProfScope ps(c, LB200_K_COLLIDE);
 	if (c->prop_pending) {
+	  gw.skip_diag = (c->knob_lazy_diag && n < nsteps - 1) ? 1 : 0;      // hydro->rho: the last step of the call stores it
 	  c->launches += c->k->collide(S, gw, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, u_out);
 	  double * t = c->f; c->f = c->fprime; c->fprime = t;
 	  c->prop_pending = 0;

@@ -199,7 +199,7 @@ collide_d3q19_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 #pragma unroll
   for (int p = 0; p < 19; p++) store_f<STREAM>(fdst + p*ns + index, f[p]);
 
-  rho_out[index] = rho;
+  if (!g.skip_diag) rho_out[index] = rho;
 #pragma unroll
   for (int ia = 0; ia < 3; ia++) u_out[ia*ns + index] = u[ia];
 
@@ -303,7 +303,7 @@ collide_d3q19_f32_kernel(const Lb200Geom g, const Lb200CollideDev cp,
 #pragma unroll
   for (int p = 0; p < 19; p++) __stcs(fdst + p*ns + index, (float) (f[p] - w19(p)));
 
-  rho_out[index] = rho;
+  if (!g.skip_diag) rho_out[index] = rho;
 #pragma unroll
   for (int ia = 0; ia < 3; ia++) u_out[ia*ns + index] = u[ia];
 }
@@ -1676,7 +1676,7 @@ phi_sector_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc, const double
   const bool inner = (ty >= 1 && ty <= PS_TY && tz >= 1 && tz <= PS_TZ);
   const bool out_site = inner && jc <= g.nl[1] && kc <= g.nl[2];
   const bool own_g = valid_g && ((ty >= 1 && ty <= PS_TY) || (ty == 0 && jc == 0))
-    && ((tz >= 1 && tz <= PS_TZ) || (tz == 0 && kc == 0));
+    && ((tz >= 1 && tz <= PS_TZ) || (tz == 0 && kc == 0)) && !g.skip_diag;
 
   // clamp the column used for loads so that inactive threads stay inside the allocation
   const int jl = ps_wrap(min(jc, g.nl[1] + 1), g.nl[1], g.wrap[1]);
@@ -2119,7 +2119,7 @@ phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
   k.out_site = inner && jc <= g.nl[1] && kc <= g.nl[2];
   k.face_row = (ty <= PS_TY);                      // rows that own faces towards j+1 / k+1
   k.own_g = k.valid_g && ((ty >= 1 && ty <= PS_TY) || (ty == 0 && jc == 0))
-    && ((tz >= 1 && tz <= PS_TZ) || (tz == 0 && kc == 0));
+    && ((tz >= 1 && tz <= PS_TZ) || (tz == 0 && kc == 0)) && !g.skip_diag;
 
   // column used for loads: clamped inside the allocation, through the periodic boundary if wrapping
   const int jl = ps_wrap(min(jc, g.nl[1] + 1), g.nl[1], g.wrap[1]);

@@ -27,6 +27,10 @@ struct Lb200Geom {
   // planes xoff+1 .. xoff+xcnt; xcnt == 0: all of 1 .. nl[0].  xchunk > 0: planes per phi-sector CTA (0: chosen
   // from the SM count).
   int xoff, xcnt, xchunk;
+  // 1: an intermediate step of a multi-step lb200_step call -- the arrays that only the caller reads are not
+  // stored (hydro->rho by collide_d3q19*, grad / delsq by the phi-sector kernels, which keep them in registers);
+  // the last step of the call stores them, so they hold what the reference's arrays hold when the call returns
+  int skip_diag;
 };
 
 // Lees-Edwards planes (reference src/leesedwards.c).  Field arrays of an LE context carry 2*nh*nplane buffer
