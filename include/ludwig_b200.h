@@ -116,6 +116,10 @@ typedef struct lb200_symm_param_s {
   double mobility;          /* physics mobility */
   double gradmu[3];         /* physics grad_mu (external chemical potential gradient) */
   int adv_order;            /* fd_advection_scheme_order 1-4 (src/advection.c:453-468; order 5 needs a 3-deep halo: not built) */
+  int conserve;             /* cahn_hilliard_options_conserve (phi_ch_info_t.conserve, src/phi_cahn_hilliard.h:31-36):
+                             * 0 = plain forward step; 1 = compensated (Kahan) sum per site, phi_ch_update_conserve,
+                             * src/phi_cahn_hilliard.c:1059-1094, 1181-1215 -- the compensation field lives in the context
+                             * like pch->csum.  2 (global subtraction, one all-reduce) is not built: LB200_EINVAL */
 } lb200_symm_param_t;
 
 /* fe_lc_param_t + beris_edw_param_t as the liquid-crystal kernels see them (src/blue_phase.h:52-75,
@@ -172,7 +176,7 @@ int lb200_pth_force_fluid_driver(lb200_t * ctx);
 /* phi_force_calculation, stress-divergence method, fluid only: src/phi_force.c:74-137,
  * src/phi_force_stress.c:171-284, src/phi_force_colloid.c:274-465 */
 int lb200_phi_force_calculation(lb200_t * ctx, const lb200_symm_param_t * sp);
-/* phi_cahn_hilliard (no noise; conserve = 0): src/phi_cahn_hilliard.c:213-288 */
+/* phi_cahn_hilliard (no noise; conserve = 0 or 1): src/phi_cahn_hilliard.c:213-288 */
 int lb200_phi_cahn_hilliard(lb200_t * ctx, const lb200_symm_param_t * sp);
 /* lb_collide (ndist = 1): src/collision.c:143-232, 253-593 */
 int lb200_lb_collide(lb200_t * ctx, const lb200_collide_param_t * cp);

@@ -73,6 +73,7 @@ struct lb200_s {
   double * delsq;
   double * grad_delsq;       // field_grad level 4 (grad_3d_27pt_fluid_d4), allocated on first use
   double * delsq_delsq;
+  double * csum;             // phi_ch_t.csum: per-site compensation of cahn_hilliard_options_conserve 1, allocated on first use
   double * str;              // pth->str (9 x nsites), allocated on first use of lb200_pth_stress_compute
   double * q;                // liquid crystal: Q (5 x nsites) and its update target
   double * qnew;
@@ -324,6 +325,7 @@ static void symm_dev(const lb200_t * c, const lb200_symm_param_t * sp, Lb200Symm
   d->order = sp->adv_order;
   d->wz = (c->g.nl[2] == 1) ? 0.0 : 1.0;
   d->rtau2 = 2.0/(1.0 + 2.0*sp->mobility);          // src/collision.c:1949-1950
+  d->csum = (sp->conserve == 1) ? c->csum : nullptr;   // allocated by conserve_prepare
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,6 +336,16 @@ static int alloc_d(double ** p, size_t n) {
   // cudaMemset on device memory returns before the fill has run, on the legacy stream, which is not ordered with
   // the contexts' non-blocking streams: without this wait the fill can land after the first upload / kernel
   CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
+  return 0;
+}
+
+// cahn_hilliard_options_conserve: validate, and create the compensation field on first use (pch->csum is created,
+// zero, with the phi_ch_t: src/phi_cahn_hilliard.c:146-153)
+static int conserve_prepare(lb200_t * c, const lb200_symm_param_t * sp) {
+  if (sp->conserve == 0) return 0;
+  if (sp->conserve != 1) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve %d: 0 and 1 (compensated sum) are built", sp->conserve);
+  if (c->le.nplane > 0) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve 1 with Lees-Edwards planes is outside this build");
+  if (c->csum == nullptr && alloc_d(&c->csum, (size_t) c->g.nsites) != 0) return LB200_ECUDA;
   return 0;
 }
 
@@ -678,7 +690,7 @@ int lb200_free(lb200_t * c) {
   cudaFree(c->q); cudaFree(c->qnew); cudaFree(c->qgrad); cudaFree(c->qdelsq);
   cudaFree(c->le_trip); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
   for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
-  cudaFree(c->f32[0]); cudaFree(c->f32[1]);
+  cudaFree(c->f32[0]); cudaFree(c->f32[1]); cudaFree(c->csum);
   cudaFree(c->flags); cudaFree(c->spin_err);
   cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->slo); cudaFree(c->shi); cudaFree(c->model_d);
   for (int i = 0; i < LB200_KCLASS_MAX; i++) {
@@ -1228,9 +1240,11 @@ int lb200_phi_cahn_hilliard(lb200_t * c, const lb200_symm_param_t * sp) {
   if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
   if (sp == nullptr) return fail(LB200_EINVAL, "null parameters");
   if (sp->adv_order < 1 || sp->adv_order > 4) return fail(LB200_EINVAL, "advection order %d: device kernels exist for 1-4 (reference src/advection.c:456-480)", sp->adv_order);
+  int rc = conserve_prepare(c, sp);
+  if (rc != 0) return rc;
   Lb200SymmDev sd;
   symm_dev(c, sp, &sd);
-  int rc = u_halo_async(c);               // hydro_u_halo inside phi_cahn_hilliard, src/phi_cahn_hilliard.c:229
+  rc = u_halo_async(c);                   // hydro_u_halo inside phi_cahn_hilliard, src/phi_cahn_hilliard.c:229
   if (rc != 0) return rc;
   // phinew holds phi everywhere (halo included) so that the swap keeps the reference's view
   CUDA_TRY(cudaMemcpyAsync(c->phinew, c->phi, (size_t) c->g.nsites*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -2422,7 +2436,10 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   Lb200SymmDev sd;
   int rc = collide_dev(c, cp, &cd);
   if (rc != 0) return rc;
-  if (binary) symm_dev(c, sp, &sd);
+  if (binary) {
+    if (c->ndist == 1 && (rc = conserve_prepare(c, sp)) != 0) return rc;
+    symm_dev(c, sp, &sd);
+  }
   if (nsteps <= 0) return 0;
   if (c->le.nplane > 0) {
     if (!binary || c->ndist != 1) return fail(LB200_EINVAL, "Lees-Edwards planes: lb200_step is implemented for the binary-fluid FD route (ndist = 1, free_energy symmetric)");
@@ -2447,7 +2464,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     const Lb200Geom & g = c->g;
     bool ok = wrap_enabled && g.per[0] && g.per[1] && g.per[2] && c->ndist == 1;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
-    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3;      // the one-sweep phi sector exists for orders 1-3
+    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr;   // the one-sweep phi sector: orders 1-3, plain update
     if (ok && binary && pipe_eligible(c, nsteps)) return step_pipe(c, cd, sd, nsteps);
     if (ok) return step_wrap(c, cd, binary ? &sd : nullptr, nsteps);
   }
@@ -2475,7 +2492,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
       }
       // all-fluid lattices: gradient + force + Cahn-Hilliard in one sweep (LB200_PHI_SECTOR=0 disables)
-      const bool use_ps = c->knob_phi_sector && c->map_all_fluid && sd.order <= 3;
+      const bool use_ps = c->knob_phi_sector && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr;
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
       if (!use_ps) {
 	ProfScope ps(c, LB200_K_GRAD);

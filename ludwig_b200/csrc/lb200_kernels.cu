@@ -1557,9 +1557,26 @@ force_ch_kernel(const Lb200Geom g, const Lb200SymmDev sp, const double * __restr
     fzm -= M*sp.gm[2];
     if (HAS_MAP) fzm *= mkzm*mk;
 
-    double ph = ph_c;
-    ph -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
-    phinew[s] = ph;
+    if (sp.csum != nullptr) {
+      // phi_ch_csum_kernel (src/phi_cahn_hilliard.c:1181-1215) with kahan_add_double (src/util_sum.c:30-40), the
+      // compensation carried from step to step in csum
+      double sum = ph_c, cs = sp.csum[s];
+      const double val[6] = {-fe, fw, -fy, fym, -sp.wz*fz, sp.wz*fzm};
+#pragma unroll
+      for (int n = 0; n < 6; n++) {
+	const double y = val[n] + cs;
+	const double t = sum + y;
+	cs = y - (t - sum);
+	sum = t;
+      }
+      sp.csum[s] = cs;
+      phinew[s] = sum;
+    }
+    else {
+      double ph = ph_c;
+      ph -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
+      phinew[s] = ph;
+    }
   }
 }
 

@@ -81,6 +81,7 @@ struct Lb200SymmDev {
   int order;
   double wz;            // 0 if nlocal[Z] == 1
   double rtau2;         // 2/(1 + 2 mobility): relaxation of the order-parameter flux (symmetric_lb)
+  double * csum;        // cahn_hilliard_options_conserve 1: per-site Kahan compensation (pch->csum); nullptr: plain update
 };
 
 struct Lb200ModelDev {       // generic (non-unrolled) model tables

@@ -909,7 +909,9 @@ int advection_order(int * order) { *order = advection_order_; return 0; }
 int phi_ch_create(pe_t * pe, cs_t * cs, lees_edw_t * le, phi_ch_info_t * info, phi_ch_t ** ppch) {
   phi_ch_t * pch = (phi_ch_t *) calloc(1, sizeof(phi_ch_t));
   if (pch == NULL) pe_fatal(pe, "calloc(phi_ch_t) failed\n");
-  if (info->conserve != 0) pe_fatal(pe, "cahn_hilliard_options_conserve != 0 is outside this build\n");
+  /* PHI_CONSERVE_COMPENSATED_SUM (1): the compensation field (pch->csum) lives in the device context;
+   * PHI_CONSERVE_GLOBAL_SUBTRACT (2) needs the initial global sum and an all-reduce: outside this build */
+  if (info->conserve != 0 && info->conserve != 1) pe_fatal(pe, "cahn_hilliard_options_conserve %d is outside this build\n", info->conserve);
   pch->pe = pe; pch->cs = cs; pch->le = le; pch->info = *info;
   *ppch = pch;
   return 0;
@@ -924,6 +926,7 @@ int phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t * hydro,
   if (noise != NULL || pch->info.noise) pe_fatal(pch->pe, "phi_cahn_hilliard: noise is outside this build\n");
   if (hydro == NULL) pe_fatal(pch->pe, "phi_cahn_hilliard: hydro == NULL is outside this build\n");
   symm_param_from(fe, &sp);
+  sp.conserve = pch->info.conserve;
   b200_time_sync(pch->cs);
   b200_check(pch->pe, lb200_phi_cahn_hilliard(cs_b200_context(pch->cs), &sp), "phi_cahn_hilliard");
   return 0;

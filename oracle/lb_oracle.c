@@ -806,6 +806,42 @@ void orc_phi_update(const orc_geom_t * g, const double * flux, double * phi) {
   }
 }
 
+/* ---- phi_ch_update_conserve -> phi_ch_csum_kernel: src/phi_cahn_hilliard.c:1059-1094, 1181-1215, with
+ * kahan_add_double (src/util_sum.c:30-40: y = val + cs; t = sum + y; cs = y - (t - sum); sum = t).
+ * csum is the per-site compensation carried from step to step (pch->csum, zero at creation). ---- */
+
+void orc_phi_update_conserve(const orc_geom_t * g, const double * flux, double * csum, double * phi) {
+  int nall[3];
+  const size_t ns = (size_t) orc_nsites(g);
+  orc_nall(g, nall);
+  const int ys = nall[Z];
+  const double wz = (g->nlocal[Z] == 1) ? 0.0 : 1.0;
+  const double * fw = flux + 0*ns;
+  const double * fe = flux + 1*ns;
+  const double * fy = flux + 2*ns;
+  const double * fz = flux + 3*ns;
+
+  #pragma omp parallel for collapse(2) schedule(static)
+  for (int ic = 1; ic <= g->nlocal[X]; ic++) {
+    for (int jc = 1; jc <= g->nlocal[Y]; jc++) {
+      for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
+	int index = orc_index(g, ic, jc, kc);
+	volatile double sum = phi[index];
+	volatile double cs  = csum[index];
+	const double val[6] = {-fe[index], fw[index], -fy[index], fy[index - ys], -wz*fz[index], wz*fz[index - 1]};
+	for (int n = 0; n < 6; n++) {
+	  volatile double y = val[n] + cs;
+	  volatile double t = sum + y;
+	  cs  = y - (t - sum);
+	  sum = t;
+	}
+	csum[index] = cs;
+	phi[index] = sum;
+      }
+    }
+  }
+}
+
 /* ---- hydro_f_zero / hydro_u_zero: src/hydro.c:217-263, 319-345 ---------------------------- */
 
 void orc_field_set(const orc_geom_t * g, int nf, double * data, const double * values) {
@@ -826,6 +862,7 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
   double * fprime = (double *) calloc(ns*m->nvel, sizeof(double));
   double * str = NULL;
   double * flux = NULL;
+  double * csum = NULL;     /* pch->csum: zero when the phi_ch_t is created, i.e. at the start of this run */
 
   assert(fprime);
   /* fprime's never-written x-halo planes hold stale data in the reference too; start equal */
@@ -835,6 +872,7 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
     str  = (double *) calloc(ns*9, sizeof(double));
     flux = (double *) calloc(ns*4, sizeof(double));
     assert(str && flux);
+    if (sp->conserve == 1) { csum = (double *) calloc(ns, sizeof(double)); assert(csum); }
   }
 
   for (int n = 0; n < nsteps; n++) {
@@ -849,7 +887,8 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
       orc_flux_mu(g, sp, phi, delsq, flux);
       orc_flux_mu_ext(g, sp, flux);
       orc_no_flux(g, NULL, flux);
-      orc_phi_update(g, flux, phi);
+      if (csum) orc_phi_update_conserve(g, flux, csum, phi);
+      else      orc_phi_update(g, flux, phi);
     }
     orc_field_set(g, 3, u, zero);
     orc_collide(g, m, cp, NULL, 0, f, force, rho, u);
@@ -861,6 +900,7 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
   free(fprime);
   free(str);
   free(flux);
+  free(csum);
 }
 
 /* ---- symmetric_lb: two-distribution binary fluid ------------------------------------------------

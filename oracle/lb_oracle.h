@@ -60,7 +60,8 @@ typedef struct orc_symm_param_s {
   double a, b, kappa;
   double mobility;
   double gradmu[3];
-  int adv_order;         /* 1, 2, 3 */
+  int adv_order;         /* 1 .. 4 */
+  int conserve;          /* cahn_hilliard_options_conserve: 0, or 1 = compensated sum (PHI_CONSERVE_COMPENSATED_SUM) */
 } orc_symm_param_t;
 
 int orc_nsites(const orc_geom_t * g);          /* hydro, fields, gradients, fluxes: with the LE buffer planes */
@@ -95,6 +96,7 @@ void orc_flux_mu(const orc_geom_t * g, const orc_symm_param_t * sp, const double
 void orc_flux_mu_ext(const orc_geom_t * g, const orc_symm_param_t * sp, double * flux);
 void orc_no_flux(const orc_geom_t * g, const char * status, double * flux);
 void orc_phi_update(const orc_geom_t * g, const double * flux, double * phi);
+void orc_phi_update_conserve(const orc_geom_t * g, const double * flux, double * csum, double * phi);
 
 void orc_field_set(const orc_geom_t * g, int nf, double * data, const double * values);
 

@@ -50,7 +50,7 @@ class CollideParam(C.Structure):
 
 class SymmParam(C.Structure):
     _fields_ = [("a", C.c_double), ("b", C.c_double), ("kappa", C.c_double),
-                ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int)]
+                ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int), ("conserve", C.c_int)]
 
 
 _lib = None
@@ -122,9 +122,9 @@ class Oracle:
         cp.force_global[:] = force
         return cp
 
-    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1):
+    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1, conserve=0):
         sp = SymmParam()
-        sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order = a, b, kappa, mobility, adv_order
+        sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order, sp.conserve = a, b, kappa, mobility, adv_order, conserve
         sp.gradmu[:] = gradmu
         return sp
 
@@ -187,6 +187,9 @@ class Oracle:
 
     def phi_update(self, flux, phi):
         self.lib.orc_phi_update(C.byref(self.g), _p(flux), _p(phi))
+
+    def phi_update_conserve(self, flux, csum, phi):
+        self.lib.orc_phi_update_conserve(C.byref(self.g), _p(flux), _p(csum), _p(phi))
 
     # ---- Lees-Edwards (oracle/lb_oracle_le.c) ---------------------------------------------------
     def le_plane_location(self, p):

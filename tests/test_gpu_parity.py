@@ -231,6 +231,73 @@ def test_cahn_hilliard(order, math, solid):
         assert close_fast(got, rphi)
 
 
+@pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+@pytest.mark.parametrize("solid", [0, 1])
+def test_cahn_hilliard_compensated_sum(math, solid):
+    """cahn_hilliard_options_conserve 1: phi_ch_update_conserve (src/phi_cahn_hilliard.c:1059-1094, 1181-1215) -- three
+    consecutive calls, so that the per-site compensation carried in the context (pch->csum) is exercised"""
+    orc = Oracle((6, 7, 34), nhalo=2)
+    rng = np.random.default_rng(19)
+    phi = 0.1 * (rng.random((1, orc.nsites)) - 0.5)
+    delsq = 0.1 * (rng.random((1, orc.nsites)) - 0.5)
+    u = np.zeros((3, orc.nsites))
+    orc.interior(u)[...] = 0.05 * (rng.random((3,) + orc.nlocal) - 0.5)
+    status = (rng.random(orc.nsites) < 0.1).astype(np.int8) if solid else None
+    spo = orc.symm_param(adv_order=3, conserve=1, **BINARY)
+    ru, rphi, csum = u.copy(), phi.copy(), np.zeros((1, orc.nsites))
+    orc.field_halo(ru)
+    with lb.Lb200(orc.nlocal, nhalo=2, have_phi=True, math=math) as sim:
+        sim.put(lb.PHI, phi); sim.put(lb.DELSQ, delsq); sim.put(lb.U, u)
+        if solid:
+            sim.put(lb.MAP, status.astype(np.float64))
+        for _ in range(3):
+            flux = np.zeros((4, orc.nsites))
+            orc.field_halo(rphi)
+            orc.advection(3, ru, rphi, flux); orc.flux_mu(spo, rphi, delsq, flux); orc.flux_mu_ext(spo, flux)
+            orc.no_flux(status, flux)
+            orc.phi_update_conserve(flux, csum, rphi)
+            sim.phi_halo()
+            sim.phi_cahn_hilliard(lb.SymmParam.make(adv_order=3, conserve=1, **BINARY))
+        got = sim.get(lb.PHI)
+    assert np.abs(csum).max() > 0.0
+    if math == lb.MATH_STRICT:
+        assert np.array_equal(orc.interior(got), orc.interior(rphi))
+    else:
+        assert close_fast(orc.interior(got), orc.interior(rphi))
+
+
+@pytest.mark.parametrize("path", ["api", "fused", "fused_halos"])
+@pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+def test_binary_steps_compensated_sum(path, math):
+    """whole time steps with cahn_hilliard_options_conserve 1 (the step falls back from the one-sweep phi sector to the
+    gradient + force / Cahn-Hilliard kernels): strict == oracle bit for bit, fast within tolerance; steps issued in two calls"""
+    nlocal, order = (12, 10, 14), 3
+    orc = Oracle(nlocal, nhalo=2)
+    st = seeded_state(orc)
+    cpo = orc.collide_param(lb.RELAX_M10, 1.0, ETA)
+    spo = orc.symm_param(adv_order=order, conserve=1, **BINARY)
+    with make_sim(orc, st, math=math) as sim:
+        cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA)
+        sp = lb.SymmParam.make(adv_order=order, conserve=1, **BINARY)
+        run_steps(sim, path, cp, sp, 7)
+        run_steps(sim, path, cp, sp, 5)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U))}
+    orc.step(cpo, spo, 1, 12, st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    for k in got:
+        a, b = orc.interior(got[k]), orc.interior(st[k])
+        if math == lb.MATH_STRICT:
+            assert np.array_equal(a, b), k
+        else:
+            assert close_fast(a, b), (k, rel_err(a, b))
+
+
+def test_conserve_global_subtract_is_rejected():
+    orc = Oracle((8, 8, 8), nhalo=2)
+    with make_sim(orc, seeded_state(orc)) as sim:
+        with pytest.raises(lb.Lb200Error):
+            sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), lb.SymmParam.make(adv_order=1, conserve=2, **BINARY), 1)
+
+
 # execution paths of a whole time step: the individual reference-named entry points; lb200_step halo-free
 # (default); lb200_step with the reference's three halo swaps; the same without the one-sweep phi sector
 STEP_PATHS = {"api": None, "fused": (1, 1), "fused_halos": (0, 1), "fused_halos_split": (0, 0)}

@@ -187,6 +187,33 @@ def test_binary_time_steps(order, nlocal):
         assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k
 
 
+@pytest.mark.parametrize("order,nlocal", [(1, (12, 10, 8)), (3, (16, 16, 16)), (2, (6, 12, 10)), (4, (8, 8, 8))])
+def test_binary_time_steps_compensated_sum(order, nlocal):
+    """cahn_hilliard_options_conserve 1 (PHI_CONSERVE_COMPENSATED_SUM): phi_ch_update_conserve / phi_ch_csum_kernel
+    (src/phi_cahn_hilliard.c:1059-1094, 1181-1215) with the per-site Kahan compensation carried from step to step;
+    oracle == compiled reference bit for bit, and different from the plain forward step (the option does something)."""
+    nsteps = 12
+    orc = Oracle(nlocal, nhalo=2)
+    with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=order, conserve=1, ghost_off=1, eta_shear=ETA, **BINARY) as s:
+        s.init_rest(1.0)
+        s.init_spinodal(8361235, 0.0, 0.05)
+        f, phi = s.get(rh.REF_F), s.get(rh.REF_PHI)
+        s.step(nsteps)
+        ref = {k: s.get(w) for k, w in (("f", rh.REF_F), ("phi", rh.REF_PHI), ("u", rh.REF_U))}
+    plain = None
+    for conserve in (1, 0):
+        st = dict(f=f.copy(), phi=phi.copy(), u=np.zeros((3, orc.nsites)), rho=np.zeros((1, orc.nsites)),
+                  force=np.zeros((3, orc.nsites)), grad=np.zeros((3, orc.nsites)), delsq=np.zeros((1, orc.nsites)))
+        orc.step(orc.collide_param(0, 1.0, ETA), orc.symm_param(adv_order=order, conserve=conserve, **BINARY), 1, nsteps,
+                 st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+        if conserve:
+            for k in ref:
+                assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k
+        else:
+            plain = st
+    assert not np.array_equal(orc.interior(plain["phi"]), orc.interior(ref["phi"]))
+
+
 @pytest.mark.parametrize("nrelax,reduced", [(0, 0), (1, 1), (2, 0)])
 @pytest.mark.parametrize("nvel", [19, 15, 27])
 def test_single_fluid_time_steps(nvel, nrelax, reduced):
