@@ -304,6 +304,7 @@ int fe_symm_param_set(fe_symm_t * fe, fe_symm_param_t values);
 int fe_symm_param(fe_symm_t * fe, fe_symm_param_t * values);
 int fe_symm_fed(fe_symm_t * fe, int index, double * fed);     /* host arrays */
 int fe_symm_mu(fe_symm_t * fe, int index, double * mu);
+int fe_symm_str(fe_symm_t * fe, int index, double s[3][3]);   /* src/symmetric.c:333-362, host arrays */
 
 /* ---- force from the phi sector: src/phi_force_stress.h:26-39, src/phi_force.h:24, fe_force_method.h */
 typedef enum {

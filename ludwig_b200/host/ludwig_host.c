@@ -822,6 +822,24 @@ int fe_symm_fed(fe_symm_t * fe, int index, double * fed) {
   return 0;
 }
 
+/* src/symmetric.c:333-362 (host arrays): P_ab = p0 delta_ab + kappa d_a phi d_b phi */
+int fe_symm_str(fe_symm_t * fe, int index, double s[3][3]) {
+  double phi, delsq, dphi[3], p0;
+  const double kappa = fe->param->kappa;
+  field_scalar(fe->phi, index, &phi);
+  field_grad_scalar_grad(fe->dphi, index, dphi);
+  delsq = fe->dphi->delsq[addr_rank0(fe->phi->nsites, index)];
+  p0 = 0.5*fe->param->a*phi*phi + 0.75*fe->param->b*phi*phi*phi*phi
+    - kappa*phi*delsq - 0.5*kappa*(dphi[X]*dphi[X] + dphi[Y]*dphi[Y] + dphi[Z]*dphi[Z]);
+  for (int ia = 0; ia < 3; ia++) {
+    for (int ib = 0; ib < 3; ib++) {
+      const double d_ab = (ia == ib);
+      s[ia][ib] = p0*d_ab + kappa*dphi[ia]*dphi[ib];
+    }
+  }
+  return 0;
+}
+
 /* src/symmetric.c:307-319 */
 int fe_symm_mu(fe_symm_t * fe, int index, double * mu) {
   double phi = fe->phi->data[addr_rank0(fe->phi->nsites, index)];

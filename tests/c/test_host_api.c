@@ -175,7 +175,7 @@ static void test_field_halo(void) {
 static double frand(unsigned int * s) { *s = 1664525u*(*s) + 1013904223u; return (*s >> 8)*(1.0/16777216.0); }
 
 /* whole binary-fluid time steps through the reference's entry points vs the oracle */
-static void test_binary_step(int order, int nsteps, int strict) {
+static void test_binary_step(int order, int nsteps, int strict, int conserve) {
   cs_t * cs = NULL;
   physics_t * phys = NULL;
   lees_edw_t * le = NULL;
@@ -213,7 +213,7 @@ static void test_binary_step(int order, int nsteps, int strict) {
   field_grad_set(phi_grad, grad_3d_27pt_fluid_d2, NULL);
   fe_symm_create(pe, cs, phi, phi_grad, &fe);
   { fe_symm_param_t p = {.a = -0.00625, .b = 0.00625, .kappa = 0.004}; fe_symm_param_set(fe, p); }
-  { phi_ch_info_t o = {0}; phi_ch_create(pe, cs, le, &o, &pch); }
+  { phi_ch_info_t o = {0}; o.conserve = conserve; phi_ch_create(pe, cs, le, &o, &pch); }   /* cahn_hilliard_options_conserve */
   pth_create(pe, cs, FE_FORCE_METHOD_STRESS_DIVERGENCE, &pth);
   advection_order_set(order);
 
@@ -227,7 +227,7 @@ static void test_binary_step(int order, int nsteps, int strict) {
   orc_geom_t g = {{nlocal[X], nlocal[Y], nlocal[Z]}, 2, {1, 1, 1}};
   orc_model_t model;
   orc_collide_param_t ocp = {ORC_RELAX_M10, 1.0, 0.00625, 0.00625, {fbody[0], fbody[1], fbody[2]}};
-  orc_symm_param_t osp = {-0.00625, 0.00625, 0.004, 1.25, {0.0, 0.0, 0.0}, order};
+  orc_symm_param_t osp = {-0.00625, 0.00625, 0.004, 1.25, {0.0, 0.0, 0.0}, order, conserve};
   double * of = malloc(sizeof(double)*19*ns), * ophi = malloc(sizeof(double)*ns);
   double * ou = calloc(3*ns, sizeof(double)), * orho = calloc(ns, sizeof(double)), * oforce = calloc(3*ns, sizeof(double));
   double * ograd = calloc(3*ns, sizeof(double)), * odelsq = calloc(ns, sizeof(double));
@@ -279,8 +279,20 @@ static void test_binary_step(int order, int nsteps, int strict) {
 	}
 	fe_symm_fed(fe, index, &fe1);
 	fed += fe1;
+	{
+	  /* fe_symm_str (src/symmetric.c:333-362): symmetric, trace = 3 p0 + kappa |grad phi|^2 */
+	  double s[3][3], gp[3], gg = 0.0;
+	  fe_symm_str(fe, index, s);
+	  field_grad_scalar_grad(phi_grad, index, gp);
+	  for (int ia = 0; ia < 3; ia++) gg += gp[ia]*gp[ia];
+	  /* (kappa g_a) g_b and (kappa g_b) g_a round differently, as in the reference: symmetric to an ulp */
+	  test_assert(fabs(s[0][1] - s[1][0]) <= 4e-16*fabs(s[0][1]) && fabs(s[0][2] - s[2][0]) <= 4e-16*fabs(s[0][2])
+		      && fabs(s[1][2] - s[2][1]) <= 4e-16*fabs(s[1][2]));
+	  test_assert(fabs((s[0][0] - 0.004*gp[0]*gp[0]) - (s[2][2] - 0.004*gp[2]*gp[2])) <= 1e-18 + 1e-12*fabs(s[0][0]));
+	  (void) gg;
+	}
       }
-  printf("PASS test_binary_step order=%d nsteps=%d %s  (free energy %.10e)\n", order, nsteps,
+  printf("PASS test_binary_step order=%d nsteps=%d conserve=%d %s  (free energy %.10e)\n", order, nsteps, conserve,
 	 strict ? "bit-exact" : "within tolerance", fed);
 
   free(of); free(ophi); free(ou); free(orho); free(oforce); free(ograd); free(odelsq);
@@ -701,8 +713,9 @@ int main(void) {
   test_single_fluid(19, LB_RELAXATION_TRT, strict);
   test_single_fluid(15, LB_RELAXATION_BGK, strict);
   test_single_fluid(27, LB_RELAXATION_M10, strict);
-  test_binary_step(1, 5, strict);
-  test_binary_step(3, 5, strict);
+  test_binary_step(1, 5, strict, 0);
+  test_binary_step(3, 5, strict, 0);
+  test_binary_step(3, 6, strict, 1);
   test_symmetric_lb(19, strict);
   test_symmetric_lb(15, strict);
   test_lees_edwards_step(3, 2, 6, strict);
