@@ -31,8 +31,7 @@ __host__ inline void lc_block_shape(int nz, dim3 & blk);
 
 // site index of (ic + dx, jc + dy, kc + dz), through the periodic boundary where the geometry says "wrap"
 __device__ __forceinline__ int lc_nbr(const Lb200Geom & g, int ic, int jc, int kc) {
-  if (g.wrap[0]) { if (ic < 1) ic += g.nl[0]; else if (ic > g.nl[0]) ic -= g.nl[0]; }
-  return le_index(g, ic, le_wy(g, jc), le_wz(g, kc));
+  return le_index(g, lb200_wrap1(ic, g.nl[0], g.wrap[0]), le_wy(g, jc), le_wz(g, kc));
 }
 
 // expand the five stored components (XX, XY, XZ, YY, YZ) of a traceless symmetric tensor

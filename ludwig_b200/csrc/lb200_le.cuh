@@ -30,14 +30,14 @@ __device__ __forceinline__ int le_x(const Lb200LeDev & le, const Lb200Geom & g, 
 }
 
 // Halo-free steps (Lb200Geom::wrap): the periodic images in y / z are read from the interior sites they mirror
-__device__ __forceinline__ int le_wy(const Lb200Geom & g, int j) {
-  if (g.wrap[1]) { if (j < 1) j += g.nl[1]; else if (j > g.nl[1]) j -= g.nl[1]; }
-  return j;
+// (select arithmetic, no branches: whether ptxas turns `if / else if` into SEL or into divergent branches depends on
+// unrelated details of the kernel -- the liquid-crystal sweeps lost 5-11 % when it chose branches)
+__device__ __forceinline__ int lb200_wrap1(int i, int n, int wrap) {
+  const int w = wrap ? n : 0;
+  return i + ((i < 1) ? w : 0) - ((i > n) ? w : 0);
 }
-__device__ __forceinline__ int le_wz(const Lb200Geom & g, int k) {
-  if (g.wrap[2]) { if (k < 1) k += g.nl[2]; else if (k > g.nl[2]) k -= g.nl[2]; }
-  return k;
-}
+__device__ __forceinline__ int le_wy(const Lb200Geom & g, int j) { return lb200_wrap1(j, g.nl[1], g.wrap[1]); }
+__device__ __forceinline__ int le_wz(const Lb200Geom & g, int k) { return lb200_wrap1(k, g.nl[2], g.wrap[2]); }
 
 __device__ __forceinline__ int le_index(const Lb200Geom & g, int ic, int jc, int kc) {
   return ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
