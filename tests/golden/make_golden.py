@@ -24,6 +24,8 @@ CASES = {
     "binary_o1": ("binary", 19, (8, 6, 7), 5, dict(adv_order=1, nrelax=0, fbody=(0.0, 0.0, 0.0), gradmu=(0, 0, 0))),
     "binary_o3_force": ("binary", 19, (6, 8, 9), 5, dict(adv_order=3, nrelax=0, fbody=(1e-6, 2e-6, 3e-6), gradmu=(1e-5, 0, -1e-5))),
     "binary_o2_trt": ("binary", 19, (5, 5, 6), 4, dict(adv_order=2, nrelax=2, fbody=(0.0, 0.0, 0.0), gradmu=(0, 0, 0))),
+    # advection order 4 (advection_le_4th) and cahn_hilliard_options_conserve 1 (phi_ch_update_conserve)
+    "binary_o4_conserve": ("binary", 19, (7, 6, 8), 6, dict(adv_order=4, conserve=1, nrelax=0, fbody=(1e-6, 0.0, -1e-6), gradmu=(0, 0, 0))),
     "single_d3q19_m10": ("single", 19, (6, 5, 7), 6, dict(nrelax=0, reduced=0, fbody=(1e-6, 2e-6, 3e-6))),
     "single_d3q19_bgk_reduced": ("single", 19, (6, 5, 7), 6, dict(nrelax=1, reduced=1, fbody=(0.0, 0.0, 0.0))),
     "single_d3q15_trt": ("single", 15, (5, 6, 4), 6, dict(nrelax=2, reduced=0, fbody=(1e-6, 0.0, 0.0))),
@@ -36,13 +38,16 @@ CASES = {
 
 
 def main():
+    only = sys.argv[1:]            # python make_golden.py [case ...]: regenerate the named cases only
     for name, (kind, nvel, nlocal, nsteps, o) in CASES.items():
+        if only and name not in only:
+            continue
         rng = np.random.default_rng(zlib.crc32(name.encode()))
         out = dict(kind=kind, nvel=nvel, nlocal=np.array(nlocal), nsteps=nsteps, nrelax=o["nrelax"],
                    fbody=np.array(o["fbody"], dtype=float))
         if kind == "binary":
             nhalo = 2
-            with rh.RefSim(nlocal, nhalo=nhalo, have_phi=1, adv_order=o["adv_order"], nrelax=o["nrelax"],
+            with rh.RefSim(nlocal, nhalo=nhalo, have_phi=1, adv_order=o["adv_order"], conserve=o.get("conserve", 0), nrelax=o["nrelax"],
                            eta_shear=0.00625, fbody=o["fbody"], gradmu=o["gradmu"], **BINARY) as s:
                 s.init_rest(1.0)
                 s.init_spinodal(8361235, 0.0, 0.1)
@@ -51,7 +56,7 @@ def main():
                 for k, w in (("f", rh.REF_F), ("phi", rh.REF_PHI), ("u", rh.REF_U), ("rho", rh.REF_RHO),
                              ("force", rh.REF_FORCE), ("grad", rh.REF_GRAD), ("delsq", rh.REF_DELSQ)):
                     out[k] = s.get(w)
-            out.update(nhalo=nhalo, adv_order=o["adv_order"], gradmu=np.array(o["gradmu"], dtype=float),
+            out.update(nhalo=nhalo, adv_order=o["adv_order"], conserve=o.get("conserve", 0), gradmu=np.array(o["gradmu"], dtype=float),
                        eta=0.00625, **BINARY)
         elif kind == "symmlb":
             nhalo = 1

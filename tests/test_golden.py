@@ -25,7 +25,8 @@ def run_oracle(g):
     if g["kind"] == "binary":
         st.update(phi=g["phi0"].copy(), grad=z(3), delsq=z(1))
         cp = orc.collide_param(g["nrelax"], 1.0, g["eta"], force=tuple(g["fbody"]))
-        sp = orc.symm_param(g["a"], g["b"], g["kappa"], g["mobility"], gradmu=tuple(g["gradmu"]), adv_order=g["adv_order"])
+        sp = orc.symm_param(g["a"], g["b"], g["kappa"], g["mobility"], gradmu=tuple(g["gradmu"]), adv_order=g["adv_order"],
+                            conserve=int(g.get("conserve", 0)))
         orc.step(cp, sp, 1, g["nsteps"], st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
     else:
         cp = orc.collide_param(g["nrelax"], 1.0, g["eta"], eta_bulk=g["eta_bulk"], force=tuple(g["fbody"]))
@@ -74,7 +75,7 @@ def test_cuda_reproduces_reference_golden(name, strict):
         if binary:
             sim.put(lb.PHI, g["phi0"])
             sp = lb.SymmParam.make(g["a"], g["b"], g["kappa"], g["mobility"], gradmu=tuple(g["gradmu"]),
-                                   adv_order=g["adv_order"])
+                                   adv_order=g["adv_order"], conserve=int(g.get("conserve", 0)))
         sim.step(cp, sp, g["nsteps"])
         keys = [("f", lb.F), ("u", lb.U), ("rho", lb.RHO)]
         if binary:
