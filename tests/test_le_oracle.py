@@ -117,8 +117,8 @@ def test_le_steps_vs_reference(n, nplanes, order):
 
 
 # ---- printed statistics of the reference's own regression logs after 10 steps ---------------------------------
-# tests/regression/d3q19-short/serial-le3d-st5/6/7.{inp,log}: 32^3, 2 planes, LE_plane_vel 0.05, LE_init_profile 1,
-# viscosity 0.1, A = -B = -0.0625, K = 0.04, mobility 0.15, 27pt gradient, advection order 1/2/3, seed 7361237
+# tests/regression/d3q19-short/serial-le3d-st5/6/7/8.{inp,log}: 32^3, 2 planes, LE_plane_vel 0.05, LE_init_profile 1,
+# viscosity 0.1, A = -B = -0.0625, K = 0.04, mobility 0.15, 27pt gradient, advection order 1/2/3/4, seed 7361237
 
 LOGS = {
     1: dict(var=2.7954511e-04, lo=-4.3686720e-02, hi=4.4289983e-02, fed=-6.9311730666e-06,
@@ -130,6 +130,10 @@ LOGS = {
     3: dict(var=3.0000123e-04, lo=-4.4451160e-02, hi=4.6772004e-02, fed=-7.4768699749e-06,
             rlo=0.99989939996, rhi=1.00007990713, momy=6.7440881e-04,
             umin=(-3.9757187e-05, -2.3465114e-02, -3.2556760e-05), umax=(3.5246929e-05, 2.3466305e-02, 3.5961973e-05)),
+    # serial-le3d-st8: advection order 4 (advection_le_4th, a host loop in the reference)
+    4: dict(var=3.3084154e-04, lo=-4.5460883e-02, hi=4.9576356e-02, fed=-8.3701208477e-06,
+            rlo=0.99989987111, rhi=1.00008439510, momy=8.0454156e-04,
+            umin=(-4.5098273e-05, -2.3468862e-02, -3.3640007e-05), umax=(3.9705279e-05, 2.3468484e-02, 3.6508777e-05)),
 }
 
 
@@ -137,7 +141,7 @@ def approx(v, digits):
     return pytest.approx(v, rel=0.5 * 10.0 ** (1 - digits), abs=1e-30)
 
 
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_serial_le3d_logs(order):
     from ludwig_b200.initial import spinodal_phi
     n = (32, 32, 32)
