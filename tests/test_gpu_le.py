@@ -159,13 +159,17 @@ def test_le_steps_fast_tolerance(n, nplanes, order, wrap):
         assert close_fast(orc.interior(got[k]), orc.interior(want[k])), (k, np.abs(orc.interior(got[k]) - orc.interior(want[k])).max())
 
 
-def test_serial_le3d_st7_log_on_gpu():
-    """the reference's own regression answer (tests/regression/d3q19-short/serial-le3d-st7.log, advection order 3)
-    from the CUDA path in fast mode: printed statistics to the printed digits"""
-    orc, sp, got, want = _run_steps((32, 32, 32), 2, 3, lb.MATH_FAST, 10, seed=7361237)
+@pytest.mark.parametrize("order,var,lo,hi,fed,uylo,uyhi", [
+    (3, 3.0000123e-04, -4.4451160e-02, 4.6772004e-02, -7.4768699749e-06, -2.3465114e-02, 2.3466305e-02),      # serial-le3d-st7.log
+    (4, 3.3084154e-04, -4.5460883e-02, 4.9576356e-02, -8.3701208477e-06, -2.3468862e-02, 2.3468484e-02)])     # serial-le3d-st8.log
+def test_serial_le3d_logs_on_gpu(order, var, lo, hi, fed, uylo, uyhi):
+    """the reference's own regression answers (tests/regression/d3q19-short/serial-le3d-st7.log, advection order 3, and
+    serial-le3d-st8.log, order 4 -- a host loop in the reference) from the CUDA path in fast mode: printed statistics to
+    the printed digits"""
+    orc, sp, got, want = _run_steps((32, 32, 32), 2, order, lb.MATH_FAST, 10, seed=7361237)
     approx = lambda v, d: pytest.approx(v, rel=0.5 * 10.0 ** (1 - d), abs=1e-30)
     s = stats_scalar(orc, got["phi"])
-    assert s[2] == approx(3.0000123e-04, 8) and s[3] == approx(-4.4451160e-02, 8) and s[4] == approx(4.6772004e-02, 8)
-    assert fed_density(orc, sp, got["phi"], got["grad"]) == approx(-7.4768699749e-06, 10)
+    assert s[2] == approx(var, 8) and s[3] == approx(lo, 8) and s[4] == approx(hi, 8)
+    assert fed_density(orc, sp, got["phi"], got["grad"]) == approx(fed, 10)
     ui = orc.interior(got["u"])
-    assert ui[1].min() == approx(-2.3465114e-02, 8) and ui[1].max() == approx(2.3466305e-02, 8)
+    assert ui[1].min() == approx(uylo, 8) and ui[1].max() == approx(uyhi, 8)
