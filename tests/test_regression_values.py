@@ -81,6 +81,35 @@ def test_serial_dist_3du_log():
     assert np.allclose(orc.interior(u)[0], 0.002, rtol=1e-13) and np.allclose(orc.interior(u)[2], 0.004, rtol=1e-13)
 
 
+def test_serial_dist_1dp_log():
+    """tests/regression/d3q19-short/serial-dist-1dp.{inp,log}: single fluid, 32^3, viscosity 0.1, reduced distribution
+    halo (lb_halo_openmp_reduced), 1-d Poiseuille profile u_x = umax x (L - x) 4 / L^2 at rho = 1 set through
+    lb_1st_moment_equilib_set (src/distribution_rt.c:516-563).  Log lines 62-67 (t = 0) and 71-82 (t = 10)."""
+    n = (32, 32, 32)
+    orc = Oracle(n, nhalo=1)
+    L, umax = 32.0, 0.001
+    ux = np.zeros(orc.nall)
+    for ic in range(1, 33):
+        x = 1.0 * (0 + ic) - 0.5
+        ux[ic, :, :] = umax * x * (L - x) * 4.0 / (L * L)
+    f = orc.equilibrium(1.0, (ux.ravel(), 0.0, 0.0))
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force = z(3), z(1), z(3)
+
+    def momentum():
+        fi = orc.interior(f).astype(np.longdouble)
+        return [float((fi * orc.cv[:, a, None, None, None]).sum()) for a in range(3)]
+
+    assert momentum()[0] == approx(2.1856000e+01, 8)
+    orc.step(orc.collide_param(0, 1.0, 0.1), None, 0, 10, f, None, u, rho, force, None, None, halo_reduced=1)
+    assert momentum()[0] == approx(2.1856000e+01, 8) and abs(momentum()[1]) < 1e-10
+    r = stats_scalar(orc, f.sum(axis=0, keepdims=True))
+    assert r[0] == approx(32768.00, 8) and r[2] == approx(1.9282755e-07, 8)
+    assert r[3] == approx(0.99932343093, 11) and r[4] == approx(1.00067708627, 11)
+    ui = orc.interior(u)
+    assert ui[0].min() == approx(5.0228587e-04, 8) and ui[0].max() == approx(8.7868636e-04, 8)
+
+
 def test_serial_spin_lb1_log():
     """tests/regression/d3q19-short/serial-spin-lb1.{inp,log}: `free_energy symmetric_lb` (two distributions,
     lb_collision_binary), 64^3, A = -B = -0.00625, K = 0.004, mobility 3.75, eta = 0.00625, nhalo = 1.
