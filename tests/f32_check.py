@@ -1,10 +1,11 @@
-"""Measured errors of the FP32-storage mode (LB200_KNOB_F32) against the FP64 oracle: python tools/f32_check.py"""
+"""Measured errors of the FP32-storage mode (LB200_KNOB_F32) against the FP64 oracle (test infrastructure, like the
+oracle itself): python tests/f32_check.py"""
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import ludwig_b200 as lb                      # noqa: E402
 from test_gpu_parity import f32_errors        # noqa: E402
 
