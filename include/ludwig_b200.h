@@ -260,13 +260,18 @@ enum lb200_knob {
   LB200_KNOB_PIPE_SMS = 5,    /* SMs provisioned for the phi-sector partition (rounded up to the device's partition
                                *    granularity, 8 on sm_100); the collision gets the rest.  Default LB200_PIPE_SMS, else 56.
                                *    Must be set before the first pipelined step */
-  LB200_KNOB_F32 = 6          /* 1: FP32 STORAGE of the D3Q19 distributions inside lb200_step (single GPU, halo-free path,
+  LB200_KNOB_F32 = 6,         /* 1: FP32 STORAGE of the D3Q19 distributions inside lb200_step (single GPU, halo-free path,
                                *    no planes): the two distribution arrays hold float(f_p - w_p) for the steps of one
                                *    call, arithmetic stays FP64, LB200_F is converted on entry and back on exit.  Not
                                *    the reference's arithmetic: each population is rounded once per step with relative
                                *    error <= 2^-24 of its deviation from the rest weight w_p (bound and measured
                                *    errors: DESIGN.md, tests/test_gpu_parity.py::test_f32_storage_error_bound).
                                *    208 instead of 360 bytes per site and step.  Default LB200_F32, else 0 */
+  LB200_KNOB_GRAD_7PT = 7     /* NOT an execution knob: selects the finite-difference scheme of the scalar order parameter,
+                               *    `fd_gradient_calculation`: 0 = 3d_27pt_fluid (default), 1 = 3d_7pt_fluid
+                               *    (grad_3d_7pt_fluid_d2, src/gradient_3d_7pt_fluid.c:76-99, 231-300) for
+                               *    lb200_phi_grad_compute and lb200_step (which then runs the gradient and the
+                               *    force / Cahn-Hilliard kernels separately; no Lees-Edwards planes).  Default LB200_GRAD_7PT, else 0 */
 };
 int lb200_set_knob(lb200_t * ctx, int knob, int value);
 /* slab pipeline of this context: 0 = not used yet, 1 = green contexts (sms[0] / sms[1] = SMs of the phi-sector /

@@ -108,6 +108,7 @@ struct lb200_s {
   int knob_wrap;             // lb200_set_knob
   int knob_phi_sector;
   int knob_peer;
+  int knob_grad7;            // fd_gradient_calculation 3d_7pt_fluid for the scalar order parameter (0: 3d_27pt_fluid)
   int knob_lazy_diag;        // rho / grad / delsq stored by the last step of an lb200_step call only (LB200_LAZY_DIAG, default 1)
   int knob_f32;              // FP32 storage of the distributions inside lb200_step (0: off)
   float * f32[2];            // float(f_p - w_p), allocated on first use
@@ -626,6 +627,7 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   c->knob_peer = getenv("LB200_PEER") ? atoi(getenv("LB200_PEER")) : 1;
   c->knob_pipe = getenv("LB200_PIPE") ? atoi(getenv("LB200_PIPE")) : 0;
   c->knob_f32 = getenv("LB200_F32") ? atoi(getenv("LB200_F32")) : 0;
+  c->knob_grad7 = getenv("LB200_GRAD_7PT") ? atoi(getenv("LB200_GRAD_7PT")) : 0;
   c->knob_lazy_diag = getenv("LB200_LAZY_DIAG") ? atoi(getenv("LB200_LAZY_DIAG")) : 1;
   c->knob_pipe_sms = getenv("LB200_PIPE_SMS") ? atoi(getenv("LB200_PIPE_SMS")) : 56;
   c->f_alloc[0] = c->f; c->f_alloc[1] = c->fprime;
@@ -643,6 +645,11 @@ int lb200_set_knob(lb200_t * c, int knob, int value) {
   else if (knob == LB200_KNOB_PHI_SECTOR) c->knob_phi_sector = (value != 0);
   else if (knob == LB200_KNOB_PEER) { c->knob_peer = (value != 0); c->wrap_x_valid = 0; }
   else if (knob == LB200_KNOB_F32) c->knob_f32 = (value != 0);
+  else if (knob == LB200_KNOB_GRAD_7PT) {
+    if (value != 0 && c->le.nplane > 0) return fail(LB200_EINVAL, "3d_7pt_fluid with Lees-Edwards planes is outside this build");
+    if (value != 0 && c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+    c->knob_grad7 = (value != 0);
+  }
   else if (knob == LB200_KNOB_PIPE) c->knob_pipe = (value < 0) ? 0 : (value > LB200_PIPE_MAXS ? LB200_PIPE_MAXS : value);
   else if (knob == LB200_KNOB_PIPE_SMS) {
     if (c->pipe_state != 0) return fail(LB200_ESTATE, "the SM partitions of the slab pipeline are already provisioned");
@@ -1104,7 +1111,8 @@ int lb200_phi_grad_compute(lb200_t * c) {
   le_field_async(c, c->phi);              // field_grad_compute -> field_leesedwards, src/field_grad.c:324
   {
     ProfScope ps(c, LB200_K_GRAD);
-    c->launches += c->k->grad27(c->stream, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);
+    if (c->knob_grad7) c->launches += c->k->grad7(c->stream, c->g, c->g.nh - 1, 1, c->phi, c->grad, c->delsq);   // grad_3d_7pt_fluid_d2
+    else               c->launches += c->k->grad27(c->stream, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);
   }
   le_grad_async(c);
   CTX_LEAVE_SYNC(c);
@@ -2441,6 +2449,8 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     symm_dev(c, sp, &sd);
   }
   if (nsteps <= 0) return 0;
+  if (binary && c->knob_grad7 && (c->ndist != 1 || c->le.nplane > 0))
+    return fail(LB200_EINVAL, "fd_gradient_calculation 3d_7pt_fluid: built for the finite-difference binary fluid without planes");
   if (c->le.nplane > 0) {
     if (!binary || c->ndist != 1) return fail(LB200_EINVAL, "Lees-Edwards planes: lb200_step is implemented for the binary-fluid FD route (ndist = 1, free_energy symmetric)");
     // fast mode on a fully periodic all-fluid lattice: the halo-free step with plane patches, provided every plane
@@ -2464,7 +2474,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     const Lb200Geom & g = c->g;
     bool ok = wrap_enabled && g.per[0] && g.per[1] && g.per[2] && c->ndist == 1;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
-    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr;   // the one-sweep phi sector: orders 1-3, plain update
+    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr && !c->knob_grad7;   // the one-sweep phi sector: orders 1-3, plain update
     if (ok && binary && pipe_eligible(c, nsteps)) return step_pipe(c, cd, sd, nsteps);
     if (ok) return step_wrap(c, cd, binary ? &sd : nullptr, nsteps);
   }
@@ -2492,11 +2502,12 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
       }
       // all-fluid lattices: gradient + force + Cahn-Hilliard in one sweep (LB200_PHI_SECTOR=0 disables)
-      const bool use_ps = c->knob_phi_sector && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr;
+      const bool use_ps = c->knob_phi_sector && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr && !c->knob_grad7;
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
       if (!use_ps) {
 	ProfScope ps(c, LB200_K_GRAD);
-	c->launches += c->k->grad27(S, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);       // field_grad_compute
+	if (c->knob_grad7) c->launches += c->k->grad7(S, c->g, c->g.nh - 1, 1, c->phi, c->grad, c->delsq);   // grad_3d_7pt_fluid_d2
+	else               c->launches += c->k->grad27(S, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);    // field_grad_compute
       }
       if (!c->u_halo_valid) {                                            // hydro_u_halo
 	if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);

@@ -639,6 +639,7 @@ int field_grad_compute(field_grad_t * obj) {
 }
 
 int grad_3d_27pt_fluid_d2(field_grad_t * fg) {
+  b200_check(fg->pe, lb200_set_knob(cs_b200_context(fg->field->cs), LB200_KNOB_GRAD_7PT, 0), "grad_3d_27pt_fluid_d2");
   b200_time_sync(fg->field->cs);       /* with planes: field_leesedwards + d2 + grad_3d_27pt_fluid_le on the device */
   b200_check(fg->pe, lb200_phi_grad_compute(cs_b200_context(fg->field->cs)), "grad_3d_27pt_fluid_d2");
   return 0;
@@ -653,7 +654,15 @@ int grad_3d_27pt_fluid_d4(field_grad_t * fg) {
 
 /* src/gradient_3d_7pt_fluid.c:76-99 */
 int grad_3d_7pt_fluid_d2(field_grad_t * fg) {
-  if (fg->field->b200_array != LB200_Q) pe_fatal(fg->pe, "grad_3d_7pt_fluid_d2: only the Q tensor field is device backed\n");
+  if (fg->field->b200_array == LB200_PHI) {
+    /* the scalar order parameter with fd_gradient_calculation 3d_7pt_fluid: field_grad_set(obj, grad_3d_7pt_fluid_d2, ...) */
+    lb200_t * ctx = cs_b200_context(fg->field->cs);
+    b200_time_sync(fg->field->cs);
+    b200_check(fg->pe, lb200_set_knob(ctx, LB200_KNOB_GRAD_7PT, 1), "grad_3d_7pt_fluid_d2");
+    b200_check(fg->pe, lb200_phi_grad_compute(ctx), "grad_3d_7pt_fluid_d2");
+    return 0;
+  }
+  if (fg->field->b200_array != LB200_Q) pe_fatal(fg->pe, "grad_3d_7pt_fluid_d2: only phi and the Q tensor field are device backed\n");
   b200_check(fg->pe, lb200_q_grad_compute(cs_b200_context(fg->field->cs)), "grad_3d_7pt_fluid_d2");
   return 0;
 }

@@ -879,7 +879,8 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
     orc_field_set(g, 3, force, zero);
     if (binary) {
       orc_field_halo(g, 1, phi);
-      orc_grad_27pt(g, phi, grad, delsq);
+      if (sp->grad_7pt) orc_grad_7pt(g, 1, phi, grad, delsq);          /* grad_3d_7pt_fluid_d2 */
+      else              orc_grad_27pt(g, phi, grad, delsq);
       orc_stress_symm(g, sp, phi, grad, delsq, str);
       orc_force_divergence(g, str, force);
       orc_field_halo(g, 3, u);

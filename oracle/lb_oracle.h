@@ -62,6 +62,7 @@ typedef struct orc_symm_param_s {
   double gradmu[3];
   int adv_order;         /* 1 .. 4 */
   int conserve;          /* cahn_hilliard_options_conserve: 0, or 1 = compensated sum (PHI_CONSERVE_COMPENSATED_SUM) */
+  int grad_7pt;          /* fd_gradient_calculation: 0 = 3d_27pt_fluid, 1 = 3d_7pt_fluid (whole steps, orc_step) */
 } orc_symm_param_t;
 
 int orc_nsites(const orc_geom_t * g);          /* hydro, fields, gradients, fluxes: with the LE buffer planes */

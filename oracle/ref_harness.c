@@ -82,6 +82,7 @@ typedef struct ref_cfg_s {
   double lc_Gamma;     /* rotational diffusion constant (beris_edw_param_t.gamma) */
   double lc_epsilon;   /* dielectric anisotropy as stored in fe_lc_param_t (includes the 1/12pi) */
   double lc_e0[3];     /* external electric field */
+  int grad_7pt;        /* fd_gradient_calculation 3d_7pt_fluid for the scalar order parameter (default 3d_27pt_fluid) */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -179,7 +180,8 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     fe_symm_param_t p = {0};
     field_create(s->pe, s->cs, s->le, "phi", &opts, &s->phi);
     field_grad_create(s->pe, s->phi, cfg->grad_level == 4 ? 4 : 2, &s->phi_grad);
-    field_grad_set(s->phi_grad, grad_3d_27pt_fluid_d2, grad_3d_27pt_fluid_d4);
+    if (cfg->grad_7pt) field_grad_set(s->phi_grad, grad_3d_7pt_fluid_d2, grad_3d_7pt_fluid_d4);
+    else               field_grad_set(s->phi_grad, grad_3d_27pt_fluid_d2, grad_3d_27pt_fluid_d4);
     fe_symm_create(s->pe, s->cs, s->phi, s->phi_grad, &s->fe);
     p.a = cfg->a; p.b = cfg->b; p.kappa = cfg->kappa;
     fe_symm_param_set(s->fe, p);

@@ -50,7 +50,8 @@ class CollideParam(C.Structure):
 
 class SymmParam(C.Structure):
     _fields_ = [("a", C.c_double), ("b", C.c_double), ("kappa", C.c_double),
-                ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int), ("conserve", C.c_int)]
+                ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int), ("conserve", C.c_int),
+                ("grad_7pt", C.c_int)]
 
 
 _lib = None
@@ -122,9 +123,10 @@ class Oracle:
         cp.force_global[:] = force
         return cp
 
-    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1, conserve=0):
+    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1, conserve=0, grad_7pt=0):
         sp = SymmParam()
         sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order, sp.conserve = a, b, kappa, mobility, adv_order, conserve
+        sp.grad_7pt = grad_7pt
         sp.gradmu[:] = gradmu
         return sp
 

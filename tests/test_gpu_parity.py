@@ -291,6 +291,48 @@ def test_binary_steps_compensated_sum(path, math):
             assert close_fast(a, b), (k, rel_err(a, b))
 
 
+@pytest.mark.parametrize("nlocal", [(8, 6, 10), (5, 7, 33)])
+def test_gradient_7pt_bit_exact(nlocal):
+    """LB200_KNOB_GRAD_7PT: grad_3d_7pt_fluid_d2 for the scalar order parameter (src/gradient_3d_7pt_fluid.c:76-99, 231-300)"""
+    orc = Oracle(nlocal, nhalo=2)
+    rng = np.random.default_rng(23)
+    phi = rng.random((1, orc.nsites))
+    grad, delsq = np.zeros((3, orc.nsites)), np.zeros((1, orc.nsites))
+    orc.grad_7pt(phi, grad, delsq)
+    with lb.Lb200(nlocal, nhalo=2, have_phi=True, math=lb.MATH_STRICT) as sim:
+        sim.set_knob(lb.KNOB_GRAD_7PT, 1)
+        sim.put(lb.PHI, phi)
+        sim.phi_grad_compute()
+        g, d = sim.get(lb.GRAD), sim.get(lb.DELSQ)
+    h = 1                                                  # region [0, N+1]^3: all but the outermost halo shell
+    v = lambda a: a.reshape((a.shape[0],) + orc.nall)[:, h:-h, h:-h, h:-h]
+    assert np.array_equal(v(g), v(grad)) and np.array_equal(v(d), v(delsq))
+
+
+@pytest.mark.parametrize("path", ["api", "fused", "fused_halos_split"])
+@pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+@pytest.mark.parametrize("nvel,nlocal,order", [(19, (12, 10, 14), 3), (27, (8, 8, 8), 2)])
+def test_binary_steps_7pt_gradient(path, math, nvel, nlocal, order):
+    """whole binary-fluid steps with fd_gradient_calculation 3d_7pt_fluid (the configuration of the reference's
+    d3q27/serial-spin-n01 and serial-le3d-st1..4 inputs): strict == oracle bit for bit, fast within tolerance"""
+    orc = Oracle(nlocal, nhalo=2, nvel=nvel)
+    st = seeded_state(orc)
+    cpo = orc.collide_param(lb.RELAX_M10, 1.0, ETA)
+    spo = orc.symm_param(adv_order=order, grad_7pt=1, **BINARY)
+    with make_sim(orc, st, math=math) as sim:
+        sim.set_knob(lb.KNOB_GRAD_7PT, 1)
+        run_steps(sim, path, lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), lb.SymmParam.make(adv_order=order, **BINARY), 10)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("force", lb.FORCE),
+                                          ("grad", lb.GRAD), ("delsq", lb.DELSQ))}
+    orc.step(cpo, spo, 1, 10, st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    for k in got:
+        a, b = orc.interior(got[k]), orc.interior(st[k])
+        if math == lb.MATH_STRICT:
+            assert np.array_equal(a, b), k
+        else:
+            assert close_fast(a, b), (k, rel_err(a, b))
+
+
 def test_conserve_global_subtract_is_rejected():
     orc = Oracle((8, 8, 8), nhalo=2)
     with make_sim(orc, seeded_state(orc)) as sim:

@@ -377,3 +377,26 @@ def test_pth_stress_then_force_driver():
     assert np.array_equal(v(strs), v(ref_str))
     orc.force_divergence(strs, force)
     assert np.array_equal(orc.interior(force), orc.interior(ref_force))
+
+
+@pytest.mark.parametrize("order,nlocal,nvel", [(1, (12, 10, 8), 19), (3, (10, 12, 14), 19), (2, (8, 8, 8), 27)])
+def test_binary_time_steps_7pt_gradient(order, nlocal, nvel):
+    """fd_gradient_calculation 3d_7pt_fluid for the scalar order parameter (grad_3d_7pt_fluid_d2,
+    src/gradient_3d_7pt_fluid.c:76-99, 231-300) in whole binary-fluid steps: oracle == compiled reference bit for bit"""
+    if not rh.available(nvel=nvel):
+        pytest.skip("reference build for this velocity set missing")
+    nsteps = 8
+    orc = Oracle(nlocal, nhalo=2, nvel=nvel)
+    with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=order, grad_7pt=1, eta_shear=ETA, nvel=nvel, **BINARY) as s:
+        s.init_rest(1.0)
+        s.init_spinodal(8361235, 0.0, 0.05)
+        f, phi = s.get(rh.REF_F), s.get(rh.REF_PHI)
+        s.step(nsteps)
+        ref = {k: s.get(w) for k, w in (("f", rh.REF_F), ("phi", rh.REF_PHI), ("u", rh.REF_U), ("force", rh.REF_FORCE),
+                                         ("grad", rh.REF_GRAD), ("delsq", rh.REF_DELSQ))}
+    st = dict(f=f.copy(), phi=phi.copy(), u=np.zeros((3, orc.nsites)), rho=np.zeros((1, orc.nsites)),
+              force=np.zeros((3, orc.nsites)), grad=np.zeros((3, orc.nsites)), delsq=np.zeros((1, orc.nsites)))
+    orc.step(orc.collide_param(0, 1.0, ETA), orc.symm_param(adv_order=order, grad_7pt=1, **BINARY), 1, nsteps,
+             st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    for k in ref:
+        assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k

@@ -147,3 +147,38 @@ def test_serial_spin_lb1_log():
     for a, (lo, hi) in enumerate(((-1.1415683e-05, 1.1538576e-05), (-1.2562973e-05, 1.1995491e-05),
                                   (-1.3597212e-05, 1.1403472e-05))):
         assert ui[a].min() == approx(lo, 8) and ui[a].max() == approx(hi, 8)
+
+
+def test_d3q27_serial_spin_n01_log():
+    """tests/regression/d3q27/serial-spin-n01.{inp,log}: D3Q27, 16^3, symmetric free energy through the finite-difference
+    route with fd_gradient_calculation 3d_7pt_fluid and advection order 2, viscosity 0.00625, mobility 1.25, seed 8361235:
+    printed statistics at t = 0 and t = 10 to the printed digits."""
+    n = (16, 16, 16)
+    orc = Oracle(n, nhalo=2, nvel=27)
+    f = orc.equilibrium(1.0, (0.0, 0.0, 0.0))
+    phi = spinodal_phi(n, 2, 8361235, 0.0, 0.1)
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+    sp = orc.symm_param(adv_order=2, grad_7pt=1, **BINARY)
+    cp = orc.collide_param(0, 1.0, ETA)
+
+    s = stats_scalar(orc, phi)
+    assert s[0] == approx(-2.2941536e+00, 8) and s[2] == approx(8.3652803e-04, 8)
+    assert s[3] == approx(-4.9986867e-02, 8) and s[4] == approx(4.9997941e-02, 8)
+    ph = phi.copy()
+    orc.field_halo(ph)
+    orc.grad_7pt(ph, grad, delsq)
+    assert fed_density(orc, sp, ph, grad) == approx(-1.2851398593e-07, 11)
+
+    orc.step(cp, sp, 1, 10, f, phi, u, rho, force, grad, delsq)
+
+    s = stats_scalar(orc, phi)
+    assert s[0] == approx(-2.2941536e+00, 8) and s[2] == approx(1.7010966e-04, 8)
+    assert s[3] == approx(-4.2252684e-02, 8) and s[4] == approx(3.9099406e-02, 8)
+    assert fed_density(orc, sp, phi, grad) == approx(-3.1541470368e-08, 11)
+    r = stats_scalar(orc, f.sum(axis=0, keepdims=True))
+    assert r[0] == approx(4096.00, 8) and r[3] == approx(0.99997295107, 11) and r[4] == approx(1.00002678655, 11)
+    ui = orc.interior(u)
+    for a, (lo, hi) in enumerate(((-1.3080740e-05, 1.4918725e-05), (-1.6836354e-05, 1.6014326e-05),
+                                  (-1.8317661e-05, 1.4310906e-05))):
+        assert ui[a].min() == approx(lo, 8) and ui[a].max() == approx(hi, 8)
