@@ -1981,7 +1981,8 @@ static bool pipe_eligible(const lb200_t * c, int nsteps) {
   const Lb200Geom & g = c->g;
   return c->knob_pipe >= 2 && !g.remote_x && c->le.nplane == 0 && c->nvel == 19 && c->unrolled19 && c->ndist == 1
     && c->map_all_fluid && nsteps >= 2 && g.nl[0] >= 8*c->knob_pipe && c->pipe_state >= 0
-    && !c->profile;          // per-kernel timing wants each kernel alone on the device
+    && !c->profile           // per-kernel timing wants each kernel alone on the device
+    && !c->knob_f32;         // FP32 storage lives in the serial step
 }
 
 static int step_pipe(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev & sd, int nsteps) {
