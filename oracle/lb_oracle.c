@@ -281,6 +281,15 @@ void orc_lb_halo(const orc_geom_t * g, const orc_model_t * m, int ndist, int red
 void orc_field_halo(const orc_geom_t * g, int nf, double * data) {
 
   const size_t ns = (size_t) orc_nsites(g);
+  /* field_halo_post packs every send buffer before field_halo_wait unpacks any (src/field.c:1412-1531).  On a lattice
+   * thinner than the halo (nlocal[d] < nhalo, e.g. 64 x 64 x 1 with nhalo 2: tests/regression/d3q19/pmpi08-le2d-fd1)
+   * the send regions reach into the halo, so what travels is the halo's content BEFORE this swap: copy from a snapshot. */
+  double * snap = NULL;
+  if (g->nlocal[X] < g->nhalo || g->nlocal[Y] < g->nhalo || g->nlocal[Z] < g->nhalo) {
+    snap = (double *) malloc((size_t) nf*ns*sizeof(double));
+    assert(snap);
+    memcpy(snap, data, (size_t) nf*ns*sizeof(double));
+  }
 
   for (int cx = -1; cx <= 1; cx++) {
     for (int cy = -1; cy <= 1; cy++) {
@@ -294,16 +303,18 @@ void orc_field_halo(const orc_geom_t * g, int nf, double * data) {
 	halo_limits(g, g->nhalo, c, &s, &r);
 	for (int n = 0; n < nf; n++) {
 	  double * d = data + (size_t) n*ns;
+	  const double * src = snap ? snap + (size_t) n*ns : d;
 	  for (int i = 0; i <= s.imax - s.imin; i++)
 	    for (int j = 0; j <= s.jmax - s.jmin; j++)
 	      for (int k = 0; k <= s.kmax - s.kmin; k++) {
 		d[orc_index(g, r.imin + i, r.jmin + j, r.kmin + k)]
-		  = absent ? 0.0 : d[orc_index(g, s.imin + i, s.jmin + j, s.kmin + k)];
+		  = absent ? 0.0 : src[orc_index(g, s.imin + i, s.jmin + j, s.kmin + k)];
 	      }
 	}
       }
     }
   }
+  free(snap);
 }
 
 /* ---- lb_collide, single distribution: src/collision.c:253-593 ---------------------------

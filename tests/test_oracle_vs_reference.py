@@ -400,3 +400,38 @@ def test_binary_time_steps_7pt_gradient(order, nlocal, nvel):
              st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
     for k in ref:
         assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k
+
+
+@pytest.mark.parametrize("nlocal", [(8, 8, 1), (1, 6, 5), (6, 1, 1)])
+def test_field_halo_on_lattices_thinner_than_the_halo(nlocal):
+    """nlocal[d] < nhalo (the reference's own pmpi08-le2d-fd1 regression runs 64 x 64 x 1 with nhalo 2): every send buffer
+    is packed before any is unpacked (src/field.c:1412-1531), so the outer halo layer receives the halo's content from
+    BEFORE the swap; the oracle reproduces that bit for bit (the CUDA library refuses such lattices: LB200_EINVAL)."""
+    orc = Oracle(nlocal, nhalo=2)
+    rng = np.random.default_rng(31)
+    with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=2, eta_shear=ETA, **BINARY) as s:
+        phi = rng.random((1, orc.nsites))
+        s.set(rh.REF_PHI, phi)
+        s.op("phi_halo")
+        ref = s.get(rh.REF_PHI)
+    orc.field_halo(phi)
+    assert np.array_equal(phi, ref)
+
+
+@pytest.mark.parametrize("nlocal,order", [((8, 8, 1), 3), ((8, 1, 6), 2)])
+def test_binary_time_steps_on_thin_lattices(nlocal, order):
+    nsteps = 6
+    orc = Oracle(nlocal, nhalo=2)
+    with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=order, ghost_off=1, eta_shear=ETA, **BINARY) as s:
+        s.init_rest(1.0)
+        s.init_spinodal(8361235, 0.0, 0.05)
+        f, phi = s.get(rh.REF_F), s.get(rh.REF_PHI)
+        s.step(nsteps)
+        ref = {k: s.get(w) for k, w in (("f", rh.REF_F), ("phi", rh.REF_PHI), ("u", rh.REF_U), ("force", rh.REF_FORCE),
+                                         ("grad", rh.REF_GRAD), ("delsq", rh.REF_DELSQ))}
+    st = dict(f=f.copy(), phi=phi.copy(), u=np.zeros((3, orc.nsites)), rho=np.zeros((1, orc.nsites)),
+              force=np.zeros((3, orc.nsites)), grad=np.zeros((3, orc.nsites)), delsq=np.zeros((1, orc.nsites)))
+    orc.step(orc.collide_param(0, 1.0, ETA), orc.symm_param(adv_order=order, **BINARY), 1, nsteps,
+             st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    for k in ref:
+        assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k
