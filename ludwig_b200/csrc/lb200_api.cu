@@ -1046,8 +1046,8 @@ int lb200_hydro_u_zero(lb200_t * c) {
 static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int reduced, cudaStream_t st) {
   if (st == nullptr) st = c->stream;
   // A periodic lattice thinner than the swap depth (e.g. 64 x 64 x 1 with nhalo 2): the reference's send regions then
-  // reach into the halo and what arrives is the halo's content before the swap (src/field.c:1329-1355, 1412-1531;
-  // reproduced by the oracle) -- not the periodic image this kernel writes.  Refuse rather than differ silently.
+  // reach into the halo and what arrives is the halo's content before the swap (src/field.c:1329-1355, 1412-1531)
+  // -- not the periodic image this kernel writes.  Refuse rather than differ silently.
   for (int a = 0; a < 3; a++) {
     if (c->g.per[a] && c->g.nl[a] < depth)
       return fail(LB200_EINVAL, "halo swap of depth %d on a periodic lattice of extent %d: lattices thinner than the halo are outside this build", depth, c->g.nl[a]);
