@@ -120,15 +120,6 @@ class ClockSampler:
         return out
 
 
-def initial_state(nlocal, nhalo, rank):
-    """Synthetic spinodal start: rho = 1, u = 0 (f = w_p), phi = 0.05 (r - 1/2), r uniform (seeded)."""
-    import numpy as np
-    nall = tuple(n + 2 * nhalo for n in nlocal)
-    ns = nall[0] * nall[1] * nall[2]
-    wv = np.array([12.0] + [2.0 if sum(abs(c) for c in cv) == 1 else 1.0 for cv in CV19[1:]]) / 36.0
-    return ns, nall, wv
-
-
 CV19 = [(0, 0, 0), (1, 1, 0), (1, 0, 1), (1, 0, 0), (1, 0, -1), (1, -1, 0), (0, 1, 1), (0, 1, 0), (0, 1, -1),
         (0, 0, 1), (0, 0, -1), (0, -1, 1), (0, -1, 0), (0, -1, -1), (-1, 1, 0), (-1, 0, 1), (-1, 0, 0),
         (-1, 0, -1), (-1, -1, 0)]
@@ -138,21 +129,39 @@ CV19 = [(0, 0, 0), (1, 1, 0), (1, 0, 1), (1, 0, 0), (1, 0, -1), (1, -1, 0), (0, 
 # CPU arm: the reference's own implementation (oracle/_ref) or the C port (oracle/), host cores
 # ------------------------------------------------------------------------------------------------------
 
-def cpu_steps_per_second(n, nsteps, warm=1):
-    """(seconds per step, kind, threads) for an n^3 binary-fluid lattice on the host CPU."""
+def host_threads():
+    """CPUs this process may run on (the box's host cores); what the CPU arm's OpenMP team is set to"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_steps_per_second(n, nsteps, warm=1, keep=False):
+    """(seconds per step, kind, threads[, state]) for an n^3 binary-fluid lattice on the host CPU.  The OpenMP team is
+    set through the library (omp_set_num_threads) to the host core count whatever OMP_NUM_THREADS says -- torchrun
+    exports OMP_NUM_THREADS=1 -- and `threads` is what omp_get_max_threads() then reports.  keep: also return the
+    initial (f, phi) and final (f, phi, u) arrays of the reference run (canonical layout) for bench.py's parity check."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    want = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(want)
     import refharness
     if refharness.available(fast=True):
+        threads = refharness.omp_threads(want, fast=True) or want
         sim = refharness.RefSim((n, n, n), nhalo=2, have_phi=1, adv_order=ADV_ORDER, eta_shear=ETA,
                                 ghost_off=1, fast=True, **BINARY)
         sim.init_rest(1.0)
         sim.init_spinodal(8361235, 0.0, 0.05)
+        state = None
+        if keep:
+            state = {"f0": sim.get(refharness.REF_F), "phi0": sim.get(refharness.REF_PHI)}
         sim.step(warm)
         t = sim.time_steps(nsteps)
+        if keep:
+            state.update(f=sim.get(refharness.REF_F), phi=sim.get(refharness.REF_PHI), u=sim.get(refharness.REF_U),
+                         nsteps=warm + nsteps, n=n)
         sim.close()
-        return t / nsteps, "reference", threads
+        return (t / nsteps, "reference", threads, state) if keep else (t / nsteps, "reference", threads)
     import numpy as np
     from oracle import Oracle
     orc = Oracle((n, n, n), nhalo=2)
@@ -165,10 +174,15 @@ def cpu_steps_per_second(n, nsteps, warm=1):
     u, rho, force, grad, delsq = z3(), z1(), z3(), z3(), z1()
     cp = orc.collide_param(0, 1.0, ETA)
     sp = orc.symm_param(adv_order=ADV_ORDER, **BINARY)
+    state = {"f0": f.copy(), "phi0": phi.copy()} if keep else None
     orc.step(cp, sp, 1, warm, f, phi, u, rho, force, grad, delsq)
     t0 = time.perf_counter()
     orc.step(cp, sp, 1, nsteps, f, phi, u, rho, force, grad, delsq)
-    return (time.perf_counter() - t0) / nsteps, "port", threads
+    t = (time.perf_counter() - t0) / nsteps
+    if keep:
+        state.update(f=f, phi=phi, u=u, nsteps=warm + nsteps, n=n)
+        return t, "port", 1, state
+    return t, "port", 1
 
 
 def run_reference_arm(args, rank, world):
@@ -194,7 +208,7 @@ def run_reference_arm(args, rank, world):
                                f"CPU sample lattice {n}^3 (target workload 256^3 per GPU)"},
         "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": threads, "kind": kind,
                          "sample": f"{args.steps} full time steps of a {n}^3 lattice after {max(args.warmup, 1)} warm-up "
-                                   f"steps, OpenMP threads = {threads}"},
+                                   f"steps, OpenMP team of {threads} threads (omp_get_max_threads)"},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -204,6 +218,86 @@ def run_reference_arm(args, rank, world):
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
+
+def rel_err_interior(sim, a, b):
+    """max |a - b| over the interior sites / max |b| (arrays in the canonical allocated layout)"""
+    import numpy as np
+    ai, bi = sim.interior(a), sim.interior(b)
+    scale = float(np.abs(bi).max())
+    d = float(np.abs(ai - bi).max())
+    return d / scale if scale > 0 else d
+
+
+def check_against_reference(lb, state, device, math):
+    """The GPU library on the CPU leg's own lattice: same initial (f, phi), same parameters, same number of steps;
+    returns max relative errors of f, phi, u against the arrays the reference's own code produced."""
+    n = state["n"]
+    with lb.Lb200((n, n, n), nhalo=2, have_phi=True, math=math, device=device) as sim:
+        sim.put(lb.F, state["f0"]); sim.put(lb.PHI, state["phi0"])
+        sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), lb.SymmParam.make(adv_order=ADV_ORDER, **BINARY), state["nsteps"])
+        out = {"f": rel_err_interior(sim, sim.get(lb.F), state["f"]),
+               "phi": rel_err_interior(sim, sim.get(lb.PHI), state["phi"]),
+               "u": rel_err_interior(sim, sim.get(lb.U), state["u"])}
+    return out
+
+
+def check_decomposition(lb, dist, torch, rank, local_rank, world, nsteps=8, nxl=32, ny=48, nz=64):
+    """x-slab run on `world` GPUs (nxl planes each) against the SAME library on one GPU over the undecomposed lattice:
+    strict mode must agree bit for bit, fast mode within 1e-12 (x-chunk boundaries of the phi sector fall on different
+    planes in the two runs).  Returns {"multi_gpu_bit_exact": bool, "multi_gpu_max_rel_err_fast": float} on rank 0."""
+    import numpy as np
+    nh = 2
+    nglob = (nxl * world, ny, nz)
+    nall_g = tuple(m + 2 * nh for m in nglob)
+    nall_l = (nxl + 2 * nh, ny + 2 * nh, nz + 2 * nh)
+    rng = np.random.default_rng(424242)
+    wv = np.array([12.0] + [2.0 if sum(abs(c) for c in cv) == 1 else 1.0 for cv in CV19[1:]]) / 36.0
+    f = np.zeros((19,) + nall_g)
+    f[:, nh:-nh, nh:-nh, nh:-nh] = wv[:, None, None, None] * (1.0 + 1e-3 * (rng.random((19,) + nglob) - 0.5))
+    phi = np.zeros((1,) + nall_g)
+    phi[:, nh:-nh, nh:-nh, nh:-nh] = 0.05 * (rng.random((1,) + nglob) - 0.5)
+
+    def slab(a):
+        out = np.zeros((a.shape[0],) + nall_l)
+        out[:, nh:nh + nxl] = a[:, nh + rank * nxl:nh + (rank + 1) * nxl]
+        return out.reshape(a.shape[0], -1)
+
+    cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA, force=(1e-6, -2e-6, 5e-7))
+    sp = lb.SymmParam.make(adv_order=ADV_ORDER, **BINARY)
+    arrays = (("f", lb.F), ("phi", lb.PHI), ("u", lb.U))
+    out = {}
+    for math, key in ((lb.MATH_STRICT, "strict"), (lb.MATH_FAST, "fast")):
+        sim = lb.Lb200((nxl, ny, nz), nhalo=nh, have_phi=True, math=math, device=local_rank, cart_size=world, cart_rank=rank)
+        ids = [sim.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sim.nccl_init(ids[0], world, rank)
+        sim.put(lb.F, slab(f)); sim.put(lb.PHI, slab(phi))
+        sim.step(cp, sp, nsteps)
+        mine = {k: np.ascontiguousarray(sim.interior(sim.get(a))) for k, a in arrays}
+        mode = sim.exchange_mode()
+        sim.close()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            with lb.Lb200(nglob, nhalo=nh, have_phi=True, math=math, device=local_rank) as one:
+                one.put(lb.F, f.reshape(19, -1)); one.put(lb.PHI, phi.reshape(1, -1))
+                one.step(cp, sp, nsteps)
+                single = {k: np.ascontiguousarray(one.interior(one.get(a))) for k, a in arrays}
+            same, err = True, 0.0
+            for k, _ in arrays:
+                full = np.concatenate([g[k] for g in gathered], axis=1)
+                same = same and bool(np.array_equal(full, single[k]))
+                scale = float(np.abs(single[k]).max())
+                err = max(err, float(np.abs(full - single[k]).max()) / (scale if scale > 0 else 1.0))
+            if key == "strict":
+                out["multi_gpu_bit_exact"] = same
+            else:
+                out["multi_gpu_max_rel_err_fast"] = err
+                out["multi_gpu_bit_exact_fast"] = same
+            out["multi_gpu_check"] = (f"{world} x-slabs of {nxl} planes ({nglob[0]}x{ny}x{nz} lattice), {nsteps} steps, exchange mode {mode}, "
+                                      "against one GPU over the undecomposed lattice")
+    return out
+
 
 def run_ours(args, rank, local_rank, world):
     import numpy as np
@@ -359,15 +453,36 @@ def run_ours(args, rank, local_rank, world):
     h2d = (19 * sim.nsites_lb + ns) * 8 / args.steps
     d2h = (1 + 3 + 1) * ns * 8 / args.steps
 
+    exch_mode = sim.exchange_mode()
+    pipe_st = sim.pipe_state()
+    sim.close()
+    del h_f, h_phi, h_u, h_rho
+
+    # ---- CPU baseline (rank 0) and parity of what was just timed ---------------------------------------
+    # check.max_rel_err_*: the library on the CPU leg's own lattice (same initial state, same steps) against the arrays
+    # the reference's own code produced; at N > 1 also the decomposed run against one GPU on the undecomposed lattice.
     cpu = None
+    check = {"phi_sum": phi_sum}
     if rank == 0 and not args.no_cpu:
         try:
             nsamp = args.cpu_size
-            tstep, kind, threads = cpu_steps_per_second(nsamp, 3, warm=1)
+            tstep, kind, threads, state = cpu_steps_per_second(nsamp, 3, warm=1, keep=True)
             cpu = {"value": nsamp ** 3 / tstep / 1e6, "unit": "MLUPS", "cores": threads, "kind": kind,
-                   "sample": f"3 full time steps of a {nsamp}^3 lattice (same physics, same parameters) after 1 warm-up step"}
+                   "sample": f"3 full time steps of a {nsamp}^3 lattice (same physics, same parameters) after 1 warm-up step, "
+                             f"OpenMP team of {threads} threads"}
+            err = check_against_reference(lb, state, local_rank, lb.MATH_STRICT if args.strict else lb.MATH_FAST)
+            check.update({"max_rel_err_f": err["f"], "max_rel_err_phi": err["phi"], "max_rel_err_u": err["u"],
+                          "against": f"the {'compiled reference' if kind == 'reference' else 'C port of the reference'} on {nsamp}^3, "
+                                     f"{state['nsteps']} steps from the same initial state (the cpu_baseline leg's run)",
+                          "tolerance": 1e-12, "ok": bool(max(err.values()) <= 1e-12)})
+            del state
         except Exception as exc:          # the baseline is reported, never allowed to sink the bench
             cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+    if world > 1 and not args.no_check:
+        try:
+            check.update(check_decomposition(lb, dist, torch, rank, local_rank, world))
+        except Exception as exc:
+            check["multi_gpu_check"] = f"failed: {exc}"
 
     if rank == 0:
         line = {
@@ -383,11 +498,11 @@ def run_ours(args, rank, local_rank, world):
                                         "halo kernels + plane patches (not the halo-free path)" if args.le else "none"),
                        "math": "strict" if args.strict else "fast(fma)",
                        "x_plane_exchange": {0: "none (one GPU)", 1: "NCCL send/recv on a second stream",
-                                            2: "NVLink peer stores from inside the kernels + flags"}[sim.exchange_mode()],
+                                            2: "NVLink peer stores from inside the kernels + flags"}[exch_mode],
                        "distribution_storage": ("f32 (float(f_p - w_p), FP64 arithmetic; LB200_KNOB_F32: error bound in "
                                                 "tests/test_gpu_parity.py::test_f32_storage_error_bound)" if args.f32 else "f64"),
                        "slab_pipeline": (lambda st: {"slabs": args.pipe, "mode": {1: "green contexts", 2: "priority streams"}.get(st[0], "off"),
-                                                     "sms_phi_sector": st[1][0], "sms_collide": st[1][1]})(sim.pipe_state()),
+                                                     "sms_phi_sector": st[1][0], "sms_collide": st[1][1]})(pipe_st),
                        "diagnostic_stores": ("hydro->rho, grad, delsq stored by the last step of each lb200_step call only (LB200_LAZY_DIAG=1)"
                                              if lazy else "every step"),
                        "l2": "inputs (2.8 GB of lattice state per sweep) exceed the 126 MB L2; no flush needed",
@@ -409,11 +524,10 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clk,
             "e2e": {"value": e2e, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "check": {"phi_sum": phi_sum},
+            "check": check,
         }
         print(json.dumps(line), flush=True)
 
-    sim.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -534,13 +648,13 @@ def run_lc(args, rank, local_rank, world):
             import refharness
             nsamp = 64
             if refharness.available(fast=True):
-                os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+                lc_threads = refharness.omp_threads(host_threads(), fast=True) or host_threads()
                 ref = refharness.RefSim((nsamp,) * 3, nhalo=2, adv_order=3, eta_shear=0.1, fast=True, lc=LC)
                 ref.init_rest(1.0); ref.lc_twist_init(2, 1.0 / 3.0)
                 ref.step(1)
                 t = ref.time_steps(3) / 3
                 ref.close()
-                cpu = {"value": nsamp ** 3 / t / 1e6, "unit": "MLUPS", "cores": os.cpu_count() or 1, "kind": "reference",
+                cpu = {"value": nsamp ** 3 / t / 1e6, "unit": "MLUPS", "cores": lc_threads, "kind": "reference",
                        "sample": f"3 full liquid-crystal time steps of a {nsamp}^3 lattice after 1 warm-up step"}
         except Exception as exc:
             cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "reference", "sample": f"failed: {exc}"}
@@ -588,6 +702,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=128, help="edge of the CPU-baseline sample lattice")
     ap.add_argument("--strict", action="store_true", help="bit-exact arithmetic mode (no FMA contraction)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the decomposed-vs-single-GPU parity run at N > 1")
     ap.add_argument("--f32", action="store_true", help="FP32 storage of the distributions inside lb200_step (LB200_KNOB_F32); "
                     "a separate mode with a stated error bound, not the FP64 headline")
     ap.add_argument("--pipe", type=int, default=int(os.environ.get("LB200_PIPE", "0")),

@@ -1839,6 +1839,11 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     if (c->f_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_f, 0));
     if (c->u_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
     if (binary && c->phi_src == SRC_EVENT) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
+    // peer stores: the neighbours' last phi sector / collision write into THIS rank's halo planes; what follows on the
+    // main stream (a copy to the host, an upload, lb200_free) must come after them (the flags stay set: the next
+    // step's own wait on the same values passes at once)
+    if (binary && c->phi_src == SRC_FLAG && (rc = flags_wait(c, S, FLAG_PS_LO, c->n_ps)) != 0) return rc;
+    if (c->f_src == SRC_FLAG && (rc = flags_wait(c, S, FLAG_COL_LO, c->n_col)) != 0) return rc;
   }
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -30,6 +30,7 @@ namespace {
 
 constexpr int TPB = 128;
 constexpr int TPB_MAX = 256;
+constexpr int LB200_MAX_DEVICES = 64;     // per-device launch state (function attributes, SM counts)
 
 // threads per block of the site-per-thread kernels; LB200_TPB (64/128/256) overrides for tuning runs
 __host__ inline int tuned_tpb() {
@@ -2211,13 +2212,16 @@ phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
 // scheduled in rounds of (SMs x resident CTAs), so pick the chunk count that minimises
 // rounds x (planes per chunk + fill).  256^3 on 148 SMs: 6 chunks of 43 planes = 1026 CTAs = 6.9 rounds.
 static int ps_pick_xc(const void * kernel, size_t smem, int tiles, int nx, int fill) {
-  static int nsm = 0;
-  if (nsm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (nsm <= 0) nsm = 148;
+  // per device: one process may hold contexts on several GPUs
+  static int nsm_dev[LB200_MAX_DEVICES] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = (dev >= 0 && dev < LB200_MAX_DEVICES) ? dev : 0;
+  if (nsm_dev[dev] == 0) {
+    cudaDeviceGetAttribute(&nsm_dev[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (nsm_dev[dev] <= 0) nsm_dev[dev] = 148;
   }
+  const int nsm = nsm_dev[dev];
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PS_NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const long long slots = (long long) nsm*per_sm;
@@ -2248,12 +2252,15 @@ int launch_phi_sector(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
   const size_t smem = sizeof(PfShared);
   const int fill = 6;       // 4 extra plane-steps + the slower generic steps of fill and drain
 #endif
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 kB of dynamic shared memory is a per-device function attribute
+  static bool configured[LB200_MAX_DEVICES] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= LB200_MAX_DEVICES || !configured[dev]) {
     cudaFuncSetAttribute(LB200_PS_KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaFuncSetAttribute(LB200_PS_KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaFuncSetAttribute(LB200_PS_KERNEL<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    configured = true;
+    if (dev >= 0 && dev < LB200_MAX_DEVICES) configured[dev] = true;
   }
   const int nx = (g.xcnt > 0) ? g.xcnt : g.nl[0];
   const int xc = (g.xchunk > 0) ? g.xchunk : ps_pick_xc((const void *) LB200_PS_KERNEL<3>, smem, gz*gy, nx, fill);
@@ -2289,7 +2296,9 @@ __global__ void spin_wait_kernel(const unsigned int * flag, unsigned int value, 
       long long t1;
       __nanosleep(200);
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > timeout_ns) { *err = 1; break; }
+      // a neighbour that never signals: fail loudly (the stream errors out, lb200_sync returns LB200_ECUDA)
+      // instead of letting the consumer kernel run on stale halo planes
+      if (t1 - t0 > timeout_ns) { *err = 1; __threadfence_system(); __trap(); }
     }
     __threadfence_system();
   }

@@ -491,6 +491,16 @@ int ref_step(ref_sim_t * s, int nsteps) {
   return 0;
 }
 
+/* OpenMP team size of the reference's kernels (target/target_x86.c runs every kernel in a `#pragma omp parallel`):
+ * n > 0 sets it for this process whatever OMP_NUM_THREADS said at start-up (torchrun exports OMP_NUM_THREADS=1);
+ * returns the team size the next kernel will use, which is what the bench reports as "cores". */
+#ifdef _OPENMP
+#include <omp.h>
+int ref_omp_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int ref_omp_threads(int n) { (void) n; return 1; }
+#endif
+
 /* Wall-clock of nsteps full steps, for the CPU baseline (bench.py --impl reference) */
 
 double ref_time_steps(ref_sim_t * s, int nsteps) {

@@ -70,9 +70,18 @@ def _lib(fast=False, nvel=19):
         lib.ref_lc_fed_sum.argtypes = [C.c_void_p]
         lib.ref_lc_fed_sum.restype = C.c_double
         lib.ref_nvel.restype = C.c_int
+        if hasattr(lib, "ref_omp_threads"):
+            lib.ref_omp_threads.argtypes = [C.c_int]
+            lib.ref_omp_threads.restype = C.c_int
         assert lib.ref_nvel() == nvel
         _libs[key] = lib
     return _libs[key]
+
+
+def omp_threads(n=0, fast=False, nvel=19):
+    """Set (n > 0) and return the OpenMP team size the reference's kernels run with in this process."""
+    lib = _lib(fast, nvel)
+    return lib.ref_omp_threads(n) if hasattr(lib, "ref_omp_threads") else 0
 
 
 class RefSim:
