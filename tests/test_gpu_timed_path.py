@@ -109,8 +109,8 @@ def test_serial_spin_fd1_log_from_the_gpu(path, math):
             sim.step_api(cp, sp, 10)
         else:
             sim.step(cp, sp, 10)
-        # the reference prints [rho] and the momentum from the distributions after lb_propagation
-        sim.lb_halo(); sim.lb_propagation()
+        # the reference prints [rho] and the momentum from the distributions after lb_propagation: the last operation
+        # of step_api; pending after lb200_step and applied by the copy to the host
         gf, gphi, gu, ggrad = sim.get(lb.F), sim.get(lb.PHI), sim.get(lb.U), sim.get(lb.GRAD)
 
     s = stats_scalar(orc, gphi)
