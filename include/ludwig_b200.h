@@ -267,6 +267,12 @@ enum lb200_knob {
                                *    error <= 2^-24 of its deviation from the rest weight w_p (bound and measured
                                *    errors: DESIGN.md, tests/test_gpu_parity.py::test_f32_storage_error_bound).
                                *    208 instead of 360 bytes per site and step.  Default LB200_F32, else 0 */
+  LB200_KNOB_FUSED = 8,       /* 1: the whole binary-fluid time step in ONE kernel (fast arithmetic mode, D3Q19, all-fluid,
+                               *    halo-free path, advection order 1-3, no planes): the phi sector and the pull-stream +
+                               *    collision of the same plane share a sweep, so the body force never goes through
+                               *    memory (368 instead of 416 bytes per site and step).  Where it does not apply the
+                               *    step runs the phi-sector kernel followed by the collision kernel.
+                               *    Default LB200_FUSED, else 1 */
   LB200_KNOB_GRAD_7PT = 7     /* NOT an execution knob: selects the finite-difference scheme of the scalar order parameter,
                                *    `fd_gradient_calculation`: 0 = 3d_27pt_fluid (default), 1 = 3d_7pt_fluid
                                *    (grad_3d_7pt_fluid_d2, src/gradient_3d_7pt_fluid.c:76-99, 231-300) for
@@ -297,7 +303,8 @@ enum lb200_kernel_class {
   LB200_K_LE = 6,           /* Lees-Edwards: buffer interpolation, plane patches, plane-crossing populations */
   LB200_K_LC_STRESS = 7,    /* liquid crystal: gradients + molecular field + stress */
   LB200_K_LC_BE = 8,        /* liquid crystal: force divergence + Beris-Edwards update */
-  LB200_KCLASS_MAX = 9
+  LB200_K_STEP_FUSED = 9,   /* phi sector + pull-stream + collision in one sweep (lb200_step, LB200_KNOB_FUSED) */
+  LB200_KCLASS_MAX = 10
 };
 int lb200_profile(lb200_t * ctx, int on);      /* clears accumulated timings */
 int lb200_profile_get(lb200_t * ctx, int kernel_class, double * total_ms, int * count);

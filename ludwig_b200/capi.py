@@ -8,7 +8,7 @@ RELAX_M10, RELAX_BGK, RELAX_TRT = 0, 1, 2
 HALO_FULL, HALO_REDUCED = 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 H2D, D2H = 1, 2
-KNOB_WRAP, KNOB_PHI_SECTOR, KNOB_PEER, KNOB_PIPE, KNOB_PIPE_SMS, KNOB_F32, KNOB_GRAD_7PT = 1, 2, 3, 4, 5, 6, 7
+KNOB_WRAP, KNOB_PHI_SECTOR, KNOB_PEER, KNOB_PIPE, KNOB_PIPE_SMS, KNOB_F32, KNOB_GRAD_7PT, KNOB_FUSED = 1, 2, 3, 4, 5, 6, 7, 8
 
 _NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1, GRAD_DELSQ: 3, DELSQ_DELSQ: 1, STR: 9,
           Q: 5, QGRAD: 15, QDELSQ: 5}
@@ -400,7 +400,7 @@ class Lb200:
             self.lb_halo()
             self.lb_propagation()
 
-    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch", "phi_sector", "le", "lc_stress", "lc_be")
+    KCLASSES = ("collide", "propagate", "halo", "grad", "force_ch", "phi_sector", "le", "lc_stress", "lc_be", "step_fused")
 
     def profile(self, on=True):
         self._check(self.lib.lb200_profile(self.h, int(on)))

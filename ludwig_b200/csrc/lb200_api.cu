@@ -97,6 +97,7 @@ struct lb200_s {
   int u_halo_valid;
 
   int prop_pending;          // lb_propagation requested, not yet applied (fused into next collide)
+  int f_yz_ready;            // f_halo_stale, but the one-kernel step has stored the populations the next pull reads in the y / z halos
   int f_halo_stale;          // halo-free lb200_step: lb_halo(f) was folded into the kernels' reads and has
                              // not been applied to the halo sites of f (done on demand with the propagation)
   int wrap_x_valid;          // halo-free lb200_step on slabs: x-planes of phi, u_x, f already exchanged
@@ -111,6 +112,7 @@ struct lb200_s {
   int knob_grad7;            // fd_gradient_calculation 3d_7pt_fluid for the scalar order parameter (0: 3d_27pt_fluid)
   int knob_lazy_diag;        // rho / grad / delsq stored by the last step of an lb200_step call only (LB200_LAZY_DIAG, default 1)
   int knob_f32;              // FP32 storage of the distributions inside lb200_step (0: off)
+  int knob_fused;            // one kernel per binary-fluid step where it applies (LB200_FUSED, default 1)
   float * f32[2];            // float(f_p - w_p), allocated on first use
   int knob_pipe;             // slab pipeline of lb200_step: number of x-slabs (0: off)
   int knob_pipe_sms;         // SMs of the phi-sector partition (the collision gets the rest)
@@ -627,6 +629,7 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   c->knob_peer = getenv("LB200_PEER") ? atoi(getenv("LB200_PEER")) : 1;
   c->knob_pipe = getenv("LB200_PIPE") ? atoi(getenv("LB200_PIPE")) : 0;
   c->knob_f32 = getenv("LB200_F32") ? atoi(getenv("LB200_F32")) : 0;
+  c->knob_fused = getenv("LB200_FUSED") ? atoi(getenv("LB200_FUSED")) : 1;
   c->knob_grad7 = getenv("LB200_GRAD_7PT") ? atoi(getenv("LB200_GRAD_7PT")) : 0;
   c->knob_lazy_diag = getenv("LB200_LAZY_DIAG") ? atoi(getenv("LB200_LAZY_DIAG")) : 1;
   c->knob_pipe_sms = getenv("LB200_PIPE_SMS") ? atoi(getenv("LB200_PIPE_SMS")) : 56;
@@ -645,6 +648,7 @@ int lb200_set_knob(lb200_t * c, int knob, int value) {
   else if (knob == LB200_KNOB_PHI_SECTOR) c->knob_phi_sector = (value != 0);
   else if (knob == LB200_KNOB_PEER) { c->knob_peer = (value != 0); c->wrap_x_valid = 0; }
   else if (knob == LB200_KNOB_F32) c->knob_f32 = (value != 0);
+  else if (knob == LB200_KNOB_FUSED) c->knob_fused = (value != 0);
   else if (knob == LB200_KNOB_GRAD_7PT) {
     if (value != 0 && c->le.nplane > 0) return fail(LB200_EINVAL, "3d_7pt_fluid with Lees-Edwards planes is outside this build");
     if (value != 0 && c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
@@ -1720,12 +1724,87 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     CUDA_TRY(cudaMalloc((void **) &c->f32[0], (size_t) 19*c->g.nsites*sizeof(float)));
     CUDA_TRY(cudaMalloc((void **) &c->f32[1], (size_t) 19*c->g.nsites*sizeof(float)));
   }
+  // one kernel per step (LB200_KNOB_FUSED): binary fluid, D3Q19 with the coded matrices, all-fluid, no planes
+  // (fast arithmetic mode; the TMA boxes of the populations need 16-byte aligned rows: even extents in z)
+  const bool fuse_ok = binary && c->knob_fused && !le && !f32 && c->nvel == 19 && c->unrolled19 && c->ndist == 1
+    && c->map_all_fluid && c->knob_pipe < 2 && sd->order <= 3 && sd->csum == nullptr
+    && c->opt.math == LB200_MATH_FAST && c->g.nh == 2 && (c->g.nall[2] & 1) == 0 && (c->g.nsites & 1) == 0
+    && c->g.nl[1] >= 2 && c->g.nl[2] >= 2;
+  if (fuse_ok && c->u_alloc[1] == nullptr) {
+    if (alloc_d(&c->u2, (size_t) 3*c->g.nsites) != 0) return LB200_ECUDA;
+    c->u_alloc[0] = c->u; c->u_alloc[1] = c->u2;
+  }
   for (int n = 0; n < nsteps; n++) {
     c->t_current += 1;                                                   // physics_control_next_step
     c->force_state = ZERO_PENDING;                                       // hydro_f_zero
     // hydro->rho, grad and delsq are read by nobody inside the step (the Lees-Edwards patches excepted, which read grad
     // and delsq): only the last step of the call stores them
     gw.skip_diag = (c->knob_lazy_diag && !le && n < nsteps - 1) ? 1 : 0;
+    if (fuse_ok && c->knob_fused && c->prop_pending) {
+      // The whole step in one sweep (LB200_KNOB_FUSED): phi sector + pull-stream + collision of the same plane, the
+      // force stays in registers.  (The first step after an upload of the distributions collides in place -- no
+      // propagation is pending -- and takes the two-kernel route below.)
+      if (remote) {
+	rc = src_wait(c, S, c->phi_src, c->ev_phi, FLAG_PS_LO, c->n_ps);
+	if (rc == 0) rc = src_wait(c, S, c->u_src, c->ev_u, FLAG_COL_LO, c->n_col);
+	if (rc == 0) rc = src_wait(c, S, c->f_src, c->ev_f, FLAG_COL_LO, c->n_col);
+	if (rc != 0) return rc;
+      }
+      // the TMA boxes of the populations read the y / z halos (and the rims of the x halo planes): valid after a
+      // one-kernel step, else one lb_halo brings them up to date
+      if (c->f_halo_stale && !c->f_yz_ready) {
+	rc = ensure_f_halo(c);
+	if (rc != 0) return rc;
+      }
+      // the phi sector of other CTAs (and of the neighbour GPUs) reads u(t-1) while this kernel writes u(t)
+      double * u_out = (c->u == c->u_alloc[0]) ? c->u_alloc[1] : c->u_alloc[0];
+      gw.peer_phi_lo = peer ? c->lo.phi[idx2(c->phinew, c->phi_alloc)] : nullptr;
+      gw.peer_phi_hi = peer ? c->hi.phi[idx2(c->phinew, c->phi_alloc)] : nullptr;
+      gw.peer_f_lo = peer ? c->lo.f[idx2(c->fprime, c->f_alloc)] : nullptr;
+      gw.peer_f_hi = peer ? c->hi.f[idx2(c->fprime, c->f_alloc)] : nullptr;
+      gw.peer_u_lo = peer ? c->lo.u[idx2(u_out, c->u_alloc)] : nullptr;
+      gw.peer_u_hi = peer ? c->hi.u[idx2(u_out, c->u_alloc)] : nullptr;
+      int launched = 0;
+      {
+	ProfScope ps(c, LB200_K_STEP_FUSED);
+	launched = c->k->step_fused(S, gw, *sd, cd, c->phi, c->u, c->f, c->fprime, c->grad, c->delsq, c->force,
+				    c->phinew, c->rho, u_out);
+      }
+      if (launched > 0) {
+	c->launches += launched;
+	c->force_state = gw.skip_diag ? ZERO_PENDING : INTERIOR_ONLY;      // the force array is written by the last step only
+	{ double * t = c->phi; c->phi = c->phinew; c->phinew = t; }
+	{ double * t = c->f; c->f = c->fprime; c->fprime = t; }
+	c->u = u_out;
+	c->u_state = INTERIOR_ONLY;
+	c->prop_pending = 1;
+	c->f_halo_stale = 1; c->f_yz_ready = 1;
+	if (peer) {
+	  c->n_ps++; c->n_col++;
+	  c->launches += c->k->signal(S, c->hi.flags + FLAG_PS_LO, c->lo.flags + FLAG_PS_HI, c->n_ps);
+	  c->launches += c->k->signal(S, c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
+	  c->phi_src = c->f_src = c->u_src = SRC_FLAG;
+	}
+	else if (remote) {
+	  CUDA_TRY(cudaEventRecord(c->ev_main, S));
+	  CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
+	  rc = wrap_exchange_phi(c, C);
+	  if (rc != 0) return rc;
+	  CUDA_TRY(cudaEventRecord(c->ev_phi, C));
+	  rc = wrap_exchange_ux(c, C);
+	  if (rc != 0) return rc;
+	  CUDA_TRY(cudaEventRecord(c->ev_u, C));
+	  rc = wrap_exchange_f(c, C);
+	  if (rc != 0) return rc;
+	  CUDA_TRY(cudaEventRecord(c->ev_f, C));
+	  c->phi_src = c->f_src = c->u_src = SRC_EVENT;
+	}
+	continue;
+      }
+      // no such kernel after all (no tensor-map entry point in this driver): the two-kernel step from now on
+      gw.peer_f_lo = gw.peer_f_hi = gw.peer_u_lo = gw.peer_u_hi = nullptr;
+      c->knob_fused = 0;
+    }
     if (binary) {
       if (remote) {
 	rc = src_wait(c, S, c->phi_src, c->ev_phi, FLAG_PS_LO, c->n_ps);
@@ -1810,7 +1889,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     }
     if (le) le_lb_bc_async(c);                                           // lb_data_apply_le_boundary_conditions
     c->prop_pending = 1;                                                 // lb_halo; lb_propagation (lazy)
-    c->f_halo_stale = 1;
+    c->f_halo_stale = 1; c->f_yz_ready = 0;
     if (peer) {
       c->n_col++;
       c->launches += c->k->signal(S, c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
@@ -2061,7 +2140,7 @@ static int step_pipe(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   c->force_state = INTERIOR_ONLY;
   c->u_state = INTERIOR_ONLY;
   c->prop_pending = 1;
-  c->f_halo_stale = 1;
+  c->f_halo_stale = 1; c->f_yz_ready = 0;
   c->phi_halo_valid = 0;
   c->u_halo_valid = 0;
   c->wrap_x_valid = 1;
@@ -2334,7 +2413,7 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
       c->u = u_out;
       c->u_state = INTERIOR_ONLY;
       c->prop_pending = 1;                                               // lb_halo; lb_propagation (lazy)
-      c->f_halo_stale = 1;
+      c->f_halo_stale = 1; c->f_yz_ready = 0;
       if (remote) {
 	CUDA_TRY(cudaEventRecord(c->ev_main, S));
 	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));

@@ -15,6 +15,9 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
+#include <cuda.h>
 #include "lb200_kernels.h"
 #include "d3q19_proj.cuh"
 
@@ -1644,7 +1647,10 @@ int launch_force_ch(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & s
 // ---------------------------------------------------------------------------------------------
 
 constexpr int PS_BZ = 32;                 // threads along z (one warp)
-constexpr int PS_BY = 16;                 // threads along y
+#ifndef LB200_PS_BY
+#define LB200_PS_BY 16
+#endif
+constexpr int PS_BY = LB200_PS_BY;        // threads along y
 constexpr int PS_NT = PS_BZ*PS_BY;        // 512
 constexpr int PS_TZ = PS_BZ - 2;          // interior columns per tile
 constexpr int PS_TY = PS_BY - 2;
@@ -2111,7 +2117,7 @@ __device__ __forceinline__ void pf_step(PfShared & sm, PfRegs & r, const PfK & k
 }
 
 template <int ORDER>
-__global__ void __launch_bounds__(PS_NT, 1)
+__global__ void __launch_bounds__(PS_NT, 512/PS_NT)
 phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
 		       const double * __restrict__ phi, const double * __restrict__ u,
 		       double * __restrict__ grad, double * __restrict__ delsq,
@@ -2211,7 +2217,7 @@ phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
 // Planes per x chunk: every chunk pays PS_XPRO extra plane-steps of pipeline fill, and the chunks are
 // scheduled in rounds of (SMs x resident CTAs), so pick the chunk count that minimises
 // rounds x (planes per chunk + fill).  256^3 on 148 SMs: 6 chunks of 43 planes = 1026 CTAs = 6.9 rounds.
-static int ps_pick_xc(const void * kernel, size_t smem, int tiles, int nx, int fill) {
+static int ps_pick_xc(const void * kernel, int nt, size_t smem, int tiles, int nx, int fill, int min_rounds = 0) {
   // per device: one process may hold contexts on several GPUs
   static int nsm_dev[LB200_MAX_DEVICES] = {0};
   int dev = 0;
@@ -2223,7 +2229,7 @@ static int ps_pick_xc(const void * kernel, size_t smem, int tiles, int nx, int f
   }
   const int nsm = nsm_dev[dev];
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PS_NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const long long slots = (long long) nsm*per_sm;
   const char * e = getenv("LB200_PS_XC");
   if (e && atoi(e) > 0) return atoi(e);
@@ -2234,6 +2240,9 @@ static int ps_pick_xc(const void * kernel, size_t smem, int tiles, int nx, int f
     if (xc < 8 && nchunk > 1) break;
     const long long rounds = ((long long) tiles*((nx + xc - 1)/xc) + slots - 1)/slots;
     const long long cost = rounds*(xc + fill);
+    // min_rounds: SMs do not run at one speed (distance to the L2 slices, neighbours' traffic); with only two or three
+    // long CTAs per SM the slowest SM sets the time, with many short ones the block scheduler evens it out
+    if (rounds < min_rounds && xc >= 16 && nchunk < nx) continue;
     if (best < 0 || cost < best) { best = cost; best_xc = xc; }
   }
   return best_xc;
@@ -2249,7 +2258,8 @@ int launch_phi_sector(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
   const int fill = 3;
 #else
 #define LB200_PS_KERNEL phi_sector_fast_kernel
-  const size_t smem = sizeof(PfShared);
+  static const int smem_pad = tuned_flag("LB200_PS_SMEM_PAD", 0);     // tuning: extra dynamic shared memory (limits CTAs per SM)
+  const size_t smem = sizeof(PfShared) + (size_t) smem_pad;
   const int fill = 6;       // 4 extra plane-steps + the slower generic steps of fill and drain
 #endif
   // the opt-in to > 48 kB of dynamic shared memory is a per-device function attribute
@@ -2263,7 +2273,7 @@ int launch_phi_sector(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
     if (dev >= 0 && dev < LB200_MAX_DEVICES) configured[dev] = true;
   }
   const int nx = (g.xcnt > 0) ? g.xcnt : g.nl[0];
-  const int xc = (g.xchunk > 0) ? g.xchunk : ps_pick_xc((const void *) LB200_PS_KERNEL<3>, smem, gz*gy, nx, fill);
+  const int xc = (g.xchunk > 0) ? g.xchunk : ps_pick_xc((const void *) LB200_PS_KERNEL<3>, PS_NT, smem, gz*gy, nx, fill);
   dim3 grd(gz, gy, (nx + xc - 1)/xc);
   if (sp.order == 1)      LB200_PS_KERNEL<1><<<grd, blk, smem, st>>>(g, sp, xc, phi, u, grad, delsq, force, phinew);
   else if (sp.order == 2) LB200_PS_KERNEL<2><<<grd, blk, smem, st>>>(g, sp, xc, phi, u, grad, delsq, force, phinew);
@@ -2339,6 +2349,7 @@ int launch_zero_outside(cudaStream_t st, const Lb200Geom & g, int ncomp, double 
   return 1;
 }
 
+#include "lb200_fused.cuh"
 #include "lb200_le.cuh"
 #include "lb200_lc.cuh"
 
@@ -2379,4 +2390,5 @@ const Lb200Kernels LB200_TABLE = {
   launch_lc_force_be,
   launch_f_convert,
   launch_collide_f32,
+  launch_step_fused,
 };

@@ -169,6 +169,13 @@ struct Lb200Kernels {
   int (*f_convert)(cudaStream_t, const Lb200Geom &, int to_f32, double * f64, float * f32);
   int (*collide_f32)(cudaStream_t, const Lb200Geom &, const Lb200CollideDev &, const float * fsrc, float * fdst,
 		     const double * force, double * rho, double * u);
+  // the whole binary-fluid time step in ONE sweep (lb200_fused.cuh): phi sector + pull-stream + collision of the
+  // same plane, the force never stored (force / rho / grad / delsq arrays written only when !skip_diag).  u_in and
+  // u_out must be different buffers.  Returns 0 without launching when this build has no such kernel (strict
+  // mode, compensated Cahn-Hilliard update): the caller then runs phi_sector + collide.
+  int (*step_fused)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, const Lb200CollideDev &,
+		    const double * phi, const double * u_in, const double * fsrc, double * fdst, double * grad,
+		    double * delsq, double * force, double * phinew, double * rho, double * u_out);
 };
 
 extern const Lb200Kernels lb200_kernels_fast;

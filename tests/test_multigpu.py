@@ -57,6 +57,25 @@ def test_lees_edwards_slabs_match_single_domain_oracle(le, peer, fast):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("peer", [1, 0])
+def test_one_kernel_step_on_slabs_matches_single_domain_oracle(peer):
+    """fast mode, no planes: the one-kernel step (LB200_KNOB_FUSED; TMA boxes of f read the x halo planes WITH their y / z
+    rims, which the neighbour's kernel stores over NVLink, or which NCCL brings) over 2 (4) GPUs, mixed with the
+    individual entry points, within tolerance of the undecomposed oracle"""
+    n = ngpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29539", os.path.join(HERE, "multigpu_parity.py"),
+           "111", "0", str(peer), "1", "0", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+    assert "MISMATCH" not in r.stdout and "OK" in r.stdout
+
+
+@pytest.mark.gpu
 def test_liquid_crystal_slabs_match_single_domain_oracle():
     """liquid crystal (Q tensor + Beris-Edwards) on x-slabs: lb200_step_lc and the individual entry points over
     2 (4) GPUs == the undecomposed liquid-crystal oracle, bit for bit (strict mode, NCCL x-planes of q, u, f)."""
