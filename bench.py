@@ -324,6 +324,89 @@ def check_decomposition(lb, dist, torch, rank, local_rank, world, nsteps=8, nxl=
     return out
 
 
+def secondary_block(lb, torch, dist, rank, local_rank, world, steps=20, warmup=3):
+    """The other BASELINE / SURVEY configurations, measured in the same run (device-resident, CUDA events on the library's
+    stream, max over ranks): short, so that the default bench stays within minutes.  Each entry: lattice per GPU, ms per step,
+    whole-job MLUPS, SURVEY's algorithmic bytes per site and the fraction of the measured HBM peak they amount to."""
+    import numpy as np
+    from ludwig_b200.initial import lc_twist_q
+    peak, _ = measured_peaks()
+    wv = np.array([12.0] + [2.0 if sum(abs(c) for c in cv) == 1 else 1.0 for cv in CV19[1:]]) / 36.0
+    out = {}
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run(name, nlocal, b_alg, note, kind="binary", math=None, decomposed=True, **kw):
+        try:
+            w = world if decomposed else 1
+            if not decomposed and rank != 0:
+                return
+            sim = lb.Lb200(nlocal, nhalo=(1 if kind == "single" else 2), have_phi=(kind == "binary"), have_q=(kind == "lc"),
+                           math=lb.MATH_FAST if math is None else math, device=local_rank, cart_size=w, cart_rank=(rank if decomposed else 0), **kw)
+            if w > 1:
+                ids = [sim.nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                sim.nccl_init(ids[0], w, rank)
+            f = np.empty((19, sim.nsites_lb))
+            f[...] = wv[:, None]
+            sim.put(lb.F, f)
+            del f
+            rng = np.random.default_rng(99 + rank)
+            cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA if kind != "lc" else 0.1)
+            if kind == "binary":
+                phi = np.zeros((1, sim.nsites))
+                sim.interior(phi)[...] = 0.05 * (rng.random((1,) + tuple(nlocal)) - 0.5)
+                sim.put(lb.PHI, phi)
+                sp = lb.SymmParam.make(adv_order=ADV_ORDER, **BINARY)
+                step = lambda k: sim.step(cp, sp, k)
+            elif kind == "lc":
+                q = np.array(lc_twist_q(nlocal, 2, LC["q0"], 1.0 / 3.0, 2))
+                sim.interior(q)[...] += 0.01 * (rng.random((5,) + tuple(nlocal)) - 0.5)
+                sim.put(lb.Q, q)
+                lc = lb.LcParam.make(adv_order=3, **LC)
+                step = lambda k: sim.step_lc(cp, lc, k)
+            else:
+                step = lambda k: sim.step(cp, None, k)
+            stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local_rank))
+            step(warmup)
+            sim.sync()
+            if dist is not None and decomposed:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step(steps)
+            e1.record(stream)
+            sim.sync()
+            ms = e0.elapsed_time(e1)
+            if decomposed:
+                ms = max_over_ranks(ms)
+            sites = float(nlocal[0]) * nlocal[1] * nlocal[2]
+            mlups = sites * w * steps / (ms * 1e-3) / 1e6
+            out[name] = {"lattice_per_gpu": list(nlocal), "n_gpus": w, "ms_per_step": ms / steps, "mlups": mlups,
+                         "algorithmic_bytes_per_site": b_alg, "frac_of_hbm_peak": mlups / w * 1e6 * b_alg / 1e9 / peak,
+                         "exchange": sim.exchange_mode(), "note": note}
+            sim.close()
+        except Exception as exc:                 # a secondary line never sinks the headline
+            out[name] = {"failed": str(exc)}
+
+    n = 256
+    run("binary_256_strict", (n, n, n), 496.0, "the headline workload in the bit-exact arithmetic mode (two kernels per step)", math=lb.MATH_STRICT)
+    run("single_fluid_d3q19_256", (n, n, n), 360.0, "config 1 family at 256^3 per GPU: MRT(M10) pull-stream-collide, one kernel per step", kind="single")
+    run("single_fluid_d3q19_64", (64, 64, 64), 360.0, "BASELINE config 1 (64^3, one GPU): launch-latency bound", kind="single", decomposed=False)
+    run("liquid_crystal_128", (128, 128, 128), 672.0, "BASELINE config 4: Q tensor + Beris-Edwards + D3Q19, 128^3 per GPU (weak)", kind="lc")
+    if (2 * n) % world == 0 and 8 % world == 0:
+        run("binary_strong_512x256x256", (2 * n // world, n, n), 496.0, "SURVEY 8(d) config 3, strong scaling: 512x256x256 over all GPUs")
+        run("lees_edwards_512x256x256", (2 * n // world, n, n), 496.0,
+            "BASELINE config 5: sheared binary fluid, 512x256x256 over all GPUs, 8 Lees-Edwards planes, plane speed 0.05",
+            le_nplanes=8, le_uy=0.05)
+    return out
+
+
 def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -523,6 +606,10 @@ def run_ours(args, rank, local_rank, world):
         except Exception as exc:
             check["multi_gpu_check"] = f"failed: {exc}"
 
+    secondary = None
+    if args.secondary:
+        secondary = secondary_block(lb, torch, dist, rank, local_rank, world)
+
     if rank == 0:
         line = {
             "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
@@ -576,6 +663,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "check": check,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
 
@@ -762,6 +850,8 @@ def main():
                     help="SMs of the phi-sector partition (LB200_KNOB_PIPE_SMS)")
     ap.add_argument("--lc", action="store_true", help="secondary workload: liquid crystal (BASELINE config 4), --size 128 unless given")
     ap.add_argument("--le", type=int, default=0, help="Lees-Edwards planes per GPU (0: none, the headline workload)")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the `secondary` block (strict mode, single fluid, liquid crystal, strong scaling, Lees-Edwards)")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: a fixed (2*size) x size x size lattice over all GPUs (default: weak, size^3 per GPU)")
     args = ap.parse_args()

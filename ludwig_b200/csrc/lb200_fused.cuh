@@ -69,6 +69,13 @@ struct FuK {                                 // per-thread / per-CTA constants
   double * peer_f_lo, * peer_f_hi, * peer_u_lo, * peer_u_hi;
 };
 
+// c_x + 1 (a = 0) or c_y + 1 (a = 1) of the 19 velocities, two bits each
+__host__ __device__ constexpr unsigned long long fu_cbits(int a) {
+  unsigned long long b = 0;
+  for (int p = 0; p < 19; p++) b |= (unsigned long long) (CV19[p][a] + 1) << (2*p);
+  return b;
+}
+
 __device__ __forceinline__ unsigned int fu_smem_u32(const void * p) { return (unsigned int) __cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void fu_mbar_init(unsigned long long * bar, unsigned int count) {
@@ -354,9 +361,7 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
 	for (int pp = 0; pp < 2; pp++) {
 	  const int p = ty + pp*BY;
 	  if (p < 19) {
-	    int cx = 0, cy = 0;
-#pragma unroll
-	    for (int i = 0; i < 19; i++) if (i == p) { cx = CV19[i][0]; cy = CV19[i][1]; }
+	    const int cx = (int) ((fu_cbits(0) >> (2*p)) & 3ull) - 1, cy = (int) ((fu_cbits(1) >> (2*p)) & 3ull) - 1;
 	    fu_tma_box(&sm.f[st][p][0], &fmap, k.kbase, k.jrow0 - cy, ps_wrap(m - cx, k.nlx, k.wx) + k.nh - 1, p, &sm.full[st]);
 	  }
 	}
