@@ -1,0 +1,128 @@
+"""the drop-in boundary, proven with the reference's OWN callers.
+
+integration/Makefile (run where the reference source tree exists; outputs travel to the GPU box like oracle/_ref) links
+the reference's unmodified objects -- src/ludwig.c, the run-time set-up, statistics, I/O; tests/unit/*.c -- with
+integration/ludwig_b200_shim.c: every call they make to a hot-path entry point (lb_collide, lb_propagation, lb_halo,
+field_halo, field_grad_compute, phi_force_calculation, phi_cahn_hilliard, hydro_*_zero, the *_memcpy family ...) is
+re-routed by ld --wrap to the C-ABI of libludwig_b200.so.  Here:
+
+  * Ludwig_b200.exe runs regression-style input files (the keys the reference's own parser reads) on the GPU, and its
+    log -- the reference's own statistics code printing what it copied back from the device -- is compared with the
+    log of Ludwig_soa.exe (the same objects without the shim, i.e. the reference itself, run on the host cores of the same
+    box) under the rules of the reference's tests/test-diff.sh + tests/awk-fp-diff.sh: version / timer / compiler lines
+    dropped, numbers equal within 1e-12 absolute;
+  * unit_b200.exe runs the reference's unit-test suites of the hot path (tests/unit/test_prop.c, test_lb_data.c,
+    test_field.c, test_hydro.c, ... compiled unchanged) with the library underneath: their own assert()s are the check.
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "integration", "_ref")
+
+# input files in the reference's own format (key value), restated here: the configuration of
+# tests/regression/d3q19-short/serial-spin-fd1.inp (BASELINE config 2 at 64^3) and relatives
+SPINODAL = {
+    "N_cycles": "10", "size": "64_64_64", "viscosity": "0.00625", "ghost_modes": "off",
+    "free_energy": "symmetric", "A": "-0.00625", "B": "0.00625", "K": "0.004", "phi0": "0.0",
+    "phi_initialisation": "spinodal", "mobility": "1.25", "fd_gradient_calculation": "3d_27pt_fluid",
+    "fd_advection_scheme_order": "1", "colloid_init": "no_colloids", "boundary_walls": "0_0_0",
+    "periodicity": "1_1_1", "freq_statistics": "10", "config_at_end": "no", "random_seed": "8361235",
+}
+CASES = {
+    "spinodal_order1": SPINODAL,                                                   # serial-spin-fd1
+    "spinodal_order3_trt": dict(SPINODAL, size="32_48_40", fd_advection_scheme_order="3", N_cycles="20", freq_statistics="5",
+                                lb_relaxation_scheme="trt", force="0.00001_0.0_-0.00002"),
+    "spinodal_7pt_bgk": dict(SPINODAL, size="32_32_32", fd_gradient_calculation="3d_7pt_fluid", fd_advection_scheme_order="2",
+                             lb_relaxation_scheme="bgk", N_cycles="10", freq_statistics="5"),
+    "single_fluid": {"N_cycles": "20", "size": "32_32_32", "viscosity": "0.1", "free_energy": "none",
+                     "distribution_initialisation": "3d_uniform_u", "distribution_uniform_u": "0.002_0.003_0.004",
+                     "colloid_init": "no_colloids", "periodicity": "1_1_1", "freq_statistics": "10", "config_at_end": "no",
+                     "boundary_walls": "0_0_0"},
+    "lees_edwards": {"N_cycles": "10", "size": "32_32_32", "viscosity": "0.1", "free_energy": "symmetric", "A": "-0.0625",
+                     "B": "0.0625", "K": "0.04", "phi0": "0.0", "phi_initialisation": "spinodal", "mobility": "0.15",
+                     "fd_gradient_calculation": "3d_27pt_fluid", "fd_advection_scheme_order": "3", "colloid_init": "no_colloids",
+                     "periodicity": "1_1_1", "freq_statistics": "10", "config_at_end": "no", "N_LE_plane": "2",
+                     "LE_plane_vel": "0.05", "LE_init_profile": "1", "random_seed": "7361237"},   # serial-le3d-st7
+}
+
+# lines tests/test-diff.sh deletes before comparing
+DROP = re.compile(r"call\)|calls\)|Welcome|Git commit:|Compiler:|\.\.name:|\.\.version-string:|\.\.options:|Target thread model:|"
+                  r"Default threads per block|OpenMP|Note assertions|Timer|user.parameters.from|GPU INFO|SIMD vector|Start time|"
+                  r"End time|Halo type|Decomposition|Local domain|Final cell list|Final cell lengths|SVN.revision")
+NUM = re.compile(r"^[+-]?(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?$")
+TOLERANCE = 1.0e-12          # tests/awk-fp-diff.sh
+
+
+def have(exe):
+    return os.path.exists(os.path.join(BIN, exe))
+
+
+def run_exe(exe, keys, cwd, env=None):
+    with open(os.path.join(cwd, "input"), "w") as fh:
+        for k, v in keys.items():
+            fh.write(f"{k} {v}\n")
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([os.path.join(BIN, exe)], cwd=cwd, capture_output=True, text=True, timeout=600, env=e)
+    assert r.returncode == 0, (exe, r.stdout[-2000:], r.stderr[-2000:])
+    return r.stdout
+
+
+def filtered(log):
+    return [ln.rstrip() for ln in log.splitlines() if ln.strip() and not DROP.search(ln)]
+
+
+def diff_logs(a, b, tol=TOLERANCE):
+    """the reference's awk-fp-diff.sh rule: same lines, tokens equal as strings or as numbers within tol (absolute)"""
+    la, lb_ = filtered(a), filtered(b)
+    bad = []
+    if len(la) != len(lb_):
+        bad.append(f"line counts differ: {len(la)} vs {len(lb_)}")
+    for x, y in zip(la, lb_):
+        tx, ty = x.split(), y.split()
+        ok = len(tx) == len(ty)
+        if ok:
+            for p, q in zip(tx, ty):
+                if p == q:
+                    continue
+                if NUM.match(p) and NUM.match(q) and abs(float(p) - float(q)) <= tol:
+                    continue
+                ok = False
+                break
+        if not ok:
+            bad.append(f"< {x}\n> {y}")
+    return bad
+
+
+@pytest.mark.skipif(not (have("Ludwig_b200.exe") and have("Ludwig_soa.exe")), reason="integration/_ref not built (needs the reference source tree)")
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_reference_driver_runs_on_the_library(case, math, tmp_path):
+    """src/ludwig.c end to end: input parsing, initialisation, H2D, time-step loop through the library, D2H, the
+    reference's own statistics -- log equal to the reference's log under the reference's own regression-diff rules"""
+    keys = CASES[case]
+    d_gpu, d_cpu = tmp_path / "gpu", tmp_path / "cpu"
+    d_gpu.mkdir(); d_cpu.mkdir()
+    got = run_exe("Ludwig_b200.exe", keys, str(d_gpu), env={"LB200_MATH": math})
+    ref = run_exe("Ludwig_soa.exe", keys, str(d_cpu), env={"OMP_NUM_THREADS": "8"})
+    assert "Completed cycle" in got and "Ludwig finished normally" in got
+    bad = diff_logs(ref, got)
+    assert not bad, "\n".join(bad[:20])
+
+
+@pytest.mark.skipif(not have("unit_b200.exe"), reason="integration/_ref not built (needs the reference source tree)")
+def test_reference_unit_suites_pass_on_the_library(tmp_path):
+    """tests/unit/test_prop.c, test_lb_data.c, test_field.c, test_field_grad.c, test_hydro.c, test_lb_model.c, test_lb_d3q19.c,
+    test_phi_ch.c, test_fe_symmetric.c, test_le.c: compiled unchanged, hot-path calls routed to the GPU library"""
+    r = subprocess.run([os.path.join(BIN, "unit_b200.exe")], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+    assert "the reference's hot-path unit suites passed" in r.stdout
+    for suite in ("test_prop", "test_lb_data", "test_field", "test_hydro"):
+        assert re.search(rf"PASS\s+\S*{suite}\b", r.stdout), suite
