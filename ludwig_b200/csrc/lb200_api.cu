@@ -97,6 +97,8 @@ struct lb200_s {
   int u_halo_valid;
 
   int prop_pending;          // lb_propagation requested, not yet applied (fused into next collide)
+  double * halo_snap;        // snapshot of an array for halo swaps on lattices thinner than the halo
+  size_t halo_snap_size;
   int f_yz_ready;            // f_halo_stale, but the one-kernel step has stored the populations the next pull reads in the y / z halos
   int f_halo_stale;          // halo-free lb200_step: lb_halo(f) was folded into the kernels' reads and has
                              // not been applied to the halo sites of f (done on demand with the propagation)
@@ -702,7 +704,7 @@ int lb200_free(lb200_t * c) {
   cudaFree(c->le_trip); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
   for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
   cudaFree(c->f32[0]); cudaFree(c->f32[1]); cudaFree(c->csum);
-  cudaFree(c->flags); cudaFree(c->spin_err);
+  cudaFree(c->flags); cudaFree(c->spin_err); cudaFree(c->halo_snap);
   cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->slo); cudaFree(c->shi); cudaFree(c->model_d);
   for (int i = 0; i < LB200_KCLASS_MAX; i++) {
     if (c->ev[i]) { for (cudaEvent_t e : *c->ev[i]) cudaEventDestroy(e); delete c->ev[i]; }
@@ -1047,24 +1049,43 @@ int lb200_hydro_u_zero(lb200_t * c) {
   return 0;
 }
 
+// a periodic dimension thinner than the halo (the reference's 2-d runs): halo swaps then deliver pre-swap halo content,
+// so what the halos hold BEFORE a swap matters and must be what the reference's arrays hold
+static bool thin_lattice(const lb200_t * c) {
+  for (int a = 0; a < 3; a++) if (c->g.per[a] && c->g.nl[a] < c->g.nh) return true;
+  return false;
+}
+
 static int halo_field(lb200_t * c, double * data, int ncomp, int depth, int reduced, cudaStream_t st) {
   if (st == nullptr) st = c->stream;
-  // A periodic lattice thinner than the swap depth (e.g. 64 x 64 x 1 with nhalo 2): the reference's send regions then
-  // reach into the halo and what arrives is the halo's content before the swap (src/field.c:1329-1355, 1412-1531)
-  // -- not the periodic image this kernel writes.  Refuse rather than differ silently.
-  for (int a = 0; a < 3; a++) {
-    if (c->g.per[a] && c->g.nl[a] < depth)
-      return fail(LB200_EINVAL, "halo swap of depth %d on a periodic lattice of extent %d: lattices thinner than the halo are outside this build", depth, c->g.nl[a]);
+  // A periodic lattice thinner than the swap depth (e.g. 64 x 64 x 1 with nhalo 2, the reference's 2-d runs): the
+  // reference's send regions then reach into the halo, and because it packs every send buffer before it unpacks any
+  // (src/field.c:1329-1355, 1412-1531) what arrives in the outer halo layers is the halo's content from BEFORE the swap.
+  // Reproduced by reading the local sources from a snapshot of the array.
+  bool thin = false;
+  for (int a = 0; a < 3; a++) thin = thin || (c->g.per[a] && c->g.nl[a] < depth);
+  const double * snapshot = nullptr;
+  if (thin) {
+    if (c->g.remote_x && c->g.nl[0] < depth) return fail(LB200_EINVAL, "x-slabs thinner than the halo");
+    const size_t need = (size_t) ncomp*c->g.nsites;
+    if (c->halo_snap_size < need) {
+      cudaFree(c->halo_snap);
+      c->halo_snap = nullptr; c->halo_snap_size = 0;
+      if (alloc_d(&c->halo_snap, need) != 0) return LB200_ECUDA;
+      c->halo_snap_size = need;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->halo_snap, data, need*sizeof(double), cudaMemcpyDeviceToDevice, st));
+    snapshot = c->halo_snap;
   }
   ProfScope ps(c, LB200_K_HALO, st);
   int rc = exchange_x(c, st, data, ncomp, depth);
   if (rc != 0) return rc;
-  c->launches += c->k->halo(st, c->g, c->model_d, ncomp, depth, reduced, data, stage_lo(c, data), stage_hi(c, data));
+  c->launches += c->k->halo(st, c->g, c->model_d, ncomp, depth, reduced, data, stage_lo(c, data), stage_hi(c, data), snapshot);
   return 0;
 }
 
 static int u_halo_async(lb200_t * c) {
-  if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+  if (c->u_state == ZERO_PENDING || (c->u_state == INTERIOR_ONLY && thin_lattice(c))) materialise_zero(c, c->u, &c->u_state);
   int rc = halo_field(c, c->u, 3, c->g.nh, 0, nullptr);
   c->u_state = ARRAY_CLEAN;              // every halo site within nhalo has just been written
   return rc;
@@ -2480,11 +2501,15 @@ static int step_le(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev &
     rc = halo_field(c, c->phi, 1, g.nh, 0, S);                           // field_halo(phi)
     if (rc != 0) return rc;
     le_field_async(c, c->phi);                                           // field_leesedwards
-    if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+    if (c->u_state == ZERO_PENDING || (c->u_state == INTERIOR_ONLY && thin_lattice(c))) materialise_zero(c, c->u, &c->u_state);
     rc = halo_field(c, c->u, 3, g.nh, 0, S);                             // hydro_u_halo
     if (rc != 0) return rc;
     c->u_state = ARRAY_CLEAN;
     le_hydro_async(c);                                                   // hydro_lees_edwards
+    if (thin_lattice(c)) {
+      // the reference updates phi in place: its halo sites keep their content until the next swap
+      CUDA_TRY(cudaMemcpyAsync(c->phinew, c->phi, (size_t) c->g.nsites*sizeof(double), cudaMemcpyDeviceToDevice, S));
+    }
     if (fused) {
       {
 	ProfScope ps(c, LB200_K_PHI_SECTOR);
@@ -2602,7 +2627,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	else               c->launches += c->k->grad27(S, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);    // field_grad_compute
       }
       if (!c->u_halo_valid) {                                            // hydro_u_halo
-	if (c->u_state == ZERO_PENDING) materialise_zero(c, c->u, &c->u_state);
+	if (c->u_state == ZERO_PENDING || (c->u_state == INTERIOR_ONLY && thin_lattice(c))) materialise_zero(c, c->u, &c->u_state);
 	CUDA_TRY(cudaEventRecord(c->ev_main, S));
 	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));
 	rc = halo_field(c, c->u, 3, c->g.nh, 0, C);
@@ -2611,6 +2636,10 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	c->u_state = ARRAY_CLEAN;
       }
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_u, 0));
+      if (thin_lattice(c)) {
+	// the reference updates phi in place: its halo sites keep their content until the next swap
+	CUDA_TRY(cudaMemcpyAsync(c->phinew, c->phi, (size_t) c->g.nsites*sizeof(double), cudaMemcpyDeviceToDevice, S));
+      }
       if (use_ps) {
 	// field_grad_compute + phi_force_calculation + phi_cahn_hilliard
 	ProfScope ps(c, LB200_K_PHI_SECTOR);

@@ -1081,7 +1081,7 @@ int launch_propagate(cudaStream_t st, const Lb200Geom & g, const Lb200ModelDev *
 template <bool REDUCED>
 __global__ void __launch_bounds__(TPB)
 halo_shell_kernel(const Lb200Geom g, const Lb200ModelDev * __restrict__ md, int ncomp, int d,
-		  double * __restrict__ data, const double * __restrict__ xlo,
+		  double * __restrict__ data, const double * __restrict__ local_src, const double * __restrict__ xlo,
 		  const double * __restrict__ xhi, long long nx_slab, long long ny_slab,
 		  long long nz_slab) {
 
@@ -1150,8 +1150,11 @@ halo_shell_kernel(const Lb200Geom g, const Lb200ModelDev * __restrict__ md, int 
     sidx = (size_t) q*g.xs + (size_t) (sj + g.nh - 1)*g.nall[2] + (sk + g.nh - 1);
   }
   else {
+    // the site one period away.  On a lattice thinner than the swap depth that site is itself a halo site, and what the
+    // reference delivers is its content from BEFORE the swap (every send buffer is packed before any is unpacked,
+    // src/field.c:1412-1531): local_src is then a snapshot of the array, otherwise the array itself
     const int si = ic + mx*g.nl[0];
-    src = data;
+    src = local_src;
     sstride = ns;
     sidx = (size_t) ((si + g.nh - 1)*g.nall[1] + (sj + g.nh - 1))*g.nall[2] + (sk + g.nh - 1);
   }
@@ -1170,7 +1173,8 @@ halo_shell_kernel(const Lb200Geom g, const Lb200ModelDev * __restrict__ md, int 
 }
 
 int launch_halo(cudaStream_t st, const Lb200Geom & g, const Lb200ModelDev * md, int ncomp,
-		int depth, int reduced, double * data, const double * xlo, const double * xhi) {
+		int depth, int reduced, double * data, const double * xlo, const double * xhi, const double * snapshot) {
+  const double * local_src = snapshot ? snapshot : data;
   const long long ey = g.nl[1] + 2*depth;
   const long long ez = g.nl[2] + 2*depth;
   const long long nx_slab = (long long) depth*ey*ez;
@@ -1178,8 +1182,8 @@ int launch_halo(cudaStream_t st, const Lb200Geom & g, const Lb200ModelDev * md, 
   const long long nz_slab = (long long) g.nl[0]*g.nl[1]*depth;
   const long long total = 2*(nx_slab + ny_slab + nz_slab);
   const int nblk = (int) ((total + TPB - 1)/TPB);
-  if (reduced) halo_shell_kernel<true><<<nblk, TPB, 0, st>>>(g, md, ncomp, depth, data, xlo, xhi, nx_slab, ny_slab, nz_slab);
-  else         halo_shell_kernel<false><<<nblk, TPB, 0, st>>>(g, md, ncomp, depth, data, xlo, xhi, nx_slab, ny_slab, nz_slab);
+  if (reduced) halo_shell_kernel<true><<<nblk, TPB, 0, st>>>(g, md, ncomp, depth, data, local_src, xlo, xhi, nx_slab, ny_slab, nz_slab);
+  else         halo_shell_kernel<false><<<nblk, TPB, 0, st>>>(g, md, ncomp, depth, data, local_src, xlo, xhi, nx_slab, ny_slab, nz_slab);
   return 1;
 }
 

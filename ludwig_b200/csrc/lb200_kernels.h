@@ -102,8 +102,10 @@ struct Lb200Kernels {
   int (*propagate)(cudaStream_t, const Lb200Geom &, const Lb200ModelDev *, int nvel, int ndist,
 		   const double * f, double * fprime);
   // halo shell of depth d for ncomp components; reduced != 0 only for distributions (needs cv)
+  // snapshot != nullptr (lattices thinner than the swap depth): local sources are read from this copy of data taken
+  // before the swap, as the reference's pack-everything-then-unpack order delivers them
   int (*halo)(cudaStream_t, const Lb200Geom &, const Lb200ModelDev *, int ncomp, int depth,
-	      int reduced, double * data, const double * xlo, const double * xhi);
+	      int reduced, double * data, const double * xlo, const double * xhi, const double * snapshot);
   int (*grad27)(cudaStream_t, const Lb200Geom &, int ne, const double * phi, double * grad, double * delsq);
   // force = [force +] -div P(phi, grad, delsq)   (accumulate = 0: plain store)
   int (*phi_force)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, int accumulate,

@@ -635,8 +635,3 @@ def test_errors():
     with lb.Lb200((4, 4, 4), nhalo=1, nvel=27) as sim:
         with pytest.raises(lb.Lb200Error):
             sim.lb_collide(lb.CollideParam.make(lb.RELAX_TRT))
-    # a periodic lattice thinner than the halo: the reference's swap delivers pre-swap halo content there
-    # (tests/test_oracle_vs_reference.py::test_field_halo_on_lattices_thinner_than_the_halo); refused, not silently different
-    with lb.Lb200((8, 8, 1), nhalo=2, have_phi=True) as sim:
-        with pytest.raises(lb.Lb200Error):
-            sim.phi_halo()

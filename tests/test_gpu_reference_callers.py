@@ -49,6 +49,12 @@ CASES = {
                      "fd_gradient_calculation": "3d_27pt_fluid", "fd_advection_scheme_order": "3", "colloid_init": "no_colloids",
                      "periodicity": "1_1_1", "freq_statistics": "10", "config_at_end": "no", "N_LE_plane": "2",
                      "LE_plane_vel": "0.05", "LE_init_profile": "1", "random_seed": "7361237"},   # serial-le3d-st7
+    # a 2-d run: the lattice is thinner than the halo (the configuration of tests/regression/d3q19/pmpi08-le2d-fd1, 100 of its steps)
+    "lees_edwards_2d": {"N_cycles": "100", "size": "64_64_1", "viscosity": "0.1", "free_energy": "symmetric", "A": "-0.0625",
+                        "B": "0.0625", "K": "0.04", "phi0": "0.0", "phi_initialisation": "spinodal", "mobility": "0.15",
+                        "fd_gradient_calculation": "3d_27pt_fluid", "fd_advection_scheme_order": "3", "colloid_init": "no_colloids",
+                        "periodicity": "1_1_1", "freq_statistics": "50", "config_at_end": "no", "N_LE_plane": "2",
+                        "LE_plane_vel": "0.05", "LE_init_profile": "1", "random_seed": "-7361237"},
 }
 
 # lines tests/test-diff.sh deletes before comparing

@@ -406,7 +406,7 @@ def test_binary_time_steps_7pt_gradient(order, nlocal, nvel):
 def test_field_halo_on_lattices_thinner_than_the_halo(nlocal):
     """nlocal[d] < nhalo (the reference's own pmpi08-le2d-fd1 regression runs 64 x 64 x 1 with nhalo 2): every send buffer
     is packed before any is unpacked (src/field.c:1412-1531), so the outer halo layer receives the halo's content from
-    BEFORE the swap; the oracle reproduces that bit for bit (the CUDA library refuses such lattices: LB200_EINVAL)."""
+    BEFORE the swap; the oracle reproduces that bit for bit (and so does the CUDA library: tests/test_gpu_thin.py)."""
     orc = Oracle(nlocal, nhalo=2)
     rng = np.random.default_rng(31)
     with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=2, eta_shear=ETA, **BINARY) as s:
