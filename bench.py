@@ -324,6 +324,37 @@ def check_decomposition(lb, dist, torch, rank, local_rank, world, nsteps=8, nxl=
     return out
 
 
+def numa_bind(torch, local_rank):
+    """Pin this process to the CPUs of the NUMA node of its GPU (sysfs), so that host buffers allocated and first touched
+    next are local to the GPU's PCIe root.  Returns what numa_unbind needs; (None, None) where the topology is not exposed."""
+    try:
+        old = os.sched_getaffinity(0)
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return (None, None)
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= old
+        if not cpus:
+            return (None, None)
+        os.sched_setaffinity(0, cpus)
+        return (old, node)
+    except Exception:
+        return (None, None)
+
+
+def numa_unbind(state):
+    if state and state[0] is not None:
+        try:
+            os.sched_setaffinity(0, state[0])
+        except Exception:
+            pass
+
+
 def secondary_block(lb, torch, dist, rank, local_rank, world, steps=20, warmup=3):
     """The other BASELINE / SURVEY configurations, measured in the same run (device-resident, CUDA events on the library's
     stream, max over ranks): short, so that the default bench stays within minutes.  Each entry: lattice per GPU, ms per step,
@@ -441,7 +472,10 @@ def run_ours(args, rank, local_rank, world):
         sim.set_knob(lb.KNOB_PIPE, args.pipe)
     ns = sim.nsites
     nall = sim.nall
-    # pinned host state (the reference's host arrays: lb->f, phi->data, hydro->u, hydro->rho)
+    # pinned host state (the reference's host arrays: lb->f, phi->data, hydro->u, hydro->rho), allocated and first touched
+    # on the NUMA node this GPU hangs off (8 ranks uploading 2.8 GB each through one socket's memory is what limits the
+    # end-to-end figure at N = 8); the affinity is restored afterwards: the CPU baseline wants every core
+    numa = numa_bind(torch, local_rank)
     h_f = torch.empty((19, sim.nsites_lb), dtype=torch.float64, pin_memory=True)
     h_phi = torch.empty((1, ns), dtype=torch.float64, pin_memory=True)
     h_u = torch.empty((3, ns), dtype=torch.float64, pin_memory=True)
@@ -455,6 +489,8 @@ def run_ours(args, rank, local_rank, world):
     pv = h_phi.numpy()[0, :sim.nsites_lb].reshape(nall)
     pv[nhalo:-nhalo, nhalo:-nhalo, nhalo:-nhalo] = 0.05 * (rng.random(nlocal) - 0.5)
 
+    h_u.zero_(); h_rho.zero_()
+    numa_unbind(numa)
     cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA)
     sp = lb.SymmParam.make(adv_order=ADV_ORDER, **BINARY)
     stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local_rank))
@@ -634,7 +670,8 @@ def run_ours(args, rank, local_rank, world):
                                              if lazy else "every step"),
                        "l2": "inputs (2.8 GB of lattice state per sweep) exceed the 126 MB L2; no flush needed",
                        "e2e_protocol": "pinned-host f+phi -> device, K steps, phi+u+rho -> pinned host "
-                                       "(the reference's own lb_memcpy/field_memcpy usage, src/ludwig.c:501-506, 985)"},
+                                       "(the reference's own lb_memcpy/field_memcpy usage, src/ludwig.c:501-506, 985)",
+                       "host_buffers_numa_node": (numa[1] if numa else None)},
             "roofline": ({"bound": "hbm", "kernel": "step_fused (27pt gradient + stress-divergence force + Cahn-Hilliard + pull-stream + MRT "
                                                     "collision in one sweep; populations by TMA tensor copies)",
                           "achieved": fu_ach, "peak": peak, "unit": "GB/s", "frac": (fu_ach / peak if fu_ach else None),

@@ -99,7 +99,8 @@ struct lb200_s {
   int prop_pending;          // lb_propagation requested, not yet applied (fused into next collide)
   double * halo_snap;        // snapshot of an array for halo swaps on lattices thinner than the halo
   size_t halo_snap_size;
-  int f_yz_ready;            // f_halo_stale, but the one-kernel step has stored the populations the next pull reads in the y / z halos
+  int fused_ready;           // the last thing that touched the lattice was a one-kernel step: it left the y / z (and peer x) halos of
+                             // f (the populations the next pull reads), phi (depth nhalo) and u (depth 1) filled for the next one
   int f_halo_stale;          // halo-free lb200_step: lb_halo(f) was folded into the kernels' reads and has
                              // not been applied to the halo sites of f (done on demand with the propagation)
   int wrap_x_valid;          // halo-free lb200_step on slabs: x-planes of phi, u_x, f already exchanged
@@ -824,6 +825,7 @@ static int do_memcpy(lb200_t * c, int array, double * host, int kind, int async)
   size_t ncomp = 0;
   int rc = array_info(c, array, &dev, &ncomp);
   if (rc != 0) return rc;
+  c->fused_ready = 0;          // uploads replace the state; downloads materialise zeros / a pending propagation in the halos
 
   if (array == LB200_F) {
     rc = materialise_propagation(c);
@@ -1034,7 +1036,7 @@ int lb200_nccl_comm_destroy(void * comm) {
 // ---- operators ------------------------------------------------------------------------------------
 
 #define CTX_ENTER(c) do { if ((c) == nullptr) return fail(LB200_EINVAL, "null context"); \
-  CUDA_TRY(cudaSetDevice((c)->device)); (c)->phi_halo_valid = 0; (c)->u_halo_valid = 0; (c)->wrap_x_valid = 0; } while (0)
+  CUDA_TRY(cudaSetDevice((c)->device)); (c)->phi_halo_valid = 0; (c)->u_halo_valid = 0; (c)->wrap_x_valid = 0; (c)->fused_ready = 0; } while (0)
 #define CTX_LEAVE_SYNC(c) do { CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaStreamSynchronize((c)->stream)); return 0; } while (0)
 
 int lb200_hydro_f_zero(lb200_t * c) {
@@ -1773,9 +1775,14 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       }
       // the TMA boxes of the populations read the y / z halos (and the rims of the x halo planes): valid after a
       // one-kernel step, else one lb_halo brings them up to date
-      if (c->f_halo_stale && !c->f_yz_ready) {
+      if (!c->fused_ready) {
 	rc = ensure_f_halo(c);
+	if (rc == 0) rc = halo_field(c, c->phi, 1, c->g.nh, 0, S);
 	if (rc != 0) return rc;
+	if (c->u_state != ARRAY_CLEAN) materialise_zero(c, c->u, &c->u_state);
+	rc = halo_field(c, c->u, 3, c->g.nh, 0, S);
+	if (rc != 0) return rc;
+	c->f_halo_stale = 1;                 // (still true for the reference's view: only what the pull reads is kept up to date)
       }
       // the phi sector of other CTAs (and of the neighbour GPUs) reads u(t-1) while this kernel writes u(t)
       double * u_out = (c->u == c->u_alloc[0]) ? c->u_alloc[1] : c->u_alloc[0];
@@ -1799,7 +1806,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	c->u = u_out;
 	c->u_state = INTERIOR_ONLY;
 	c->prop_pending = 1;
-	c->f_halo_stale = 1; c->f_yz_ready = 1;
+	c->f_halo_stale = 1; c->fused_ready = 1;
 	if (peer) {
 	  c->n_ps++; c->n_col++;
 	  c->launches += c->k->signal(S, c->hi.flags + FLAG_PS_LO, c->lo.flags + FLAG_PS_HI, c->n_ps);
@@ -1910,7 +1917,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     }
     if (le) le_lb_bc_async(c);                                           // lb_data_apply_le_boundary_conditions
     c->prop_pending = 1;                                                 // lb_halo; lb_propagation (lazy)
-    c->f_halo_stale = 1; c->f_yz_ready = 0;
+    c->f_halo_stale = 1; c->fused_ready = 0;
     if (peer) {
       c->n_col++;
       c->launches += c->k->signal(S, c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
@@ -2161,7 +2168,7 @@ static int step_pipe(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   c->force_state = INTERIOR_ONLY;
   c->u_state = INTERIOR_ONLY;
   c->prop_pending = 1;
-  c->f_halo_stale = 1; c->f_yz_ready = 0;
+  c->f_halo_stale = 1; c->fused_ready = 0;
   c->phi_halo_valid = 0;
   c->u_halo_valid = 0;
   c->wrap_x_valid = 1;
@@ -2434,7 +2441,7 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
       c->u = u_out;
       c->u_state = INTERIOR_ONLY;
       c->prop_pending = 1;                                               // lb_halo; lb_propagation (lazy)
-      c->f_halo_stale = 1; c->f_yz_ready = 0;
+      c->f_halo_stale = 1; c->fused_ready = 0;
       if (remote) {
 	CUDA_TRY(cudaEventRecord(c->ev_main, S));
 	CUDA_TRY(cudaStreamWaitEvent(C, c->ev_main, 0));

@@ -41,21 +41,24 @@ template <int BY> struct FuGeo {
   static constexpr int PY = BY + 2;
   static constexpr int PN = PZ*PY;
   static constexpr int FBLK = ((TY*FU_ROW + 15)/16)*16;   // doubles per staged population (128-byte aligned blocks)
+  static constexpr int PSLOT = ((PN + 15)/16)*16;         // doubles per staged phi plane [PY][34]
+  static constexpr int USLOT = ((BY*FU_ROW + 15)/16)*16;  // doubles per staged velocity-component plane [BY][34]
 };
 
 template <int BY> struct FuShared {
   double f[FU_NSTAGE][19][FuGeo<BY>::FBLK];  // staged boxes [TY rows][34] of the pulled populations
-  double phi[PF_RING][FuGeo<BY>::PN];        // ring of phi planes, slot = (plane - first plane) % 6
+  double phi[PF_RING][FuGeo<BY>::PSLOT];     // ring of phi planes [PY rows][34], slot = (plane - first plane) % 6
+  double u[3][2][FuGeo<BY>::USLOT];          // u_y, u_z planes [BY rows][34], slot = plane % 3
+  double ux[3][FuGeo<BY>::USLOT];            // u_x, slot = plane % 3
   double g[2][6][FuGeo<BY>::NT];             // Pxy, Pyy, Pyz, Pxz, Pzz, mu of a plane
-  double u[3][2][FuGeo<BY>::NT];             // u_y, u_z, slot = plane % 3
-  double ux[3][FuGeo<BY>::NT];               // u_x, slot = plane % 3
   double fl[2][2][FuGeo<BY>::NT];            // y and z face fluxes (face between the site and site+1)
-  unsigned long long full[FU_NSTAGE];        // mbarriers: the bytes of a stage have landed
+  unsigned long long full[FU_NSTAGE];        // mbarriers: the populations of a stage have landed
+  unsigned long long pl[PF_RING];            // mbarriers: the phi / u planes issued at phase q have landed
 };
 
 struct FuK {                                 // per-thread / per-CTA constants
-  int pc, tid, col, scol, pcol0, pcol1, e0, e1;
-  bool has_e1, valid_g, out_site, face_row, own_g, skip_diag, odd, has_sites;
+  int pc, tid, col, scol;
+  bool valid_g, out_site, face_row, own_g, skip_diag, odd, has_sites;
   int fmode;                                 // tuning experiments: 0 bulk copies, 1 direct loads, 2 no loads (timing only)
   int xs, nh, nlx, wx, i0, i1;
   size_t ns;
@@ -64,6 +67,9 @@ struct FuK {                                 // per-thread / per-CTA constants
   int kbase, jrow0;                          // box origin: array z index / array row index of the first interior row
   int sy, sz;                                // +1: the site's image lies one period up (site on the low boundary), -1: down, 0: none
   int imy, imz;                              // element offsets of those images
+  int py, pz;                                // the same for the nhalo-deep images of phi (sites within nhalo of a boundary)
+  int tu;                                    // own element of a staged velocity plane
+  int imy_unit, imz_unit;                    // one period in y / z (elements)
   double M, kappa, a, b, mg0, mg1, mg2, wz;
   double * peer_lo, * peer_hi;               // neighbour GPUs' phi' arrays (nullptr: none)
   double * peer_f_lo, * peer_f_hi, * peer_u_lo, * peer_u_hi;
@@ -99,6 +105,11 @@ __device__ __forceinline__ void fu_tma_box(void * dst, const CUtensorMap * map, 
 					   unsigned long long * bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
 	       :: "r"(fu_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(fu_smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void fu_tma_box3(void * dst, const CUtensorMap * map, int c0, int c1, int c2, unsigned long long * bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+	       :: "r"(fu_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(fu_smem_u32(bar)) : "memory");
 }
 
 template <int PZ>
@@ -166,6 +177,12 @@ __device__ __forceinline__ void fu_collide(FuShared<BY> & sm, const FuK & k, con
   // the low boundary has its image one period up, where the populations with c = -1 in that dimension are pulled from.
   if ((k.sy | k.sz) != 0) {
 #pragma unroll
+    for (int ia = 0; ia < 3; ia++) {
+      if (k.sy != 0) u_out[ia*k.ns + s + k.imy] = uu[ia];
+      if (k.sz != 0) u_out[ia*k.ns + s + k.imz] = uu[ia];
+      if (k.sy != 0 && k.sz != 0) u_out[ia*k.ns + s + k.imy + k.imz] = uu[ia];
+    }
+#pragma unroll
     for (int p = 0; p < 19; p++) {
       const bool my = (CV19[p][1] != 0) && (CV19[p][1] == -k.sy);
       const bool mz = (CV19[p][2] != 0) && (CV19[p][2] == -k.sz);
@@ -204,7 +221,8 @@ __device__ __forceinline__ void fu_collide(FuShared<BY> & sm, const FuK & k, con
 
 template <int ORDER, bool GHOST, int BY>
 __global__ void __launch_bounds__(FuGeo<BY>::NT, 1)
-step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, const Lb200SymmDev sp,
+step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap phimap,
+		  const __grid_constant__ CUtensorMap umap, const Lb200Geom g, const Lb200SymmDev sp,
 		  const Lb200CollideDev cp, int xc, int fmode, int skew,
 		  const double * __restrict__ phi, const double * __restrict__ u,
 		  const double * __restrict__ fsrc, double * __restrict__ fdst,
@@ -264,21 +282,11 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
   k.sz = (g.wrap[2] && kc == 1) ? 1 : ((g.wrap[2] && kc == g.nl[2]) ? -1 : 0);
   if (g.nl[1] == 1) k.sy = 0;                      // (a one-site dimension: the fused step is not used, see the launcher)
   k.imy = k.sy*g.nl[1]*ys; k.imz = k.sz*g.nl[2];
-  if (!k.out_site) { k.sy = 0; k.sz = 0; }
-
-  // cooperative phi plane load: element e of the (PY x PZ) tile <-> (jbase-1+r, kbase-1+c)
-  k.e0 = k.tid; k.e1 = k.tid + G::NT;
-  {
-    const int r0 = k.e0/G::PZ, c0 = k.e0%G::PZ;
-    const int r1 = k.e1/G::PZ, c1 = k.e1%G::PZ;
-    const int pj0 = ps_wrap(min(jbase - 1 + r0, g.nl[1] + nh), g.nl[1], g.wrap[1]);
-    const int pk0 = ps_wrap(min(kbase - 1 + c0, g.nl[2] + nh), g.nl[2], g.wrap[2]);
-    const int pj1 = ps_wrap(min(jbase - 1 + r1, g.nl[1] + nh), g.nl[1], g.wrap[1]);
-    const int pk1 = ps_wrap(min(kbase - 1 + c1, g.nl[2] + nh), g.nl[2], g.wrap[2]);
-    k.pcol0 = (pj0 + nh - 1)*ys + (pk0 + nh - 1);
-    k.pcol1 = (pj1 + nh - 1)*ys + (pk1 + nh - 1);
-    k.has_e1 = (k.e1 < G::PN);
-  }
+  k.py = (g.wrap[1] && jc <= nh) ? 1 : ((g.wrap[1] && jc > g.nl[1] - nh) ? -1 : 0);
+  k.pz = (g.wrap[2] && kc <= nh) ? 1 : ((g.wrap[2] && kc > g.nl[2] - nh) ? -1 : 0);
+  if (!k.out_site) { k.sy = 0; k.sz = 0; k.py = 0; k.pz = 0; }
+  k.tu = ty*FU_ROW + tz + 1;
+  k.imy_unit = g.nl[1]*ys; k.imz_unit = g.nl[2];
 
   const int istart = k.i0 - 2;
 
@@ -288,25 +296,34 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
   if (k.tid == 0) {
 #pragma unroll
     for (int s = 0; s < FU_NSTAGE; s++) fu_mbar_init(&sm.full[s], (unsigned int) BY);
+#pragma unroll
+    for (int s = 0; s < PF_RING; s++) fu_mbar_init(&sm.pl[s], 1u);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
 
+  __syncthreads();                                 // the barriers are initialised
+
+  // array coordinates of the staged planes: phi rows jbase-1 .. jbase+BY (array row jbase + nh - 2), u rows jbase .. jbase+BY-1
+  const int prow = jbase + nh - 2, urow = jbase + nh - 1;
+  const bool issuer = (k.tid == 32*(BY - 1));      // lane 0 of the last warp (an apron row: no collision work)
+
   // prologue: phi planes istart .. istart+3 -> ring slots 0 .. 3; u_x(istart+1), u_x(istart+2) -> slots 1, 2;
   // u_y, u_z (istart+1) -> slot 1.  (The first plane-step prefetches phi(istart+4), u_x(istart+3), u_y/u_z(istart+2).)
+  // They use barrier pl[5], whose first regular use is five plane-steps away.
+  if (issuer) {
+    fu_mbar_expect(&sm.pl[5], (unsigned int) (8*(4*G::PY*FU_ROW + 4*BY*FU_ROW)));
 #pragma unroll
-  for (int d = 0; d < 4; d++) {
-    const int xo = (ps_wrap(istart + d, k.nlx, k.wx) + nh - 1)*k.xs;
-    pf_cp_async8(&sm.phi[d][k.e0], phi + xo + k.pcol0);
-    if (k.has_e1) pf_cp_async8(&sm.phi[d][k.e1], phi + xo + k.pcol1);
-    if (d == 1 || d == 2) pf_cp_async8(&sm.ux[d][k.tid], u + xo + k.col);
-    if (d == 1) {
-      pf_cp_async8(&sm.u[1][0][k.tid], u + k.ns + xo + k.col);
-      pf_cp_async8(&sm.u[1][1][k.tid], u + 2*k.ns + xo + k.col);
+    for (int d = 0; d < 4; d++) {
+      const int xp = ps_wrap(istart + d, k.nlx, k.wx) + nh - 1;
+      fu_tma_box3(&sm.phi[d][0], &phimap, k.kbase, prow, xp, &sm.pl[5]);
+      if (d == 1 || d == 2) fu_tma_box(&sm.ux[d][0], &umap, k.kbase, urow, xp, 0, &sm.pl[5]);
+      if (d == 1) {
+	fu_tma_box(&sm.u[1][0][0], &umap, k.kbase, urow, xp, 1, &sm.pl[5]);
+	fu_tma_box(&sm.u[1][1][0], &umap, k.kbase, urow, xp, 2, &sm.pl[5]);
+      }
     }
   }
-  pf_cp_async_commit();
-  pf_cp_async_wait<0>();
-  __syncthreads();
+  fu_mbar_wait(&sm.pl[5], 0u);
 
   PfRegs r;
   r.uxc = 0.0;                                     // u_x(n): not used before n = i0 - 1
@@ -335,21 +352,20 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
     const int u1 = (u0 + 1 >= 3) ? u0 - 2 : u0 + 1;
     const int u2 = (u0 + 2 >= 3) ? u0 - 1 : u0 + 2;
 
-    // ---- 1. asynchronous prefetch: phi(n+4), u_x(n+3), u_y / u_z (n+2); the source rows of the populations of plane n+1 ----
+    // ---- 1. asynchronous prefetch (TMA): phi(n+4), u_x(n+3), u_y / u_z (n+2); the populations of plane n+1 ----
     {
-      const int xo2 = (ps_wrap(n + 2, k.nlx, k.wx) + k.nh - 1)*k.xs;
-      const int xo3 = (ps_wrap(n + 3, k.nlx, k.wx) + k.nh - 1)*k.xs;
-      const int xo4 = (ps_wrap(n + 4, k.nlx, k.wx) + k.nh - 1)*k.xs;
-      if (n + 4 <= k.i1 + 2) {
-	pf_cp_async8(&sm.phi[q4][k.e0], phi + xo4 + k.pcol0);
-	if (k.has_e1) pf_cp_async8(&sm.phi[q4][k.e1], phi + xo4 + k.pcol1);
+      if (issuer) {
+	const bool do_phi = (n + 4 <= k.i1 + 2), do_ux = (n + 3 <= k.i1 + 1), do_uyz = (n + 2 <= k.i1);
+	// (the prologue's use of pl[5] was phase 0 of that barrier: the regular uses start one phase later)
+	fu_mbar_expect(&sm.pl[q], (unsigned int) (8*((do_phi ? G::PY*FU_ROW : 0) + (do_ux ? BY*FU_ROW : 0) + (do_uyz ? 2*BY*FU_ROW : 0))));
+	if (do_phi) fu_tma_box3(&sm.phi[q4][0], &phimap, k.kbase, prow, ps_wrap(n + 4, k.nlx, k.wx) + k.nh - 1, &sm.pl[q]);
+	if (do_ux) fu_tma_box(&sm.ux[u0][0], &umap, k.kbase, urow, ps_wrap(n + 3, k.nlx, k.wx) + k.nh - 1, 0, &sm.pl[q]);
+	if (do_uyz) {
+	  const int xp = ps_wrap(n + 2, k.nlx, k.wx) + k.nh - 1;
+	  fu_tma_box(&sm.u[u2][0][0], &umap, k.kbase, urow, xp, 1, &sm.pl[q]);
+	  fu_tma_box(&sm.u[u2][1][0], &umap, k.kbase, urow, xp, 2, &sm.pl[q]);
+	}
       }
-      if (n + 3 <= k.i1 + 1) pf_cp_async8(&sm.ux[u0][tid], u + xo3 + k.col);
-      if (n + 2 <= k.i1) {
-	pf_cp_async8(&sm.u[u2][0][tid], u + k.ns + xo2 + k.col);
-	pf_cp_async8(&sm.u[u2][1][tid], u + 2*k.ns + xo2 + k.col);
-      }
-      pf_cp_async_commit();
 
       const int m = n + 1;
       if (k.fmode == 0 && tz == 0 && k.has_sites && m >= k.i0 && m <= k.i1) {
@@ -414,7 +430,7 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
 
     // ---- 3. plane n: x-face flux (n | n+1), force, y/z face fluxes ----
     const double ph_c = fm[pc];
-    const double uxp = sm.ux[u1][tid];               // u_x(n+1)
+    const double uxp = sm.ux[u1][k.tu];              // u_x(n+1)
     double fx = 0.0, fy = 0.0, fz = 0.0;
     double F0 = 0.0, F1 = 0.0, F2 = 0.0;
     if (do_fx && k.face_row) {
@@ -422,7 +438,8 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
 
       if (do_full) {
 	const double (* gb)[G::NT] = sm.g[q & 1];
-	const double (* ub)[G::NT] = sm.u[u0];
+	const double (* ub)[G::USLOT] = sm.u[u0];
+	const int tu = k.tu;
 
 	if (k.out_site) {
 	  F0 = 0.5*(((r.gm_xx - gp_xx) + (gb[0][tym] - gb[0][typ])) + (gb[3][tzm] - gb[3][tzp]));
@@ -432,9 +449,9 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
 
 	double ph_yp2 = 0.0, ph_zp2 = 0.0;
 	if (ORDER == 3) { ph_yp2 = fm[pc + 2*G::PZ]; ph_zp2 = fm[pc + 2]; }
-	fy = adv_face<ORDER, false>(ub[0][tid], ub[0][typ], fm[pc - G::PZ], ph_c, fm[pc + G::PZ], ph_yp2)
+	fy = adv_face<ORDER, false>(ub[0][tu], ub[0][tu + FU_ROW], fm[pc - G::PZ], ph_c, fm[pc + G::PZ], ph_yp2)
 	  - k.M*(gb[5][typ] - r.gc_mu) - k.mg1;
-	fz = adv_face<ORDER, false>(ub[1][tid], ub[1][tzp], fm[pc - 1], ph_c, fm[pc + 1], ph_zp2)
+	fz = adv_face<ORDER, false>(ub[1][tu], ub[1][tu + 1], fm[pc - 1], ph_c, fm[pc + 1], ph_zp2)
 	  - k.M*(gb[5][tzp] - r.gc_mu) - k.mg2;
 	sm.fl[q & 1][0][tid] = fy;
 	sm.fl[q & 1][1][tid] = fz;
@@ -447,9 +464,26 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
       const int s = (n - 1 + k.nh - 1)*k.xs + k.scol;
       const double phn = r.phim1 - (((r.fxm1 - r.fxm2) + (r.fy_prev - fl[0][tym])) + k.wz*(r.fz_prev - fl[1][tzm]));
       phinew[s] = phn;
-      // the planes the neighbour GPUs' next phi sector reads, straight into their halo planes
-      if (k.peer_lo != nullptr && n - 1 <= k.nh) k.peer_lo[(size_t) s + (size_t) k.nlx*k.xs] = phn;
-      if (k.peer_hi != nullptr && n - 1 > k.nlx - k.nh) k.peer_hi[(size_t) s - (size_t) k.nlx*k.xs] = phn;
+      // periodic images within nhalo of a y / z boundary (read by the next step's TMA boxes of phi)
+      const int ipy = k.py*k.imy_unit, ipz = k.pz*k.imz_unit;
+      if (k.py != 0) phinew[s + ipy] = phn;
+      if (k.pz != 0) phinew[s + ipz] = phn;
+      if (k.py != 0 && k.pz != 0) phinew[s + ipy + ipz] = phn;
+      // the planes the neighbour GPUs' next phi sector reads, straight into their halo planes (with their y / z images)
+      if (k.peer_lo != nullptr && n - 1 <= k.nh) {
+	double * pl = k.peer_lo + ((size_t) s + (size_t) k.nlx*k.xs);
+	pl[0] = phn;
+	if (k.py != 0) pl[ipy] = phn;
+	if (k.pz != 0) pl[ipz] = phn;
+	if (k.py != 0 && k.pz != 0) pl[ipy + ipz] = phn;
+      }
+      if (k.peer_hi != nullptr && n - 1 > k.nlx - k.nh) {
+	double * ph = k.peer_hi + ((size_t) s - (size_t) k.nlx*k.xs);
+	ph[0] = phn;
+	if (k.py != 0) ph[ipy] = phn;
+	if (k.pz != 0) ph[ipz] = phn;
+	if (k.py != 0 && k.pz != 0) ph[ipy + ipz] = phn;
+      }
     }
 
     // ---- 5. rotate the own-column history ----
@@ -469,8 +503,13 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
     }
     Fs0 = F0; Fs1 = F1; Fs2 = F2;
 
-    // the phi / u planes issued ONE plane-step ago have landed (read by every thread after the barrier)
-    pf_cp_async_wait<1>();
+    // the phi / u planes issued ONE plane-step ago have landed (every thread reads them after the barrier)
+    if (n > istart) {
+      const int qp = (q == 0) ? 5 : q - 1;
+      // use count of pl[qp]: the prologue used pl[5] once before the march started
+      const int uses = (n - 1 - istart)/6 + (qp == 5 ? 1 : 0);
+      fu_mbar_wait(&sm.pl[qp], (unsigned int) (uses & 1));
+    }
     __syncthreads();
     q = q1;
   }
@@ -481,16 +520,17 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const Lb200Geom g, c
 typedef CUresult (*fu_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
 				 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
 				 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-struct FuMapEntry { const void * ptr; int nall[3]; int nsites; int ty; CUtensorMap map; };
-static const CUtensorMap * fu_tensor_map(const double * f, const Lb200Geom & g, int ty) {
+struct FuMapEntry { const void * ptr; int nall[3]; int nsites; int ncomp, bz, by; CUtensorMap map; };
+// ncomp = 0: a scalar field (rank 3: z, y, x); else rank 4 with the component as the slowest dimension
+static bool fu_tensor_map(const double * a, const Lb200Geom & g, int ncomp, int bz, int by, CUtensorMap * out) {
   static std::mutex mtx;
   static std::vector<FuMapEntry *> cache;
   static fu_encode_fn encode = nullptr;
   static bool tried = false;
   std::lock_guard<std::mutex> lock(mtx);
   for (FuMapEntry * e : cache) {
-    if (e->ptr == (const void *) f && e->nall[0] == g.nall[0] && e->nall[1] == g.nall[1] && e->nall[2] == g.nall[2]
-	&& e->nsites == g.nsites && e->ty == ty) return &e->map;
+    if (e->ptr == (const void *) a && e->nall[0] == g.nall[0] && e->nall[1] == g.nall[1] && e->nall[2] == g.nall[2]
+	&& e->nsites == g.nsites && e->ncomp == ncomp && e->bz == bz && e->by == by) { *out = e->map; return true; }
   }
   if (!tried) {
     tried = true;
@@ -500,21 +540,24 @@ static const CUtensorMap * fu_tensor_map(const double * f, const Lb200Geom & g, 
 	&& q == cudaDriverEntryPointSuccess) encode = (fu_encode_fn) fn;
     else cudaGetLastError();
   }
-  if (encode == nullptr) return nullptr;
+  if (encode == nullptr) return false;
   FuMapEntry * e = new FuMapEntry;
-  e->ptr = f; e->nall[0] = g.nall[0]; e->nall[1] = g.nall[1]; e->nall[2] = g.nall[2]; e->nsites = g.nsites; e->ty = ty;
-  const cuuint64_t dims[4] = {(cuuint64_t) g.nall[2], (cuuint64_t) g.nall[1], (cuuint64_t) g.nall[0], 19};
+  e->ptr = a; e->nall[0] = g.nall[0]; e->nall[1] = g.nall[1]; e->nall[2] = g.nall[2]; e->nsites = g.nsites;
+  e->ncomp = ncomp; e->bz = bz; e->by = by;
+  const cuuint32_t rank = ncomp > 0 ? 4 : 3;
+  const cuuint64_t dims[4] = {(cuuint64_t) g.nall[2], (cuuint64_t) g.nall[1], (cuuint64_t) g.nall[0], (cuuint64_t) (ncomp > 0 ? ncomp : 1)};
   const cuuint64_t strides[3] = {(cuuint64_t) g.ys*8, (cuuint64_t) g.xs*8, (cuuint64_t) g.nsites*8};
-  const cuuint32_t box[4] = {(cuuint32_t) FU_ROW, (cuuint32_t) ty, 1, 1};
+  const cuuint32_t box[4] = {(cuuint32_t) bz, (cuuint32_t) by, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  if (encode(&e->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *) f, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  if (encode(&e->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, (void *) a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 	     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
     delete e;
-    return nullptr;
+    return false;
   }
   if (cache.size() >= 64) { delete cache.front(); cache.erase(cache.begin()); }      // contexts come and go
   cache.push_back(e);
-  return &e->map;
+  *out = e->map;
+  return true;
 }
 
 template <int BY>
@@ -537,15 +580,16 @@ int launch_step_fused_by(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDe
 #undef LB200_FU_ATTR
     if (dev >= 0 && dev < LB200_MAX_DEVICES) configured[dev] = true;
   }
-  const CUtensorMap * fmap = fu_tensor_map(fsrc, g, G::TY);
-  if (fmap == nullptr) return 0;
+  CUtensorMap fmap, phimap, umap;
+  if (!fu_tensor_map(fsrc, g, 19, FU_ROW, G::TY, &fmap) || !fu_tensor_map(phi, g, 0, FU_ROW, G::PY, &phimap)
+      || !fu_tensor_map(u, g, 3, FU_ROW, BY, &umap)) return 0;
   const int nx = (g.xcnt > 0) ? g.xcnt : g.nl[0];
   const int xc = (g.xchunk > 0) ? g.xchunk
     : ps_pick_xc((const void *) step_fused_kernel<3, false, BY>, G::NT, smem, gz*gy, nx, 4, 10);
   dim3 grd(gz, gy, (nx + xc - 1)/xc);
   static const int fmode = tuned_flag("LB200_FUSED_FMODE", 0);
   static const int skew = tuned_flag("LB200_FUSED_SKEW", 1);
-#define LB200_FU_GO(O, GH) step_fused_kernel<O, GH, BY><<<grd, blk, smem, st>>>(*fmap, g, sp, cp, xc, fmode, skew, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out)
+#define LB200_FU_GO(O, GH) step_fused_kernel<O, GH, BY><<<grd, blk, smem, st>>>(fmap, phimap, umap, g, sp, cp, xc, fmode, skew, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out)
   if (cp.ghost) {
     if (sp.order == 1) LB200_FU_GO(1, true); else if (sp.order == 2) LB200_FU_GO(2, true); else LB200_FU_GO(3, true);
   }
