@@ -69,6 +69,7 @@ struct FuK {                                 // per-thread / per-CTA constants
   int imy, imz;                              // element offsets of those images
   int py, pz;                                // the same for the nhalo-deep images of phi (sites within nhalo of a boundary)
   int tu;                                    // own element of a staged velocity plane
+  unsigned int smb;                          // shared-window address of the FuShared block
   int imy_unit, imz_unit;                    // one period in y / z (elements)
   double M, kappa, a, b, mg0, mg1, mg2, wz;
   double * peer_lo, * peer_hi;               // neighbour GPUs' phi' arrays (nullptr: none)
@@ -84,13 +85,13 @@ __host__ __device__ constexpr unsigned long long fu_cbits(int a) {
 
 __device__ __forceinline__ unsigned int fu_smem_u32(const void * p) { return (unsigned int) __cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void fu_mbar_init(unsigned long long * bar, unsigned int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(fu_smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void fu_mbar_init(unsigned int bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void fu_mbar_expect(unsigned long long * bar, unsigned int bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(fu_smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void fu_mbar_expect(unsigned int bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void fu_mbar_wait(unsigned long long * bar, unsigned int parity) {
+__device__ __forceinline__ void fu_mbar_wait(unsigned int bar, unsigned int parity) {
   asm volatile("{\n"
 	       ".reg .pred p;\n"
 	       "FU_WAIT_%=:\n"
@@ -98,18 +99,18 @@ __device__ __forceinline__ void fu_mbar_wait(unsigned long long * bar, unsigned 
 	       "@p bra FU_DONE_%=;\n"
 	       "bra FU_WAIT_%=;\n"
 	       "FU_DONE_%=:\n"
-	       "}\n" :: "r"(fu_smem_u32(bar)), "r"(parity) : "memory");
+	       "}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 // global -> shared TMA box load: coordinates (z, y, x, population) in elements of the 4-d tensor map of f
-__device__ __forceinline__ void fu_tma_box(void * dst, const CUtensorMap * map, int c0, int c1, int c2, int c3,
-					   unsigned long long * bar) {
+__device__ __forceinline__ void fu_tma_box(unsigned int dst, const CUtensorMap * map, int c0, int c1, int c2, int c3,
+					   unsigned int bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
-	       :: "r"(fu_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(fu_smem_u32(bar)) : "memory");
+	       :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void fu_tma_box3(void * dst, const CUtensorMap * map, int c0, int c1, int c2, unsigned long long * bar) {
+__device__ __forceinline__ void fu_tma_box3(unsigned int dst, const CUtensorMap * map, int c0, int c1, int c2, unsigned int bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
-	       :: "r"(fu_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(fu_smem_u32(bar)) : "memory");
+	       :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
 template <int PZ>
@@ -125,6 +126,9 @@ __device__ __forceinline__ void fu_plane_sums(const double * __restrict__ q, int
   Cy = ap - am;
   Cz = ((mp - mm) + (zp - zm)) + (pp - pm);
 }
+
+// shared-window addresses of the staging areas and their barriers
+#define FU_AD(member) (k.smb + (unsigned int) offsetof(FuShared<BY>, member))
 
 // pull-stream + collision of the own site of plane m with the force (F0, F1, F2) (lb_collide, src/collision.c:253-593)
 template <bool GHOST, int BY>
@@ -149,7 +153,7 @@ __device__ __forceinline__ void fu_collide(FuShared<BY> & sm, const FuK & k, con
   }
   else {
     const int st = (m - k.i0) % FU_NSTAGE;
-    if (k.fmode == 0) fu_mbar_wait(&sm.full[st], (unsigned int) (((m - k.i0)/FU_NSTAGE) & 1));
+    if (k.fmode == 0) fu_mbar_wait(FU_AD(full) + 8u*st, (unsigned int) (((m - k.i0)/FU_NSTAGE) & 1));
     const double * __restrict__ fb = &sm.f[st][0][k.frow*FU_ROW + k.flane];
 #pragma unroll
     for (int p = 0; p < 19; p++) f[p] = fb[p*FuGeo<BY>::FBLK + 1 - CV19[p][2]];
@@ -164,10 +168,15 @@ __device__ __forceinline__ void fu_collide(FuShared<BY> & sm, const FuK & k, con
   }
   d3q19_mode2f<GHOST>(mode, f);
 
+  {
+    // one 64-bit pointer increment per population instead of a 64-bit multiply-add chain
+    double * pf = fdst + s;
 #pragma unroll
-  for (int p = 0; p < 19; p++) __stcs(fdst + p*k.ns + s, f[p]);
+    for (int p = 0; p < 19; p++) { __stcs(pf, f[p]); pf += k.ns; }
+    double * pu = u_out + s;
 #pragma unroll
-  for (int ia = 0; ia < 3; ia++) u_out[ia*k.ns + s] = uu[ia];
+    for (int ia = 0; ia < 3; ia++) { *pu = uu[ia]; pu += k.ns; }
+  }
   if (!k.skip_diag) {
     rho_out[s] = rho;
     force[s] = F0; force[k.ns + s] = F1; force[2*k.ns + s] = F2;
@@ -286,6 +295,7 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
   k.pz = (g.wrap[2] && kc <= nh) ? 1 : ((g.wrap[2] && kc > g.nl[2] - nh) ? -1 : 0);
   if (!k.out_site) { k.sy = 0; k.sz = 0; k.py = 0; k.pz = 0; }
   k.tu = ty*FU_ROW + tz + 1;
+  k.smb = fu_smem_u32(&sm);
   k.imy_unit = g.nl[1]*ys; k.imz_unit = g.nl[2];
 
   const int istart = k.i0 - 2;
@@ -295,9 +305,9 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
 
   if (k.tid == 0) {
 #pragma unroll
-    for (int s = 0; s < FU_NSTAGE; s++) fu_mbar_init(&sm.full[s], (unsigned int) BY);
+    for (int s = 0; s < FU_NSTAGE; s++) fu_mbar_init(FU_AD(full) + 8u*s, (unsigned int) BY);
 #pragma unroll
-    for (int s = 0; s < PF_RING; s++) fu_mbar_init(&sm.pl[s], 1u);
+    for (int s = 0; s < PF_RING; s++) fu_mbar_init(FU_AD(pl) + 8u*s, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
 
@@ -311,19 +321,19 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
   // u_y, u_z (istart+1) -> slot 1.  (The first plane-step prefetches phi(istart+4), u_x(istart+3), u_y/u_z(istart+2).)
   // They use barrier pl[5], whose first regular use is five plane-steps away.
   if (issuer) {
-    fu_mbar_expect(&sm.pl[5], (unsigned int) (8*(4*G::PY*FU_ROW + 4*BY*FU_ROW)));
+    fu_mbar_expect(FU_AD(pl) + 40u, (unsigned int) (8*(4*G::PY*FU_ROW + 4*BY*FU_ROW)));
 #pragma unroll
     for (int d = 0; d < 4; d++) {
       const int xp = ps_wrap(istart + d, k.nlx, k.wx) + nh - 1;
-      fu_tma_box3(&sm.phi[d][0], &phimap, k.kbase, prow, xp, &sm.pl[5]);
-      if (d == 1 || d == 2) fu_tma_box(&sm.ux[d][0], &umap, k.kbase, urow, xp, 0, &sm.pl[5]);
+      fu_tma_box3(FU_AD(phi) + 8u*G::PSLOT*d, &phimap, k.kbase, prow, xp, FU_AD(pl) + 40u);
+      if (d == 1 || d == 2) fu_tma_box(FU_AD(ux) + 8u*G::USLOT*d, &umap, k.kbase, urow, xp, 0, FU_AD(pl) + 40u);
       if (d == 1) {
-	fu_tma_box(&sm.u[1][0][0], &umap, k.kbase, urow, xp, 1, &sm.pl[5]);
-	fu_tma_box(&sm.u[1][1][0], &umap, k.kbase, urow, xp, 2, &sm.pl[5]);
+	fu_tma_box(FU_AD(u) + 8u*G::USLOT*2, &umap, k.kbase, urow, xp, 1, FU_AD(pl) + 40u);
+	fu_tma_box(FU_AD(u) + 8u*G::USLOT*3, &umap, k.kbase, urow, xp, 2, FU_AD(pl) + 40u);
       }
     }
   }
-  fu_mbar_wait(&sm.pl[5], 0u);
+  fu_mbar_wait(FU_AD(pl) + 40u, 0u);
 
   PfRegs r;
   r.uxc = 0.0;                                     // u_x(n): not used before n = i0 - 1
@@ -357,13 +367,14 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
       if (issuer) {
 	const bool do_phi = (n + 4 <= k.i1 + 2), do_ux = (n + 3 <= k.i1 + 1), do_uyz = (n + 2 <= k.i1);
 	// (the prologue's use of pl[5] was phase 0 of that barrier: the regular uses start one phase later)
-	fu_mbar_expect(&sm.pl[q], (unsigned int) (8*((do_phi ? G::PY*FU_ROW : 0) + (do_ux ? BY*FU_ROW : 0) + (do_uyz ? 2*BY*FU_ROW : 0))));
-	if (do_phi) fu_tma_box3(&sm.phi[q4][0], &phimap, k.kbase, prow, ps_wrap(n + 4, k.nlx, k.wx) + k.nh - 1, &sm.pl[q]);
-	if (do_ux) fu_tma_box(&sm.ux[u0][0], &umap, k.kbase, urow, ps_wrap(n + 3, k.nlx, k.wx) + k.nh - 1, 0, &sm.pl[q]);
+	const unsigned int plq = FU_AD(pl) + 8u*q;
+	fu_mbar_expect(plq, (unsigned int) (8*((do_phi ? G::PY*FU_ROW : 0) + (do_ux ? BY*FU_ROW : 0) + (do_uyz ? 2*BY*FU_ROW : 0))));
+	if (do_phi) fu_tma_box3(FU_AD(phi) + 8u*G::PSLOT*q4, &phimap, k.kbase, prow, ps_wrap(n + 4, k.nlx, k.wx) + k.nh - 1, plq);
+	if (do_ux) fu_tma_box(FU_AD(ux) + 8u*G::USLOT*u0, &umap, k.kbase, urow, ps_wrap(n + 3, k.nlx, k.wx) + k.nh - 1, 0, plq);
 	if (do_uyz) {
 	  const int xp = ps_wrap(n + 2, k.nlx, k.wx) + k.nh - 1;
-	  fu_tma_box(&sm.u[u2][0][0], &umap, k.kbase, urow, xp, 1, &sm.pl[q]);
-	  fu_tma_box(&sm.u[u2][1][0], &umap, k.kbase, urow, xp, 2, &sm.pl[q]);
+	  fu_tma_box(FU_AD(u) + 8u*G::USLOT*(2*u2), &umap, k.kbase, urow, xp, 1, plq);
+	  fu_tma_box(FU_AD(u) + 8u*G::USLOT*(2*u2 + 1), &umap, k.kbase, urow, xp, 2, plq);
 	}
       }
 
@@ -372,13 +383,14 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
 	// population p arrives from the site at -c_p (lb_propagation, src/propagation.c:153-200): one box per population,
 	// TY rows from row j - c_y of plane m - c_x; lane 0 of warp w issues populations w and w + BY
 	const int st = (m - k.i0) % FU_NSTAGE;
-	fu_mbar_expect(&sm.full[st], (unsigned int) ((ty + BY < 19 ? 2 : 1)*G::TY*FU_ROW*8));
+	const unsigned int fst = FU_AD(full) + 8u*st;
+	fu_mbar_expect(fst, (unsigned int) ((ty + BY < 19 ? 2 : 1)*G::TY*FU_ROW*8));
 #pragma unroll
 	for (int pp = 0; pp < 2; pp++) {
 	  const int p = ty + pp*BY;
 	  if (p < 19) {
 	    const int cx = (int) ((fu_cbits(0) >> (2*p)) & 3ull) - 1, cy = (int) ((fu_cbits(1) >> (2*p)) & 3ull) - 1;
-	    fu_tma_box(&sm.f[st][p][0], &fmap, k.kbase, k.jrow0 - cy, ps_wrap(m - cx, k.nlx, k.wx) + k.nh - 1, p, &sm.full[st]);
+	    fu_tma_box(FU_AD(f) + 8u*G::FBLK*(19*st + p), &fmap, k.kbase, k.jrow0 - cy, ps_wrap(m - cx, k.nlx, k.wx) + k.nh - 1, p, fst);
 	  }
 	}
       }
@@ -508,7 +520,7 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
       const int qp = (q == 0) ? 5 : q - 1;
       // use count of pl[qp]: the prologue used pl[5] once before the march started
       const int uses = (n - 1 - istart)/6 + (qp == 5 ? 1 : 0);
-      fu_mbar_wait(&sm.pl[qp], (unsigned int) (uses & 1));
+      fu_mbar_wait(FU_AD(pl) + 8u*qp, (unsigned int) (uses & 1));
     }
     __syncthreads();
     q = q1;
