@@ -11,8 +11,14 @@
  * declaration it mirrors (paths relative to the reference root).  Host arrays use the reference's
  * -DADDR_SOA addressing (src/memory.h:182-195): lb->f[LB_ADDR(nsite, ndist, nvel, index, n, p)].
  *
- * Not mirrored (outside SURVEY.md section 8): run-time input parsing, I/O, statistics, colloids,
- * walls, noise, Lees-Edwards planes (lees_edw_t exists with zero planes only), viscosity models.
+ * Mirrored beyond the bare time step: Lees-Edwards planes (lees_edw_t with planes), the symmetric_lb and liquid-crystal
+ * sectors, the reference's restart-file writers / readers (lb_io_*, field_io_*).  Not mirrored (outside SURVEY.md
+ * section 8): run-time input parsing, statistics, colloids, walls, noise, viscosity models.
+ *
+ * This header is a stand-alone, self-contained statement of that interface (its structs are cut-down look-alikes).
+ * The proof that the library is a drop-in for the reference's OWN structs and callers is integration/: the reference's
+ * src/ludwig.c and tests/unit/*.c, unchanged, linked against libludwig_b200.so through integration/ludwig_b200_shim.c,
+ * which is compiled against the reference's own headers (tests/test_gpu_reference_callers.py).
  */
 #ifndef LUDWIG_HOST_H
 #define LUDWIG_HOST_H

@@ -597,7 +597,7 @@ int launch_step_fused_by(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDe
       || !fu_tensor_map(u, g, 3, FU_ROW, BY, &umap)) return 0;
   const int nx = (g.xcnt > 0) ? g.xcnt : g.nl[0];
   const int xc = (g.xchunk > 0) ? g.xchunk
-    : ps_pick_xc((const void *) step_fused_kernel<3, false, BY>, G::NT, smem, gz*gy, nx, 4, 10);
+    : ps_pick_xc((const void *) step_fused_kernel<3, false, BY>, G::NT, smem, gz*gy, nx, 4, 1);
   dim3 grd(gz, gy, (nx + xc - 1)/xc);
   static const int fmode = tuned_flag("LB200_FUSED_FMODE", 0);
   static const int skew = tuned_flag("LB200_FUSED_SKEW", 1);

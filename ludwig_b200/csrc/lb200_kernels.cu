@@ -2221,7 +2221,7 @@ phi_sector_fast_kernel(const Lb200Geom g, const Lb200SymmDev sp, int xc,
 // Planes per x chunk: every chunk pays PS_XPRO extra plane-steps of pipeline fill, and the chunks are
 // scheduled in rounds of (SMs x resident CTAs), so pick the chunk count that minimises
 // rounds x (planes per chunk + fill).  256^3 on 148 SMs: 6 chunks of 43 planes = 1026 CTAs = 6.9 rounds.
-static int ps_pick_xc(const void * kernel, int nt, size_t smem, int tiles, int nx, int fill, int min_rounds = 0) {
+static int ps_pick_xc(const void * kernel, int nt, size_t smem, int tiles, int nx, int fill, int balance = 0) {
   // per device: one process may hold contexts on several GPUs
   static int nsm_dev[LB200_MAX_DEVICES] = {0};
   int dev = 0;
@@ -2243,10 +2243,11 @@ static int ps_pick_xc(const void * kernel, int nt, size_t smem, int tiles, int n
     const int xc = (nx + nchunk - 1)/nchunk;
     if (xc < 8 && nchunk > 1) break;
     const long long rounds = ((long long) tiles*((nx + xc - 1)/xc) + slots - 1)/slots;
-    const long long cost = rounds*(xc + fill);
-    // min_rounds: SMs do not run at one speed (distance to the L2 slices, neighbours' traffic); with only two or three
-    // long CTAs per SM the slowest SM sets the time, with many short ones the block scheduler evens it out
-    if (rounds < min_rounds && xc >= 16 && nchunk < nx) continue;
+    long long cost = rounds*(xc + fill)*100;
+    // balance: SMs do not run at one speed (distance to the L2 slices, neighbours' traffic); with only two or three long
+    // CTAs per SM the slowest SM sets the time (measured at 256^3: + 15 % with 2 rounds, + 8 % with 4, ~0 with 10),
+    // with many short ones the block scheduler evens it out
+    if (balance) cost += cost*40/(100*rounds);
     if (best < 0 || cost < best) { best = cost; best_xc = xc; }
   }
   return best_xc;
