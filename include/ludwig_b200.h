@@ -119,7 +119,7 @@ typedef struct lb200_symm_param_s {
   int conserve;             /* cahn_hilliard_options_conserve (phi_ch_info_t.conserve, src/phi_cahn_hilliard.h:31-36):
                              * 0 = plain forward step; 1 = compensated (Kahan) sum per site, phi_ch_update_conserve,
                              * src/phi_cahn_hilliard.c:1059-1094, 1181-1215 -- the compensation field lives in the context
-                             * like pch->csum.  2 (global subtraction, one all-reduce) is not built: LB200_EINVAL */
+                             * like pch->csum; 2 = global subtraction after the forward step (lb200_phi_conserve_sum below) */
 } lb200_symm_param_t;
 
 /* fe_lc_param_t + beris_edw_param_t as the liquid-crystal kernels see them (src/blue_phase.h:52-75,
@@ -178,6 +178,16 @@ int lb200_pth_force_fluid_driver(lb200_t * ctx);
 int lb200_phi_force_calculation(lb200_t * ctx, const lb200_symm_param_t * sp);
 /* phi_cahn_hilliard (no noise; conserve = 0 or 1): src/phi_cahn_hilliard.c:213-288 */
 int lb200_phi_cahn_hilliard(lb200_t * ctx, const lb200_symm_param_t * sp);
+/* cahn_hilliard_options_conserve 2 (PHI_CONSERVE_GLOBAL_SUBTRACT, src/phi_cahn_hilliard.c:1102-1169): after every forward step
+ * (sum_fluid phi - sum0)/nfluid is subtracted at every fluid site -- the one place of the path with a global reduction
+ * (x-slabs: NCCL all-gather of one pair per GPU, added in rank order in compensated arithmetic, so the result does not
+ * depend on the GPU count beyond the last bit of the sum).  sum0 is phi->field_init_sum of the reference, which its
+ * statistics code computes at time 0 (cahn_hilliard_stats_time0, src/cahn_hilliard_stats.c:58-76):
+ *   lb200_phi_conserve_sum   computes the compensated sum of the CURRENT phi over the fluid sites of the whole lattice
+ *                            (collective over the slabs), returns it and keeps it as sum0;
+ *   lb200_phi_init_sum_set   sets sum0 to a value the caller has (the binding passes phi->field_init_sum). */
+int lb200_phi_conserve_sum(lb200_t * ctx, double * sum);
+int lb200_phi_init_sum_set(lb200_t * ctx, double sum0);
 /* lb_collide (ndist = 1): src/collision.c:143-232, 253-593 */
 int lb200_lb_collide(lb200_t * ctx, const lb200_collide_param_t * cp);
 /* symmetric_lb (`free_energy symmetric_lb`, options.ndist = 2: array LB200_F holds [density | order parameter]

@@ -372,6 +372,8 @@ int __wrap_phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t *
   if (pch->info.noise) pe_fatal(pch->pe, "libludwig_b200: order-parameter noise is outside this library\n");
   b200_symm_param(fe, pch, &sp);
   b200_time_sync(pch->pe, s);
+  /* cahn_hilliard_options_conserve 2 restores the sum the driver's statistics took at time 0 (src/cahn_hilliard_stats.c:58-76) */
+  if (sp.conserve == 2) b200_check(pch->pe, lb200_phi_init_sum_set(s->ctx, phi->field_init_sum), "phi_init_sum");
   b200_check(pch->pe, lb200_phi_cahn_hilliard(s->ctx, &sp), "phi_cahn_hilliard");
   return 0;
 }

@@ -155,6 +155,8 @@ def load_library():
     lib.lb200_step_lc.argtypes = [C.c_void_p, C.POINTER(CollideParam), C.POINTER(LcParam), C.c_int]
     lib.lb200_phi_force_calculation.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
     lib.lb200_phi_cahn_hilliard.argtypes = [C.c_void_p, C.POINTER(SymmParam)]
+    lib.lb200_phi_conserve_sum.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.lb200_phi_init_sum_set.argtypes = [C.c_void_p, C.c_double]
     lib.lb200_lb_collide.argtypes = [C.c_void_p, C.POINTER(CollideParam)]
     lib.lb200_step.argtypes = [C.c_void_p, C.POINTER(CollideParam), C.POINTER(SymmParam), C.c_int]
     lib.lb200_lb_collision_binary.argtypes = [C.c_void_p, C.POINTER(CollideParam), C.POINTER(SymmParam)]
@@ -341,6 +343,16 @@ class Lb200:
 
     def phi_force_calculation(self, sp):
         self._check(self.lib.lb200_phi_force_calculation(self.h, C.byref(sp)))
+
+    def phi_conserve_sum(self):
+        """lb200_phi_conserve_sum: the compensated sum of phi over the fluid sites of the whole lattice (collective over
+        the slabs); kept as the value cahn_hilliard_options_conserve 2 restores."""
+        v = C.c_double()
+        self._check(self.lib.lb200_phi_conserve_sum(self.h, C.byref(v)))
+        return v.value
+
+    def phi_init_sum_set(self, v):
+        self._check(self.lib.lb200_phi_init_sum_set(self.h, C.c_double(v)))
 
     def phi_cahn_hilliard(self, sp):
         self._check(self.lib.lb200_phi_cahn_hilliard(self.h, C.byref(sp)))

@@ -97,6 +97,9 @@ struct lb200_s {
   int u_halo_valid;
 
   int prop_pending;          // lb_propagation requested, not yet applied (fused into next collide)
+  double * psum;             // conserve 2: scratch of the phi sums (partials | result[2] | all ranks | total[2])
+  double phi_init_sum;       // phi->field_init_sum (cahn_hilliard_stats_time0): the sum the global correction restores
+  int phi_init_sum_set;
   double * halo_snap;        // snapshot of an array for halo swaps on lattices thinner than the halo
   size_t halo_snap_size;
   int fused_ready;           // the last thing that touched the lattice was a one-kernel step: it left the y / z (and peer x) halos of
@@ -349,7 +352,12 @@ static int alloc_d(double ** p, size_t n) {
 // zero, with the phi_ch_t: src/phi_cahn_hilliard.c:146-153)
 static int conserve_prepare(lb200_t * c, const lb200_symm_param_t * sp) {
   if (sp->conserve == 0) return 0;
-  if (sp->conserve != 1) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve %d: 0 and 1 (compensated sum) are built", sp->conserve);
+  if (sp->conserve == 2) {
+    // PHI_CONSERVE_GLOBAL_SUBTRACT: needs the initial sum (the reference takes it from its statistics code at time 0)
+    if (!c->phi_init_sum_set) return fail(LB200_ESTATE, "cahn_hilliard_options_conserve 2: no initial sum (lb200_phi_conserve_sum / lb200_phi_init_sum_set first)");
+    return 0;
+  }
+  if (sp->conserve != 1) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve %d: 0, 1 (compensated sum) and 2 (global subtraction) are built", sp->conserve);
   if (c->le.nplane > 0) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve 1 with Lees-Edwards planes is outside this build");
   if (c->csum == nullptr && alloc_d(&c->csum, (size_t) c->g.nsites) != 0) return LB200_ECUDA;
   return 0;
@@ -705,7 +713,7 @@ int lb200_free(lb200_t * c) {
   cudaFree(c->le_trip); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
   for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
   cudaFree(c->f32[0]); cudaFree(c->f32[1]); cudaFree(c->csum);
-  cudaFree(c->flags); cudaFree(c->spin_err); cudaFree(c->halo_snap);
+  cudaFree(c->flags); cudaFree(c->spin_err); cudaFree(c->halo_snap); cudaFree(c->psum);
   cudaFree(c->status); cudaFree(c->xlo); cudaFree(c->xhi); cudaFree(c->slo); cudaFree(c->shi); cudaFree(c->model_d);
   for (int i = 0; i < LB200_KCLASS_MAX; i++) {
     if (c->ev[i]) { for (cudaEvent_t e : *c->ev[i]) cudaEventDestroy(e); delete c->ev[i]; }
@@ -1277,6 +1285,67 @@ int lb200_phi_force_calculation(lb200_t * c, const lb200_symm_param_t * sp) {
   CTX_LEAVE_SYNC(c);
 }
 
+// ---- cahn_hilliard_options_conserve 2 (src/phi_cahn_hilliard.c:1102-1169) --------------------------------------
+// psum layout (doubles): [0, 2B] partials + fluid count | [2B+2, 2B+4) this GPU's (sum, nfluid) | [2B+4, 2B+4+2P) every
+// rank's | [2B+4+2P, +2) the global (sum, nfluid)
+static int phi_sum_async(lb200_t * c, const double * phi, cudaStream_t st, double ** total) {
+  const int B = c->k->psum_blocks, P = c->opt.cart_size;
+  if (c->psum == nullptr) {
+    if (alloc_d(&c->psum, (size_t) 2*B + 8 + 2*P) != 0) return LB200_ECUDA;
+    CUDA_TRY(cudaMemsetAsync(c->psum, 0, ((size_t) 2*B + 8 + 2*P)*sizeof(double), st));
+  }
+  double * mine = c->psum + 2*B + 2, * all = c->psum + 2*B + 4, * tot = all + 2*P;
+  c->launches += c->k->phi_sum(st, c->g, phi, status_ptr(c), c->psum, mine);
+  if (P > 1) {
+#ifdef LB200_NO_NCCL
+    return fail(LB200_ECOMM, "library built without NCCL");
+#else
+    if (c->nccl == nullptr) return fail(LB200_ECOMM, "cart_size > 1 but no NCCL communicator attached (lb200_attach_nccl)");
+    // the one exchange of the path that is not nearest-neighbour: all-gather, then every GPU adds in rank order
+    if (ncclAllGather(mine, all, 2, ncclDouble, (ncclComm_t) c->nccl, st) != ncclSuccess) return fail(LB200_ECOMM, "ncclAllGather of the phi sums failed");
+    c->launches += c->k->phi_sum_ranks(st, all, P, tot);
+#endif
+  }
+  else {
+    tot = mine;
+  }
+  *total = tot;
+  return 0;
+}
+
+// phi_ch_subtract_sum_phi_after_forward_step on the array that has just been advanced
+static int phi_conserve_subtract_async(lb200_t * c, double * phi, cudaStream_t st) {
+  double * tot = nullptr;
+  int rc = phi_sum_async(c, phi, st, &tot);
+  if (rc != 0) return rc;
+  c->launches += c->k->phi_subtract(st, c->g, tot, c->phi_init_sum, status_ptr(c), phi);
+  return 0;
+}
+
+// cahn_hilliard_stats_time0 (src/cahn_hilliard_stats.c:58-76): the sum of phi over the fluid sites of the whole lattice,
+// compensated, kept as the value conserve 2 restores after every step
+int lb200_phi_conserve_sum(lb200_t * c, double * sum) {
+  CTX_ENTER(c);
+  if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
+  double * tot = nullptr;
+  int rc = phi_sum_async(c, c->phi, c->stream, &tot);
+  if (rc != 0) return rc;
+  double h[2] = {0.0, 0.0};
+  CUDA_TRY(cudaMemcpyAsync(h, tot, 2*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->phi_init_sum = h[0];
+  c->phi_init_sum_set = 1;
+  if (sum != nullptr) *sum = h[0];
+  return 0;
+}
+
+int lb200_phi_init_sum_set(lb200_t * c, double phi0) {
+  if (c == nullptr) return fail(LB200_EINVAL, "null context");
+  c->phi_init_sum = phi0;
+  c->phi_init_sum_set = 1;
+  return 0;
+}
+
 int lb200_phi_cahn_hilliard(lb200_t * c, const lb200_symm_param_t * sp) {
   CTX_ENTER(c);
   if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
@@ -1298,6 +1367,7 @@ int lb200_phi_cahn_hilliard(lb200_t * c, const lb200_symm_param_t * sp) {
     ProfScope ps(c, LB200_K_FORCE_CH);
     c->launches += c->k->cahn_hilliard(c->stream, c->g, sd, c->phi, c->delsq, c->u, status_ptr(c), c->phinew);
   }
+  if (sp->conserve == 2 && (rc = phi_conserve_subtract_async(c, c->phinew, c->stream)) != 0) return rc;
   double * t = c->phi; c->phi = c->phinew; c->phinew = t;
   CTX_LEAVE_SYNC(c);
 }
@@ -2572,6 +2642,10 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     if (c->ndist == 1 && (rc = conserve_prepare(c, sp)) != 0) return rc;
     symm_dev(c, sp, &sd);
   }
+  // conserve 2: a global sum sits between the Cahn-Hilliard update and everything that reads the new phi -- the
+  // reference-structured step (halo kernels), not the halo-free one whose kernels hand planes to the neighbours as they go
+  const bool conserve2 = binary && c->ndist == 1 && sp->conserve == 2;
+  if (conserve2 && c->le.nplane > 0) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve 2 with Lees-Edwards planes is outside this build");
   if (nsteps <= 0) return 0;
   if (binary && c->knob_grad7 && (c->ndist != 1 || c->le.nplane > 0))
     return fail(LB200_EINVAL, "fd_gradient_calculation 3d_7pt_fluid: built for the finite-difference binary fluid without planes");
@@ -2598,7 +2672,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     const Lb200Geom & g = c->g;
     bool ok = wrap_enabled && g.per[0] && g.per[1] && g.per[2] && c->ndist == 1;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
-    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr && !c->knob_grad7;   // the one-sweep phi sector: orders 1-3, plain update
+    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr && !c->knob_grad7 && !conserve2;   // the one-sweep phi sector: orders 1-3, plain update
     if (ok && binary && pipe_eligible(c, nsteps)) return step_pipe(c, cd, sd, nsteps);
     if (ok) return step_wrap(c, cd, binary ? &sd : nullptr, nsteps);
   }
@@ -2666,6 +2740,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	}
       }
       c->force_state = INTERIOR_ONLY;
+      if (conserve2 && (rc = phi_conserve_subtract_async(c, c->phinew, S)) != 0) return rc;
       double * t = c->phi; c->phi = c->phinew; c->phinew = t;
       // halo of the NEW phi (needed by the next step's gradient) while the collision runs
       CUDA_TRY(cudaEventRecord(c->ev_main, S));

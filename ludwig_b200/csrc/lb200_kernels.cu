@@ -2319,6 +2319,102 @@ __global__ void spin_wait_kernel(const unsigned int * flag, unsigned int value, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// cahn_hilliard_options_conserve 2 (PHI_CONSERVE_GLOBAL_SUBTRACT): after the forward step the sum of phi over the
+// fluid sites is brought back to its initial value by subtracting (sum - sum0)/nfluid everywhere
+// (phi_ch_subtract_sum_phi_after_forward_step, src/phi_cahn_hilliard.c:1102-1169, kernels :1225-1319).  The
+// reference's own summation order depends on its thread count; here the order is fixed (so results are reproducible
+// run to run and independent of the GPU count up to the last bit of the sum) and the sum is compensated
+// (Neumaier), as the reference's statistics code compensates the initial sum (src/cahn_hilliard_stats.c:150-330).
+//   partial[2b], partial[2b+1] = (sum, compensation) of block b; partial[2 nblk] = fluid sites of the lattice
+// ---------------------------------------------------------------------------------------------
+
+constexpr int PSUM_BLOCKS = 256;
+constexpr int PSUM_TPB = 256;
+
+__device__ __forceinline__ void neumaier_add(double & sum, double & c, double v) {
+  const double t = sum + v;
+  c += (fabs(sum) >= fabs(v)) ? ((sum - t) + v) : ((v - t) + sum);
+  sum = t;
+}
+
+__global__ void __launch_bounds__(PSUM_TPB)
+phi_sum_partial_kernel(const Lb200Geom g, const double * __restrict__ phi, const char * __restrict__ status,
+		       double * __restrict__ partial) {
+  __shared__ double ssum[PSUM_TPB], scmp[PSUM_TPB];
+  __shared__ int scnt[PSUM_TPB];
+  const long long nint = (long long) g.nl[0]*g.nl[1]*g.nl[2];
+  double sum = 0.0, cmp = 0.0;
+  int cnt = 0;
+  // interior sites in (i, j, k) order, dealt round-robin to the threads of the grid
+  for (long long q = (long long) blockIdx.x*PSUM_TPB + threadIdx.x; q < nint; q += (long long) PSUM_BLOCKS*PSUM_TPB) {
+    const int kc = 1 + (int) (q % g.nl[2]);
+    const int jc = 1 + (int) ((q/g.nl[2]) % g.nl[1]);
+    const int ic = 1 + (int) (q/((long long) g.nl[2]*g.nl[1]));
+    const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+    if (status == nullptr || status[index] == 0) { neumaier_add(sum, cmp, phi[index]); cnt += 1; }
+  }
+  ssum[threadIdx.x] = sum; scmp[threadIdx.x] = cmp; scnt[threadIdx.x] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0, c = 0.0;
+    int n = 0;
+    for (int t = 0; t < PSUM_TPB; t++) { neumaier_add(s, c, ssum[t]); c += scmp[t]; n += scnt[t]; }
+    partial[2*blockIdx.x] = s; partial[2*blockIdx.x + 1] = c;
+    atomicAdd(reinterpret_cast<int *>(partial + 2*PSUM_BLOCKS), n);          // integer: order does not matter
+  }
+}
+
+// result[0] = compensated sum of the partials, result[1] = fluid sites (as a double); one thread, fixed order
+__global__ void phi_sum_final_kernel(double * __restrict__ partial, double * __restrict__ result) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0.0, c = 0.0;
+  for (int b = 0; b < PSUM_BLOCKS; b++) { neumaier_add(s, c, partial[2*b]); c += partial[2*b + 1]; }
+  result[0] = s + c;
+  result[1] = (double) *reinterpret_cast<int *>(partial + 2*PSUM_BLOCKS);
+  *reinterpret_cast<int *>(partial + 2*PSUM_BLOCKS) = 0;
+}
+
+// all[2r], all[2r+1] = (sum, nfluid) of rank r -> total[0], total[1], summed in rank order on every GPU
+__global__ void phi_sum_ranks_kernel(const double * __restrict__ all, int nranks, double * __restrict__ total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0.0, c = 0.0, n = 0.0;
+  for (int r = 0; r < nranks; r++) { neumaier_add(s, c, all[2*r]); n += all[2*r + 1]; }
+  total[0] = s + c; total[1] = n;
+}
+
+__global__ void __launch_bounds__(TPB_MAX)
+phi_subtract_kernel(const Lb200Geom g, const double * __restrict__ total, double phi0, const char * __restrict__ status,
+		    double * __restrict__ phi) {
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ic = 1 + blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+  const int index = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+  if (status != nullptr && status[index] != 0) return;
+  // phi -= (correct->phi - correct->phi0)/correct->nfluid, src/phi_cahn_hilliard.c:1312
+  phi[index] = phi[index] - (total[0] - phi0)/total[1];
+}
+
+int launch_phi_sum(cudaStream_t st, const Lb200Geom & g, const double * phi, const char * status, double * partial, double * result) {
+  phi_sum_partial_kernel<<<PSUM_BLOCKS, PSUM_TPB, 0, st>>>(g, phi, status, partial);
+  phi_sum_final_kernel<<<1, 32, 0, st>>>(partial, result);
+  return 2;
+}
+
+int launch_phi_sum_ranks(cudaStream_t st, const double * all, int nranks, double * total) {
+  phi_sum_ranks_kernel<<<1, 32, 0, st>>>(all, nranks, total);
+  return 1;
+}
+
+int launch_phi_subtract(cudaStream_t st, const Lb200Geom & g, const double * total, double phi0, const char * status, double * phi) {
+  dim3 blk;
+  block_shape(g.nl[2], blk);
+  dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
+  phi_subtract_kernel<<<grd, blk, 0, st>>>(g, total, phi0, status, phi);
+  return 1;
+}
+
 int launch_signal(cudaStream_t st, unsigned int * a, unsigned int * b, unsigned int value) {
   signal_kernel<<<1, 32, 0, st>>>(a, b, value);
   return 1;
@@ -2396,4 +2492,8 @@ const Lb200Kernels LB200_TABLE = {
   launch_f_convert,
   launch_collide_f32,
   launch_step_fused,
+  launch_phi_sum,
+  launch_phi_sum_ranks,
+  launch_phi_subtract,
+  PSUM_BLOCKS,
 };

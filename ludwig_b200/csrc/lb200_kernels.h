@@ -178,6 +178,13 @@ struct Lb200Kernels {
   int (*step_fused)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, const Lb200CollideDev &,
 		    const double * phi, const double * u_in, const double * fsrc, double * fdst, double * grad,
 		    double * delsq, double * force, double * phinew, double * rho, double * u_out);
+  // cahn_hilliard_options_conserve 2: result[0] = compensated sum of phi over the fluid interior sites of this GPU in a
+  // fixed order, result[1] = their number; partial: 2*psum_blocks + 1 doubles of scratch (zero before the first call).
+  // phi_sum_ranks: all[2r], all[2r+1] of every rank -> total[0..1] in rank order.  phi_subtract: phi -= (total[0] - phi0)/total[1]
+  int (*phi_sum)(cudaStream_t, const Lb200Geom &, const double * phi, const char * status, double * partial, double * result);
+  int (*phi_sum_ranks)(cudaStream_t, const double * all, int nranks, double * total);
+  int (*phi_subtract)(cudaStream_t, const Lb200Geom &, const double * total, double phi0, const char * status, double * phi);
+  int psum_blocks;
 };
 
 extern const Lb200Kernels lb200_kernels_fast;

@@ -817,6 +817,56 @@ void orc_phi_update(const orc_geom_t * g, const double * flux, double * phi) {
   }
 }
 
+/* ---- cahn_hilliard_options_conserve 2 (all-fluid lattices) ------------------------------------------------------
+ * phi_ch_subtract_sum_phi_after_forward_step, src/phi_cahn_hilliard.c:1102-1169: kernel1 (:1225-1282) adds phi over the fluid
+ * sites with plain += (here: one thread, i.e. (ic, jc, kc) order), kernel2 (:1290-1319) subtracts (sum - phi0)/nfluid.
+ * phi0 = phi->field_init_sum from cahn_hilliard_stats_time0 (src/cahn_hilliard_stats.c:58-76): with conserve != 0 the
+ * statistics use the doubly compensated (Klein) sum of csum (zero at time 0) and phi, src/cahn_hilliard_stats.c:270-330,
+ * src/util_sum.c:108-180 -- restated for one thread. */
+
+typedef struct { double sum, cs, ccs; } orc_klein_t;
+
+static void orc_klein_add_double(orc_klein_t * k, double val) {        /* klein_add_double, src/util_sum.c:144-166 */
+  double t, c, cc;
+  t = k->sum + val;
+  if (fabs(k->sum) >= fabs(val)) c = (k->sum - t) + val;
+  else                           c = (val - t) + k->sum;
+  k->sum = t;
+  t = k->cs + c;
+  if (fabs(k->cs) >= fabs(c)) cc = (k->cs - t) + c;
+  else                        cc = (c - t) + k->cs;
+  k->cs = t;
+  k->ccs = k->ccs + cc;
+}
+
+double orc_phi_sum_time0(const orc_geom_t * g, const double * phi) {
+  orc_klein_t thread = {0.0, 0.0, 0.0}, block = {0.0, 0.0, 0.0}, total = {0.0, 0.0, 0.0};
+  for (int ic = 1; ic <= g->nlocal[X]; ic++)
+    for (int jc = 1; jc <= g->nlocal[Y]; jc++)
+      for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
+	orc_klein_add_double(&thread, 0.0);                                  /* the compensation field, zero at time 0 */
+	orc_klein_add_double(&thread, phi[orc_index(g, ic, jc, kc)]);
+      }
+  /* the per-thread, per-block and global accumulations (klein_add, src/util_sum.c:168-180) for one thread, one block */
+  orc_klein_add_double(&block, thread.sum); orc_klein_add_double(&block, thread.cs); orc_klein_add_double(&block, thread.ccs);
+  orc_klein_add_double(&total, block.sum); orc_klein_add_double(&total, block.cs); orc_klein_add_double(&total, block.ccs);
+  return total.sum + total.cs + total.ccs;                                   /* klein_sum */
+}
+
+void orc_phi_subtract_sum(const orc_geom_t * g, double phi_init_sum, double * phi) {
+  double sum = 0.0;
+  int nfluid = 0;
+  for (int ic = 1; ic <= g->nlocal[X]; ic++)
+    for (int jc = 1; jc <= g->nlocal[Y]; jc++)
+      for (int kc = 1; kc <= g->nlocal[Z]; kc++) { sum += phi[orc_index(g, ic, jc, kc)]; nfluid += 1; }
+  for (int ic = 1; ic <= g->nlocal[X]; ic++)
+    for (int jc = 1; jc <= g->nlocal[Y]; jc++)
+      for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
+	const int index = orc_index(g, ic, jc, kc);
+	phi[index] -= (sum - phi_init_sum)/nfluid;
+      }
+}
+
 /* ---- phi_ch_update_conserve -> phi_ch_csum_kernel: src/phi_cahn_hilliard.c:1059-1094, 1181-1215, with
  * kahan_add_double (src/util_sum.c:30-40: y = val + cs; t = sum + y; cs = y - (t - sum); sum = t).
  * csum is the per-site compensation carried from step to step (pch->csum, zero at creation). ---- */
@@ -901,6 +951,7 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
       orc_no_flux(g, NULL, flux);
       if (csum) orc_phi_update_conserve(g, flux, csum, phi);
       else      orc_phi_update(g, flux, phi);
+      if (sp->conserve == 2) orc_phi_subtract_sum(g, sp->phi_init_sum, phi);
     }
     orc_field_set(g, 3, u, zero);
     orc_collide(g, m, cp, NULL, 0, f, force, rho, u);

@@ -61,8 +61,9 @@ typedef struct orc_symm_param_s {
   double mobility;
   double gradmu[3];
   int adv_order;         /* 1 .. 4 */
-  int conserve;          /* cahn_hilliard_options_conserve: 0, or 1 = compensated sum (PHI_CONSERVE_COMPENSATED_SUM) */
+  int conserve;          /* cahn_hilliard_options_conserve: 0, 1 = compensated sum, 2 = global subtraction after the forward step */
   int grad_7pt;          /* fd_gradient_calculation: 0 = 3d_27pt_fluid, 1 = 3d_7pt_fluid (whole steps, orc_step) */
+  double phi_init_sum;   /* conserve 2: phi->field_init_sum, the sum the global correction restores (orc_phi_sum_time0) */
 } orc_symm_param_t;
 
 int orc_nsites(const orc_geom_t * g);          /* hydro, fields, gradients, fluxes: with the LE buffer planes */
@@ -70,6 +71,10 @@ int orc_nsites_lb(const orc_geom_t * g);       /* distributions, map: cs_nsites 
 int orc_index(const orc_geom_t * g, int ic, int jc, int kc);
 
 int orc_model_create(int nvel, orc_model_t * model);
+
+/* cahn_hilliard_options_conserve 2 */
+double orc_phi_sum_time0(const orc_geom_t * g, const double * phi);
+void orc_phi_subtract_sum(const orc_geom_t * g, double phi_init_sum, double * phi);
 
 /* lb_propagation: fprime <- pull(f) on the interior, self copy on y/z halo of x in [1,N] */
 void orc_propagation(const orc_geom_t * g, const orc_model_t * m, int ndist,

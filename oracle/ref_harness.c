@@ -54,6 +54,7 @@
 #include "gradient_3d_7pt_fluid.h"
 #include "colloids.h"
 #include "io_event.h"
+#include "cahn_hilliard_stats.h"
 
 typedef struct ref_cfg_s {
   int ntotal[3];
@@ -423,6 +424,13 @@ double ref_lc_fed_sum(ref_sim_t * s) {
       }
   return sum;
 }
+/* cahn_hilliard_options_conserve 2: the initial sum of the driver's statistics code (src/ludwig.c calls it once before the loop) */
+double ref_phi_stats_time0(ref_sim_t * s) {
+  cahn_hilliard_stats_time0(s->pch, s->phi, s->map);
+  return s->phi->field_init_sum;
+}
+int ref_phi_init_sum_set(ref_sim_t * s, double v) { s->phi->field_init_sum = v; return 0; }
+
 int ref_cahn_hilliard(ref_sim_t * s) {
   return phi_cahn_hilliard(s->pch, (fe_t *) s->fe, s->phi, s->hydro, s->map, NULL);
 }

@@ -112,7 +112,14 @@ def main():
     sim.set_knob(lb.KNOB_PEER, peer)
     sim.put(lb.F, slab(st["f"])); sim.put(lb.PHI, slab(st["phi"]))
     cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA, force=fg)
-    sp = lb.SymmParam.make(adv_order=3, **BINARY)
+    conserve2 = bool(os.environ.get("LB200_TEST_CONSERVE2"))
+    sp = lb.SymmParam.make(adv_order=3, conserve=2 if conserve2 else 0, **BINARY)
+    sum0 = 0.0
+    if conserve2:
+        # cahn_hilliard_options_conserve 2: the initial sum over ALL slabs (collective), offset so that the correction is visible
+        sum0 = sim.phi_conserve_sum() + 1.0e-3
+        assert abs(sum0 - 1.0e-3 - orc_g.phi_sum_time0(st["phi"])) <= 4*np.spacing(abs(sum0))
+        sim.phi_init_sum_set(sum0)
     # every path over the decomposed lattice, and the hand-overs between them: halo-free lb200_step (only the
     # planes the kernels read cross NVLink), the individual entry points (full halo swaps), lb200_step again
     if not binary:
@@ -136,7 +143,8 @@ def main():
             orc_g.le_step(orc_g.collide_param(0, 1.0, ETA, force=fg), orc_g.symm_param(adv_order=3, **BINARY), 0, nsteps,
                           st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
         elif binary:
-            orc_g.step(orc_g.collide_param(0, 1.0, ETA, force=fg), orc_g.symm_param(adv_order=3, **BINARY), 1, nsteps,
+            orc_g.step(orc_g.collide_param(0, 1.0, ETA, force=fg),
+                       orc_g.symm_param(adv_order=3, conserve=2 if conserve2 else 0, phi_init_sum=sum0, **BINARY), 1, nsteps,
                        st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"], halo_reduced=reduced)
         else:
             orc_g.step(orc_g.collide_param(0, 1.0, ETA, force=fg), None, 0, nsteps,
@@ -145,7 +153,7 @@ def main():
             if not binary and k in ("phi", "force"):
                 continue
             full = np.concatenate([g[k] for g in gathered], axis=1)
-            same = close_fast(full, orc_g.interior(st[k])) if fast else np.array_equal(full, orc_g.interior(st[k]))
+            same = close_fast(full, orc_g.interior(st[k])) if (fast or conserve2) else np.array_equal(full, orc_g.interior(st[k]))
             print(f"multigpu parity world={world} periodic={periodic} reduced={reduced} {k}: {'OK' if same else 'MISMATCH'}", flush=True)
             ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -51,7 +51,7 @@ class CollideParam(C.Structure):
 class SymmParam(C.Structure):
     _fields_ = [("a", C.c_double), ("b", C.c_double), ("kappa", C.c_double),
                 ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int), ("conserve", C.c_int),
-                ("grad_7pt", C.c_int)]
+                ("grad_7pt", C.c_int), ("phi_init_sum", C.c_double)]
 
 
 _lib = None
@@ -123,10 +123,11 @@ class Oracle:
         cp.force_global[:] = force
         return cp
 
-    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1, conserve=0, grad_7pt=0):
+    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1, conserve=0, grad_7pt=0, phi_init_sum=0.0):
         sp = SymmParam()
         sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order, sp.conserve = a, b, kappa, mobility, adv_order, conserve
         sp.grad_7pt = grad_7pt
+        sp.phi_init_sum = phi_init_sum
         sp.gradmu[:] = gradmu
         return sp
 
@@ -189,6 +190,13 @@ class Oracle:
 
     def phi_update(self, flux, phi):
         self.lib.orc_phi_update(C.byref(self.g), _p(flux), _p(phi))
+
+    def phi_sum_time0(self, phi):
+        self.lib.orc_phi_sum_time0.restype = C.c_double
+        return self.lib.orc_phi_sum_time0(C.byref(self.g), _p(phi))
+
+    def phi_subtract_sum(self, phi_init_sum, phi):
+        self.lib.orc_phi_subtract_sum(C.byref(self.g), C.c_double(phi_init_sum), _p(phi))
 
     def phi_update_conserve(self, flux, csum, phi):
         self.lib.orc_phi_update_conserve(C.byref(self.g), _p(flux), _p(csum), _p(phi))

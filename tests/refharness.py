@@ -70,6 +70,9 @@ def _lib(fast=False, nvel=19):
         lib.ref_lc_fed_sum.argtypes = [C.c_void_p]
         lib.ref_lc_fed_sum.restype = C.c_double
         lib.ref_nvel.restype = C.c_int
+        lib.ref_phi_stats_time0.argtypes = [C.c_void_p]
+        lib.ref_phi_stats_time0.restype = C.c_double
+        lib.ref_phi_init_sum_set.argtypes = [C.c_void_p, C.c_double]
         if hasattr(lib, "ref_omp_threads"):
             lib.ref_omp_threads.argtypes = [C.c_int]
             lib.ref_omp_threads.restype = C.c_int
@@ -165,6 +168,13 @@ class RefSim:
     def io(self, name, timestep):
         """lb_io_write / lb_io_read / field_io_write / field_io_read in the current directory"""
         return getattr(self.lib, "ref_" + name)(self.h, timestep)
+
+    def phi_stats_time0(self):
+        """cahn_hilliard_stats_time0: sets and returns phi->field_init_sum (needed by conserve 2)"""
+        return self.lib.ref_phi_stats_time0(self.h)
+
+    def phi_init_sum_set(self, v):
+        self.lib.ref_phi_init_sum_set(self.h, v)
 
     def op(self, name):
         return getattr(self.lib, "ref_" + name)(self.h)

@@ -76,6 +76,24 @@ def test_one_kernel_step_on_slabs_matches_single_domain_oracle(peer):
 
 
 @pytest.mark.gpu
+def test_conserve_2_all_gather_on_slabs(monkeypatch):
+    """cahn_hilliard_options_conserve 2 over 2 (4) GPUs: the one global reduction of the path (NCCL all-gather of one pair per
+    GPU, added in rank order) -- initial sum and corrected steps against the undecomposed oracle"""
+    n = ngpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    env = dict(os.environ, LB200_TEST_CONSERVE2="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(HERE, "multigpu_parity.py"),
+           "111", "0", "0", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+    assert "MISMATCH" not in r.stdout and "OK" in r.stdout
+
+
+@pytest.mark.gpu
 def test_liquid_crystal_slabs_match_single_domain_oracle():
     """liquid crystal (Q tensor + Beris-Edwards) on x-slabs: lb200_step_lc and the individual entry points over
     2 (4) GPUs == the undecomposed liquid-crystal oracle, bit for bit (strict mode, NCCL x-planes of q, u, f)."""

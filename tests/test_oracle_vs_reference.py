@@ -435,3 +435,37 @@ def test_binary_time_steps_on_thin_lattices(nlocal, order):
              st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
     for k in ref:
         assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k
+
+
+def test_conserve_2_global_subtraction_vs_reference():
+    """cahn_hilliard_options_conserve 2 (phi_ch_subtract_sum_phi_after_forward_step, src/phi_cahn_hilliard.c:1102-1169): the
+    initial sum of the statistics code (doubly compensated) and whole time steps with the correction, oracle == compiled
+    reference bit for bit with one OpenMP thread (the reference's own summation order depends on its thread count).  With a
+    deliberately offset initial sum the correction is far above rounding, so the test also shows that it is applied."""
+    nlocal, nsteps = (8, 6, 10), 5
+    orc = Oracle(nlocal, nhalo=2)
+    before = rh.omp_threads(0)
+    rh.omp_threads(1)
+    try:
+        for offset in (0.0, 1.0e-3):
+            with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=3, conserve=2, ghost_off=1, eta_shear=ETA, **BINARY) as s:
+                s.init_rest(1.0)
+                s.init_spinodal(8361235, 0.0, 0.05)
+                f, phi = s.get(rh.REF_F), s.get(rh.REF_PHI)
+                sum0 = s.phi_stats_time0()
+                assert sum0 == orc.phi_sum_time0(phi)
+                s.phi_init_sum_set(sum0 + offset)
+                s.step(nsteps)
+                ref = {k: s.get(w) for k, w in (("f", rh.REF_F), ("phi", rh.REF_PHI), ("u", rh.REF_U))}
+            st = dict(f=f.copy(), phi=phi.copy(), u=np.zeros((3, orc.nsites)), rho=np.zeros((1, orc.nsites)),
+                      force=np.zeros((3, orc.nsites)), grad=np.zeros((3, orc.nsites)), delsq=np.zeros((1, orc.nsites)))
+            orc.step(orc.collide_param(0, 1.0, ETA), orc.symm_param(adv_order=3, conserve=2, phi_init_sum=sum0 + offset, **BINARY), 1, nsteps,
+                     st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+            for k in ref:
+                assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), (k, offset)
+            if offset:
+                # the sum has been pulled to the offset value
+                assert abs(orc.interior(st["phi"]).sum() - (sum0 + offset)) < 1e-12
+    finally:
+        if before > 0:
+            rh.omp_threads(before)
