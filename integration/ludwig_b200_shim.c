@@ -44,6 +44,9 @@
 #include "leesedwards.h"
 #include "noise.h"
 #include "wall.h"
+#include "colloids.h"
+#include "blue_phase.h"
+#include "blue_phase_beris_edwards.h"
 
 #include "ludwig_b200.h"
 
@@ -340,6 +343,49 @@ int __wrap_field_grad_compute(field_grad_t * obj) {               /* src/field_g
   return __real_field_grad_compute(obj);
 }
 
+/* ---- liquid crystal: parameters ------------------------------------------------------------------------------ */
+
+/* beris_edw_t is opaque outside its own file: the rotational diffusion constant is taken where the driver sets it */
+static beris_edw_param_t be_param_;
+static int be_param_known_ = 0;
+
+int __real_beris_edw_param_set(beris_edw_t * be, beris_edw_param_t * values);
+int __wrap_beris_edw_param_set(beris_edw_t * be, beris_edw_param_t * values) {   /* src/blue_phase_beris_edwards.c:215-225 */
+  be_param_ = *values;
+  be_param_known_ = 1;
+  return __real_beris_edw_param_set(be, values);
+}
+
+static void b200_lc_param(pe_t * pe, fe_t * fe, lb200_lc_param_t * lc) {
+  const fe_lc_param_t * p = ((fe_lc_t *) fe)->param;
+  memset(lc, 0, sizeof(*lc));
+  if (p->is_active) pe_fatal(pe, "libludwig_b200: active liquid crystals are outside this library\n");
+  if (p->is_redshift_updated || p->redshift != 1.0) pe_fatal(pe, "libludwig_b200: redshift != 1 is outside this library\n");
+  lc->a0 = p->a0; lc->q0 = p->q0; lc->gamma = p->gamma; lc->kappa0 = p->kappa0; lc->kappa1 = p->kappa1; lc->xi = p->xi;
+  lc->epsilon = p->epsilon;
+  for (int a = 0; a < 3; a++) lc->e0[a] = p->e0[a]*p->coswt;
+  lc->Gamma = be_param_known_ ? be_param_.gamma : 0.0;
+  advection_order(&lc->adv_order);
+}
+
+int __real_beris_edw_update(beris_edw_t * be, fe_t * fe, field_t * fq, field_grad_t * fq_grad, hydro_t * hydro,
+			    colloids_info_t * cinfo, map_t * map, noise_t * noise);
+int __wrap_beris_edw_update(beris_edw_t * be, fe_t * fe, field_t * fq, field_grad_t * fq_grad, hydro_t * hydro,
+			    colloids_info_t * cinfo, map_t * map, noise_t * noise) {   /* src/blue_phase_beris_edwards.c:266-296 */
+  slot_t * s = slot_find(fq->cs, 0);
+  lb200_lc_param_t lc;
+  int ncolloid = 0;
+  if (s == NULL || s->ctx == NULL || b200_field_array(s, fq) != LB200_Q) return __real_beris_edw_update(be, fe, fq, fq_grad, hydro, cinfo, map, noise);
+  if (hydro == NULL) pe_fatal(fq->pe, "libludwig_b200: beris_edw_update without hydrodynamics is outside this library\n");
+  if (cinfo) colloids_info_ntotal(cinfo, &ncolloid);
+  if (ncolloid > 0) pe_fatal(fq->pe, "libludwig_b200: colloids are outside this library\n");
+  if (!be_param_known_ || be_param_.noise) pe_fatal(fq->pe, "libludwig_b200: order-parameter noise is outside this library\n");
+  if (fe == NULL || fe->id != FE_LC) pe_fatal(fq->pe, "libludwig_b200: beris_edw_update: free_energy lc_blue_phase only\n");
+  b200_lc_param(fq->pe, fe, &lc);
+  b200_check(fq->pe, lb200_beris_edw_update(s->ctx, &lc), "beris_edw_update");
+  return 0;
+}
+
 /* ---- order-parameter sector ---------------------------------------------------------------------------------- */
 
 int __real_phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t * wall, pth_t * pth, fe_t * fe, map_t * map,
@@ -350,12 +396,21 @@ int __wrap_phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t *
   lb200_symm_param_t sp;
   if (hydro == NULL) return 0;
   if (pth->method == FE_FORCE_METHOD_NO_FORCE) return 0;
+  if (s != NULL && s->ctx != NULL && s->has_q && fe != NULL && fe->id == FE_LC) {
+    /* liquid crystal: pth_stress_compute (fe_lc_stress_v) + pth_force_fluid_driver, src/phi_force.c:100-110 */
+    lb200_lc_param_t lc;
+    if (pth->method != FE_FORCE_METHOD_STRESS_DIVERGENCE) pe_fatal(pe, "libludwig_b200: fe_force_method stress_divergence only\n");
+    if (wall_present(wall)) pe_fatal(pe, "libludwig_b200: walls are outside this library\n");
+    b200_lc_param(pe, fe, &lc);
+    b200_check(pe, lb200_lc_force_calculation(s->ctx, &lc), "phi_force_calculation (liquid crystal)");
+    return 0;
+  }
   if (s == NULL || s->ctx == NULL || b200_field_array(s, phi) != LB200_PHI) {
     return __real_phi_force_calculation(pe, cs, le, wall, pth, fe, map, phi, hydro);
   }
-  if (fe == NULL || fe->id != FE_SYMMETRIC) pe_fatal(pe, "libludwig_b200: phi_force_calculation: free_energy symmetric only\n");
   if (pth->method != FE_FORCE_METHOD_STRESS_DIVERGENCE) pe_fatal(pe, "libludwig_b200: fe_force_method stress_divergence only\n");
   if (wall_present(wall)) pe_fatal(pe, "libludwig_b200: walls are outside this library\n");
+  if (fe == NULL || fe->id != FE_SYMMETRIC) pe_fatal(pe, "libludwig_b200: phi_force_calculation: free_energy symmetric / lc_blue_phase only\n");
   b200_symm_param(fe, NULL, &sp);
   b200_time_sync(pe, s);
   b200_check(pe, lb200_phi_force_calculation(s->ctx, &sp), "phi_force_calculation");

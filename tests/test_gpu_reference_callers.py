@@ -55,6 +55,16 @@ CASES = {
                         "fd_gradient_calculation": "3d_27pt_fluid", "fd_advection_scheme_order": "3", "colloid_init": "no_colloids",
                         "periodicity": "1_1_1", "freq_statistics": "50", "config_at_end": "no", "N_LE_plane": "2",
                         "LE_plane_vel": "0.05", "LE_init_profile": "1", "random_seed": "-7361237"},
+    # liquid crystal: Landau-de Gennes Q tensor + Beris-Edwards (BASELINE config 4; the configuration of
+    # tests/regression/d3q19/pmpi08-chol-s01 at 48 x 32 x 64)
+    "cholesteric": {"N_start": "0", "N_cycles": "10", "size": "48_32_64", "reduced_halo": "no", "viscosity": "1.0",
+                    "isothermal_fluctuations": "off", "free_energy": "lc_blue_phase", "fd_advection_scheme_order": "3",
+                    "fd_gradient_calculation": "3d_7pt_fluid", "lc_a0": "0.01", "lc_gamma": "3.0", "lc_q0": "0.19635",
+                    "lc_kappa0": "0.000648456", "lc_kappa1": "0.000648456", "lc_xi": "0.7", "lc_Gamma": "0.5",
+                    "lc_q_initialisation": "twist", "lc_q_init_amplitude": "0.333333333333333", "lc_init_redshift": "1.0",
+                    "lc_anchoring_method": "two", "lc_wall_anchoring": "normal", "lc_coll_anchoring": "normal",
+                    "lc_anchoring_strength_colloid": "0.002593824", "colloid_init": "no_colloids", "periodicity": "1_1_1",
+                    "freq_statistics": "10", "config_at_end": "no", "random_seed": "8361235"},
 }
 
 # lines tests/test-diff.sh deletes before comparing
