@@ -131,16 +131,31 @@ __device__ __forceinline__ void fu_plane_sums(const double * __restrict__ q, int
 #define FU_AD(member) (k.smb + (unsigned int) offsetof(FuShared<BY>, member))
 
 // pull-stream + collision of the own site of plane m with the force (F0, F1, F2) (lb_collide, src/collision.c:253-593)
-template <bool GHOST, int BY>
+// the 19 populations pulled to the own site of plane m, out of the staged boxes (waits for the stage to land)
+template <int BY>
+__device__ __forceinline__ void fu_collide_read(FuShared<BY> & sm, const FuK & k, const int m, double (&f)[19]) {
+  const int st = (m - k.i0) % FU_NSTAGE;
+  fu_mbar_wait(FU_AD(full) + 8u*st, (unsigned int) (((m - k.i0)/FU_NSTAGE) & 1));
+  const double * __restrict__ fb = &sm.f[st][0][k.frow*FU_ROW + k.flane];
+#pragma unroll
+  for (int p = 0; p < 19; p++) f[p] = fb[p*FuGeo<BY>::FBLK + 1 - CV19[p][2]];
+}
+
+template <bool GHOST, int BY, bool HAVE_F = false>
 __device__ __forceinline__ void fu_collide(FuShared<BY> & sm, const FuK & k, const Lb200CollideDev & cp, const int m,
 					   const double F0, const double F1, const double F2,
 					   const double * __restrict__ fsrc, double * __restrict__ fdst,
 					   double * __restrict__ force, double * __restrict__ rho_out,
-					   double * __restrict__ u_out) {
+					   double * __restrict__ u_out, const double * fin = nullptr) {
   const size_t s = (size_t) ((m + k.nh - 1)*k.xs + k.scol);
   double f[19], mode[19], fo[3], uu[3], rho;
 
-  if (k.fmode == 1) {
+  if (HAVE_F) {
+    // (the caller has taken the populations out of the stage already: fu_collide_read)
+#pragma unroll
+    for (int p = 0; p < 19; p++) f[p] = fin[p];
+  }
+  else if (k.fmode == 1) {
     const int oxm = (k.wx && m == 1)     ?  (k.nlx - 1)*k.xs : -k.xs;
     const int oxp = (k.wx && m == k.nlx) ? -(k.nlx - 1)*k.xs :  k.xs;
 #pragma unroll
@@ -612,6 +627,10 @@ int launch_step_fused_by(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDe
   return 1;
 }
 
+int launch_step_fused_ws(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const Lb200CollideDev & cp,
+			 const double * phi, const double * u, const double * fsrc, double * fdst, double * grad,
+			 double * delsq, double * force, double * phinew, double * rho, double * u_out);
+
 // 1: launched; 0: this build / configuration has no one-kernel step (the caller runs the two-kernel step)
 int launch_step_fused(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const Lb200CollideDev & cp,
 		      const double * phi, const double * u, const double * fsrc, double * fdst, double * grad,
@@ -619,6 +638,8 @@ int launch_step_fused(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
   if (sp.order < 1 || sp.order > 3 || sp.csum != nullptr) return 0;
   // the staged source rows start at even array indices: 16-byte aligned only if every row does
   if (g.nh != 2 || (g.nall[2] & 1) || (g.nsites & 1) || (g.nl[2] & 1) || g.nl[1] < 2 || g.nl[2] < 2) return 0;
+  static const int ws = tuned_flag("LB200_FUSED_WS", 1);      // warp-specialised roles (lb200_fused_ws.cuh); 0: every warp does both halves
+  if (ws) return launch_step_fused_ws(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
   static const int by = tuned_flag("LB200_FUSED_BY", 10);
   if (by == 8) return launch_step_fused_by<8>(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
   return launch_step_fused_by<10>(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);

@@ -2451,6 +2451,7 @@ int launch_zero_outside(cudaStream_t st, const Lb200Geom & g, int ncomp, double 
 }
 
 #include "lb200_fused.cuh"
+#include "lb200_fused_ws.cuh"
 #include "lb200_le.cuh"
 #include "lb200_lc.cuh"
 
