@@ -672,8 +672,8 @@ def run_ours(args, rank, local_rank, world):
                        "e2e_protocol": "pinned-host f+phi -> device, K steps, phi+u+rho -> pinned host "
                                        "(the reference's own lb_memcpy/field_memcpy usage, src/ludwig.c:501-506, 985)",
                        "host_buffers_numa_node": (numa[1] if numa else None)},
-            "roofline": ({"bound": "hbm", "kernel": "step_fused (27pt gradient + stress-divergence force + Cahn-Hilliard + pull-stream + MRT "
-                                                    "collision in one sweep; populations by TMA tensor copies)",
+            "roofline": ({"bound": "hbm", "kernel": "step_fused_ws (27pt gradient + stress-divergence force + Cahn-Hilliard + pull-stream + MRT "
+                                                    "collision in one sweep: warp-specialised phi-sector / collision / TMA-loader warps)",
                           "achieved": fu_ach, "peak": peak, "unit": "GB/s", "frac": (fu_ach / peak if fu_ach else None),
                           "traffic": fu_traffic, "peak_source": peak_src,
                           "algorithmic_bytes_per_site": fu_alg,
