@@ -1821,7 +1821,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   // (fast arithmetic mode; the TMA boxes of the populations need 16-byte aligned rows: even extents in z)
   const bool fuse_ok = binary && c->knob_fused && !le && !f32 && c->nvel == 19 && c->unrolled19 && c->ndist == 1
     && c->map_all_fluid && c->knob_pipe < 2 && sd->order <= 3 && sd->csum == nullptr
-    && c->opt.math == LB200_MATH_FAST && c->g.nh == 2 && (c->g.nall[2] & 1) == 0 && (c->g.nsites & 1) == 0
+    && c->g.nh == 2 && (c->g.nall[2] & 1) == 0 && (c->g.nsites & 1) == 0
     && c->g.nl[1] >= 2 && c->g.nl[2] >= 2;
   if (fuse_ok && c->u_alloc[1] == nullptr) {
     if (alloc_d(&c->u2, (size_t) 3*c->g.nsites) != 0) return LB200_ECUDA;

@@ -27,8 +27,7 @@
 // u is double-buffered by the caller (the phi sector reads u(t-1) of neighbouring sites while the collision of
 // other CTAs writes u(t)); phi / phinew and f / fprime are double-buffered anyway.
 
-#ifndef LB200_STRICT
-
+constexpr int FU_RING = 6;                   // phi planes in flight: n .. n+2 read, n+3 landed, n+4 in flight
 constexpr int FU_NSTAGE = 3;
 constexpr int FU_ROW = 34;                   // doubles per staged row: pulled z range [kbase, kbase+31] inside an aligned run
 
@@ -47,13 +46,13 @@ template <int BY> struct FuGeo {
 
 template <int BY> struct FuShared {
   double f[FU_NSTAGE][19][FuGeo<BY>::FBLK];  // staged boxes [TY rows][34] of the pulled populations
-  double phi[PF_RING][FuGeo<BY>::PSLOT];     // ring of phi planes [PY rows][34], slot = (plane - first plane) % 6
+  double phi[FU_RING][FuGeo<BY>::PSLOT];     // ring of phi planes [PY rows][34], slot = (plane - first plane) % 6
   double u[3][2][FuGeo<BY>::USLOT];          // u_y, u_z planes [BY rows][34], slot = plane % 3
   double ux[3][FuGeo<BY>::USLOT];            // u_x, slot = plane % 3
   double g[2][6][FuGeo<BY>::NT];             // Pxy, Pyy, Pyz, Pxz, Pzz, mu of a plane
   double fl[2][2][FuGeo<BY>::NT];            // y and z face fluxes (face between the site and site+1)
   unsigned long long full[FU_NSTAGE];        // mbarriers: the populations of a stage have landed
-  unsigned long long pl[PF_RING];            // mbarriers: the phi / u planes issued at phase q have landed
+  unsigned long long pl[FU_RING];            // mbarriers: the phi / u planes issued at phase q have landed
 };
 
 struct FuK {                                 // per-thread / per-CTA constants
@@ -243,6 +242,7 @@ __device__ __forceinline__ void fu_collide(FuShared<BY> & sm, const FuK & k, con
   }
 }
 
+#ifndef LB200_STRICT
 template <int ORDER, bool GHOST, int BY>
 __global__ void __launch_bounds__(FuGeo<BY>::NT, 1)
 step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap phimap,
@@ -322,7 +322,7 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
 #pragma unroll
     for (int s = 0; s < FU_NSTAGE; s++) fu_mbar_init(FU_AD(full) + 8u*s, (unsigned int) BY);
 #pragma unroll
-    for (int s = 0; s < PF_RING; s++) fu_mbar_init(FU_AD(pl) + 8u*s, 1u);
+    for (int s = 0; s < FU_RING; s++) fu_mbar_init(FU_AD(pl) + 8u*s, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
 
@@ -542,6 +542,8 @@ step_fused_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
   }
 }
 
+#endif   // the every-warp-does-both kernel: fast arithmetic mode only
+
 // Tensor maps of the distribution arrays (rank 4: z, y, x, population; box 34 x TY x 1 x 1), created on first use
 // through the driver entry point and cached per (array, geometry, box).
 typedef CUresult (*fu_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -587,6 +589,7 @@ static bool fu_tensor_map(const double * a, const Lb200Geom & g, int ncomp, int 
   return true;
 }
 
+#ifndef LB200_STRICT
 template <int BY>
 int launch_step_fused_by(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const Lb200CollideDev & cp,
 			 const double * phi, const double * u, const double * fsrc, double * fdst, double * grad,
@@ -627,30 +630,26 @@ int launch_step_fused_by(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDe
   return 1;
 }
 
+#endif
+
 int launch_step_fused_ws(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const Lb200CollideDev & cp,
 			 const double * phi, const double * u, const double * fsrc, double * fdst, double * grad,
 			 double * delsq, double * force, double * phinew, double * rho, double * u_out);
 
-// 1: launched; 0: this build / configuration has no one-kernel step (the caller runs the two-kernel step)
+// 1: launched; 0: this configuration has no one-kernel step (the caller runs the two-kernel step)
 int launch_step_fused(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const Lb200CollideDev & cp,
 		      const double * phi, const double * u, const double * fsrc, double * fdst, double * grad,
 		      double * delsq, double * force, double * phinew, double * rho, double * u_out) {
   if (sp.order < 1 || sp.order > 3 || sp.csum != nullptr) return 0;
   // the staged source rows start at even array indices: 16-byte aligned only if every row does
   if (g.nh != 2 || (g.nall[2] & 1) || (g.nsites & 1) || (g.nl[2] & 1) || g.nl[1] < 2 || g.nl[2] < 2) return 0;
+#ifndef LB200_STRICT
   static const int ws = tuned_flag("LB200_FUSED_WS", 1);      // warp-specialised roles (lb200_fused_ws.cuh); 0: every warp does both halves
-  if (ws) return launch_step_fused_ws(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
-  static const int by = tuned_flag("LB200_FUSED_BY", 10);
-  if (by == 8) return launch_step_fused_by<8>(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
-  return launch_step_fused_by<10>(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
-}
-
-#else
-
-int launch_step_fused(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, const Lb200CollideDev &,
-		      const double *, const double *, const double *, double *, double *,
-		      double *, double *, double *, double *, double *) {
-  return 0;
-}
-
+  if (!ws) {
+    static const int by = tuned_flag("LB200_FUSED_BY", 10);
+    if (by == 8) return launch_step_fused_by<8>(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
+    return launch_step_fused_by<10>(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
+  }
 #endif
+  return launch_step_fused_ws(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
+}

@@ -14,8 +14,6 @@
 // (setmaxnreg was tried first -- 12 producer warps at 120-128 registers, 8 consumer warps at 64: it deadlocks, because the
 // increase can only be served from what the decrease of the SAME CTA released, 8 x 32 x 32 registers < 12 x 32 x 24.)
 
-#ifndef LB200_STRICT
-
 constexpr int FW_BY = 10;                            // tile rows incl. apron (producer warps 0 .. 9)
 constexpr int FW_NPROD = 10;                         // producer warps = tile rows
 constexpr int FW_NCONS = 8;                          // consumer warps = interior rows
@@ -122,7 +120,7 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
 #pragma unroll
     for (int s = 0; s < FU_NSTAGE; s++) { fu_mbar_init(FU_AD(full) + 8u*s, 1u); fu_mbar_init(FW_AD(sempty) + 8u*s, (unsigned int) FW_NCONS); }
 #pragma unroll
-    for (int s = 0; s < PF_RING; s++) fu_mbar_init(FU_AD(pl) + 8u*s, 1u);
+    for (int s = 0; s < FU_RING; s++) fu_mbar_init(FU_AD(pl) + 8u*s, 1u);
 #pragma unroll
     for (int s = 0; s < FW_NF; s++) { fu_mbar_init(FW_AD(ffull) + 8u*s, 1u); fu_mbar_init(FW_AD(fempty) + 8u*s, (unsigned int) FW_NCONS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -154,6 +152,7 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
   }
   fu_mbar_wait(FU_AD(pl) + 40u, 0u);
 
+#ifndef LB200_STRICT
   PfRegs r;
   r.uxc = 0.0;                                     // u_x(n): not used before n = i0 - 1
   fu_plane_sums<G::PZ>(sm.phi[0], k.pc, r.Bm, r.Cym, r.Czm);
@@ -162,7 +161,13 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
   r.gc_xx = r.gc_xy = r.gc_xz = r.gc_mu = 0.0;
   r.phim1 = 0.0;
   r.fxm1 = r.fxm2 = r.fy_prev = r.fz_prev = 0.0;
-
+#else
+  // strict arithmetic (the reference's operation order, phi_sector_kernel): own-column history of the march
+  double gm_p0 = 0.0, gm_x = 0.0, gm_y = 0.0, gm_z = 0.0, gm_mu = 0.0;      // plane n-1
+  double gc_p0 = 0.0, gc_x = 0.0, gc_y = 0.0, gc_z = 0.0, gc_mu = 0.0;      // plane n
+  double phim1 = 0.0, phim2 = 0.0;                                        // phi(n-1), phi(n-2), own column
+  double uxm = 0.0, uxc = 0.0;                                            // u_x(n-1), u_x(n)
+#endif
 
   const int tid = k.tid, pc = k.pc;
   const int typ = tid + G::BZ, tym = tid - G::BZ, tzp = tid + 1, tzm = tid - 1;
@@ -200,6 +205,7 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
 
     }
 
+#ifndef LB200_STRICT
     const double * __restrict__ fm = sm.phi[q];
     const double * __restrict__ fc = sm.phi[q1];
     const double * __restrict__ fp = sm.phi[q2];
@@ -309,6 +315,165 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
     r.uxc = uxp;
 
 
+#else
+    const double * __restrict__ fm = sm.phi[q];
+    const double * __restrict__ fc = sm.phi[q1];
+    const double * __restrict__ fp = sm.phi[q2];
+    const double uxp = sm.ux[u1][k.tu];              // u_x(n+1)
+    double F0 = 0.0, F1 = 0.0, F2 = 0.0;
+
+    // ---- 2. gradient of plane n+1 at the own column, from phi planes n, n+1, n+2: the reference's summation order
+    //         (src/gradient_3d_27pt_fluid.c:268-358), then p0 and mu of that site (src/symmetric.c:307-319, 371-416) ----
+    double gp_p0 = 0.0, gp_x = 0.0, gp_y = 0.0, gp_z = 0.0, gp_mu = 0.0;
+    if (k.valid_g && do_grad) {
+      constexpr int PZ = G::PZ;
+      const double m_mm = fm[pc-PZ-1], m_m0 = fm[pc-PZ], m_mp = fm[pc-PZ+1];
+      const double m_0m = fm[pc   -1], m_00 = fm[pc   ], m_0p = fm[pc   +1];
+      const double m_pm = fm[pc+PZ-1], m_p0 = fm[pc+PZ], m_pp = fm[pc+PZ+1];
+      const double c_mm = fc[pc-PZ-1], c_m0 = fc[pc-PZ], c_mp = fc[pc-PZ+1];
+      const double c_0m = fc[pc   -1], c_00 = fc[pc   ], c_0p = fc[pc   +1];
+      const double c_pm = fc[pc+PZ-1], c_p0 = fc[pc+PZ], c_pp = fc[pc+PZ+1];
+      const double p_mm = fp[pc-PZ-1], p_m0 = fp[pc-PZ], p_mp = fp[pc-PZ+1];
+      const double p_0m = fp[pc   -1], p_00 = fp[pc   ], p_0p = fp[pc   +1];
+      const double p_pm = fp[pc+PZ-1], p_p0 = fp[pc+PZ], p_pp = fp[pc+PZ+1];
+
+      gp_x = 0.5*r9*
+	(+ p_mm - m_mm + p_m0 - m_m0 + p_mp - m_mp
+	 + p_0m - m_0m + p_00 - m_00 + p_0p - m_0p
+	 + p_pm - m_pm + p_p0 - m_p0 + p_pp - m_pp);
+      gp_y = 0.5*r9*
+	(+ m_pm - m_mm + m_p0 - m_m0 + m_pp - m_mp
+	 + c_pm - c_mm + c_p0 - c_m0 + c_pp - c_mp
+	 + p_pm - p_mm + p_p0 - p_m0 + p_pp - p_mp);
+      gp_z = 0.5*r9*
+	(+ m_mp - m_mm + m_0p - m_0m + m_pp - m_pm
+	 + c_mp - c_mm + c_0p - c_0m + c_pp - c_pm
+	 + p_mp - p_mm + p_0p - p_0m + p_pp - p_pm);
+      const double dsq = r9*
+	(+ m_mm + m_m0 + m_mp + m_0m + m_00 + m_0p + m_pm + m_p0 + m_pp
+	 + c_mm + c_m0 + c_mp + c_0m        + c_0p + c_pm + c_p0 + c_pp
+	 + p_mm + p_m0 + p_mp + p_0m + p_00 + p_0p + p_pm + p_p0 + p_pp
+	 - 26.0*c_00);
+
+      SiteFE sf;
+      sf.phi = c_00; sf.delsq = dsq; sf.gx = gp_x; sf.gy = gp_y; sf.gz = gp_z;
+      gp_p0 = symm_p0(sp, sf);
+      gp_mu = symm_mu(sp, c_00, dsq);
+
+      const int ig = n + 1;
+      const bool own_x = (ig >= k.i0 && ig <= k.i1) || (ig == 0 && k.i0 == 1) || (ig == k.nlx + 1 && k.i1 == k.nlx);
+      if (k.own_g && own_x) {
+	const size_t sidx = (size_t) ((ig + k.nh - 1)*k.xs + k.scol);
+	grad[sidx] = gp_x;
+	grad[k.ns + sidx] = gp_y;
+	grad[2*k.ns + sidx] = gp_z;
+	delsq[sidx] = dsq;
+      }
+    }
+    {
+      double (* gb)[G::NT] = sm.g[q1 & 1];
+      gb[0][tid] = gp_p0; gb[1][tid] = gp_x; gb[2][tid] = gp_y; gb[3][tid] = gp_z; gb[4][tid] = gp_mu;
+    }
+
+    // ---- 3. force and Cahn-Hilliard update of plane n (src/phi_force_colloid.c:315-465, src/advection.c:946-1141,
+    //         src/phi_cahn_hilliard.c:350-404, 1018-1049, 1373-1397): the reference's operations in the reference's order ----
+    const double ph_c = fm[pc];
+    if (do_full && k.out_site) {
+      const double (* gb)[G::NT] = sm.g[q & 1];
+      const double (* ub)[G::USLOT] = sm.u[u0];
+      const int tu = k.tu;
+      const int s = (n + k.nh - 1)*k.xs + k.scol;
+
+      // force = - div P, accumulation order +x, -x, +y, -y, +z, -z
+      double fo[3], p0c[3], p1[3];
+      ps_pcol(sp, 0, gc_p0, gc_x, gc_y, gc_z, p0c);
+      ps_pcol(sp, 0, gp_p0, gp_x, gp_y, gp_z, p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] = -0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 0, gm_p0, gm_x, gm_y, gm_z, p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] += 0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 1, gc_p0, gc_x, gc_y, gc_z, p0c);
+      ps_pcol(sp, 1, gb[0][typ], gb[1][typ], gb[2][typ], gb[3][typ], p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] -= 0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 1, gb[0][tym], gb[1][tym], gb[2][tym], gb[3][tym], p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] += 0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 2, gc_p0, gc_x, gc_y, gc_z, p0c);
+      ps_pcol(sp, 2, gb[0][tzp], gb[1][tzp], gb[2][tzp], gb[3][tzp], p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] -= 0.5*(p1[a] + p0c[a]);
+      ps_pcol(sp, 2, gb[0][tzm], gb[1][tzm], gb[2][tzm], gb[3][tzm], p1);
+#pragma unroll
+      for (int a = 0; a < 3; a++) fo[a] += 0.5*(p1[a] + p0c[a]);
+      F0 = fo[0]; F1 = fo[1]; F2 = fo[2];
+
+      // Cahn-Hilliard: six face fluxes in registers, forward Euler
+      const double M = sp.mobility;
+      const double mu0 = gc_mu;
+      const double ph_xm = phim1, ph_xm2 = phim2, ph_xp = fc[pc], ph_xp2 = fp[pc];
+      const double ph_ym = fm[pc - G::PZ], ph_yp = fm[pc + G::PZ];
+      const double ph_zm = fm[pc - 1], ph_zp = fm[pc + 1];
+      double ph_ym2 = 0.0, ph_yp2 = 0.0, ph_zm2 = 0.0, ph_zp2 = 0.0;
+      if (ORDER == 3) {
+	ph_ym2 = fm[pc - 2*G::PZ]; ph_yp2 = fm[pc + 2*G::PZ];
+	ph_zm2 = fm[pc - 2];       ph_zp2 = fm[pc + 2];
+      }
+      const double uy_c = ub[0][tu], uy_ym = ub[0][tu - FU_ROW], uy_yp = ub[0][tu + FU_ROW];
+      const double uz_c = ub[1][tu], uz_zm = ub[1][tu - 1], uz_zp = ub[1][tu + 1];
+
+      double fw = adv_face<ORDER, true>(uxm, uxc, ph_xm2, ph_xm, ph_c, ph_xp);
+      fw -= M*(mu0 - gm_mu);
+      fw -= M*sp.gm[0];
+      double fe = adv_face<ORDER, false>(uxc, uxp, ph_xm, ph_c, ph_xp, ph_xp2);
+      fe -= M*(gp_mu - mu0);
+      fe -= M*sp.gm[0];
+      double fy = adv_face<ORDER, false>(uy_c, uy_yp, ph_ym, ph_c, ph_yp, ph_yp2);
+      fy -= M*(gb[4][typ] - mu0);
+      fy -= M*sp.gm[1];
+      double fym = adv_face<ORDER, false>(uy_ym, uy_c, ph_ym2, ph_ym, ph_c, ph_yp);
+      fym -= M*(mu0 - gb[4][tym]);
+      fym -= M*sp.gm[1];
+      double fz = adv_face<ORDER, false>(uz_c, uz_zp, ph_zm, ph_c, ph_zp, ph_zp2);
+      fz -= M*(gb[4][tzp] - mu0);
+      fz -= M*sp.gm[2];
+      double fzm = adv_face<ORDER, false>(uz_zm, uz_c, ph_zm2, ph_zm, ph_c, ph_zp);
+      fzm -= M*(mu0 - gb[4][tzm]);
+      fzm -= M*sp.gm[2];
+
+      double phn = ph_c;
+      phn -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
+      phinew[s] = phn;
+      // periodic images within nhalo of a y / z boundary (read by the next step's TMA boxes of phi)
+      const int ipy = k.py*k.imy_unit, ipz = k.pz*k.imz_unit;
+      if (k.py != 0) phinew[s + ipy] = phn;
+      if (k.pz != 0) phinew[s + ipz] = phn;
+      if (k.py != 0 && k.pz != 0) phinew[s + ipy + ipz] = phn;
+      // the planes the neighbour GPUs' next phi sector reads, straight into their halo planes (with their y / z images)
+      if (k.peer_lo != nullptr && n <= k.nh) {
+	double * pl = k.peer_lo + ((size_t) s + (size_t) k.nlx*k.xs);
+	pl[0] = phn;
+	if (k.py != 0) pl[ipy] = phn;
+	if (k.pz != 0) pl[ipz] = phn;
+	if (k.py != 0 && k.pz != 0) pl[ipy + ipz] = phn;
+      }
+      if (k.peer_hi != nullptr && n > k.nlx - k.nh) {
+	double * ph = k.peer_hi + ((size_t) s - (size_t) k.nlx*k.xs);
+	ph[0] = phn;
+	if (k.py != 0) ph[ipy] = phn;
+	if (k.pz != 0) ph[ipz] = phn;
+	if (k.py != 0 && k.pz != 0) ph[ipy + ipz] = phn;
+      }
+    }
+
+    // ---- 4. rotate the own-column history ----
+    gm_p0 = gc_p0; gm_x = gc_x; gm_y = gc_y; gm_z = gc_z; gm_mu = gc_mu;
+    gc_p0 = gp_p0; gc_x = gp_x; gc_y = gp_y; gc_z = gp_z; gc_mu = gp_mu;
+    phim2 = phim1; phim1 = ph_c;
+    uxm = uxc; uxc = uxp;
+
+#endif
     // ---- 6. hand the force of plane n to the collision warps ----
     if (do_full && k.has_sites) {
       const int fs = (n - k.i0) % FW_NF;
@@ -412,4 +577,4 @@ int launch_step_fused_ws(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDe
   return 1;
 }
 
-#endif
+

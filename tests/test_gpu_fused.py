@@ -4,8 +4,8 @@ stored by the producing kernel.  Checked against the CPU oracle on identical inp
 leaves behind: f, phi, u, rho, force, grad, delsq), against the two-kernel step of the same library, and through the
 transitions between the two (first step after an upload, single operators after a fused step, several calls).
 
-Bar: fast mode within 1e-12 relative (absolute floor 1e-14 for velocities); the strict build has no fused kernel and must
-keep running the bit-exact two-kernel step."""
+Bar: fast mode within 1e-12 relative (absolute floor 1e-14 for velocities); strict mode (the same kernel compiled without FMA
+contraction, its phi-sector warps in the reference's operation order) BIT-EXACT."""
 import numpy as np
 import pytest
 
@@ -47,28 +47,47 @@ def oracle_run(nlocal, order, nrelax, nsteps):
 
 
 # 40 x 26 x 64: 4 x 3 tiles of 8 x 30 columns (the last ones ragged), chunks of 8 .. 40 planes
+@pytest.mark.parametrize("math_mode", [lb.MATH_FAST, lb.MATH_STRICT], ids=["fast", "strict"])
 @pytest.mark.parametrize("xc", [0, 9, 20, 40])
 @pytest.mark.parametrize("order,nrelax", [(1, lb.RELAX_M10), (2, lb.RELAX_TRT), (3, lb.RELAX_M10), (3, lb.RELAX_BGK)])
-def test_fused_step_matches_the_oracle(order, nrelax, xc, monkeypatch):
+def test_fused_step_matches_the_oracle(order, nrelax, xc, math_mode, monkeypatch):
     if xc:
         monkeypatch.setenv("LB200_PS_XC", str(xc))
     nlocal = (40, 26, 64)
     orc, st0, st = oracle_run(nlocal, order, nrelax, 12)
-    got, prof = gpu_run(nlocal, st0, order, nrelax, 12)
+    got, prof = gpu_run(nlocal, st0, order, nrelax, 12, math=math_mode)
     # the first step after the upload collides in place (two kernels), the other 11 are one kernel each
     assert prof["step_fused"][1] == 11 and prof["collide"][1] == 1 and prof["phi_sector"][1] == 1, prof
     for k in got:
-        assert close_fast(orc.interior(got[k]), orc.interior(st[k])), (k, rel_err(orc.interior(got[k]), orc.interior(st[k])))
+        if math_mode == lb.MATH_STRICT:
+            assert np.array_equal(orc.interior(got[k]), orc.interior(st[k])), k
+        else:
+            assert close_fast(orc.interior(got[k]), orc.interior(st[k])), (k, rel_err(orc.interior(got[k]), orc.interior(st[k])))
 
 
-@pytest.mark.parametrize("nlocal", [(16, 8, 8), (8, 30, 32), (24, 62, 34), (12, 4, 4)])
-def test_fused_step_small_and_ragged_lattices(nlocal):
-    """one tile holding both periodic boundaries, tiles whose last row / column is cut, lattices as thin as the halo allows"""
-    orc, st0, st = oracle_run(nlocal, 3, lb.RELAX_M10, 9)
-    got, prof = gpu_run(nlocal, st0, 3, lb.RELAX_M10, 9, calls=3)
-    assert prof["step_fused"][1] == 8, prof
+def test_every_warp_does_both_variant(monkeypatch):
+    """LB200_FUSED_WS=0: the earlier form of the one-kernel step (no warp specialisation), kept for comparison runs"""
+    monkeypatch.setenv("LB200_FUSED_WS", "0")
+    nlocal = (40, 26, 64)
+    orc, st0, st = oracle_run(nlocal, 3, lb.RELAX_M10, 8)
+    got, prof = gpu_run(nlocal, st0, 3, lb.RELAX_M10, 8)
+    assert prof["step_fused"][1] == 7
     for k in got:
         assert close_fast(orc.interior(got[k]), orc.interior(st[k])), (k, rel_err(orc.interior(got[k]), orc.interior(st[k])))
+
+
+@pytest.mark.parametrize("math_mode", [lb.MATH_FAST, lb.MATH_STRICT], ids=["fast", "strict"])
+@pytest.mark.parametrize("nlocal", [(16, 8, 8), (8, 30, 32), (24, 62, 34), (12, 4, 4)])
+def test_fused_step_small_and_ragged_lattices(nlocal, math_mode):
+    """one tile holding both periodic boundaries, tiles whose last row / column is cut, lattices as thin as the halo allows"""
+    orc, st0, st = oracle_run(nlocal, 3, lb.RELAX_M10, 9)
+    got, prof = gpu_run(nlocal, st0, 3, lb.RELAX_M10, 9, calls=3, math=math_mode)
+    assert prof["step_fused"][1] == 8, prof
+    for k in got:
+        if math_mode == lb.MATH_STRICT:
+            assert np.array_equal(orc.interior(got[k]), orc.interior(st[k])), k
+        else:
+            assert close_fast(orc.interior(got[k]), orc.interior(st[k])), (k, rel_err(orc.interior(got[k]), orc.interior(st[k])))
 
 
 def test_fused_and_two_kernel_steps_agree():
@@ -84,9 +103,9 @@ def test_fused_and_two_kernel_steps_agree():
         assert close_fast(orc.interior(a[k]), orc.interior(b[k])), (k, rel_err(orc.interior(a[k]), orc.interior(b[k])))
 
 
-def test_odd_extent_and_strict_mode_take_the_two_kernel_step():
-    """the TMA boxes need 16-byte aligned rows (even Nz); the strict build keeps the bit-exact two-kernel step"""
-    for nlocal, math in (((16, 16, 15), lb.MATH_FAST), ((16, 16, 16), lb.MATH_STRICT)):
+def test_odd_extent_takes_the_two_kernel_step():
+    """the TMA boxes need 16-byte aligned rows (even Nz): odd extents keep the two-kernel step, in both arithmetic modes"""
+    for nlocal, math in (((16, 16, 15), lb.MATH_FAST), ((16, 16, 15), lb.MATH_STRICT)):
         orc, st0, st = oracle_run(nlocal, 3, lb.RELAX_M10, 5)
         got, prof = gpu_run(nlocal, st0, 3, lb.RELAX_M10, 5, math=math)
         assert prof["step_fused"][1] == 0 and prof["collide"][1] == 5, prof
