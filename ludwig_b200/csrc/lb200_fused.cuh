@@ -183,13 +183,21 @@ __device__ __forceinline__ void fu_collide(FuShared<BY> & sm, const FuK & k, con
   d3q19_mode2f<GHOST>(mode, f);
 
   {
-    // one 64-bit pointer increment per population instead of a 64-bit multiply-add chain
-    double * pf = fdst + s;
+    // one 64-bit BYTE-pointer increment per population (2 instructions) instead of index -> address chains (4)
+    // (the add is opaque to the compiler, which otherwise rebuilds every address from a running index: 4 instructions)
+    const unsigned long long nsb = (unsigned long long) k.ns*sizeof(double);
+    unsigned long long pf = (unsigned long long) (fdst + s);
 #pragma unroll
-    for (int p = 0; p < 19; p++) { __stcs(pf, f[p]); pf += k.ns; }
-    double * pu = u_out + s;
+    for (int p = 0; p < 19; p++) {
+      __stcs(reinterpret_cast<double *>(pf), f[p]);
+      asm("add.u64 %0, %0, %1;" : "+l"(pf) : "l"(nsb));
+    }
+    unsigned long long pu = (unsigned long long) (u_out + s);
 #pragma unroll
-    for (int ia = 0; ia < 3; ia++) { *pu = uu[ia]; pu += k.ns; }
+    for (int ia = 0; ia < 3; ia++) {
+      *reinterpret_cast<double *>(pu) = uu[ia];
+      asm("add.u64 %0, %0, %1;" : "+l"(pu) : "l"(nsb));
+    }
   }
   if (!k.skip_diag) {
     rho_out[s] = rho;
