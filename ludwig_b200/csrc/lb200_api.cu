@@ -119,6 +119,7 @@ struct lb200_s {
   int knob_lazy_diag;        // rho / grad / delsq stored by the last step of an lb200_step call only (LB200_LAZY_DIAG, default 1)
   int knob_f32;              // FP32 storage of the distributions inside lb200_step (0: off)
   int knob_fused;            // one kernel per binary-fluid step where it applies (LB200_FUSED, default 1)
+  int knob_fused_le;         // ... also with Lees-Edwards planes (LB200_FUSED_LE, default 1; 0: two kernels + patches)
   float * f32[2];            // float(f_p - w_p), allocated on first use
   int knob_pipe;             // slab pipeline of lb200_step: number of x-slabs (0: off)
   int knob_pipe_sms;         // SMs of the phi-sector partition (the collision gets the rest)
@@ -150,6 +151,8 @@ struct lb200_s {
   int t_start, t_current;    // physics_control_* (src/physics.c:600-647)
   int * le_trip;             // device: (x-1, x, x+1) plane triples of the gradient patch
   int le_ntrip;
+  int * le_trip_fused;       // the same + the four real planes beyond (one-kernel step: the sweep keeps grad / delsq in registers)
+  int le_ntrip_fused;
   int * le_xlist;            // device: the x-planes within nhalo of a plane (force / Cahn-Hilliard patch)
   int le_nxlist;
   double * le_term;          // 3*nplane*Ny*Nz: summands of the per-plane force flux correction
@@ -449,6 +452,16 @@ static int le_alloc(lb200_t * c) {
   }
   c->le_ntrip = (int) trip.size()/3;
   c->le_nxlist = (int) xl.size();
+  // one-kernel step: the force / Cahn-Hilliard patch of planes ic-1 .. ic+2 also reads grad and delsq of ic-2, ic-1, ic+2, ic+3,
+  // which the sweep does not store on intermediate steps
+  std::vector<int> tripf(trip);
+  for (int p = 0; p < npl; p++) {
+    const int ic = c->le.loc[p];
+    for (int x : {ic - 2, ic - 1, ic + 2, ic + 3}) tripf.insert(tripf.end(), {x - 1, x, x + 1});
+  }
+  c->le_ntrip_fused = (int) tripf.size()/3;
+  if (cudaMalloc((void **) &c->le_trip_fused, tripf.size()*sizeof(int)) != cudaSuccess) return -1;
+  if (cudaMemcpyAsync(c->le_trip_fused, tripf.data(), tripf.size()*sizeof(int), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -1;
   if (cudaMalloc((void **) &c->le_trip, trip.size()*sizeof(int)) != cudaSuccess) return -1;
   if (cudaMalloc((void **) &c->le_xlist, xl.size()*sizeof(int)) != cudaSuccess) return -1;
   // on the context's own (non-blocking) stream, which orders them before every kernel of this context: a legacy-stream
@@ -641,6 +654,7 @@ int lb200_create(const lb200_options_t * o, lb200_t ** pctx) {
   c->knob_pipe = getenv("LB200_PIPE") ? atoi(getenv("LB200_PIPE")) : 0;
   c->knob_f32 = getenv("LB200_F32") ? atoi(getenv("LB200_F32")) : 0;
   c->knob_fused = getenv("LB200_FUSED") ? atoi(getenv("LB200_FUSED")) : 1;
+  c->knob_fused_le = getenv("LB200_FUSED_LE") ? atoi(getenv("LB200_FUSED_LE")) : 1;
   c->knob_grad7 = getenv("LB200_GRAD_7PT") ? atoi(getenv("LB200_GRAD_7PT")) : 0;
   c->knob_lazy_diag = getenv("LB200_LAZY_DIAG") ? atoi(getenv("LB200_LAZY_DIAG")) : 1;
   c->knob_pipe_sms = getenv("LB200_PIPE_SMS") ? atoi(getenv("LB200_PIPE_SMS")) : 56;
@@ -710,7 +724,7 @@ int lb200_free(lb200_t * c) {
   cudaFree(c->phi); cudaFree(c->phinew); cudaFree(c->grad); cudaFree(c->delsq);
   cudaFree(c->grad_delsq); cudaFree(c->delsq_delsq); cudaFree(c->str);
   cudaFree(c->q); cudaFree(c->qnew); cudaFree(c->qgrad); cudaFree(c->qdelsq);
-  cudaFree(c->le_trip); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
+  cudaFree(c->le_trip); cudaFree(c->le_trip_fused); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
   for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
   cudaFree(c->f32[0]); cudaFree(c->f32[1]); cudaFree(c->csum);
   cudaFree(c->flags); cudaFree(c->spin_err); cudaFree(c->halo_snap); cudaFree(c->psum);
@@ -1819,7 +1833,9 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   }
   // one kernel per step (LB200_KNOB_FUSED): binary fluid, D3Q19 with the coded matrices, all-fluid, no planes
   // (fast arithmetic mode; the TMA boxes of the populations need 16-byte aligned rows: even extents in z)
-  const bool fuse_ok = binary && c->knob_fused && !le && !f32 && c->nvel == 19 && c->unrolled19 && c->ndist == 1
+  // (with Lees-Edwards planes: the sweep runs over the whole lattice as if there were none, then the 2*nhalo x-planes per
+  // plane whose stencils cross it are produced again by the patch kernels through the buffer planes)
+  const bool fuse_ok = binary && c->knob_fused && (!le || c->knob_fused_le) && !f32 && c->nvel == 19 && c->unrolled19 && c->ndist == 1
     && c->map_all_fluid && c->knob_pipe < 2 && sd->order <= 3 && sd->csum == nullptr
     && c->g.nh == 2 && (c->g.nall[2] & 1) == 0 && (c->g.nsites & 1) == 0
     && c->g.nl[1] >= 2 && c->g.nl[2] >= 2;
@@ -1837,6 +1853,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       // The whole step in one sweep (LB200_KNOB_FUSED): phi sector + pull-stream + collision of the same plane, the
       // force stays in registers.  (The first step after an upload of the distributions collides in place -- no
       // propagation is pending -- and takes the two-kernel route below.)
+      if (le) gw.skip_diag = (c->knob_lazy_diag && n < nsteps - 1) ? 1 : 0;  // (the patches form the gradients they read themselves)
       if (remote) {
 	rc = src_wait(c, S, c->phi_src, c->ev_phi, FLAG_PS_LO, c->n_ps);
 	if (rc == 0) rc = src_wait(c, S, c->u_src, c->ev_u, FLAG_COL_LO, c->n_col);
@@ -1853,6 +1870,11 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	rc = halo_field(c, c->u, 3, c->g.nh, 0, S);
 	if (rc != 0) return rc;
 	c->f_halo_stale = 1;                 // (still true for the reference's view: only what the pull reads is kept up to date)
+      }
+      if (le) {
+	// field_leesedwards, hydro_lees_edwards: the buffer planes, from interior columns
+	le_field_async(c, c->phi, &gw);
+	le_hydro_async(c, &gw);
       }
       // the phi sector of other CTAs (and of the neighbour GPUs) reads u(t-1) while this kernel writes u(t)
       double * u_out = (c->u == c->u_alloc[0]) ? c->u_alloc[1] : c->u_alloc[0];
@@ -1871,9 +1893,35 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       if (launched > 0) {
 	c->launches += launched;
 	c->force_state = gw.skip_diag ? ZERO_PENDING : INTERIOR_ONLY;      // the force array is written by the last step only
+	if (le) {
+	  // planes loc-1 .. loc+2 of every Lees-Edwards plane again, through the buffer planes: gradients (also of the two
+	  // planes either side, which the sweep kept in registers), flux-form force with the plane correction, Cahn-Hilliard
+	  // with the averaged plane fluxes -> force, phinew; then pull-stream + collision of these planes with that force
+	  Lb200Geom gl = gw;
+	  gl.peer_phi_lo = gl.peer_phi_hi = gl.peer_f_lo = gl.peer_f_hi = gl.peer_u_lo = gl.peer_u_hi = nullptr;
+	  {
+	    ProfScope ps(c, LB200_K_LE);
+	    c->launches += c->k->le_grad_planes(S, gl, 0, c->le_ntrip_fused, c->le_trip_fused, c->phi, c->grad, c->delsq);
+	  }
+	  le_force_ch_async(c, *sd, c->le_nxlist, c->le_xlist, 1, 1, 0, c->phinew, &gl);
+	  ProfScope ps(c, LB200_K_LE);
+	  for (int p = 0; p < c->le.nplane; p++) {
+	    Lb200Geom gc = gl;
+	    gc.xoff = c->le.loc[p] - c->g.nh; gc.xcnt = 2*c->g.nh;
+	    c->launches += c->k->collide(S, gc, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, u_out);
+	  }
+	}
 	{ double * t = c->phi; c->phi = c->phinew; c->phinew = t; }
 	{ double * t = c->f; c->f = c->fprime; c->fprime = t; }
 	c->u = u_out;
+	if (le) {
+	  le_lb_bc_async(c);                                                // lb_data_apply_le_boundary_conditions
+	  // the y / z images of what the patches produced (the sweep stored the images of its own values)
+	  ProfScope ps(c, LB200_K_LE);
+	  c->launches += c->k->le_yz_images(S, c->g, c->le_nxlist, c->le_xlist, c->nvel, 1, c->f);
+	  c->launches += c->k->le_yz_images(S, c->g, c->le_nxlist, c->le_xlist, 1, c->g.nh, c->phi);
+	  c->launches += c->k->le_yz_images(S, c->g, c->le_nxlist, c->le_xlist, 3, 1, c->u);
+	}
 	c->u_state = INTERIOR_ONLY;
 	c->prop_pending = 1;
 	c->f_halo_stale = 1; c->fused_ready = 1;
@@ -1902,6 +1950,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       // no such kernel after all (no tensor-map entry point in this driver): the two-kernel step from now on
       gw.peer_f_lo = gw.peer_f_hi = gw.peer_u_lo = gw.peer_u_hi = nullptr;
       c->knob_fused = 0;
+      if (le) gw.skip_diag = 0;
     }
     if (binary) {
       if (remote) {

@@ -2496,5 +2496,6 @@ const Lb200Kernels LB200_TABLE = {
   launch_phi_sum,
   launch_phi_sum_ranks,
   launch_phi_subtract,
+  launch_le_yz_images,
   PSUM_BLOCKS,
 };

@@ -184,6 +184,9 @@ struct Lb200Kernels {
   int (*phi_sum)(cudaStream_t, const Lb200Geom &, const double * phi, const char * status, double * partial, double * result);
   int (*phi_sum_ranks)(cudaStream_t, const double * all, int nranks, double * total);
   int (*phi_subtract)(cudaStream_t, const Lb200Geom &, const double * total, double phi0, const char * status, double * phi);
+  // y / z periodic images (depth d) of ncomp components on a list of x-planes (the one-kernel step with Lees-Edwards
+  // planes: the patched planes' images)
+  int (*le_yz_images)(cudaStream_t, const Lb200Geom &, int nx, const int * xlist, int ncomp, int depth, double * data);
   int psum_blocks;
 };
 

@@ -547,3 +547,44 @@ int launch_le_lb_bc(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le,
   le_lb_interp_kernel<<<grd, blk, 0, st>>>(g, le, fix, md, ndist, sbuf, f);
   return 2;
 }
+
+// ---------------------------------------------------------------------------------------------
+// y / z periodic images, depth d, of ncomp components on a list of x-planes.  The one-kernel step (lb200_fused*.cuh) keeps
+// the images of f', phi' and u up to date from the warps that produce them; the planes next to a Lees-Edwards plane
+// are produced again by the patch kernels, which write interior sites only: this brings their images up to date.
+// One thread per shell site (2d full rows of the allocation's cross-section, then 2d sites of each interior row).
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(TPB)
+le_yz_images_kernel(const Lb200Geom g, const int * __restrict__ xlist, int ncomp, int d, double * __restrict__ data) {
+  const int ny = g.nl[1], nz = g.nl[2];
+  const int ez = nz + 2*d;
+  const int nshell = 2*d*ez + 2*d*ny;
+  int q = blockIdx.x*blockDim.x + threadIdx.x;
+  if (q >= nshell) return;
+  int jc, kc;
+  if (q < 2*d*ez) {
+    const int r = q/ez;
+    jc = (r < d) ? 1 - d + r : ny + 1 + (r - d);
+    kc = 1 - d + q % ez;
+  }
+  else {
+    q -= 2*d*ez;
+    const int t = q % (2*d);
+    jc = 1 + q/(2*d);
+    kc = (t < d) ? 1 - d + t : nz + 1 + (t - d);
+  }
+  const int ic = xlist[blockIdx.y];
+  const int dst = le_index(g, ic, jc, kc);
+  const int src = le_index(g, ic, lb200_wrap1(jc, ny, 1), lb200_wrap1(kc, nz, 1));
+  const size_t ns = (size_t) g.nsites;
+  for (int n = 0; n < ncomp; n++) data[n*ns + dst] = data[n*ns + src];
+}
+
+int launch_le_yz_images(cudaStream_t st, const Lb200Geom & g, int nx, const int * xlist, int ncomp, int depth, double * data) {
+  if (nx == 0 || depth <= 0) return 0;
+  const int nshell = 2*depth*(g.nl[2] + 2*depth) + 2*depth*g.nl[1];
+  dim3 grd((nshell + TPB - 1)/TPB, nx, 1);
+  le_yz_images_kernel<<<grd, TPB, 0, st>>>(g, xlist, ncomp, depth, data);
+  return 1;
+}

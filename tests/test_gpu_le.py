@@ -173,3 +173,50 @@ def test_serial_le3d_logs_on_gpu(order, var, lo, hi, fed, uylo, uyhi):
     assert fed_density(orc, sp, got["phi"], got["grad"]) == approx(fed, 10)
     ui = orc.interior(got["u"])
     assert ui[1].min() == approx(uylo, 8) and ui[1].max() == approx(uyhi, 8)
+
+
+def _run_steps_profiled(n, nplanes, order, nsteps, calls, seed=13):
+    orc, sim, sp_o, sp_g = make(n, nplanes, order, lb.MATH_FAST)
+    f = np.zeros((19, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f)
+    phi = np.zeros((1, orc.nsites))
+    phi[:, :orc.nsites_lb] = spinodal_phi(n, 2, seed, 0.0, 0.1)
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+    with sim:
+        sim.put(lb.F, f); sim.put(lb.PHI, phi)
+        sim.profile(True)
+        for _ in range(calls):
+            sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), sp_g, nsteps // calls)
+        sim.sync()
+        prof = sim.profile_get()
+        sim.profile(False)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("rho", lb.RHO),
+                                          ("force", lb.FORCE), ("grad", lb.GRAD), ("delsq", lb.DELSQ))}
+    orc.le_step(orc.collide_param(0, 1.0, ETA), sp_o, 0, nsteps, f, phi, u, rho, force, grad, delsq)
+    want = dict(f=f, phi=phi, u=u, rho=rho, force=force, grad=grad, delsq=delsq)
+    return orc, got, want, prof
+
+
+@pytest.mark.parametrize("n,nplanes,order,calls", [((32, 26, 64), 2, 3, 1), ((16, 16, 40), 1, 3, 3), ((48, 12, 8), 3, 1, 1),
+                                                   ((24, 16, 16), 2, 2, 2), ((64, 40, 36), 4, 3, 1)])
+def test_le_one_kernel_step(n, nplanes, order, calls):
+    """the one-kernel step with Lees-Edwards planes: the sweep over the whole lattice, then planes loc-1 .. loc+2 of every
+    plane produced again through the buffer planes (gradient, flux-form force, Cahn-Hilliard, pull-stream + collision,
+    plane-crossing populations, y / z images) -- 12 steps in `calls` calls against the oracle, every field"""
+    orc, got, want, prof = _run_steps_profiled(n, nplanes, order, 12, calls)
+    assert prof["step_fused"][1] == 11 and prof["phi_sector"][1] == 1, prof
+    for k in want:
+        assert close_fast(orc.interior(got[k]), orc.interior(want[k])), (k, np.abs(orc.interior(got[k]) - orc.interior(want[k])).max())
+
+
+def test_le_one_kernel_step_equals_two_kernel_step(monkeypatch):
+    """LB200_FUSED_LE=0 (phi sector + collision + patches) and the one-kernel form give the same fields within the fast bar"""
+    n = (32, 24, 32)
+    orc, a, want, pa = _run_steps_profiled(n, 2, 3, 20, 1)
+    monkeypatch.setenv("LB200_FUSED_LE", "0")
+    orc, b, want, pb = _run_steps_profiled(n, 2, 3, 20, 1)
+    assert pa["step_fused"][1] == 19 and pb["step_fused"][1] == 0
+    for k in a:
+        assert close_fast(orc.interior(a[k]), orc.interior(b[k])), k
+        assert close_fast(orc.interior(a[k]), orc.interior(want[k])), k
