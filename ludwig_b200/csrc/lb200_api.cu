@@ -119,7 +119,9 @@ struct lb200_s {
   int knob_lazy_diag;        // rho / grad / delsq stored by the last step of an lb200_step call only (LB200_LAZY_DIAG, default 1)
   int knob_f32;              // FP32 storage of the distributions inside lb200_step (0: off)
   int knob_fused;            // one kernel per binary-fluid step where it applies (LB200_FUSED, default 1)
-  int knob_fused_le;         // ... also with Lees-Edwards planes (LB200_FUSED_LE, default 1; 0: two kernels + patches)
+  int knob_fused_le;         // ... also with Lees-Edwards planes (LB200_FUSED_LE: 1 = default, the patch chain after the sweep;
+                             // 2: next to it on its own stream (measured: no faster, the chain's grids take whole SMs from
+                             // the sweep); 0: two kernels + patches)
   float * f32[2];            // float(f_p - w_p), allocated on first use
   int knob_pipe;             // slab pipeline of lb200_step: number of x-slabs (0: off)
   int knob_pipe_sms;         // SMs of the phi-sector partition (the collision gets the rest)
@@ -151,6 +153,8 @@ struct lb200_s {
   int t_start, t_current;    // physics_control_* (src/physics.c:600-647)
   int * le_trip;             // device: (x-1, x, x+1) plane triples of the gradient patch
   int le_ntrip;
+  cudaStream_t le_stream;    // the patch chain of the one-kernel step runs here, next to the sweep (high priority)
+  cudaEvent_t ev_le_a, ev_le_b;
   int * le_trip_fused;       // the same + the four real planes beyond (one-kernel step: the sweep keeps grad / delsq in registers)
   int le_ntrip_fused;
   int * le_xlist;            // device: the x-planes within nhalo of a plane (force / Cahn-Hilliard patch)
@@ -462,6 +466,14 @@ static int le_alloc(lb200_t * c) {
   c->le_ntrip_fused = (int) tripf.size()/3;
   if (cudaMalloc((void **) &c->le_trip_fused, tripf.size()*sizeof(int)) != cudaSuccess) return -1;
   if (cudaMemcpyAsync(c->le_trip_fused, tripf.data(), tripf.size()*sizeof(int), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -1;
+  {
+    // the patch chain's own stream: above the sweep's priority, so that its small grids take the SMs the sweep's CTAs free
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess
+	|| cudaStreamCreateWithPriority(&c->le_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); c->le_stream = nullptr; }
+    if (cudaEventCreateWithFlags(&c->ev_le_a, cudaEventDisableTiming) != cudaSuccess
+	|| cudaEventCreateWithFlags(&c->ev_le_b, cudaEventDisableTiming) != cudaSuccess) return -1;
+  }
   if (cudaMalloc((void **) &c->le_trip, trip.size()*sizeof(int)) != cudaSuccess) return -1;
   if (cudaMalloc((void **) &c->le_xlist, xl.size()*sizeof(int)) != cudaSuccess) return -1;
   // on the context's own (non-blocking) stream, which orders them before every kernel of this context: a legacy-stream
@@ -724,6 +736,9 @@ int lb200_free(lb200_t * c) {
   cudaFree(c->phi); cudaFree(c->phinew); cudaFree(c->grad); cudaFree(c->delsq);
   cudaFree(c->grad_delsq); cudaFree(c->delsq_delsq); cudaFree(c->str);
   cudaFree(c->q); cudaFree(c->qnew); cudaFree(c->qgrad); cudaFree(c->qdelsq);
+  if (c->le_stream) cudaStreamDestroy(c->le_stream);
+  if (c->ev_le_a) cudaEventDestroy(c->ev_le_a);
+  if (c->ev_le_b) cudaEventDestroy(c->ev_le_b);
   cudaFree(c->le_trip); cudaFree(c->le_trip_fused); cudaFree(c->le_xlist); cudaFree(c->le_term); cudaFree(c->le_fcor); cudaFree(c->le_chx); cudaFree(c->le_sbuf);
   for (int i = 0; i < c->nmapped; i++) cudaIpcCloseMemHandle(c->mapped[i]);
   cudaFree(c->f32[0]); cudaFree(c->f32[1]); cudaFree(c->csum);
@@ -1131,22 +1146,22 @@ int lb200_phi_halo(lb200_t * c) {
 }
 
 // field_leesedwards, src/field.c:418-510
-static int le_field_async(lb200_t * c, double * phi, const Lb200Geom * gw = nullptr) {
+static int le_field_async(lb200_t * c, double * phi, const Lb200Geom * gw = nullptr, cudaStream_t st = nullptr) {
   if (c->le.nplane == 0) return 0;
   Lb200LeInterp ip;
   le_interp_cubic(c, &ip);
-  ProfScope ps(c, LB200_K_LE);
-  c->launches += c->k->le_interp(c->stream, gw ? *gw : c->g, c->le, ip, 1, 1, c->g.nh, phi);
+  ProfScope ps(c, LB200_K_LE, st);
+  c->launches += c->k->le_interp(st ? st : c->stream, gw ? *gw : c->g, c->le, ip, 1, 1, c->g.nh, phi);
   return 0;
 }
 
 // hydro_lees_edwards, src/hydro.c:350-440
-static int le_hydro_async(lb200_t * c, const Lb200Geom * gw = nullptr) {
+static int le_hydro_async(lb200_t * c, const Lb200Geom * gw = nullptr, cudaStream_t st = nullptr) {
   if (c->le.nplane == 0) return 0;
   Lb200LeInterp ip;
   le_interp_linear(c, &ip);
-  ProfScope ps(c, LB200_K_LE);
-  c->launches += c->k->le_interp(c->stream, gw ? *gw : c->g, c->le, ip, 0, 3, c->g.nh, c->u);
+  ProfScope ps(c, LB200_K_LE, st);
+  c->launches += c->k->le_interp(st ? st : c->stream, gw ? *gw : c->g, c->le, ip, 0, 3, c->g.nh, c->u);
   return 0;
 }
 
@@ -1200,25 +1215,26 @@ int lb200_physics_control_timestep(const lb200_t * c) { return c ? c->t_current 
 // phi_force_flux / phi_cahn_hilliard with planes: the generic kernels of lb200_le.cuh on nx planes
 // (xlist == nullptr: the whole lattice)
 static int le_force_ch_async(lb200_t * c, const Lb200SymmDev & sd, int nx, const int * xlist, int do_force, int do_ch,
-			     int accumulate, double * phinew, const Lb200Geom * gw = nullptr) {
+			     int accumulate, double * phinew, const Lb200Geom * gw = nullptr, cudaStream_t st = nullptr) {
   Lb200LeFix fx;
   le_fix_param(c, &fx);
   const Lb200Geom & g = gw ? *gw : c->g;
-  ProfScope ps(c, LB200_K_LE);
-  if (do_force) c->launches += c->k->le_force_prep(c->stream, g, c->le, sd, c->phi, c->grad, c->delsq, c->le_term, c->le_fcor);
-  if (do_ch)    c->launches += c->k->le_ch_prep(c->stream, g, c->le, sd, c->phi, c->delsq, c->u, status_ptr(c), c->le_chx);
-  c->launches += c->k->le_force_ch(c->stream, g, c->le, sd, fx, nx, xlist, do_force, do_ch, accumulate, c->phi, c->grad,
+  if (st == nullptr) st = c->stream;
+  ProfScope ps(c, LB200_K_LE, st);
+  if (do_force) c->launches += c->k->le_force_prep(st, g, c->le, sd, c->phi, c->grad, c->delsq, c->le_term, c->le_fcor);
+  if (do_ch)    c->launches += c->k->le_ch_prep(st, g, c->le, sd, c->phi, c->delsq, c->u, status_ptr(c), c->le_chx);
+  c->launches += c->k->le_force_ch(st, g, c->le, sd, fx, nx, xlist, do_force, do_ch, accumulate, c->phi, c->grad,
 				   c->delsq, c->u, status_ptr(c), c->le_fcor, c->le_chx, c->force, phinew);
   return 0;
 }
 
 // lb_data_apply_le_boundary_conditions, src/model_le.c:78-180 (in place on the post-collision distributions)
-static int le_lb_bc_async(lb200_t * c) {
+static int le_lb_bc_async(lb200_t * c, double * f = nullptr, cudaStream_t st = nullptr) {
   if (c->le.nplane == 0) return 0;
   Lb200LeFix fx;
   le_lb_param(c, &fx);
-  ProfScope ps(c, LB200_K_LE);
-  c->launches += c->k->le_lb_bc(c->stream, c->g, c->le, fx, c->model_d, c->ndist, c->f, c->le_sbuf);
+  ProfScope ps(c, LB200_K_LE, st);
+  c->launches += c->k->le_lb_bc(st ? st : c->stream, c->g, c->le, fx, c->model_d, c->ndist, f ? f : c->f, c->le_sbuf);
   return 0;
 }
 
@@ -1835,7 +1851,9 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
   // (fast arithmetic mode; the TMA boxes of the populations need 16-byte aligned rows: even extents in z)
   // (with Lees-Edwards planes: the sweep runs over the whole lattice as if there were none, then the 2*nhalo x-planes per
   // plane whose stencils cross it are produced again by the patch kernels through the buffer planes)
-  const bool fuse_ok = binary && c->knob_fused && (!le || c->knob_fused_le) && !f32 && c->nvel == 19 && c->unrolled19 && c->ndist == 1
+  bool le_uniform = (c->le.xblock >= 2*c->g.nh + 4);                     // one plane every xblock x-planes (the sweep's store mask)
+  for (int p = 1; p < c->le.nplane; p++) le_uniform = le_uniform && (c->le.loc[p] == c->le.loc[0] + p*c->le.xblock);
+  const bool fuse_ok = binary && c->knob_fused && (!le || (c->knob_fused_le && le_uniform)) && !f32 && c->nvel == 19 && c->unrolled19 && c->ndist == 1
     && c->map_all_fluid && c->knob_pipe < 2 && sd->order <= 3 && sd->csum == nullptr
     && c->g.nh == 2 && (c->g.nall[2] & 1) == 0 && (c->g.nsites & 1) == 0
     && c->g.nl[1] >= 2 && c->g.nl[2] >= 2;
@@ -1871,13 +1889,53 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	if (rc != 0) return rc;
 	c->f_halo_stale = 1;                 // (still true for the reference's view: only what the pull reads is kept up to date)
       }
-      if (le) {
-	// field_leesedwards, hydro_lees_edwards: the buffer planes, from interior columns
-	le_field_async(c, c->phi, &gw);
-	le_hydro_async(c, &gw);
-      }
       // the phi sector of other CTAs (and of the neighbour GPUs) reads u(t-1) while this kernel writes u(t)
       double * u_out = (c->u == c->u_alloc[0]) ? c->u_alloc[1] : c->u_alloc[0];
+      // Lees-Edwards planes.  The sweep runs over the whole lattice as if there were none but stores nothing for the
+      // 2*nhalo x-planes per plane whose stencils cross it; the PATCH CHAIN produces those through the buffer planes:
+      // field_leesedwards + hydro_lees_edwards (buffer planes), gradients of planes loc-2 .. loc+3 and of the buffers,
+      // flux-form force with the plane correction + Cahn-Hilliard with the averaged plane fluxes (-> force, phinew),
+      // pull-stream + collision of the planes with that force, lb_data_apply_le_boundary_conditions, y / z images.
+      // It reads only what the previous step left (phi, u, f) and writes only what the sweep leaves out, so it may run
+      // NEXT TO the sweep on its own high-priority stream (LB200_FUSED_LE=2, intermediate steps; on the last step of a
+      // call the sweep also stores grad / delsq everywhere, which the chain must overwrite next to the planes).  Measured
+      // at 256^3, one plane: 1.321 ms next to the sweep, 1.332 after it; 512 x 256 x 256, 8 planes: 3.01 / 2.97 ms -- the
+      // sweep's CTAs fill the SMs (228 kB of shared memory each), so the chain's grids run on SMs taken from the sweep,
+      // not beside it.  Default: after the sweep.
+      const bool le_conc = le && c->le_stream != nullptr && !c->profile && gw.skip_diag && c->knob_fused_le >= 2;
+      auto le_chain = [&](cudaStream_t T) {
+	Lb200Geom gl = gw;
+	gl.peer_phi_lo = gl.peer_phi_hi = gl.peer_f_lo = gl.peer_f_hi = gl.peer_u_lo = gl.peer_u_hi = nullptr;
+	{
+	  Lb200LeInterp ipc, ipl;
+	  le_interp_cubic(c, &ipc);
+	  le_interp_linear(c, &ipl);
+	  ProfScope ps(c, LB200_K_LE, T);
+	  c->launches += c->k->le_interp_both(T, gl, c->le, ipc, ipl, c->g.nh, c->phi, c->u);
+	}
+	{
+	  ProfScope ps(c, LB200_K_LE, T);
+	  c->launches += c->k->le_grad_planes(T, gl, 0, c->le_ntrip_fused, c->le_trip_fused, c->phi, c->grad, c->delsq);
+	}
+	le_force_ch_async(c, *sd, c->le_nxlist, c->le_xlist, 1, 1, 0, c->phinew, &gl, T);
+	{
+	  ProfScope ps(c, LB200_K_LE, T);
+	  for (int p = 0; p < c->le.nplane; p++) {
+	    Lb200Geom gc = gl;
+	    gc.xoff = c->le.loc[p] - c->g.nh; gc.xcnt = 2*c->g.nh;
+	    c->launches += c->k->collide(T, gc, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, u_out);
+	  }
+	}
+	le_lb_bc_async(c, c->fprime, T);
+	ProfScope ps(c, LB200_K_LE, T);
+	c->launches += c->k->le_yz_images(T, c->g, c->le_nxlist, c->le_xlist, c->fprime, c->nvel, 1, c->phinew, 1, c->g.nh, u_out, 3, 1);
+      };
+      if (le_conc) {
+	CUDA_TRY(cudaEventRecord(c->ev_le_a, S));
+	CUDA_TRY(cudaStreamWaitEvent(c->le_stream, c->ev_le_a, 0));
+	le_chain(c->le_stream);
+	CUDA_TRY(cudaEventRecord(c->ev_le_b, c->le_stream));
+      }
       gw.peer_phi_lo = peer ? c->lo.phi[idx2(c->phinew, c->phi_alloc)] : nullptr;
       gw.peer_phi_hi = peer ? c->hi.phi[idx2(c->phinew, c->phi_alloc)] : nullptr;
       gw.peer_f_lo = peer ? c->lo.f[idx2(c->fprime, c->f_alloc)] : nullptr;
@@ -1888,40 +1946,17 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       {
 	ProfScope ps(c, LB200_K_STEP_FUSED);
 	launched = c->k->step_fused(S, gw, *sd, cd, c->phi, c->u, c->f, c->fprime, c->grad, c->delsq, c->force,
-				    c->phinew, c->rho, u_out);
+				    c->phinew, c->rho, u_out, le ? c->le.loc[0] - c->g.nh + 1 : 0, le ? c->le.xblock : 0);
       }
+      if (le_conc) CUDA_TRY(cudaStreamWaitEvent(S, c->ev_le_b, 0));
+      if (le_conc && launched <= 0) return fail(LB200_ECUDA, "one-kernel step: launch refused after the Lees-Edwards patch chain was issued");
       if (launched > 0) {
 	c->launches += launched;
 	c->force_state = gw.skip_diag ? ZERO_PENDING : INTERIOR_ONLY;      // the force array is written by the last step only
-	if (le) {
-	  // planes loc-1 .. loc+2 of every Lees-Edwards plane again, through the buffer planes: gradients (also of the two
-	  // planes either side, which the sweep kept in registers), flux-form force with the plane correction, Cahn-Hilliard
-	  // with the averaged plane fluxes -> force, phinew; then pull-stream + collision of these planes with that force
-	  Lb200Geom gl = gw;
-	  gl.peer_phi_lo = gl.peer_phi_hi = gl.peer_f_lo = gl.peer_f_hi = gl.peer_u_lo = gl.peer_u_hi = nullptr;
-	  {
-	    ProfScope ps(c, LB200_K_LE);
-	    c->launches += c->k->le_grad_planes(S, gl, 0, c->le_ntrip_fused, c->le_trip_fused, c->phi, c->grad, c->delsq);
-	  }
-	  le_force_ch_async(c, *sd, c->le_nxlist, c->le_xlist, 1, 1, 0, c->phinew, &gl);
-	  ProfScope ps(c, LB200_K_LE);
-	  for (int p = 0; p < c->le.nplane; p++) {
-	    Lb200Geom gc = gl;
-	    gc.xoff = c->le.loc[p] - c->g.nh; gc.xcnt = 2*c->g.nh;
-	    c->launches += c->k->collide(S, gc, cd, model_ptr(c), c->nvel, 1, c->f, c->fprime, c->force, status_ptr(c), c->rho, u_out);
-	  }
-	}
+	if (le && !le_conc) le_chain(S);
 	{ double * t = c->phi; c->phi = c->phinew; c->phinew = t; }
 	{ double * t = c->f; c->f = c->fprime; c->fprime = t; }
 	c->u = u_out;
-	if (le) {
-	  le_lb_bc_async(c);                                                // lb_data_apply_le_boundary_conditions
-	  // the y / z images of what the patches produced (the sweep stored the images of its own values)
-	  ProfScope ps(c, LB200_K_LE);
-	  c->launches += c->k->le_yz_images(S, c->g, c->le_nxlist, c->le_xlist, c->nvel, 1, c->f);
-	  c->launches += c->k->le_yz_images(S, c->g, c->le_nxlist, c->le_xlist, 1, c->g.nh, c->phi);
-	  c->launches += c->k->le_yz_images(S, c->g, c->le_nxlist, c->le_xlist, 3, 1, c->u);
-	}
 	c->u_state = INTERIOR_ONLY;
 	c->prop_pending = 1;
 	c->f_halo_stale = 1; c->fused_ready = 1;

@@ -642,22 +642,24 @@ int launch_step_fused_by(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDe
 
 int launch_step_fused_ws(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const Lb200CollideDev & cp,
 			 const double * phi, const double * u, const double * fsrc, double * fdst, double * grad,
-			 double * delsq, double * force, double * phinew, double * rho, double * u_out);
+			 double * delsq, double * force, double * phinew, double * rho, double * u_out, int le_x0, int le_xb);
 
-// 1: launched; 0: this configuration has no one-kernel step (the caller runs the two-kernel step)
+// 1: launched; 0: this configuration has no one-kernel step (the caller runs the two-kernel step).
+// le_xb > 0: Lees-Edwards planes every le_xb x-planes, the first between x = le_x0 + 1 and le_x0 + 2 -- the sweep stores
+// nothing (phinew, f', u, rho, force) for x-planes le_x0 .. le_x0 + 3 (+ m le_xb): the caller's patch kernels produce them
 int launch_step_fused(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const Lb200CollideDev & cp,
 		      const double * phi, const double * u, const double * fsrc, double * fdst, double * grad,
-		      double * delsq, double * force, double * phinew, double * rho, double * u_out) {
+		      double * delsq, double * force, double * phinew, double * rho, double * u_out, int le_x0, int le_xb) {
   if (sp.order < 1 || sp.order > 3 || sp.csum != nullptr) return 0;
   // the staged source rows start at even array indices: 16-byte aligned only if every row does
   if (g.nh != 2 || (g.nall[2] & 1) || (g.nsites & 1) || (g.nl[2] & 1) || g.nl[1] < 2 || g.nl[2] < 2) return 0;
 #ifndef LB200_STRICT
   static const int ws = tuned_flag("LB200_FUSED_WS", 1);      // warp-specialised roles (lb200_fused_ws.cuh); 0: every warp does both halves
-  if (!ws) {
+  if (!ws && le_xb <= 0) {
     static const int by = tuned_flag("LB200_FUSED_BY", 10);
     if (by == 8) return launch_step_fused_by<8>(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
     return launch_step_fused_by<10>(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
   }
 #endif
-  return launch_step_fused_ws(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out);
+  return launch_step_fused_ws(st, g, sp, cp, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out, le_x0, le_xb);
 }

@@ -40,7 +40,7 @@ template <int ORDER, bool GHOST>
 __global__ void __launch_bounds__(FW_NT, 1)
 step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap phimap,
 		     const __grid_constant__ CUtensorMap umap, const Lb200Geom g, const Lb200SymmDev sp,
-		     const Lb200CollideDev cp, int xc,
+		     const Lb200CollideDev cp, int xc, int le_x0, int le_xb,
 		     const double * __restrict__ phi, const double * __restrict__ u,
 		     const double * __restrict__ fsrc, double * __restrict__ fdst,
 		     double * __restrict__ grad, double * __restrict__ delsq,
@@ -174,8 +174,13 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
   const double r9 = (1.0/9.0), r18 = 0.5*(1.0/9.0);
   const int fidx = (ty - 1)*32 + tz;                // own slot of the force block (interior rows)
 
+  // Lees-Edwards planes (le_xb > 0: one every le_xb x-planes; le_x0 = the plane below the first one, minus one): the 2*nhalo
+  // x-planes whose stencils cross a plane are produced by the patch kernels, concurrently -- nothing is stored for them here
+  int ler = (le_xb > 0) ? (istart - 1 - le_x0 + 2*le_xb) % le_xb : 0;      // (plane n-1) relative to the patched window
   int q = 0;                                       // phase: (plane n - first plane) % 6
   for (int n = istart; n <= k.i1 + 1; n++) {
+    const bool le_skip = (le_xb > 0) && (ler < 4);
+    if (++ler == le_xb) ler = 0;
     const bool do_grad = (n <= k.i1);
     const bool do_fx   = (n >= k.i0 - 1 && n <= k.i1);
     const bool do_full = (n >= k.i0 && n <= k.i1);
@@ -276,7 +281,7 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
     }
 
     // ---- 4. phi update of plane n-1, whose y/z face fluxes were published one plane-step ago ----
-    if (do_upd && k.out_site) {
+    if (do_upd && k.out_site && !le_skip) {
       const double (* fl)[G::NT] = sm.fl[q1 & 1];
       const int s = (n - 1 + k.nh - 1)*k.xs + k.scol;
       const double phn = r.phim1 - (((r.fxm1 - r.fxm2) + (r.fy_prev - fl[0][tym])) + k.wz*(r.fz_prev - fl[1][tzm]));
@@ -513,7 +518,10 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
   else {
     // ================================ pull-stream + collision ================================
     const int fidx = (ty - 1)*32 + tz;
+    int ler = (le_xb > 0) ? (k.i0 - le_x0 + 2*le_xb) % le_xb : 0;
     for (int m = k.i0; m <= k.i1 && k.has_sites; m++) {
+      const bool le_skip = (le_xb > 0) && (ler < 4);     // a plane next to a Lees-Edwards plane: collided by the patch kernels
+      if (++ler == le_xb) ler = 0;
       const int fs = (m - k.i0) % FW_NF;
       // the populations of the own site (every lane reads its slot, so that the stage can be released by the warp) ...
       double f[19];
@@ -523,7 +531,7 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
       const double F0 = sw.F[fs][0][fidx], F1 = sw.F[fs][1][fidx], F2 = sw.F[fs][2][fidx];
       __syncwarp();
       if (tz == 0) { fw_mbar_arrive(FW_AD(sempty) + 8u*((m - k.i0) % FU_NSTAGE)); fw_mbar_arrive(FW_AD(fempty) + 8u*fs); }
-      if (k.out_site) fu_collide<GHOST, BY, true>(sm, k, cp, m, F0, F1, F2, fsrc, fdst, force, rho_out, u_out, f);
+      if (k.out_site && !le_skip) fu_collide<GHOST, BY, true>(sm, k, cp, m, F0, F1, F2, fsrc, fdst, force, rho_out, u_out, f);
     }
   }
 }
@@ -532,7 +540,7 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
 
 int launch_step_fused_ws(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, const Lb200CollideDev & cp,
 			 const double * phi, const double * u, const double * fsrc, double * fdst, double * grad,
-			 double * delsq, double * force, double * phinew, double * rho, double * u_out) {
+			 double * delsq, double * force, double * phinew, double * rho, double * u_out, int le_x0, int le_xb) {
   constexpr int BY = FW_BY;
   using G = FuGeo<BY>;
   const int ext = g.skip_diag ? 0 : 1;
@@ -566,7 +574,7 @@ int launch_step_fused_ws(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDe
     }
   }
   dim3 grd(gz, gy, (nx + xc - 1)/xc);
-#define LB200_FW_GO(O, GH) step_fused_ws_kernel<O, GH><<<grd, FW_NT, smem, st>>>(fmap, phimap, umap, g, sp, cp, xc, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out)
+#define LB200_FW_GO(O, GH) step_fused_ws_kernel<O, GH><<<grd, FW_NT, smem, st>>>(fmap, phimap, umap, g, sp, cp, xc, le_x0, le_xb, phi, u, fsrc, fdst, grad, delsq, force, phinew, rho, u_out)
   if (cp.ghost) {
     if (sp.order == 1) LB200_FW_GO(1, true); else if (sp.order == 2) LB200_FW_GO(2, true); else LB200_FW_GO(3, true);
   }

@@ -2497,5 +2497,6 @@ const Lb200Kernels LB200_TABLE = {
   launch_phi_sum_ranks,
   launch_phi_subtract,
   launch_le_yz_images,
+  launch_le_interp_both,
   PSUM_BLOCKS,
 };

@@ -174,19 +174,24 @@ struct Lb200Kernels {
   // the whole binary-fluid time step in ONE sweep (lb200_fused.cuh): phi sector + pull-stream + collision of the
   // same plane, the force never stored (force / rho / grad / delsq arrays written only when !skip_diag).  u_in and
   // u_out must be different buffers.  Returns 0 without launching when this build has no such kernel (strict
-  // mode, compensated Cahn-Hilliard update): the caller then runs phi_sector + collide.
+  // mode, compensated Cahn-Hilliard update): the caller then runs phi_sector + collide.  le_xb > 0 (Lees-Edwards planes
+  // every le_xb x-planes): nothing is stored for x-planes le_x0 .. le_x0 + 3 (+ m le_xb), the patch kernels produce them.
   int (*step_fused)(cudaStream_t, const Lb200Geom &, const Lb200SymmDev &, const Lb200CollideDev &,
 		    const double * phi, const double * u_in, const double * fsrc, double * fdst, double * grad,
-		    double * delsq, double * force, double * phinew, double * rho, double * u_out);
+		    double * delsq, double * force, double * phinew, double * rho, double * u_out, int le_x0, int le_xb);
   // cahn_hilliard_options_conserve 2: result[0] = compensated sum of phi over the fluid interior sites of this GPU in a
   // fixed order, result[1] = their number; partial: 2*psum_blocks + 1 doubles of scratch (zero before the first call).
   // phi_sum_ranks: all[2r], all[2r+1] of every rank -> total[0..1] in rank order.  phi_subtract: phi -= (total[0] - phi0)/total[1]
   int (*phi_sum)(cudaStream_t, const Lb200Geom &, const double * phi, const char * status, double * partial, double * result);
   int (*phi_sum_ranks)(cudaStream_t, const double * all, int nranks, double * total);
   int (*phi_subtract)(cudaStream_t, const Lb200Geom &, const double * total, double phi0, const char * status, double * phi);
-  // y / z periodic images (depth d) of ncomp components on a list of x-planes (the one-kernel step with Lees-Edwards
+  // y / z periodic images of up to three arrays on a list of x-planes (the one-kernel step with Lees-Edwards
   // planes: the patched planes' images)
-  int (*le_yz_images)(cudaStream_t, const Lb200Geom &, int nx, const int * xlist, int ncomp, int depth, double * data);
+  int (*le_yz_images)(cudaStream_t, const Lb200Geom &, int nx, const int * xlist, double * d0, int ncomp0, int depth0,
+		      double * d1, int ncomp1, int depth1, double * d2, int ncomp2, int depth2);
+  // field_leesedwards(phi) + hydro_lees_edwards(u) in one launch
+  int (*le_interp_both)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200LeInterp & cubic,
+			const Lb200LeInterp & linear, int zext, double * phi, double * u);
   int psum_blocks;
 };
 

@@ -93,6 +93,59 @@ le_interp_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, const
   }
 }
 
+// field_leesedwards(phi) and hydro_lees_edwards(u) in one launch (the patch chain of the one-kernel step): same
+// expressions as le_interp_kernel<true> / <false>
+__global__ void __launch_bounds__(TPB_MAX)
+le_interp_both_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, const Lb200LeInterp ipc, const Lb200LeInterp ipl,
+		      int zext, double * __restrict__ phi, double * __restrict__ u) {
+  const int kc = 1 - zext + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 - g.nh + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ib = blockIdx.z;
+  if (kc > g.nl[2] + zext || jc > g.nl[1] + g.nh) return;
+  const int nh = g.nh;
+  const int p = ib/(2*nh);
+  const int r = ib % (2*nh);
+  const int ic = le.loc[p] - (nh - 1) + r;
+  const int sgn = (r < nh) ? 0 : 1;
+  const int ny = g.nl[1];
+  const size_t ns = (size_t) g.nsites;
+  const int dst = le_index(g, g.nl[0] + nh + 1 + ib, jc, kc);
+  const int ks = le_wz(g, kc);
+  {
+    const int jdy = ipc.jdy[sgn];
+    const int j0 = 1 + (jc - jdy - 3 + 2*ny) % ny;
+    const int j1 = 1 + j0 % ny;
+    const int j2 = 1 + j1 % ny;
+    const int j3 = 1 + j2 % ny;
+    const double w0 = ipc.w[sgn][0], w1 = ipc.w[sgn][1], w2 = ipc.w[sgn][2], w3 = ipc.w[sgn][3];
+    phi[dst] = - w0*phi[le_index(g, ic, j0, ks)] + w1*phi[le_index(g, ic, j1, ks)]
+      - w2*phi[le_index(g, ic, j2, ks)] + w3*phi[le_index(g, ic, j3, ks)];
+  }
+  {
+    const int jdy = ipl.jdy[sgn];
+    const int j1 = 1 + (jc - jdy - 2 + 2*ny) % ny;
+    const int j2 = 1 + j1 % ny;
+    const double fr = ipl.w[sgn][0], omfr = ipl.w[sgn][1];
+    const int s1 = le_index(g, ic, j1, ks), s2 = le_index(g, ic, j2, ks);
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+      const double * d = u + n*ns;
+      const double ule = (n == 1) ? le.uy*(sgn ? 1 : -1) : 0.0;
+      u[n*ns + dst] = ule + d[s1]*fr + d[s2]*omfr;
+    }
+  }
+}
+
+int launch_le_interp_both(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le, const Lb200LeInterp & ipc,
+			  const Lb200LeInterp & ipl, int zext, double * phi, double * u) {
+  if (le.nplane == 0) return 0;
+  dim3 blk;
+  block_shape(g.nl[2] + 2*zext, blk);
+  dim3 grd((g.nl[2] + 2*zext + blk.x - 1)/blk.x, (g.nall[1] + blk.y - 1)/blk.y, 2*g.nh*le.nplane);
+  le_interp_both_kernel<<<grd, blk, 0, st>>>(g, le, ipc, ipl, zext, phi, u);
+  return 1;
+}
+
 int launch_le_interp(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le, const Lb200LeInterp & ip,
 		     int cubic, int ncomp, int zext, double * data) {
   if (le.nplane == 0) return 0;
@@ -475,9 +528,9 @@ le_lb_reproject_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le,
     double rho = 0.0;
     double gv[3] = {0.0, 0.0, 0.0};
     double ds[3][3];
-    for (int p = 0; p < nvel; p++) rho += f[(size_t) (n*nvel + p)*ns + index];
-    for (int p = 0; p < nvel; p++) {
+    for (int p = 0; p < nvel; p++) {               // (each accumulator sees the reference's order of additions)
       const double fp = f[(size_t) (n*nvel + p)*ns + index];
+      rho += fp;
       for (int ia = 0; ia < 3; ia++) gv[ia] += md->cv[p][ia]*fp;
     }
     for (int ia = 0; ia < 3; ia++)
@@ -555,8 +608,15 @@ int launch_le_lb_bc(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le,
 // One thread per shell site (2d full rows of the allocation's cross-section, then 2d sites of each interior row).
 // ---------------------------------------------------------------------------------------------
 
+struct Lb200Images { double * data[3]; int ncomp[3]; int depth[3]; };
+
 __global__ void __launch_bounds__(TPB)
-le_yz_images_kernel(const Lb200Geom g, const int * __restrict__ xlist, int ncomp, int d, double * __restrict__ data) {
+le_yz_images_kernel(const Lb200Geom g, const int * __restrict__ xlist, const Lb200Images im) {
+  // grid layer -> (array, component)
+  int n = blockIdx.z, a = 0;
+  if (n >= im.ncomp[0]) { n -= im.ncomp[0]; a = 1; if (n >= im.ncomp[1]) { n -= im.ncomp[1]; a = 2; } }
+  const int d = im.depth[a];
+  double * __restrict__ data = im.data[a];
   const int ny = g.nl[1], nz = g.nl[2];
   const int ez = nz + 2*d;
   const int nshell = 2*d*ez + 2*d*ny;
@@ -578,13 +638,22 @@ le_yz_images_kernel(const Lb200Geom g, const int * __restrict__ xlist, int ncomp
   const int dst = le_index(g, ic, jc, kc);
   const int src = le_index(g, ic, lb200_wrap1(jc, ny, 1), lb200_wrap1(kc, nz, 1));
   const size_t ns = (size_t) g.nsites;
-  for (int n = 0; n < ncomp; n++) data[n*ns + dst] = data[n*ns + src];
+  data[n*ns + dst] = data[n*ns + src];
 }
 
-int launch_le_yz_images(cudaStream_t st, const Lb200Geom & g, int nx, const int * xlist, int ncomp, int depth, double * data) {
-  if (nx == 0 || depth <= 0) return 0;
-  const int nshell = 2*depth*(g.nl[2] + 2*depth) + 2*depth*g.nl[1];
-  dim3 grd((nshell + TPB - 1)/TPB, nx, 1);
-  le_yz_images_kernel<<<grd, TPB, 0, st>>>(g, xlist, ncomp, depth, data);
+// up to three arrays (data == nullptr: none) in one launch
+int launch_le_yz_images(cudaStream_t st, const Lb200Geom & g, int nx, const int * xlist,
+			double * d0, int ncomp0, int depth0, double * d1, int ncomp1, int depth1, double * d2, int ncomp2, int depth2) {
+  if (nx == 0) return 0;
+  Lb200Images im;
+  im.data[0] = d0; im.ncomp[0] = d0 ? ncomp0 : 0; im.depth[0] = depth0;
+  im.data[1] = d1; im.ncomp[1] = d1 ? ncomp1 : 0; im.depth[1] = depth1;
+  im.data[2] = d2; im.ncomp[2] = d2 ? ncomp2 : 0; im.depth[2] = depth2;
+  int dmax = 0, nl = 0;
+  for (int a = 0; a < 3; a++) if (im.ncomp[a] > 0) { dmax = max(dmax, im.depth[a]); nl += im.ncomp[a]; }
+  if (nl == 0 || dmax <= 0) return 0;
+  const int nshell = 2*dmax*(g.nl[2] + 2*dmax) + 2*dmax*g.nl[1];
+  dim3 grd((nshell + TPB - 1)/TPB, nx, nl);
+  le_yz_images_kernel<<<grd, TPB, 0, st>>>(g, xlist, im);
   return 1;
 }

@@ -210,6 +210,40 @@ def test_le_one_kernel_step(n, nplanes, order, calls):
         assert close_fast(orc.interior(got[k]), orc.interior(want[k])), (k, np.abs(orc.interior(got[k]) - orc.interior(want[k])).max())
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_le_one_kernel_step_chain_modes(mode, monkeypatch):
+    """LB200_FUSED_LE=2: the patch chain runs next to the sweep on its own stream on intermediate steps; 1 (default): after
+    it.  Same kernels on the same data: identical results, and equal to the oracle within the fast bar after 30 steps"""
+    monkeypatch.setenv("LB200_FUSED_LE", mode)
+    n = (48, 26, 36)
+    orc, got, want, prof = _run_steps_profiled(n, 2, 3, 30, 2)
+    assert prof["step_fused"][1] == 29
+    for k in want:
+        assert close_fast(orc.interior(got[k]), orc.interior(want[k])), (k, np.abs(orc.interior(got[k]) - orc.interior(want[k])).max())
+
+
+def test_le_chain_next_to_the_sweep_is_deterministic(monkeypatch):
+    """the concurrent chain (not profiled: that is when it runs on its own stream) twice, and once serial: bit-identical"""
+    def run(mode):
+        monkeypatch.setenv("LB200_FUSED_LE", mode)
+        orc, sim, sp_o, sp_g = make((64, 32, 32), 4, 3, lb.MATH_FAST)
+        f = np.zeros((19, orc.nsites_lb))
+        orc.le_init_shear_profile(1.0, ETA, f)
+        phi = np.zeros((1, orc.nsites))
+        phi[:, :orc.nsites_lb] = spinodal_phi((64, 32, 32), 2, 5, 0.0, 0.1)
+        with sim:
+            sim.put(lb.F, f); sim.put(lb.PHI, phi)
+            for _ in range(3):
+                sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), sp_g, 15)
+            return orc, {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("force", lb.FORCE), ("grad", lb.GRAD))}
+    orc, a = run("2")
+    orc, b = run("2")
+    orc, s = run("1")
+    for k in a:
+        assert np.array_equal(orc.interior(a[k]), orc.interior(b[k])), k
+        assert np.array_equal(orc.interior(a[k]), orc.interior(s[k])), k
+
+
 def test_le_one_kernel_step_equals_two_kernel_step(monkeypatch):
     """LB200_FUSED_LE=0 (phi sector + collision + patches) and the one-kernel form give the same fields within the fast bar"""
     n = (32, 24, 32)
