@@ -139,6 +139,8 @@ struct lb200_s {
   double * u2;               // second velocity buffer: the collision writes the one the neighbours' phi sector is not reading
   unsigned int * flags;      // [0] phi sector done on the low / [1] high neighbour, [2] collision low / [3] high
   int * spin_err;
+  int spin_used;             // the spinning wait kernel has been launched in this context
+  int joint_signal;          // the last signal set the phi flags and the f / u flags together (signal2)
   PeerLink lo, hi;
   void * mapped[14];         // everything opened with cudaIpcOpenMemHandle
   int nmapped;
@@ -761,11 +763,21 @@ int lb200_nsites_lb(const lb200_t * c) { return c ? c->nsites_lb : LB200_EINVAL;
 long long lb200_launch_count(const lb200_t * c) { return c ? c->launches : 0; }
 void * lb200_stream(lb200_t * c) { return c ? (void *) c->stream : nullptr; }
 
+// The fallback flag wait (a spinning kernel, when the driver has no stream memory operations) gives up after 20 s:
+// whatever ran after it then read halo planes that never arrived.  Checked wherever the host waits for the stream.
+static int spin_check(lb200_t * c) {
+  if (!c->spin_used) return 0;
+  int e = 0;
+  CUDA_TRY(cudaMemcpy(&e, c->spin_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e != 0) return fail(LB200_ECOMM, "a neighbour GPU's boundary planes did not arrive within 20 s (peer-store flag wait timed out)");
+  return 0;
+}
+
 int lb200_sync(lb200_t * c) {
   if (c == nullptr) return fail(LB200_EINVAL, "null context");
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
-  return 0;
+  return spin_check(c);
 }
 
 static const char * status_ptr(const lb200_t * c) { return c->map_all_fluid ? nullptr : c->status; }
@@ -898,7 +910,10 @@ static int do_memcpy(lb200_t * c, int array, double * host, int kind, int async)
   return 0;
 }
 
-int lb200_memcpy(lb200_t * c, int array, double * host, int kind) { return do_memcpy(c, array, host, kind, 0); }
+int lb200_memcpy(lb200_t * c, int array, double * host, int kind) {
+  const int rc = do_memcpy(c, array, host, kind, 0);
+  return (rc == 0 && kind == LB200_DEVICE_TO_HOST) ? spin_check(c) : rc;
+}
 int lb200_memcpy_async(lb200_t * c, int array, double * host, int kind) { return do_memcpy(c, array, host, kind, 1); }
 
 int lb200_device_ptr(lb200_t * c, int array, void ** ptr) {
@@ -1673,6 +1688,7 @@ static int flags_wait(lb200_t * c, cudaStream_t st, int ilo, unsigned int value)
     }
     else {
       c->launches += c->k->spin_wait(st, c->flags + i, value, 20000, c->spin_err);
+      c->spin_used = 1;
     }
   }
   return 0;
@@ -1873,9 +1889,12 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
       // propagation is pending -- and takes the two-kernel route below.)
       if (le) gw.skip_diag = (c->knob_lazy_diag && n < nsteps - 1) ? 1 : 0;  // (the patches form the gradients they read themselves)
       if (remote) {
-	rc = src_wait(c, S, c->phi_src, c->ev_phi, FLAG_PS_LO, c->n_ps);
+	// (after a one-kernel step the neighbours set the phi flags and then the f / u flags from one thread, with a fence in
+	// between: the second pair implies the first)
+	const bool joint = c->joint_signal && c->phi_src == SRC_FLAG && c->u_src == SRC_FLAG && c->f_src == SRC_FLAG;
+	if (!joint) rc = src_wait(c, S, c->phi_src, c->ev_phi, FLAG_PS_LO, c->n_ps);
 	if (rc == 0) rc = src_wait(c, S, c->u_src, c->ev_u, FLAG_COL_LO, c->n_col);
-	if (rc == 0) rc = src_wait(c, S, c->f_src, c->ev_f, FLAG_COL_LO, c->n_col);
+	if (rc == 0 && !(c->f_src == SRC_FLAG && c->u_src == SRC_FLAG)) rc = src_wait(c, S, c->f_src, c->ev_f, FLAG_COL_LO, c->n_col);
 	if (rc != 0) return rc;
       }
       // the TMA boxes of the populations read the y / z halos (and the rims of the x halo planes): valid after a
@@ -1962,9 +1981,10 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	c->f_halo_stale = 1; c->fused_ready = 1;
 	if (peer) {
 	  c->n_ps++; c->n_col++;
-	  c->launches += c->k->signal(S, c->hi.flags + FLAG_PS_LO, c->lo.flags + FLAG_PS_HI, c->n_ps);
-	  c->launches += c->k->signal(S, c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
+	  c->launches += c->k->signal2(S, c->hi.flags + FLAG_PS_LO, c->lo.flags + FLAG_PS_HI, c->n_ps,
+				       c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
 	  c->phi_src = c->f_src = c->u_src = SRC_FLAG;
+	  c->joint_signal = 1;
 	}
 	else if (remote) {
 	  CUDA_TRY(cudaEventRecord(c->ev_main, S));
@@ -2018,6 +2038,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
 	// the new phi planes are already in the neighbours' halo planes: tell them
 	c->n_ps++;
 	c->launches += c->k->signal(S, c->hi.flags + FLAG_PS_LO, c->lo.flags + FLAG_PS_HI, c->n_ps);
+	c->joint_signal = 0;
 	c->phi_src = SRC_FLAG;
       }
       else if (remote) {
@@ -2075,6 +2096,7 @@ static int step_wrap(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev
     if (peer) {
       c->n_col++;
       c->launches += c->k->signal(S, c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
+      c->joint_signal = 0;
       c->f_src = c->u_src = SRC_FLAG;
     }
     else if (remote) {
@@ -2567,6 +2589,7 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
 	if ((rc = peer_copy_planes(c, C, c->q, c->lo.phi[iq], c->hi.phi[iq], 0, 5, g.nh, 1, 1)) != 0) return rc;
 	c->n_ps++;
 	c->launches += c->k->signal(C, c->hi.flags + FLAG_PS_LO, c->lo.flags + FLAG_PS_HI, c->n_ps);
+	c->joint_signal = 0;
 	q_src = SRC_FLAG;
       }
       else {
@@ -2606,6 +2629,7 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
 	  if ((rc = peer_copy_f(c, C, c->f, c->lo.f[jf], c->hi.f[jf])) != 0) return rc;
 	  c->n_col++;
 	  c->launches += c->k->signal(C, c->hi.flags + FLAG_COL_LO, c->lo.flags + FLAG_COL_HI, c->n_col);
+	  c->joint_signal = 0;
 	  u_src = f_src = SRC_FLAG;
 	}
 	else {

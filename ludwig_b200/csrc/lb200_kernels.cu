@@ -2302,6 +2302,19 @@ __global__ void signal_kernel(unsigned int * a, unsigned int * b, unsigned int v
   }
 }
 
+// two flag pairs at one point of the stream (the one-kernel step produces the phi planes and the f / u planes together)
+__global__ void signal2_kernel(unsigned int * a, unsigned int * b, unsigned int vab, unsigned int * c, unsigned int * d, unsigned int vcd) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (a != nullptr) *((volatile unsigned int *) a) = vab;
+    if (b != nullptr) *((volatile unsigned int *) b) = vab;
+    __threadfence_system();                        // whoever sees the second pair's value also sees the first pair's
+    if (c != nullptr) *((volatile unsigned int *) c) = vcd;
+    if (d != nullptr) *((volatile unsigned int *) d) = vcd;
+    __threadfence_system();
+  }
+}
+
 __global__ void spin_wait_kernel(const unsigned int * flag, unsigned int value, long long timeout_ns, int * err) {
   if (threadIdx.x == 0) {
     long long t0;
@@ -2420,6 +2433,11 @@ int launch_signal(cudaStream_t st, unsigned int * a, unsigned int * b, unsigned 
   return 1;
 }
 
+int launch_signal2(cudaStream_t st, unsigned int * a, unsigned int * b, unsigned int vab, unsigned int * c, unsigned int * d, unsigned int vcd) {
+  signal2_kernel<<<1, 32, 0, st>>>(a, b, vab, c, d, vcd);
+  return 1;
+}
+
 int launch_spin_wait(cudaStream_t st, const unsigned int * flag, unsigned int value, int timeout_ms, int * err) {
   spin_wait_kernel<<<1, 32, 0, st>>>(flag, value, (long long) timeout_ms*1000000LL, err);
   return 1;
@@ -2498,5 +2516,6 @@ const Lb200Kernels LB200_TABLE = {
   launch_phi_subtract,
   launch_le_yz_images,
   launch_le_interp_both,
+  launch_signal2,
   PSUM_BLOCKS,
 };

@@ -192,6 +192,8 @@ struct Lb200Kernels {
   // field_leesedwards(phi) + hydro_lees_edwards(u) in one launch
   int (*le_interp_both)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200LeInterp & cubic,
 			const Lb200LeInterp & linear, int zext, double * phi, double * u);
+  // signal() for two flag pairs with their own values, one launch
+  int (*signal2)(cudaStream_t, unsigned int * a, unsigned int * b, unsigned int vab, unsigned int * c, unsigned int * d, unsigned int vcd);
   int psum_blocks;
 };
 
