@@ -17,7 +17,7 @@
  *
  * This header is a stand-alone, self-contained statement of that interface (its structs are cut-down look-alikes).
  * The proof that the library is a drop-in for the reference's OWN structs and callers is integration/: the reference's
- * src/ludwig.c and tests/unit/*.c, unchanged, linked against libludwig_b200.so through integration/ludwig_b200_shim.c,
+ * src/ludwig.c and tests/unit/test_*.c, unchanged, linked against libludwig_b200.so through integration/ludwig_b200_shim.c,
  * which is compiled against the reference's own headers (tests/test_gpu_reference_callers.py).
  */
 #ifndef LUDWIG_HOST_H
@@ -124,6 +124,24 @@ typedef enum lb_relaxation_enum {LB_RELAXATION_M10, LB_RELAXATION_BGK, LB_RELAXA
 typedef enum lb_halo_enum {LB_HALO_FULL = 1, LB_HALO_REDUCED = 2} lb_halo_enum_t;
 typedef enum lb_dist_enum_type {LB_RHO = 0, LB_PHI = 1} lb_dist_enum_t;
 
+/* src/io_options.h:22-52, src/io_info_args.h:33-38 (record format of the files lb_io_* / field_io_* write and read) */
+typedef enum io_mode_enum {IO_MODE_INVALID, IO_MODE_MPIIO} io_mode_enum_t;
+typedef enum io_record_format_enum {IO_RECORD_INVALID, IO_RECORD_ASCII, IO_RECORD_BINARY} io_record_format_enum_t;
+typedef enum io_metadata_version_enum {IO_METADATA_INVALID, IO_METADATA_SINGLE_V1, IO_METADATA_MULTI_V1, IO_METADATA_V2} io_metadata_version_enum_t;
+typedef struct io_options_s {
+  io_mode_enum_t mode;
+  io_record_format_enum_t iorformat;      /* IO_RECORD_ASCII: " %22.15e" per datum; IO_RECORD_BINARY (default): doubles */
+  io_metadata_version_enum_t metadata_version;
+  int report;
+  int asynchronous;
+  int compression_levl;
+  int iogrid[3];                          /* {1, 1, 1}: one file (the only decomposition of a one-process host layer) */
+} io_options_t;
+typedef struct io_info_args_s {io_options_t input; io_options_t output; int grid[3]; int iofreq;} io_info_args_t;
+io_options_t io_options_default(void);
+io_options_t io_options_with_format(io_mode_enum_t mode, io_record_format_enum_t iorf);
+io_info_args_t io_info_args_default(void);
+
 typedef struct lb_data_options_s {
   int ndim;
   int nvel;
@@ -132,6 +150,7 @@ typedef struct lb_data_options_s {
   lb_halo_enum_t halo;
   int reportimbalance;
   int usefirsttouch;
+  io_info_args_t iodata;                  /* src/lb_data_options.h:41 */
 } lb_data_options_t;
 
 typedef struct lb_model_s {
@@ -178,7 +197,9 @@ int lb_collision_relaxation_set(lb_t * lb, lb_relaxation_enum_t nrelax);     /* 
 int lb_collide_param_commit(lb_t * lb);                                      /* src/lb_data.h:166 */
 
 /* ---- field_t: src/field.h:68-130, src/field_options.h ---------------------------------------- */
-typedef struct field_options_s {int ndata; int nhcomm; int haloscheme; int haloverbose; int usefirsttouch;} field_options_t;
+typedef struct field_options_s {int ndata; int nhcomm; int haloscheme; int haloverbose; int usefirsttouch;
+				io_info_args_t iodata;   /* src/field_options.h:36 */
+} field_options_t;
 field_options_t field_options_default(void);
 field_options_t field_options_ndata_nhalo(int ndata, int nhalo);
 
@@ -393,10 +414,17 @@ int beris_edw_update(beris_edw_t * be, fe_t * fe, field_t * fq, field_grad_t * f
  * interior sites in (ic, jc, kc) order with kc fastest, one binary record per site (distributions: ndist*nvel
  * doubles in (n, p) order; fields: nf doubles), plus "<stub>-metadata.001-001" (JSON, written once).  Files are
  * byte-identical with the reference's default (mpiio, binary, single file) output, so either code restarts from
- * the other's. */
+ * the other's.  options.iodata.{input,output}.iorformat = IO_RECORD_ASCII selects the reference's text records
+ * (src/lb_data.c:1579-1640, src/field.c:931-1000: " %22.15e" per datum; distributions: one line of ndist values per
+ * velocity; fields: one line of nf values per site), again byte-identical. */
 typedef struct io_event_s {int unused;} io_event_t;
+#define LB_RECORD_LENGTH_ASCII 23        /* src/lb_data.h:45 */
 int lb_write_buf(const lb_t * lb, int index, char * buf);
 int lb_read_buf(lb_t * lb, int index, const char * buf);
+int lb_write_buf_ascii(const lb_t * lb, int index, char * buf);
+int lb_read_buf_ascii(lb_t * lb, int index, const char * buf);
+int field_write_buf_ascii(field_t * field, int index, char * buf);
+int field_read_buf_ascii(field_t * field, int index, const char * buf);
 int lb_io_write(lb_t * lb, int timestep, io_event_t * event);
 int lb_io_read(lb_t * lb, int timestep, io_event_t * event);
 int field_write_buf(field_t * field, int index, char * buf);

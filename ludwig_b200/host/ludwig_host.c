@@ -354,9 +354,21 @@ static int lb_model_init(lb_model_t * m, int nvel) {
   return 0;
 }
 
+/* src/io_options.c:36-120, src/io_info_args.c:24-36 */
+io_options_t io_options_with_format(io_mode_enum_t mode, io_record_format_enum_t iorf) {
+  io_options_t o = {.mode = mode, .iorformat = iorf, .metadata_version = IO_METADATA_V2, .report = 0, .asynchronous = 0,
+		    .compression_levl = 0, .iogrid = {1, 1, 1}};
+  return o;
+}
+io_options_t io_options_default(void) { return io_options_with_format(IO_MODE_MPIIO, IO_RECORD_BINARY); }
+io_info_args_t io_info_args_default(void) {
+  io_info_args_t a = {.input = io_options_default(), .output = io_options_default(), .grid = {1, 1, 1}, .iofreq = 100000};
+  return a;
+}
+
 lb_data_options_t lb_data_options_default(void) {
   lb_data_options_t o = {.ndim = 3, .nvel = 19, .ndist = 1, .nrelax = LB_RELAXATION_M10, .halo = LB_HALO_FULL,
-			 .reportimbalance = 0, .usefirsttouch = 0};
+			 .reportimbalance = 0, .usefirsttouch = 0, .iodata = io_info_args_default()};
   return o;
 }
 
@@ -515,8 +527,11 @@ int lb_init_rest_f(lb_t * lb, double rho0) {
 
 /* ---- field_t ------------------------------------------------------------------------------------------- */
 
-field_options_t field_options_default(void) { field_options_t o = {.ndata = 1, .nhcomm = 0}; return o; }
-field_options_t field_options_ndata_nhalo(int ndata, int nhalo) { field_options_t o = {.ndata = ndata, .nhcomm = nhalo}; return o; }
+field_options_t field_options_default(void) { field_options_t o = {.ndata = 1, .nhcomm = 0, .iodata = io_info_args_default()}; return o; }
+field_options_t field_options_ndata_nhalo(int ndata, int nhalo) {
+  field_options_t o = {.ndata = ndata, .nhcomm = nhalo, .iodata = io_info_args_default()};
+  return o;
+}
 
 static int field_create_tagged(pe_t * pe, cs_t * cs, lees_edw_t * le, const char * name,
 			       const field_options_t * opts, int tag, field_t ** pobj) {
@@ -1075,7 +1090,7 @@ static void io_file_name(const char * stub, int it, char * filename, size_t bufs
 }
 
 /* the reference's metadata file for the default options (mode mpiio, binary records, one file): same text */
-static int io_metadata_write_default(cs_t * cs, const char * stub, int count) {
+static int io_metadata_write_default(cs_t * cs, const char * stub, int count, int ascii) {
   char filename[BUFSIZ];
   FILE * fp = NULL;
   int nplanes = cs->le ? lees_edw_nplane_total(cs->le) : 0;
@@ -1097,10 +1112,10 @@ static int io_metadata_write_default(cs_t * cs, const char * stub, int count) {
 	    cs->le->opts.nt0, num);
   }
   fprintf(fp, "\n\t\t}\n\t},\n");
-  fprintf(fp, "\t\"io_options\":\t{\n\t\t\"Mode\":\t\"mpiio\",\n\t\t\"Record format\":\t\"binary\",\n\t\t\"Metadata version\":\t3,\n"
-	  "\t\t\"Report\":\tfalse,\n\t\t\"Asynchronous\":\tfalse,\n\t\t\"Compression level\":\t0,\n\t\t\"I/O grid\":\t[1, 1, 1]\n\t},\n");
-  fprintf(fp, "\t\"io_element\":\t{\n\t\t\"MPI_Datatype\":\t\"MPI_DOUBLE\",\n\t\t\"Size (bytes)\":\t8,\n\t\t\"Count\":\t%d,\n"
-	  "\t\t\"Endianness\":\t\"LITTLE_ENDIAN\"\n\t},\n", count);
+  fprintf(fp, "\t\"io_options\":\t{\n\t\t\"Mode\":\t\"mpiio\",\n\t\t\"Record format\":\t\"%s\",\n\t\t\"Metadata version\":\t3,\n"
+	  "\t\t\"Report\":\tfalse,\n\t\t\"Asynchronous\":\tfalse,\n\t\t\"Compression level\":\t0,\n\t\t\"I/O grid\":\t[1, 1, 1]\n\t},\n", ascii ? "ascii" : "binary");
+  fprintf(fp, "\t\"io_element\":\t{\n\t\t\"MPI_Datatype\":\t\"%s\",\n\t\t\"Size (bytes)\":\t%d,\n\t\t\"Count\":\t%d,\n"
+	  "\t\t\"Endianness\":\t\"LITTLE_ENDIAN\"\n\t},\n", ascii ? "MPI_CHAR" : "MPI_DOUBLE", ascii ? 1 : 8, count);
   fprintf(fp, "\t\"io_subfile\":\t{\n\t\t\"Number of files\":\t1,\n\t\t\"File index\":\t0,\n\t\t\"Topology\":\t[1, 1, 1],\n"
 	  "\t\t\"Coordinate\":\t[0, 0, 0],\n\t\t\"Data ndims\":\t3,\n\t\t\"File size (sites)\":\t[%d, %d, %d],\n"
 	  "\t\t\"File offset (sites)\":\t[0, 0, 0]\n\t}\n}", cs->nlocal[X], cs->nlocal[Y], cs->nlocal[Z]);
@@ -1144,6 +1159,62 @@ int field_read_buf(field_t * field, int index, const char * buf) {
   return 0;
 }
 
+/* src/lb_data.c:1579-1640: ndist values per line, one line per velocity */
+int lb_write_buf_ascii(const lb_t * lb, int index, char * buf) {
+  const int nbyte = LB_RECORD_LENGTH_ASCII;
+  int ifail = 0;
+  for (int p = 0; p < lb->nvel; p++) {
+    char tmp[64];
+    const int poffset = p*(lb->ndist*nbyte + 1);
+    for (int n = 0; n < lb->ndist; n++) {
+      int np = snprintf(tmp, sizeof(tmp), " %22.15e", lb->f[LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, n, p)]);
+      if (np != nbyte) ifail = 1;
+      memcpy(buf + poffset + n*nbyte, tmp, nbyte);
+    }
+    buf[poffset + lb->ndist*nbyte] = '\n';
+  }
+  return ifail;
+}
+
+int lb_read_buf_ascii(lb_t * lb, int index, const char * buf) {
+  const int nbyte = LB_RECORD_LENGTH_ASCII;
+  int ifail = 0;
+  for (int p = 0; p < lb->nvel; p++) {
+    const int poffset = p*(lb->ndist*nbyte + 1);
+    for (int n = 0; n < lb->ndist; n++) {
+      char tmp[64] = {0};
+      memcpy(tmp, buf + poffset + n*nbyte, nbyte);
+      if (sscanf(tmp, "%le", lb->f + LB_ADDR(lb->nsite, lb->ndist, lb->nvel, index, n, p)) != 1) ifail = 1;
+    }
+  }
+  return ifail;
+}
+
+/* src/field.c:931-1000: nf values and a newline per site */
+int field_write_buf_ascii(field_t * field, int index, char * buf) {
+  const int nbyte = 23;
+  int ifail = 0;
+  for (int n = 0; n < field->nf; n++) {
+    char tmp[64];
+    int np = snprintf(tmp, sizeof(tmp), " %22.15e", field->data[addr_rank1(field->nsites, field->nf, index, n)]);
+    if (np != nbyte) ifail = 1;
+    memcpy(buf + n*nbyte, tmp, nbyte);
+  }
+  buf[field->nf*nbyte] = '\n';
+  return ifail;
+}
+
+int field_read_buf_ascii(field_t * field, int index, const char * buf) {
+  const int nbyte = 23;
+  int ifail = 0;
+  for (int n = 0; n < field->nf; n++) {
+    char tmp[64] = {0};
+    memcpy(tmp, buf + n*nbyte, nbyte);
+    if (sscanf(tmp, "%le", field->data + addr_rank1(field->nsites, field->nf, index, n)) != 1) ifail = 1;
+  }
+  return ifail;
+}
+
 /* the aggregator: interior sites in (ic, jc, kc) order (cs_limits, src/lb_data.c:1646-1673, src/field.c:1590-1625) */
 static int io_file_transfer(cs_t * cs, const char * filename, size_t szelement, int write,
 			    void * obj, int (* wbuf)(void *, int, char *), int (* rbuf)(void *, int, const char *)) {
@@ -1181,6 +1252,10 @@ static int lb_wbuf_(void * o, int index, char * buf) { return lb_write_buf((cons
 static int lb_rbuf_(void * o, int index, const char * buf) { return lb_read_buf((lb_t *) o, index, buf); }
 static int field_wbuf_(void * o, int index, char * buf) { return field_write_buf((field_t *) o, index, buf); }
 static int field_rbuf_(void * o, int index, const char * buf) { return field_read_buf((field_t *) o, index, buf); }
+static int lb_wbufa_(void * o, int index, char * buf) { return lb_write_buf_ascii((const lb_t *) o, index, buf); }
+static int lb_rbufa_(void * o, int index, const char * buf) { return lb_read_buf_ascii((lb_t *) o, index, buf); }
+static int field_wbufa_(void * o, int index, char * buf) { return field_write_buf_ascii((field_t *) o, index, buf); }
+static int field_rbufa_(void * o, int index, const char * buf) { return field_read_buf_ascii((field_t *) o, index, buf); }
 
 /* src/lb_data.c:1716-1830.  The device copy is brought to the host first (and pushed back after a read) when the
  * lattice has one; a host-only lb_t (no device use yet) is written / read as it stands. */
@@ -1188,9 +1263,11 @@ int lb_io_write(lb_t * lb, int timestep, io_event_t * event) {
   char filename[BUFSIZ];
   (void) event;
   if (lb->cs->ctx) lb_memcpy(lb, tdpMemcpyDeviceToHost);
-  if (io_metadata_write_default(lb->cs, "dist", lb->ndist*lb->nvel) != 0) pe_fatal(lb->pe, "Could not write dist metadata\n");
+  const int ascii = (lb->opts.iodata.output.iorformat == IO_RECORD_ASCII);
+  const size_t szel = ascii ? (size_t) lb->nvel*(1 + LB_RECORD_LENGTH_ASCII*lb->ndist) : sizeof(double)*lb->ndist*lb->nvel;
+  if (io_metadata_write_default(lb->cs, "dist", ascii ? (int) szel : lb->ndist*lb->nvel, ascii) != 0) pe_fatal(lb->pe, "Could not write dist metadata\n");
   io_file_name("dist", timestep, filename, BUFSIZ);
-  if (io_file_transfer(lb->cs, filename, sizeof(double)*lb->ndist*lb->nvel, 1, lb, lb_wbuf_, lb_rbuf_) != 0) {
+  if (io_file_transfer(lb->cs, filename, szel, 1, lb, ascii ? lb_wbufa_ : lb_wbuf_, ascii ? lb_rbufa_ : lb_rbuf_) != 0) {
     pe_fatal(lb->pe, "Error: could not write distribution file: %s\n", filename);
   }
   return 0;
@@ -1199,8 +1276,10 @@ int lb_io_write(lb_t * lb, int timestep, io_event_t * event) {
 int lb_io_read(lb_t * lb, int timestep, io_event_t * event) {
   char filename[BUFSIZ];
   (void) event;
+  const int ascii = (lb->opts.iodata.input.iorformat == IO_RECORD_ASCII);
+  const size_t szel = ascii ? (size_t) lb->nvel*(1 + LB_RECORD_LENGTH_ASCII*lb->ndist) : sizeof(double)*lb->ndist*lb->nvel;
   io_file_name("dist", timestep, filename, BUFSIZ);
-  if (io_file_transfer(lb->cs, filename, sizeof(double)*lb->ndist*lb->nvel, 0, lb, lb_wbuf_, lb_rbuf_) != 0) {
+  if (io_file_transfer(lb->cs, filename, szel, 0, lb, ascii ? lb_wbufa_ : lb_wbuf_, ascii ? lb_rbufa_ : lb_rbuf_) != 0) {
     pe_fatal(lb->pe, "Error: could not read distribuiion file: %s\n", filename);
   }
   if (lb->cs->ctx) lb_memcpy(lb, tdpMemcpyHostToDevice);
@@ -1212,9 +1291,11 @@ int field_io_write(field_t * field, int timestep, io_event_t * event) {
   char filename[BUFSIZ];
   (void) event;
   if (field->cs->ctx && field->b200_array >= 0) field_memcpy(field, tdpMemcpyDeviceToHost);
-  if (io_metadata_write_default(field->cs, field->name, field->nf) != 0) pe_fatal(field->pe, "Could not write %s metadata\n", field->name);
+  const int ascii = (field->opts.iodata.output.iorformat == IO_RECORD_ASCII);
+  const size_t szel = ascii ? (size_t) (1 + 23*field->nf) : sizeof(double)*field->nf;
+  if (io_metadata_write_default(field->cs, field->name, ascii ? (int) szel : field->nf, ascii) != 0) pe_fatal(field->pe, "Could not write %s metadata\n", field->name);
   io_file_name(field->name, timestep, filename, BUFSIZ);
-  if (io_file_transfer(field->cs, filename, sizeof(double)*field->nf, 1, field, field_wbuf_, field_rbuf_) != 0) {
+  if (io_file_transfer(field->cs, filename, szel, 1, field, ascii ? field_wbufa_ : field_wbuf_, ascii ? field_rbufa_ : field_rbuf_) != 0) {
     pe_fatal(field->pe, "Error: could not write file: %s\n", filename);
   }
   return 0;
@@ -1223,8 +1304,10 @@ int field_io_write(field_t * field, int timestep, io_event_t * event) {
 int field_io_read(field_t * field, int timestep, io_event_t * event) {
   char filename[BUFSIZ];
   (void) event;
+  const int ascii = (field->opts.iodata.input.iorformat == IO_RECORD_ASCII);
+  const size_t szel = ascii ? (size_t) (1 + 23*field->nf) : sizeof(double)*field->nf;
   io_file_name(field->name, timestep, filename, BUFSIZ);
-  if (io_file_transfer(field->cs, filename, sizeof(double)*field->nf, 0, field, field_wbuf_, field_rbuf_) != 0) {
+  if (io_file_transfer(field->cs, filename, szel, 0, field, ascii ? field_wbufa_ : field_wbuf_, ascii ? field_rbufa_ : field_rbuf_) != 0) {
     pe_fatal(field->pe, "Error: could not read file: %s\n", filename);
   }
   if (field->cs->ctx && field->b200_array >= 0) field_memcpy(field, tdpMemcpyHostToDevice);

@@ -84,6 +84,7 @@ typedef struct ref_cfg_s {
   double lc_epsilon;   /* dielectric anisotropy as stored in fe_lc_param_t (includes the 1/12pi) */
   double lc_e0[3];     /* external electric field */
   int grad_7pt;        /* fd_gradient_calculation 3d_7pt_fluid for the scalar order parameter (default 3d_27pt_fluid) */
+  int io_ascii;        /* 1: default_io_format ascii (distributions and order-parameter field, input and output) */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -164,6 +165,7 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
   { lb_data_options_t opts = lb_data_options_ndim_nvel_ndist(NDIM, NVEL, cfg->ndist);
     opts.nrelax = (lb_relaxation_enum_t) cfg->nrelax;
     opts.halo = cfg->halo_reduced ? LB_HALO_REDUCED : LB_HALO_FULL;
+    if (cfg->io_ascii) opts.iodata.input.iorformat = opts.iodata.output.iorformat = IO_RECORD_ASCII;
     lb_data_create(s->pe, s->cs, &opts, &s->lb); }
   if (cfg->ghost_off) lb_collision_ghost_modes_off(s->lb);
 
@@ -179,6 +181,7 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     field_options_t opts = field_options_ndata_nhalo(1, cfg->nhalo);
     phi_ch_info_t ch = {0};
     fe_symm_param_t p = {0};
+    if (cfg->io_ascii) opts.iodata.input.iorformat = opts.iodata.output.iorformat = IO_RECORD_ASCII;
     field_create(s->pe, s->cs, s->le, "phi", &opts, &s->phi);
     field_grad_create(s->pe, s->phi, cfg->grad_level == 4 ? 4 : 2, &s->phi_grad);
     if (cfg->grad_7pt) field_grad_set(s->phi_grad, grad_3d_7pt_fluid_d2, grad_3d_7pt_fluid_d4);
@@ -204,6 +207,7 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     fe_lc_param_t p = {0};
     beris_edw_param_t bp = {0};
     int ncell[3] = {2, 2, 2};
+    if (cfg->io_ascii) opts.iodata.input.iorformat = opts.iodata.output.iorformat = IO_RECORD_ASCII;
     field_create(s->pe, s->cs, s->le, "q", &opts, &s->q);
     field_grad_create(s->pe, s->q, 2, &s->q_grad);
     field_grad_set(s->q_grad, grad_3d_7pt_fluid_d2, grad_3d_7pt_fluid_d4);

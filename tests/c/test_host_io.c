@@ -2,7 +2,7 @@
  * test_host_io.c -- on-disk formats through Ludwig's own host function names (include/ludwig_host.h).
  * CPU only (no device context is ever created).  Driven by tests/test_host_io.py:
  *
- *   test_host_io.exe write <nx> <ny> <nz> <nvel> <ndist> <nf> <fieldname> <le_planes>
+ *   test_host_io.exe write <nx> <ny> <nz> <nvel> <ndist> <nf> <fieldname> <le_planes> [ascii]
  *       fills lb->f and the field with the tag function below and writes dist-000000007.001-001,
  *       <fieldname>-000000007.001-001 and their metadata into the current directory;
  *   test_host_io.exe read  ... (same arguments)
@@ -36,8 +36,13 @@ int main(int argc, char ** argv) {
   cs_init(cs);
   cs_nlocal(cs, nlocal);
   { lees_edw_options_t o = {.nplanes = nplanes, .type = LE_SHEAR_TYPE_STEADY, .uy = 0.05}; lees_edw_create(pe, cs, &o, &le); }
-  { lb_data_options_t o = lb_data_options_ndim_nvel_ndist(3, nvel, ndist); lb_data_create(pe, cs, &o, &lb); }
-  { field_options_t o = field_options_ndata_nhalo(nf, 2); field_create(pe, cs, le, argv[8], &o, &fld); }
+  const int ascii = (argc > 10 && strcmp(argv[10], "ascii") == 0);
+  { lb_data_options_t o = lb_data_options_ndim_nvel_ndist(3, nvel, ndist);
+    if (ascii) o.iodata.input = o.iodata.output = io_options_with_format(IO_MODE_MPIIO, IO_RECORD_ASCII);
+    lb_data_create(pe, cs, &o, &lb); }
+  { field_options_t o = field_options_ndata_nhalo(nf, 2);
+    if (ascii) o.iodata.input = o.iodata.output = io_options_with_format(IO_MODE_MPIIO, IO_RECORD_ASCII);
+    field_create(pe, cs, le, argv[8], &o, &fld); }
 
   if (write) {
     for (int ic = 1; ic <= nlocal[X]; ic++)

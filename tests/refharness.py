@@ -26,7 +26,8 @@ class RefCfg(C.Structure):
                 ("grad_level", C.c_int), ("le_nplanes", C.c_int), ("le_uy", C.c_double),
                 ("have_q", C.c_int), ("lc_a0", C.c_double), ("lc_q0", C.c_double), ("lc_gamma", C.c_double),
                 ("lc_kappa0", C.c_double), ("lc_kappa1", C.c_double), ("lc_xi", C.c_double), ("lc_Gamma", C.c_double),
-                ("lc_epsilon", C.c_double), ("lc_e0", C.c_double * 3), ("grad_7pt", C.c_int)]
+                ("lc_epsilon", C.c_double), ("lc_e0", C.c_double * 3), ("grad_7pt", C.c_int),
+                ("io_ascii", C.c_int)]
 
 
 def _so(fast=False, nvel=19):
@@ -93,7 +94,7 @@ class RefSim:
     def __init__(self, ntotal, nhalo=1, periodic=(1, 1, 1), ndist=1, nrelax=0, ghost_off=0,
                  halo_reduced=0, have_phi=0, adv_order=1, conserve=0, rho0=1.0, eta_shear=1.0 / 6.0,
                  eta_bulk=None, fbody=(0, 0, 0), a=0.0, b=0.0, kappa=0.0, mobility=0.0,
-                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2, le_nplanes=0, le_uy=0.0, lc=None, grad_7pt=0):
+                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2, le_nplanes=0, le_uy=0.0, lc=None, grad_7pt=0, io_ascii=0):
         self.lib = _lib(fast, nvel)
         cfg = RefCfg()
         cfg.ntotal[:] = ntotal
@@ -108,6 +109,7 @@ class RefSim:
         cfg.gradmu[:] = gradmu
         cfg.grad_level = grad_level
         cfg.grad_7pt = grad_7pt
+        cfg.io_ascii = io_ascii
         cfg.le_nplanes, cfg.le_uy = le_nplanes, le_uy
         if lc is not None:
             # liquid crystal: dict(a0, q0, gamma, kappa0, kappa1, xi, Gamma[, epsilon, e0])

@@ -32,11 +32,14 @@ def tags(n, nhalo, ncomp, offset=0.0):
     return a.reshape(ncomp, -1)
 
 
+@pytest.mark.parametrize("fmt", ["binary_records", "ascii_records"])
 @pytest.mark.parametrize("case", ["binary", "symmlb", "lc", "le"])
-def test_files_match_reference(case, tmp_path):
+def test_files_match_reference(case, fmt, tmp_path):
+    """fmt ascii_records: options.iodata.{input,output}.iorformat = IO_RECORD_ASCII (the reference's default_io_format ascii)"""
     build_exe()
+    ascii_ = int(fmt == "ascii_records")
     n = (6, 4, 5) if case != "le" else (16, 4, 5)
-    kw = dict(nhalo=2, adv_order=1, eta_shear=0.1)
+    kw = dict(nhalo=2, adv_order=1, eta_shear=0.1, io_ascii=ascii_)
     nvel, ndist, nf, name, planes = 19, 1, 1, "phi", 0
     if case == "binary":
         kw.update(have_phi=1, a=-0.1, b=0.1, kappa=0.1, mobility=0.1)
@@ -63,7 +66,7 @@ def test_files_match_reference(case, tmp_path):
             assert s.io("lb_io_write", 7) == 0 and s.io("field_io_write", 7) == 0
     finally:
         os.chdir(cwd)
-    args = [str(x) for x in (*n, nvel, ndist, nf, name, planes)]
+    args = [str(x) for x in (*n, nvel, ndist, nf, name, planes)] + (["ascii"] if ascii_ else [])
     r = subprocess.run([EXE, "write"] + args, cwd=dours, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
     files = sorted(os.listdir(dref))
