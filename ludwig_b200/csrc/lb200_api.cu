@@ -367,7 +367,6 @@ static int conserve_prepare(lb200_t * c, const lb200_symm_param_t * sp) {
     return 0;
   }
   if (sp->conserve != 1) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve %d: 0, 1 (compensated sum) and 2 (global subtraction) are built", sp->conserve);
-  if (c->le.nplane > 0) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve 1 with Lees-Edwards planes is outside this build");
   if (c->csum == nullptr && alloc_d(&c->csum, (size_t) c->g.nsites) != 0) return LB200_ECUDA;
   return 0;
 }
@@ -2673,12 +2672,12 @@ int lb200_step_lc(lb200_t * c, const lb200_collide_param_t * cp, const lb200_lc_
 //   strict: the reference's operations everywhere (flux-form force on the whole lattice): bit-identical.
 //   fast  : the one-sweep phi-sector kernel for the bulk, then the planes whose stencils cross a Lees-Edwards
 //           plane (2*nhalo per plane) are redone by the generic plane kernels through the buffer planes.
-static int step_le(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev & sd, int nsteps) {
+static int step_le(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev & sd, int nsteps, bool conserve2) {
   cudaStream_t S = c->stream;
   const Lb200Geom & g = c->g;
   int rc = ensure_f_halo(c);
   if (rc != 0) return rc;
-  const bool fused = (c->opt.math == LB200_MATH_FAST) && c->knob_phi_sector && c->map_all_fluid && sd.order <= 3;
+  const bool fused = (c->opt.math == LB200_MATH_FAST) && c->knob_phi_sector && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr;
 
   for (int n = 0; n < nsteps; n++) {
     c->t_current += 1;                                                   // physics_control_next_step
@@ -2711,6 +2710,8 @@ static int step_le(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev &
       le_grad_async(c);
       le_force_ch_async(c, sd, g.nl[0], nullptr, 1, 1, 0, c->phinew);
     }
+    // cahn_hilliard_options_conserve 2: the same correction with or without planes (src/phi_cahn_hilliard.c:281-285)
+    if (conserve2 && (rc = phi_conserve_subtract_async(c, c->phinew, S)) != 0) return rc;
     c->force_state = INTERIOR_ONLY;
     { double * t = c->phi; c->phi = c->phinew; c->phinew = t; }
     c->u_state = ZERO_PENDING;                                           // hydro_u_zero
@@ -2753,7 +2754,6 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   // conserve 2: a global sum sits between the Cahn-Hilliard update and everything that reads the new phi -- the
   // reference-structured step (halo kernels), not the halo-free one whose kernels hand planes to the neighbours as they go
   const bool conserve2 = binary && c->ndist == 1 && sp->conserve == 2;
-  if (conserve2 && c->le.nplane > 0) return fail(LB200_EINVAL, "cahn_hilliard_options_conserve 2 with Lees-Edwards planes is outside this build");
   if (nsteps <= 0) return 0;
   if (binary && c->knob_grad7 && (c->ndist != 1 || c->le.nplane > 0))
     return fail(LB200_EINVAL, "fd_gradient_calculation 3d_7pt_fluid: built for the finite-difference binary fluid without planes");
@@ -2763,11 +2763,11 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     // patch (and its +-2 stencil) stays clear of the slab boundary planes that the neighbours exchange
     const Lb200Geom & g = c->g;
     bool ok = (c->opt.math == LB200_MATH_FAST) && c->knob_wrap && c->knob_phi_sector && c->map_all_fluid
-      && g.per[0] && g.per[1] && g.per[2] && sd.order <= 3;
+      && g.per[0] && g.per[1] && g.per[2] && sd.order <= 3 && sd.csum == nullptr && !conserve2;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
     for (int p = 0; p < c->le.nplane; p++) ok = ok && (c->le.loc[p] - g.nh - 1 >= 1) && (c->le.loc[p] + g.nh + 2 <= g.nl[0]);
     if (ok) return step_wrap(c, cd, &sd, nsteps);
-    return step_le(c, cd, sd, nsteps);
+    return step_le(c, cd, sd, nsteps, conserve2);
   }
   if (c->ndist == 2) {
     if (!binary) return fail(LB200_EINVAL, "ndist = 2 needs the free-energy parameters");

@@ -447,9 +447,25 @@ le_force_ch_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, con
     fzm -= M*sp.gm[2];
     if (status) fzm *= mkzm*mk;
 
-    double ph = ph_c;
-    ph -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
-    phinew[s] = ph;
+    if (sp.csum != nullptr) {
+      // cahn_hilliard_options_conserve 1: phi_ch_csum_kernel (src/phi_cahn_hilliard.c:1181-1215), as in force_ch_kernel
+      double sum = ph_c, cs = sp.csum[s];
+      const double val[6] = {-fe, fw, -fy, fym, -sp.wz*fz, sp.wz*fzm};
+#pragma unroll
+      for (int n = 0; n < 6; n++) {
+	const double y = val[n] + cs;
+	const double t = sum + y;
+	cs = y - (t - sum);
+	sum = t;
+      }
+      sp.csum[s] = cs;
+      phinew[s] = sum;
+    }
+    else {
+      double ph = ph_c;
+      ph -= (+ fe - fw + fy - fym + sp.wz*fz - sp.wz*fzm);
+      phinew[s] = ph;
+    }
   }
 }
 

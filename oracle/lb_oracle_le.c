@@ -586,8 +586,10 @@ void orc_le_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
   const double zero[3] = {0.0, 0.0, 0.0};
   double * fprime = (double *) calloc(nsf*m->nvel, sizeof(double));
   double * flux = (double *) calloc(ns*4, sizeof(double));
+  double * csum = NULL;     /* cahn_hilliard_options_conserve 1: pch->csum, zero when the phi_ch_t is created */
   assert(fprime && flux);
   memcpy(fprime, f, nsf*m->nvel*sizeof(double));
+  if (sp->conserve == 1) { csum = (double *) calloc(ns, sizeof(double)); assert(csum); }
 
   for (int n = 0; n < nsteps; n++) {
     const int tcurrent = tcurrent0 + n + 1;              /* physics_control_next_step */
@@ -607,7 +609,10 @@ void orc_le_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
     orc_flux_mu_ext(g, sp, flux);
     orc_no_flux(g, NULL, flux);
     orc_le_fix_fluxes(g, le, time, flux);
-    orc_phi_update(g, flux, phi);
+    /* src/phi_cahn_hilliard.c:276-285: the same choice of update with or without planes */
+    if (csum) orc_phi_update_conserve(g, flux, csum, phi);
+    else      orc_phi_update(g, flux, phi);
+    if (sp->conserve == 2) orc_phi_subtract_sum(g, sp->phi_init_sum, phi);
 
     orc_field_set(g, 3, u, zero);
     orc_collide(g, m, cp, NULL, 0, f, force, rho, u);
@@ -619,4 +624,5 @@ void orc_le_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
 
   free(fprime);
   free(flux);
+  free(csum);
 }

@@ -254,3 +254,41 @@ def test_le_one_kernel_step_equals_two_kernel_step(monkeypatch):
     for k in a:
         assert close_fast(orc.interior(a[k]), orc.interior(b[k])), k
         assert close_fast(orc.interior(a[k]), orc.interior(want[k])), k
+
+
+@pytest.mark.parametrize("math_mode", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+@pytest.mark.parametrize("conserve", [1, 2])
+def test_le_steps_with_conserve_options(conserve, math_mode):
+    """cahn_hilliard_options_conserve 1 (compensated per-site sum: bit-exact in strict mode) and 2 (global subtraction after
+    the forward step, to 1e-14: the device sum is compensated, the reference's a plain one) with Lees-Edwards planes; the
+    oracle for both is pinned to the compiled reference in tests/test_le_oracle.py::test_le_steps_conserve_vs_reference"""
+    n, nplanes, order, nsteps = (16, 12, 10), 2, 3, 8
+    orc = Oracle(n, nhalo=2, le_nplanes=nplanes, le_uy=UY)
+    f = np.zeros((19, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f)
+    phi = np.zeros((1, orc.nsites))
+    phi[:, :orc.nsites_lb] = spinodal_phi(n, 2, 13, 0.0, 0.1)
+    sum0 = orc.phi_sum_time0(phi) + 1.0e-3 if conserve == 2 else 0.0
+    with lb.Lb200(n, nhalo=2, have_phi=True, math=math_mode, le_nplanes=nplanes, le_uy=UY) as sim:
+        sim.put(lb.F, f); sim.put(lb.PHI, phi)
+        if conserve == 2:
+            sim.phi_init_sum_set(sum0)
+        sp_g = lb.SymmParam.make(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order, conserve=conserve)
+        sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), sp_g, nsteps // 2)
+        sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), sp_g, nsteps - nsteps // 2)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("force", lb.FORCE))}
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+    sp_o = orc.symm_param(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order, conserve=conserve, phi_init_sum=sum0)
+    orc.le_step(orc.collide_param(0, 1.0, ETA), sp_o, 0, nsteps, f, phi, u, rho, force, grad, delsq)
+    want = dict(f=f, phi=phi, u=u, force=force)
+    for k in want:
+        a, b = orc.interior(got[k]), orc.interior(want[k])
+        if math_mode == lb.MATH_STRICT and conserve == 1:
+            assert np.array_equal(a, b), k
+        elif math_mode == lb.MATH_STRICT:
+            assert np.abs(a - b).max() <= 1e-14*np.abs(b).max(), k
+        else:
+            assert close_fast(a, b), (k, np.abs(a - b).max())
+    if conserve == 2:
+        assert abs(orc.interior(got["phi"]).sum() - sum0) < 1e-11

@@ -14,8 +14,8 @@ ETA = 0.1
 UY = 0.05
 
 
-def make(n, nplanes, order, uy=UY):
-    ref = R.RefSim(n, nhalo=2, have_phi=1, adv_order=order, eta_shear=ETA, le_nplanes=nplanes, le_uy=uy, **FE)
+def make(n, nplanes, order, uy=UY, conserve=0):
+    ref = R.RefSim(n, nhalo=2, have_phi=1, adv_order=order, eta_shear=ETA, le_nplanes=nplanes, le_uy=uy, conserve=conserve, **FE)
     orc = Oracle(n, nhalo=2, le_nplanes=nplanes, le_uy=uy)
     assert ref.nsites == orc.nsites_lb and ref.nsites_le == orc.nsites
     return ref, orc
@@ -114,6 +114,38 @@ def test_le_steps_vs_reference(n, nplanes, order):
         for name, a, what in (("f", f, R.REF_F), ("phi", phi, R.REF_PHI), ("u", u, R.REF_U), ("rho", rho, R.REF_RHO),
                               ("force", force, R.REF_FORCE), ("grad", grad, R.REF_GRAD), ("delsq", delsq, R.REF_DELSQ)):
             assert np.array_equal(orc.interior(a), orc.interior(ref.get(what))), name
+
+
+@pytest.mark.parametrize("conserve", [1, 2])
+def test_le_steps_conserve_vs_reference(conserve):
+    """cahn_hilliard_options_conserve 1 (compensated per-site sum) and 2 (global subtraction; one OpenMP thread, the
+    reference's own summation order depends on the thread count) with Lees-Edwards planes: src/phi_cahn_hilliard.c:276-285"""
+    n, nplanes, order, nsteps = (16, 8, 10), 2, 3, 8
+    before = R.omp_threads(0)
+    R.omp_threads(1)
+    try:
+        ref, orc = make(n, nplanes, order, conserve=conserve)
+        with ref:
+            ref.init_spinodal(13, 0.0, 0.05)
+            ref.op("le_init_shear_profile")
+            f = ref.get(R.REF_F); phi = ref.get(R.REF_PHI)
+            sum0 = 0.0
+            if conserve == 2:
+                sum0 = ref.phi_stats_time0() + 1.0e-3        # offset: the correction is far above rounding
+                ref.phi_init_sum_set(sum0)
+            z = lambda k: np.zeros((k, orc.nsites))
+            u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+            ref.step(nsteps)
+            cp = orc.collide_param(0, 1.0, ETA)
+            sp = orc.symm_param(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order, conserve=conserve, phi_init_sum=sum0)
+            orc.le_step(cp, sp, 0, nsteps, f, phi, u, rho, force, grad, delsq)
+            for name, a, what in (("f", f, R.REF_F), ("phi", phi, R.REF_PHI), ("u", u, R.REF_U), ("force", force, R.REF_FORCE)):
+                assert np.array_equal(orc.interior(a), orc.interior(ref.get(what))), name
+            if conserve == 2:
+                assert abs(orc.interior(phi).sum() - sum0) < 1e-11
+    finally:
+        if before > 0:
+            R.omp_threads(before)
 
 
 # ---- printed statistics of the reference's own regression logs after 10 steps ---------------------------------
