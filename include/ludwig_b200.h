@@ -123,7 +123,7 @@ typedef struct lb200_symm_param_s {
 } lb200_symm_param_t;
 
 /* fe_lc_param_t + beris_edw_param_t as the liquid-crystal kernels see them (src/blue_phase.h:52-75,
- * src/blue_phase_beris_edwards.h:30-37); redshift 1, no activity, no noise */
+ * src/blue_phase_beris_edwards.h:30-37); redshift 1, no noise */
 typedef struct lb200_lc_param_s {
   double a0, q0, gamma;     /* lc_a0, lc_q0, lc_gamma */
   double kappa0, kappa1;    /* lc_kappa0, lc_kappa1 (as the reference, its vectorised molecular field and free-energy
@@ -133,6 +133,10 @@ typedef struct lb200_lc_param_s {
   double epsilon;           /* lc_dielectric_anisotropy / (12 pi), as stored by fe_lc_param_set (src/blue_phase.c:249-252) */
   double e0[3];             /* electric_e0 */
   int adv_order;            /* fd_advection_scheme_order 1-4 (src/advection.c:453-468; order 5 needs a 3-deep halo: not built) */
+  int is_active;            /* lc_activity: the active stress zeta0 d_ab - zeta1 Q_ab is added to the stress
+                             * (fe_lc_compute_stress_active, src/blue_phase.c:934-972; fe_lc_stress_v :1825-1845) */
+  double zeta0, zeta1;      /* lc_active_zeta0, lc_active_zeta1 */
+  double zeta2;             /* lc_active_zeta2: the polarisation-gradient term; must be 0 (LB200_EINVAL otherwise) */
 } lb200_lc_param_t;
 
 const char * lb200_last_error(void);

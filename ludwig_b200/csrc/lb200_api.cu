@@ -2367,6 +2367,8 @@ static int lc_dev(lb200_t * c, const lb200_lc_param_t * lc, Lb200LcDev * d) {
   d->Gamma = lc->Gamma; d->epsilon = lc->epsilon;
   for (int a = 0; a < 3; a++) d->e0[a] = lc->e0[a];
   d->order = lc->adv_order;
+  if (lc->is_active && lc->zeta2 != 0.0) return fail(LB200_EINVAL, "lc_active_zeta2 != 0 (polarisation-gradient active stress, fe_lc_active_stress) is outside this build");
+  d->is_active = (lc->is_active != 0); d->zeta0 = lc->zeta0; d->zeta1 = lc->zeta1;
   return 0;
 }
 

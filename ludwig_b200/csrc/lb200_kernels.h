@@ -64,6 +64,8 @@ struct Lb200LcDev {
   double epsilon;       // dielectric anisotropy, already divided by 12 pi
   double e0[3];
   int order;            // advection order 1..3
+  int is_active;        // active stress zeta0 d_ab - zeta1 Q_ab (lc_activity)
+  double zeta0, zeta1;
 };
 
 struct Lb200CollideDev {

@@ -415,6 +415,17 @@ lc_stress_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, int ne
   lc_h_fast(p, q, dq, dsq, h, sh);
   lc_stress_fast(p, q, dq, h, sh, s);
 #endif
+  if (p.is_active) {
+    // fe_lc_compute_stress_active (src/blue_phase.c:934-972) with zeta2 = 0, added as fe_lc_stress_v does (:1825-1845)
+#pragma unroll
+    for (int ia = 0; ia < 3; ia++)
+#pragma unroll
+      for (int ib = 0; ib < 3; ib++) {
+	double sa = p.zeta0*LC_D[ia][ib] - p.zeta1*q[ia][ib];
+	sa = -sa;
+	s[ia][ib] += sa;
+      }
+  }
   const int idx = le_index(g, ic, jc, kc);
 #pragma unroll
   for (int ia = 0; ia < 3; ia++)

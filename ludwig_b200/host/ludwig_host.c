@@ -1067,6 +1067,7 @@ static void lc_param_from(fe_t * fe, const beris_edw_t * be, lb200_lc_param_t * 
   for (int a = 0; a < 3; a++) lc->e0[a] = p->e0[a]*p->coswt;
   lc->Gamma = be ? be->param.gamma : 0.0;
   lc->adv_order = advection_order_;
+  lc->is_active = p->is_active; lc->zeta0 = p->zeta0; lc->zeta1 = p->zeta1; lc->zeta2 = p->zeta2;
 }
 
 /* src/blue_phase_beris_edwards.c:266-296 */

@@ -250,6 +250,19 @@ void orc_lc_stress(const orc_geom_t * g, const orc_lc_param_t * p, const double 
 	lc_expand(q_, grad, delsq, ns, index, q, dq, dsq);
 	orc_lc_compute_h(p, q, dq, dsq, h);
 	orc_lc_compute_stress(p, q, dq, h, s);
+	if (p->is_active) {
+	  /* fe_lc_stress_v, src/blue_phase.c:1825-1845, with fe_lc_compute_stress_active, :934-972 (the documented form);
+	   * dp = grad of the polarisation field, identically zero here (zeta2 term of fe_lc_active_stress not built) */
+	  const double dp[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+	  double sa[3][3];
+	  for (int ia = 0; ia < 3; ia++)
+	    for (int ib = 0; ib < 3; ib++)
+	      sa[ia][ib] = p->zeta0*(ia == ib) - p->zeta1*q[ia][ib] - p->zeta2*(dp[ia][ib] + dp[ib][ia]);
+	  for (int ia = 0; ia < 3; ia++)
+	    for (int ib = 0; ib < 3; ib++) sa[ia][ib] = -sa[ia][ib];
+	  for (int ia = 0; ia < 3; ia++)
+	    for (int ib = 0; ib < 3; ib++) s[ia][ib] += sa[ia][ib];
+	}
 	for (int ia = 0; ia < 3; ia++)
 	  for (int ib = 0; ib < 3; ib++) str[(size_t) (ia*3 + ib)*ns + index] = s[ia][ib];
       }

@@ -85,6 +85,8 @@ typedef struct ref_cfg_s {
   double lc_e0[3];     /* external electric field */
   int grad_7pt;        /* fd_gradient_calculation 3d_7pt_fluid for the scalar order parameter (default 3d_27pt_fluid) */
   int io_ascii;        /* 1: default_io_format ascii (distributions and order-parameter field, input and output) */
+  int lc_active;       /* lc_activity yes */
+  double lc_zeta0, lc_zeta1;   /* lc_active_zeta0, lc_active_zeta1 (zeta2 = 0) */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -216,6 +218,8 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     p.kappa0 = cfg->lc_kappa0; p.kappa1 = cfg->lc_kappa1; p.xi = cfg->lc_xi;
     p.redshift = 1.0; p.rredshift = 1.0;
     p.epsilon = cfg->lc_epsilon;
+    /* /root/reference/src/blue_phase_rt.c:157-170 */
+    p.is_active = cfg->lc_active; p.zeta0 = cfg->lc_zeta0; p.zeta1 = cfg->lc_zeta1; p.zeta2 = 0.0;
     p.e0[0] = cfg->lc_e0[0]; p.e0[1] = cfg->lc_e0[1]; p.e0[2] = cfg->lc_e0[2];
     p.coswt = 1.0;
     fe_lc_param_set(s->fe_lc, &p);

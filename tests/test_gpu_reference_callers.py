@@ -66,6 +66,9 @@ CASES = {
                     "lc_anchoring_strength_colloid": "0.002593824", "colloid_init": "no_colloids", "periodicity": "1_1_1",
                     "freq_statistics": "10", "config_at_end": "no", "random_seed": "8361235"},
 }
+# active liquid crystal: lc_activity yes with the constants of tests/regression/d3q19-short/serial-actv-s01.inp
+CASES["active_cholesteric"] = dict(CASES["cholesteric"], lc_activity="yes", lc_active_zeta0="0.33333333333333333",
+                                   lc_active_zeta1="0.005", size="32_32_32")
 
 # lines tests/test-diff.sh deletes before comparing
 DROP = re.compile(r"call\)|calls\)|Welcome|Git commit:|Compiler:|\.\.name:|\.\.version-string:|\.\.options:|Target thread model:|"

@@ -14,6 +14,8 @@ pytestmark = pytest.mark.skipif(not R.available(), reason="reference library ora
 CHOL = dict(a0=0.01, q0=0.19635, gamma=3.0, kappa0=0.000648456, kappa1=0.000648456, xi=0.7, Gamma=0.5)
 FLD = dict(a0=0.084334998544, q0=0.05, gamma=3.085714285714, kappa0=0.01, kappa1=0.013, xi=0.7, Gamma=0.3,
            epsilon=41.4, e0=(0.01, 0.0, 0.003))
+# lc_activity yes (active nematic / cholesteric: the constants of tests/regression/d3q19-short/serial-actv-s01.inp)
+ACT = dict(CHOL, zeta0=1.0 / 3.0, zeta1=0.005)
 ETA = 0.1
 
 
@@ -26,7 +28,7 @@ def make(n, lc, order):
 
 
 @pytest.mark.parametrize("n", [(8, 6, 10), (12, 12, 12)])
-@pytest.mark.parametrize("lc", [CHOL, FLD], ids=["chol", "field"])
+@pytest.mark.parametrize("lc", [CHOL, FLD, ACT], ids=["chol", "field", "active"])
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_lc_operators_vs_reference(n, lc, order):
     ref, orc, p = make(n, lc, order)
@@ -79,7 +81,8 @@ def test_lc_operators_vs_reference(n, lc, order):
         assert np.array_equal(orc.interior(q), orc.interior(ref.get(R.REF_Q)))
 
 
-@pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 16), FLD, 1), ((10, 12, 6), FLD, 2), ((8, 10, 12), CHOL, 4)])
+@pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 16), FLD, 1), ((10, 12, 6), FLD, 2), ((8, 10, 12), CHOL, 4),
+                                        ((10, 8, 12), ACT, 3)])
 def test_lc_steps_vs_reference(n, lc, order):
     ref, orc, p = make(n, lc, order)
     with ref:
