@@ -123,7 +123,7 @@ typedef struct lb200_symm_param_s {
 } lb200_symm_param_t;
 
 /* fe_lc_param_t + beris_edw_param_t as the liquid-crystal kernels see them (src/blue_phase.h:52-75,
- * src/blue_phase_beris_edwards.h:30-37); redshift 1, no noise */
+ * src/blue_phase_beris_edwards.h:30-37); static redshift, no noise */
 typedef struct lb200_lc_param_s {
   double a0, q0, gamma;     /* lc_a0, lc_q0, lc_gamma */
   double kappa0, kappa1;    /* lc_kappa0, lc_kappa1 (as the reference, its vectorised molecular field and free-energy
@@ -137,6 +137,9 @@ typedef struct lb200_lc_param_s {
                              * (fe_lc_compute_stress_active, src/blue_phase.c:934-972; fe_lc_stress_v :1825-1845) */
   double zeta0, zeta1;      /* lc_active_zeta0, lc_active_zeta1 */
   double zeta2;             /* lc_active_zeta2: the polarisation-gradient term; must be 0 (LB200_EINVAL otherwise) */
+  double redshift;          /* lc_init_redshift (fe_lc_param_t.redshift; 0 is read as 1): q0 / redshift, kappa redshift^2 in the
+                             * molecular field, free-energy density and stress (src/blue_phase.c:2117-2120, 1933-1934, 2300-2302).
+                             * Static: lc_redshift_update (fe_lc_redshift_compute) is not built */
 } lb200_lc_param_t;
 
 const char * lb200_last_error(void);

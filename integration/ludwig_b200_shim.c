@@ -360,13 +360,14 @@ static void b200_lc_param(pe_t * pe, fe_t * fe, lb200_lc_param_t * lc) {
   const fe_lc_param_t * p = ((fe_lc_t *) fe)->param;
   memset(lc, 0, sizeof(*lc));
   if (p->is_active && p->zeta2 != 0.0) pe_fatal(pe, "libludwig_b200: lc_active_zeta2 != 0 is outside this library\n");
-  if (p->is_redshift_updated || p->redshift != 1.0) pe_fatal(pe, "libludwig_b200: redshift != 1 is outside this library\n");
+  if (p->is_redshift_updated) pe_fatal(pe, "libludwig_b200: lc_redshift_update is outside this library\n");
   lc->a0 = p->a0; lc->q0 = p->q0; lc->gamma = p->gamma; lc->kappa0 = p->kappa0; lc->kappa1 = p->kappa1; lc->xi = p->xi;
   lc->epsilon = p->epsilon;
   for (int a = 0; a < 3; a++) lc->e0[a] = p->e0[a]*p->coswt;
   lc->Gamma = be_param_known_ ? be_param_.gamma : 0.0;
   advection_order(&lc->adv_order);
   lc->is_active = p->is_active; lc->zeta0 = p->zeta0; lc->zeta1 = p->zeta1; lc->zeta2 = p->zeta2;
+  lc->redshift = p->redshift;
 }
 
 int __real_beris_edw_update(beris_edw_t * be, fe_t * fe, field_t * fq, field_grad_t * fq_grad, hydro_t * hydro,

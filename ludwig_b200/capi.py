@@ -55,17 +55,18 @@ class LcParam(C.Structure):
     _fields_ = [("a0", C.c_double), ("q0", C.c_double), ("gamma", C.c_double), ("kappa0", C.c_double),
                 ("kappa1", C.c_double), ("xi", C.c_double), ("Gamma", C.c_double), ("epsilon", C.c_double),
                 ("e0", C.c_double * 3), ("adv_order", C.c_int), ("is_active", C.c_int), ("zeta0", C.c_double),
-                ("zeta1", C.c_double), ("zeta2", C.c_double)]
+                ("zeta1", C.c_double), ("zeta2", C.c_double), ("redshift", C.c_double)]
 
     @classmethod
     def make(cls, a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon=0.0, e0=(0.0, 0.0, 0.0), adv_order=1,
-             zeta0=None, zeta1=0.0, zeta2=0.0):
+             zeta0=None, zeta1=0.0, zeta2=0.0, redshift=1.0):
         p = cls()
         p.a0, p.q0, p.gamma, p.kappa0, p.kappa1, p.xi, p.Gamma, p.epsilon = a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon
         p.e0[:] = e0
         p.adv_order = adv_order
         p.is_active = int(zeta0 is not None)      # lc_activity yes: zeta0 / zeta1 / zeta2 are read
         p.zeta0, p.zeta1, p.zeta2 = (zeta0 or 0.0), zeta1, zeta2
+        p.redshift = redshift
         return p
 
 

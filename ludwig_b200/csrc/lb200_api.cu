@@ -2369,6 +2369,9 @@ static int lc_dev(lb200_t * c, const lb200_lc_param_t * lc, Lb200LcDev * d) {
   d->order = lc->adv_order;
   if (lc->is_active && lc->zeta2 != 0.0) return fail(LB200_EINVAL, "lc_active_zeta2 != 0 (polarisation-gradient active stress, fe_lc_active_stress) is outside this build");
   d->is_active = (lc->is_active != 0); d->zeta0 = lc->zeta0; d->zeta1 = lc->zeta1;
+  d->redshift = (lc->redshift != 0.0) ? lc->redshift : 1.0;
+  if (fabs(d->redshift) < 1.0e-5) return fail(LB200_EINVAL, "redshift %g below FE_REDSHIFT_MIN (src/blue_phase.c:29-32)", d->redshift);
+  d->rredshift = 1.0/d->redshift;
   return 0;
 }
 

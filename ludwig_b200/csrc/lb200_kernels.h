@@ -66,6 +66,7 @@ struct Lb200LcDev {
   int order;            // advection order 1..3
   int is_active;        // active stress zeta0 d_ab - zeta1 Q_ab (lc_activity)
   double zeta0, zeta1;
+  double redshift, rredshift;   // static redshift and its reciprocal (1.0/redshift, formed on the host as fe_lc_redshift_set does)
 };
 
 struct Lb200CollideDev {

@@ -71,8 +71,8 @@ __device__ __forceinline__ void lc_load_star(const Lb200Geom & g, const double *
 __device__ __forceinline__ void lc_compute_h(const Lb200LcDev & p, const double q[3][3], const double dq[3][3][3],
 					     const double dsq[3][3], double h[3][3]) {
   const double r3 = (1.0/3.0);
-  const double q0 = 1.0*p.q0;
-  const double kappa0 = 1.0*1.0*p.kappa0;
+  const double q0 = p.rredshift*p.q0;
+  const double kappa0 = p.redshift*p.redshift*p.kappa0;
   const double kappa1 = kappa0;
   const double gamma = p.gamma;
   double q2 = 0.0, edq = 0.0, e2 = 0.0;
@@ -143,8 +143,8 @@ __device__ __forceinline__ void lc_compute_h(const Lb200LcDev & p, const double 
 // fe_lc_compute_fed_v, src/blue_phase.c:1908-2075
 __device__ __forceinline__ double lc_compute_fed(const Lb200LcDev & p, const double q[3][3], const double dq[3][3][3]) {
   const double r3 = 1.0/3.0;
-  const double q0 = 1.0*p.q0;
-  const double kappa0 = 1.0*1.0*p.kappa0;
+  const double q0 = p.rredshift*p.q0;
+  const double kappa0 = p.redshift*p.redshift*p.kappa0;
   const double kappa1 = kappa0;
   double q2 = 0.0, q3 = 0.0, dq0 = 0.0, dq1 = 0.0, efield = 0.0;
 
@@ -200,9 +200,9 @@ __device__ __forceinline__ double lc_compute_fed(const Lb200LcDev & p, const dou
 __device__ __forceinline__ void lc_compute_stress(const Lb200LcDev & p, const double q[3][3], const double dq[3][3][3],
 						  const double h[3][3], double s[3][3]) {
   const double r3 = (1.0/3.0);
-  const double q0 = p.q0*1.0;
-  const double kappa0 = p.kappa0*1.0*1.0;
-  const double kappa1 = p.kappa1*1.0*1.0;
+  const double q0 = p.q0*p.rredshift;
+  const double kappa0 = p.kappa0*p.redshift*p.redshift;
+  const double kappa1 = p.kappa1*p.redshift*p.redshift;
   const double xi = p.xi;
   double qh = 0.0;
   double p0 = lc_compute_fed(p, q, dq);
@@ -266,7 +266,7 @@ struct LcShared {
 __device__ __forceinline__ void lc_h_fast(const Lb200LcDev & p, const double q[3][3], const double dq[3][3][3],
 					  const double dsq[3][3], double h[3][3], LcShared & sh) {
   const double r3 = (1.0/3.0);
-  const double q0 = p.q0, k0 = p.kappa0;
+  const double q0 = p.q0*p.rredshift, k0 = p.kappa0*p.redshift*p.redshift;
   double q2 = 0.0;
 #pragma unroll
   for (int a = 0; a < 3; a++)
@@ -309,7 +309,7 @@ __device__ __forceinline__ void lc_h_fast(const Lb200LcDev & p, const double q[3
 __device__ __forceinline__ void lc_stress_fast(const Lb200LcDev & p, const double q[3][3], const double dq[3][3][3],
 						const double h[3][3], const LcShared & sh, double s[3][3]) {
   const double r3 = (1.0/3.0);
-  const double q0 = p.q0, k0 = p.kappa0, k1 = p.kappa1, xi = p.xi;
+  const double q0 = p.q0*p.rredshift, k0 = p.kappa0*p.redshift*p.redshift, k1 = p.kappa1*p.redshift*p.redshift, xi = p.xi;
   // free-energy density (kappa1 = kappa0 there, as in the reference's vectorised form)
   double q3 = 0.0, dq0 = 0.0, dq1 = 0.0, efield = 0.0, qh = 0.0;
 #pragma unroll

@@ -1016,9 +1016,10 @@ int fe_lc_param_set(fe_lc_t * fe, const fe_lc_param_t * values) {
   const double pi = 3.1415926535897932385;           /* PI_DOUBLE, src/util.h */
   *fe->param = *values;
   fe->param->epsilon *= (1.0/(12.0*pi));
-  if (fe->param->redshift != 1.0 || fe->param->is_redshift_updated) pe_fatal(fe->pe, "liquid crystal: redshift != 1 is outside this build\n");
-  if (fe->param->is_active) pe_fatal(fe->pe, "liquid crystal: active stress is outside this build\n");
-  fe->param->rredshift = 1.0;
+  if (fe->param->is_redshift_updated) pe_fatal(fe->pe, "liquid crystal: lc_redshift_update is outside this build\n");
+  if (fe->param->is_active && fe->param->zeta2 != 0.0) pe_fatal(fe->pe, "liquid crystal: lc_active_zeta2 != 0 is outside this build\n");
+  if (fe->param->redshift == 0.0) fe->param->redshift = 1.0;
+  fe->param->rredshift = 1.0/fe->param->redshift;            /* fe_lc_redshift_set, src/blue_phase.c:1357-1366 */
   if (fe->param->coswt == 0.0) fe->param->coswt = 1.0;
   return 0;
 }
@@ -1068,6 +1069,7 @@ static void lc_param_from(fe_t * fe, const beris_edw_t * be, lb200_lc_param_t * 
   lc->Gamma = be ? be->param.gamma : 0.0;
   lc->adv_order = advection_order_;
   lc->is_active = p->is_active; lc->zeta0 = p->zeta0; lc->zeta1 = p->zeta1; lc->zeta2 = p->zeta2;
+  lc->redshift = p->redshift;
 }
 
 /* src/blue_phase_beris_edwards.c:266-296 */

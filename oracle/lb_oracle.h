@@ -165,7 +165,7 @@ void orc_le_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
 
 /* ---- liquid crystal: Landau-de Gennes Q tensor + Beris-Edwards, oracle/lb_oracle_lc.c ----
  * q[n*ns + i], n = XX, XY, XZ, YY, YZ; qgrad[(n*3 + a)*ns + i]; qdelsq[n*ns + i]; str[(a*3 + b)*ns + i];
- * flux[(face*5 + n)*ns + i], face = w, e, y, z.  Redshift 1, no noise / colloids; activity: zeta0, zeta1 (zeta2 = 0). */
+ * flux[(face*5 + n)*ns + i], face = w, e, y, z.  Static redshift, no noise / colloids; activity: zeta0, zeta1 (zeta2 = 0). */
 typedef struct orc_lc_param_s {
   double a0, q0, gamma, kappa0, kappa1, xi;   /* fe_lc_param_t, src/blue_phase.h:52-75 */
   double Gamma;                               /* beris_edw_param_t.gamma: rotational diffusion constant */
@@ -173,6 +173,7 @@ typedef struct orc_lc_param_s {
   double e0[3];                               /* external electric field */
   int is_active;                              /* lc_activity */
   double zeta0, zeta1, zeta2;                 /* lc_active_zeta0/1/2 (zeta2: the dp field is zero unless fe_lc_active_stress ran) */
+  double redshift, rredshift;                 /* lc_init_redshift and its reciprocal (fe_lc_redshift_set, src/blue_phase.c:1357-1366); static */
 } orc_lc_param_t;
 
 void orc_grad_7pt(const orc_geom_t * g, int nf, const double * field, double * grad, double * delsq);

@@ -87,8 +87,8 @@ static void lc_expand(const double * q_, const double * grad, const double * del
 void orc_lc_compute_h(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3], double dsq[3][3],
 		      double h[3][3]) {
   const double r3 = (1.0/3.0);
-  const double q0 = 1.0*p->q0;
-  const double kappa0 = 1.0*1.0*p->kappa0;
+  const double q0 = p->rredshift*p->q0;
+  const double kappa0 = p->redshift*p->redshift*p->kappa0;
   const double kappa1 = kappa0;
   const double gamma = p->gamma;
   double q2 = 0.0, edq = 0.0, e2 = 0.0, sum;
@@ -145,8 +145,8 @@ void orc_lc_compute_h(const orc_lc_param_t * p, double q[3][3], double dq[3][3][
 
 double orc_lc_compute_fed(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3]) {
   const double r3 = 1.0/3.0;
-  const double q0 = 1.0*p->q0;
-  const double kappa0 = 1.0*1.0*p->kappa0;
+  const double q0 = p->rredshift*p->q0;
+  const double kappa0 = p->redshift*p->redshift*p->kappa0;
   const double kappa1 = kappa0;
   double q2 = 0.0, q3 = 0.0, dq0 = 0.0, dq1 = 0.0, efield = 0.0, sum;
 
@@ -196,9 +196,9 @@ double orc_lc_compute_fed(const orc_lc_param_t * p, double q[3][3], double dq[3]
 void orc_lc_compute_stress(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3], double h[3][3],
 			   double s[3][3]) {
   const double r3 = (1.0/3.0);
-  const double q0 = p->q0*1.0;
-  const double kappa0 = p->kappa0*1.0*1.0;
-  const double kappa1 = p->kappa1*1.0*1.0;
+  const double q0 = p->q0*p->rredshift;
+  const double kappa0 = p->kappa0*p->redshift*p->redshift;
+  const double kappa1 = p->kappa1*p->redshift*p->redshift;
   const double xi = p->xi;
   double qh = 0.0;
   double p0 = orc_lc_compute_fed(p, q, dq);

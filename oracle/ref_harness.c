@@ -87,6 +87,7 @@ typedef struct ref_cfg_s {
   int io_ascii;        /* 1: default_io_format ascii (distributions and order-parameter field, input and output) */
   int lc_active;       /* lc_activity yes */
   double lc_zeta0, lc_zeta1;   /* lc_active_zeta0, lc_active_zeta1 (zeta2 = 0) */
+  double lc_redshift;  /* lc_init_redshift (0: 1.0); no dynamic update */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -216,7 +217,7 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     fe_lc_create(s->pe, s->cs, s->le, s->q, s->q_grad, &s->fe_lc);
     p.a0 = cfg->lc_a0; p.q0 = cfg->lc_q0; p.gamma = cfg->lc_gamma;
     p.kappa0 = cfg->lc_kappa0; p.kappa1 = cfg->lc_kappa1; p.xi = cfg->lc_xi;
-    p.redshift = 1.0; p.rredshift = 1.0;
+    p.redshift = (cfg->lc_redshift != 0.0) ? cfg->lc_redshift : 1.0; p.rredshift = 1.0/p.redshift;
     p.epsilon = cfg->lc_epsilon;
     /* /root/reference/src/blue_phase_rt.c:157-170 */
     p.is_active = cfg->lc_active; p.zeta0 = cfg->lc_zeta0; p.zeta1 = cfg->lc_zeta1; p.zeta2 = 0.0;

@@ -18,6 +18,7 @@ CHOL = dict(a0=0.01, q0=0.19635, gamma=3.0, kappa0=0.000648456, kappa1=0.0006484
 FLD = dict(a0=0.084334998544, q0=0.05, gamma=3.085714285714, kappa0=0.01, kappa1=0.013, xi=0.7, Gamma=0.3,
            epsilon=41.4 * (1.0 / (12.0 * np.pi)), e0=(0.01, 0.0, 0.003))
 ACT = dict(CHOL, zeta0=1.0 / 3.0, zeta1=0.005)       # lc_activity yes (serial-actv-s01.inp's constants)
+RSH = dict(FLD, redshift=0.93)                       # lc_init_redshift != 1 (static)
 ETA = 0.1
 
 
@@ -33,7 +34,7 @@ def state(orc, lc, seed=17, axis=2):
 
 
 @pytest.mark.parametrize("n", [(8, 6, 10), (12, 12, 40)])
-@pytest.mark.parametrize("lc", [CHOL, FLD, ACT], ids=["chol", "field", "active"])
+@pytest.mark.parametrize("lc", [CHOL, FLD, ACT, RSH], ids=["chol", "field", "active", "redshift"])
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_lc_operators_strict_bit_exact(n, lc, order):
     orc = Oracle(n, nhalo=2)
@@ -92,7 +93,7 @@ def _run(n, lc, order, math, nsteps, path):
 
 @pytest.mark.parametrize("path", ["wrap", "halo", "api", "mixed"])
 @pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 40), FLD, 1), ((10, 12, 6), FLD, 2), ((8, 10, 12), CHOL, 4),
-                                        ((10, 8, 12), ACT, 3)])
+                                        ((10, 8, 12), ACT, 3), ((8, 12, 10), RSH, 3)])
 def test_lc_steps_strict_bit_exact(n, lc, order, path):
     orc, got, want = _run(n, lc, order, lb.MATH_STRICT, 10, path)
     for k in want:
@@ -102,7 +103,7 @@ def test_lc_steps_strict_bit_exact(n, lc, order, path):
 
 @pytest.mark.parametrize("path", ["wrap", "halo"])
 @pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 40), FLD, 1), ((32, 32, 32), CHOL, 2), ((8, 10, 12), CHOL, 4),
-                                        ((16, 16, 16), ACT, 3)])
+                                        ((16, 16, 16), ACT, 3), ((16, 8, 16), RSH, 3)])
 def test_lc_steps_fast_tolerance(n, lc, order, path):
     orc, got, want = _run(n, lc, order, lb.MATH_FAST, 20, path)
     for k in want:

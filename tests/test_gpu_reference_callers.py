@@ -69,6 +69,8 @@ CASES = {
 # active liquid crystal: lc_activity yes with the constants of tests/regression/d3q19-short/serial-actv-s01.inp
 CASES["active_cholesteric"] = dict(CASES["cholesteric"], lc_activity="yes", lc_active_zeta0="0.33333333333333333",
                                    lc_active_zeta1="0.005", size="32_32_32")
+# static redshift (lc_init_redshift != 1, no dynamic update)
+CASES["cholesteric_redshift"] = dict(CASES["cholesteric"], lc_init_redshift="0.95", size="32_32_32")
 
 # lines tests/test-diff.sh deletes before comparing
 DROP = re.compile(r"call\)|calls\)|Welcome|Git commit:|Compiler:|\.\.name:|\.\.version-string:|\.\.options:|Target thread model:|"

@@ -16,6 +16,7 @@ FLD = dict(a0=0.084334998544, q0=0.05, gamma=3.085714285714, kappa0=0.01, kappa1
            epsilon=41.4, e0=(0.01, 0.0, 0.003))
 # lc_activity yes (active nematic / cholesteric: the constants of tests/regression/d3q19-short/serial-actv-s01.inp)
 ACT = dict(CHOL, zeta0=1.0 / 3.0, zeta1=0.005)
+RSH = dict(FLD, redshift=0.93)                                # lc_init_redshift != 1 (static), two elastic constants
 ETA = 0.1
 
 
@@ -28,7 +29,7 @@ def make(n, lc, order):
 
 
 @pytest.mark.parametrize("n", [(8, 6, 10), (12, 12, 12)])
-@pytest.mark.parametrize("lc", [CHOL, FLD, ACT], ids=["chol", "field", "active"])
+@pytest.mark.parametrize("lc", [CHOL, FLD, ACT, RSH], ids=["chol", "field", "active", "redshift"])
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_lc_operators_vs_reference(n, lc, order):
     ref, orc, p = make(n, lc, order)
@@ -82,7 +83,7 @@ def test_lc_operators_vs_reference(n, lc, order):
 
 
 @pytest.mark.parametrize("n,lc,order", [((12, 10, 8), CHOL, 3), ((8, 8, 16), FLD, 1), ((10, 12, 6), FLD, 2), ((8, 10, 12), CHOL, 4),
-                                        ((10, 8, 12), ACT, 3)])
+                                        ((10, 8, 12), ACT, 3), ((8, 12, 10), RSH, 3)])
 def test_lc_steps_vs_reference(n, lc, order):
     ref, orc, p = make(n, lc, order)
     with ref:
