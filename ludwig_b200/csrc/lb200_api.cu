@@ -1546,18 +1546,22 @@ int lb200_lb_collision_binary(lb200_t * c, const lb200_collide_param_t * cp, con
 static int step_lb2(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev & sd, int nsteps) {
   int rc = 0;
   for (int n = 0; n < nsteps; n++) {
+    c->t_current += 1;                                                   // physics_control_next_step
     c->force_state = ZERO_PENDING;
     rc = phi_lb_to_field_async(c);
     if (rc != 0) return rc;
     rc = halo_field(c, c->phi, 1, c->g.nh, 0, nullptr);
     if (rc != 0) return rc;
+    le_field_async(c, c->phi);                                           // field_grad_compute -> field_leesedwards (planes only)
     {
       ProfScope ps(c, LB200_K_GRAD);
       c->launches += c->k->grad27(c->stream, c->g, c->g.nh - 1, c->phi, c->grad, c->delsq);
     }
+    le_grad_async(c);                                                    // the planes next to a Lees-Edwards plane, and the buffers
     c->u_state = ZERO_PENDING;
     rc = collide_binary_async(c, cd, sd);
     if (rc != 0) return rc;
+    le_lb_bc_async(c);                                                   // lb_data_apply_le_boundary_conditions, both distributions
     rc = halo_field(c, c->f, c->nvel*c->ndist, 1, c->opt.halo_scheme == LB200_HALO_REDUCED, nullptr);
     if (rc != 0) return rc;
     c->prop_pending = 1;
@@ -2763,7 +2767,8 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   if (binary && c->knob_grad7 && (c->ndist != 1 || c->le.nplane > 0))
     return fail(LB200_EINVAL, "fd_gradient_calculation 3d_7pt_fluid: built for the finite-difference binary fluid without planes");
   if (c->le.nplane > 0) {
-    if (!binary || c->ndist != 1) return fail(LB200_EINVAL, "Lees-Edwards planes: lb200_step is implemented for the binary-fluid FD route (ndist = 1, free_energy symmetric)");
+    if (!binary) return fail(LB200_EINVAL, "Lees-Edwards planes: lb200_step is implemented for the binary fluid (free_energy symmetric / symmetric_lb)");
+    if (c->ndist == 2) return step_lb2(c, cd, sd, nsteps);              // symmetric_lb: two distributions, no finite-difference sector
     // fast mode on a fully periodic all-fluid lattice: the halo-free step with plane patches, provided every plane
     // patch (and its +-2 stencil) stays clear of the slab boundary planes that the neighbours exchange
     const Lb200Geom & g = c->g;

@@ -975,7 +975,7 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
  * d3q19_mode2f_phi (src/collision.c:2856-3135) / generic loop (:974-1008).                          */
 
 void orc_phi_lb_to_field(const orc_geom_t * g, const orc_model_t * m, const double * f, double * phi) {
-  const size_t ns = (size_t) orc_nsites(g);
+  const size_t ns = (size_t) orc_nsites_lb(g);          /* the distributions carry no Lees-Edwards buffer planes */
   #pragma omp parallel for collapse(2) schedule(static)
   for (int ic = 1; ic <= g->nlocal[X]; ic++)
     for (int jc = 1; jc <= g->nlocal[Y]; jc++)
@@ -988,7 +988,7 @@ void orc_phi_lb_to_field(const orc_geom_t * g, const orc_model_t * m, const doub
 }
 
 void orc_phi_lb_from_field(const orc_geom_t * g, const orc_model_t * m, const double * phi, double * f) {
-  const size_t ns = (size_t) orc_nsites(g);
+  const size_t ns = (size_t) orc_nsites_lb(g);
   for (int ic = 1; ic <= g->nlocal[X]; ic++)
     for (int jc = 1; jc <= g->nlocal[Y]; jc++)
       for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
@@ -1183,6 +1183,7 @@ void orc_collide_binary(const orc_geom_t * g, const orc_model_t * m, const orc_c
 			const double * phi, const double * grad, const double * delsq, double * u) {
 
   const size_t ns = (size_t) orc_nsites(g);
+  const size_t nsf = (size_t) orc_nsites_lb(g);         /* distributions (no Lees-Edwards buffer planes) */
   const int nvel = m->nvel;
 
   #pragma omp parallel for collapse(2) schedule(static)
@@ -1192,8 +1193,8 @@ void orc_collide_binary(const orc_geom_t * g, const orc_model_t * m, const orc_c
 	int index = orc_index(g, ic, jc, kc);
 	double fs[27], gs[27], hf[3], gr[3], uu[3];
 	for (int p = 0; p < nvel; p++) {
-	  fs[p] = f[(size_t) p*ns + index];
-	  gs[p] = f[(size_t) (nvel + p)*ns + index];
+	  fs[p] = f[(size_t) p*nsf + index];
+	  gs[p] = f[(size_t) (nvel + p)*nsf + index];
 	}
 	for (int ia = 0; ia < 3; ia++) {
 	  hf[ia] = force[(size_t) ia*ns + index];
@@ -1201,8 +1202,8 @@ void orc_collide_binary(const orc_geom_t * g, const orc_model_t * m, const orc_c
 	}
 	collide_binary_site(m, cp, sp, fs, gs, hf, phi[index], gr, delsq[index], uu);
 	for (int p = 0; p < nvel; p++) {
-	  f[(size_t) p*ns + index] = fs[p];
-	  f[(size_t) (nvel + p)*ns + index] = gs[p];
+	  f[(size_t) p*nsf + index] = fs[p];
+	  f[(size_t) (nvel + p)*nsf + index] = gs[p];
 	}
 	for (int ia = 0; ia < 3; ia++) u[(size_t) ia*ns + index] = uu[ia];
       }

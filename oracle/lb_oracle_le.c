@@ -576,6 +576,39 @@ void orc_le_init_shear_profile(const orc_geom_t * g, const orc_model_t * m, cons
 
 /* ---- one time step with planes, reference driver order src/ludwig.c:528-860 --------------------------------- */
 
+/* symmetric_lb (two distributions) with planes, src/ludwig.c:528-860: phi_lb_to_field; field_halo(phi); field_grad_compute
+ * (field_leesedwards, gradient, buffer-region gradients); lb_collide (lb_collision_binary); lb_data_apply_le_boundary_conditions
+ * on both distributions; lb_halo; lb_propagation.  (Regression case: tests/regression/d3q19-short/serial-le2d-lb1.inp) */
+void orc_le_step_lb2(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
+		     const orc_symm_param_t * sp, const orc_le_t * le, int tcurrent0, int nsteps,
+		     double * f, double * phi, double * u, double * force, double * grad, double * delsq) {
+  const size_t nsf = (size_t) orc_nsites_lb(g);
+  const size_t nf = nsf*2*m->nvel;
+  const double zero[3] = {0.0, 0.0, 0.0};
+  double * fprime = (double *) calloc(nf, sizeof(double));
+  assert(fprime);
+  memcpy(fprime, f, nf*sizeof(double));
+
+  for (int n = 0; n < nsteps; n++) {
+    const int tcurrent = tcurrent0 + n + 1;
+    const double tstep = 1.0*tcurrent;
+    const double time = 1.0*(0 + tcurrent - 1.0);
+    orc_field_set(g, 3, force, zero);
+    orc_phi_lb_to_field(g, m, f, phi);
+    orc_field_halo(g, 1, phi);
+    orc_le_field(g, le, time, 1, phi);
+    orc_grad_27pt(g, phi, grad, delsq);
+    orc_le_grad_buffer(g, g->nhalo - 1, phi, grad, delsq);
+    orc_field_set(g, 3, u, zero);
+    orc_collide_binary(g, m, cp, sp, f, force, phi, grad, delsq, u);
+    orc_le_lb_bc(g, m, le, tstep, 2, f);
+    orc_lb_halo(g, m, 2, 0, f);
+    orc_propagation(g, m, 2, f, fprime);
+    memcpy(f, fprime, nf*sizeof(double));
+  }
+  free(fprime);
+}
+
 void orc_le_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
 		 const orc_symm_param_t * sp, const orc_le_t * le, int tcurrent0, int nsteps,
 		 double * f, double * phi, double * u, double * rho, double * force,

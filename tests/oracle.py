@@ -231,6 +231,10 @@ class Oracle:
         self.lib.orc_le_init_shear_profile(C.byref(self.g), C.byref(self.m), C.byref(self.le), C.c_double(rho0),
                                            C.c_double(eta), _p(f))
 
+    def le_step_lb2(self, cp, sp, tcurrent0, nsteps, f, phi, u, force, grad, delsq):
+        self.lib.orc_le_step_lb2(C.byref(self.g), C.byref(self.m), C.byref(cp), C.byref(sp), C.byref(self.le),
+                                 C.c_int(tcurrent0), C.c_int(nsteps), _p(f), _p(phi), _p(u), _p(force), _p(grad), _p(delsq))
+
     def le_step(self, cp, sp, tcurrent0, nsteps, f, phi, u, rho, force, grad, delsq):
         self.lib.orc_le_step(C.byref(self.g), C.byref(self.m), C.byref(cp), C.byref(sp), C.byref(self.le),
                              tcurrent0, nsteps, _p(f), _p(phi), _p(u), _p(rho), _p(force), _p(grad), _p(delsq))

@@ -292,3 +292,53 @@ def test_le_steps_with_conserve_options(conserve, math_mode):
             assert close_fast(a, b), (k, np.abs(a - b).max())
     if conserve == 2:
         assert abs(orc.interior(got["phi"]).sum() - sum0) < 1e-11
+
+
+LB2 = dict(a=-0.0625, b=0.0625, kappa=0.04, mobility=0.45)      # serial-le2d-lb1.inp
+
+
+def _lb2_le_run(n, nplanes, math_mode, nsteps, seed=13, calls=1):
+    orc = Oracle(n, nhalo=2, le_nplanes=nplanes, le_uy=UY)
+    phi = np.zeros((1, orc.nsites))
+    phi[:, :orc.nsites_lb] = spinodal_phi(n, 2, seed, 0.0, 0.1)
+    f = np.zeros((38, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f[:19])
+    orc.phi_lb_from_field(phi, f)
+    with lb.Lb200(n, nhalo=2, ndist=2, have_phi=True, math=math_mode, le_nplanes=nplanes, le_uy=UY) as sim:
+        sim.put(lb.F, f); sim.put(lb.PHI, phi)
+        sp_g = lb.SymmParam.make(LB2["a"], LB2["b"], LB2["kappa"], LB2["mobility"])
+        for _ in range(calls):
+            sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), sp_g, nsteps // calls)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("grad", lb.GRAD), ("delsq", lb.DELSQ))}
+        assert sim.physics_control_timestep() == nsteps
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, force, grad, delsq = z(3), z(3), z(3), z(1)
+    orc.le_step_lb2(orc.collide_param(0, 1.0, ETA), orc.symm_param(LB2["a"], LB2["b"], LB2["kappa"], LB2["mobility"]),
+                    0, nsteps, f, phi, u, force, grad, delsq)
+    return orc, got, dict(f=f, phi=phi, u=u, grad=grad, delsq=delsq)
+
+
+@pytest.mark.parametrize("n,nplanes", [((16, 12, 8), 2), ((16, 8, 10), 1), ((32, 16, 1), 2)])
+def test_le_symmetric_lb_steps_strict_bit_exact(n, nplanes):
+    """free_energy symmetric_lb (two distributions) with Lees-Edwards planes, 3-d and 2-d (a lattice thinner than the halo):
+    the oracle is pinned to the compiled reference and to serial-le2d-lb1.log in tests/test_le_oracle.py"""
+    orc, got, want = _lb2_le_run(n, nplanes, lb.MATH_STRICT, 10, calls=2)
+    for k in want:
+        assert np.array_equal(orc.interior(got[k]), orc.interior(want[k])), k
+
+
+def test_serial_le2d_lb1_log_on_gpu():
+    """tests/regression/d3q19-short/serial-le2d-lb1.log (64 x 64 x 1, 2 planes, 200 steps) from the CUDA path, fast mode:
+    the printed statistics to the printed digits"""
+    orc, got, want = _lb2_le_run((64, 64, 1), 2, lb.MATH_FAST, 200)
+    approx = lambda v, d: pytest.approx(v, rel=0.5 * 10.0 ** (1 - d), abs=1e-30)
+    phi = np.zeros((1, orc.nsites))
+    orc.phi_lb_to_field(got["f"], phi)                      # the driver's statistics recompute phi first (src/ludwig.c:2415-2420)
+    s = stats_scalar(orc, phi)
+    assert s[2] == approx(4.5598599e-03, 7) and s[3] == approx(-2.1040506e-01, 7) and s[4] == approx(2.3299586e-01, 7)
+    r = stats_scalar(orc, got["f"][:19].sum(axis=0, keepdims=True))
+    assert r[3] == approx(0.99956275287, 10) and r[4] == approx(1.00179280622, 10)
+    ui = orc.interior(got["u"])
+    assert ui[1].min() == approx(-2.4492205e-02, 7) and ui[1].max() == approx(2.4612861e-02, 7)
+    for k in want:
+        assert close_fast(orc.interior(got[k]), orc.interior(want[k])), k

@@ -148,6 +148,30 @@ def test_le_steps_conserve_vs_reference(conserve):
             R.omp_threads(before)
 
 
+@pytest.mark.parametrize("n,nplanes", [((16, 12, 8), 2), ((16, 8, 10), 1), ((32, 16, 1), 2)])
+def test_le_symmetric_lb_steps_vs_reference(n, nplanes):
+    """free_energy symmetric_lb (two distributions, lb_collision_binary) with Lees-Edwards planes -- the configuration of
+    tests/regression/d3q19-short/serial-le2d-lb1.inp, here also in 3-d: whole time steps, every field bit for bit"""
+    par = dict(a=-0.0625, b=0.0625, kappa=0.04, mobility=0.45)
+    ref = R.RefSim(n, nhalo=2, ndist=2, have_phi=1, eta_shear=ETA, ghost_off=1, le_nplanes=nplanes, le_uy=UY, **par)
+    orc = Oracle(n, nhalo=2, le_nplanes=nplanes, le_uy=UY)
+    with ref:
+        ref.init_spinodal(13, 0.0, 0.05)
+        ref.op("le_init_shear_profile")
+        ref.op("phi_lb_from_field")
+        f = ref.get(R.REF_F); phi = ref.get(R.REF_PHI)
+        nsteps = 10
+        ref.step(nsteps)
+        z = lambda k: np.zeros((k, orc.nsites))
+        u, force, grad, delsq = z(3), z(3), z(3), z(1)
+        cp = orc.collide_param(0, 1.0, ETA)
+        sp = orc.symm_param(par["a"], par["b"], par["kappa"], par["mobility"])
+        orc.le_step_lb2(cp, sp, 0, nsteps, f, phi, u, force, grad, delsq)
+        for name, a, what in (("f", f, R.REF_F), ("phi", phi, R.REF_PHI), ("u", u, R.REF_U), ("grad", grad, R.REF_GRAD),
+                              ("delsq", delsq, R.REF_DELSQ)):
+            assert np.array_equal(orc.interior(a), orc.interior(ref.get(what))), name
+
+
 # ---- printed statistics of the reference's own regression logs after 10 steps ---------------------------------
 # tests/regression/d3q19-short/serial-le3d-st5/6/7/8.{inp,log}: 32^3, 2 planes, LE_plane_vel 0.05, LE_init_profile 1,
 # viscosity 0.1, A = -B = -0.0625, K = 0.04, mobility 0.15, 27pt gradient, advection order 1/2/3/4, seed 7361237
@@ -202,6 +226,36 @@ def test_serial_le3d_logs(order):
     ui = orc.interior(u)
     for a in range(3):
         assert ui[a].min() == approx(L["umin"][a], 8) and ui[a].max() == approx(L["umax"][a], 8)
+
+
+def test_serial_le2d_lb1_log():
+    """tests/regression/d3q19-short/serial-le2d-lb1.{inp,log}: symmetric_lb with two planes on 64 x 64 x 1, 200 steps, seed 13,
+    -- the printed statistics of the reference's own regression answer from the oracle"""
+    from ludwig_b200.initial import spinodal_phi
+    n = (64, 64, 1)
+    par = dict(a=-0.0625, b=0.0625, kappa=0.04, mobility=0.45)
+    orc = Oracle(n, nhalo=2, le_nplanes=2, le_uy=UY)
+    phi = np.zeros((1, orc.nsites))
+    phi[:, :orc.nsites_lb] = spinodal_phi(n, 2, 13, 0.0, 0.1)
+    f = np.zeros((38, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f[:19])
+    orc.phi_lb_from_field(phi, f)
+    s0 = stats_scalar(orc, phi)
+    assert s0[0] == approx(-1.1802440e-02, 8) and s0[2] == approx(8.2680383e-04, 8)
+    assert s0[3] == approx(-4.9977721e-02, 8) and s0[4] == approx(4.9988335e-02, 8)
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, force, grad, delsq = z(3), z(3), z(3), z(1)
+    orc.le_step_lb2(orc.collide_param(0, 1.0, ETA), orc.symm_param(par["a"], par["b"], par["kappa"], par["mobility"]),
+                    0, 200, f, phi, u, force, grad, delsq)
+    # the driver's statistics recompute phi from the distributions first (src/ludwig.c:2415-2420)
+    orc.phi_lb_to_field(f, phi)
+    s = stats_scalar(orc, phi)
+    assert s[2] == approx(4.5598599e-03, 7) and s[3] == approx(-2.1040506e-01, 7) and s[4] == approx(2.3299586e-01, 7)
+    r = stats_scalar(orc, f[:19].sum(axis=0, keepdims=True))
+    assert r[0] == approx(4096.00, 8) and r[3] == approx(0.99956275287, 10) and r[4] == approx(1.00179280622, 10)
+    ui = orc.interior(u)
+    assert ui[0].min() == approx(-6.8035452e-04, 7) and ui[0].max() == approx(5.8780061e-04, 7)
+    assert ui[1].min() == approx(-2.4492205e-02, 7) and ui[1].max() == approx(2.4612861e-02, 7)
 
 
 def test_le2d_thin_lattice_long_run_vs_reference():
