@@ -47,6 +47,10 @@
 #include "colloids.h"
 #include "blue_phase.h"
 #include "blue_phase_beris_edwards.h"
+#include "runtime.h"
+#include "wall_rt.h"
+#include "colloids_rt.h"
+#include "map.h"
 
 #include "ludwig_b200.h"
 
@@ -359,6 +363,9 @@ int __wrap_beris_edw_param_set(beris_edw_t * be, beris_edw_param_t * values) {  
 static void b200_lc_param(pe_t * pe, fe_t * fe, lb200_lc_param_t * lc) {
   const fe_lc_param_t * p = ((fe_lc_t *) fe)->param;
   memset(lc, 0, sizeof(*lc));
+  /* the reference refreshes the phase of the electric field (param->coswt) whenever a caller asks for the device copy of the
+   * free energy before a kernel (fe_lc_target -> fe_lc_param_commit, src/blue_phase.c:191-225); those callers are replaced here */
+  fe_lc_param_commit((fe_lc_t *) fe);
   if (p->is_active && p->zeta2 != 0.0) pe_fatal(pe, "libludwig_b200: lc_active_zeta2 != 0 is outside this library\n");
   if (p->is_redshift_updated) pe_fatal(pe, "libludwig_b200: lc_redshift_update is outside this library\n");
   lc->a0 = p->a0; lc->q0 = p->q0; lc->gamma = p->gamma; lc->kappa0 = p->kappa0; lc->kappa1 = p->kappa1; lc->xi = p->xi;
@@ -378,7 +385,9 @@ int __wrap_beris_edw_update(beris_edw_t * be, fe_t * fe, field_t * fq, field_gra
   lb200_lc_param_t lc;
   int ncolloid = 0;
   if (s == NULL || s->ctx == NULL || b200_field_array(s, fq) != LB200_Q) return __real_beris_edw_update(be, fe, fq, fq_grad, hydro, cinfo, map, noise);
-  if (hydro == NULL) pe_fatal(fq->pe, "libludwig_b200: beris_edw_update without hydrodynamics is outside this library\n");
+  /* hydro == NULL: relaxational dynamics only -- the reference leaves the velocity gradient and the advective fluxes at zero
+   * (src/blue_phase_beris_edwards.c:278-283, 605); the same update with u = 0 */
+  if (hydro == NULL) b200_check(fq->pe, lb200_hydro_u_zero(s->ctx), "beris_edw_update (no hydrodynamics)");
   if (cinfo) colloids_info_ntotal(cinfo, &ncolloid);
   if (ncolloid > 0) pe_fatal(fq->pe, "libludwig_b200: colloids are outside this library\n");
   if (!be_param_known_ || be_param_.noise) pe_fatal(fq->pe, "libludwig_b200: order-parameter noise is outside this library\n");
@@ -435,6 +444,43 @@ int __wrap_phi_cahn_hilliard(phi_ch_t * pch, fe_t * fe, field_t * phi, hydro_t *
   return 0;
 }
 
+/* ---- what this library covers, checked every time step ------------------------------------------------------------
+ * fluid-only lattices (no walls, no colloids, no porous-media map), free energy none / symmetric / symmetric_lb /
+ * lc_blue_phase.  Anything else would run partly on the device and partly on the host with different views of the data:
+ * the run is refused, loudly, rather than finished with wrong numbers.  The driver's wall and colloid objects are seen where it
+ * creates them (wall_rt_init, colloids_init_rt: src/ludwig.c:274-277). */
+
+static wall_t * wall_seen_ = NULL;
+static colloids_info_t * cinfo_seen_ = NULL;
+
+int __real_wall_rt_init(pe_t * pe, cs_t * cs, rt_t * rt, lb_t * lb, map_t * map, wall_t ** wall);
+int __wrap_wall_rt_init(pe_t * pe, cs_t * cs, rt_t * rt, lb_t * lb, map_t * map, wall_t ** wall) {
+  int rc = __real_wall_rt_init(pe, cs, rt, lb, map, wall);
+  wall_seen_ = wall ? *wall : NULL;
+  return rc;
+}
+
+int __real_colloids_init_rt(pe_t * pe, rt_t * rt, cs_t * cs, colloids_info_t ** pinfo, colloid_io_t ** pcio,
+			    interact_t ** interact, wall_t * wall, map_t * map, const lb_model_t * model);
+int __wrap_colloids_init_rt(pe_t * pe, rt_t * rt, cs_t * cs, colloids_info_t ** pinfo, colloid_io_t ** pcio,
+			    interact_t ** interact, wall_t * wall, map_t * map, const lb_model_t * model) {
+  int rc = __real_colloids_init_rt(pe, rt, cs, pinfo, pcio, interact, wall, map, model);
+  cinfo_seen_ = pinfo ? *pinfo : NULL;
+  return rc;
+}
+
+static void b200_scope_check(pe_t * pe, map_t * map, fe_t * fe) {
+  int n = 0;
+  if (wall_seen_ && wall_present(wall_seen_)) pe_fatal(pe, "libludwig_b200: walls are outside this library\n");
+  if (cinfo_seen_) colloids_info_ntotal(cinfo_seen_, &n);
+  if (n > 0) pe_fatal(pe, "libludwig_b200: colloids are outside this library\n");
+  if (map) map_pm(map, &n);
+  if (map && n) pe_fatal(pe, "libludwig_b200: porous media are outside this library\n");
+  if (fe && fe->id != FE_SYMMETRIC && fe->id != FE_LC) {
+    pe_fatal(pe, "libludwig_b200: this free energy is outside this library (none, symmetric, symmetric_lb, lc_blue_phase)\n");
+  }
+}
+
 /* ---- distributions -------------------------------------------------------------------------------------------- */
 
 int __real_lb_collide(lb_t * lb, hydro_t * hydro, map_t * map, noise_t * noise, fe_t * fe, visc_t * visc);
@@ -447,6 +493,7 @@ int __wrap_lb_collide(lb_t * lb, hydro_t * hydro, map_t * map, noise_t * noise, 
   int t;
   if (hydro == NULL) return 0;                                    /* :147 */
   if (s == NULL || s->ctx == NULL) return __real_lb_collide(lb, hydro, map, noise, fe, visc);
+  b200_scope_check(lb->pe, map, fe);
   if (visc != NULL) pe_fatal(lb->pe, "libludwig_b200: viscosity models are outside this library\n");
   if (lb->param->noise) pe_fatal(lb->pe, "libludwig_b200: lb_fluctuations are outside this library\n");
   memset(&cp, 0, sizeof(cp));

@@ -688,7 +688,6 @@ int lb200_set_knob(lb200_t * c, int knob, int value) {
   else if (knob == LB200_KNOB_F32) c->knob_f32 = (value != 0);
   else if (knob == LB200_KNOB_FUSED) c->knob_fused = (value != 0);
   else if (knob == LB200_KNOB_GRAD_7PT) {
-    if (value != 0 && c->le.nplane > 0) return fail(LB200_EINVAL, "3d_7pt_fluid with Lees-Edwards planes is outside this build");
     if (value != 0 && c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
     c->knob_grad7 = (value != 0);
   }
@@ -1186,7 +1185,8 @@ static int le_grad_async(lb200_t * c, const Lb200Geom * gw = nullptr) {
   ProfScope ps(c, LB200_K_LE);
   // halo-free steps: every reader takes its y / z neighbours from the interior, so only interior (j, k) are needed
   const int ne = (gw && gw->wrap[1] && gw->wrap[2]) ? 0 : c->g.nh - 1;
-  c->launches += c->k->le_grad_planes(c->stream, gw ? *gw : c->g, ne, c->le_ntrip, c->le_trip, c->phi, c->grad, c->delsq);
+  // (fd_gradient_calculation 3d_7pt_fluid: the launcher takes -ne - 1)
+  c->launches += c->k->le_grad_planes(c->stream, gw ? *gw : c->g, c->knob_grad7 ? -ne - 1 : ne, c->le_ntrip, c->le_trip, c->phi, c->grad, c->delsq);
   return 0;
 }
 
@@ -2686,7 +2686,8 @@ static int step_le(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev &
   const Lb200Geom & g = c->g;
   int rc = ensure_f_halo(c);
   if (rc != 0) return rc;
-  const bool fused = (c->opt.math == LB200_MATH_FAST) && c->knob_phi_sector && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr;
+  const bool fused = (c->opt.math == LB200_MATH_FAST) && c->knob_phi_sector && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr
+    && !c->knob_grad7;
 
   for (int n = 0; n < nsteps; n++) {
     c->t_current += 1;                                                   // physics_control_next_step
@@ -2714,7 +2715,8 @@ static int step_le(lb200_t * c, const Lb200CollideDev & cd, const Lb200SymmDev &
     else {
       {
 	ProfScope ps(c, LB200_K_GRAD);
-	c->launches += c->k->grad27(S, g, g.nh - 1, c->phi, c->grad, c->delsq);
+	if (c->knob_grad7) c->launches += c->k->grad7(S, g, g.nh - 1, 1, c->phi, c->grad, c->delsq);   // grad_3d_7pt_fluid_d2
+	else               c->launches += c->k->grad27(S, g, g.nh - 1, c->phi, c->grad, c->delsq);
       }
       le_grad_async(c);
       le_force_ch_async(c, sd, g.nl[0], nullptr, 1, 1, 0, c->phinew);
@@ -2764,8 +2766,8 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   // reference-structured step (halo kernels), not the halo-free one whose kernels hand planes to the neighbours as they go
   const bool conserve2 = binary && c->ndist == 1 && sp->conserve == 2;
   if (nsteps <= 0) return 0;
-  if (binary && c->knob_grad7 && (c->ndist != 1 || c->le.nplane > 0))
-    return fail(LB200_EINVAL, "fd_gradient_calculation 3d_7pt_fluid: built for the finite-difference binary fluid without planes");
+  if (binary && c->knob_grad7 && c->ndist != 1)
+    return fail(LB200_EINVAL, "fd_gradient_calculation 3d_7pt_fluid: built for the finite-difference binary fluid (ndist = 1)");
   if (c->le.nplane > 0) {
     if (!binary) return fail(LB200_EINVAL, "Lees-Edwards planes: lb200_step is implemented for the binary fluid (free_energy symmetric / symmetric_lb)");
     if (c->ndist == 2) return step_lb2(c, cd, sd, nsteps);              // symmetric_lb: two distributions, no finite-difference sector
@@ -2773,7 +2775,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     // patch (and its +-2 stencil) stays clear of the slab boundary planes that the neighbours exchange
     const Lb200Geom & g = c->g;
     bool ok = (c->opt.math == LB200_MATH_FAST) && c->knob_wrap && c->knob_phi_sector && c->map_all_fluid
-      && g.per[0] && g.per[1] && g.per[2] && sd.order <= 3 && sd.csum == nullptr && !conserve2;
+      && g.per[0] && g.per[1] && g.per[2] && sd.order <= 3 && sd.csum == nullptr && !conserve2 && !c->knob_grad7;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
     for (int p = 0; p < c->le.nplane; p++) ok = ok && (c->le.loc[p] - g.nh - 1 >= 1) && (c->le.loc[p] + g.nh + 2 <= g.nl[0]);
     if (ok) return step_wrap(c, cd, &sd, nsteps);

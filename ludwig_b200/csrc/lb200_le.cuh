@@ -164,6 +164,7 @@ int launch_le_interp(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le
 // grad27_kernel.
 // ---------------------------------------------------------------------------------------------
 
+template <bool SEVEN>
 __global__ void __launch_bounds__(TPB)
 le_grad_planes_kernel(const Lb200Geom g, const int ne, const int * __restrict__ trip,
 		      const double * __restrict__ field, double * __restrict__ grad, double * __restrict__ delsq) {
@@ -177,6 +178,19 @@ le_grad_planes_kernel(const Lb200Geom g, const int ne, const int * __restrict__ 
   const double r9 = (1.0/9.0);
   const int index = le_index(g, xc, jc, kc);
   const int jm = le_wy(g, jc - 1), jp = le_wy(g, jc + 1), km = le_wz(g, kc - 1), kp = le_wz(g, kc + 1);
+  if (SEVEN) {
+    // fd_gradient_calculation 3d_7pt_fluid: grad_3d_7pt_fluid_kernel_v / grad_3d_7pt_fluid_le (src/gradient_3d_7pt_fluid.c:231-300,
+    // 317-440), same expressions as grad7_kernel
+    const double f0 = field[index];
+    const double fxm = field[le_index(g, xm, jc, kc)], fxp = field[le_index(g, xp, jc, kc)];
+    const double fym = field[le_index(g, xc, jm, kc)], fyp = field[le_index(g, xc, jp, kc)];
+    const double fzm = field[le_index(g, xc, jc, km)], fzp = field[le_index(g, xc, jc, kp)];
+    grad[0*ns + index] = 0.5*(fxp - fxm);
+    grad[1*ns + index] = 0.5*(fyp - fym);
+    grad[2*ns + index] = 0.5*(fzp - fzm);
+    delsq[index] = fxp + fxm + fyp + fym + fzp + fzm - 6.0*f0;
+    return;
+  }
 
   double m_mm, m_m0, m_mp, m_0m, m_00, m_0p, m_pm, m_p0, m_pp;
   double c_mm, c_m0, c_mp, c_0m, c_00, c_0p, c_pm, c_p0, c_pp;
@@ -209,12 +223,16 @@ le_grad_planes_kernel(const Lb200Geom g, const int ne, const int * __restrict__ 
      - 26.0*c_00);
 }
 
-int launch_le_grad_planes(cudaStream_t st, const Lb200Geom & g, int ne, int ntrip, const int * trip,
+// ne < 0: the 7-point stencil (3d_7pt_fluid), extension -ne - 1
+int launch_le_grad_planes(cudaStream_t st, const Lb200Geom & g, int ne_, int ntrip, const int * trip,
 			  const double * phi, double * grad, double * delsq) {
   if (ntrip == 0) return 0;
+  const bool seven = (ne_ < 0);
+  const int ne = seven ? -ne_ - 1 : ne_;
   const int ey = g.nl[1] + 2*ne, ez = g.nl[2] + 2*ne;
   dim3 grd((ey*ez + TPB - 1)/TPB, ntrip, 1);
-  le_grad_planes_kernel<<<grd, TPB, 0, st>>>(g, ne, trip, phi, grad, delsq);
+  if (seven) le_grad_planes_kernel<true><<<grd, TPB, 0, st>>>(g, ne, trip, phi, grad, delsq);
+  else       le_grad_planes_kernel<false><<<grd, TPB, 0, st>>>(g, ne, trip, phi, grad, delsq);
   return 1;
 }
 

@@ -158,6 +158,7 @@ void orc_le_init_shear_profile(const orc_geom_t * g, const orc_model_t * m, cons
 			       double rho0, double eta, double * f);
 /* whole steps with planes (src/ludwig.c:528-860); tcurrent0 = physics t_current before the first step
  * (t_start = 0); on return the caller's clock is tcurrent0 + nsteps */
+void orc_le_grad7_buffer(const orc_geom_t * g, int nextra, const double * field, double * grad, double * delsq);
 void orc_le_step_lb2(const orc_geom_t * g, const orc_model_t * m, const orc_collide_param_t * cp,
 		     const orc_symm_param_t * sp, const orc_le_t * le, int tcurrent0, int nsteps,
 		     double * f, double * phi, double * u, double * force, double * grad, double * delsq);

@@ -36,14 +36,15 @@ void orc_grad_7pt(const orc_geom_t * g, int nf, const double * field, double * g
   const size_t ns = (size_t) orc_nsites(g);
   const int nextra = g->nhalo - 1;
   const int ys = g->nlocal[Z] + 2*g->nhalo;
-  const int xs = ys*(g->nlocal[Y] + 2*g->nhalo);
 
   #pragma omp parallel for collapse(2) schedule(static)
   for (int ic = 1 - nextra; ic <= g->nlocal[X] + nextra; ic++) {
     for (int jc = 1 - nextra; jc <= g->nlocal[Y] + nextra; jc++) {
       for (int kc = 1 - nextra; kc <= g->nlocal[Z] + nextra; kc++) {
 	const int index = orc_index(g, ic, jc, kc);
-	const int indexm1 = index - xs, indexp1 = index + xs;      /* no Lees-Edwards planes here */
+	/* x-neighbours through the Lees-Edwards buffer planes next to a plane (src/gradient_3d_7pt_fluid.c:231-246) */
+	const int indexm1 = orc_index(g, orc_le_ic_to_buff(g, ic, -1), jc, kc);
+	const int indexp1 = orc_index(g, orc_le_ic_to_buff(g, ic, +1), jc, kc);
 	for (int n = 0; n < nf; n++) {
 	  const double * f = field + (size_t) n*ns;
 	  grad[(size_t) (n*3 + X)*ns + index] = 0.5*(f[indexp1] - f[indexm1]);

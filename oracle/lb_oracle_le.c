@@ -210,6 +210,37 @@ static void grad27_at(const double * field, size_t ns, int ys, int indexm1, int 
      - 26.0*field[index]);
 }
 
+/* grad_3d_7pt_fluid_le, src/gradient_3d_7pt_fluid.c:317-440: the same buffer-plane triples with the 7-point formulae */
+static void grad7_at(const double * field, size_t ns, int ys, int indexm1, int index, int indexp1, double * grad, double * delsq) {
+  grad[0*ns + index] = 0.5*(field[indexp1] - field[indexm1]);
+  grad[1*ns + index] = 0.5*(field[index + ys] - field[index - ys]);
+  grad[2*ns + index] = 0.5*(field[index + 1] - field[index - 1]);
+  delsq[index] = field[indexp1] + field[indexm1] + field[index + ys] + field[index - ys] + field[index + 1] + field[index - 1]
+    - 6.0*field[index];
+}
+
+void orc_le_grad7_buffer(const orc_geom_t * g, int nextra, const double * field, double * grad, double * delsq) {
+  const size_t ns = (size_t) orc_nsites(g);
+  const int * nl = g->nlocal;
+  const int ys = nl[Z] + 2*g->nhalo;
+  for (int np = 0; np < g->le_nplanes; np++) {
+    int ic = orc_le_plane_location(g, np);
+    for (int nh = 1; nh <= nextra; nh++) {
+      int ic0 = orc_le_ic_to_buff(g, ic, nh - 1), ic1 = orc_le_ic_to_buff(g, ic, nh), ic2 = orc_le_ic_to_buff(g, ic, nh + 1);
+      for (int jc = 1 - nextra; jc <= nl[Y] + nextra; jc++)
+	for (int kc = 1 - nextra; kc <= nl[Z] + nextra; kc++)
+	  grad7_at(field, ns, ys, orc_index(g, ic0, jc, kc), orc_index(g, ic1, jc, kc), orc_index(g, ic2, jc, kc), grad, delsq);
+    }
+    ic += 1;
+    for (int nh = 1; nh <= nextra; nh++) {
+      int ic2 = orc_le_ic_to_buff(g, ic, -nh + 1), ic1 = orc_le_ic_to_buff(g, ic, -nh), ic0 = orc_le_ic_to_buff(g, ic, -nh - 1);
+      for (int jc = 1 - nextra; jc <= nl[Y] + nextra; jc++)
+	for (int kc = 1 - nextra; kc <= nl[Z] + nextra; kc++)
+	  grad7_at(field, ns, ys, orc_index(g, ic0, jc, kc), orc_index(g, ic1, jc, kc), orc_index(g, ic2, jc, kc), grad, delsq);
+    }
+  }
+}
+
 void orc_le_grad_buffer(const orc_geom_t * g, int nextra, const double * field, double * grad, double * delsq) {
 
   const size_t ns = (size_t) orc_nsites(g);
@@ -632,8 +663,14 @@ void orc_le_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
     orc_field_set(g, 3, force, zero);
     orc_field_halo(g, 1, phi);
     orc_le_field(g, le, time, 1, phi);                   /* field_grad_compute: src/field_grad.c:324 */
-    orc_grad_27pt(g, phi, grad, delsq);
-    orc_le_grad_buffer(g, g->nhalo - 1, phi, grad, delsq);
+    if (sp->grad_7pt) {                                  /* fd_gradient_calculation 3d_7pt_fluid */
+      orc_grad_7pt(g, 1, phi, grad, delsq);
+      orc_le_grad7_buffer(g, g->nhalo - 1, phi, grad, delsq);
+    }
+    else {
+      orc_grad_27pt(g, phi, grad, delsq);
+      orc_le_grad_buffer(g, g->nhalo - 1, phi, grad, delsq);
+    }
     orc_le_phi_force(g, sp, phi, grad, delsq, force);
     orc_field_halo(g, 3, u);
     orc_le_hydro(g, le, time, 1, u);

@@ -342,3 +342,32 @@ def test_serial_le2d_lb1_log_on_gpu():
     assert ui[1].min() == approx(-2.4492205e-02, 7) and ui[1].max() == approx(2.4612861e-02, 7)
     for k in want:
         assert close_fast(orc.interior(got[k]), orc.interior(want[k])), k
+
+
+@pytest.mark.parametrize("math_mode", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 3), ((16, 8, 10), 1, 2)])
+def test_le_steps_7pt_gradient(n, nplanes, order, math_mode):
+    """fd_gradient_calculation 3d_7pt_fluid with planes (grad_3d_7pt_fluid_le; the configuration of the reference's
+    serial-le3d-st1..4): oracle pinned to the compiled reference in tests/test_le_oracle.py"""
+    orc, sim, sp_o, sp_g = make(n, nplanes, order, math_mode)
+    sp_o = orc.symm_param(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order, grad_7pt=1)
+    f = np.zeros((19, orc.nsites_lb))
+    orc.le_init_shear_profile(1.0, ETA, f)
+    phi = np.zeros((1, orc.nsites))
+    phi[:, :orc.nsites_lb] = spinodal_phi(n, 2, 13, 0.0, 0.1)
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+    with sim:
+        sim.set_knob(lb.KNOB_GRAD_7PT, 1)
+        sim.put(lb.F, f); sim.put(lb.PHI, phi)
+        sim.step(lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA), sp_g, 10)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("force", lb.FORCE), ("grad", lb.GRAD),
+                                          ("delsq", lb.DELSQ))}
+    orc.le_step(orc.collide_param(0, 1.0, ETA), sp_o, 0, 10, f, phi, u, rho, force, grad, delsq)
+    want = dict(f=f, phi=phi, u=u, force=force, grad=grad, delsq=delsq)
+    for k in want:
+        a, b = orc.interior(got[k]), orc.interior(want[k])
+        if math_mode == lb.MATH_STRICT:
+            assert np.array_equal(a, b), k
+        else:
+            assert close_fast(a, b), (k, np.abs(a - b).max())

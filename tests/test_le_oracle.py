@@ -14,8 +14,9 @@ ETA = 0.1
 UY = 0.05
 
 
-def make(n, nplanes, order, uy=UY, conserve=0):
-    ref = R.RefSim(n, nhalo=2, have_phi=1, adv_order=order, eta_shear=ETA, le_nplanes=nplanes, le_uy=uy, conserve=conserve, **FE)
+def make(n, nplanes, order, uy=UY, conserve=0, grad_7pt=0):
+    ref = R.RefSim(n, nhalo=2, have_phi=1, adv_order=order, eta_shear=ETA, le_nplanes=nplanes, le_uy=uy, conserve=conserve,
+                   grad_7pt=grad_7pt, **FE)
     orc = Oracle(n, nhalo=2, le_nplanes=nplanes, le_uy=uy)
     assert ref.nsites == orc.nsites_lb and ref.nsites_le == orc.nsites
     return ref, orc
@@ -113,6 +114,24 @@ def test_le_steps_vs_reference(n, nplanes, order):
         orc.le_step(cp, sp, 0, nsteps, f, phi, u, rho, force, grad, delsq)
         for name, a, what in (("f", f, R.REF_F), ("phi", phi, R.REF_PHI), ("u", u, R.REF_U), ("rho", rho, R.REF_RHO),
                               ("force", force, R.REF_FORCE), ("grad", grad, R.REF_GRAD), ("delsq", delsq, R.REF_DELSQ)):
+            assert np.array_equal(orc.interior(a), orc.interior(ref.get(what))), name
+
+
+@pytest.mark.parametrize("n,nplanes,order", [((16, 12, 8), 2, 3), ((16, 8, 10), 1, 2)])
+def test_le_steps_7pt_gradient_vs_reference(n, nplanes, order):
+    """fd_gradient_calculation 3d_7pt_fluid with planes (grad_3d_7pt_fluid_le; tests/regression/d3q19-short/serial-le3d-st1..4)"""
+    ref, orc = make(n, nplanes, order, grad_7pt=1)
+    with ref:
+        ref.init_spinodal(13, 0.0, 0.05)
+        ref.op("le_init_shear_profile")
+        f = ref.get(R.REF_F); phi = ref.get(R.REF_PHI)
+        z = lambda k: np.zeros((k, orc.nsites))
+        u, rho, force, grad, delsq = z(3), z(1), z(3), z(3), z(1)
+        ref.step(10)
+        sp = orc.symm_param(FE["a"], FE["b"], FE["kappa"], FE["mobility"], adv_order=order, grad_7pt=1)
+        orc.le_step(orc.collide_param(0, 1.0, ETA), sp, 0, 10, f, phi, u, rho, force, grad, delsq)
+        for name, a, what in (("f", f, R.REF_F), ("phi", phi, R.REF_PHI), ("u", u, R.REF_U), ("force", force, R.REF_FORCE),
+                              ("grad", grad, R.REF_GRAD), ("delsq", delsq, R.REF_DELSQ)):
             assert np.array_equal(orc.interior(a), orc.interior(ref.get(what))), name
 
 
