@@ -157,3 +157,47 @@ def test_reference_unit_suites_pass_on_the_library(tmp_path):
     assert "the reference's hot-path unit suites passed" in r.stdout
     for suite in ("test_prop", "test_lb_data", "test_field", "test_hydro"):
         assert re.search(rf"PASS\s+\S*{suite}\b", r.stdout), suite
+
+
+# ---- the reference's own regression inputs (tests/regression/d3q19-short/serial-*.inp, restated as key / value pairs in
+# tests/golden/regression_inputs_d3q19_short.json by tools/make_regression_inputs.py) -- a sample of the full sweep
+# (tools/regression_sweep.py, profiles/r02_regression_sweep.md: 26 logs equal, 75 explicit refusals, 0 different)
+import json
+
+REGRESSION = json.load(open(os.path.join(ROOT, "tests", "golden", "regression_inputs_d3q19_short.json")))
+IN_SCOPE = ["serial-le3d-st1", "serial-le3d-st7", "serial-le2d-lb1", "serial-relx-bp1", "serial-chol-fld", "serial-symm-dr1",
+            "serial-dist-3du", "serial-init-bp1", "serial-spin-lb1"]
+OUT_OF_SCOPE = {"serial-auto-c01": "colloids are outside this library", "serial-wall-st2": "walls are outside this library",
+                "serial-elec-gc1": "porous media are outside this library", "serial-pola-r01": "this free energy is outside this library"}
+
+
+def run_pairs(exe, pairs, cwd, env=None):
+    with open(os.path.join(cwd, "input"), "w") as fh:
+        for k, v in pairs:
+            fh.write(f"{k} {v}\n")
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([os.path.join(BIN, exe)], cwd=cwd, capture_output=True, text=True, timeout=600, env=e)
+
+
+@pytest.mark.skipif(not (have("Ludwig_b200.exe") and have("Ludwig_soa.exe")), reason="integration/_ref not built (needs the reference source tree)")
+@pytest.mark.parametrize("case", IN_SCOPE)
+def test_reference_regression_input_matches(case, tmp_path):
+    d_gpu, d_cpu = tmp_path / "gpu", tmp_path / "cpu"
+    d_gpu.mkdir(); d_cpu.mkdir()
+    got = run_pairs("Ludwig_b200.exe", REGRESSION[case], str(d_gpu), env={"LB200_MATH": "strict"})
+    ref = run_pairs("Ludwig_soa.exe", REGRESSION[case], str(d_cpu), env={"OMP_NUM_THREADS": "8"})
+    assert ref.returncode == 0 and "Ludwig finished normally" in ref.stdout
+    assert got.returncode == 0 and "Ludwig finished normally" in got.stdout, (got.stdout[-1500:], got.stderr[-1500:])
+    bad = diff_logs(ref.stdout, got.stdout)
+    assert not bad, "\n".join(bad[:20])
+
+
+@pytest.mark.skipif(not have("Ludwig_b200.exe"), reason="integration/_ref not built (needs the reference source tree)")
+@pytest.mark.parametrize("case", list(OUT_OF_SCOPE))
+def test_reference_regression_input_outside_the_scope_is_refused(case, tmp_path):
+    """walls, colloids, other free energies: an explicit message and the reference's own pe_fatal exit (its serial MPI stub's
+    MPI_Abort ends the process with status 0) -- never a finished run with other numbers"""
+    got = run_pairs("Ludwig_b200.exe", REGRESSION[case], str(tmp_path), env={"LB200_MATH": "strict"})
+    assert "Ludwig finished normally" not in got.stdout and "Completed cycle" not in got.stdout
+    assert OUT_OF_SCOPE[case] in (got.stdout + got.stderr)
