@@ -28,8 +28,8 @@ def main():
     for name in sorted(os.listdir(d)):
         if name.startswith("serial-") and name.endswith(".inp"):
             cases[name[:-4]] = parse(os.path.join(d, name))
-    with open(out, "w") as fh:
-        json.dump(cases, fh, indent=0, sort_keys=True)
+    with open(out, "w") as fh:                                    # one case per line
+        fh.write("{\n" + ",\n".join(json.dumps(k) + ": " + json.dumps(v) for k, v in sorted(cases.items())) + "\n}\n")
     print(len(cases), "cases ->", out)
 
 
