@@ -290,6 +290,8 @@ enum lb200_knob {
                                *    memory (368 instead of 416 bytes per site and step).  Where it does not apply the
                                *    step runs the phi-sector kernel followed by the collision kernel.
                                *    Default LB200_FUSED, else 1 */
+  LB200_KNOB_QGRAD_2D5 = 9,   /* 1: fd_gradient_calculation 2d_5pt_fluid for the Q tensor (grad_2d_5pt_fluid_d2,
+                               *    src/gradient_2d_5pt_fluid.c:53-72): lattices with nlocal[Z] = 1.  0 (default): 3d_7pt_fluid */
   LB200_KNOB_GRAD_7PT = 7     /* NOT an execution knob: selects the finite-difference scheme of the scalar order parameter,
                                *    `fd_gradient_calculation`: 0 = 3d_27pt_fluid (default), 1 = 3d_7pt_fluid
                                *    (grad_3d_7pt_fluid_d2, src/gradient_3d_7pt_fluid.c:76-99, 231-300) for

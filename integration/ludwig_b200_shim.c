@@ -34,6 +34,7 @@
 #include "field_grad.h"
 #include "gradient_3d_27pt_fluid.h"
 #include "gradient_3d_7pt_fluid.h"
+#include "gradient_2d_5pt_fluid.h"
 #include "hydro.h"
 #include "free_energy.h"
 #include "symmetric.h"
@@ -339,11 +340,12 @@ int __wrap_field_grad_compute(field_grad_t * obj) {               /* src/field_g
     }
     return 0;
   }
-  if (a == LB200_Q && obj->d2 == grad_3d_7pt_fluid_d2) {
+  if (a == LB200_Q && (obj->d2 == grad_3d_7pt_fluid_d2 || obj->d2 == grad_2d_5pt_fluid_d2)) {
+    b200_check(obj->pe, lb200_set_knob(s->ctx, LB200_KNOB_QGRAD_2D5, obj->d2 == grad_2d_5pt_fluid_d2), "field_grad_compute");
     b200_check(obj->pe, lb200_q_grad_compute(s->ctx), "field_grad_compute");
     return 0;
   }
-  if (a >= 0) pe_fatal(obj->pe, "libludwig_b200: fd_gradient_calculation of this run has no device kernel (3d_27pt_fluid, 3d_7pt_fluid)\n");
+  if (a >= 0) pe_fatal(obj->pe, "libludwig_b200: fd_gradient_calculation of this run has no device kernel (3d_27pt_fluid, 3d_7pt_fluid; Q tensor: 3d_7pt_fluid, 2d_5pt_fluid)\n");
   return __real_field_grad_compute(obj);
 }
 

@@ -9,6 +9,7 @@ HALO_FULL, HALO_REDUCED = 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 H2D, D2H = 1, 2
 KNOB_WRAP, KNOB_PHI_SECTOR, KNOB_PEER, KNOB_PIPE, KNOB_PIPE_SMS, KNOB_F32, KNOB_GRAD_7PT, KNOB_FUSED = 1, 2, 3, 4, 5, 6, 7, 8
+KNOB_QGRAD_2D5 = 9
 
 _NCOMP = {PHI: 1, U: 3, RHO: 1, FORCE: 3, GRAD: 3, DELSQ: 1, MAP: 1, GRAD_DELSQ: 3, DELSQ_DELSQ: 1, STR: 9,
           Q: 5, QGRAD: 15, QDELSQ: 5}

@@ -116,6 +116,7 @@ struct lb200_s {
   int knob_phi_sector;
   int knob_peer;
   int knob_grad7;            // fd_gradient_calculation 3d_7pt_fluid for the scalar order parameter (0: 3d_27pt_fluid)
+  int knob_qgrad2d;          // fd_gradient_calculation 2d_5pt_fluid for the Q tensor (0: 3d_7pt_fluid)
   int knob_lazy_diag;        // rho / grad / delsq stored by the last step of an lb200_step call only (LB200_LAZY_DIAG, default 1)
   int knob_f32;              // FP32 storage of the distributions inside lb200_step (0: off)
   int knob_fused;            // one kernel per binary-fluid step where it applies (LB200_FUSED, default 1)
@@ -690,6 +691,11 @@ int lb200_set_knob(lb200_t * c, int knob, int value) {
   else if (knob == LB200_KNOB_GRAD_7PT) {
     if (value != 0 && c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
     c->knob_grad7 = (value != 0);
+  }
+  else if (knob == LB200_KNOB_QGRAD_2D5) {
+    if (value != 0 && c->q == nullptr) return fail(LB200_ESTATE, "no q in this context");
+    if (value != 0 && c->g.nl[2] != 1) return fail(LB200_EINVAL, "2d_5pt_fluid needs a lattice with one plane in z");
+    c->knob_qgrad2d = (value != 0);
   }
   else if (knob == LB200_KNOB_PIPE) c->knob_pipe = (value < 0) ? 0 : (value > LB200_PIPE_MAXS ? LB200_PIPE_MAXS : value);
   else if (knob == LB200_KNOB_PIPE_SMS) {
@@ -2376,6 +2382,7 @@ static int lc_dev(lb200_t * c, const lb200_lc_param_t * lc, Lb200LcDev * d) {
   d->redshift = (lc->redshift != 0.0) ? lc->redshift : 1.0;
   if (fabs(d->redshift) < 1.0e-5) return fail(LB200_EINVAL, "redshift %g below FE_REDSHIFT_MIN (src/blue_phase.c:29-32)", d->redshift);
   d->rredshift = 1.0/d->redshift;
+  d->g2d = c->knob_qgrad2d;
   return 0;
 }
 
@@ -2396,7 +2403,7 @@ int lb200_q_grad_compute(lb200_t * c) {
   }
   {
     ProfScope ps(c, LB200_K_GRAD);
-    c->launches += c->k->grad7(c->stream, c->g, c->g.nh - 1, 5, c->q, c->qgrad, c->qdelsq);
+    c->launches += c->k->grad7(c->stream, c->g, c->g.nh - 1, c->knob_qgrad2d ? -5 : 5, c->q, c->qgrad, c->qdelsq);   // (-5: 2d_5pt_fluid)
   }
   CTX_LEAVE_SYNC(c);
 }

@@ -67,6 +67,7 @@ struct Lb200LcDev {
   int is_active;        // active stress zeta0 d_ab - zeta1 Q_ab (lc_activity)
   double zeta0, zeta1;
   double redshift, rredshift;   // static redshift and its reciprocal (1.0/redshift, formed on the host as fe_lc_redshift_set does)
+  int g2d;              // fd_gradient_calculation 2d_5pt_fluid (lattices with one plane in z)
 };
 
 struct Lb200CollideDev {
@@ -164,6 +165,7 @@ struct Lb200Kernels {
 		  int ndist, double * f, double * sbuf);
   // liquid crystal (lb200_lc.cuh): 7-point gradient arrays of nf components on [1-ne, N+ne]^3; the stress from the
   // 7-point star of Q; force from the stored stress and / or the Beris-Edwards update in one sweep
+  // (nf < 0: -nf components with the 2d_5pt_fluid stencil, on the plane kc = 1 only)
   int (*grad7)(cudaStream_t, const Lb200Geom &, int ne, int nf, const double * field, double * grad, double * delsq);
   int (*lc_stress)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int nex, int ne, const double * q, double * str);
   int (*lc_force_be)(cudaStream_t, const Lb200Geom &, const Lb200LcDev &, int do_force, int do_be, int accumulate,

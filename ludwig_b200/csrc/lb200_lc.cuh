@@ -42,8 +42,10 @@ __device__ __forceinline__ void lc_expand5(const double c[5], double t[3][3]) {
 }
 
 // q, d_a q, laplacian(q) at a site from its 7-point star (grad_3d_7pt_fluid_kernel_v, src/gradient_3d_7pt_fluid.c:231-300)
+// g2d: fd_gradient_calculation 2d_5pt_fluid (src/gradient_2d_5pt_fluid.c:108-172) -- a host loop over the plane kc = 1 in the
+// reference: no z terms there, and gradient arrays that stay zero at kc != 1 (the stress on the z halo sites reads zeros)
 __device__ __forceinline__ void lc_load_star(const Lb200Geom & g, const double * __restrict__ qf, int ic, int jc, int kc,
-					     double q[3][3], double dq[3][3][3], double dsq[3][3]) {
+					     double q[3][3], double dq[3][3][3], double dsq[3][3], int g2d = 0) {
   const size_t ns = (size_t) g.nsites;
   const int s = lc_nbr(g, ic, jc, kc);
   const int sxm = lc_nbr(g, ic - 1, jc, kc), sxp = lc_nbr(g, ic + 1, jc, kc);
@@ -59,6 +61,11 @@ __device__ __forceinline__ void lc_load_star(const Lb200Geom & g, const double *
     gy[n] = 0.5*(fyp - fym);
     gz[n] = 0.5*(fzp - fzm);
     d2[n] = fxp + fxm + fyp + fym + fzp + fzm - 6.0*f0;
+    if (g2d) {
+      gz[n] = 0.0;
+      d2[n] = fxp + fxm + fyp + fym - 4.0*f0;
+      if (kc != 1) { gx[n] = 0.0; gy[n] = 0.0; d2[n] = 0.0; }
+    }
   }
   lc_expand5(c, q);
   lc_expand5(gx, dq[0]);
@@ -363,12 +370,13 @@ __device__ __forceinline__ void lc_stress_fast(const Lb200LcDev & p, const doubl
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(TPB_MAX)
-grad7_kernel(const Lb200Geom g, int ne, int nf, const double * __restrict__ field, double * __restrict__ grad,
+grad7_kernel(const Lb200Geom g, int ne, int nf, int g2d, const double * __restrict__ field, double * __restrict__ grad,
 	     double * __restrict__ delsq) {
   const int kc = 1 - ne + blockIdx.x*blockDim.x + threadIdx.x;
   const int jc = 1 - ne + blockIdx.y*blockDim.y + threadIdx.y;
   const int ic = 1 - ne + blockIdx.z;
   if (kc > g.nl[2] + ne || jc > g.nl[1] + ne) return;
+  if (g2d && kc != 1) return;                      // 2d_5pt_fluid: the plane kc = 1 only
   const size_t ns = (size_t) g.nsites;
   const int s = le_index(g, ic, jc, kc);
   const int sxm = lc_nbr(g, ic - 1, jc, kc), sxp = lc_nbr(g, ic + 1, jc, kc);
@@ -379,16 +387,18 @@ grad7_kernel(const Lb200Geom g, int ne, int nf, const double * __restrict__ fiel
     const double f0 = f[s], fxm = f[sxm], fxp = f[sxp], fym = f[sym], fyp = f[syp], fzm = f[szm], fzp = f[szp];
     grad[(size_t) (n*3 + 0)*ns + s] = 0.5*(fxp - fxm);
     grad[(size_t) (n*3 + 1)*ns + s] = 0.5*(fyp - fym);
-    grad[(size_t) (n*3 + 2)*ns + s] = 0.5*(fzp - fzm);
-    delsq[n*ns + s] = fxp + fxm + fyp + fym + fzp + fzm - 6.0*f0;
+    grad[(size_t) (n*3 + 2)*ns + s] = g2d ? 0.0 : 0.5*(fzp - fzm);
+    delsq[n*ns + s] = g2d ? fxp + fxm + fyp + fym - 4.0*f0 : fxp + fxm + fyp + fym + fzp + fzm - 6.0*f0;
   }
 }
 
-int launch_grad7(cudaStream_t st, const Lb200Geom & g, int ne, int nf, const double * field, double * grad, double * delsq) {
+// nf < 0: -nf components with the 2d_5pt_fluid stencil (the plane kc = 1 only)
+int launch_grad7(cudaStream_t st, const Lb200Geom & g, int ne, int nf_, const double * field, double * grad, double * delsq) {
+  const int g2d = (nf_ < 0), nf = g2d ? -nf_ : nf_;
   dim3 blk;
   block_shape(g.nl[2] + 2*ne, blk);
   dim3 grd((g.nl[2] + 2*ne + blk.x - 1)/blk.x, (g.nl[1] + 2*ne + blk.y - 1)/blk.y, g.nl[0] + 2*ne);
-  grad7_kernel<<<grd, blk, 0, st>>>(g, ne, nf, field, grad, delsq);
+  grad7_kernel<<<grd, blk, 0, st>>>(g, ne, nf, g2d, field, grad, delsq);
   return 1;
 }
 
@@ -406,7 +416,7 @@ lc_stress_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, int ne
   if (kc > g.nl[2] + ne || jc > g.nl[1] + ne) return;
   const size_t ns = (size_t) g.nsites;
   double q[3][3], dq[3][3][3], dsq[3][3], h[3][3], s[3][3];
-  lc_load_star(g, qf, ic, jc, kc, q, dq, dsq);
+  lc_load_star(g, qf, ic, jc, kc, q, dq, dsq, p.g2d);
 #ifdef LB200_STRICT
   lc_compute_h(p, q, dq, dsq, h);
   lc_compute_stress(p, q, dq, h, s);
@@ -489,7 +499,7 @@ lc_force_be_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, cons
     const double r3 = (1.0/3.0);
     const double dt = 1.0;
     double q[3][3], dq[3][3][3], dsq[3][3], h[3][3];
-    lc_load_star(g, qf, ic, jc, kc, q, dq, dsq);
+    lc_load_star(g, qf, ic, jc, kc, q, dq, dsq, p.g2d);
 #ifdef LB200_STRICT
     lc_compute_h(p, q, dq, dsq, h);
 #else
@@ -594,8 +604,8 @@ lc_force_be_kernel(const Lb200Geom g, const __grid_constant__ Lb200LcDev p, cons
       c[n] = f0;
       gx[n] = 0.5*(fxp - fxm);
       gy[n] = 0.5*(fyp - fym);
-      gz[n] = 0.5*(fzp - fzm);
-      d2[n] = fxp + fxm + fyp + fym + fzp + fzm - 6.0*f0;
+      gz[n] = p.g2d ? 0.0 : 0.5*(fzp - fzm);
+      d2[n] = p.g2d ? fxp + fxm + fyp + fym - 4.0*f0 : fxp + fxm + fyp + fym + fzp + fzm - 6.0*f0;
       const double fw  = adv_face<ORDER, true>(ux_m, ux_c, fxm2, fxm, f0, fxp);
       const double fe  = adv_face<ORDER, false>(ux_c, ux_p, fxm, f0, fxp, fxp2);
       const double fy  = adv_face<ORDER, false>(uy_c, uy_p, fym, f0, fyp, fyp2);

@@ -178,9 +178,11 @@ typedef struct orc_lc_param_s {
   int is_active;                              /* lc_activity */
   double zeta0, zeta1, zeta2;                 /* lc_active_zeta0/1/2 (zeta2: the dp field is zero unless fe_lc_active_stress ran) */
   double redshift, rredshift;                 /* lc_init_redshift and its reciprocal (fe_lc_redshift_set, src/blue_phase.c:1357-1366); static */
+  int grad_2d5;                               /* fd_gradient_calculation 2d_5pt_fluid (orc_lc_step; lattices with nlocal[Z] = 1) */
 } orc_lc_param_t;
 
 void orc_grad_7pt(const orc_geom_t * g, int nf, const double * field, double * grad, double * delsq);
+void orc_grad_2d_5pt(const orc_geom_t * g, int nf, const double * field, double * grad, double * delsq);
 void orc_lc_compute_h(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3], double dsq[3][3], double h[3][3]);
 double orc_lc_compute_fed(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3]);
 void orc_lc_compute_stress(const orc_lc_param_t * p, double q[3][3], double dq[3][3][3], double h[3][3], double s[3][3]);

@@ -58,6 +58,30 @@ void orc_grad_7pt(const orc_geom_t * g, int nf, const double * field, double * g
   }
 }
 
+/* ---- grad_2d_5pt_fluid_d2 -> grad_2d_5pt_fluid_operator: src/gradient_2d_5pt_fluid.c:53-72, 108-172.  A host loop in the reference
+ * over (ic, jc) at kc = 1 ONLY: the z component of the gradient is zero, and the arrays keep whatever they held at kc != 1 (zero
+ * from their allocation) -- which the stress on the z halo sites then reads (pth_stress_compute sweeps [0, N + 1]^3). ---- */
+
+void orc_grad_2d_5pt(const orc_geom_t * g, int nf, const double * field, double * grad, double * delsq) {
+  const size_t ns = (size_t) orc_nsites(g);
+  const int nextra = g->nhalo - 1;
+  const int ys = g->nlocal[Z] + 2*g->nhalo;
+  for (int ic = 1 - nextra; ic <= g->nlocal[X] + nextra; ic++) {
+    for (int jc = 1 - nextra; jc <= g->nlocal[Y] + nextra; jc++) {
+      const int index = orc_index(g, ic, jc, 1);
+      const int indexm1 = orc_index(g, orc_le_ic_to_buff(g, ic, -1), jc, 1);
+      const int indexp1 = orc_index(g, orc_le_ic_to_buff(g, ic, +1), jc, 1);
+      for (int n = 0; n < nf; n++) {
+	const double * f = field + (size_t) n*ns;
+	grad[(size_t) (n*3 + X)*ns + index] = 0.5*(f[indexp1] - f[indexm1]);
+	grad[(size_t) (n*3 + Y)*ns + index] = 0.5*(f[index + ys] - f[index - ys]);
+	grad[(size_t) (n*3 + Z)*ns + index] = 0.0;
+	delsq[(size_t) n*ns + index] = f[indexp1] + f[indexm1] + f[index + ys] + f[index - ys] - 4.0*f[index];
+      }
+    }
+  }
+}
+
 /* ---- expansion of the compressed tensors at a site: src/blue_phase.c:1689-1722 ------------------------------ */
 
 static void lc_expand(const double * q_, const double * grad, const double * delsq, size_t ns, int index,
@@ -459,7 +483,8 @@ void orc_lc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_
   for (int n = 0; n < nsteps; n++) {
     orc_field_set(g, 3, force, zero);
     orc_field_halo(g, NQAB, q);
-    orc_grad_7pt(g, NQAB, q, qgrad, qdelsq);
+    if (p->grad_2d5) orc_grad_2d_5pt(g, NQAB, q, qgrad, qdelsq);       /* fd_gradient_calculation 2d_5pt_fluid */
+    else             orc_grad_7pt(g, NQAB, q, qgrad, qdelsq);
     orc_lc_stress(g, p, q, qgrad, qdelsq, str);
     orc_force_divergence(g, str, force);
     orc_field_halo(g, 3, u);

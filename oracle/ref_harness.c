@@ -52,6 +52,7 @@
 #include "blue_phase_init.h"
 #include "blue_phase_beris_edwards.h"
 #include "gradient_3d_7pt_fluid.h"
+#include "gradient_2d_5pt_fluid.h"
 #include "colloids.h"
 #include "io_event.h"
 #include "cahn_hilliard_stats.h"
@@ -88,6 +89,7 @@ typedef struct ref_cfg_s {
   int lc_active;       /* lc_activity yes */
   double lc_zeta0, lc_zeta1;   /* lc_active_zeta0, lc_active_zeta1 (zeta2 = 0) */
   double lc_redshift;  /* lc_init_redshift (0: 1.0); no dynamic update */
+  int lc_grad_2d5;     /* fd_gradient_calculation 2d_5pt_fluid for the Q tensor */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -213,7 +215,8 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     if (cfg->io_ascii) opts.iodata.input.iorformat = opts.iodata.output.iorformat = IO_RECORD_ASCII;
     field_create(s->pe, s->cs, s->le, "q", &opts, &s->q);
     field_grad_create(s->pe, s->q, 2, &s->q_grad);
-    field_grad_set(s->q_grad, grad_3d_7pt_fluid_d2, grad_3d_7pt_fluid_d4);
+    if (cfg->lc_grad_2d5) field_grad_set(s->q_grad, grad_2d_5pt_fluid_d2, grad_2d_5pt_fluid_d4);
+    else                  field_grad_set(s->q_grad, grad_3d_7pt_fluid_d2, grad_3d_7pt_fluid_d4);
     fe_lc_create(s->pe, s->cs, s->le, s->q, s->q_grad, &s->fe_lc);
     p.a0 = cfg->lc_a0; p.q0 = cfg->lc_q0; p.gamma = cfg->lc_gamma;
     p.kappa0 = cfg->lc_kappa0; p.kappa1 = cfg->lc_kappa1; p.xi = cfg->lc_xi;

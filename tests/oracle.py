@@ -31,7 +31,7 @@ class LcParam(C.Structure):
     _fields_ = [("a0", C.c_double), ("q0", C.c_double), ("gamma", C.c_double), ("kappa0", C.c_double),
                 ("kappa1", C.c_double), ("xi", C.c_double), ("Gamma", C.c_double), ("epsilon", C.c_double),
                 ("e0", C.c_double * 3), ("is_active", C.c_int), ("zeta0", C.c_double), ("zeta1", C.c_double),
-                ("zeta2", C.c_double), ("redshift", C.c_double), ("rredshift", C.c_double)]
+                ("zeta2", C.c_double), ("redshift", C.c_double), ("rredshift", C.c_double), ("grad_2d5", C.c_int)]
 
 
 class LeParam(C.Structure):
@@ -240,14 +240,18 @@ class Oracle:
                              tcurrent0, nsteps, _p(f), _p(phi), _p(u), _p(rho), _p(force), _p(grad), _p(delsq))
 
     # ---- liquid crystal (oracle/lb_oracle_lc.c) ----------------------------------------------------
-    def lc_param(self, a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon=0.0, e0=(0.0, 0.0, 0.0), zeta0=None, zeta1=0.0, redshift=1.0):
+    def lc_param(self, a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon=0.0, e0=(0.0, 0.0, 0.0), zeta0=None, zeta1=0.0, redshift=1.0, grad_2d5=0):
         p = LcParam()
         p.a0, p.q0, p.gamma, p.kappa0, p.kappa1, p.xi, p.Gamma, p.epsilon = a0, q0, gamma, kappa0, kappa1, xi, Gamma, epsilon
         p.e0[:] = e0
         p.is_active = int(zeta0 is not None)
         p.zeta0, p.zeta1, p.zeta2 = (zeta0 or 0.0), zeta1, 0.0
         p.redshift, p.rredshift = redshift, 1.0 / redshift
+        p.grad_2d5 = grad_2d5
         return p
+
+    def grad_2d_5pt(self, field, grad, delsq):
+        self.lib.orc_grad_2d_5pt(C.byref(self.g), field.shape[0], _p(field), _p(grad), _p(delsq))
 
     def grad_7pt(self, field, grad, delsq):
         self.lib.orc_grad_7pt(C.byref(self.g), field.shape[0], _p(field), _p(grad), _p(delsq))

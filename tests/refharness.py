@@ -28,7 +28,7 @@ class RefCfg(C.Structure):
                 ("lc_kappa0", C.c_double), ("lc_kappa1", C.c_double), ("lc_xi", C.c_double), ("lc_Gamma", C.c_double),
                 ("lc_epsilon", C.c_double), ("lc_e0", C.c_double * 3), ("grad_7pt", C.c_int),
                 ("io_ascii", C.c_int), ("lc_active", C.c_int), ("lc_zeta0", C.c_double), ("lc_zeta1", C.c_double),
-                ("lc_redshift", C.c_double)]
+                ("lc_redshift", C.c_double), ("lc_grad_2d5", C.c_int)]
 
 
 def _so(fast=False, nvel=19):
@@ -122,6 +122,7 @@ class RefSim:
             cfg.lc_active = int(lc.get("zeta0") is not None)
             cfg.lc_zeta0, cfg.lc_zeta1 = (lc.get("zeta0") or 0.0), lc.get("zeta1", 0.0)
             cfg.lc_redshift = lc.get("redshift", 1.0)
+            cfg.lc_grad_2d5 = int(lc.get("grad_2d5", 0))
         self.cfg = cfg
         self.h = self.lib.ref_create(C.byref(cfg))
         self.nsites = self.lib.ref_nsites(self.h)

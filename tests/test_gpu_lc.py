@@ -129,3 +129,34 @@ def test_pmpi08_chol_s01_log_on_gpu():
     assert qi[1].min() == approx(-2.4999462e-01, 8) and qi[1].max() == approx(2.4999462e-01, 8)
     assert qi[3].mean() == approx(8.3292223e-02, 8)
     assert uz.min() == approx(-4.2438997e-10, 6) and uz.max() == approx(4.2438990e-10, 6)
+
+
+@pytest.mark.parametrize("math_mode", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+@pytest.mark.parametrize("path", ["step", "api"])
+def test_lc_active_nematic_2d(path, math_mode):
+    """an active nematic on a 2-d lattice (one plane in z, thinner than the halo) with fd_gradient_calculation 2d_5pt_fluid --
+    the configuration of tests/regression/d3q19-short/serial-actv-s01.inp; the oracle is pinned to the compiled reference in
+    tests/test_lc_oracle.py::test_lc_active_2d_steps_vs_reference"""
+    lc = dict(a0=1.0, q0=0.0, gamma=3.0, kappa0=0.04, kappa1=0.04, xi=0.7, Gamma=0.3375, zeta0=1.0 / 3.0, zeta1=0.005)
+    n, order, nsteps, eta = (32, 24, 1), 1, 12, 1.3333
+    orc = Oracle(n, nhalo=2)
+    p = orc.lc_param(grad_2d5=1, **lc)
+    pg = lb.LcParam.make(adv_order=order, **lc)
+    f, q, _ = state(orc, dict(lc, q0=0.19635), seed=5, axis=0)
+    z = lambda k: np.zeros((k, orc.nsites))
+    u, rho, force, qgrad, qdelsq = z(3), z(1), z(3), z(15), z(5)
+    cp = lb.CollideParam.make(lb.RELAX_M10, 1.0, eta)
+    with lb.Lb200(n, nhalo=2, have_q=True, math=math_mode) as sim:
+        sim.set_knob(lb.KNOB_QGRAD_2D5, 1)
+        sim.put(lb.F, f); sim.put(lb.Q, q)
+        (sim.step_lc if path == "step" else sim.step_lc_api)(cp, pg, nsteps)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("q", lb.Q), ("u", lb.U), ("force", lb.FORCE))}
+    orc.lc_step(orc.collide_param(0, 1.0, eta), p, order, nsteps, f, q, u, rho, force, qgrad, qdelsq)
+    want = dict(f=f, q=q, u=u, force=force)
+    assert np.abs(orc.interior(u)).max() > 1e-8
+    for k in want:
+        a, b = orc.interior(got[k]), orc.interior(want[k])
+        if math_mode == lb.MATH_STRICT:
+            assert np.array_equal(a, b), k
+        else:
+            assert close_fast(a, b), (k, np.abs(a - b).max())

@@ -161,11 +161,11 @@ def test_reference_unit_suites_pass_on_the_library(tmp_path):
 
 # ---- the reference's own regression inputs (tests/regression/d3q19-short/serial-*.inp, restated as key / value pairs in
 # tests/golden/regression_inputs_d3q19_short.json by tools/make_regression_inputs.py) -- a sample of the full sweep
-# (tools/regression_sweep.py, profiles/r02_regression_sweep.md: 26 logs equal, 75 explicit refusals, 0 different)
+# (tools/regression_sweep.py, profiles/r02_regression_sweep.md: 28 logs equal, 73 explicit refusals, 0 different)
 import json
 
 REGRESSION = json.load(open(os.path.join(ROOT, "tests", "golden", "regression_inputs_d3q19_short.json")))
-IN_SCOPE = ["serial-le3d-st1", "serial-le3d-st7", "serial-le2d-lb1", "serial-relx-bp1", "serial-chol-fld", "serial-symm-dr1",
+IN_SCOPE = ["serial-actv-s01", "serial-le3d-st1", "serial-le3d-st7", "serial-le2d-lb1", "serial-relx-bp1", "serial-chol-fld", "serial-symm-dr1",
             "serial-dist-3du", "serial-init-bp1", "serial-spin-lb1"]
 OUT_OF_SCOPE = {"serial-auto-c01": "colloids are outside this library", "serial-wall-st2": "walls are outside this library",
                 "serial-elec-gc1": "porous media are outside this library", "serial-pola-r01": "this free energy is outside this library"}

@@ -105,6 +105,33 @@ def test_lc_steps_vs_reference(n, lc, order):
         assert np.abs(orc.interior(u)).max() > 1e-8          # the stress drives a flow: the coupling is exercised
 
 
+def test_lc_active_2d_steps_vs_reference():
+    """an active nematic on a 2-d lattice with the 2d_5pt_fluid gradient (the configuration of
+    tests/regression/d3q19-short/serial-actv-s01.inp): whole time steps, every field bit for bit"""
+    lc = dict(a0=1.0, q0=0.0, gamma=3.0, kappa0=0.04, kappa1=0.04, xi=0.7, Gamma=0.3375, zeta0=1.0 / 3.0, zeta1=0.005, grad_2d5=1)
+    n, order = (32, 24, 1), 1
+    ref = R.RefSim(n, nhalo=2, adv_order=order, eta_shear=1.3333, lc=lc)
+    orc = Oracle(n, nhalo=2)
+    p = orc.lc_param(**lc)
+    with ref:
+        ref.init_rest(1.0)
+        ref.lc_twist_init(0, 1.0 / 3.0)
+        rng = np.random.default_rng(5)
+        q = ref.get(R.REF_Q)
+        orc.interior(q)[...] += 0.05 * (rng.random(orc.interior(q).shape) - 0.5)
+        ref.set(R.REF_Q, q)
+        f = ref.get(R.REF_F)
+        z = lambda k: np.zeros((k, orc.nsites))
+        u, rho, force, qgrad, qdelsq = z(3), z(1), z(3), z(15), z(5)
+        nsteps = 12
+        ref.step(nsteps)
+        orc.lc_step(orc.collide_param(0, 1.0, 1.3333), p, order, nsteps, f, q, u, rho, force, qgrad, qdelsq)
+        for name, a, what in (("f", f, R.REF_F), ("q", q, R.REF_Q), ("u", u, R.REF_U), ("force", force, R.REF_FORCE),
+                              ("qgrad", qgrad, R.REF_QGRAD), ("qdelsq", qdelsq, R.REF_QDELSQ)):
+            assert np.array_equal(orc.interior(a), orc.interior(ref.get(what))), name
+        assert np.abs(orc.interior(u)).max() > 1e-8
+
+
 # ---- printed statistics of the reference's own regression logs ---------------------------------------------------
 
 def approx(v, digits):
