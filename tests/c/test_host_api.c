@@ -573,7 +573,8 @@ static void test_liquid_crystal_step(int order, int nsteps, int strict) {
   orc_geom_t g = {{nlocal[X], nlocal[Y], nlocal[Z]}, 2, {1, 1, 1}, 0};
   orc_model_t model;
   orc_collide_param_t ocp = {ORC_RELAX_M10, 1.0, eta, eta, {0.0, 0.0, 0.0}};
-  orc_lc_param_t olc = {p.a0, p.q0, p.gamma, p.kappa0, p.kappa1, p.xi, bp.gamma, 0.0, {0.0, 0.0, 0.0}};
+  orc_lc_param_t olc = {.a0 = p.a0, .q0 = p.q0, .gamma = p.gamma, .kappa0 = p.kappa0, .kappa1 = p.kappa1, .xi = p.xi,
+			.Gamma = bp.gamma, .redshift = 1.0, .rredshift = 1.0};
   double * of = malloc(sizeof(double)*19*ns), * oq = malloc(sizeof(double)*NQAB*ns);
   double * ou = calloc(3*ns, sizeof(double)), * orho = calloc(ns, sizeof(double)), * oforce = calloc(3*ns, sizeof(double));
   double * ograd = calloc(15*ns, sizeof(double)), * odelsq = calloc(5*ns, sizeof(double));
