@@ -120,6 +120,9 @@ typedef struct lb200_symm_param_s {
                              * 0 = plain forward step; 1 = compensated (Kahan) sum per site, phi_ch_update_conserve,
                              * src/phi_cahn_hilliard.c:1059-1094, 1181-1215 -- the compensation field lives in the context
                              * like pch->csum; 2 = global subtraction after the forward step (lb200_phi_conserve_sum below) */
+  int force_method;         /* fe_force_method (src/phi_force.c:99-133): 0 = stress_divergence (default), 1 = phi_gradmu
+                             * (force = -phi grad mu - phi grad_mu_ext, src/phi_grad_mu.c).  With Lees-Edwards planes the
+                             * reference uses its flux method whatever this says, and so does the library */
 } lb200_symm_param_t;
 
 /* fe_lc_param_t + beris_edw_param_t as the liquid-crystal kernels see them (src/blue_phase.h:52-75,

@@ -421,10 +421,13 @@ int __wrap_phi_force_calculation(pe_t * pe, cs_t * cs, lees_edw_t * le, wall_t *
   if (s == NULL || s->ctx == NULL || b200_field_array(s, phi) != LB200_PHI) {
     return __real_phi_force_calculation(pe, cs, le, wall, pth, fe, map, phi, hydro);
   }
-  if (pth->method != FE_FORCE_METHOD_STRESS_DIVERGENCE) pe_fatal(pe, "libludwig_b200: fe_force_method stress_divergence only\n");
+  if (pth->method != FE_FORCE_METHOD_STRESS_DIVERGENCE && pth->method != FE_FORCE_METHOD_PHI_GRADMU) {
+    pe_fatal(pe, "libludwig_b200: fe_force_method stress_divergence / phi_gradmu only\n");
+  }
   if (wall_present(wall)) pe_fatal(pe, "libludwig_b200: walls are outside this library\n");
   if (fe == NULL || fe->id != FE_SYMMETRIC) pe_fatal(pe, "libludwig_b200: phi_force_calculation: free_energy symmetric / lc_blue_phase only\n");
   b200_symm_param(fe, NULL, &sp);
+  sp.force_method = (pth->method == FE_FORCE_METHOD_PHI_GRADMU);
   b200_time_sync(pe, s);
   b200_check(pe, lb200_phi_force_calculation(s->ctx, &sp), "phi_force_calculation");
   return 0;

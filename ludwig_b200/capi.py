@@ -42,12 +42,14 @@ class CollideParam(C.Structure):
 
 class SymmParam(C.Structure):
     _fields_ = [("a", C.c_double), ("b", C.c_double), ("kappa", C.c_double),
-                ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int), ("conserve", C.c_int)]
+                ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int), ("conserve", C.c_int),
+                ("force_method", C.c_int)]
 
     @classmethod
-    def make(cls, a, b, kappa, mobility, gradmu=(0.0, 0.0, 0.0), adv_order=1, conserve=0):
+    def make(cls, a, b, kappa, mobility, gradmu=(0.0, 0.0, 0.0), adv_order=1, conserve=0, force_method=0):
         sp = cls()
         sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order, sp.conserve = a, b, kappa, mobility, adv_order, conserve
+        sp.force_method = force_method
         sp.gradmu[:] = gradmu
         return sp
 

@@ -345,6 +345,7 @@ static void symm_dev(const lb200_t * c, const lb200_symm_param_t * sp, Lb200Symm
   d->wz = (c->g.nl[2] == 1) ? 0.0 : 1.0;
   d->rtau2 = 2.0/(1.0 + 2.0*sp->mobility);          // src/collision.c:1949-1950
   d->csum = (sp->conserve == 1) ? c->csum : nullptr;   // allocated by conserve_prepare
+  d->force_method = sp->force_method;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1329,6 +1330,7 @@ int lb200_phi_force_calculation(lb200_t * c, const lb200_symm_param_t * sp) {
   CTX_ENTER(c);
   if (c->phi == nullptr) return fail(LB200_ESTATE, "no phi in this context");
   if (sp == nullptr) return fail(LB200_EINVAL, "null parameters");
+  if (sp->force_method < 0 || sp->force_method > 1) return fail(LB200_EINVAL, "fe_force_method %d: 0 (stress_divergence) and 1 (phi_gradmu) are built", sp->force_method);
   Lb200SymmDev sd;
   symm_dev(c, sp, &sd);
   phi_force_async(c, sd);
@@ -2761,6 +2763,8 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
   if (cp == nullptr) return fail(LB200_EINVAL, "null collision parameters");
   const int binary = (sp != nullptr && c->phi != nullptr);
   if (binary && (sp->adv_order < 1 || sp->adv_order > 4)) return fail(LB200_EINVAL, "advection order %d", sp->adv_order);
+  if (binary && (sp->force_method < 0 || sp->force_method > 1)) return fail(LB200_EINVAL, "fe_force_method %d: 0 (stress_divergence) and 1 (phi_gradmu) are built", sp->force_method);
+  if (binary && sp->force_method == 1 && c->ndist != 1) return fail(LB200_EINVAL, "fe_force_method phi_gradmu: the finite-difference binary fluid (ndist = 1)");
   Lb200CollideDev cd;
   Lb200SymmDev sd;
   int rc = collide_dev(c, cp, &cd);
@@ -2799,7 +2803,8 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
     const Lb200Geom & g = c->g;
     bool ok = wrap_enabled && g.per[0] && g.per[1] && g.per[2] && c->ndist == 1;
     for (int a = 0; a < 3; a++) ok = ok && (g.nl[a] >= 2*g.nh);
-    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr && !c->knob_grad7 && !conserve2;   // the one-sweep phi sector: orders 1-3, plain update
+    if (binary) ok = ok && ps_on && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr && !c->knob_grad7 && !conserve2
+		  && sd.force_method == 0;   // the one-sweep phi sector: orders 1-3, plain update
     if (ok && binary && pipe_eligible(c, nsteps)) return step_pipe(c, cd, sd, nsteps);
     if (ok) return step_wrap(c, cd, binary ? &sd : nullptr, nsteps);
   }
@@ -2827,7 +2832,8 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	CUDA_TRY(cudaEventRecord(c->ev_phi, C));
       }
       // all-fluid lattices: gradient + force + Cahn-Hilliard in one sweep (LB200_PHI_SECTOR=0 disables)
-      const bool use_ps = c->knob_phi_sector && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr && !c->knob_grad7;
+      const bool use_ps = c->knob_phi_sector && c->map_all_fluid && sd.order <= 3 && sd.csum == nullptr && !c->knob_grad7
+	&& sd.force_method == 0;
       CUDA_TRY(cudaStreamWaitEvent(S, c->ev_phi, 0));
       if (!use_ps) {
 	ProfScope ps(c, LB200_K_GRAD);
@@ -2857,7 +2863,7 @@ int lb200_step(lb200_t * c, const lb200_collide_param_t * cp, const lb200_symm_p
 	// phi_force_calculation + phi_cahn_hilliard: one sweep, or two lighter ones (LB200_SPLIT_FCH=1)
 	static const int split = getenv("LB200_SPLIT_FCH") ? atoi(getenv("LB200_SPLIT_FCH")) : 0;
 	ProfScope ps(c, LB200_K_FORCE_CH);
-	if (split) {
+	if (split || sd.force_method != 0) {                             // (phi_gradmu: its own force kernel)
 	  c->launches += c->k->phi_force(S, c->g, sd, 0, c->phi, c->grad, c->delsq, c->force);
 	  c->launches += c->k->cahn_hilliard(S, c->g, sd, c->phi, c->delsq, c->u, status_ptr(c), c->phinew);
 	}

@@ -1614,8 +1614,42 @@ int launch_force_ch_t(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev &
   return 1;
 }
 
+// fe_force_method phi_gradmu (src/phi_force.c:110-121): force += -phi grad mu (phi_grad_mu_fluid_kernel, src/phi_grad_mu.c:272-340),
+// then force += -phi grad_mu_ext when that is not zero (phi_grad_mu_external_kernel, :352-384) -- two additions, as two kernels
+// adding to hydro->force make them.  mu of the neighbours from phi and delsq (fe_symm_mu, src/symmetric.c:307-319).
+__global__ void __launch_bounds__(TPB)
+phi_gradmu_kernel(const Lb200Geom g, const Lb200SymmDev sp, const int accumulate, const double * __restrict__ phi,
+		  const double * __restrict__ delsq, double * __restrict__ force) {
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ic = 1 + blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+  const int s = ((ic + g.nh - 1)*g.nall[1] + (jc + g.nh - 1))*g.nall[2] + (kc + g.nh - 1);
+  const size_t ns = (size_t) g.nsites;
+  const int off[3] = {g.xs, g.ys, 1};
+  const bool ext = (sp.gm[0] != 0.0 || sp.gm[1] != 0.0 || sp.gm[2] != 0.0);
+  const double phi0 = phi[s];
+#pragma unroll
+  for (int ia = 0; ia < 3; ia++) {
+    const double mum1 = symm_mu(sp, phi[s - off[ia]], delsq[s - off[ia]]);
+    const double mup1 = symm_mu(sp, phi[s + off[ia]], delsq[s + off[ia]]);
+    double f = 0.0;
+    f += -phi0*0.5*(mup1 - mum1);
+    double out = accumulate ? force[ia*ns + s] + f : 0.0 + f;
+    if (ext) out += -phi0*sp.gm[ia];
+    force[ia*ns + s] = out;
+  }
+}
+
 int launch_phi_force(cudaStream_t st, const Lb200Geom & g, const Lb200SymmDev & sp, int accumulate,
 		     const double * phi, const double * grad, const double * delsq, double * force) {
+  if (sp.force_method == 1) {
+    dim3 blk;
+    block_shape_n(g.nl[2], TPB, blk);
+    dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, g.nl[0]);
+    phi_gradmu_kernel<<<grd, blk, 0, st>>>(g, sp, accumulate, phi, delsq, force);
+    return 1;
+  }
   return launch_force_ch_t<true, false>(st, g, sp, accumulate, phi, grad, delsq, nullptr, nullptr,
 					force, nullptr);
 }

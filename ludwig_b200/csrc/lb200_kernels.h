@@ -86,6 +86,8 @@ struct Lb200SymmDev {
   double wz;            // 0 if nlocal[Z] == 1
   double rtau2;         // 2/(1 + 2 mobility): relaxation of the order-parameter flux (symmetric_lb)
   double * csum;        // cahn_hilliard_options_conserve 1: per-site Kahan compensation (pch->csum); nullptr: plain update
+  int force_method;     // fe_force_method: 0 = stress_divergence, 1 = phi_gradmu (phi_force only: the sweeps that fuse the force
+                        // with other operators are the stress-divergence form)
 };
 
 struct Lb200ModelDev {       // generic (non-unrolled) model tables

@@ -717,6 +717,40 @@ static double symm_mu(const orc_symm_param_t * sp, double phi, double delsq) {
   return sp->a*phi + sp->b*phi*phi*phi - sp->kappa*delsq;
 }
 
+/* ---- fe_force_method phi_gradmu: phi_grad_mu_fluid + phi_grad_mu_external, src/phi_grad_mu.c:52-82, 124-176, kernels :272-340,
+ * 352-384.  Each adds to hydro->force (hydro_f_local_add); the external part runs only when grad_mu != 0. ---- */
+
+void orc_phi_force_gradmu(const orc_geom_t * g, const orc_symm_param_t * sp, const double * phi, const double * delsq,
+			  double * force) {
+  const size_t ns = (size_t) orc_nsites(g);
+  const int ys = g->nlocal[Z] + 2*g->nhalo;
+  const int xs = ys*(g->nlocal[Y] + 2*g->nhalo);
+  const int is_grad_mu = (sp->gradmu[X] != 0.0 || sp->gradmu[Y] != 0.0 || sp->gradmu[Z] != 0.0);
+  for (int ic = 1; ic <= g->nlocal[X]; ic++)
+    for (int jc = 1; jc <= g->nlocal[Y]; jc++)
+      for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
+	const int index = orc_index(g, ic, jc, kc);
+	const int off[3] = {xs, ys, 1};
+	const double phi0 = phi[index];
+	for (int ia = 0; ia < 3; ia++) {
+	  const double mum1 = symm_mu(sp, phi[index - off[ia]], delsq[index - off[ia]]);
+	  const double mup1 = symm_mu(sp, phi[index + off[ia]], delsq[index + off[ia]]);
+	  double f = 0.0;
+	  f += -phi0*0.5*(mup1 - mum1);
+	  force[(size_t) ia*ns + index] += f;
+	}
+      }
+  if (is_grad_mu) {
+    for (int ic = 1; ic <= g->nlocal[X]; ic++)
+      for (int jc = 1; jc <= g->nlocal[Y]; jc++)
+	for (int kc = 1; kc <= g->nlocal[Z]; kc++) {
+	  const int index = orc_index(g, ic, jc, kc);
+	  const double phi0 = phi[index];
+	  for (int ia = 0; ia < 3; ia++) force[(size_t) ia*ns + index] += -phi0*sp->gradmu[ia];
+	}
+  }
+}
+
 void orc_flux_mu(const orc_geom_t * g, const orc_symm_param_t * sp, const double * phi,
 		 const double * delsq, double * flux) {
   int nall[3];
@@ -942,8 +976,11 @@ void orc_step(const orc_geom_t * g, const orc_model_t * m, const orc_collide_par
       orc_field_halo(g, 1, phi);
       if (sp->grad_7pt) orc_grad_7pt(g, 1, phi, grad, delsq);          /* grad_3d_7pt_fluid_d2 */
       else              orc_grad_27pt(g, phi, grad, delsq);
-      orc_stress_symm(g, sp, phi, grad, delsq, str);
-      orc_force_divergence(g, str, force);
+      if (sp->force_method == 1) orc_phi_force_gradmu(g, sp, phi, delsq, force);
+      else {
+	orc_stress_symm(g, sp, phi, grad, delsq, str);
+	orc_force_divergence(g, str, force);
+      }
       orc_field_halo(g, 3, u);
       orc_advection(g, sp->adv_order, u, phi, flux);
       orc_flux_mu(g, sp, phi, delsq, flux);

@@ -64,6 +64,7 @@ typedef struct orc_symm_param_s {
   int conserve;          /* cahn_hilliard_options_conserve: 0, 1 = compensated sum, 2 = global subtraction after the forward step */
   int grad_7pt;          /* fd_gradient_calculation: 0 = 3d_27pt_fluid, 1 = 3d_7pt_fluid (whole steps, orc_step) */
   double phi_init_sum;   /* conserve 2: phi->field_init_sum, the sum the global correction restores (orc_phi_sum_time0) */
+  int force_method;      /* fe_force_method: 0 = stress_divergence, 1 = phi_gradmu (src/phi_force.c:99-121) */
 } orc_symm_param_t;
 
 int orc_nsites(const orc_geom_t * g);          /* hydro, fields, gradients, fluxes: with the LE buffer planes */
@@ -102,6 +103,9 @@ void orc_flux_mu(const orc_geom_t * g, const orc_symm_param_t * sp, const double
 void orc_flux_mu_ext(const orc_geom_t * g, const orc_symm_param_t * sp, double * flux);
 void orc_no_flux(const orc_geom_t * g, const char * status, double * flux);
 void orc_phi_update(const orc_geom_t * g, const double * flux, double * phi);
+/* fe_force_method phi_gradmu: force += -phi grad mu (phi_grad_mu_fluid), then += -phi grad_mu_ext (phi_grad_mu_external) */
+void orc_phi_force_gradmu(const orc_geom_t * g, const orc_symm_param_t * sp, const double * phi, const double * delsq,
+			  double * force);
 void orc_phi_update_conserve(const orc_geom_t * g, const double * flux, double * csum, double * phi);
 
 void orc_field_set(const orc_geom_t * g, int nf, double * data, const double * values);

@@ -90,6 +90,7 @@ typedef struct ref_cfg_s {
   double lc_zeta0, lc_zeta1;   /* lc_active_zeta0, lc_active_zeta1 (zeta2 = 0) */
   double lc_redshift;  /* lc_init_redshift (0: 1.0); no dynamic update */
   int lc_grad_2d5;     /* fd_gradient_calculation 2d_5pt_fluid for the Q tensor */
+  int force_gradmu;    /* fe_force_method phi_gradmu (binary fluid, FD route) */
 } ref_cfg_t;
 
 typedef struct ref_sim_s {
@@ -202,7 +203,7 @@ ref_sim_t * ref_create(const ref_cfg_t * cfg) {
     else {
       ch.conserve = cfg->conserve;
       phi_ch_create(s->pe, s->cs, s->le, &ch, &s->pch);
-      pth_create(s->pe, s->cs, FE_FORCE_METHOD_STRESS_DIVERGENCE, &s->pth);
+      pth_create(s->pe, s->cs, cfg->force_gradmu ? FE_FORCE_METHOD_PHI_GRADMU : FE_FORCE_METHOD_STRESS_DIVERGENCE, &s->pth);
       advection_order_set(cfg->adv_order);
     }
   }

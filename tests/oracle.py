@@ -52,7 +52,7 @@ class CollideParam(C.Structure):
 class SymmParam(C.Structure):
     _fields_ = [("a", C.c_double), ("b", C.c_double), ("kappa", C.c_double),
                 ("mobility", C.c_double), ("gradmu", C.c_double * 3), ("adv_order", C.c_int), ("conserve", C.c_int),
-                ("grad_7pt", C.c_int), ("phi_init_sum", C.c_double)]
+                ("grad_7pt", C.c_int), ("phi_init_sum", C.c_double), ("force_method", C.c_int)]
 
 
 _lib = None
@@ -124,11 +124,13 @@ class Oracle:
         cp.force_global[:] = force
         return cp
 
-    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1, conserve=0, grad_7pt=0, phi_init_sum=0.0):
+    def symm_param(self, a, b, kappa, mobility, gradmu=(0, 0, 0), adv_order=1, conserve=0, grad_7pt=0, phi_init_sum=0.0,
+                   force_method=0):
         sp = SymmParam()
         sp.a, sp.b, sp.kappa, sp.mobility, sp.adv_order, sp.conserve = a, b, kappa, mobility, adv_order, conserve
         sp.grad_7pt = grad_7pt
         sp.phi_init_sum = phi_init_sum
+        sp.force_method = force_method
         sp.gradmu[:] = gradmu
         return sp
 

@@ -28,7 +28,7 @@ class RefCfg(C.Structure):
                 ("lc_kappa0", C.c_double), ("lc_kappa1", C.c_double), ("lc_xi", C.c_double), ("lc_Gamma", C.c_double),
                 ("lc_epsilon", C.c_double), ("lc_e0", C.c_double * 3), ("grad_7pt", C.c_int),
                 ("io_ascii", C.c_int), ("lc_active", C.c_int), ("lc_zeta0", C.c_double), ("lc_zeta1", C.c_double),
-                ("lc_redshift", C.c_double), ("lc_grad_2d5", C.c_int)]
+                ("lc_redshift", C.c_double), ("lc_grad_2d5", C.c_int), ("force_gradmu", C.c_int)]
 
 
 def _so(fast=False, nvel=19):
@@ -95,7 +95,7 @@ class RefSim:
     def __init__(self, ntotal, nhalo=1, periodic=(1, 1, 1), ndist=1, nrelax=0, ghost_off=0,
                  halo_reduced=0, have_phi=0, adv_order=1, conserve=0, rho0=1.0, eta_shear=1.0 / 6.0,
                  eta_bulk=None, fbody=(0, 0, 0), a=0.0, b=0.0, kappa=0.0, mobility=0.0,
-                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2, le_nplanes=0, le_uy=0.0, lc=None, grad_7pt=0, io_ascii=0):
+                 gradmu=(0, 0, 0), fast=False, nvel=19, grad_level=2, le_nplanes=0, le_uy=0.0, lc=None, grad_7pt=0, io_ascii=0, force_gradmu=0):
         self.lib = _lib(fast, nvel)
         cfg = RefCfg()
         cfg.ntotal[:] = ntotal
@@ -111,6 +111,7 @@ class RefSim:
         cfg.grad_level = grad_level
         cfg.grad_7pt = grad_7pt
         cfg.io_ascii = io_ascii
+        cfg.force_gradmu = force_gradmu
         cfg.le_nplanes, cfg.le_uy = le_nplanes, le_uy
         if lc is not None:
             # liquid crystal: dict(a0, q0, gamma, kappa0, kappa1, xi, Gamma[, epsilon, e0])

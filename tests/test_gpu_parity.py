@@ -333,6 +333,30 @@ def test_binary_steps_7pt_gradient(path, math, nvel, nlocal, order):
             assert close_fast(a, b), (k, rel_err(a, b))
 
 
+@pytest.mark.parametrize("path", ["api", "fused", "fused_halos_split"])
+@pytest.mark.parametrize("math", [lb.MATH_STRICT, lb.MATH_FAST], ids=["strict", "fast"])
+@pytest.mark.parametrize("gradmu", [(0.0, 0.0, 0.0), (1e-5, -2e-5, 3e-5)])
+def test_binary_steps_force_method_phi_gradmu(path, math, gradmu):
+    """fe_force_method phi_gradmu (force = -phi grad mu - phi grad_mu_ext; the configuration of the reference's
+    serial-muex-st1 input): the oracle is pinned to the compiled reference in tests/test_oracle_vs_reference.py"""
+    nlocal, order = (12, 10, 14), 3
+    orc = Oracle(nlocal, nhalo=2)
+    st = seeded_state(orc)
+    cpo = orc.collide_param(lb.RELAX_M10, 1.0, ETA)
+    spo = orc.symm_param(adv_order=order, gradmu=gradmu, force_method=1, **BINARY)
+    with make_sim(orc, st, math=math) as sim:
+        run_steps(sim, path, lb.CollideParam.make(lb.RELAX_M10, 1.0, ETA),
+                  lb.SymmParam.make(adv_order=order, gradmu=gradmu, force_method=1, **BINARY), 10)
+        got = {k: sim.get(a) for k, a in (("f", lb.F), ("phi", lb.PHI), ("u", lb.U), ("force", lb.FORCE))}
+    orc.step(cpo, spo, 1, 10, st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    for k in got:
+        a, b = orc.interior(got[k]), orc.interior(st[k])
+        if math == lb.MATH_STRICT:
+            assert np.array_equal(a, b), k
+        else:
+            assert close_fast(a, b), (k, rel_err(a, b))
+
+
 def test_conserve_global_subtract_is_rejected():
     orc = Oracle((8, 8, 8), nhalo=2)
     with make_sim(orc, seeded_state(orc)) as sim:

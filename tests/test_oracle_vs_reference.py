@@ -187,6 +187,28 @@ def test_binary_time_steps(order, nlocal):
         assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k
 
 
+@pytest.mark.parametrize("gradmu", [(0.0, 0.0, 0.0), (1e-5, -2e-5, 3e-5)])
+@pytest.mark.parametrize("order,nlocal", [(1, (12, 10, 8)), (3, (16, 16, 16))])
+def test_binary_time_steps_force_method_phi_gradmu(order, nlocal, gradmu):
+    """fe_force_method phi_gradmu (src/phi_force.c:110-121): force = -phi grad mu (phi_grad_mu_fluid) - phi grad_mu_ext
+    (phi_grad_mu_external), instead of the stress divergence -- the configuration of serial-muex-st1.inp"""
+    nsteps = 8
+    orc = Oracle(nlocal, nhalo=2)
+    with rh.RefSim(nlocal, nhalo=2, have_phi=1, adv_order=order, ghost_off=1, eta_shear=ETA, gradmu=gradmu, force_gradmu=1,
+                   **BINARY) as s:
+        s.init_rest(1.0)
+        s.init_spinodal(8361235, 0.0, 0.05)
+        f, phi = s.get(rh.REF_F), s.get(rh.REF_PHI)
+        s.step(nsteps)
+        ref = {k: s.get(w) for k, w in (("f", rh.REF_F), ("phi", rh.REF_PHI), ("u", rh.REF_U), ("force", rh.REF_FORCE))}
+    st = dict(f=f, phi=phi, u=np.zeros((3, orc.nsites)), rho=np.zeros((1, orc.nsites)),
+              force=np.zeros((3, orc.nsites)), grad=np.zeros((3, orc.nsites)), delsq=np.zeros((1, orc.nsites)))
+    orc.step(orc.collide_param(0, 1.0, ETA), orc.symm_param(adv_order=order, gradmu=gradmu, force_method=1, **BINARY), 1, nsteps,
+             st["f"], st["phi"], st["u"], st["rho"], st["force"], st["grad"], st["delsq"])
+    for k in ref:
+        assert np.array_equal(orc.interior(st[k]), orc.interior(ref[k])), k
+
+
 @pytest.mark.parametrize("order,nlocal", [(1, (12, 10, 8)), (3, (16, 16, 16)), (2, (6, 12, 10)), (4, (8, 8, 8))])
 def test_binary_time_steps_compensated_sum(order, nlocal):
     """cahn_hilliard_options_conserve 1 (PHI_CONSERVE_COMPENSATED_SUM): phi_ch_update_conserve / phi_ch_csum_kernel
