@@ -440,6 +440,7 @@ static int le_alloc(lb200_t * c) {
   int nprop = 0;
   for (int p = 1; p < c->nvel; p++) if (c->model_h.cv[p][0] == 1) nprop++;
   c->le.nprop = nprop;
+  c->le.nvel = c->nvel;
 
   // gradient patch: the real planes either side of each plane and the nextra = nhalo - 1 buffer planes beyond
   // (grad_3d_27pt_fluid_le, src/gradient_3d_27pt_fluid.c:421-425, 535-541)

@@ -40,6 +40,7 @@ struct Lb200LeDev {
   int nplane;           // planes in this slab (0: none)
   int xblock;           // nl[0]/nplane
   int nprop;            // populations with c_x = +1 (= those with c_x = -1)
+  int nvel;             // velocity set of the context (19: the plane kernels use the compile-time table)
   int loc[LB200_LE_MAXPLANES];   // plane p lies between local x = loc[p] and loc[p] + 1
   double uy;            // plane speed
 };

@@ -537,6 +537,70 @@ int launch_le_force_ch(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & 
 // shifted by whole sites, which the second kernel does by indexing).
 // ---------------------------------------------------------------------------------------------
 
+// D3Q19: the same statements with the velocity set as a compile-time table and every loop unrolled (the generic form below
+// reads cv from global memory inside data-dependent loops: 13 us for two planes of 256^2 sites; this one 2-3x less)
+__global__ void __launch_bounds__(TPB_MAX)
+le_lb_reproject19_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, const Lb200ModelDev * __restrict__ md,
+			 int ndist, const double * __restrict__ f, double * __restrict__ sbuf) {
+  const int kc = 1 + blockIdx.x*blockDim.x + threadIdx.x;
+  const int jc = 1 + blockIdx.y*blockDim.y + threadIdx.y;
+  const int ix = blockIdx.z;
+  if (kc > g.nl[2] || jc > g.nl[1]) return;
+  const int iplane = ix/2, iside = ix % 2;
+  const int cx = 1 - 2*iside;
+  const int ic = iside + le.loc[iplane];
+  const int index = le_index(g, ic, jc, kc);
+  const size_t ns = (size_t) g.nsites;
+  const size_t nyz = (size_t) g.nl[1]*g.nl[2];
+  const size_t q = (size_t) (jc - 1)*g.nl[2] + (kc - 1);
+  constexpr int nvel = 19;
+  const double cs2 = (1.0/3.0);
+  const double rcs2 = 1.0/cs2;
+  double du[3] = {0.0, 0.0, 0.0};
+  du[1] = le.uy;
+  du[1] = -1.0*cx*du[1];
+
+  for (int n = 0; n < ndist; n++) {
+    double fl[nvel];
+#pragma unroll
+    for (int p = 0; p < nvel; p++) fl[p] = f[(size_t) (n*nvel + p)*ns + index];
+    double rho = 0.0;
+    double gv[3] = {0.0, 0.0, 0.0};
+    double ds[3][3];
+#pragma unroll
+    for (int p = 0; p < nvel; p++) {
+      rho += fl[p];
+#pragma unroll
+      for (int ia = 0; ia < 3; ia++) gv[ia] += CV19[p][ia]*fl[p];
+    }
+#pragma unroll
+    for (int ia = 0; ia < 3; ia++)
+#pragma unroll
+      for (int ib = 0; ib < 3; ib++)
+	ds[ia][ib] = (gv[ia]*du[ib] + du[ia]*gv[ib] + rho*du[ia]*du[ib]);
+    int ip = 0;
+#pragma unroll
+    for (int p = 1; p < nvel; p++) {
+      if (CV19[p][0] != cx) continue;
+      const double udotc = du[1]*CV19[p][1];
+      double sdotq = 0.0;
+#pragma unroll
+      for (int ia = 0; ia < 3; ia++) {
+#pragma unroll
+	for (int ib = 0; ib < 3; ib++) {
+	  const double dab = cs2*(ia == ib);
+	  const double qab = (CV19[p][ia]*CV19[p][ib] - dab);
+	  sdotq += ds[ia][ib]*qab;
+	}
+      }
+      double fp = fl[p];
+      fp += md->wv[p]*(rho*udotc*rcs2 + 0.5*sdotq*rcs2*rcs2);
+      sbuf[((size_t) (ix*ndist + n)*le.nprop + ip)*nyz + q] = fp;
+      ip++;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TPB_MAX)
 le_lb_reproject_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, const Lb200ModelDev * __restrict__ md,
 		       int ndist, const double * __restrict__ f, double * __restrict__ sbuf) {
@@ -630,7 +694,8 @@ int launch_le_lb_bc(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le,
   dim3 blk;
   block_shape(g.nl[2], blk);
   dim3 grd((g.nl[2] + blk.x - 1)/blk.x, (g.nl[1] + blk.y - 1)/blk.y, 2*le.nplane);
-  le_lb_reproject_kernel<<<grd, blk, 0, st>>>(g, le, md, ndist, f, sbuf);
+  if (le.nvel == 19) le_lb_reproject19_kernel<<<grd, blk, 0, st>>>(g, le, md, ndist, f, sbuf);
+  else               le_lb_reproject_kernel<<<grd, blk, 0, st>>>(g, le, md, ndist, f, sbuf);
   le_lb_interp_kernel<<<grd, blk, 0, st>>>(g, le, fix, md, ndist, sbuf, f);
   return 2;
 }
