@@ -76,7 +76,7 @@ struct FuK {                                 // per-thread / per-CTA constants
 };
 
 // c_x + 1 (a = 0) or c_y + 1 (a = 1) of the 19 velocities, two bits each
-__host__ __device__ constexpr unsigned long long fu_cbits(int a) {
+__device__ constexpr unsigned long long fu_cbits(int a) {
   unsigned long long b = 0;
   for (int p = 0; p < 19; p++) b |= (unsigned long long) (CV19[p][a] + 1) << (2*p);
   return b;

@@ -31,8 +31,6 @@ __device__ __forceinline__ void fw_mbar_arrive(unsigned int bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar) : "memory");
 }
 template <int ID, int N> __device__ __forceinline__ void fw_bar_sync() { asm volatile("bar.sync %0, %1;\n" :: "n"(ID), "n"(N) : "memory"); }
-template <int N> __device__ __forceinline__ void fw_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"(N)); }
-template <int N> __device__ __forceinline__ void fw_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(N)); }
 
 #define FW_AD(member) (k.smb + (unsigned int) offsetof(FwShared, member))
 
@@ -185,6 +183,9 @@ step_fused_ws_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_cons
     const bool do_fx   = (n >= k.i0 - 1 && n <= k.i1);
     const bool do_full = (n >= k.i0 && n <= k.i1);
     const bool do_upd  = (n >= k.i0 + 1);
+#ifdef LB200_STRICT
+    (void) le_skip; (void) do_fx; (void) do_upd; (void) r18;   // (planes: the fast build only; the strict march updates plane n itself)
+#endif
     const int q1 = (q + 1 >= 6) ? q - 5 : q + 1;
     const int q2 = (q + 2 >= 6) ? q - 4 : q + 2;
     const int q4 = (q + 4 >= 6) ? q - 2 : q + 4;

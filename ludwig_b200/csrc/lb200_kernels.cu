@@ -1708,7 +1708,7 @@ __device__ __forceinline__ int ps_wrap(int j, int n, int w) {
   return w ? (j < 1 ? j + n : (j > n ? j - n : j)) : j;
 }
 
-__device__ __forceinline__ void ps_pcol(const Lb200SymmDev & sp, int B, double p0, double gx, double gy,
+[[maybe_unused]] __device__ __forceinline__ void ps_pcol(const Lb200SymmDev & sp, int B, double p0, double gx, double gy,
 					double gz, double p[3]) {
   const double gb = (B == 0) ? gx : (B == 1) ? gy : gz;
   const double d0 = (B == 0), d1 = (B == 1), d2 = (B == 2);
