@@ -55,14 +55,14 @@ def main():
         for name, pairs in cases.items():
             rc, out, err = run("Ludwig_soa.exe", pairs, {"OMP_NUM_THREADS": str(args.threads)}, args.timeout)
             ok = (rc == 0 and "Ludwig finished normally" in out)
-            with open(os.path.join(SWEEP, name + ".log"), "w") as fh:
+            with open(os.path.join(SWEEP, name.replace("/", "__") + ".log"), "w") as fh:
                 fh.write(out if ok else "REF-FAILED rc=%d\n%s\n%s" % (rc, out[-2000:], err[-2000:]))
             print(name, "ok" if ok else "REF-FAILED", flush=True)
         return
     from test_gpu_reference_callers import diff_logs
     results = {}
     for name, pairs in cases.items():
-        path = os.path.join(SWEEP, name + ".log")
+        path = os.path.join(SWEEP, name.replace("/", "__") + ".log")
         ref = open(path).read() if os.path.exists(path) else "REF-FAILED (no log)"
         if ref.startswith("REF-FAILED"):
             results[name] = {"outcome": "REF-FAILED", "detail": ref.splitlines()[-1][:200] if ref.splitlines() else ""}
