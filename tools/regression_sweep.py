@@ -23,7 +23,7 @@ BIN = os.path.join(ROOT, "integration", "_ref")
 SWEEP = os.path.join(BIN, "sweep")
 
 
-def run(exe, pairs, env, timeout):
+def run(exe, pairs, env, timeout, bindir=None):
     with tempfile.TemporaryDirectory() as d:
         with open(os.path.join(d, "input"), "w") as fh:
             for k, v in pairs:
@@ -31,7 +31,7 @@ def run(exe, pairs, env, timeout):
         e = dict(os.environ)
         e.update(env)
         try:
-            r = subprocess.run([os.path.join(BIN, exe)], cwd=d, capture_output=True, text=True, timeout=timeout, env=e)
+            r = subprocess.run([os.path.join(bindir or BIN, exe)], cwd=d, capture_output=True, text=True, timeout=timeout, env=e)
             return r.returncode, r.stdout, r.stderr
         except subprocess.TimeoutExpired:
             return -999, "", "timeout"
@@ -46,14 +46,16 @@ def main():
     ap.add_argument("--timeout", type=int, default=120)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "regression_sweep.json"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--model", default="", help="d3q15 / d3q27: the drivers of integration/_ref/<model>/ (make MODEL=... drivers)")
     args = ap.parse_args()
     cases = json.load(open(args.inputs))
     if args.only:
         cases = {k: v for k, v in cases.items() if args.only in k}
     os.makedirs(SWEEP, exist_ok=True)
+    bindir = os.path.join(BIN, args.model) if args.model else BIN
     if args.side == "reference":
         for name, pairs in cases.items():
-            rc, out, err = run("Ludwig_soa.exe", pairs, {"OMP_NUM_THREADS": str(args.threads)}, args.timeout)
+            rc, out, err = run("Ludwig_soa.exe", pairs, {"OMP_NUM_THREADS": str(args.threads)}, args.timeout, bindir)
             ok = (rc == 0 and "Ludwig finished normally" in out)
             with open(os.path.join(SWEEP, name.replace("/", "__") + ".log"), "w") as fh:
                 fh.write(out if ok else "REF-FAILED rc=%d\n%s\n%s" % (rc, out[-2000:], err[-2000:]))
@@ -68,7 +70,7 @@ def main():
             results[name] = {"outcome": "REF-FAILED", "detail": ref.splitlines()[-1][:200] if ref.splitlines() else ""}
             print(name, "REF-FAILED", flush=True)
             continue
-        rc, out, err = run("Ludwig_b200.exe", pairs, {"LB200_MATH": args.math}, args.timeout)
+        rc, out, err = run("Ludwig_b200.exe", pairs, {"LB200_MATH": args.math}, args.timeout, bindir)
         text = out + err
         if rc == 0 and "Ludwig finished normally" in out:
             bad = diff_logs(ref, out)
