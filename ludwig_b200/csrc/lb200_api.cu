@@ -1243,8 +1243,13 @@ static int le_force_ch_async(lb200_t * c, const Lb200SymmDev & sd, int nx, const
   const Lb200Geom & g = gw ? *gw : c->g;
   if (st == nullptr) st = c->stream;
   ProfScope ps(c, LB200_K_LE, st);
-  if (do_force) c->launches += c->k->le_force_prep(st, g, c->le, sd, c->phi, c->grad, c->delsq, c->le_term, c->le_fcor);
-  if (do_ch)    c->launches += c->k->le_ch_prep(st, g, c->le, sd, c->phi, c->delsq, c->u, status_ptr(c), c->le_chx);
+  if (do_force && do_ch) {
+    c->launches += c->k->le_prep_both(st, g, c->le, sd, c->phi, c->grad, c->delsq, c->u, status_ptr(c), c->le_term, c->le_fcor, c->le_chx);
+  }
+  else {
+    if (do_force) c->launches += c->k->le_force_prep(st, g, c->le, sd, c->phi, c->grad, c->delsq, c->le_term, c->le_fcor);
+    if (do_ch)    c->launches += c->k->le_ch_prep(st, g, c->le, sd, c->phi, c->delsq, c->u, status_ptr(c), c->le_chx);
+  }
   c->launches += c->k->le_force_ch(st, g, c->le, sd, fx, nx, xlist, do_force, do_ch, accumulate, c->phi, c->grad,
 				   c->delsq, c->u, status_ptr(c), c->le_fcor, c->le_chx, c->force, phinew);
   return 0;

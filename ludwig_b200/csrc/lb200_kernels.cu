@@ -2537,6 +2537,7 @@ const Lb200Kernels LB200_TABLE = {
   launch_le_grad_planes,
   launch_le_force_prep,
   launch_le_ch_prep,
+  launch_le_prep_both,
   launch_le_force_ch,
   launch_le_lb_bc,
   launch_grad7,

@@ -160,6 +160,10 @@ struct Lb200Kernels {
 		       const double * grad, const double * delsq, double * term, double * fcor);
   int (*le_ch_prep)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200SymmDev &, const double * phi,
 		    const double * delsq, const double * u, const char * status, double * chx);
+  // le_force_prep + le_ch_prep (fast build: one sweep over the planes + a fixed-order sum of block partials)
+  int (*le_prep_both)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200SymmDev &, const double * phi,
+		      const double * grad, const double * delsq, const double * u, const char * status, double * term,
+		      double * fcor, double * chx);
   int (*le_force_ch)(cudaStream_t, const Lb200Geom &, const Lb200LeDev &, const Lb200SymmDev &, const Lb200LeFix &,
 		     int nx, const int * xlist, int do_force, int do_ch, int accumulate, const double * phi,
 		     const double * grad, const double * delsq, const double * u, const char * status,

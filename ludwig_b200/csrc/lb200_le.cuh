@@ -346,6 +346,71 @@ le_ch_xflux_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, con
   chx[(size_t) (2*p + side)*nyz + q] = fx;
 }
 
+#ifndef LB200_STRICT
+// Fast build, force AND Cahn-Hilliard wanted: the summands of the force correction, their per-block sums and the raw x-face
+// fluxes either side of every plane in ONE launch, then one small launch that adds the block sums in a fixed order
+// (le_force_term_kernel + le_force_sum_kernel + le_ch_xflux_kernel: 22 us of three dependent launches -> 2 launches).
+constexpr int LE_PREP_NT = 128;
+template <int ORDER>
+__global__ void __launch_bounds__(LE_PREP_NT)
+le_prep_kernel(const Lb200Geom g, const __grid_constant__ Lb200LeDev le, const Lb200SymmDev sp,
+	       const double * __restrict__ phi, const double * __restrict__ grad, const double * __restrict__ delsq,
+	       const double * __restrict__ u, const char * __restrict__ status, double * __restrict__ partial,
+	       double * __restrict__ chx) {
+  __shared__ double sh[3][LE_PREP_NT];
+  const int nyz = g.nl[1]*g.nl[2];
+  const int q = blockIdx.x*LE_PREP_NT + threadIdx.x;
+  const int p = blockIdx.y;
+  double t[3] = {0.0, 0.0, 0.0};
+  if (q < nyz) {
+    const int jc = 1 + q/g.nl[2], kc = 1 + q % g.nl[2];
+    const size_t ns = (size_t) g.nsites;
+    const int ic = le.loc[p];
+    double p0[3], p1[3], fluxe[3], fluxw[3];
+    le_pcol_x(sp, phi, grad, delsq, ns, le_index(g, ic, jc, kc), p0);
+    le_pcol_x(sp, phi, grad, delsq, ns, le_index(g, le_x(le, g, ic, +1), jc, kc), p1);
+    for (int a = 0; a < 3; a++) fluxe[a] = 0.5*(p1[a] + p0[a]);
+    le_pcol_x(sp, phi, grad, delsq, ns, le_index(g, ic + 1, jc, kc), p0);
+    le_pcol_x(sp, phi, grad, delsq, ns, le_index(g, le_x(le, g, ic + 1, -1), jc, kc), p1);
+    for (int a = 0; a < 3; a++) fluxw[a] = 0.5*(p1[a] + p0[a]);
+    for (int a = 0; a < 3; a++) t[a] = - fluxe[a] + fluxw[a];
+    chx[(size_t) (2*p + 0)*nyz + q] = le_ch_xflux<ORDER, false>(g, le, sp, phi, delsq, u, status, ic, jc, kc);
+    chx[(size_t) (2*p + 1)*nyz + q] = le_ch_xflux<ORDER, true>(g, le, sp, phi, delsq, u, status, ic + 1, jc, kc);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) sh[a][threadIdx.x] = t[a];
+  __syncthreads();
+  for (int w = LE_PREP_NT/2; w > 0; w >>= 1) {
+    if ((int) threadIdx.x < w) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) sh[a][threadIdx.x] += sh[a][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) partial[(size_t) (p*3 + threadIdx.x)*gridDim.x + blockIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void __launch_bounds__(LE_RED_NT)
+le_prep_sum_kernel(int nblk, const double * __restrict__ partial, double * __restrict__ fcor) {
+  __shared__ double sh[LE_RED_NT];
+  const double * t = partial + (size_t) blockIdx.x*nblk;       // blockIdx.x = p*3 + a
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += LE_RED_NT) s += t[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = LE_RED_NT/2; w > 0; w >>= 1) {
+    if ((int) threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) fcor[blockIdx.x] = sh[0];
+}
+#endif
+
+// both preparations; term: at least 3*nplane*ceil(Ny*Nz/128) doubles (the 3*nplane*Ny*Nz summand array of the separate form is)
+int launch_le_prep_both(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le, const Lb200SymmDev & sp,
+			const double * phi, const double * grad, const double * delsq, const double * u, const char * status,
+			double * term, double * fcor, double * chx);
+
 // One thread per interior site of the x-planes in xlist (nullptr: every plane).  Force: flux form with the
 // plane correction.  Cahn-Hilliard: as force_ch_kernel with the x-neighbours through the buffer planes and,
 // next to a plane, the x-face flux averaged with the interpolated flux of the other side
@@ -509,6 +574,25 @@ int launch_le_ch_prep(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & l
   else if (sp.order == 4) le_ch_xflux_kernel<4><<<grd, blk, 0, st>>>(g, le, sp, phi, delsq, u, status, chx);
   else                    le_ch_xflux_kernel<3><<<grd, blk, 0, st>>>(g, le, sp, phi, delsq, u, status, chx);
   return 1;
+}
+
+int launch_le_prep_both(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le, const Lb200SymmDev & sp,
+			const double * phi, const double * grad, const double * delsq, const double * u, const char * status,
+			double * term, double * fcor, double * chx) {
+#ifdef LB200_STRICT
+  // the reference's sequential sum over (j, k): the separate kernels
+  return launch_le_force_prep(st, g, le, sp, phi, grad, delsq, term, fcor) + launch_le_ch_prep(st, g, le, sp, phi, delsq, u, status, chx);
+#else
+  const int nyz = g.nl[1]*g.nl[2];
+  const int nblk = (nyz + LE_PREP_NT - 1)/LE_PREP_NT;
+  dim3 grd(nblk, le.nplane, 1);
+  if (sp.order == 1)      le_prep_kernel<1><<<grd, LE_PREP_NT, 0, st>>>(g, le, sp, phi, grad, delsq, u, status, term, chx);
+  else if (sp.order == 2) le_prep_kernel<2><<<grd, LE_PREP_NT, 0, st>>>(g, le, sp, phi, grad, delsq, u, status, term, chx);
+  else if (sp.order == 4) le_prep_kernel<4><<<grd, LE_PREP_NT, 0, st>>>(g, le, sp, phi, grad, delsq, u, status, term, chx);
+  else                    le_prep_kernel<3><<<grd, LE_PREP_NT, 0, st>>>(g, le, sp, phi, grad, delsq, u, status, term, chx);
+  le_prep_sum_kernel<<<3*le.nplane, LE_RED_NT, 0, st>>>(nblk, term, fcor);
+  return 2;
+#endif
 }
 
 int launch_le_force_ch(cudaStream_t st, const Lb200Geom & g, const Lb200LeDev & le, const Lb200SymmDev & sp,
